@@ -1,0 +1,5 @@
+"""newton_b200 - B200-native batched rigid-body stepper behind Newton's solver API."""
+from .sim import (  # noqa: F401
+    MAXVAL, BodyFlags, Contacts, Control, GeoType, JointDofConfig, JointType, Model, ModelBuilder,
+    ModelFlags, ShapeConfig, ShapeFlags, State, StateFlags, eval_fk,
+)

@@ -1,0 +1,117 @@
+"""Mass / centre of mass / inertia of primitive shapes (host side, runs once at build time).
+
+Same closed forms as the reference (``newton/_src/geometry/inertia.py:78-300`` primitives,
+``:570-605`` ``transform_inertia``, ``:608-766`` ``compute_inertia_shape``) so that models built
+here carry the same body constants as models built by the reference builder.
+"""
+
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from ..sim.enums import GeoType
+from ..utils.xform import quat_to_matrix
+
+
+def compute_inertia_sphere(density, r):
+    m = density * 4.0 / 3.0 * math.pi * r * r * r
+    Ia = 2.0 / 5.0 * m * r * r
+    return m, np.zeros(3), np.diag([Ia, Ia, Ia])
+
+
+def compute_inertia_capsule(density, r, hh):
+    h = 2.0 * hh
+    ms = density * (4.0 / 3.0) * math.pi * r * r * r
+    mc = density * math.pi * r * r * h
+    m = ms + mc
+    Ia = mc * (0.25 * r * r + (1.0 / 12.0) * h * h) + ms * (0.4 * r * r + 0.375 * r * h + 0.25 * h * h)
+    Ib = (mc * 0.5 + ms * 0.4) * r * r
+    return m, np.zeros(3), np.diag([Ia, Ia, Ib])
+
+
+def compute_inertia_cylinder(density, r, hh, barrel_radius=0.0):
+    if barrel_radius != 0.0:
+        raise NotImplementedError("barrel cylinders are outside the hot-path scope (SURVEY.md §8)")
+    h = 2.0 * hh
+    m = density * math.pi * r * r * h
+    Ia = 1.0 / 12.0 * m * (3.0 * r * r + h * h)
+    Ib = 0.5 * m * r * r
+    return m, np.zeros(3), np.diag([Ia, Ia, Ib])
+
+
+def compute_inertia_ellipsoid(density, rx, ry, rz):
+    m = density * (4.0 / 3.0) * math.pi * rx * ry * rz
+    return (
+        m,
+        np.zeros(3),
+        np.diag([0.2 * m * (ry * ry + rz * rz), 0.2 * m * (rx * rx + rz * rz), 0.2 * m * (rx * rx + ry * ry)]),
+    )
+
+
+def compute_inertia_box(density, hx, hy, hz):
+    m = density * 8.0 * hx * hy * hz
+    return (
+        m,
+        np.zeros(3),
+        np.diag(
+            [
+                1.0 / 3.0 * m * (hy * hy + hz * hz),
+                1.0 / 3.0 * m * (hx * hx + hz * hz),
+                1.0 / 3.0 * m * (hx * hx + hy * hy),
+            ]
+        ),
+    )
+
+
+def compute_inertia_shape(geo_type, scale, density, is_solid=True, thickness=0.001):
+    """(mass, com, inertia-about-com) of a primitive (reference ``inertia.py:608-766``)."""
+    if density == 0.0 or geo_type == GeoType.PLANE:
+        return 0.0, np.zeros(3), np.zeros((3, 3))
+    fns = {
+        GeoType.SPHERE: lambda s: compute_inertia_sphere(density, s[0]),
+        GeoType.BOX: lambda s: compute_inertia_box(density, s[0], s[1], s[2]),
+        GeoType.CAPSULE: lambda s: compute_inertia_capsule(density, s[0], s[1]),
+        GeoType.CYLINDER: lambda s: compute_inertia_cylinder(density, s[0], s[1], s[2] if len(s) > 2 else 0.0),
+        GeoType.ELLIPSOID: lambda s: compute_inertia_ellipsoid(density, s[0], s[1], s[2]),
+    }
+    if geo_type not in fns:
+        raise NotImplementedError(f"inertia of shape type {geo_type} is outside the hot-path scope")
+    solid = fns[geo_type](scale)
+    if is_solid:
+        return solid
+    if thickness == 0.0:
+        return 0.0, solid[1], np.zeros((3, 3))
+    inner = [max(x - thickness, 0.0) for x in scale]
+    if geo_type == GeoType.CYLINDER:
+        inner[2] = scale[2] - thickness if scale[2] > 0.0 else 0.0
+    hollow = fns[geo_type](inner)
+    return solid[0] - hollow[0], solid[1], solid[2] - hollow[2]
+
+
+def transform_inertia(mass, inertia, offset, quat):
+    """Rotate by ``quat`` then parallel-axis shift by ``offset`` (reference ``inertia.py:570-605``)."""
+    R = quat_to_matrix(quat)
+    offset = np.asarray(offset, dtype=np.float64)
+    return R @ np.asarray(inertia, dtype=np.float64) @ R.T + mass * (
+        np.dot(offset, offset) * np.eye(3) - np.outer(offset, offset)
+    )
+
+
+def compute_shape_radius(geo_type, scale):
+    """Bounding-sphere radius (reference ``geometry/utils.py:73-127``)."""
+    s = np.abs(np.asarray(scale, dtype=np.float64))
+    if geo_type == GeoType.SPHERE:
+        return float(s[0])
+    if geo_type == GeoType.BOX:
+        return float(np.linalg.norm(s))
+    if geo_type in (GeoType.CAPSULE, GeoType.CYLINDER, GeoType.CONE):
+        return float(s[0] + s[1])
+    if geo_type == GeoType.ELLIPSOID:
+        return float(max(s))
+    if geo_type == GeoType.PLANE:
+        if s[0] > 0.0 and s[1] > 0.0:
+            return float(np.linalg.norm(s)) * 0.5
+        return 1.0e6
+    return 10.0

@@ -1,0 +1,174 @@
+"""Synthetic scenes for the BASELINE.json configs.
+
+Each function returns a finalized :class:`newton_b200.Model` built exactly as the corresponding
+reference example/test builds its scene, so the oracle and the CUDA path see identical inputs:
+
+* config 1 ``pendulum_model``   - ``newton/examples/basic/example_basic_pendulum.py:32-70``
+* config 2 ``box_stack_model``  - ``newton/tests/test_solver_xpbd.py:1798-1804`` (5 unit cubes on a plane)
+* config 3/4/5 ``quadruped_model`` - ``newton/examples/basic/example_basic_urdf.py:39-87``
+  (13-link quadruped, Anymal-class topology: 13 bodies / 13 joints / 18 dofs / 19 coords)
+
+The quadruped URDF text is generated here from the link/joint table (numbers from SURVEY.md
+Appendix B.8) instead of vendoring the reference asset.
+"""
+
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from .sim.articulation import eval_fk
+from .sim.builder import ModelBuilder
+from .utils import xform as X
+
+_HALF_PI = "1.57079632679"
+
+
+def quadruped_urdf() -> str:
+    """URDF text of the 13-link quadruped (base + 4 x {HAA, THIGH, SHANK}), cylinders only."""
+
+    def link(name, length, radius, rpy="0 0 0", xyz="0 0 0"):
+        return (
+            f'<link name="{name}"><collision><origin rpy="{rpy}" xyz="{xyz}"/>'
+            f'<geometry><cylinder length="{length}" radius="{radius}"/></geometry></collision></link>'
+        )
+
+    def joint(name, parent, child, xyz, rpy="0 0 0", dynamics=False):
+        dyn = '<dynamics damping="0.0" friction="0.0"/>' if dynamics else ""
+        return (
+            f'<joint name="{name}" type="revolute"><parent link="{parent}"/><child link="{child}"/>'
+            f'<axis xyz="1 0 0"/><limit effort="80.0" velocity="20."/><origin rpy="{rpy}" xyz="{xyz}"/>{dyn}</joint>'
+        )
+
+    parts = ['<?xml version="1.0"?><robot name="quadruped">', link("base", 0.75, 0.1, rpy=f"0 {_HALF_PI} 0")]
+    legs = [
+        ("LF", "0.2999 0.104 0.0", "0 0 0", "0 0.05 0", f"0 0 {_HALF_PI}"),
+        ("RF", "0.2999 -0.104 0.0", "0 0 0", "0 -0.05 0", f"0 0 -{_HALF_PI}"),
+        ("LH", "-0.2999 0.104 0.0", "0 0 3.1415", "0 -0.05 0", f"0 0 {_HALF_PI}"),
+        ("RH", "-0.2999 -0.104 0.0", "0 0 3.1415", "0 0.05 0", f"0 0 -{_HALF_PI}"),
+    ]
+    for p, haa_xyz, haa_rpy, hfe_xyz, hfe_rpy in legs:
+        parts.append(joint(f"{p}_HAA", "base", f"{p}_HAA", haa_xyz, haa_rpy))
+        parts.append(link(f"{p}_HAA", 0.05, 0.04, rpy=f"{_HALF_PI} 0 0"))
+        parts.append(joint(f"{p}_HFE", f"{p}_HAA", f"{p}_THIGH", hfe_xyz, hfe_rpy, dynamics=True))
+        parts.append(link(f"{p}_THIGH", 0.25, 0.02, xyz="0 0 -0.125"))
+        parts.append(joint(f"{p}_KFE", f"{p}_THIGH", f"{p}_SHANK", "0 0.0 -0.25", dynamics=True))
+        parts.append(link(f"{p}_SHANK", 0.25, 0.02, xyz="0 0 -0.125"))
+    parts.append("</robot>")
+    return "".join(parts)
+
+
+def quadruped_builder() -> ModelBuilder:
+    """One quadruped, configured as ``example_basic_urdf.py:39-74``."""
+    q = ModelBuilder()
+    q.default_joint_cfg.armature = 0.01
+    q.default_joint_cfg.target_ke = 2000.0
+    q.default_joint_cfg.target_kd = 1.0
+    q.default_shape_cfg.mu = 1.0
+    q.add_urdf(
+        quadruped_urdf(),
+        xform=X.transform((0.0, 0.0, 0.7)),
+        floating=True,
+        enable_self_collisions=False,
+        ignore_inertial_definitions=True,
+    )
+    for b in range(q.body_count):  # extra inertia for stability (example_basic_urdf.py:64-70)
+        q.body_inertia[b] = q.body_inertia[b] + np.eye(3) * 0.01
+        q.body_inv_inertia[b] = np.linalg.inv(q.body_inertia[b])
+    q.joint_q[-12:] = [0.2, 0.4, -0.6, -0.2, -0.4, 0.6, -0.2, 0.4, -0.6, 0.2, -0.4, 0.6]
+    q.joint_target_q[-12:] = q.joint_q[-12:]
+    return q
+
+
+def _finish(scene: ModelBuilder, device, run_fk=True):
+    model = scene.finalize(device="cpu")
+    if run_fk and model.joint_count:
+        eval_fk(model, model.joint_q, model.joint_qd, model)
+    return model.to(device) if str(device) != "cpu" else model
+
+
+def quadruped_model(world_count: int, device="cpu", seed: int | None = 1, noise: float = 0.02):
+    """Config 3: ``world_count`` quadrupeds + one global ground plane.
+
+    Per-env perturbation: ``joint_q[7:] += N(0, noise)`` with ``default_rng(seed)``,
+    targets follow; ``seed=None`` keeps every env identical to the stock example.
+    """
+    quad = quadruped_builder()
+    scene = ModelBuilder()
+    scene.replicate(quad, world_count)
+    scene.add_ground_plane(cfg=quad.default_shape_cfg)
+    if seed is not None and noise > 0.0:
+        rng = np.random.default_rng(seed)
+        per = quad.joint_coord_count
+        jq = np.asarray(scene.joint_q, dtype=np.float64).reshape(world_count, per)
+        jq[:, 7:] += rng.normal(0.0, noise, size=(world_count, per - 7))
+        scene.joint_q = jq.reshape(-1).tolist()
+        scene.joint_target_q = list(scene.joint_q)
+    return _finish(scene, device)
+
+
+def box_stack_model(world_count: int, device="cpu", seed: int | None = 0, n_boxes: int = 5):
+    """Config 2: ``world_count`` stacks of ``n_boxes`` unit cubes on a shared ground plane.
+
+    Cubes have half-extent 0.5 with centres at z = 0.5 + i (``tests/test_solver_xpbd.py:1798-1804``);
+    each stack is yawed by ``U(-0.05, 0.05)`` rad drawn from ``default_rng(seed)``.
+    """
+    rng = np.random.default_rng(seed) if seed is not None else None
+    scene = ModelBuilder()
+    for _ in range(world_count):
+        yaw = float(rng.uniform(-0.05, 0.05)) if rng is not None else 0.0
+        rot = X.quat_from_axis_angle((0.0, 0.0, 1.0), yaw)
+        scene.begin_world()
+        for i in range(n_boxes):
+            b = scene.add_body(xform=X.transform((0.0, 0.0, 0.5 + i), rot))
+            scene.add_shape_box(b, hx=0.5, hy=0.5, hz=0.5)
+        scene.end_world()
+    scene.add_ground_plane()
+    return _finish(scene, device)
+
+
+def pendulum_model(device="cpu"):
+    """Config 1: double pendulum of ``example_basic_pendulum.py:32-70`` (2 box links, 2 revolute joints)."""
+    b = ModelBuilder()
+    hx, hy, hz = 1.0, 0.1, 0.1
+    link_0 = b.add_link()
+    b.add_shape_box(link_0, hx=hx, hy=hy, hz=hz)
+    link_1 = b.add_link()
+    b.add_shape_box(link_1, hx=hx, hy=hy, hz=hz)
+    rot = X.quat_from_axis_angle((0.0, 0.0, 1.0), -math.pi * 0.5)
+    j0 = b.add_joint_revolute(
+        parent=-1, child=link_0, axis=(0.0, 1.0, 0.0),
+        parent_xform=X.transform((0.0, 0.0, 5.0), rot), child_xform=X.transform((-hx, 0.0, 0.0)),
+    )
+    j1 = b.add_joint_revolute(
+        parent=link_0, child=link_1, axis=(0.0, 1.0, 0.0),
+        parent_xform=X.transform((hx, 0.0, 0.0)), child_xform=X.transform((-hx, 0.0, 0.0)),
+    )
+    b.add_articulation([j0, j1], label="pendulum")
+    b.add_ground_plane()
+    return _finish(b, device)
+
+
+def shapes_on_plane_model(world_count: int = 1, device="cpu", seed: int | None = 3):
+    """Mixed primitives dropped on a plane (in the spirit of ``example_basic_shapes.py``): a sphere,
+    a capsule, a cylinder and a box per world - exercises every analytic plane collider."""
+    rng = np.random.default_rng(seed) if seed is not None else None
+    scene = ModelBuilder()
+    for _ in range(world_count):
+        scene.begin_world()
+        jitter = (lambda: rng.uniform(-0.02, 0.02, size=3)) if rng is not None else (lambda: np.zeros(3))
+        b = scene.add_body(xform=X.transform(np.array([0.0, -2.0, 0.6]) + jitter()))
+        scene.add_shape_sphere(b, radius=0.5)
+        b = scene.add_body(xform=X.transform(np.array([0.0, 0.0, 0.45]) + jitter(),
+                                             X.quat_from_axis_angle((0.0, 1.0, 0.0), 1.2)))
+        scene.add_shape_capsule(b, radius=0.3, half_height=0.7)
+        b = scene.add_body(xform=X.transform(np.array([0.0, 2.0, 0.65]) + jitter()))
+        scene.add_shape_cylinder(b, radius=0.4, half_height=0.6)
+        b = scene.add_body(xform=X.transform(np.array([0.0, 4.0, 0.3]) + jitter(),
+                                             X.quat_from_axis_angle((1.0, 0.0, 0.0), 0.3)))
+        scene.add_shape_box(b, hx=0.5, hy=0.35, hz=0.25)
+        scene.end_world()
+    scene.add_ground_plane()
+    return _finish(scene, device)

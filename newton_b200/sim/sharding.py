@@ -1,0 +1,113 @@
+"""World-range sharding of a Model across ranks.
+
+Worlds are independent (reference ``geometry/broad_phase_common.py:263-268`` rejects cross-world
+pairs; ``sim/builder.py:12921-13021`` emits contact pairs per world) and every entity array is
+stored world-contiguous (``*_world_start``: reference ``sim/model.py:1081,1180,883``), so rank ``r``
+of ``G`` owns worlds ``[r*W/G, (r+1)*W/G)`` as pure slices plus an index rebase.  World ``-1``
+shapes (e.g. the ground plane) are static and replicated on every rank.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .model import _BODY_FIELDS, _COORD_FIELDS, _DOF_FIELDS, _JOINT_FIELDS, _SHAPE_FIELDS, Model
+
+
+def world_range(world_count: int, rank: int, world_size: int) -> tuple[int, int]:
+    if world_count % world_size != 0:
+        raise ValueError(f"world_count={world_count} is not divisible by world_size={world_size}")
+    per = world_count // world_size
+    return rank * per, (rank + 1) * per
+
+
+def shard_model(model: Model, rank: int, world_size: int) -> Model:
+    w0, w1 = world_range(model.world_count, rank, world_size)
+    bws = model.numpy("body_world_start")
+    jws = model.numpy("joint_world_start")
+    sws = model.numpy("shape_world_start")
+    aws = model.numpy("articulation_world_start")
+    dws = model.numpy("joint_dof_world_start")
+    cws = model.numpy("joint_coord_world_start")
+    if bws[0] != 0 or bws[-1] != bws[-2] or jws[0] != 0 or jws[-1] != jws[-2]:
+        raise NotImplementedError("sharding requires that only shapes live in the global world (-1)")
+    if sws[0] != 0:
+        raise NotImplementedError("sharding requires global shapes to be stored at the tail")
+    b0, b1 = int(bws[w0]), int(bws[w1])
+    j0, j1 = int(jws[w0]), int(jws[w1])
+    s0, s1 = int(sws[w0]), int(sws[w1])
+    a0, a1 = int(aws[w0]), int(aws[w1])
+    d0, d1 = int(dws[w0]), int(dws[w1])
+    c0, c1 = int(cws[w0]), int(cws[w1])
+    g0, g1 = int(sws[-2]), int(sws[-1])  # global tail shapes
+    n_local_shapes = s1 - s0
+    out = Model(model.device)
+    out.world_count = w1 - w0
+    out.up_axis = model.up_axis
+    out.use_coord_layout_targets = model.use_coord_layout_targets
+    out.body_count, out.joint_count = b1 - b0, j1 - j0
+    out.shape_count = n_local_shapes + (g1 - g0)
+    out.joint_dof_count, out.joint_coord_count = d1 - d0, c1 - c0
+    out.articulation_count = a1 - a0
+    out.max_joints_per_articulation = model.max_joints_per_articulation
+    out.max_dofs_per_articulation = model.max_dofs_per_articulation
+    out.body_label = model.body_label[b0:b1]
+    out.joint_label = model.joint_label[j0:j1]
+
+    def cut(name, lo, hi):
+        return getattr(model, name)[lo:hi].clone()
+
+    for n in _BODY_FIELDS:
+        setattr(out, n, cut(n, b0, b1))
+    for n in _JOINT_FIELDS:
+        setattr(out, n, cut(n, j0, j1))
+    for n in _DOF_FIELDS:
+        setattr(out, n, cut(n, d0, d1))
+    for n in _COORD_FIELDS:
+        setattr(out, n, cut(n, c0, c1))
+    out.joint_target_q = cut("joint_target_q", c0, c1)
+    for n in _SHAPE_FIELDS:
+        setattr(out, n, torch.cat([cut(n, s0, s1), cut(n, g0, g1)]))
+
+    def rebase(t, off):
+        return torch.where(t >= 0, t - off, t)
+
+    out.body_world = rebase(out.body_world, w0)
+    out.joint_world = rebase(out.joint_world, w0)
+    out.shape_world = rebase(out.shape_world, w0)
+    out.joint_parent = rebase(out.joint_parent, b0)
+    out.joint_child = rebase(out.joint_child, b0)
+    out.joint_ancestor = rebase(out.joint_ancestor, j0)
+    out.joint_articulation = rebase(out.joint_articulation, a0)
+    out.shape_body = rebase(out.shape_body, b0)
+    out.joint_q_start = model.joint_q_start[j0 : j1 + 1].clone() - c0
+    out.joint_qd_start = model.joint_qd_start[j0 : j1 + 1].clone() - d0
+    out.joint_target_q_start = out.joint_q_start
+    out.articulation_start = model.articulation_start[a0 : a1 + 1].clone() - j0
+    out.articulation_start[-1] = j1 - j0
+    out.articulation_end = model.articulation_end[a0:a1].clone() - j0
+    out.articulation_world = rebase(model.articulation_world[a0:a1].clone(), w0)
+
+    def starts(ws, lo, tail):
+        v = ws[w0 : w1 + 1].astype(np.int64) - lo
+        return torch.tensor([*v.tolist(), int(v[-1]) + tail], dtype=torch.int32, device=model.device)
+
+    out.body_world_start = starts(bws, b0, 0)
+    out.joint_world_start = starts(jws, j0, 0)
+    out.shape_world_start = starts(sws, s0, g1 - g0)
+    out.articulation_world_start = starts(aws, a0, 0)
+    out.joint_dof_world_start = starts(dws, d0, 0)
+    out.joint_coord_world_start = starts(cws, c0, 0)
+
+    pairs = model.numpy("shape_contact_pairs").astype(np.int64)
+    sw = model.numpy("shape_world")
+    wa, wb = sw[pairs[:, 0]], sw[pairs[:, 1]]
+    pw = np.where(wa >= 0, wa, wb)
+    keep = ((pw >= w0) & (pw < w1)) | ((wa == -1) & (wb == -1))
+    p = pairs[keep]
+    remap = np.where(p >= g0, p - g0 + n_local_shapes, p - s0)
+    out.shape_contact_pairs = torch.from_numpy(remap.astype(np.int32)).to(model.device)
+    out.shape_contact_pair_count = int(remap.shape[0])
+    out.gravity = torch.cat([model.gravity[w0:w1], model.gravity[-1:]]).clone()
+    return out
