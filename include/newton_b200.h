@@ -1,0 +1,224 @@
+/*
+ * newton_b200.h - C-ABI of the B200-native batched rigid-body stepper.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / warp
+ * types.  Every array uses the reference's element layout so the pointers of a reference
+ * `newton.Model` / `State` / `Control` / `Contacts` (wp.array.ptr) can be passed unchanged:
+ *
+ *   transform       7 x f32  [px,py,pz, qx,qy,qz,qw]          (reference core/types.py:57-64)
+ *   spatial_vector  6 x f32  [linear(3), angular(3)]          (reference sim/state.py:131-135)
+ *   mat33           9 x f32  row-major
+ *   vec3            3 x f32
+ *   indices         int32;   joint_enabled is 1 byte per joint (wp.bool)
+ *
+ * Each entry point cites the reference interface it replaces.  All device work is enqueued on the
+ * caller's stream; no entry point synchronises, allocates device memory (except *_create) or
+ * reads results back, so every call is capturable in a CUDA graph exactly like the reference's
+ * `wp.ScopedCapture` usage (newton/examples/basic/example_basic_urdf.py:112-115).
+ *
+ * The oracle (oracle/oracle.cpp, test infrastructure only) consumes the same POD structs with
+ * HOST pointers.
+ */
+#ifndef NEWTON_B200_H
+#define NEWTON_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum nb2_status {
+    NB2_OK = 0,
+    NB2_ERR_INVALID_ARGUMENT = 1, /* NULL pointer, negative count, inconsistent sizes         */
+    NB2_ERR_UNSUPPORTED = 2,      /* model uses a feature outside the hot-path scope (§8)     */
+    NB2_ERR_CUDA = 3,             /* a CUDA runtime call failed; see nb2_last_error()          */
+    NB2_ERR_CAPACITY = 4          /* a per-environment limit of the fused kernels is exceeded  */
+} nb2_status;
+
+/* Static model arrays read by the hot path.
+ * Replaces the `Model` fields listed in SURVEY.md §8(a4): reference sim/model.py:1060-1079 (bodies),
+ * :1123-1175 (joints), :808-883 (shapes), :1249-1282 (articulations), :1300 (gravity). */
+typedef struct nb2_model_desc {
+    int32_t world_count;
+    int32_t body_count;
+    int32_t joint_count;
+    int32_t joint_dof_count;
+    int32_t joint_coord_count;
+    int32_t shape_count;
+    int32_t shape_pair_count;
+    int32_t articulation_count;
+    /* bodies [body_count] */
+    const float* body_com;           /* vec3  */
+    const float* body_mass;          /* f32   */
+    const float* body_inv_mass;      /* f32   */
+    const float* body_inertia;       /* mat33 */
+    const float* body_inv_inertia;   /* mat33 */
+    const int32_t* body_flags;       /* BodyFlags; KINEMATIC = 2 */
+    const int32_t* body_world;       /* -1 = global */
+    const int32_t* body_world_start; /* [world_count + 2] */
+    /* joints [joint_count] */
+    const int32_t* joint_type;       /* JointType */
+    const uint8_t* joint_enabled;    /* bool */
+    const int32_t* joint_parent;     /* body index or -1 */
+    const int32_t* joint_child;
+    const int32_t* joint_ancestor;   /* parent joint index or -1 */
+    const int32_t* joint_articulation;
+    const float* joint_X_p;          /* transform */
+    const float* joint_X_c;          /* transform */
+    const int32_t* joint_q_start;    /* [joint_count + 1] */
+    const int32_t* joint_qd_start;   /* [joint_count + 1] */
+    const int32_t* joint_target_q_start; /* == joint_q_start (coord layout) or joint_qd_start */
+    const int32_t* joint_dof_dim;    /* [joint_count, 2] (linear, angular) */
+    const int32_t* joint_world_start;/* [world_count + 2] */
+    /* dofs [joint_dof_count] */
+    const float* joint_axis;         /* vec3 */
+    const float* joint_limit_lower;
+    const float* joint_limit_upper;
+    const float* joint_limit_ke;
+    const float* joint_limit_kd;
+    const float* joint_target_ke;
+    const float* joint_target_kd;
+    const float* joint_armature;
+    /* articulations */
+    const int32_t* articulation_start; /* [articulation_count + 1] */
+    /* shapes [shape_count] */
+    const int32_t* shape_body;
+    const int32_t* shape_type;       /* GeoType */
+    const float* shape_transform;    /* transform (body frame) */
+    const float* shape_scale;        /* vec3 */
+    const float* shape_margin;
+    const float* shape_gap;
+    const float* shape_collision_radius;
+    const int32_t* shape_flags;
+    const int32_t* shape_world;
+    const int32_t* shape_world_start;/* [world_count + 2] */
+    const float* shape_material_ke;
+    const float* shape_material_kd;
+    const float* shape_material_kf;
+    const float* shape_material_ka;
+    const float* shape_material_mu;
+    const float* shape_material_mu_torsional;
+    const float* shape_material_mu_rolling;
+    const float* shape_material_restitution;
+    /* explicit broad-phase pairs [shape_pair_count, 2] (reference model.shape_contact_pairs) */
+    const int32_t* shape_contact_pairs;
+    /* gravity [world_count + 1] vec3, last slot = global world -1 (reference sim/model.py:1300-1307);
+       gravity_count is the number of vec3 entries actually present (1 for implicit single-world models) */
+    const float* gravity;
+    int32_t gravity_count;
+} nb2_model_desc;
+
+/* Reference `State` arrays (sim/state.py:119-171). Pointers may be NULL when the count is zero. */
+typedef struct nb2_state_view {
+    float* body_q;        /* transform [body_count]       */
+    float* body_qd;       /* spatial_vector [body_count]  */
+    float* body_f;        /* spatial_vector [body_count]  */
+    float* joint_q;       /* f32 [joint_coord_count]      */
+    float* joint_qd;      /* f32 [joint_dof_count]        */
+    float* body_parent_f; /* optional, may be NULL        */
+} nb2_state_view;
+
+/* Reference `Control` arrays (sim/control.py:32-74). */
+typedef struct nb2_control_view {
+    const float* joint_f;         /* [joint_dof_count]   */
+    const float* joint_target_q;  /* indexed through joint_target_q_start */
+    const float* joint_target_qd; /* [joint_dof_count]   */
+    const float* joint_act;       /* [joint_dof_count], may be NULL */
+} nb2_control_view;
+
+/* Reference `Contacts` rigid arrays (sim/contacts.py:234-276). */
+typedef struct nb2_contacts_view {
+    int32_t rigid_contact_max;
+    int32_t* rigid_contact_count; /* i32[1] */
+    int32_t* shape0;
+    int32_t* shape1;
+    float* point0;  /* vec3, body frame of shape0's body */
+    float* point1;
+    float* offset0; /* vec3 */
+    float* offset1;
+    float* normal;  /* vec3, world, A -> B */
+    float* margin0;
+    float* margin1;
+    int32_t* tids;
+} nb2_contacts_view;
+
+/* Constructor kwargs of reference SolverXPBD (solvers/xpbd/solver_xpbd.py:99-116). */
+typedef struct nb2_xpbd_params {
+    int32_t iterations;
+    float joint_linear_relaxation;
+    float joint_angular_relaxation;
+    float joint_linear_compliance;
+    float joint_angular_compliance;
+    float rigid_contact_relaxation;
+    int32_t rigid_contact_con_weighting;
+    float angular_damping;
+    int32_t enable_restitution;
+} nb2_xpbd_params;
+
+/* Constructor kwargs of reference SolverFeatherstone (solvers/featherstone/solver_featherstone.py:135-146). */
+typedef struct nb2_featherstone_params {
+    float angular_damping;
+    int32_t update_mass_matrix_interval;
+    float friction_smoothing;
+} nb2_featherstone_params;
+
+typedef struct nb2_model nb2_model; /* opaque: env partition, contact blocks, solver scratch */
+
+/* --- lifecycle ------------------------------------------------------------------------------ */
+
+/* Ingest device pointers + counts, validate the env partition, allocate contact blocks and scratch.
+ * Replaces the per-solver / per-pipeline construction work of reference SolverXPBD.__init__
+ * (solver_xpbd.py:99-182) and CollisionPipeline.__init__ (sim/collide.py:1104-1670).
+ * `device` is the CUDA ordinal the pointers live on. */
+nb2_status nb2_model_create(const nb2_model_desc* desc, int32_t device, nb2_model** out);
+void nb2_model_destroy(nb2_model* model);
+
+/* Reference SolverBase.notify_model_changed (solvers/solver.py:394-429): the kernels read the Model
+ * arrays live, so only derived tables (env partition, joint adjacency) are rebuilt. */
+nb2_status nb2_model_notify_changed(nb2_model* model, const nb2_model_desc* desc, int32_t flags);
+
+/* Capacity the pipeline needs in a Contacts object (reference _estimate_rigid_contact_max,
+ * sim/collide.py:553-652 gives an upper bound; this is the exact per-pair bound used by the blocks). */
+int32_t nb2_model_rigid_contact_max(const nb2_model* model);
+
+/* --- hot path ------------------------------------------------------------------------------- */
+
+/* Reference CollisionPipeline.collide(state, contacts) (sim/collide.py:1765-2207): AABBs, explicit
+ * broad phase, analytic + GJK/MPR narrow phase, contact write-out.  Contacts are always written to
+ * the model's env-major contact blocks (consumed by nb2_xpbd_step / nb2_featherstone_step); when
+ * `contacts` is non-NULL they are additionally compacted into the reference `Contacts` arrays in
+ * deterministic (env, sort-key) order and `rigid_contact_count[0]` is set. */
+nb2_status nb2_collide(nb2_model* model, const float* body_q, const nb2_contacts_view* contacts, void* cuda_stream);
+
+/* Reference SolverXPBD.step(state_in, state_out, control, contacts, dt) (solver_xpbd.py:329-862).
+ * `use_contacts` = 0 mirrors `contacts=None`.  Contacts come from the last nb2_collide() on this model.
+ * Writes state_out.body_q/body_qd; like the reference it may also overwrite state_in.body_q/body_qd
+ * (ping-pong scratch, solver_xpbd.py:290-300). */
+nb2_status nb2_xpbd_step(nb2_model* model, const nb2_xpbd_params* params, const nb2_state_view* state_in,
+                         const nb2_state_view* state_out, const nb2_control_view* control, int32_t use_contacts,
+                         float dt, void* cuda_stream);
+
+/* Reference SolverBase.integrate_bodies (solvers/solver.py:267-307; kernel :112-170). */
+nb2_status nb2_integrate_bodies(nb2_model* model, const nb2_state_view* state_in, const nb2_state_view* state_out,
+                                float angular_damping, float dt, void* cuda_stream);
+
+/* Reference SolverFeatherstone.step (solvers/featherstone/solver_featherstone.py:461-1066). */
+nb2_status nb2_featherstone_step(nb2_model* model, const nb2_featherstone_params* params,
+                                 const nb2_state_view* state_in, const nb2_state_view* state_out,
+                                 const nb2_control_view* control, int32_t use_contacts, float dt, void* cuda_stream);
+
+/* Reference newton.eval_fk (sim/articulation.py:500-574): joint_q/joint_qd -> body_q/body_qd. */
+nb2_status nb2_eval_fk(nb2_model* model, const float* joint_q, const float* joint_qd, float* body_q, float* body_qd,
+                       void* cuda_stream);
+
+/* --- diagnostics ---------------------------------------------------------------------------- */
+const char* nb2_last_error(void);
+/* Number of kernels this library has launched since load (for bench.py's gpu_launches claim). */
+int64_t nb2_kernel_launch_count(void);
+const char* nb2_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEWTON_B200_H */

@@ -82,20 +82,20 @@ def eval_fk(model, joint_q, joint_qd, state) -> None:
         if p >= 0:
             w_parent = body_qd[p][3:]
             com_p = X.transform_point(body_q[p], com[p])
-            v_parent_origin = body_qd[p][:3] + np.cross(w_parent, x_child - com_p)
+            v_parent_origin = body_qd[p][:3] + X.cross(w_parent, x_child - com_p)
         lin_w = X.transform_vector(X_wpj, v_lin)
         ang_w = X.transform_vector(X_wpj, v_ang)
         c = child[i]
         if t in (JointType.FREE, JointType.DISTANCE):
             com_c = X.transform_point(X_wc, com[c])
-            lin_origin = lin_w + np.cross(ang_w, x_child - com_c)  # COM twist -> origin twist
+            lin_origin = lin_w + X.cross(ang_w, x_child - com_c)  # COM twist -> origin twist
         else:
-            lin_origin = lin_w + np.cross(ang_w, x_child - X_wcj[:3])
+            lin_origin = lin_w + X.cross(ang_w, x_child - X_wcj[:3])
         v_o = v_parent_origin + lin_origin
         w = w_parent + ang_w
         body_q[c] = X_wc
         com_c = X.transform_point(X_wc, com[c])
-        body_qd[c] = np.concatenate([v_o + np.cross(w, com_c - x_child), w])
+        body_qd[c] = np.concatenate([v_o + X.cross(w, com_c - x_child), w])
 
     state.body_q.copy_(torch.from_numpy(body_q.astype(np.float32)))
     state.body_qd.copy_(torch.from_numpy(body_qd.astype(np.float32)))

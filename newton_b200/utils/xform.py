@@ -12,6 +12,10 @@ import math
 import numpy as np
 
 
+def cross(a, b):
+    return np.array([a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]])
+
+
 def quat_identity():
     return np.array([0.0, 0.0, 0.0, 1.0])
 
@@ -38,7 +42,7 @@ def quat_rotate(q, v):
     v = np.asarray(v, dtype=np.float64)
     u = q[:3]
     w = q[3]
-    return v * (2.0 * w * w - 1.0) + u * (2.0 * np.dot(u, v)) + np.cross(u, v) * (2.0 * w)
+    return v * (2.0 * w * w - 1.0) + u * (2.0 * (u[0] * v[0] + u[1] * v[1] + u[2] * v[2])) + cross(u, v) * (2.0 * w)
 
 
 def quat_rotate_inv(q, v):

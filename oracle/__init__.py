@@ -1,0 +1,180 @@
+"""CPU oracle - TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import this package.  The product path (``newton_b200``) never does and fails loudly without
+its CUDA library.
+
+``liboracle.so`` (built from ``oracle/oracle.cpp`` by ``oracle/Makefile``) restates the reference
+kernels of SURVEY.md §8(a) on the CPU; this module wraps it behind classes with the reference's own
+call signatures (``SolverXPBD.step``, ``CollisionPipeline.collide`` ...) operating on CPU tensors.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import torch
+
+from newton_b200 import _abi
+from newton_b200.sim.model import Contacts
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force: bool = False) -> str:
+    """Compile ``liboracle.so`` with g++ (``-ffp-contract=off``)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h"))]
+    srcs.append(os.path.join(_HERE, "..", "include", "newton_b200.h"))
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True, capture_output=True)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(so):
+            build()
+        _LIB = C.CDLL(so)
+        _LIB.orc_collide.restype = C.c_int
+        _LIB.orc_primitive_pair.restype = C.c_int
+        _LIB.orc_convex_pair.restype = C.c_int
+        _LIB.orc_version.restype = C.c_char_p
+    return _LIB
+
+
+def _check_cpu(model):
+    if str(model.device) != "cpu":
+        raise ValueError("the oracle runs on CPU tensors only")
+
+
+class CollisionPipeline:
+    """Oracle for reference ``CollisionPipeline`` (``sim/collide.py:1104-2207``), ``broad_phase="explicit"``."""
+
+    def __init__(self, model, *, broad_phase=None, rigid_contact_max=None, deterministic=True):
+        _check_cpu(model)
+        if broad_phase not in (None, "explicit"):
+            raise NotImplementedError("oracle implements the explicit broad phase")
+        self.model = model
+        self.deterministic = deterministic
+        self._desc = _abi.model_desc(model)
+        self.rigid_contact_max = (
+            int(rigid_contact_max) if rigid_contact_max is not None else max(1000, 5 * model.shape_contact_pair_count)
+        )
+        self.candidate_count = 0
+
+    def contacts(self) -> Contacts:
+        return Contacts(self.rigid_contact_max, 0, device="cpu",
+                        requested_attributes=self.model._requested_contact_attributes)
+
+    def collide(self, state, contacts, *, soft_contact_margin=None, dt=None):
+        v = _abi.contacts_view(contacts)
+        self.candidate_count = lib().orc_collide(
+            C.byref(self._desc), C.c_void_p(_abi.ptr(state.body_q)), C.byref(v), C.c_int(1 if self.deterministic else 0)
+        )
+
+
+class SolverXPBD:
+    """Oracle for reference ``SolverXPBD`` (``solvers/xpbd/solver_xpbd.py:99-862``), rigid-body path."""
+
+    def __init__(self, model, *, iterations=2, soft_body_relaxation=0.9, soft_contact_relaxation=0.9,
+                 joint_linear_relaxation=0.7, joint_angular_relaxation=0.4, joint_linear_compliance=0.0,
+                 joint_angular_compliance=0.0, rigid_contact_relaxation=0.8, rigid_contact_con_weighting=True,
+                 angular_damping=0.0, enable_restitution=False, deterministic=None):
+        _check_cpu(model)
+        if enable_restitution:
+            raise NotImplementedError("oracle: enable_restitution")
+        self.model = model
+        self._desc = _abi.model_desc(model)
+        self.params = _abi.XPBDParams(iterations, joint_linear_relaxation, joint_angular_relaxation,
+                                      joint_linear_compliance, joint_angular_compliance, rigid_contact_relaxation,
+                                      1 if rigid_contact_con_weighting else 0, angular_damping, 0)
+
+    def step(self, state_in, state_out, control, contacts, dt):
+        if control is None:
+            control = self.model.control(clone_variables=False)
+        sv_in, sv_out, cv = _abi.state_view(state_in), _abi.state_view(state_out), _abi.control_view(control)
+        if contacts is not None:
+            ctv = _abi.contacts_view(contacts)
+            ctp = C.byref(ctv)
+        else:
+            ctp = None
+        lib().orc_xpbd_step(C.byref(self._desc), C.byref(self.params), C.byref(sv_in), C.byref(sv_out), C.byref(cv), ctp,
+                            C.c_float(dt))
+
+    def integrate_bodies(self, model, state_in, state_out, dt, angular_damping=0.0):
+        sv_in, sv_out = _abi.state_view(state_in), _abi.state_view(state_out)
+        lib().orc_integrate_bodies(C.byref(self._desc), C.byref(sv_in), C.byref(sv_out), C.c_float(angular_damping),
+                                   C.c_float(dt))
+
+
+class SolverFeatherstone:
+    """Oracle for reference ``SolverFeatherstone`` (``solvers/featherstone/solver_featherstone.py:135-1066``)."""
+
+    def __init__(self, model, *, angular_damping=0.05, update_mass_matrix_interval=1, friction_smoothing=1.0,
+                 use_tile_gemm=False, fuse_cholesky=True, deterministic=None):
+        _check_cpu(model)
+        self.model = model
+        self._desc = _abi.model_desc(model)
+        self.params = _abi.FeatherstoneParams(angular_damping, update_mass_matrix_interval, friction_smoothing)
+
+    def step(self, state_in, state_out, control, contacts, dt):
+        if control is None:
+            control = self.model.control(clone_variables=False)
+        sv_in, sv_out, cv = _abi.state_view(state_in), _abi.state_view(state_out), _abi.control_view(control)
+        if contacts is not None:
+            ctv = _abi.contacts_view(contacts)
+            ctp = C.byref(ctv)
+        else:
+            ctp = None
+        lib().orc_featherstone_step(C.byref(self._desc), C.byref(self.params), C.byref(sv_in), C.byref(sv_out),
+                                    C.byref(cv), ctp, C.c_float(dt))
+
+
+def primitive_pair(type_a, scale_a, xform_a, type_b, scale_b, xform_b, plane_box_margin=0.0):
+    """One analytic collider call: returns (is_analytic, dist[4], pos[4,3], normal[3])."""
+    sa = np.asarray(scale_a, dtype=np.float32)
+    sb = np.asarray(scale_b, dtype=np.float32)
+    xa = np.asarray(xform_a, dtype=np.float32)
+    xb = np.asarray(xform_b, dtype=np.float32)
+    dist = np.zeros(4, dtype=np.float32)
+    pos = np.zeros((4, 3), dtype=np.float32)
+    n = np.zeros(3, dtype=np.float32)
+    ok = lib().orc_primitive_pair(
+        int(type_a), C.c_void_p(sa.ctypes.data), C.c_void_p(xa.ctypes.data), int(type_b), C.c_void_p(sb.ctypes.data),
+        C.c_void_p(xb.ctypes.data), C.c_float(plane_box_margin), C.c_void_p(dist.ctypes.data),
+        C.c_void_p(pos.ctypes.data), C.c_void_p(n.ctypes.data),
+    )
+    return bool(ok), dist, pos, n
+
+
+def convex_pair(type_a, scale_a, xform_a, type_b, scale_b, xform_b, gap_sum=0.2):
+    """GJK/MPR + manifold for one convex pair: returns (count, dist[5], pos[5,3], normal[5,3])."""
+    sa = np.asarray(scale_a, dtype=np.float32)
+    sb = np.asarray(scale_b, dtype=np.float32)
+    xa = np.asarray(xform_a, dtype=np.float32)
+    xb = np.asarray(xform_b, dtype=np.float32)
+    dist = np.zeros(5, dtype=np.float32)
+    pos = np.zeros((5, 3), dtype=np.float32)
+    n = np.zeros((5, 3), dtype=np.float32)
+    cnt = lib().orc_convex_pair(
+        int(type_a), C.c_void_p(sa.ctypes.data), C.c_void_p(xa.ctypes.data), int(type_b), C.c_void_p(sb.ctypes.data),
+        C.c_void_p(xb.ctypes.data), C.c_float(gap_sum), C.c_void_p(dist.ctypes.data), C.c_void_p(pos.ctypes.data),
+        C.c_void_p(n.ctypes.data),
+    )
+    return cnt, dist, pos, n
+
+
+def shape_aabbs(model, body_q):
+    d = _abi.model_desc(model)
+    lo = np.zeros((model.shape_count, 3), dtype=np.float32)
+    hi = np.zeros((model.shape_count, 3), dtype=np.float32)
+    lib().orc_compute_shape_aabbs(C.byref(d), C.c_void_p(_abi.ptr(body_q)), C.c_void_p(lo.ctypes.data),
+                                  C.c_void_p(hi.ctypes.data))
+    return lo, hi

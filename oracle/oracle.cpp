@@ -1,0 +1,181 @@
+// oracle.cpp - TEST INFRASTRUCTURE ONLY.  Never linked, imported or executed by the product path
+// (newton_b200/), only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+//
+// CPU restatement of the reference's per-substep hot path behind the same POD structs as
+// include/newton_b200.h, with HOST pointers:
+//   orc_collide            <- CollisionPipeline.collide      reference sim/collide.py:1765-2207
+//   orc_xpbd_step          <- SolverXPBD.step                reference solvers/xpbd/solver_xpbd.py:329-862
+//   orc_integrate_bodies   <- SolverBase.integrate_bodies    reference solvers/solver.py:267-307
+//   orc_featherstone_step  <- SolverFeatherstone.step        reference solvers/featherstone/solver_featherstone.py:461-1066
+//
+// PARITY STATUS: "parity unpinned" at the bit level.  The reference cannot run in the authoring container or on
+// the GPU box (NVIDIA Warp, which JIT-compiles every reference kernel, is not installed and there is no network),
+// and the reference ships no golden vectors for this path.  The oracle is therefore pinned against
+// every known-answer check the reference's own tests hold for the path (closed-form collider expectations from
+// newton/tests/test_collision_primitives.py, analytic physics from test_physics_verification.py, example
+// test_final() assertions) in tests/test_oracle_*.py; the Warp built-ins are restated in oracle_math.h.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "oracle_collide.h"
+#include "oracle_featherstone.h"
+#include "oracle_gjk.h"
+#include "oracle_xpbd.h"
+
+using namespace orc;
+
+namespace {
+
+void effective_inv_mass(const nb2_model_desc& m, std::vector<float>& inv_m, std::vector<float>& inv_I) {
+    // reference solvers/solver.py:173-187 (_update_effective_inv_mass_inertia)
+    inv_m.resize(m.body_count);
+    inv_I.resize(size_t(m.body_count) * 9);
+    for (int i = 0; i < m.body_count; ++i) {
+        bool kin = (m.body_flags[i] & BODY_KINEMATIC) != 0;
+        inv_m[i] = kin ? 0.0f : m.body_inv_mass[i];
+        for (int k = 0; k < 9; ++k) inv_I[9 * i + k] = kin ? 0.0f : m.body_inv_inertia[9 * i + k];
+    }
+}
+
+void store_contacts(const std::vector<RawContact>& cs, const nb2_contacts_view& out) {
+    int n = int(cs.size());
+    out.rigid_contact_count[0] = n;  // count keeps growing past capacity, writes dropped (collide.py:176-177)
+    for (int i = 0; i < n && i < out.rigid_contact_max; ++i) {
+        const RawContact& c = cs[i];
+        out.shape0[i] = c.shape0;
+        out.shape1[i] = c.shape1;
+        store3(out.point0 + 3 * i, c.point0);
+        store3(out.point1 + 3 * i, c.point1);
+        store3(out.offset0 + 3 * i, c.offset0);
+        store3(out.offset1 + 3 * i, c.offset1);
+        store3(out.normal + 3 * i, c.normal);
+        out.margin0[i] = c.margin0;
+        out.margin1[i] = c.margin1;
+        if (out.tids) out.tids[i] = 0;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// CollisionPipeline.collide with broad_phase="explicit".  deterministic != 0 applies the radix sort by
+// make_contact_sort_key (reference collide.py:2054-2073), the canonical order used for parity.
+int orc_collide(const nb2_model_desc* m, const float* body_q, const nb2_contacts_view* contacts, int deterministic) {
+    CollideResult res;
+    collide_primitives(*m, body_q, res);
+    gjk_mpr_pairs(*m, body_q, res);
+    if (deterministic)
+        std::stable_sort(res.contacts.begin(), res.contacts.end(),
+                         [](const RawContact& a, const RawContact& b) { return a.key < b.key; });
+    store_contacts(res.contacts, *contacts);
+    return res.candidate_count;
+}
+
+void orc_integrate_bodies(const nb2_model_desc* m, const nb2_state_view* in, const nb2_state_view* out, float angular_damping,
+                          float dt) {
+    integrate_bodies(*m, in->body_q, in->body_qd, in->body_f, angular_damping, dt, out->body_q, out->body_qd);
+}
+
+// SolverXPBD.step, rigid-body part (reference solver_xpbd.py:329-862).
+void orc_xpbd_step(const nb2_model_desc* mp, const nb2_xpbd_params* p, const nb2_state_view* state_in,
+                   const nb2_state_view* state_out, const nb2_control_view* control, const nb2_contacts_view* contacts, float dt) {
+    const nb2_model_desc& m = *mp;
+    if (m.body_count == 0) return;
+    std::vector<float> inv_m, inv_I;
+    effective_inv_mass(m, inv_m, inv_I);
+    const size_t B = size_t(m.body_count);
+    std::vector<float> body_deltas(B * 6, 0.f), inv_weight(B, 0.f);
+    std::vector<float> body_f_tmp(state_in->body_f, state_in->body_f + B * 6);
+    if (m.joint_count) apply_joint_forces(m, state_in->body_q, control->joint_f, dt, body_f_tmp.data());
+    integrate_bodies(m, state_in->body_q, state_in->body_qd, body_f_tmp.data(), p->angular_damping, dt, state_out->body_q,
+                     state_out->body_qd);
+    float* body_q = state_out->body_q;
+    float* body_qd = state_out->body_qd;
+    int counter = 0;  // _body_delta_counter (solver_xpbd.py:283-300)
+    auto apply = [&](const float* weights) {
+        float *q_in, *qd_in, *q_new, *qd_new;
+        if (counter == 0) {
+            q_in = state_out->body_q; qd_in = state_out->body_qd; q_new = state_in->body_q; qd_new = state_in->body_qd;
+        } else {
+            q_in = state_in->body_q; qd_in = state_in->body_qd; q_new = state_out->body_q; qd_new = state_out->body_qd;
+        }
+        counter = 1 - counter;
+        apply_body_deltas(m, q_in, qd_in, inv_m.data(), inv_I.data(), body_deltas.data(), weights, dt, q_new, qd_new);
+        body_q = q_new;
+        body_qd = qd_new;
+    };
+    for (int it = 0; it < p->iterations; ++it) {
+        std::fill(body_deltas.begin(), body_deltas.end(), 0.f);
+        if (contacts) {
+            float* w = nullptr;
+            if (p->rigid_contact_con_weighting) {
+                std::fill(inv_weight.begin(), inv_weight.end(), 0.f);
+                w = inv_weight.data();
+            }
+            solve_body_contact_positions(m, body_q, body_qd, inv_m.data(), inv_I.data(), *contacts, p->rigid_contact_relaxation,
+                                         dt, body_deltas.data(), w);
+            apply(w);
+        }
+        if (m.joint_count) {
+            std::fill(body_deltas.begin(), body_deltas.end(), 0.f);
+            solve_body_joints(m, body_q, body_qd, inv_m.data(), inv_I.data(), *control, p->joint_linear_compliance,
+                              p->joint_angular_compliance, p->joint_angular_relaxation, p->joint_linear_relaxation, dt,
+                              body_deltas.data());
+            apply(nullptr);
+        }
+    }
+    if (body_q != state_out->body_q) {
+        std::memcpy(state_out->body_q, body_q, B * 7 * sizeof(float));
+        std::memcpy(state_out->body_qd, body_qd, B * 6 * sizeof(float));
+    }
+    // copy_kinematic_body_state_kernel (kernels.py:19-32)
+    for (int i = 0; i < m.body_count; ++i) {
+        if ((m.body_flags[i] & BODY_KINEMATIC) == 0) continue;
+        std::memcpy(state_out->body_q + 7 * i, state_in->body_q + 7 * i, 7 * sizeof(float));
+        std::memcpy(state_out->body_qd + 6 * i, state_in->body_qd + 6 * i, 6 * sizeof(float));
+    }
+}
+
+void orc_featherstone_step(const nb2_model_desc* m, const nb2_featherstone_params* p, const nb2_state_view* state_in,
+                           const nb2_state_view* state_out, const nb2_control_view* control, const nb2_contacts_view* contacts,
+                           float dt) {
+    featherstone_step(*m, *p, *state_in, *state_out, *control, contacts, dt);
+}
+
+// ---- unit-level hooks for known-answer tests ------------------------------------------------------
+// One analytic pair: types/scales/transforms in, up to 4 (distance, position) + normal out.
+int orc_primitive_pair(int type_a, const float* scale_a, const float* xform_a, int type_b, const float* scale_b,
+                       const float* xform_b, float plane_box_margin, float* dist4, float* pos12, float* normal3) {
+    float d[4];
+    vec3 p[4], n;
+    bool ok = primitive_pair(type_a, load3(scale_a), transform::load(xform_a), type_b, load3(scale_b), transform::load(xform_b),
+                             plane_box_margin, d, p, n);
+    for (int i = 0; i < 4; ++i) {
+        dist4[i] = d[i];
+        store3(pos12 + 3 * i, p[i]);
+    }
+    store3(normal3, n);
+    return ok ? 1 : 0;
+}
+
+void orc_compute_shape_aabbs(const nb2_model_desc* m, const float* body_q, float* lower, float* upper) {
+    std::vector<ShapeGeom> g;
+    compute_shape_aabbs(*m, body_q, g);
+    for (int i = 0; i < m->shape_count; ++i) {
+        store3(lower + 3 * i, g[i].aabb_lower);
+        store3(upper + 3 * i, g[i].aabb_upper);
+    }
+}
+
+// Convex pair through MPR/GJK + manifold (oracle_gjk.h): returns contact count, fills up to 5 contacts.
+int orc_convex_pair(int type_a, const float* scale_a, const float* xform_a, int type_b, const float* scale_b,
+                    const float* xform_b, float gap_sum, float* dist5, float* pos15, float* normal15) {
+    return convex_pair_test(type_a, load3(scale_a), transform::load(xform_a), type_b, load3(scale_b),
+                            transform::load(xform_b), gap_sum, dist5, pos15, normal15);
+}
+
+const char* orc_version(void) { return "oracle-r1"; }
+
+}  // extern "C"
