@@ -3,3 +3,5 @@ from .sim import (  # noqa: F401
     MAXVAL, BodyFlags, Contacts, Control, GeoType, JointDofConfig, JointType, Model, ModelBuilder,
     ModelFlags, ShapeConfig, ShapeFlags, State, StateFlags, eval_fk,
 )
+from .sim.collide import CollisionPipeline  # noqa: F401,E402
+from . import solvers  # noqa: F401,E402

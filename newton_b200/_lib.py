@@ -1,0 +1,128 @@
+"""Loader for ``libnewton_b200.so`` - the C-ABI library holding every CUDA kernel of the hot path.
+
+There is no CPU fallback: if the library is missing or a call fails, an exception is raised.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnewton_b200.so")
+_lib = None
+
+STATUS = {0: "NB2_OK", 1: "NB2_ERR_INVALID_ARGUMENT", 2: "NB2_ERR_UNSUPPORTED", 3: "NB2_ERR_CUDA", 4: "NB2_ERR_CAPACITY"}
+
+# every symbol include/newton_b200.h declares
+EXPORTED_SYMBOLS = (
+    "nb2_model_create", "nb2_model_destroy", "nb2_model_notify_changed", "nb2_model_rigid_contact_max", "nb2_collide",
+    "nb2_xpbd_step", "nb2_integrate_bodies", "nb2_featherstone_step", "nb2_eval_fk", "nb2_last_error",
+    "nb2_kernel_launch_count", "nb2_version",
+)
+
+
+class Nb2Error(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded library (raises if it has not been built: run ``python -m newton_b200.build``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Nb2Error(
+                f"{LIB_PATH} is missing - build it with `python -m newton_b200.build` (nvcc, sm_100a). "
+                "newton_b200 has no CPU or PyTorch fallback for the hot path."
+            )
+        L = C.CDLL(LIB_PATH)
+        P = C.c_void_p
+        L.nb2_model_create.argtypes = [C.POINTER(_abi.ModelDesc), C.c_int32, C.POINTER(P)]
+        L.nb2_model_create.restype = C.c_int
+        L.nb2_model_destroy.argtypes = [P]
+        L.nb2_model_destroy.restype = None
+        L.nb2_model_notify_changed.argtypes = [P, C.POINTER(_abi.ModelDesc), C.c_int32]
+        L.nb2_model_notify_changed.restype = C.c_int
+        L.nb2_model_rigid_contact_max.argtypes = [P]
+        L.nb2_model_rigid_contact_max.restype = C.c_int32
+        L.nb2_collide.argtypes = [P, P, C.POINTER(_abi.ContactsView), P]
+        L.nb2_collide.restype = C.c_int
+        L.nb2_xpbd_step.argtypes = [P, C.POINTER(_abi.XPBDParams), C.POINTER(_abi.StateView), C.POINTER(_abi.StateView),
+                                    C.POINTER(_abi.ControlView), C.c_int32, C.c_float, P]
+        L.nb2_xpbd_step.restype = C.c_int
+        L.nb2_integrate_bodies.argtypes = [P, C.POINTER(_abi.StateView), C.POINTER(_abi.StateView), C.c_float, C.c_float, P]
+        L.nb2_integrate_bodies.restype = C.c_int
+        L.nb2_featherstone_step.argtypes = [P, C.POINTER(_abi.FeatherstoneParams), C.POINTER(_abi.StateView),
+                                            C.POINTER(_abi.StateView), C.POINTER(_abi.ControlView), C.c_int32, C.c_float, P]
+        L.nb2_featherstone_step.restype = C.c_int
+        L.nb2_eval_fk.argtypes = [P, P, P, P, P, P]
+        L.nb2_eval_fk.restype = C.c_int
+        L.nb2_last_error.restype = C.c_char_p
+        L.nb2_kernel_launch_count.restype = C.c_int64
+        L.nb2_version.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = lib().nb2_last_error().decode()
+        if status == 2:
+            raise NotImplementedError(f"{what}: {msg}")
+        if status == 1:
+            raise ValueError(f"{what}: {msg}")
+        raise Nb2Error(f"{what}: {STATUS.get(status, status)}: {msg}")
+
+
+def kernel_launch_count() -> int:
+    return int(lib().nb2_kernel_launch_count())
+
+
+class NativeModel:
+    """Owner of one ``nb2_model`` handle; shared by the pipeline and solvers built on the same Model."""
+
+    def __init__(self, model):
+        import torch
+
+        dev = torch.device(model.device) if not isinstance(model.device, torch.device) else model.device
+        if dev.type != "cuda":
+            raise Nb2Error(
+                f"newton_b200 solvers run on CUDA devices only (model.device={model.device}); there is no CPU path. "
+                "Use oracle/ (test infrastructure) for CPU checks."
+            )
+        self.model = model
+        self.device_index = dev.index if dev.index is not None else torch.cuda.current_device()
+        self.desc = _abi.model_desc(model)
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device_index):
+            check(lib().nb2_model_create(C.byref(self.desc), self.device_index, C.byref(handle)), "nb2_model_create")
+        self.handle = handle
+        self.rigid_contact_max = int(lib().nb2_model_rigid_contact_max(handle))
+
+    def notify_model_changed(self, flags: int):
+        self.desc = _abi.model_desc(self.model)
+        check(lib().nb2_model_notify_changed(self.handle, C.byref(self.desc), int(flags)), "nb2_model_notify_changed")
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                lib().nb2_model_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def native_model(model) -> NativeModel:
+    nm = getattr(model, "_nb2_native", None)
+    if nm is None:
+        nm = NativeModel(model)
+        model._nb2_native = nm
+    return nm
+
+
+def current_stream_ptr(model) -> C.c_void_p:
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream(native_model(model).device_index).cuda_stream)

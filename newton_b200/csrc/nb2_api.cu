@@ -1,0 +1,351 @@
+// nb2_api.cu - C-ABI entry points of libnewton_b200.so (include/newton_b200.h) and model ingestion.
+//
+// nb2_model_create() derives, once, the tables the fused per-environment kernels need from the reference-layout
+// Model arrays: the env partition (worlds are contiguous index ranges: reference sim/model.py:1081-1097), the
+// per-env explicit pair lists re-ordered by the deterministic contact key (reference geometry/contact_data.py:59-87),
+// the per-body joint adjacency used for ordered (atomic-free) Jacobi accumulation, and the env-major contact blocks.
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "nb2_internal.cuh"
+
+namespace nb2 {
+
+static thread_local std::string g_last_error;
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+template <typename T>
+static nb2_status fetch(const T* dptr, size_t n, std::vector<T>& out) {
+    out.resize(n);
+    if (n == 0) return NB2_OK;
+    if (!dptr) {
+        set_error("nb2_model_create: required model array is NULL");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    NB2_CUDA_CHECK(cudaMemcpy(out.data(), dptr, n * sizeof(T), cudaMemcpyDeviceToHost));
+    return NB2_OK;
+}
+
+template <typename T>
+static nb2_status upload(nb2_model* m, const std::vector<T>& v, const T** out) {
+    void* p = nullptr;
+    size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    NB2_CUDA_CHECK(cudaMalloc(&p, bytes));
+    m->allocations.push_back(p);
+    if (!v.empty()) NB2_CUDA_CHECK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = static_cast<const T*>(p);
+    return NB2_OK;
+}
+
+static int pow2_at_least(int x) {
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+static nb2_status build_tables(nb2_model* m, const nb2_model_desc& d) {
+    HostTables& h = m->host;
+    const int W = d.world_count, B = d.body_count, J = d.joint_count, S = d.shape_count, P = d.shape_pair_count;
+    if (W <= 0 || B < 0 || J < 0 || S < 0 || P < 0) {
+        set_error("nb2_model_create: invalid counts");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    std::vector<int> bws, jws, sws, shape_world, shape_type, shape_body, jparent, jchild, pairs, art_start, jart;
+    nb2_status st;
+    if ((st = fetch(d.body_world_start, size_t(W) + 2, bws))) return st;
+    if ((st = fetch(d.joint_world_start, size_t(W) + 2, jws))) return st;
+    if ((st = fetch(d.shape_world_start, size_t(W) + 2, sws))) return st;
+    if ((st = fetch(d.shape_world, size_t(S), shape_world))) return st;
+    if ((st = fetch(d.shape_type, size_t(S), shape_type))) return st;
+    if ((st = fetch(d.shape_body, size_t(S), shape_body))) return st;
+    if ((st = fetch(d.joint_parent, size_t(J), jparent))) return st;
+    if ((st = fetch(d.joint_child, size_t(J), jchild))) return st;
+    if ((st = fetch(d.shape_contact_pairs, size_t(P) * 2, pairs))) return st;
+    if ((st = fetch(d.articulation_start, size_t(d.articulation_count) + 1, art_start))) return st;
+    if ((st = fetch(d.joint_articulation, size_t(J), jart))) return st;
+
+    // ---- env partition ----------------------------------------------------------------------
+    const bool implicit_single = (W == 1) && (bws[0] == B) && (jws[0] == J) && (sws[0] == S);
+    int E;
+    h.global_shapes.clear();
+    if (implicit_single) {  // model built without begin_world(): everything lives in world -1 (builder.py:11276)
+        E = 1;
+        h.env_body_start = {0, B};
+        h.env_joint_start = {0, J};
+        h.env_shape_start = {0, S};
+    } else {
+        if (bws[0] != 0 || bws[W] != B || jws[0] != 0 || jws[W] != J) {
+            set_error("bodies/joints in the global world (-1) of a multi-world model are not supported by the fused kernels");
+            return NB2_ERR_UNSUPPORTED;
+        }
+        E = W;
+        h.env_body_start.assign(bws.begin(), bws.begin() + W + 1);
+        h.env_joint_start.assign(jws.begin(), jws.begin() + W + 1);
+        h.env_shape_start.assign(sws.begin(), sws.begin() + W + 1);
+        for (int s = 0; s < sws[0]; ++s) h.global_shapes.push_back(s);
+        for (int s = sws[W]; s < S; ++s) h.global_shapes.push_back(s);
+        for (int s : h.global_shapes)
+            if (shape_body[s] != -1) {
+                set_error("global (world -1) shapes must be static (body == -1)");
+                return NB2_ERR_UNSUPPORTED;
+            }
+    }
+    // articulations per env (articulations are world-contiguous like joints)
+    h.env_art_start.assign(size_t(E) + 1, 0);
+    {
+        int a = 0;
+        for (int e = 0; e < E; ++e) {
+            h.env_art_start[e] = a;
+            while (a < d.articulation_count && art_start[a] < h.env_joint_start[e + 1]) ++a;
+        }
+        h.env_art_start[E] = d.articulation_count;
+    }
+    auto env_of_shape = [&](int s) -> int {
+        if (implicit_single) return 0;
+        return shape_world[s];
+    };
+    // ---- pairs: group by env, order shapes by type, sort by the deterministic contact key ----
+    struct PairRec { int env; int64_t key; int sa, sb; };
+    std::vector<PairRec> recs;
+    recs.reserve(P);
+    for (int t = 0; t < P; ++t) {
+        int s1 = pairs[2 * t], s2 = pairs[2 * t + 1];
+        if (s1 < 0 || s2 < 0 || s1 >= S || s2 >= S || s1 == s2) continue;
+        int w1 = env_of_shape(s1), w2 = env_of_shape(s2);
+        int env = w1 >= 0 ? w1 : w2;
+        if (w1 >= 0 && w2 >= 0 && w1 != w2) continue;  // cross-world pairs never collide
+        if (env < 0) continue;                           // static-vs-static global pair: no dynamic body involved
+        int sa = s1, sb = s2;
+        if (shape_type[sa] > shape_type[sb]) std::swap(sa, sb);  // narrow_phase.py:525-528
+        int64_t key = ((int64_t(sa) & 0xFFFFF) << 43) | ((int64_t(sb) & 0xFFFFF) << 23);
+        recs.push_back({env, key, sa, sb});
+    }
+    std::stable_sort(recs.begin(), recs.end(), [](const PairRec& a, const PairRec& b) {
+        return a.env != b.env ? a.env < b.env : a.key < b.key;
+    });
+    h.env_pair_start.assign(size_t(E) + 1, 0);
+    h.pairs.clear();
+    h.pairs.reserve(recs.size());
+    {
+        size_t i = 0;
+        for (int e = 0; e < E; ++e) {
+            h.env_pair_start[e] = int(h.pairs.size());
+            const int ss = h.env_shape_start[e], se = h.env_shape_start[e + 1];
+            const int nloc = se - ss;
+            auto slot_of = [&](int s) -> int {
+                if (s >= ss && s < se) return s - ss;
+                for (size_t g = 0; g < h.global_shapes.size(); ++g)
+                    if (h.global_shapes[g] == s) return nloc + int(g);
+                return -1;
+            };
+            for (; i < recs.size() && recs[i].env == e; ++i) {
+                int a = slot_of(recs[i].sa), b = slot_of(recs[i].sb);
+                if (a < 0 || b < 0) {
+                    set_error("contact pair references a shape outside its world");
+                    return NB2_ERR_INVALID_ARGUMENT;
+                }
+                h.pairs.push_back(make_int2(a, b));
+            }
+        }
+        h.env_pair_start[E] = int(h.pairs.size());
+    }
+    // ---- contact-block slot ranges: 5 slots per pair (<= 4 analytic, <= 5 manifold contacts) ----
+    h.env_slot_start.assign(size_t(E) + 1, 0);
+    for (int e = 0; e < E; ++e)
+        h.env_slot_start[e + 1] = h.env_slot_start[e] + 5 * (h.env_pair_start[e + 1] - h.env_pair_start[e]);
+    // ---- per-body joint adjacency in joint order (parent entry before child entry of the same joint) ----
+    h.body_joint_start.assign(size_t(B) + 1, 0);
+    for (int j = 0; j < J; ++j) {
+        if (jparent[j] >= 0) h.body_joint_start[jparent[j] + 1]++;
+        if (jchild[j] >= 0) h.body_joint_start[jchild[j] + 1]++;
+    }
+    for (int b = 0; b < B; ++b) h.body_joint_start[b + 1] += h.body_joint_start[b];
+    h.body_joint_entry.assign(size_t(h.body_joint_start[B]), 0);
+    {
+        std::vector<int> fill(h.body_joint_start.begin(), h.body_joint_start.end() - 1);
+        int e = 0;
+        for (int j = 0; j < J; ++j) {
+            while (e + 1 < E && j >= h.env_joint_start[e + 1]) ++e;
+            int jl = j - h.env_joint_start[e];
+            if (jparent[j] >= 0) h.body_joint_entry[fill[jparent[j]]++] = (jl << 1) | 0;
+            if (jchild[j] >= 0) h.body_joint_entry[fill[jchild[j]]++] = (jl << 1) | 1;
+            int bs = h.env_body_start[e], be = h.env_body_start[e + 1];
+            if ((jparent[j] >= 0 && (jparent[j] < bs || jparent[j] >= be)) || jchild[j] < bs || jchild[j] >= be) {
+                set_error("joint connects bodies of different worlds");
+                return NB2_ERR_INVALID_ARGUMENT;
+            }
+        }
+    }
+    DevModel& dv = m->dev;
+    dv.d = d;
+    dv.env_count = E;
+    dv.global_shape_count = int(h.global_shapes.size());
+    dv.max_env_bodies = dv.max_env_joints = dv.max_env_slots_shapes = dv.max_env_pairs = dv.max_env_contact_slots = 0;
+    for (int e = 0; e < E; ++e) {
+        dv.max_env_bodies = std::max(dv.max_env_bodies, h.env_body_start[e + 1] - h.env_body_start[e]);
+        dv.max_env_joints = std::max(dv.max_env_joints, h.env_joint_start[e + 1] - h.env_joint_start[e]);
+        dv.max_env_slots_shapes =
+            std::max(dv.max_env_slots_shapes, h.env_shape_start[e + 1] - h.env_shape_start[e] + dv.global_shape_count);
+        dv.max_env_pairs = std::max(dv.max_env_pairs, h.env_pair_start[e + 1] - h.env_pair_start[e]);
+        dv.max_env_contact_slots = std::max(dv.max_env_contact_slots, h.env_slot_start[e + 1] - h.env_slot_start[e]);
+    }
+    dv.slot_total = h.env_slot_start[E];
+    m->lanes_per_env =
+        std::min(32, std::max(8, pow2_at_least(std::max({dv.max_env_bodies, dv.max_env_joints, std::min(dv.max_env_pairs, 32)}))));
+    return NB2_OK;
+}
+
+static void free_allocations(nb2_model* m) {
+    for (void* p : m->allocations) cudaFree(p);
+    m->allocations.clear();
+}
+
+static nb2_status upload_tables(nb2_model* m) {
+    HostTables& h = m->host;
+    DevModel& dv = m->dev;
+    nb2_status st;
+    if ((st = upload(m, h.env_body_start, &dv.env_body_start))) return st;
+    if ((st = upload(m, h.env_joint_start, &dv.env_joint_start))) return st;
+    if ((st = upload(m, h.env_shape_start, &dv.env_shape_start))) return st;
+    if ((st = upload(m, h.env_pair_start, &dv.env_pair_start))) return st;
+    if ((st = upload(m, h.env_slot_start, &dv.env_slot_start))) return st;
+    if ((st = upload(m, h.env_art_start, &dv.env_art_start))) return st;
+    if ((st = upload(m, h.global_shapes, &dv.global_shapes))) return st;
+    if ((st = upload(m, h.pairs, &dv.pairs))) return st;
+    if ((st = upload(m, h.body_joint_start, &dv.body_joint_start))) return st;
+    if ((st = upload(m, h.body_joint_entry, &dv.body_joint_entry))) return st;
+    void* p = nullptr;
+    size_t cb_bytes = std::max<size_t>(size_t(dv.slot_total) * CF_COUNT, 1) * sizeof(float);
+    NB2_CUDA_CHECK(cudaMalloc(&p, cb_bytes));
+    NB2_CUDA_CHECK(cudaMemset(p, 0, cb_bytes));
+    m->allocations.push_back(p);
+    dv.cb = static_cast<float*>(p);
+    NB2_CUDA_CHECK(cudaMalloc(&p, (size_t(dv.env_count) + 1) * sizeof(int)));
+    NB2_CUDA_CHECK(cudaMemset(p, 0, (size_t(dv.env_count) + 1) * sizeof(int)));
+    m->allocations.push_back(p);
+    dv.env_contact_count = static_cast<int*>(p);
+    NB2_CUDA_CHECK(cudaMalloc(&p, (size_t(dv.env_count) + 1) * sizeof(int)));
+    NB2_CUDA_CHECK(cudaMemset(p, 0, (size_t(dv.env_count) + 1) * sizeof(int)));
+    m->allocations.push_back(p);
+    dv.env_contact_offset = static_cast<int*>(p);
+    return NB2_OK;
+}
+
+}  // namespace nb2
+
+using namespace nb2;
+
+extern "C" {
+
+nb2_status nb2_model_create(const nb2_model_desc* desc, int32_t device, nb2_model** out) {
+    if (!desc || !out) {
+        set_error("nb2_model_create: NULL argument");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    *out = nullptr;
+    NB2_CUDA_CHECK(cudaSetDevice(device));
+    nb2_model* m = new nb2_model();
+    m->device = device;
+    nb2_status st = build_tables(m, *desc);
+    if (st == NB2_OK) st = upload_tables(m);
+    if (st != NB2_OK) {
+        free_allocations(m);
+        delete m;
+        return st;
+    }
+    *out = m;
+    return NB2_OK;
+}
+
+void nb2_model_destroy(nb2_model* model) {
+    if (!model) return;
+    cudaSetDevice(model->device);
+    free_allocations(model);
+    delete model;
+}
+
+nb2_status nb2_model_notify_changed(nb2_model* model, const nb2_model_desc* desc, int32_t flags) {
+    (void)flags;
+    if (!model || !desc) {
+        set_error("nb2_model_notify_changed: NULL argument");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    // The kernels read the Model arrays live; only refresh the borrowed pointers (topology changes need a new model).
+    if (desc->body_count != model->dev.d.body_count || desc->joint_count != model->dev.d.joint_count ||
+        desc->shape_count != model->dev.d.shape_count || desc->shape_pair_count != model->dev.d.shape_pair_count) {
+        set_error("nb2_model_notify_changed: topology changed; create a new nb2_model");
+        return NB2_ERR_UNSUPPORTED;
+    }
+    model->dev.d = *desc;
+    return NB2_OK;
+}
+
+int32_t nb2_model_rigid_contact_max(const nb2_model* model) { return model ? model->dev.slot_total : 0; }
+
+nb2_status nb2_collide(nb2_model* model, const float* body_q, const nb2_contacts_view* contacts, void* cuda_stream) {
+    if (!model || (!body_q && model->dev.d.body_count > 0)) {
+        set_error("nb2_collide: NULL argument");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    return launch_collide(model, body_q, contacts, static_cast<cudaStream_t>(cuda_stream));
+}
+
+nb2_status nb2_xpbd_step(nb2_model* model, const nb2_xpbd_params* params, const nb2_state_view* state_in,
+                         const nb2_state_view* state_out, const nb2_control_view* control, int32_t use_contacts, float dt,
+                         void* cuda_stream) {
+    if (!model || !params || !state_in || !state_out || !control) {
+        set_error("nb2_xpbd_step: NULL argument");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    if (params->iterations < 0 || !(dt > 0.0f)) {
+        set_error("nb2_xpbd_step: iterations must be >= 0 and dt > 0");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    if (params->enable_restitution) {
+        set_error("nb2_xpbd_step: enable_restitution is not implemented yet");
+        return NB2_ERR_UNSUPPORTED;
+    }
+    return launch_xpbd_step(model, *params, *state_in, *state_out, *control, use_contacts, dt,
+                            static_cast<cudaStream_t>(cuda_stream));
+}
+
+nb2_status nb2_integrate_bodies(nb2_model* model, const nb2_state_view* state_in, const nb2_state_view* state_out,
+                                float angular_damping, float dt, void* cuda_stream) {
+    if (!model || !state_in || !state_out) {
+        set_error("nb2_integrate_bodies: NULL argument");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    return launch_integrate_bodies(model, *state_in, *state_out, angular_damping, dt, static_cast<cudaStream_t>(cuda_stream));
+}
+
+nb2_status nb2_featherstone_step(nb2_model* model, const nb2_featherstone_params* params, const nb2_state_view* state_in,
+                                 const nb2_state_view* state_out, const nb2_control_view* control, int32_t use_contacts,
+                                 float dt, void* cuda_stream) {
+    if (!model || !params || !state_in || !state_out || !control) {
+        set_error("nb2_featherstone_step: NULL argument");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    return launch_featherstone_step(model, *params, *state_in, *state_out, *control, use_contacts, dt,
+                                    static_cast<cudaStream_t>(cuda_stream));
+}
+
+nb2_status nb2_eval_fk(nb2_model* model, const float* joint_q, const float* joint_qd, float* body_q, float* body_qd,
+                       void* cuda_stream) {
+    if (!model || !joint_q || !joint_qd || !body_q || !body_qd) {
+        set_error("nb2_eval_fk: NULL argument");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    return launch_eval_fk(model, joint_q, joint_qd, body_q, body_qd, static_cast<cudaStream_t>(cuda_stream));
+}
+
+const char* nb2_last_error(void) { return g_last_error.c_str(); }
+int64_t nb2_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+const char* nb2_version(void) { return "newton_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

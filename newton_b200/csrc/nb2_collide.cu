@@ -1,0 +1,589 @@
+// nb2_collide.cu - fused per-environment collision pipeline for sm_100a.
+//
+// One sub-warp group of L lanes owns one environment (a CTA is a single warp holding 32/L environments, so every
+// synchronisation is a __syncwarp and ~14 independent CTAs per SM cover 4096 environments on 148 SMs in one wave):
+//
+//   phase 1  shape world transforms + AABBs          (reference sim/collide.py:283-472 compute_shape_aabbs)
+//   phase 2  explicit-pair AABB test                 (reference geometry/broad_phase_nxn.py:29-69)
+//            analytic narrow phase                   (reference geometry/narrow_phase.py:459-1014,
+//                                                     geometry/collision_primitive.py)
+//            GJK/MPR + manifold for convex pairs     (reference geometry/narrow_phase.py:1041-1216)   [nb2_gjk.cuh]
+//            contact write-out                       (reference sim/collide.py:166-254 write_contact)
+//
+// The candidate-pair queue, the global atomic slot counter and the GJK re-queue of the reference disappear: the
+// env's pair list is pre-sorted by the deterministic contact key, so a segmented prefix sum inside the group gives
+// every contact its slot in key order - the order `CollisionPipeline(deterministic=True)` produces by radix sort.
+// Contacts land in env-major SoA "contact blocks" that the solver kernels read directly; an optional export pass
+// (scan + scatter) compacts them into the reference `Contacts` arrays.
+#include "nb2_gjk.cuh"
+#include "nb2_internal.cuh"
+#include "nb2_math.cuh"
+
+namespace nb2 {
+
+enum { GEO_PLANE = 1, GEO_SPHERE = 3, GEO_CAPSULE = 4, GEO_ELLIPSOID = 5, GEO_CYLINDER = 6, GEO_BOX = 7, GEO_CONE = 9 };
+#define NB2_MAXVAL 1.0e10f
+
+// ---- analytic colliders --------------------------------------------------------------------------
+NB2_DEV void plane_sphere(V3 n, V3 pp, V3 sp, float r, float& dist, V3& pos) {
+    dist = dot(sp - pp, n) - r;
+    pos = sp - n * (r + 0.5f * dist);
+}
+NB2_DEV void sphere_sphere(V3 p1, float r1, V3 p2, float r2, float& dist, V3& pos, V3& n) {
+    V3 dir = p2 - p1;
+    float d = len(dir);
+    n = d == 0.0f ? V3(1.f, 0.f, 0.f) : dir / d;
+    dist = d - (r1 + r2);
+    pos = p1 + n * (r1 + 0.5f * dist);
+}
+NB2_DEV V3 closest_on_segment(V3 a, V3 b, V3 pt) {
+    V3 ab = b - a;
+    float t = dot(pt - a, ab) / (dot(ab, ab) + 1e-6f);
+    return a + clamp_w(t, 0.0f, 1.0f) * ab;
+}
+NB2_DEV void plane_box(V3 n, V3 pp, V3 bp, const M33& R, V3 half, float margin, float dist[4], V3 pos[4]) {
+    float center_dist = dot(bp - pp, n);
+    int ncontact = 0, worst = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        V3 c((i & 1) ? half.x : -half.x, (i & 2) ? half.y : -half.y, (i & 4) ? half.z : -half.z);
+        c = mv(R, c);
+        float cdist = center_dist + dot(n, c);
+        if (cdist > margin) continue;
+        V3 cpos = c + bp - 0.5f * n * cdist;
+        if (ncontact < 4) {
+            dist[ncontact] = cdist;
+            pos[ncontact] = cpos;
+            if (ncontact == 0 || cdist > dist[worst]) worst = ncontact;
+            ncontact += 1;
+        } else if (cdist < dist[worst]) {
+            dist[worst] = cdist;
+            pos[worst] = cpos;
+            worst = 0;
+            if (dist[1] > dist[worst]) worst = 1;
+            if (dist[2] > dist[worst]) worst = 2;
+            if (dist[3] > dist[worst]) worst = 3;
+        }
+    }
+}
+NB2_DEV void plane_cylinder(V3 n, V3 pp, V3 cp, V3 axis, float radius, float hh, float dist[4], V3 pos[4]) {
+    const float kFlatCos = 0.92387953251128673848f;  // cos 22.5 deg
+    float dna = dot(n, axis);
+    if (dna > 0.0f) {
+        axis = -axis;
+        dna = -dna;
+    }
+    V3 cap = cp + axis * hh;
+    V3 perp_align = -n + axis * dna;
+    float pl2 = dot(perp_align, perp_align);
+    bool has_align = pl2 > 1e-10f;
+    if (has_align) perp_align = perp_align * (1.0f / sqrtf(pl2));
+    bool flat = (-dna) >= kFlatCos;
+    V3 perp_fixed;
+    if (flat || !has_align) {
+        V3 ref(1.f, 0.f, 0.f);
+        if (fabsf(dot(axis, ref)) > 0.9f) ref = V3(0.f, 1.f, 0.f);
+        perp_fixed = unit(ref - axis * dot(axis, ref));
+    }
+    V3 deepest_perp = has_align ? perp_align : perp_fixed;
+    V3 dpt = cap + deepest_perp * radius;
+    float dd = dot(dpt - pp, n);
+    V3 dpos = dpt - n * (dd * 0.5f);
+    dist[0] = dd;
+    pos[0] = dpos;
+    int nc = 1;
+    float mt = 0.01f * fmax_w(radius, hh);
+    float mt2 = mt * mt;
+    if (flat) {
+        V3 u = perp_fixed * radius;
+        V3 v = cross(axis, perp_fixed) * radius;
+        const float c120 = -0.5f, s120 = 0.8660254f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            V3 pt = k == 0 ? cap + u : (k == 1 ? cap + c120 * u + s120 * v : cap + c120 * u - s120 * v);
+            float d = dot(pt - pp, n);
+            V3 p = pt - n * (d * 0.5f);
+            if (nc < 4 && len2(p - dpos) > mt2) {
+                dist[nc] = d;
+                pos[nc] = p;
+                nc += 1;
+            }
+        }
+    } else {
+        V3 perp_roll = has_align ? perp_align : perp_fixed;
+        V3 u = perp_roll * radius;
+        V3 v = cross(axis, perp_roll) * radius;
+        V3 pt = cp - axis * hh + u;
+        float d = dot(pt - pp, n);
+        V3 p = pt - n * (d * 0.5f);
+        if (nc < 4 && len2(p - dpos) > mt2) {
+            dist[nc] = d;
+            pos[nc] = p;
+            nc += 1;
+        }
+        V3 ptp = cap + v, ptn = cap - v;
+        float dp = dot(ptp - pp, n), dn = dot(ptn - pp, n);
+        bool use_p = dp <= dn;
+        pt = use_p ? ptp : ptn;
+        d = use_p ? dp : dn;
+        p = pt - n * (d * 0.5f);
+        if (nc < 4 && len2(p - dpos) > mt2) {
+            dist[nc] = d;
+            pos[nc] = p;
+            nc += 1;
+        }
+    }
+}
+NB2_DEV void capsule_capsule(V3 p1, V3 a1, float r1, float hl1, V3 p2, V3 a2, float r2, float hl2, float dist[4], V3 pos[4], V3& n) {
+    V3 ax1 = a1 * hl1, ax2 = a2 * hl2, dif = p1 - p2;
+    float ma = dot(ax1, ax1), mb = -dot(ax1, ax2), mc = dot(ax2, ax2), u = -dot(ax1, dif), v = dot(ax2, dif);
+    float det = ma * mc - mb * mb;
+    if (fabsf(det) >= 1e-15f) {
+        float inv_det = 1.0f / det;
+        float x1 = (mc * u - mb * v) * inv_det, x2 = (ma * v - mb * u) * inv_det;
+        if (x1 > 1.0f) { x1 = 1.0f; x2 = (v - mb) / mc; }
+        else if (x1 < -1.0f) { x1 = -1.0f; x2 = (v + mb) / mc; }
+        if (x2 > 1.0f) { x2 = 1.0f; x1 = clamp_w((u - mb) / ma, -1.0f, 1.0f); }
+        else if (x2 < -1.0f) { x2 = -1.0f; x1 = clamp_w((u + mb) / ma, -1.0f, 1.0f); }
+        sphere_sphere(p1 + ax1 * x1, r1, p2 + ax2 * x2, r2, dist[0], pos[0], n);
+    } else {
+        float x2 = clamp_w((v - mb) / mc, -1.0f, 1.0f);
+        sphere_sphere(p1 + ax1, r1, p2 + ax2 * x2, r2, dist[0], pos[0], n);
+        x2 = clamp_w((v + mb) / mc, -1.0f, 1.0f);
+        V3 n2;
+        sphere_sphere(p1 - ax1, r1, p2 + ax2 * x2, r2, dist[1], pos[1], n2);
+    }
+}
+NB2_DEV void sphere_cylinder(V3 sp, float sr, V3 cp, V3 axis, float cr, float chh, float& dist, V3& pos, V3& n) {
+    V3 vec = sp - cp;
+    float x = dot(vec, axis);
+    V3 a_proj = axis * x;
+    V3 p_proj = vec - a_proj;
+    float pp2 = dot(p_proj, p_proj);
+    bool side = fabsf(x) < chh, capc = pp2 < cr * cr;
+    if (side && capc) {
+        float dist_cap = chh - fabsf(x), dist_radius = cr - sqrtf(pp2);
+        if (dist_cap < dist_radius) side = false;
+        else capc = false;
+    }
+    if (side) {
+        sphere_sphere(sp, sr, cp + a_proj, cr, dist, pos, n);
+    } else if (capc) {
+        V3 pc, pn;
+        if (x > 0.0f) { pc = cp + axis * chh; pn = axis; }
+        else { pc = cp - axis * chh; pn = -axis; }
+        plane_sphere(pn, pc, sp, sr, dist, pos);
+        n = -pn;
+    } else {
+        float s = sqrtf(pp2);
+        float inv_len = 1.0f / (s != 0.0f ? s : 1e-15f);
+        p_proj = p_proj * (cr * inv_len);
+        V3 cap_offset = axis * ((x < 0.0f ? -1.0f : 1.0f) * chh);
+        sphere_sphere(sp, sr, cp + cap_offset + p_proj, 0.0f, dist, pos, n);
+    }
+}
+NB2_DEV void sphere_box(V3 sp, float sr, V3 bp, const M33& R, V3 half, float& dist, V3& position, V3& n) {
+    V3 center = mtv(R, sp - bp);
+    V3 clamped = vmax(-half, vmin(half, center));
+    V3 diff = clamped - center;
+    float d = len(diff);
+    V3 dir = d == 0.0f ? diff : diff / d;
+    V3 pos;
+    if (d <= 1e-6f) {
+        float closest = 2.0f * (half.x + half.y + half.z);
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            float fd = fabsf(((i % 2) ? 1.0f : -1.0f) * half.get(i / 2) - center.get(i / 2));
+            if (closest > fd) { closest = fd; k = i; }
+        }
+        V3 nearest;
+        nearest.set(k / 2, (k % 2) ? -1.0f : 1.0f);
+        pos = center + nearest * (sr - closest) / 2.0f;
+        n = mv(R, nearest);
+        dist = -closest - sr;
+    } else {
+        V3 deepest = center + dir * sr;
+        pos = 0.5f * (clamped + deepest);
+        n = mv(R, dir);
+        dist = d - sr;
+    }
+    position = bp + mv(R, pos);
+}
+
+// World AABB of one shape, expanded by margin + gap (compute_shape_aabbs).
+NB2_DEV void shape_aabb(int type, V3 scale, const Xf& X, float gap_eff, float coll_radius, V3& lo, V3& hi) {
+    V3 pos = X.p;
+    V3 mvv(gap_eff, gap_eff, gap_eff);
+    V3 he;
+    if (type == GEO_PLANE && scale.x == 0.0f && scale.y == 0.0f) {
+        V3 normal = qrot(X.q, V3(0.f, 0.f, 1.f));
+        const float EXT = 1.0e6f;
+        V3 e(EXT, EXT, EXT);
+        lo = pos - e - mvv;
+        hi = pos + e + mvv;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            float ni = normal.get(i);
+            if (fabsf(ni) > 0.5f) {
+                float lateral = fabsf(normal.get((i + 1) % 3)) + fabsf(normal.get((i + 2) % 3));
+                float rise = lateral * EXT / fabsf(ni);
+                if (ni > 0.0f) hi.set(i, fmin_w(hi.get(i), pos.get(i) + rise + gap_eff));
+                else lo.set(i, fmax_w(lo.get(i), pos.get(i) - rise - gap_eff));
+            }
+        }
+        return;
+    } else if (type == GEO_SPHERE) {
+        he = V3(scale.x, scale.x, scale.x);
+    } else if (type == GEO_BOX) {
+        V3 r0 = qrot(X.q, V3(1.f, 0.f, 0.f)), r1 = qrot(X.q, V3(0.f, 1.f, 0.f)), r2 = qrot(X.q, V3(0.f, 0.f, 1.f));
+        he = V3(fabsf(r0.x) * scale.x + fabsf(r1.x) * scale.y + fabsf(r2.x) * scale.z,
+                fabsf(r0.y) * scale.x + fabsf(r1.y) * scale.y + fabsf(r2.y) * scale.z,
+                fabsf(r0.z) * scale.x + fabsf(r1.z) * scale.y + fabsf(r2.z) * scale.z);
+    } else if (type == GEO_CAPSULE) {
+        V3 axis = qrot(X.q, V3(0.f, 0.f, 1.f));
+        he = V3(scale.x, scale.x, scale.x) + vabs(axis) * scale.y;
+    } else if (type == GEO_CYLINDER) {
+        float radius = scale.x, hh = scale.y, br = scale.z;
+        if (br >= hh && br > 0.0f) radius += (hh * hh) / (br + sqrtf(br * br - hh * hh));
+        V3 r0 = qrot(X.q, V3(1.f, 0.f, 0.f)), r1 = qrot(X.q, V3(0.f, 1.f, 0.f)), r2 = qrot(X.q, V3(0.f, 0.f, 1.f));
+        he = V3(radius * sqrtf(r0.x * r0.x + r1.x * r1.x) + hh * fabsf(r2.x), radius * sqrtf(r0.y * r0.y + r1.y * r1.y) + hh * fabsf(r2.y),
+                radius * sqrtf(r0.z * r0.z + r1.z * r1.z) + hh * fabsf(r2.z));
+    } else if (type == GEO_ELLIPSOID) {
+        M33 R = qmat(X.q);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            float a = R.at(i, 0) * scale.x, b = R.at(i, 1) * scale.y, c = R.at(i, 2) * scale.z;
+            he.set(i, sqrtf(a * a + b * b + c * c));
+        }
+    } else {
+        he = V3(coll_radius, coll_radius, coll_radius);
+    }
+    lo = pos - he - mvv;
+    hi = pos + he + mvv;
+}
+
+struct PairGeom {
+    int type;
+    V3 scale;
+    float margin, gap, radius;
+    Xf X;
+};
+
+// Shared-memory record of one shape slot: world transform + expanded AABB.
+struct __align__(4) SlotRec {
+    float x[7];
+    float lo[3];
+    float hi[3];
+};
+
+template <int L>
+__global__ void __launch_bounds__(32) collide_kernel(DevModel M, const float* __restrict__ body_q) {
+    constexpr int G = 32 / L;  // environments per warp
+    extern __shared__ unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int grp = lane / L;
+    const int l = lane % L;
+    const unsigned gmask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << (grp * L));
+    const int env = blockIdx.x * G + grp;
+    const bool live = env < M.env_count;
+    SlotRec* slots = reinterpret_cast<SlotRec*>(smem_raw) + size_t(grp) * M.max_env_slots_shapes;
+    const nb2_model_desc& d = M.d;
+
+    int ss = 0, nloc = 0, nslots = 0, bs = 0, ps = 0, np = 0, slot0 = 0;
+    if (live) {
+        ss = M.env_shape_start[env];
+        nloc = M.env_shape_start[env + 1] - ss;
+        nslots = nloc + M.global_shape_count;
+        bs = M.env_body_start[env];
+        ps = M.env_pair_start[env];
+        np = M.env_pair_start[env + 1] - ps;
+        slot0 = M.env_slot_start[env];
+    }
+    // ---- phase 1: transforms + AABBs -----------------------------------------------------------
+    for (int s = l; s < nslots; s += L) {
+        int sid = s < nloc ? ss + s : M.global_shapes[s - nloc];
+        int body = d.shape_body[sid];
+        Xf X = ldx(d.shape_transform + 7 * sid);
+        if (body != -1) X = xmul(ldx(body_q + 7 * body), X);
+        float margin = d.shape_margin[sid];
+        V3 lo, hi;
+        shape_aabb(d.shape_type[sid], ld3(d.shape_scale + 3 * sid), X, margin + d.shape_gap[sid], d.shape_collision_radius[sid], lo, hi);
+        stx(slots[s].x, X);
+        st3(slots[s].lo, lo);
+        st3(slots[s].hi, hi);
+    }
+    __syncwarp();
+    // ---- phase 2: pairs -> contacts -------------------------------------------------------------
+    int n_total = 0;
+    const int rounds = (np + L - 1) / L;
+    int max_rounds = rounds;
+#pragma unroll
+    for (int o = 16; o >= L; o >>= 1) max_rounds = max(max_rounds, __shfl_xor_sync(0xffffffffu, max_rounds, o));
+    for (int r = 0; r < max_rounds; ++r) {
+        const int p = r * L + l;
+        unsigned vmask = 0;  // bit i set -> contact candidate i of this pair is emitted
+        float cdist[5];
+        V3 cpos[5], cnorm[5];
+        int sa = 0, sb = 0;
+        float reff_a = 0.f, reff_b = 0.f, marg_a = 0.f, marg_b = 0.f;
+        if (live && p < np) {
+            int2 pr = M.pairs[ps + p];
+            V3 alo = ld3(slots[pr.x].lo), ahi = ld3(slots[pr.x].hi), blo = ld3(slots[pr.y].lo), bhi = ld3(slots[pr.y].hi);
+            bool overlap = alo.x <= bhi.x && ahi.x >= blo.x && alo.y <= bhi.y && ahi.y >= blo.y && alo.z <= bhi.z && ahi.z >= blo.z;
+            if (overlap) {
+                sa = pr.x < nloc ? ss + pr.x : M.global_shapes[pr.x - nloc];
+                sb = pr.y < nloc ? ss + pr.y : M.global_shapes[pr.y - nloc];
+                const int ta = d.shape_type[sa], tb = d.shape_type[sb];
+                V3 sca = ld3(d.shape_scale + 3 * sa), scb = ld3(d.shape_scale + 3 * sb);
+                Xf Xa = ldx(slots[pr.x].x), Xb = ldx(slots[pr.y].x);
+                marg_a = d.shape_margin[sa];
+                marg_b = d.shape_margin[sb];
+                const float gap_sum = d.shape_gap[sa] + d.shape_gap[sb];
+                const bool early_gjk = ta >= GEO_ELLIPSOID || tb == GEO_CONE || (ta == GEO_CAPSULE && tb > GEO_CAPSULE);
+                bool analytic = false;
+                float dist[4] = {NB2_MAXVAL, NB2_MAXVAL, NB2_MAXVAL, NB2_MAXVAL};
+                V3 pos[4], normal;
+                if (!early_gjk) {
+                    if (ta == GEO_SPHERE || ta == GEO_CAPSULE) reff_a = sca.x;
+                    if (tb == GEO_SPHERE || tb == GEO_CAPSULE) reff_b = scb.x;
+                    analytic = true;
+                    bool use_pc = ta == GEO_PLANE && tb == GEO_CYLINDER;
+                    if (use_pc && scb.z > 0.0f) {
+                        V3 pn = qrot(Xa.q, V3(0.f, 0.f, 1.f)), ca = qrot(Xb.q, V3(0.f, 0.f, 1.f));
+                        use_pc = fabsf(dot(pn, ca)) * scb.z >= scb.y;
+                    }
+                    if (ta == GEO_PLANE && tb == GEO_SPHERE) {
+                        normal = qrot(Xa.q, V3(0.f, 0.f, 1.f));
+                        plane_sphere(normal, Xa.p, Xb.p, scb.x, dist[0], pos[0]);
+                    } else if (ta == GEO_PLANE && tb == GEO_ELLIPSOID) {
+                        V3 pn = qrot(Xa.q, V3(0.f, 0.f, 1.f));
+                        M33 R = qmat(Xb.q);
+                        V3 sup = -unit(cmul(mtv(R, pn), scb));
+                        V3 pt = Xb.p + mv(R, cmul(sup, scb));
+                        dist[0] = dot(pn, pt - Xa.p);
+                        pos[0] = pt - pn * dist[0] * 0.5f;
+                        normal = pn;
+                    } else if (ta == GEO_PLANE && tb == GEO_BOX) {
+                        normal = qrot(Xa.q, V3(0.f, 0.f, 1.f));
+                        plane_box(normal, Xa.p, Xb.p, qmat(Xb.q), scb, gap_sum + marg_a + marg_b, dist, pos);
+                    } else if (ta == GEO_SPHERE && tb == GEO_SPHERE) {
+                        sphere_sphere(Xa.p, sca.x, Xb.p, scb.x, dist[0], pos[0], normal);
+                    } else if (ta == GEO_PLANE && tb == GEO_CAPSULE) {
+                        normal = qrot(Xa.q, V3(0.f, 0.f, 1.f));
+                        V3 seg = qrot(Xb.q, V3(0.f, 0.f, 1.f)) * scb.y;
+                        plane_sphere(normal, Xa.p, Xb.p + seg, scb.x, dist[0], pos[0]);
+                        plane_sphere(normal, Xa.p, Xb.p - seg, scb.x, dist[1], pos[1]);
+                    } else if (use_pc) {
+                        normal = qrot(Xa.q, V3(0.f, 0.f, 1.f));
+                        plane_cylinder(normal, Xa.p, Xb.p, qrot(Xb.q, V3(0.f, 0.f, 1.f)), scb.x, scb.y, dist, pos);
+                    } else if (ta == GEO_SPHERE && tb == GEO_CAPSULE) {
+                        V3 seg = qrot(Xb.q, V3(0.f, 0.f, 1.f)) * scb.y;
+                        V3 pt = closest_on_segment(Xb.p - seg, Xb.p + seg, Xa.p);
+                        sphere_sphere(Xa.p, sca.x, pt, scb.x, dist[0], pos[0], normal);
+                    } else if (ta == GEO_CAPSULE && tb == GEO_CAPSULE) {
+                        capsule_capsule(Xa.p, qrot(Xa.q, V3(0.f, 0.f, 1.f)), sca.x, sca.y, Xb.p, qrot(Xb.q, V3(0.f, 0.f, 1.f)), scb.x,
+                                        scb.y, dist, pos, normal);
+                    } else if (ta == GEO_SPHERE && tb == GEO_CYLINDER && scb.z == 0.0f) {
+                        sphere_cylinder(Xa.p, sca.x, Xb.p, qrot(Xb.q, V3(0.f, 0.f, 1.f)), scb.x, scb.y, dist[0], pos[0], normal);
+                    } else if (ta == GEO_SPHERE && tb == GEO_BOX) {
+                        sphere_box(Xa.p, sca.x, Xb.p, qmat(Xb.q), scb, dist[0], pos[0], normal);
+                    } else {
+                        analytic = false;
+                    }
+                }
+                if (analytic) {
+                    const float tsn = reff_a + reff_b + marg_a + marg_b;
+                    const V3 nn = unit(normal);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        cdist[i] = dist[i];
+                        cpos[i] = pos[i];
+                        cnorm[i] = normal;
+                        if (dist[i] < NB2_MAXVAL) {
+                            // _contact_passes_gap_check_precomputed (contact_data.py:138-156)
+                            V3 a_w = pos[i] - nn * (0.5f * dist[i] + reff_a);
+                            V3 b_w = pos[i] + nn * (0.5f * dist[i] + reff_b);
+                            float dd = dot(b_w - a_w, nn) - tsn;
+                            if (dd <= gap_sum) vmask |= 1u << i;
+                        }
+                    }
+                } else {
+                    ConvexShape A{ta, sca, Xa, marg_a, d.shape_gap[sa], d.shape_collision_radius[sa]};
+                    ConvexShape Bc{tb, scb, Xb, marg_b, d.shape_gap[sb], d.shape_collision_radius[sb]};
+                    vmask = convex_pair_contacts(A, Bc, cdist, cpos, cnorm, reff_a, reff_b);
+                }
+            }
+        }
+        const int cnt = __popc(vmask);
+        // segmented exclusive scan of cnt over the L lanes of this group
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < L; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, o, L);
+            if (l >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, L - 1, L);
+        int slot = slot0 + n_total + (incl - cnt);
+        if (cnt > 0) {
+            const int body0 = d.shape_body[sa], body1 = d.shape_body[sb];
+            const Xf Xbw_a = body0 == -1 ? Xf() : xinv(ldx(body_q + 7 * body0));
+            const Xf Xbw_b = body1 == -1 ? Xf() : xinv(ldx(body_q + 7 * body1));
+            const float mu = (d.shape_material_mu[sa] + d.shape_material_mu[sb]) / 2.0f;
+            const float mut = (d.shape_material_mu_torsional[sa] + d.shape_material_mu_torsional[sb]) / 2.0f;
+            const float mur = (d.shape_material_mu_rolling[sa] + d.shape_material_mu_rolling[sb]) / 2.0f;
+            const float ke = 0.5f * (d.shape_material_ke[sa] + d.shape_material_ke[sb]);
+            const float kd = 0.5f * (d.shape_material_kd[sa] + d.shape_material_kd[sb]);
+            const float kf = 0.5f * (d.shape_material_kf[sa] + d.shape_material_kf[sb]);
+            const float ka = 0.5f * (d.shape_material_ka[sa] + d.shape_material_ka[sb]);
+            float* cb = M.cb;
+            const size_t T = size_t(M.slot_total);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                if (!(vmask & (1u << i))) continue;
+                // write_contact (collide.py:210-254): world contact -> body-frame points / offsets
+                V3 n = unit(cnorm[i]);
+                V3 a_w = cpos[i] - n * (0.5f * cdist[i] + reff_a);
+                V3 b_w = cpos[i] + n * (0.5f * cdist[i] + reff_b);
+                float om_a = reff_a + marg_a, om_b = reff_b + marg_b;
+                V3 p0 = xpoint(Xbw_a, a_w), p1 = xpoint(Xbw_b, b_w);
+                V3 o0 = xvec(Xbw_a, om_a * n), o1 = xvec(Xbw_b, -om_b * n);
+                cb[CF_BODY_A * T + slot] = __int_as_float(body0 >= 0 ? body0 - bs : -1);
+                cb[CF_BODY_B * T + slot] = __int_as_float(body1 >= 0 ? body1 - bs : -1);
+                cb[CF_SHAPE0 * T + slot] = __int_as_float(sa);
+                cb[CF_SHAPE1 * T + slot] = __int_as_float(sb);
+                cb[CF_P0X * T + slot] = p0.x; cb[CF_P0Y * T + slot] = p0.y; cb[CF_P0Z * T + slot] = p0.z;
+                cb[CF_P1X * T + slot] = p1.x; cb[CF_P1Y * T + slot] = p1.y; cb[CF_P1Z * T + slot] = p1.z;
+                cb[CF_O0X * T + slot] = o0.x; cb[CF_O0Y * T + slot] = o0.y; cb[CF_O0Z * T + slot] = o0.z;
+                cb[CF_O1X * T + slot] = o1.x; cb[CF_O1Y * T + slot] = o1.y; cb[CF_O1Z * T + slot] = o1.z;
+                cb[CF_NX * T + slot] = n.x; cb[CF_NY * T + slot] = n.y; cb[CF_NZ * T + slot] = n.z;
+                cb[CF_MARGIN0 * T + slot] = om_a;
+                cb[CF_MARGIN1 * T + slot] = om_b;
+                cb[CF_MU * T + slot] = mu;
+                cb[CF_MU_TORSIONAL * T + slot] = mut;
+                cb[CF_MU_ROLLING * T + slot] = mur;
+                cb[CF_KE * T + slot] = ke;
+                cb[CF_KD * T + slot] = kd;
+                cb[CF_KF * T + slot] = kf;
+                cb[CF_KA * T + slot] = ka;
+                slot += 1;
+            }
+        }
+        n_total += total;
+    }
+    if (live && l == 0) M.env_contact_count[env] = n_total;
+}
+
+// ---- export to the reference `Contacts` arrays ---------------------------------------------------
+// Single-CTA exclusive scan of the per-env counts (E <= a few 10^5), then one group per env scatters its block.
+__global__ void __launch_bounds__(1024) contact_scan_kernel(const int* __restrict__ counts, int E, int* __restrict__ offsets,
+                                                            int* __restrict__ rigid_contact_count) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < E; base += 1024) {
+        int i = base + threadIdx.x;
+        int v = i < E ? counts[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = warp_sums[threadIdx.x];
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (threadIdx.x >= o) wi += t;
+            }
+            warp_sums[threadIdx.x] = wi - w;
+        }
+        __syncthreads();
+        int excl = carry + warp_sums[threadIdx.x >> 5] + incl - v;
+        if (i < E) offsets[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        offsets[E] = carry;
+        if (rigid_contact_count) rigid_contact_count[0] = carry;
+    }
+}
+
+__global__ void __launch_bounds__(128) contact_export_kernel(DevModel M, nb2_contacts_view out) {
+    const int env = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (env >= M.env_count) return;
+    const int lane = threadIdx.x & 31;
+    const int n = M.env_contact_count[env];
+    const int src0 = M.env_slot_start[env];
+    const int dst0 = M.env_contact_offset[env];
+    const size_t T = size_t(M.slot_total);
+    const float* cb = M.cb;
+    for (int c = lane; c < n; c += 32) {
+        const int s = src0 + c, o = dst0 + c;
+        if (o >= out.rigid_contact_max) break;  // overflow: count keeps growing, writes dropped (collide.py:176-177)
+        out.shape0[o] = __float_as_int(cb[CF_SHAPE0 * T + s]);
+        out.shape1[o] = __float_as_int(cb[CF_SHAPE1 * T + s]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            out.point0[3 * o + k] = cb[(CF_P0X + k) * T + s];
+            out.point1[3 * o + k] = cb[(CF_P1X + k) * T + s];
+            out.offset0[3 * o + k] = cb[(CF_O0X + k) * T + s];
+            out.offset1[3 * o + k] = cb[(CF_O1X + k) * T + s];
+            out.normal[3 * o + k] = cb[(CF_NX + k) * T + s];
+        }
+        out.margin0[o] = cb[CF_MARGIN0 * T + s];
+        out.margin1[o] = cb[CF_MARGIN1 * T + s];
+        if (out.tids) out.tids[o] = 0;
+    }
+}
+
+template <int L>
+static nb2_status launch_collide_L(nb2_model* m, const float* body_q, cudaStream_t s) {
+    const DevModel& M = m->dev;
+    const int G = 32 / L;
+    const int blocks = (M.env_count + G - 1) / G;
+    const size_t smem = size_t(G) * M.max_env_slots_shapes * sizeof(SlotRec);
+    if (smem > 200 * 1024) {
+        set_error("collide: too many shapes per environment for the fused kernel");
+        return NB2_ERR_CAPACITY;
+    }
+    if (smem > 48 * 1024)
+        NB2_CUDA_CHECK(cudaFuncSetAttribute(collide_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    collide_kernel<L><<<blocks, 32, smem, s>>>(M, body_q);
+    count_launch();
+    NB2_CUDA_CHECK(cudaGetLastError());
+    return NB2_OK;
+}
+
+nb2_status launch_collide(nb2_model* m, const float* body_q, const nb2_contacts_view* contacts, cudaStream_t s) {
+    const DevModel& M = m->dev;
+    if (M.env_count == 0 || M.d.shape_count == 0) return NB2_OK;
+    nb2_status st;
+    switch (m->lanes_per_env) {
+        case 8: st = launch_collide_L<8>(m, body_q, s); break;
+        case 16: st = launch_collide_L<16>(m, body_q, s); break;
+        default: st = launch_collide_L<32>(m, body_q, s); break;
+    }
+    if (st != NB2_OK) return st;
+    if (contacts) {
+        if (!contacts->rigid_contact_count || !contacts->shape0 || !contacts->shape1 || !contacts->point0 || !contacts->point1 ||
+            !contacts->offset0 || !contacts->offset1 || !contacts->normal || !contacts->margin0 || !contacts->margin1) {
+            set_error("nb2_collide: contacts view has NULL arrays");
+            return NB2_ERR_INVALID_ARGUMENT;
+        }
+        contact_scan_kernel<<<1, 1024, 0, s>>>(M.env_contact_count, M.env_count, M.env_contact_offset, contacts->rigid_contact_count);
+        contact_export_kernel<<<(M.env_count + 3) / 4, 128, 0, s>>>(M, *contacts);
+        count_launch(2);
+        NB2_CUDA_CHECK(cudaGetLastError());
+    }
+    return NB2_OK;
+}
+
+}  // namespace nb2

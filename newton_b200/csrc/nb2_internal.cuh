@@ -1,0 +1,93 @@
+// nb2_internal.cuh - private definitions shared by the translation units of libnewton_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/newton_b200.h"
+
+namespace nb2 {
+
+// Number of float/int fields of one contact slot in the env-major contact blocks (DESIGN.md "contact hand-off").
+// Field f of slot s lives at cb[f * slot_total + s]: lanes read consecutive slots -> coalesced 128-byte lines.
+enum ContactField {
+    CF_BODY_A = 0,  // int: env-local body index or -1
+    CF_BODY_B,
+    CF_SHAPE0,  // int: model shape ids (for export)
+    CF_SHAPE1,
+    CF_P0X, CF_P0Y, CF_P0Z,     // point0 (body frame of A)
+    CF_P1X, CF_P1Y, CF_P1Z,     // point1 (body frame of B)
+    CF_O0X, CF_O0Y, CF_O0Z,     // offset0
+    CF_O1X, CF_O1Y, CF_O1Z,     // offset1
+    CF_NX, CF_NY, CF_NZ,        // normal A->B (world)
+    CF_MARGIN0, CF_MARGIN1,
+    CF_MU, CF_MU_TORSIONAL, CF_MU_ROLLING,  // pair-averaged friction coefficients
+    CF_KE, CF_KD, CF_KF, CF_KA,             // pair-averaged penalty parameters (Featherstone / semi-implicit contact)
+    CF_COUNT
+};
+
+// Everything a kernel needs, passed by value (all pointers are device pointers).
+struct DevModel {
+    nb2_model_desc d;           // the reference-layout Model arrays (borrowed)
+    int env_count;
+    const int* env_body_start;     // [E+1]
+    const int* env_joint_start;    // [E+1]
+    const int* env_shape_start;    // [E+1] env-local shapes
+    const int* env_pair_start;     // [E+1] into pairs[]
+    const int* env_slot_start;     // [E+1] contact-block slot ranges
+    const int* env_art_start;      // [E+1] articulations
+    const int* global_shapes;      // ids of world -1 shapes, appended to every env's slot table
+    int global_shape_count;
+    const int2* pairs;             // per env: (slot_a, slot_b), type-ordered (type_a <= type_b), sorted by contact key
+    const int* body_joint_start;   // [B+1] CSR of (joint_local << 1 | is_child) in joint order
+    const int* body_joint_entry;
+    float* cb;                     // contact blocks: CF_COUNT planes of slot_total words
+    int slot_total;
+    int* env_contact_count;        // [E]
+    int* env_contact_offset;       // [E+1] exclusive scan, written by the export path
+    int max_env_bodies, max_env_joints, max_env_slots_shapes, max_env_pairs, max_env_contact_slots;
+};
+
+struct HostTables {
+    std::vector<int> env_body_start, env_joint_start, env_shape_start, env_pair_start, env_slot_start, env_art_start;
+    std::vector<int> global_shapes;
+    std::vector<int2> pairs;
+    std::vector<int> body_joint_start, body_joint_entry;
+};
+
+}  // namespace nb2
+
+struct nb2_model {
+    int device = 0;
+    nb2::DevModel dev{};
+    nb2::HostTables host;
+    std::vector<void*> allocations;
+    int lanes_per_env = 32;  // sub-warp group width used by the fused kernels
+    int featherstone_step_count = 0;
+};
+
+namespace nb2 {
+void set_error(const std::string& msg);
+void count_launch(int n = 1);
+nb2_status launch_collide(nb2_model* m, const float* body_q, const nb2_contacts_view* contacts, cudaStream_t s);
+nb2_status launch_xpbd_step(nb2_model* m, const nb2_xpbd_params& p, const nb2_state_view& in, const nb2_state_view& out,
+                            const nb2_control_view& ctl, int use_contacts, float dt, cudaStream_t s);
+nb2_status launch_integrate_bodies(nb2_model* m, const nb2_state_view& in, const nb2_state_view& out, float angular_damping,
+                                   float dt, cudaStream_t s);
+nb2_status launch_featherstone_step(nb2_model* m, const nb2_featherstone_params& p, const nb2_state_view& in,
+                                    const nb2_state_view& out, const nb2_control_view& ctl, int use_contacts, float dt,
+                                    cudaStream_t s);
+nb2_status launch_eval_fk(nb2_model* m, const float* joint_q, const float* joint_qd, float* body_q, float* body_qd,
+                          cudaStream_t s);
+}  // namespace nb2
+
+#define NB2_CUDA_CHECK(expr)                                                                          \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            nb2::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                       \
+            return NB2_ERR_CUDA;                                                                      \
+        }                                                                                             \
+    } while (0)

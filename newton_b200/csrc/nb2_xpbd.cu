@@ -1,0 +1,729 @@
+// nb2_xpbd.cu - fused XPBD rigid-body substep for sm_100a (reference SolverXPBD.step, solver_xpbd.py:329-862).
+//
+// The reference runs `2 + iterations*6 + 1` kernel launches per substep, each re-reading body state from
+// HBM/L2 and summing per-body corrections with float atomics.  Here ONE launch does the whole substep for
+// every environment: a sub-warp group of L lanes owns one environment (a CTA is one warp = 32/L environments),
+// body state lives in shared memory for the entire Jacobi loop, and the atomics are replaced by ordered
+// per-body sums (contacts in contact order, joints in joint order, parent before child) - which is exactly the
+// order the reference's serial CPU device produces, so results are run-to-run deterministic.
+//
+//   apply_joint_forces            kernels.py:945-1075     joint lanes -> ordered per-body sum into body_f copy
+//   integrate_bodies              solver.py:112-170       body lanes
+//   per iteration:
+//     solve_body_contact_positions  kernels.py:2164-2399  contact lanes -> smem delta records
+//     apply_body_deltas (weighted)  kernels.py:864-933    body lanes, ordered sum over the env's contacts
+//     solve_body_joints             kernels.py:1513-2044  joint lanes -> smem delta records
+//     apply_body_deltas             kernels.py:864-933    body lanes, ordered sum over the body's joints (CSR)
+//   copy_kinematic_body_state      kernels.py:19-32       implicit: kinematic bodies are never modified
+#include "nb2_internal.cuh"
+#include "nb2_math.cuh"
+
+namespace nb2 {
+
+enum { JT_PRISMATIC = 0, JT_REVOLUTE = 1, JT_BALL = 2, JT_FIXED = 3, JT_FREE = 4, JT_DISTANCE = 5, JT_D6 = 6, JT_ROD = 7 };
+enum { BODY_KINEMATIC = 2 };
+
+// shared-memory body record (floats): odd stride -> consecutive bodies hit different banks
+enum { BR_Q = 0, BR_QD = 7, BR_COM = 13, BR_INVM = 16, BR_INVI = 17, BR_I = 26, BR_SIZE = 35 };
+enum { DR_SIZE = 13 };  // delta record: lin_a, ang_a, lin_b, ang_b, active
+
+struct BodyView {
+    Xf X;
+    V3 com;
+    float inv_m;
+    M33 inv_I;
+    V3 v, w;
+};
+
+NB2_DEV BodyView load_body(const float* rec) {
+    BodyView b;
+    b.X = ldx(rec + BR_Q);
+    b.v = ld3(rec + BR_QD);
+    b.w = ld3(rec + BR_QD + 3);
+    b.com = ld3(rec + BR_COM);
+    b.inv_m = rec[BR_INVM];
+    b.inv_I = ldm(rec + BR_INVI);
+    return b;
+}
+NB2_DEV BodyView static_body() {  // body index -1: the world
+    BodyView b;
+    b.inv_m = 0.f;
+    b.inv_I = m33_zero();
+    return b;
+}
+
+// shared denominators of compute_contact_constraint_delta / compute_positional_correction (kernels.py:2063-2075)
+NB2_DEV float generalized_inv_mass(const BodyView& a, const BodyView& b, V3 lin_a, V3 lin_b, V3 ang_a, V3 ang_b) {
+    float denom = 0.0f;
+    denom += len2(lin_a) * a.inv_m;
+    denom += len2(lin_b) * b.inv_m;
+    V3 ra = qrot_inv(a.X.q, ang_a);
+    V3 rb = qrot_inv(b.X.q, ang_b);
+    denom += dot(ra, mv(a.inv_I, ra));
+    denom += dot(rb, mv(b.inv_I, rb));
+    return denom;
+}
+NB2_DEV float contact_delta(float err, const BodyView& a, const BodyView& b, V3 lin_a, V3 lin_b, V3 ang_a, V3 ang_b, float relaxation,
+                            float dt) {
+    float denom = generalized_inv_mass(a, b, lin_a, lin_b, ang_a, ang_b);
+    float dl = -err;
+    if (denom > 0.0f) dl /= dt * denom;
+    return dl * relaxation;
+}
+NB2_DEV float positional_correction(float err, float derr, const BodyView& a, const BodyView& b, V3 lin_a, V3 lin_b, V3 ang_a, V3 ang_b,
+                                    float compliance, float damping, float dt) {
+    float denom = generalized_inv_mass(a, b, lin_a, lin_b, ang_a, ang_b);
+    float alpha = compliance, gamma = compliance * damping;
+    float dl = -(err + alpha * 0.0f + gamma * derr);
+    if (denom + alpha > 0.0f) dl /= (dt + gamma) * denom + alpha / dt;
+    return dl;
+}
+NB2_DEV float angular_correction(float err, float derr, const BodyView& a, const BodyView& b, V3 ang_a, V3 ang_b, float compliance,
+                                 float damping, float dt) {
+    float denom = 0.0f;
+    V3 ra = qrot_inv(a.X.q, ang_a);
+    V3 rb = qrot_inv(b.X.q, ang_b);
+    denom += dot(ra, mv(a.inv_I, ra));
+    denom += dot(rb, mv(b.inv_I, rb));
+    float alpha = compliance, gamma = compliance * damping;
+    float dl = -(err + alpha * 0.0f + gamma * derr);
+    if (denom + alpha > 0.0f) dl /= (dt + gamma) * denom + alpha / dt;
+    return dl;
+}
+
+struct AxisSetup {
+    V3 lim_lo, lim_up, target_pos, stiffness, target_vel, damping;
+};
+// "compute joint target, stiffness, damping" (kernels.py:1691-1751 linear, :1911-1973 angular)
+NB2_DEV AxisSetup gather_axes(const nb2_model_desc& d, const nb2_control_view& ctl, int axis_start, int target_start, int offset,
+                              int count) {
+    AxisSetup s;
+    V3 pos_t, pos_w, vel_t, vel_w;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (count > k) {
+            int ai = axis_start + offset + k, ti = target_start + offset + k;
+            V3 axis = ld3(d.joint_axis + 3 * ai);
+            V3 lo_t = axis * d.joint_limit_lower[ai], up_t = axis * d.joint_limit_upper[ai];
+            V3 lo = vmin(lo_t, up_t), up = vmax(lo_t, up_t);
+            if (k == 0) {
+                s.lim_lo = lo;
+                s.lim_up = up;
+            } else {
+                s.lim_lo = vmin(s.lim_lo, lo);
+                s.lim_up = vmax(s.lim_up, up);
+            }
+            float ke = d.joint_target_ke[ai], kd = d.joint_target_kd[ai];
+            if (ke > 0.0f) {
+                V3 wa = axis * ke;
+                pos_t += wa * ctl.joint_target_q[ti];
+                pos_w += vabs(wa);
+            }
+            if (kd > 0.0f) {
+                V3 wa = axis * kd;
+                vel_t += wa * ctl.joint_target_qd[ai];
+                vel_w += vabs(wa);
+            }
+        }
+    }
+    s.target_pos = pos_t;
+    s.stiffness = pos_w;
+    s.target_vel = vel_t;
+    s.damping = vel_w;
+    if (s.stiffness.x > 0.0f) s.target_pos.x /= s.stiffness.x;
+    if (s.stiffness.y > 0.0f) s.target_pos.y /= s.stiffness.y;
+    if (s.stiffness.z > 0.0f) s.target_pos.z /= s.stiffness.z;
+    if (s.damping.x > 0.0f) s.target_vel.x /= s.damping.x;
+    if (s.damping.y > 0.0f) s.target_vel.y /= s.damping.y;
+    if (s.damping.z > 0.0f) s.target_vel.z /= s.damping.z;
+    return s;
+}
+
+struct Deltas {
+    V3 lin_p, ang_p, lin_c, ang_c;
+};
+
+// solve_body_joints for one joint (kernels.py:1513-2044).  `bodies` = this env's shared-memory records.
+NB2_DEV bool solve_joint(const nb2_model_desc& d, const nb2_control_view& ctl, const nb2_xpbd_params& P, int j, int body0,
+                         const float* bodies, float dt, Deltas& out) {
+    const int type = d.joint_type[j];
+    if (!d.joint_enabled[j] || type == JT_FREE) return false;
+    const int id_c = d.joint_child[j] - body0;
+    const int id_p_raw = d.joint_parent[j];
+    const int id_p = id_p_raw >= 0 ? id_p_raw - body0 : -1;
+    const Xf X_pj = ldx(d.joint_X_p + 7 * j), X_cj = ldx(d.joint_X_c + 7 * j);
+    BodyView bp = static_body();
+    Xf X_wp = X_pj;
+    Xf pose_p = X_pj;
+    if (id_p >= 0) {
+        bp = load_body(bodies + id_p * BR_SIZE);
+        pose_p = bp.X;
+        X_wp = xmul(pose_p, X_wp);
+    } else {
+        bp.X = pose_p;  // tf_a of the correction helpers is pose_p = X_pj for world-attached joints
+    }
+    BodyView bc = load_body(bodies + id_c * BR_SIZE);
+    const Xf pose_c = bc.X;
+    const Xf X_wc = xmul(pose_c, X_cj);
+    if (bp.inv_m == 0.0f && bc.inv_m == 0.0f) return false;
+    V3 lin_dp, ang_dp, lin_dc, ang_dc;
+    const Xf rel_pose = xmul(xinv(X_wp), X_wc);
+    const V3 rel_p = rel_pose.p;
+    const V3 x_p = X_wp.p, x_c = X_wc.p;
+    const int axis_start = d.joint_qd_start[j];
+    const int target_start = d.joint_target_q_start[j];
+    const int lin_count = d.joint_dof_dim[2 * j], ang_count = d.joint_dof_dim[2 * j + 1];
+    const V3 wcom_p = xpoint(pose_p, bp.com);
+    const V3 wcom_c = xpoint(pose_c, bc.com);
+    const V3 vel_p = bp.v, omega_p = bp.w, vel_c = bc.v, omega_c = bc.w;
+
+    if (type == JT_DISTANCE) {
+        V3 r_p = x_p - wcom_p, r_c = x_c - wcom_c;
+        float lower = d.joint_limit_lower[axis_start], upper = d.joint_limit_upper[axis_start];
+        if (lower < 0.0f && upper < 0.0f) return false;
+        V3 ad = x_c - x_p;
+        float dist = len(ad);
+        float err = 0.0f;
+        if (lower >= 0.0f && dist < lower) err = dist - lower;
+        else if (upper >= 0.0f && dist > upper) err = dist - upper;
+        if (fabsf(err) > 1e-9f) {
+            V3 lc;
+            if (dist > 1e-9f) lc = ad / dist;
+            else {
+                V3 cd = wcom_c - wcom_p;
+                lc = len2(cd) > 1e-18f ? unit(cd) : xvec(X_wp, V3(1.f, 0.f, 0.f));
+            }
+            V3 lp = -lc, ap = -cross(r_p, lc), ac = cross(r_c, lc);
+            float derr = dot(lp, vel_p) + dot(lc, vel_c) + dot(ap, omega_p) + dot(ac, omega_c);
+            float compliance = P.joint_linear_compliance;
+            float ke = d.joint_target_ke[axis_start];
+            if (ke > 0.0f) compliance = 1.0f / ke;
+            float damping = d.joint_target_kd[axis_start];
+            float dl = positional_correction(err, derr, bp, bc, lp, lc, ap, ac, compliance, damping, dt);
+            lin_dp += lp * (dl * P.joint_linear_relaxation);
+            ang_dp += ap * (dl * P.joint_angular_relaxation);
+            lin_dc += lc * (dl * P.joint_linear_relaxation);
+            ang_dc += ac * (dl * P.joint_angular_relaxation);
+        }
+    } else {
+        const AxisSetup s = gather_axes(d, ctl, axis_start, target_start, 0, lin_count);
+        V3 proj = rel_p;
+#pragma unroll
+        for (int dim = 0; dim < 3; ++dim) {
+            float lo = s.lim_lo.get(dim), up = s.lim_up.get(dim), e = rel_p.get(dim);
+            if (e < lo) proj.set(dim, lo);
+            else if (e > up) proj.set(dim, up);
+            else if (s.stiffness.get(dim) > 0.0f) proj.set(dim, clamp_w(s.target_pos.get(dim), lo, up));
+        }
+        const M33 frame_p = qmat(X_wp.q);
+        const V3 r_p = xpoint(X_wp, proj) - wcom_p;
+        const V3 r_c = x_c - wcom_c;
+#pragma unroll
+        for (int dim = 0; dim < 3; ++dim) {
+            float e = rel_p.get(dim);
+            V3 lc(frame_p.at(0, dim), frame_p.at(1, dim), frame_p.at(2, dim));
+            V3 lp = -lc, ap = -cross(r_p, lc), ac = cross(r_c, lc);
+            float derr = dot(lp, vel_p) + dot(lc, vel_c) + dot(ap, omega_p) + dot(ac, omega_c);
+            float err = 0.0f, compliance = P.joint_linear_compliance, damping = 0.0f;
+            float derr_rel = derr - s.target_vel.get(dim);
+            float lo = s.lim_lo.get(dim), up = s.lim_up.get(dim);
+            if (e < lo) err = e - lo;
+            else if (e > up) err = e - up;
+            else {
+                float tp = clamp_w(s.target_pos.get(dim), lo, up);
+                float ks = s.stiffness.get(dim), kdm = s.damping.get(dim);
+                if (ks > 0.0f) {
+                    err = e - tp;
+                    compliance = 1.0f / ks;
+                    damping = kdm;
+                } else if (kdm > 0.0f) {
+                    compliance = 1.0f / kdm;
+                    damping = kdm;
+                }
+            }
+            if (fabsf(err) > 1e-9f || fabsf(derr_rel) > 1e-9f) {
+                float dl = positional_correction(err, derr_rel, bp, bc, lp, lc, ap, ac, compliance, damping, dt);
+                lin_dp += lp * (dl * P.joint_linear_relaxation);
+                ang_dp += ap * (dl * P.joint_angular_relaxation);
+                lin_dc += lc * (dl * P.joint_linear_relaxation);
+                ang_dc += ac * (dl * P.joint_angular_relaxation);
+            }
+        }
+    }
+
+    if (type == JT_FIXED || type == JT_PRISMATIC || type == JT_REVOLUTE || type == JT_D6) {
+        const Q4 q_p = X_wp.q;
+        Q4 q_c = X_wc.q;
+        if (qdot(q_p, q_c) < 0.0f) q_c = qscale(q_c, -1.0f);
+        const Q4 rq = qmul(qconj(q_p), q_c);
+        const Q4 qtwist = qunit(Q4(rq.x, 0.0f, 0.0f, rq.w));
+        const Q4 qswing = qmul(rq, qconj(qtwist));
+        const float sn = sqrtf(rq.x * rq.x + rq.w * rq.w);
+        const float invs = 1.0f / sn;
+        const float invscube = invs * invs * invs;
+        float err_0 = 2.0f * asinf(clamp_w(qtwist.x, -1.0f, 1.0f));
+        float err_1 = qswing.y, err_2 = qswing.z;
+        Q4 g0(invs - rq.x * rq.x * invscube, 0.0f, 0.0f, -(rq.w * rq.x) * invscube);
+        Q4 g1(-rq.w * (rq.w * rq.z + rq.x * rq.y) * invscube, rq.w * invs, -rq.x * invs, rq.x * (rq.w * rq.z + rq.x * rq.y) * invscube);
+        Q4 g2(rq.w * (rq.w * rq.y - rq.x * rq.z) * invscube, rq.x * invs, rq.w * invs, rq.x * (rq.z * rq.x - rq.w * rq.y) * invscube);
+        g0 = qscale(g0, 2.0f / fabsf(qtwist.w));
+        const float swing_sq = qswing.w * qswing.w;
+        if (swing_sq + 1.0e-4f < 1.0f) {
+            float dd = sqrtf(1.0f - qswing.w * qswing.w);
+            float theta = 2.0f * acosf(clamp_w(qswing.w, -1.0f, 1.0f));
+            float scale = theta / dd;
+            err_1 *= scale;
+            err_2 *= scale;
+            g1 = qscale(g1, scale);
+            g2 = qscale(g2, scale);
+        }
+        const AxisSetup s = gather_axes(d, ctl, axis_start, target_start, lin_count, ang_count);
+        const Q4 qc_inv = qconj(q_c);
+#pragma unroll
+        for (int dim = 0; dim < 3; ++dim) {
+            float e = dim == 0 ? err_0 : (dim == 1 ? err_1 : err_2);
+            Q4 grad = dim == 0 ? g0 : (dim == 1 ? g1 : g2);
+            Q4 quat_c = qmul(qmul(qscale(q_p, 0.5f), grad), qc_inv);
+            V3 ac(quat_c.x, quat_c.y, quat_c.z);
+            V3 ap = -ac;
+            float derr = dot(ap, omega_p) + dot(ac, omega_c);
+            float err = 0.0f, compliance = P.joint_angular_compliance, damping = 0.0f;
+            float derr_rel = derr - s.target_vel.get(dim) * len(ac);
+            float lo = s.lim_lo.get(dim), up = s.lim_up.get(dim);
+            if (e < lo) err = e - lo;
+            else if (e > up) err = e - up;
+            else {
+                float tp = clamp_w(s.target_pos.get(dim), lo, up);
+                float ks = s.stiffness.get(dim), kdm = s.damping.get(dim);
+                if (ks > 0.0f) {
+                    err = e - tp;
+                    compliance = 1.0f / ks;
+                    damping = kdm;
+                } else if (kdm > 0.0f) {
+                    damping = kdm;
+                    compliance = 1.0f / kdm;
+                }
+            }
+            float dl = angular_correction(err, derr_rel, bp, bc, ap, ac, compliance, damping, dt) * P.joint_angular_relaxation;
+            ang_dp += ap * dl;
+            ang_dc += ac * dl;
+        }
+    }
+    out.lin_p = lin_dp;
+    out.ang_p = ang_dp;
+    out.lin_c = lin_dc;
+    out.ang_c = ang_dc;
+    return true;
+}
+
+// apply_joint_forces for one joint (kernels.py:945-1075): wrench subtracted from the parent / added to the child.
+NB2_DEV bool joint_force_wrench(const nb2_model_desc& d, const float* joint_f, int j, int body0, const float* bodies, Deltas& out) {
+    const int type = d.joint_type[j];
+    if (!d.joint_enabled[j] || type == JT_FIXED || type == JT_ROD) return false;
+    const int qd_start = d.joint_qd_start[j];
+    const int lin_count = d.joint_dof_dim[2 * j], ang_count = d.joint_dof_dim[2 * j + 1];
+    const int ndof = (type == JT_FREE || type == JT_DISTANCE) ? 6 : (type == JT_BALL ? 3 : lin_count + ang_count);
+    bool any = false;
+    for (int k = 0; k < ndof; ++k) any |= joint_f[qd_start + k] != 0.0f;
+    if (!any) return false;  // a zero wrench leaves body_f bit-identical
+    const int id_c = d.joint_child[j] - body0;
+    const int id_p_raw = d.joint_parent[j];
+    const int id_p = id_p_raw >= 0 ? id_p_raw - body0 : -1;
+    V3 f_total, t_total;
+    if (type == JT_FREE || type == JT_DISTANCE) {
+        f_total = V3(joint_f[qd_start], joint_f[qd_start + 1], joint_f[qd_start + 2]);
+        t_total = V3(joint_f[qd_start + 3], joint_f[qd_start + 4], joint_f[qd_start + 5]);
+        out.lin_p = f_total;
+        out.ang_p = t_total;
+        out.lin_c = f_total;
+        out.ang_c = t_total;
+        return true;
+    }
+    const Xf X_pj = ldx(d.joint_X_p + 7 * j), X_cj = ldx(d.joint_X_c + 7 * j);
+    Xf X_wp = X_pj, pose_p = X_pj;
+    V3 com_p;
+    if (id_p >= 0) {
+        pose_p = ldx(bodies + id_p * BR_SIZE + BR_Q);
+        X_wp = xmul(pose_p, X_wp);
+        com_p = ld3(bodies + id_p * BR_SIZE + BR_COM);
+    }
+    V3 r_p = X_wp.p - xpoint(pose_p, com_p);
+    Xf pose_c = ldx(bodies + id_c * BR_SIZE + BR_Q);
+    Xf X_wc = xmul(pose_c, X_cj);
+    V3 r_c = X_wc.p - xpoint(pose_c, ld3(bodies + id_c * BR_SIZE + BR_COM));
+    if (type == JT_BALL) {
+        t_total = V3(joint_f[qd_start], joint_f[qd_start + 1], joint_f[qd_start + 2]);
+    } else {
+        for (int k = 0; k < 3; ++k)
+            if (lin_count > k) f_total += joint_f[qd_start + k] * xvec(X_wp, ld3(d.joint_axis + 3 * (qd_start + k)));
+        for (int k = 0; k < 3; ++k)
+            if (ang_count > k)
+                t_total += joint_f[qd_start + lin_count + k] * xvec(X_wp, ld3(d.joint_axis + 3 * (qd_start + lin_count + k)));
+    }
+    out.lin_p = f_total;
+    out.ang_p = t_total + cross(r_p, f_total);
+    out.lin_c = f_total;
+    out.ang_c = t_total + cross(r_c, f_total);
+    return true;
+}
+
+NB2_DEV void store_deltas(float* rec, const Deltas& dl, float active) {
+    st3(rec + 0, dl.lin_p);
+    st3(rec + 3, dl.ang_p);
+    st3(rec + 6, dl.lin_c);
+    st3(rec + 9, dl.ang_c);
+    rec[12] = active;
+}
+
+// apply_body_deltas for one body held in shared memory (kernels.py:864-933), in place.
+NB2_DEV void apply_delta(float* rec, V3 dlin, V3 dang, float inv_weight, bool weighted, float dt) {
+    const float inv_m = rec[BR_INVM];
+    if (inv_m == 0.0f) return;
+    const M33 inv_I = ldm(rec + BR_INVI), I = ldm(rec + BR_I);
+    const V3 p0 = ld3(rec + BR_Q);
+    const Q4 q0(rec[BR_Q + 3], rec[BR_Q + 4], rec[BR_Q + 5], rec[BR_Q + 6]);
+    const V3 v0 = ld3(rec + BR_QD), w0 = ld3(rec + BR_QD + 3);
+    float weight = 1.0f;
+    if (weighted && inv_weight > 0.0f) weight = 1.0f / inv_weight;
+    const V3 dp = dlin * (inv_m * weight);
+    const V3 dq = dang * weight;
+    const V3 wb = qrot_inv(q0, w0);
+    const V3 dwb = mv(inv_I, qrot_inv(q0, dq));
+    const V3 tb = cross(dwb, mv(I, wb + dwb)) + cross(wb, mv(I, dwb));
+    const V3 dw1 = qrot(q0, dwb - mv(mscale(dt, inv_I), tb));
+    const V3 h = dw1 * dt;
+    Q4 q1 = qadd(q0, qmul(qscale(Q4(h.x, h.y, h.z, 0.0f), 0.5f), q0));
+    q1 = qunit(q1);
+    const V3 com = ld3(rec + BR_COM);
+    const V3 x_com = p0 + qrot(q0, com);
+    V3 p1 = x_com + dp * dt;
+    p1 -= qrot(q1, com);
+    V3 v1 = v0 + dp, w1 = w0 + dw1;
+    if (len(v1) < 1e-4f) v1 = V3();
+    if (len(w1) < 1e-4f) w1 = V3();
+    st3(rec + BR_Q, p1);
+    rec[BR_Q + 3] = q1.x; rec[BR_Q + 4] = q1.y; rec[BR_Q + 5] = q1.z; rec[BR_Q + 6] = q1.w;
+    st3(rec + BR_QD, v1);
+    st3(rec + BR_QD + 3, w1);
+}
+
+template <int L>
+__global__ void __launch_bounds__(32) xpbd_step_kernel(DevModel M, nb2_xpbd_params P, nb2_state_view sin, nb2_state_view sout,
+                                                        nb2_control_view ctl, int use_contacts, float dt) {
+    constexpr int G = 32 / L;
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31;
+    const int grp = lane / L, l = lane % L;
+    const int env = blockIdx.x * G + grp;
+    const bool live = env < M.env_count;
+    const nb2_model_desc& d = M.d;
+    const int rec_cap = max(M.max_env_contact_slots, M.max_env_joints);
+    const int per_env = M.max_env_bodies * BR_SIZE + rec_cap * DR_SIZE + M.max_env_contact_slots;
+    float* bodies = smem + size_t(grp) * per_env;
+    float* drec = bodies + M.max_env_bodies * BR_SIZE;
+    int* cpair = reinterpret_cast<int*>(drec + rec_cap * DR_SIZE);
+
+    int b0 = 0, nb = 0, j0 = 0, nj = 0, slot0 = 0, nc = 0;
+    if (live) {
+        b0 = M.env_body_start[env];
+        nb = M.env_body_start[env + 1] - b0;
+        j0 = M.env_joint_start[env];
+        nj = M.env_joint_start[env + 1] - j0;
+        slot0 = M.env_slot_start[env];
+        nc = use_contacts ? M.env_contact_count[env] : 0;
+    }
+    // ---- load body state + constants into shared memory ------------------------------------------
+    for (int b = l; b < nb; b += L) {
+        const int gb = b0 + b;
+        float* rec = bodies + b * BR_SIZE;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) rec[BR_Q + k] = sin.body_q[7 * gb + k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) rec[BR_QD + k] = sin.body_qd[6 * gb + k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) rec[BR_COM + k] = d.body_com[3 * gb + k];
+        const bool kin = (d.body_flags[gb] & BODY_KINEMATIC) != 0;  // _update_effective_inv_mass_inertia (solver.py:173-187)
+        rec[BR_INVM] = kin ? 0.0f : d.body_inv_mass[gb];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            rec[BR_INVI + k] = kin ? 0.0f : d.body_inv_inertia[9 * gb + k];
+            rec[BR_I + k] = d.body_inertia[9 * gb + k];
+        }
+    }
+    for (int c = l; c < nc; c += L) {
+        const size_t T = size_t(M.slot_total);
+        int ba = __float_as_int(M.cb[CF_BODY_A * T + slot0 + c]), bb = __float_as_int(M.cb[CF_BODY_B * T + slot0 + c]);
+        cpair[c] = (ba & 0xffff) | (bb << 16);
+    }
+    __syncwarp();
+    // ---- apply_joint_forces: per-joint wrenches, then ordered per-body accumulation into a body_f copy ----
+    for (int j = l; j < nj; j += L) {
+        Deltas w;
+        bool act = joint_force_wrench(d, ctl.joint_f, j0 + j, b0, bodies, w);
+        if (!act) w = Deltas();
+        store_deltas(drec + j * DR_SIZE, w, act ? 1.0f : 0.0f);
+    }
+    __syncwarp();
+    // ---- integrate_bodies (solver.py:64-107) ----------------------------------------------------
+    for (int b = l; b < nb; b += L) {
+        const int gb = b0 + b;
+        float* rec = bodies + b * BR_SIZE;
+        V3 f0 = ld3(sin.body_f + 6 * gb), t0 = ld3(sin.body_f + 6 * gb + 3);
+        for (int k = M.body_joint_start[gb]; k < M.body_joint_start[gb + 1]; ++k) {
+            const int e = M.body_joint_entry[k];
+            const float* r = drec + (e >> 1) * DR_SIZE;
+            if (r[12] != 0.0f) {
+                if (e & 1) { f0 += ld3(r + 6); t0 += ld3(r + 9); }
+                else { f0 -= ld3(r + 0); t0 -= ld3(r + 3); }
+            }
+        }
+        if ((d.body_flags[gb] & BODY_KINEMATIC) != 0) continue;  // kinematic bodies pass through (solver.py:132-139)
+        const V3 x0 = ld3(rec + BR_Q);
+        const Q4 r0(rec[BR_Q + 3], rec[BR_Q + 4], rec[BR_Q + 5], rec[BR_Q + 6]);
+        const V3 v0 = ld3(rec + BR_QD), w0 = ld3(rec + BR_QD + 3);
+        const V3 com = ld3(rec + BR_COM);
+        const float inv_mass = d.body_inv_mass[gb];
+        const M33 inertia = ldm(rec + BR_I);
+        const M33 inv_inertia = ldm(d.body_inv_inertia + 9 * gb);
+        int wi = d.body_world[gb];
+        if (wi < 0) wi += d.gravity_count;
+        const V3 g = ld3(d.gravity + 3 * wi);
+        const V3 x_com = x0 + qrot(r0, com);
+        const V3 v1 = v0 + (f0 * inv_mass + g * (inv_mass != 0.0f ? 1.0f : 0.0f)) * dt;
+        const V3 x1 = x_com + v1 * dt;
+        const V3 wb = qrot_inv(r0, w0);
+        const V3 tb = qrot_inv(r0, t0) - cross(wb, mv(inertia, wb));
+        V3 w1 = qrot(r0, wb + mv(inv_inertia, tb) * dt);
+        const Q4 r1 = qunit(qadd(r0, qscale(qscale(qmul(Q4(w1.x, w1.y, w1.z, 0.0f), r0), 0.5f), dt)));
+        w1 *= 1.0f - P.angular_damping * dt;
+        st3(rec + BR_Q, x1 - qrot(r1, com));
+        rec[BR_Q + 3] = r1.x; rec[BR_Q + 4] = r1.y; rec[BR_Q + 5] = r1.z; rec[BR_Q + 6] = r1.w;
+        st3(rec + BR_QD, v1);
+        st3(rec + BR_QD + 3, w1);
+    }
+    __syncwarp();
+    // ---- Jacobi iterations ---------------------------------------------------------------------------
+    const size_t T = size_t(M.slot_total);
+    const float* cb = M.cb;
+    for (int it = 0; it < P.iterations; ++it) {
+        if (use_contacts) {
+            // solve_body_contact_positions (kernels.py:2164-2399)
+            for (int c = l; c < nc; c += L) {
+                const int s = slot0 + c;
+                const int pr = cpair[c];
+                const int ba = int(short(pr & 0xffff)), bb = pr >> 16;
+                Deltas dl;
+                float active = 0.0f;
+                if (ba != bb) {
+                    BodyView A = ba >= 0 ? load_body(bodies + ba * BR_SIZE) : static_body();
+                    BodyView B = bb >= 0 ? load_body(bodies + bb * BR_SIZE) : static_body();
+                    const V3 p0(cb[CF_P0X * T + s], cb[CF_P0Y * T + s], cb[CF_P0Z * T + s]);
+                    const V3 p1(cb[CF_P1X * T + s], cb[CF_P1Y * T + s], cb[CF_P1Z * T + s]);
+                    const V3 n(cb[CF_NX * T + s], cb[CF_NY * T + s], cb[CF_NZ * T + s]);
+                    V3 bx_a = xpoint(A.X, p0), bx_b = xpoint(B.X, p1);
+                    const float dpen = dot(n, bx_b - bx_a) - (cb[CF_MARGIN0 * T + s] + cb[CF_MARGIN1 * T + s]);
+                    if (dpen < 0.0f) {
+                        active = 1.0f;
+                        const float mu = cb[CF_MU * T + s], mu_t = cb[CF_MU_TORSIONAL * T + s], mu_r = cb[CF_MU_ROLLING * T + s];
+                        V3 r_a = bx_a - xpoint(A.X, A.com), r_b = bx_b - xpoint(B.X, B.com);
+                        V3 ang_a = -cross(r_a, n), ang_b = cross(r_b, n);
+                        const float lambda_n = contact_delta(dpen, A, B, -n, n, ang_a, ang_b, P.rigid_contact_relaxation, dt);
+                        V3 lin_da = -n * lambda_n, lin_db = n * lambda_n, ang_da = ang_a * lambda_n, ang_db = ang_b * lambda_n;
+                        if (mu > 0.0f) {
+                            const V3 o0(cb[CF_O0X * T + s], cb[CF_O0Y * T + s], cb[CF_O0Z * T + s]);
+                            const V3 o1(cb[CF_O1X * T + s], cb[CF_O1Y * T + s], cb[CF_O1Z * T + s]);
+                            bx_a = xpoint(A.X, p0 + o0);
+                            bx_b = xpoint(B.X, p1 + o1);
+                            V3 delta = bx_b - bx_a;
+                            V3 fd = delta - dot(n, delta) * n;
+                            r_a = bx_a - xpoint(A.X, A.com);
+                            r_b = bx_b - xpoint(B.X, B.com);
+                            V3 rel_v_kin;
+                            if (ba >= 0 && (d.body_flags[b0 + ba] & BODY_KINEMATIC) != 0) {
+                                V3 v_a = cross(A.w, r_a) + A.v;
+                                rel_v_kin = rel_v_kin - (v_a - dot(n, v_a) * n);
+                            }
+                            if (bb >= 0 && (d.body_flags[b0 + bb] & BODY_KINEMATIC) != 0) {
+                                V3 v_b = cross(B.w, r_b) + B.v;
+                                rel_v_kin = rel_v_kin + (v_b - dot(n, v_b) * n);
+                            }
+                            fd += rel_v_kin * dt;
+                            V3 perp = unit(fd);
+                            ang_a = -cross(r_a, perp);
+                            ang_b = cross(r_b, perp);
+                            float err = len(fd);
+                            if (err > 0.0f) {
+                                float lambda_fr = contact_delta(err, A, B, -perp, perp, ang_a, ang_b, P.rigid_contact_relaxation, dt);
+                                lambda_fr = fmax_w(lambda_fr, -lambda_n * mu);
+                                lin_da -= perp * lambda_fr;
+                                lin_db += perp * lambda_fr;
+                                ang_da += ang_a * lambda_fr;
+                                ang_db += ang_b * lambda_fr;
+                            }
+                        }
+                        V3 dom = B.w - A.w;
+                        if (mu_t > 0.0f) {
+                            float err = dot(dom, n) * dt;
+                            if (fabsf(err) > 0.0f) {
+                                float lt = contact_delta(err, A, B, V3(), V3(), -n, n, P.rigid_contact_relaxation, dt);
+                                lt = clamp_w(lt, -lambda_n * mu_t, lambda_n * mu_t);
+                                ang_da -= n * lt;
+                                ang_db += n * lt;
+                            }
+                        }
+                        if (mu_r > 0.0f) {
+                            dom -= dot(n, dom) * n;
+                            float err = len(dom) * dt;
+                            if (err > 0.0f) {
+                                V3 rn = unit(dom);
+                                float lr = contact_delta(err, A, B, V3(), V3(), -rn, rn, P.rigid_contact_relaxation, dt);
+                                lr = fmax_w(lr, -lambda_n * mu_r);
+                                ang_da -= rn * lr;
+                                ang_db += rn * lr;
+                            }
+                        }
+                        dl.lin_p = lin_da;
+                        dl.ang_p = ang_da;
+                        dl.lin_c = lin_db;
+                        dl.ang_c = ang_db;
+                    }
+                }
+                store_deltas(drec + c * DR_SIZE, dl, active);
+            }
+            __syncwarp();
+            // ordered per-body sum (contact order; side A before side B) + weighted apply
+            for (int b = l; b < nb; b += L) {
+                V3 dlin, dang;
+                float cnt = 0.0f;
+                for (int c = 0; c < nc; ++c) {
+                    const int pr = cpair[c];
+                    const int ba = int(short(pr & 0xffff)), bb = pr >> 16;
+                    if (ba != b && bb != b) continue;
+                    const float* r = drec + c * DR_SIZE;
+                    if (r[12] == 0.0f) continue;
+                    if (ba == b) { dlin += ld3(r + 0); dang += ld3(r + 3); cnt += 1.0f; }
+                    if (bb == b) { dlin += ld3(r + 6); dang += ld3(r + 9); cnt += 1.0f; }
+                }
+                apply_delta(bodies + b * BR_SIZE, dlin, dang, cnt, P.rigid_contact_con_weighting != 0, dt);
+            }
+            __syncwarp();
+        }
+        if (d.joint_count > 0) {
+            // solve_body_joints (kernels.py:1513-2044)
+            for (int j = l; j < nj; j += L) {
+                Deltas dl;
+                bool act = solve_joint(d, ctl, P, j0 + j, b0, bodies, dt, dl);
+                if (!act) dl = Deltas();
+                store_deltas(drec + j * DR_SIZE, dl, act ? 1.0f : 0.0f);
+            }
+            __syncwarp();
+            for (int b = l; b < nb; b += L) {
+                const int gb = b0 + b;
+                V3 dlin, dang;
+                for (int k = M.body_joint_start[gb]; k < M.body_joint_start[gb + 1]; ++k) {
+                    const int e = M.body_joint_entry[k];
+                    const float* r = drec + (e >> 1) * DR_SIZE;
+                    if (r[12] == 0.0f) continue;
+                    if (e & 1) { dlin += ld3(r + 6); dang += ld3(r + 9); }
+                    else { dlin += ld3(r + 0); dang += ld3(r + 3); }
+                }
+                apply_delta(bodies + b * BR_SIZE, dlin, dang, 0.0f, false, dt);
+            }
+            __syncwarp();
+        }
+    }
+    // ---- write back -------------------------------------------------------------------------------------
+    for (int b = l; b < nb; b += L) {
+        const int gb = b0 + b;
+        const float* rec = bodies + b * BR_SIZE;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) sout.body_q[7 * gb + k] = rec[BR_Q + k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) sout.body_qd[6 * gb + k] = rec[BR_QD + k];
+    }
+}
+
+// Stand-alone integrate_bodies (reference SolverBase.integrate_bodies, solver.py:267-307): one thread per body.
+__global__ void __launch_bounds__(256) integrate_bodies_kernel(nb2_model_desc d, nb2_state_view sin, nb2_state_view sout,
+                                                                float angular_damping, float dt) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= d.body_count) return;
+    Xf X = ldx(sin.body_q + 7 * b);
+    V3 v0 = ld3(sin.body_qd + 6 * b), w0 = ld3(sin.body_qd + 6 * b + 3);
+    if ((d.body_flags[b] & BODY_KINEMATIC) != 0) {
+        stx(sout.body_q + 7 * b, X);
+        st3(sout.body_qd + 6 * b, v0);
+        st3(sout.body_qd + 6 * b + 3, w0);
+        return;
+    }
+    V3 f0 = ld3(sin.body_f + 6 * b), t0 = ld3(sin.body_f + 6 * b + 3);
+    const V3 com = ld3(d.body_com + 3 * b);
+    const float inv_mass = d.body_inv_mass[b];
+    const M33 inertia = ldm(d.body_inertia + 9 * b), inv_inertia = ldm(d.body_inv_inertia + 9 * b);
+    int wi = d.body_world[b];
+    if (wi < 0) wi += d.gravity_count;
+    const V3 g = ld3(d.gravity + 3 * wi);
+    const V3 x_com = X.p + qrot(X.q, com);
+    const V3 v1 = v0 + (f0 * inv_mass + g * (inv_mass != 0.0f ? 1.0f : 0.0f)) * dt;
+    const V3 x1 = x_com + v1 * dt;
+    const V3 wb = qrot_inv(X.q, w0);
+    const V3 tb = qrot_inv(X.q, t0) - cross(wb, mv(inertia, wb));
+    V3 w1 = qrot(X.q, wb + mv(inv_inertia, tb) * dt);
+    const Q4 r1 = qunit(qadd(X.q, qscale(qscale(qmul(Q4(w1.x, w1.y, w1.z, 0.0f), X.q), 0.5f), dt)));
+    w1 *= 1.0f - angular_damping * dt;
+    stx(sout.body_q + 7 * b, Xf(x1 - qrot(r1, com), r1));
+    st3(sout.body_qd + 6 * b, v1);
+    st3(sout.body_qd + 6 * b + 3, w1);
+}
+
+template <int L>
+static nb2_status launch_xpbd_L(nb2_model* m, const nb2_xpbd_params& p, const nb2_state_view& in, const nb2_state_view& out,
+                                const nb2_control_view& ctl, int use_contacts, float dt, cudaStream_t s) {
+    const DevModel& M = m->dev;
+    const int G = 32 / L;
+    const int blocks = (M.env_count + G - 1) / G;
+    const int rec_cap = std::max(M.max_env_contact_slots, M.max_env_joints);
+    const size_t per_env = size_t(M.max_env_bodies) * BR_SIZE + size_t(rec_cap) * DR_SIZE + size_t(M.max_env_contact_slots);
+    const size_t smem = per_env * G * sizeof(float);
+    if (smem > 220 * 1024 || M.max_env_bodies > 32000) {
+        set_error("xpbd_step: environment too large for the fused shared-memory kernel (bodies/contacts per env)");
+        return NB2_ERR_CAPACITY;
+    }
+    if (smem > 48 * 1024)
+        NB2_CUDA_CHECK(cudaFuncSetAttribute(xpbd_step_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    xpbd_step_kernel<L><<<blocks, 32, smem, s>>>(M, p, in, out, ctl, use_contacts, dt);
+    count_launch();
+    NB2_CUDA_CHECK(cudaGetLastError());
+    return NB2_OK;
+}
+
+nb2_status launch_xpbd_step(nb2_model* m, const nb2_xpbd_params& p, const nb2_state_view& in, const nb2_state_view& out,
+                            const nb2_control_view& ctl, int use_contacts, float dt, cudaStream_t s) {
+    const DevModel& M = m->dev;
+    if (M.d.body_count == 0) return NB2_OK;
+    if (!in.body_q || !in.body_qd || !in.body_f || !out.body_q || !out.body_qd) {
+        set_error("nb2_xpbd_step: state arrays are NULL");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    if (M.d.joint_count > 0 && (!ctl.joint_f || !ctl.joint_target_q || !ctl.joint_target_qd)) {
+        set_error("nb2_xpbd_step: control arrays are NULL");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    switch (m->lanes_per_env) {
+        case 8: return launch_xpbd_L<8>(m, p, in, out, ctl, use_contacts, dt, s);
+        case 16: return launch_xpbd_L<16>(m, p, in, out, ctl, use_contacts, dt, s);
+        default: return launch_xpbd_L<32>(m, p, in, out, ctl, use_contacts, dt, s);
+    }
+}
+
+nb2_status launch_integrate_bodies(nb2_model* m, const nb2_state_view& in, const nb2_state_view& out, float angular_damping, float dt,
+                                   cudaStream_t s) {
+    const nb2_model_desc& d = m->dev.d;
+    if (d.body_count == 0) return NB2_OK;
+    integrate_bodies_kernel<<<(d.body_count + 255) / 256, 256, 0, s>>>(d, in, out, angular_damping, dt);
+    count_launch();
+    NB2_CUDA_CHECK(cudaGetLastError());
+    return NB2_OK;
+}
+
+}  // namespace nb2

@@ -1,0 +1,58 @@
+"""``CollisionPipeline`` - drop-in for the reference class (``newton/_src/sim/collide.py:1104-2207``).
+
+Same constructor kwargs and methods (``contacts()``, ``collide(state, contacts, *, dt=None)``) for the
+in-scope configuration: ``broad_phase="explicit"`` over ``model.shape_contact_pairs``, primitive +
+convex shapes.  All work happens in ``nb2_collide`` (one fused kernel,
+plus scan + scatter when exporting to the ``Contacts`` arrays).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+from .. import _abi, _lib
+from .model import Contacts
+
+
+class CollisionPipeline:
+    def __init__(self, model, *, broad_phase: str | None = None, rigid_contact_max: int | None = None,
+                 deterministic: bool = False, soft_contact_margin: float = 0.01, requires_grad: bool = False,
+                 export_contacts: bool = True, **unsupported):
+        if broad_phase not in (None, "explicit"):
+            raise NotImplementedError(
+                f"broad_phase={broad_phase!r}: only the explicit pair list is in the hot-path scope (SURVEY.md §8(f) row 3)"
+            )
+        if requires_grad:
+            raise NotImplementedError("differentiable contacts are out of scope")
+        for k, v in unsupported.items():
+            if v not in (None, False):
+                raise NotImplementedError(f"CollisionPipeline option {k!r} is outside the hot-path scope")
+        self.model = model
+        self.device = model.device
+        self._native = _lib.native_model(model)
+        # Contacts are always produced in deterministic (env, sort-key) order, so `deterministic` is a no-op.
+        self.deterministic = deterministic
+        self.export_contacts = export_contacts
+        native_max = self._native.rigid_contact_max
+        if rigid_contact_max is not None and rigid_contact_max < native_max and export_contacts:
+            # smaller user capacity is allowed: like the reference, the count keeps growing and excess writes are dropped
+            pass
+        self.rigid_contact_max = int(rigid_contact_max) if rigid_contact_max is not None else max(native_max, 1)
+        self.soft_contact_margin = soft_contact_margin
+
+    def contacts(self) -> Contacts:
+        """Allocate a :class:`Contacts` buffer sized for this pipeline (reference ``collide.py:1691-1730``)."""
+        c = Contacts(self.rigid_contact_max, 0, device=self.device,
+                     requested_attributes=self.model._requested_contact_attributes)
+        return c
+
+    def collide(self, state, contacts, *, soft_contact_margin=None, dt=None):
+        """Populate ``contacts`` from ``state.body_q`` (reference ``collide.py:1765-2207``)."""
+        view = None
+        if contacts is not None:
+            contacts._nb2_blocks = self._native
+            if self.export_contacts:
+                view = C.byref(_abi.contacts_view(contacts))
+        st = _lib.lib().nb2_collide(self._native.handle, C.c_void_p(_abi.ptr(state.body_q)), view,
+                                    _lib.current_stream_ptr(self.model))
+        _lib.check(st, "nb2_collide")

@@ -1,0 +1,4 @@
+from .solver import SolverBase
+from .xpbd import SolverXPBD
+
+__all__ = ["SolverBase", "SolverXPBD"]

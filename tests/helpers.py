@@ -1,0 +1,45 @@
+"""Shared helpers for parity tests: run the same loop through the oracle (CPU) and the CUDA path."""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def simulate(model, pipeline_cls, solver_cls, *, substeps, dt, solver_kwargs=None, collide=True, control=None,
+             record_contacts=False):
+    """`collide -> step -> swap` loop exactly as the reference examples run it (example_basic_urdf.py:117-135)."""
+    solver = solver_cls(model, **(solver_kwargs or {}))
+    pipe = pipeline_cls(model) if collide else None
+    s0, s1 = model.state(), model.state()
+    ctrl = control if control is not None else model.control()
+    contacts = pipe.contacts() if pipe is not None else None
+    counts = []
+    for _ in range(substeps):
+        s0.clear_forces()
+        if pipe is not None:
+            pipe.collide(s0, contacts)
+            if record_contacts:
+                counts.append(int(contacts.rigid_contact_count.item()))
+        solver.step(s0, s1, ctrl, contacts, dt)
+        s0, s1 = s1, s0
+    return s0, contacts, counts
+
+
+def canonical_contacts(contacts, model):
+    """Contacts sorted by (shape0, shape1, insertion order) as numpy arrays - order-independent comparison key."""
+    n = int(contacts.rigid_contact_count.item())
+    n = min(n, contacts.rigid_contact_max)
+    g = lambda t: t[:n].detach().cpu().numpy()  # noqa: E731
+    s0, s1 = g(contacts.rigid_contact_shape0), g(contacts.rigid_contact_shape1)
+    order = np.lexsort((np.arange(n), s1, s0))
+    out = {"shape0": s0[order], "shape1": s1[order]}
+    for name in ("point0", "point1", "offset0", "offset1", "normal", "margin0", "margin1"):
+        out[name] = g(getattr(contacts, "rigid_contact_" + name))[order]
+    return n, out
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(1e-12, np.max(np.abs(b))))
