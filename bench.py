@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark: env-steps/s of the collide -> SolverXPBD.step substep loop.
+
+Workload (BASELINE.json configs[2], the config the metric is quoted on): 4096 Anymal-class quadruped
+environments (13 bodies / 13 joints / 18 dofs each, vendored-URDF topology built by newton_b200.scenes),
+SolverXPBD(iterations=8), 4 substeps per frame at 50 fps (dt = 5 ms), fp32, synthetic per-env perturbation
+(default_rng(1)).  One bench "step" = one frame = 4 x (clear_forces, collide, solver.step, swap) for every env,
+replayed as one CUDA graph exactly as the reference examples do (example_basic_urdf.py:112-143).
+
+  python bench.py --gpus N --steps K --warmup W          # N>1: launched by torchrun, one rank per GPU
+  python bench.py --impl reference ...                   # the CPU oracle (reference restatement) on host cores
+
+Prints ONE JSON line (see the task contract): whole-job env-steps/s, e2e (host buffers through the public API),
+roofline of the dominant kernel, cpu_baseline, clocks.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 4096
+SUBSTEPS = 4
+ITERATIONS = 8
+FPS = 50
+DT = 1.0 / FPS / SUBSTEPS
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=50)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="native", choices=["native", "reference"])
+    p.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU (weak scaling)")
+    p.add_argument("--strict", action="store_true", help="use the strict-fp library (bit-reproduces the oracle)")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def workload_config(envs, n_gpus):
+    return {
+        "workload": f"{envs * n_gpus} quadruped (Anymal-class, 13 bodies/18 dofs) envs, SolverXPBD iterations={ITERATIONS}, "
+                    f"{SUBSTEPS} substeps/frame @ {FPS} fps, explicit broad phase, ground plane; BASELINE.json configs[2]"
+                    + ("" if n_gpus == 1 else f" sharded {envs}/GPU (configs[4] layout)"),
+        "envs_per_gpu": envs,
+        "substeps_per_step": SUBSTEPS,
+        "iterations": ITERATIONS,
+        "dt": DT,
+        "parallelism": f"env-sharded x{n_gpus}" if n_gpus > 1 else "single GPU",
+        "l2": "flushed between timed steps (256 MiB memset outside the timed events)",
+    }
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples nvidia-smi during the timed region (profiling recipe's clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": float(max(smax)) if smax else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+# ------------------------------------------------------------------------------------------------ native arm
+def run_native(args):
+    import torch.distributed as dist
+
+    import newton_b200
+    from newton_b200 import _lib, scenes
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched through torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.strict:
+        os.environ["NB2_LIB"] = os.path.join(ROOT, "newton_b200", "libnewton_b200_strict.so")
+
+    envs = args.envs
+    # every rank owns `envs` worlds (weak scaling); per-rank seed so shards differ like slices of one big scene
+    model = scenes.quadruped_model(envs, device="cpu", seed=1 + rank).to(dev)
+    pipeline = newton_b200.CollisionPipeline(model)
+    solver = newton_b200.solvers.SolverXPBD(model, iterations=ITERATIONS)
+    state_0, state_1 = model.state(), model.state()
+    control = model.control()
+    contacts = pipeline.contacts()
+
+    def simulate():
+        nonlocal state_0, state_1
+        for _ in range(SUBSTEPS):
+            state_0.clear_forces()
+            pipeline.collide(state_0, contacts)
+            solver.step(state_0, state_1, control, contacts, DT)
+            state_0, state_1 = state_1, state_0
+
+    # settle the robots on the ground first (untimed) so the timed frames carry the steady-state contact load
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        for _ in range(60):
+            simulate()
+    torch.cuda.synchronize()
+    launches_before = _lib.kernel_launch_count()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=stream):
+        simulate()
+    launches_per_step = _lib.kernel_launch_count() - launches_before  # kernels captured in one frame graph
+    assert SUBSTEPS % 2 == 0  # state_0/state_1 swap parity: the graph ends where it began
+
+    gathered_q = gathered_qd = None
+    if world > 1:  # end-of-frame state gather over NVLink; part of every timed step
+        gathered_q = torch.empty((world, *state_0.body_q.shape), dtype=torch.float32, device=dev)
+        gathered_qd = torch.empty((world, *state_0.body_qd.shape), dtype=torch.float32, device=dev)
+
+    def step_device():
+        graph.replay()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered_q, state_0.body_q)
+            dist.all_gather_into_tensor(gathered_qd, state_0.body_qd)
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        if sampler:
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            flush.zero_()  # evict L2 (126 MB) between timed steps; not inside the timed events
+            a.record()
+            fn()
+            b.record()
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), clocks
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    total_ms, clocks = timed(step_device, args.steps, max(args.warmup, 3), sampler)
+    env_steps = envs * world * SUBSTEPS * args.steps
+    value = env_steps / (total_ms * 1e-3)
+
+    # ---- e2e: host buffers through the public API (H2D of the step's control inputs, D2H of the resulting state)
+    h_target = model.joint_target_q.cpu().pin_memory()
+    h_jf = torch.zeros_like(control.joint_f, device="cpu").pin_memory()
+    h_q = torch.empty_like(state_0.body_q, device="cpu").pin_memory()
+    h_qd = torch.empty_like(state_0.body_qd, device="cpu").pin_memory()
+
+    def step_e2e():
+        control.joint_target_q.copy_(h_target, non_blocking=True)
+        control.joint_f.copy_(h_jf, non_blocking=True)
+        step_device()
+        h_q.copy_(state_0.body_q, non_blocking=True)
+        h_qd.copy_(state_0.body_qd, non_blocking=True)
+
+    e2e_ms, _ = timed(step_e2e, args.steps, 3)
+    e2e_value = env_steps / (e2e_ms * 1e-3)
+    h2d = h_target.numel() * 4 + h_jf.numel() * 4
+    d2h = h_q.numel() * 4 + h_qd.numel() * 4
+
+    # ---- roofline of the dominant kernel (xpbd_step_kernel): CUDA events around single launches on this stream
+    n_c = float(contacts.rigid_contact_count.item()) / envs
+    reps = 40
+    evs = []
+    for _ in range(5):
+        pipeline.collide(state_0, contacts)
+        solver.step(state_0, state_1, control, contacts, DT)
+    for _ in range(reps):
+        pipeline.collide(state_0, contacts)
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        solver.step(state_0, state_1, control, contacts, DT)
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    # algorithmic bytes per env-substep of the solver kernel: state in (988) + out (676) +
+    # control (220) + one read of each 80-byte contact; the matching contact write belongs to the collide kernel
+    alg_bytes_env = 1884.0 + 80.0 * n_c
+    achieved = alg_bytes_env * envs / (kern_ms * 1e-3) / 1e9
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    roofline = {
+        "bound": "hbm", "kernel": "xpbd_step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": None, "peak_source": "measured" if peaks else "fallback",
+        "algorithmic_bytes_per_env_substep": alg_bytes_env, "kernel_ms": kern_ms, "contacts_per_env": n_c,
+    }
+
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu_baseline = oracle_throughput(min(envs, 1024), frames=2, threads=os.cpu_count() or 1)
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(envs, world), "impl": "native",
+            "fp_mode": "strict" if args.strict else "fast",
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "gpu_launches_per_step": int(launches_per_step),
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def oracle_throughput(envs: int, frames: int, threads: int) -> dict:
+    """Times the CPU oracle (restatement of the reference's Warp-CPU kernels) on `envs` environments split over
+    `threads` host threads (environments are independent; ctypes releases the GIL)."""
+    import oracle
+    from newton_b200 import scenes
+
+    oracle.build()
+    threads = max(1, min(threads, envs))
+    per = envs // threads
+    envs = per * threads
+    base = scenes.quadruped_model(envs, device="cpu", seed=1)
+    shards = [base.shard(r, threads) for r in range(threads)] if threads > 1 else [base]
+
+    def make(m):
+        return dict(m=m, pipe=oracle.CollisionPipeline(m), solver=oracle.SolverXPBD(m, iterations=ITERATIONS), s0=m.state(),
+                    s1=m.state(), ctrl=m.control())
+
+    ctx = [make(m) for m in shards]
+    for c in ctx:
+        c["contacts"] = c["pipe"].contacts()
+
+    def run(c, n_frames):
+        for _ in range(n_frames * SUBSTEPS):
+            c["s0"].clear_forces()
+            c["pipe"].collide(c["s0"], c["contacts"])
+            c["solver"].step(c["s0"], c["s1"], c["ctrl"], c["contacts"], DT)
+            c["s0"], c["s1"] = c["s1"], c["s0"]
+
+    def run_all(n_frames):
+        ts = [threading.Thread(target=run, args=(c, n_frames)) for c in ctx]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+
+    run_all(15)  # settle onto the ground (untimed) so the timed frames carry contacts
+    t0 = time.perf_counter()
+    run_all(frames)
+    dt = time.perf_counter() - t0
+    return {
+        "value": envs * SUBSTEPS * frames / dt, "unit": UNIT, "cores": threads, "kind": "port",
+        "sample": f"{envs} envs x {frames} frames x {SUBSTEPS} substeps (same scene/solver settings), oracle C++ port of the "
+                  f"reference kernels, {threads} host threads; the reference itself (Warp) cannot run here",
+        "seconds": dt,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    envs = min(args.envs, 1024)
+    frames = 2
+    steps = max(1, args.steps)
+    warm = max(0, min(args.warmup, 2))
+    # each "step" is a bounded sample: `frames` frames of `envs` envs; keep the total run within minutes
+    steps = min(steps, 5)
+    vals = []
+    for i in range(warm + steps):
+        r = oracle_throughput(envs, frames, threads)
+        if i >= warm:
+            vals.append(r)
+    value = float(np.mean([v["value"] for v in vals]))
+    sec = float(np.mean([v["seconds"] for v in vals]))
+    cb = dict(vals[-1])
+    cb["value"] = value
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args.envs, args.gpus), "impl": "reference", "cpu_baseline": cb,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference arm = CPU oracle (C++ restatement of the reference's Warp kernels); the unmodified reference "
+                "needs NVIDIA Warp, which is not installed and cannot be installed offline (see DESIGN.md)",
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

@@ -11,7 +11,7 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnewton_b200.so")
+LIB_PATH = os.environ.get("NB2_LIB") or os.path.join(_HERE, "libnewton_b200.so")
 _lib = None
 
 STATUS = {0: "NB2_OK", 1: "NB2_ERR_INVALID_ARGUMENT", 2: "NB2_ERR_UNSUPPORTED", 3: "NB2_ERR_CUDA", 4: "NB2_ERR_CAPACITY"}

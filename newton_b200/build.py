@@ -9,6 +9,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnewton_b200.so")
+# Strict-fp variant: no FMA contraction + correctly rounded trig -> bit-reproduces the CPU oracle (parity tests).
+LIB_STRICT = os.path.join(HERE, "libnewton_b200_strict.so")
+STRICT_FLAGS = ["-fmad=false", "-DNB2_STRICT_FP=1"]
 SOURCES = ["nb2_api.cu", "nb2_collide.cu", "nb2_xpbd.cu", "nb2_featherstone.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
@@ -31,27 +34,29 @@ def needs_build() -> bool:
     return any(os.path.getmtime(p) > t for p in deps)
 
 
-def build(force: bool = False, verbose: bool = False, extra_flags: list[str] | None = None) -> str:
-    """Compile every CUDA source into one shared library; returns its path."""
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source into the product library and its strict-fp twin; returns the product path."""
+    if not force and not needs_build() and os.path.exists(LIB_STRICT):
         return LIB
-    objs = []
-    flags = NVCC_FLAGS + (extra_flags or [])
-    if verbose:
-        flags = flags + ["-Xptxas", "-v"]
     procs = []
-    for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        objs.append(obj)
-        cmd = [_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj]
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    variants = ((LIB, ".o", []), (LIB_STRICT, ".strict.o", STRICT_FLAGS))
+    for _lib_path, suffix, extra in variants:
+        flags = NVCC_FLAGS + extra
+        if verbose:
+            flags = flags + ["-Xptxas", "-v"]
+        for src in SOURCES:
+            obj = os.path.join(CSRC, src.replace(".cu", suffix))
+            cmd = [_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj]
+            procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()
         if verbose or p.returncode != 0:
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-    subprocess.run([_nvcc(), "-shared", "-o", LIB, *objs, "-lcudart"], check=True)
+    for lib_path, suffix, _extra in variants:
+        objs = [os.path.join(CSRC, src.replace(".cu", suffix)) for src in SOURCES]
+        subprocess.run([_nvcc(), "-shared", "-o", lib_path, *objs, "-lcudart"], check=True)
     return LIB
 
 

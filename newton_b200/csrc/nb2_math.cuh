@@ -49,6 +49,20 @@ NB2_DEV V3 vmax(V3 a, V3 b) { return V3(fmax_w(a.x, b.x), fmax_w(a.y, b.y), fmax
 NB2_DEV V3 vabs(V3 a) { return V3(fabsf(a.x), fabsf(a.y), fabsf(a.z)); }
 NB2_DEV V3 cmul(V3 a, V3 b) { return V3(a.x * b.x, a.y * b.y, a.z * b.z); }
 
+// Inverse trig used by the swing-twist joint rows.  NB2_STRICT_FP selects correctly-rounded results (double
+// evaluation rounded to fp32), which together with -fmad=false makes the kernels bit-reproduce the CPU oracle.
+#ifdef NB2_STRICT_FP
+NB2_DEV float asin_w(float x) { return (float)asin((double)x); }
+NB2_DEV float acos_w(float x) { return (float)acos((double)x); }
+NB2_DEV float sin_w(float x) { return (float)sin((double)x); }
+NB2_DEV float cos_w(float x) { return (float)cos((double)x); }
+#else
+NB2_DEV float asin_w(float x) { return asinf(x); }
+NB2_DEV float acos_w(float x) { return acosf(x); }
+NB2_DEV float sin_w(float x) { return sinf(x); }
+NB2_DEV float cos_w(float x) { return cosf(x); }
+#endif
+
 struct Q4 {
     float x, y, z, w;
     NB2_DEV Q4() : x(0.f), y(0.f), z(0.f), w(1.f) {}

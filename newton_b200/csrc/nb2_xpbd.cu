@@ -261,7 +261,7 @@ NB2_DEV bool solve_joint(const nb2_model_desc& d, const nb2_control_view& ctl, c
         const float sn = sqrtf(rq.x * rq.x + rq.w * rq.w);
         const float invs = 1.0f / sn;
         const float invscube = invs * invs * invs;
-        float err_0 = 2.0f * asinf(clamp_w(qtwist.x, -1.0f, 1.0f));
+        float err_0 = 2.0f * asin_w(clamp_w(qtwist.x, -1.0f, 1.0f));
         float err_1 = qswing.y, err_2 = qswing.z;
         Q4 g0(invs - rq.x * rq.x * invscube, 0.0f, 0.0f, -(rq.w * rq.x) * invscube);
         Q4 g1(-rq.w * (rq.w * rq.z + rq.x * rq.y) * invscube, rq.w * invs, -rq.x * invs, rq.x * (rq.w * rq.z + rq.x * rq.y) * invscube);
@@ -270,7 +270,7 @@ NB2_DEV bool solve_joint(const nb2_model_desc& d, const nb2_control_view& ctl, c
         const float swing_sq = qswing.w * qswing.w;
         if (swing_sq + 1.0e-4f < 1.0f) {
             float dd = sqrtf(1.0f - qswing.w * qswing.w);
-            float theta = 2.0f * acosf(clamp_w(qswing.w, -1.0f, 1.0f));
+            float theta = 2.0f * acos_w(clamp_w(qswing.w, -1.0f, 1.0f));
             float scale = theta / dd;
             err_1 *= scale;
             err_2 *= scale;

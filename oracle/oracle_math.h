@@ -53,6 +53,12 @@ inline vec3 vmin(vec3 a, vec3 b) { return vec3(minf(a.x, b.x), minf(a.y, b.y), m
 inline vec3 vmax(vec3 a, vec3 b) { return vec3(maxf(a.x, b.x), maxf(a.y, b.y), maxf(a.z, b.z)); }
 inline vec3 vabs(vec3 a) { return vec3(std::fabs(a.x), std::fabs(a.y), std::fabs(a.z)); }
 
+// Correctly-rounded fp32 inverse trig / trig (double evaluation rounded to float): what glibc's asinf/acosf
+// deliver in practice, written explicitly so the strict CUDA build can reproduce it bit for bit.
+inline float asin_w(float x) { return (float)std::asin((double)x); }
+inline float acos_w(float x) { return (float)std::acos((double)x); }
+inline float sin_w(float x) { return (float)std::sin((double)x); }
+inline float cos_w(float x) { return (float)std::cos((double)x); }
 inline float clampf(float x, float a, float b) { return minf(maxf(a, x), b); }
 inline float nonzero(float x) { return x != 0.0f ? 1.0f : 0.0f; }
 inline float signf(float x) { return x < 0.0f ? -1.0f : 1.0f; }
@@ -103,8 +109,8 @@ inline vec3 quat_rotate_inv(quat q, vec3 v) {
 }
 inline quat quat_from_axis_angle(vec3 axis, float angle) {
     float half = angle * 0.5f;
-    float w = std::cos(half);
-    float s = std::sin(half);
+    float w = cos_w(half);
+    float s = sin_w(half);
     vec3 v = axis * s;
     return quat(v.x, v.y, v.z, w);
 }

@@ -552,7 +552,7 @@ inline void solve_body_joints(const nb2_model_desc& m, const float* body_q, cons
             float s_ = std::sqrt(rel_q.x * rel_q.x + rel_q.w * rel_q.w);
             float invs = 1.0f / s_;
             float invscube = invs * invs * invs;
-            float err_0 = 2.0f * std::asin(clampf(qtwist.x, -1.0f, 1.0f));
+            float err_0 = 2.0f * asin_w(clampf(qtwist.x, -1.0f, 1.0f));
             float err_1 = qswing.y;
             float err_2 = qswing.z;
             quat grad_0(invs - rel_q.x * rel_q.x * invscube, 0.0f, 0.0f, -(rel_q.w * rel_q.x) * invscube);
@@ -565,7 +565,7 @@ inline void solve_body_joints(const nb2_model_desc& m, const float* body_q, cons
             const float angularEps = 1.0e-4f;
             if (swing_sq + angularEps < 1.0f) {
                 float d = std::sqrt(1.0f - qswing.w * qswing.w);
-                float theta = 2.0f * std::acos(clampf(qswing.w, -1.0f, 1.0f));
+                float theta = 2.0f * acos_w(clampf(qswing.w, -1.0f, 1.0f));
                 float scale = theta / d;
                 err_1 *= scale;
                 err_2 *= scale;
