@@ -43,11 +43,11 @@ UNIT = "env-steps/s"
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=50)
-    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--steps", type=int, default=1000)
+    p.add_argument("--warmup", type=int, default=20)
     p.add_argument("--impl", default="native", choices=["native", "reference"])
     p.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU (weak scaling)")
-    p.add_argument("--strict", action="store_true", help="use the strict-fp library (bit-reproduces the oracle)")
+    p.add_argument("--fast-fp", action="store_true", help="use the FMA-contracted twin library (not bit-exact vs the oracle)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     return p.parse_args()
 
@@ -136,8 +136,8 @@ def run_native(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    if args.strict:
-        os.environ["NB2_LIB"] = os.path.join(ROOT, "newton_b200", "libnewton_b200_strict.so")
+    if args.fast_fp:
+        os.environ["NB2_LIB"] = os.path.join(ROOT, "newton_b200", "libnewton_b200_fast.so")
 
     envs = args.envs
     # every rank owns `envs` worlds (weak scaling); per-rank seed so shards differ like slices of one big scene
@@ -171,8 +171,8 @@ def run_native(args):
 
     gathered_q = gathered_qd = None
     if world > 1:  # end-of-frame state gather over NVLink; part of every timed step
-        gathered_q = torch.empty((world, *state_0.body_q.shape), dtype=torch.float32, device=dev)
-        gathered_qd = torch.empty((world, *state_0.body_qd.shape), dtype=torch.float32, device=dev)
+        gathered_q = torch.empty((world * state_0.body_q.shape[0], 7), dtype=torch.float32, device=dev)
+        gathered_qd = torch.empty((world * state_0.body_qd.shape[0], 6), dtype=torch.float32, device=dev)
 
     def step_device():
         graph.replay()
@@ -273,7 +273,7 @@ def run_native(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(envs, world), "impl": "native",
-            "fp_mode": "strict" if args.strict else "fast",
+            "fp_mode": "fast(fma)" if args.fast_fp else "strict (bit-exact vs oracle)",
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches_per_step * args.steps),

@@ -10,7 +10,7 @@ def simulate(model, pipeline_cls, solver_cls, *, substeps, dt, solver_kwargs=Non
              record_contacts=False):
     """`collide -> step -> swap` loop exactly as the reference examples run it (example_basic_urdf.py:117-135)."""
     solver = solver_cls(model, **(solver_kwargs or {}))
-    pipe = pipeline_cls(model) if collide else None
+    pipe = pipeline_cls(model) if (collide and pipeline_cls is not None) else None
     s0, s1 = model.state(), model.state()
     ctrl = control if control is not None else model.control()
     contacts = pipe.contacts() if pipe is not None else None

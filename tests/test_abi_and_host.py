@@ -1,0 +1,123 @@
+"""CPU-only checks: the C-ABI library loads and exports every declared symbol, host-side model construction,
+world-range sharding (single process and 2-rank gloo), and that the product refuses to run without CUDA."""
+
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import newton_b200
+from newton_b200 import _abi, _lib, scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "newton_b200.h")).read()
+    declared = set(re.findall(r"\b(nb2_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    L = _lib.lib()
+    for sym in declared:
+        assert hasattr(L, sym), sym
+    assert b"sm_100a" in L.nb2_version()
+
+
+def test_abi_struct_matches_header_field_order():
+    header = open(os.path.join(ROOT, "include", "newton_b200.h")).read()
+    body = header.split("typedef struct nb2_model_desc {")[1].split("} nb2_model_desc;")[0]
+    body = re.sub(r"/[*].*?[*]/", "", body, flags=re.S)
+    names = re.findall(r"\b([A-Za-z_0-9]+)\s*;", body)
+    assert names == [n for n, _ in _abi.ModelDesc._fields_]
+
+
+def test_product_refuses_cpu_models():
+    m = scenes.quadruped_model(1, seed=None)
+    with pytest.raises(_lib.Nb2Error):
+        newton_b200.solvers.SolverXPBD(m)
+    with pytest.raises(_lib.Nb2Error):
+        newton_b200.CollisionPipeline(m)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "newton_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f
+
+
+def test_quadruped_model_layout():
+    m = scenes.quadruped_model(3, seed=None)
+    assert (m.body_count, m.joint_count, m.shape_count) == (39, 39, 40)
+    assert (m.joint_dof_count, m.joint_coord_count) == (54, 57)
+    assert m.shape_contact_pair_count == 39
+    np.testing.assert_array_equal(m.numpy("body_world_start"), [0, 13, 26, 39, 39])
+    np.testing.assert_array_equal(m.numpy("shape_world_start"), [0, 13, 26, 39, 40])
+    assert m.gravity.shape == (4, 3)
+    # base: cylinder r=0.1 len=0.75 at density 1000 -> m = pi r^2 L rho
+    assert m.body_mass[0].item() == pytest.approx(np.pi * 0.01 * 0.75 * 1000.0, rel=1e-6)
+    assert m.numpy("joint_type")[:3].tolist() == [4, 1, 1]
+    # HAA joints take the builder default target_kd, HFE/KFE declare damping 0 (quadruped.urdf <dynamics>)
+    assert m.numpy("joint_target_kd")[6:9].tolist() == [1.0, 0.0, 0.0]
+    assert m.body_q[0, 2].item() == pytest.approx(0.7)
+
+
+def test_shard_is_pure_slice():
+    m = scenes.quadruped_model(4, seed=7)
+    a, b = m.shard(0, 2), m.shard(1, 2)
+    assert a.world_count == b.world_count == 2 and a.body_count == 26 and a.shape_count == 27
+    np.testing.assert_array_equal(torch.cat([a.body_q, b.body_q]).numpy(), m.body_q.numpy())
+    np.testing.assert_array_equal(b.numpy("joint_child"), m.numpy("joint_child")[26:] - 26)
+    np.testing.assert_array_equal(b.numpy("shape_contact_pairs")[:, 1], 26)  # the replicated ground plane
+    assert b.numpy("shape_body")[-1] == -1
+
+
+def test_sharded_oracle_equals_monolithic(oracle_lib):
+    """Environments are independent: simulating shards separately must reproduce the monolithic run bit for bit."""
+    from tests.helpers import simulate
+
+    m = scenes.quadruped_model(4, seed=7)
+    m.joint_q.view(4, -1)[:, 2] = 0.48
+    newton_b200.eval_fk(m, m.joint_q, m.joint_qd, m)
+    kw = {"iterations": 3}
+    full, _, _ = simulate(m, oracle_lib.CollisionPipeline, oracle_lib.SolverXPBD, substeps=40, dt=0.005, solver_kwargs=kw)
+    parts = [simulate(m.shard(r, 2), oracle_lib.CollisionPipeline, oracle_lib.SolverXPBD, substeps=40, dt=0.005, solver_kwargs=kw)[0]
+             for r in range(2)]
+    np.testing.assert_array_equal(torch.cat([p.body_q for p in parts]).numpy(), full.body_q.numpy())
+    np.testing.assert_array_equal(torch.cat([p.body_qd for p in parts]).numpy(), full.body_qd.numpy())
+
+
+def test_two_rank_gloo_state_gather(tmp_path):
+    """N>1 path on CPU: 2 ranks each simulate their world shard with the oracle, then all_gather body_q (gloo)."""
+    script = tmp_path / "rank.py"
+    script.write_text(
+        "import os, sys, numpy as np, torch, torch.distributed as dist\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import newton_b200, oracle\n"
+        "from newton_b200 import scenes\n"
+        "from tests.helpers import simulate\n"
+        "dist.init_process_group('gloo')\n"
+        "r, w = dist.get_rank(), dist.get_world_size()\n"
+        "m = scenes.quadruped_model(4, seed=7)\n"
+        "m.joint_q.view(4, -1)[:, 2] = 0.48\n"
+        "newton_b200.eval_fk(m, m.joint_q, m.joint_qd, m)\n"
+        "kw = {'iterations': 2}\n"
+        "s, _, _ = simulate(m.shard(r, w), oracle.CollisionPipeline, oracle.SolverXPBD, substeps=20, dt=0.005, solver_kwargs=kw)\n"
+        "out = torch.empty((w * s.body_q.shape[0], 7))\n"
+        "dist.all_gather_into_tensor(out, s.body_q.contiguous())\n"
+        "if r == 0:\n"
+        "    full, _, _ = simulate(m, oracle.CollisionPipeline, oracle.SolverXPBD, substeps=20, dt=0.005, solver_kwargs=kw)\n"
+        "    assert np.array_equal(out.reshape(-1, 7).numpy(), full.body_q.numpy())\n"
+        "    print('GATHER_OK')\n"
+        "dist.destroy_process_group()\n"
+    )
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", str(script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert "GATHER_OK" in out.stdout

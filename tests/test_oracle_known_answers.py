@@ -1,0 +1,233 @@
+"""Pins the CPU oracle against the known-answer checks the REFERENCE's own tests hold for this path.
+
+The reference ships no golden files for collision / XPBD; what it does hold are
+closed-form expectation tables and example end-state assertions.  Those are restated here with citations:
+
+* analytic collider tables   - newton/tests/test_collision_primitives.py:429-1500 (distance to 1e-5)
+* example_basic_urdf final   - newton/examples/basic/example_basic_urdf.py:145-161 via tests/test_examples.py:349-357
+* free fall                  - newton/tests/test_physics_verification.py (semi-implicit Euler closed form)
+"""
+
+import math
+
+import numpy as np
+import pytest
+
+from newton_b200 import GeoType, scenes
+from newton_b200.sim.builder import ModelBuilder
+from newton_b200.utils import xform as X
+
+I7 = [0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0]
+
+
+def _xf(p, q=(0.0, 0.0, 0.0, 1.0)):
+    return [*p, *q]
+
+
+def _plane_xf(normal, pos):
+    return _xf(pos, X.quat_between_vectors((0.0, 0.0, 1.0), normal))
+
+
+def _axis_q(axis):
+    return X.quat_between_vectors((0.0, 0.0, 1.0), axis)
+
+
+# reference test_collision_primitives.py:436-447
+PLANE_SPHERE = [
+    ([0, 0, 1], [0, 0, 0], [0, 0, 2.0], 1.0, 1.0), ([0, 0, 1], [0, 0, 0], [0, 0, 1.5], 1.0, 0.5),
+    ([0, 0, 1], [0, 0, 0], [0, 0, 1.0], 1.0, 0.0), ([0, 0, 1], [0, 0, 0], [0, 0, 0.8], 1.0, -0.2),
+    ([0, 0, 1], [0, 0, 0], [0, 0, 0.5], 1.0, -0.5), ([0, 0, 1], [0, 0, 0], [0, 0, 0.2], 1.0, -0.8),
+    ([1, 0, 0], [1, 0, 0], [2.0, 0, 0], 0.5, 0.5), ([1, 0, 0], [1, 0, 0], [1.5, 0, 0], 0.5, 0.0),
+    ([1, 0, 0], [1, 0, 0], [1.3, 0, 0], 0.5, -0.2),
+]
+
+
+@pytest.mark.parametrize("n,pp,sp,r,expected", PLANE_SPHERE)
+def test_plane_sphere(oracle_lib, n, pp, sp, r, expected):
+    ok, dist, pos, normal = oracle_lib.primitive_pair(GeoType.PLANE, (0, 0, 0), _plane_xf(n, pp), GeoType.SPHERE, (r, 0, 0), _xf(sp))
+    assert ok
+    assert dist[0] == pytest.approx(expected, abs=1e-5)
+    np.testing.assert_allclose(normal, n, atol=1e-6)
+    if expected < 0:  # contact lies between the sphere surface and the plane (reference :470-497)
+        assert np.linalg.norm(pos[0] - np.array(sp)) < r + 0.01
+
+
+# reference test_collision_primitives.py:512-527
+SPHERE_SPHERE = [
+    ([0, 0, 0], 1.0, [3.5, 0, 0], 1.0, 1.5), ([0, 0, 0], 1.0, [3.0, 0, 0], 1.0, 1.0), ([0, 0, 0], 1.0, [2.5, 0, 0], 1.0, 0.5),
+    ([0, 0, 0], 1.0, [2.0, 0, 0], 1.0, 0.0), ([0, 0, 0], 1.0, [1.8, 0, 0], 1.0, -0.2), ([0, 0, 0], 1.0, [1.5, 0, 0], 1.0, -0.5),
+    ([0, 0, 0], 1.0, [1.2, 0, 0], 1.0, -0.8), ([0, 0, 0], 0.5, [2.0, 0, 0], 1.0, 0.5), ([0, 0, 0], 0.5, [1.5, 0, 0], 1.0, 0.0),
+    ([0, 0, 0], 0.5, [1.2, 0, 0], 1.0, -0.3),
+]
+
+
+@pytest.mark.parametrize("p1,r1,p2,r2,expected", SPHERE_SPHERE)
+def test_sphere_sphere(oracle_lib, p1, r1, p2, r2, expected):
+    ok, dist, pos, normal = oracle_lib.primitive_pair(GeoType.SPHERE, (r1, 0, 0), _xf(p1), GeoType.SPHERE, (r2, 0, 0), _xf(p2))
+    assert ok
+    assert dist[0] == pytest.approx(expected, abs=1e-5)
+    assert np.linalg.norm(normal) == pytest.approx(1.0, abs=1e-5)
+    assert np.dot(normal, np.array(p2) - np.array(p1)) > 0  # points from geom 0 into geom 1
+    # contact position is the midpoint between the two surfaces (reference :570-585)
+    a = np.array(p1) + normal * r1
+    b = np.array(p2) - normal * r2
+    np.testing.assert_allclose(pos[0], 0.5 * (a + b), atol=1e-5)
+
+
+# reference test_collision_primitives.py:601-612 (capsule at origin, axis Z, r=0.5, half-length 1; sphere r=0.5)
+SPHERE_CAPSULE = [([0, 1.5, 0], 0.5), ([0, 1.0, 0], 0.0), ([0, 0.9, 0], -0.1), ([0, 0.8, 0], -0.2),
+                  ([0, 0, 2.5], 0.5), ([0, 0, 2.0], 0.0), ([0, 0, 1.9], -0.1), ([0, 0, 1.8], -0.2)]
+
+
+@pytest.mark.parametrize("sp,expected", SPHERE_CAPSULE)
+def test_sphere_capsule(oracle_lib, sp, expected):
+    ok, dist, _, normal = oracle_lib.primitive_pair(GeoType.SPHERE, (0.5, 0, 0), _xf(sp), GeoType.CAPSULE, (0.5, 1.0, 0), I7)
+    assert ok
+    assert dist[0] == pytest.approx(expected, abs=1e-5)
+
+
+# reference test_collision_primitives.py:712-790 (parallel capsules along X, r=0.5, half-length 1)
+@pytest.mark.parametrize("y,expected", [(2.0, 1.0), (1.5, 0.5), (1.0, 0.0), (0.9, -0.1), (0.8, -0.2), (0.7, -0.3)])
+def test_capsule_capsule_parallel(oracle_lib, y, expected):
+    q = _axis_q((1.0, 0.0, 0.0))
+    ok, dist, _, normal = oracle_lib.primitive_pair(GeoType.CAPSULE, (0.5, 1.0, 0), _xf((0, 0, 0), q), GeoType.CAPSULE,
+                                                    (0.5, 1.0, 0), _xf((0, y, 0), q))
+    assert ok
+    assert dist[0] == pytest.approx(expected, abs=1e-4)
+    assert dist[1] == pytest.approx(expected, abs=1e-4)  # parallel axes produce two contacts
+    np.testing.assert_allclose(normal, [0, 1, 0], atol=1e-4)
+
+
+# reference test_collision_primitives.py:904-913 (ellipsoid half-axes (1,1,1.5))
+@pytest.mark.parametrize("z,expected", [(2.5, 1.0), (2.0, 0.5), (1.5, 0.0), (1.4, -0.1), (1.3, -0.2), (1.0, -0.5)])
+def test_plane_ellipsoid(oracle_lib, z, expected):
+    ok, dist, _, normal = oracle_lib.primitive_pair(GeoType.PLANE, (0, 0, 0), I7, GeoType.ELLIPSOID, (1.0, 1.0, 1.5), _xf((0, 0, z)))
+    assert ok
+    assert dist[0] == pytest.approx(expected, abs=1e-5)
+
+
+# reference test_collision_primitives.py:978-1060 (cylinder r=1, half-height 1 along Z; sphere r=0.5)
+@pytest.mark.parametrize("sp,expected", [([2.0, 0, 0], 0.5), ([1.5, 0, 0], 0.0), ([1.4, 0, 0], -0.1), ([1.3, 0, 0], -0.2),
+                                         ([0, 0, 2.0], 0.5), ([0, 0, 1.5], 0.0), ([0, 0, 1.4], -0.1)])
+def test_sphere_cylinder(oracle_lib, sp, expected):
+    ok, dist, _, _ = oracle_lib.primitive_pair(GeoType.SPHERE, (0.5, 0, 0), _xf(sp), GeoType.CYLINDER, (1.0, 1.0, 0.0), I7)
+    assert ok
+    assert dist[0] == pytest.approx(expected, abs=1e-5)
+
+
+# reference test_collision_primitives.py:1149-1165 (unit half-extent box at origin)
+SPHERE_BOX = [([2.5, 0, 0], 0.5, 1.0), ([2.0, 0, 0], 0.5, 0.5), ([1.5, 0, 0], 0.5, 0.0), ([1.4, 0, 0], 0.5, -0.1),
+              ([1.3, 0, 0], 0.5, -0.2), ([1.2, 0, 0], 0.5, -0.3), ([0, 0, 2.0], 0.5, 0.5), ([0, 0, 1.5], 0.5, 0.0),
+              ([0, 0, 1.3], 0.5, -0.2), ([0, 0, 0.4], 0.3, -0.9)]
+
+
+@pytest.mark.parametrize("sp,r,expected", SPHERE_BOX)
+def test_sphere_box(oracle_lib, sp, r, expected):
+    ok, dist, _, _ = oracle_lib.primitive_pair(GeoType.SPHERE, (r, 0, 0), _xf(sp), GeoType.BOX, (1.0, 1.0, 1.0), I7)
+    assert ok
+    assert dist[0] == pytest.approx(expected, abs=1e-5)
+
+
+# reference test_collision_primitives.py:1265-1274 (horizontal capsule r=0.5, half-length 1)
+@pytest.mark.parametrize("z,expected", [(2.0, 1.5), (1.5, 1.0), (1.0, 0.5), (0.5, 0.0), (0.4, -0.1), (0.3, -0.2), (0.2, -0.3)])
+def test_plane_capsule(oracle_lib, z, expected):
+    ok, dist, pos, _ = oracle_lib.primitive_pair(GeoType.PLANE, (0, 0, 0), I7, GeoType.CAPSULE, (0.5, 1.0, 0),
+                                                 _xf((0, 0, z), _axis_q((1.0, 0.0, 0.0))))
+    assert ok
+    assert dist[0] == pytest.approx(expected, abs=1e-5) and dist[1] == pytest.approx(expected, abs=1e-5)
+    assert abs(abs(pos[0][0]) - 1.0) < 1e-5 and pos[0][0] * pos[1][0] < 0  # one contact under each end cap
+
+
+# reference test_collision_primitives.py:1349-1360 (unit box): (center z, expected contact count, expected distance)
+@pytest.mark.parametrize("z,count,expected", [(2.0, 0, 1.0), (1.0, 4, 0.0), (0.9, 4, -0.1), (0.8, 4, -0.2), (0.7, 4, -0.3), (0.5, 4, -0.5)])
+def test_plane_box(oracle_lib, z, count, expected):
+    ok, dist, pos, _ = oracle_lib.primitive_pair(GeoType.PLANE, (0, 0, 0), I7, GeoType.BOX, (1.0, 1.0, 1.0), _xf((0, 0, z)),
+                                                 plane_box_margin=0.0)
+    assert ok
+    valid = dist < 1e9
+    assert int(valid.sum()) == count
+    for d in dist[valid]:
+        assert d == pytest.approx(expected, abs=1e-5)
+
+
+# plane-cylinder: upright cylinder (flat mode: deepest rim point + fixed tripod), reference collision_primitive.py:534-683,
+# expectations in the style of test_collision_primitives.py:1444-1470 (lowest rim point = center_z - half_height)
+@pytest.mark.parametrize("z", [2.0, 1.0, 0.9, 0.6])
+def test_plane_cylinder_upright(oracle_lib, z):
+    ok, dist, pos, normal = oracle_lib.primitive_pair(GeoType.PLANE, (0, 0, 0), I7, GeoType.CYLINDER, (0.5, 1.0, 0.0), _xf((0, 0, z)))
+    assert ok
+    valid = dist < 1e9
+    assert int(valid.sum()) == 3  # one tripod point coincides with the "deepest" point and is merged
+    for d in dist[valid]:
+        assert d == pytest.approx(z - 1.0, abs=1e-5)
+    r = np.linalg.norm(pos[valid][:, :2], axis=1)
+    np.testing.assert_allclose(r, 0.5, atol=1e-5)  # contacts sit on the cap rim
+
+
+def test_plane_cylinder_rolling(oracle_lib):
+    """Cylinder lying on its side: deepest generator end + opposite end + one cap-rim point (rolling mode)."""
+    ok, dist, pos, _ = oracle_lib.primitive_pair(GeoType.PLANE, (0, 0, 0), I7, GeoType.CYLINDER, (0.5, 1.0, 0.0),
+                                                 _xf((0, 0, 0.45), _axis_q((1.0, 0.0, 0.0))))
+    assert ok
+    valid = dist < 1e9
+    assert int(valid.sum()) >= 2
+    assert dist[0] == pytest.approx(-0.05, abs=1e-5) and dist[1] == pytest.approx(-0.05, abs=1e-5)
+    assert abs(pos[0][0] - pos[1][0]) == pytest.approx(2.0, abs=1e-5)  # the two ends of the contact generator
+
+
+def test_example_basic_urdf_final_state(oracle_lib):
+    """The reference example's own end-state assertion (example_basic_urdf.py:145-161; 200 frames x 10 substeps,
+    SolverXPBD defaults): every link slower than 0.15, every root within 0.01 of z = 0.46."""
+    worlds = 4
+    model = scenes.quadruped_model(worlds, seed=None)
+    pipe = oracle_lib.CollisionPipeline(model)
+    solver = oracle_lib.SolverXPBD(model)
+    s0, s1, ctrl, contacts = model.state(), model.state(), model.control(), pipe.contacts()
+    dt = 1.0 / 100 / 10
+    for _ in range(200 * 10):
+        s0.clear_forces()
+        pipe.collide(s0, contacts)
+        solver.step(s0, s1, ctrl, contacts, dt)
+        s0, s1 = s1, s0
+    q, qd = s0.body_q.numpy(), s0.body_qd.numpy()
+    assert np.abs(qd).max() < 0.15
+    per = model.body_count // worlds
+    for w in range(worlds):
+        assert abs(q[w * per, 2] - 0.46) < 0.01
+
+
+def test_free_fall_matches_semi_implicit_closed_form(oracle_lib):
+    """A free body under gravity: v_n = g n dt, z_n = z_0 + g dt^2 n(n+1)/2 (semi-implicit Euler, solver.py:64-107)."""
+    b = ModelBuilder()
+    body = b.add_body(xform=X.transform((0.0, 0.0, 10.0)))
+    b.add_shape_sphere(body, radius=0.1)
+    model = b.finalize()
+    solver = oracle_lib.SolverXPBD(model, iterations=1)
+    s0, s1 = model.state(), model.state()
+    dt, n = 1e-3, 200
+    for _ in range(n):
+        s0.clear_forces()
+        solver.step(s0, s1, None, None, dt)
+        s0, s1 = s1, s0
+    g = -9.81
+    assert s0.body_qd[0, 2].item() == pytest.approx(g * n * dt, rel=1e-5)
+    assert s0.body_q[0, 2].item() == pytest.approx(10.0 + g * dt * dt * n * (n + 1) / 2, rel=1e-6)
+
+
+def test_sphere_rests_on_ground(oracle_lib):
+    """Sphere dropped on the plane settles at z = radius (reference tests/test_rigid_contact.py shapes-on-plane)."""
+    b = ModelBuilder()
+    body = b.add_body(xform=X.transform((0.0, 0.0, 0.6)))
+    b.add_shape_sphere(body, radius=0.5)
+    b.add_ground_plane()
+    model = b.finalize()
+    pipe = oracle_lib.CollisionPipeline(model)
+    solver = oracle_lib.SolverXPBD(model, iterations=4)
+    s0, s1, contacts = model.state(), model.state(), pipe.contacts()
+    for _ in range(600):
+        s0.clear_forces()
+        pipe.collide(s0, contacts)
+        solver.step(s0, s1, None, contacts, 1.0 / 600)
+        s0, s1 = s1, s0
+    assert s0.body_q[0, 2].item() == pytest.approx(0.5, abs=2e-3)
+    assert abs(s0.body_qd[0, 2].item()) < 1e-2
