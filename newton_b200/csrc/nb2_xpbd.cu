@@ -408,7 +408,7 @@ NB2_DEV void apply_delta(float* rec, V3 dlin, V3 dang, float inv_weight, bool we
 }
 
 template <int L>
-__global__ void __launch_bounds__(32) xpbd_step_kernel(DevModel M, nb2_xpbd_params P, nb2_state_view sin, nb2_state_view sout,
+__global__ void __launch_bounds__(32, 16) xpbd_step_kernel(DevModel M, nb2_xpbd_params P, nb2_state_view sin, nb2_state_view sout,
                                                         nb2_control_view ctl, int use_contacts, float dt) {
     constexpr int G = 32 / L;
     extern __shared__ float smem[];
@@ -691,6 +691,9 @@ static nb2_status launch_xpbd_L(nb2_model* m, const nb2_xpbd_params& p, const nb
     }
     if (smem > 48 * 1024)
         NB2_CUDA_CHECK(cudaFuncSetAttribute(xpbd_step_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    // one-warp CTAs: ask for the largest shared-memory carve-out so ~16 CTAs (one wave of 4096 envs on 148 SMs) fit per SM
+    NB2_CUDA_CHECK(cudaFuncSetAttribute(xpbd_step_kernel<L>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
     xpbd_step_kernel<L><<<blocks, 32, smem, s>>>(M, p, in, out, ctl, use_contacts, dt);
     count_launch();
     NB2_CUDA_CHECK(cudaGetLastError());
