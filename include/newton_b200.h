@@ -80,6 +80,7 @@ typedef struct nb2_model_desc {
     const float* joint_target_ke;
     const float* joint_target_kd;
     const float* joint_armature;
+    const float* joint_damping;
     /* articulations */
     const int32_t* articulation_start; /* [articulation_count + 1] */
     /* shapes [shape_count] */

@@ -75,6 +75,7 @@ class ModelDesc(C.Structure):
         ("joint_target_ke", C.c_void_p),
         ("joint_target_kd", C.c_void_p),
         ("joint_armature", C.c_void_p),
+        ("joint_damping", C.c_void_p),
         ("articulation_start", C.c_void_p),
         ("shape_body", C.c_void_p),
         ("shape_type", C.c_void_p),

@@ -182,6 +182,76 @@ static nb2_status build_tables(nb2_model* m, const nb2_model_desc& d) {
             }
         }
     }
+    // ---- articulation tables for the Featherstone kernel ----------------------------------------
+    {
+        std::vector<int> janc, jqd, bflags;
+        if ((st = fetch(d.joint_ancestor, size_t(J), janc))) return st;
+        if ((st = fetch(d.body_flags, size_t(B), bflags))) return st;
+        for (int b = 0; b < B; ++b)
+            if (bflags[b] & 2) {
+                h.featherstone_supported = false;
+                h.featherstone_reason = "kinematic bodies";
+            }
+        for (int j = 0; j < J; ++j)
+            if (jchild[j] != j) {  // the reference's spatial_mass indexes body_I_s by joint index (kernels.py:1476-1477)
+                h.featherstone_supported = false;
+                h.featherstone_reason = "joint j must drive body j (the reference mass matrix assumes body index == joint index)";
+            }
+        if ((st = fetch(d.joint_qd_start, size_t(J) + 1, jqd))) return st;
+        h.joint_depth.assign(size_t(J), 0);
+        h.joint_anc_mask.assign(size_t(J), 0ull);
+        h.art_H_start.assign(size_t(d.articulation_count) + 1, 0);
+        h.env_H_start.assign(size_t(E) + 1, 0);
+        int max_depth = 0;
+        for (int a = 0; a < d.articulation_count; ++a) {
+            const int j0 = art_start[a], j1 = art_start[a + 1];
+            if (j1 - j0 > 64) {
+                h.featherstone_supported = false;
+                h.featherstone_reason = "articulations with more than 64 joints";
+            }
+            for (int j = j0; j < j1; ++j) {
+                int anc = janc[j];
+                if (anc >= j || (anc >= 0 && anc < j0)) {
+                    h.featherstone_supported = false;
+                    h.featherstone_reason = "joints must be stored parent-before-child inside their articulation";
+                    anc = -1;
+                }
+                h.joint_depth[j] = anc >= 0 ? h.joint_depth[anc] + 1 : 0;
+                h.joint_anc_mask[j] = (anc >= 0 ? h.joint_anc_mask[anc] : 0ull) | (1ull << ((j - j0) & 63));
+                max_depth = std::max(max_depth, h.joint_depth[j]);
+                if (jart[j] != a) {
+                    h.featherstone_supported = false;
+                    h.featherstone_reason = "joints outside an articulation";
+                }
+            }
+        }
+        int e = 0, max_env_H = 0, max_env_arts = 0;
+        for (int ee = 0; ee < E; ++ee) {
+            int acc = 0;
+            for (int a = h.env_art_start[ee]; a < h.env_art_start[ee + 1]; ++a) {
+                h.art_H_start[a] = acc;
+                int nd = jqd[art_start[a + 1]] - jqd[art_start[a]];
+                acc += nd * nd;
+            }
+            h.env_H_start[ee + 1] = h.env_H_start[ee] + acc;
+            max_env_H = std::max(max_env_H, acc);
+            max_env_arts = std::max(max_env_arts, h.env_art_start[ee + 1] - h.env_art_start[ee]);
+        }
+        (void)e;
+        m->dev.max_depth = max_depth;
+        m->dev.max_env_H = max_env_H;
+        m->dev.max_env_arts = max_env_arts;
+        int max_dofs = 0, max_coords = 0;
+        std::vector<int> jq;
+        if ((st = fetch(d.joint_q_start, size_t(J) + 1, jq))) return st;
+        for (int ee = 0; ee < E; ++ee) {
+            int ja = h.env_joint_start[ee], jb = h.env_joint_start[ee + 1];
+            max_dofs = std::max(max_dofs, jqd[jb] - jqd[ja]);
+            max_coords = std::max(max_coords, jq[jb] - jq[ja]);
+        }
+        m->dev.max_env_dofs = max_dofs;
+        m->dev.max_env_coords = max_coords;
+    }
     DevModel& dv = m->dev;
     dv.d = d;
     dv.env_count = E;
@@ -220,7 +290,18 @@ static nb2_status upload_tables(nb2_model* m) {
     if ((st = upload(m, h.pairs, &dv.pairs))) return st;
     if ((st = upload(m, h.body_joint_start, &dv.body_joint_start))) return st;
     if ((st = upload(m, h.body_joint_entry, &dv.body_joint_entry))) return st;
+    if ((st = upload(m, h.joint_depth, &dv.joint_depth))) return st;
+    if ((st = upload(m, h.joint_anc_mask, &dv.joint_anc_mask))) return st;
+    if ((st = upload(m, h.art_H_start, &dv.art_H_start))) return st;
+    if ((st = upload(m, h.env_H_start, &dv.env_H_start))) return st;
     void* p = nullptr;
+    {
+        size_t nL = std::max<size_t>(size_t(h.env_H_start.back()), 1);
+        NB2_CUDA_CHECK(cudaMalloc(&p, nL * sizeof(float)));
+        NB2_CUDA_CHECK(cudaMemset(p, 0, nL * sizeof(float)));
+        m->allocations.push_back(p);
+        dv.fs_L = static_cast<float*>(p);
+    }
     size_t cb_bytes = std::max<size_t>(size_t(dv.slot_total) * CF_COUNT, 1) * sizeof(float);
     NB2_CUDA_CHECK(cudaMalloc(&p, cb_bytes));
     NB2_CUDA_CHECK(cudaMemset(p, 0, cb_bytes));

@@ -1,13 +1,808 @@
-// nb2_featherstone.cu - placeholder until the Featherstone milestone lands.
+// nb2_featherstone.cu - fused articulated-body step for sm_100a (reference SolverFeatherstone.step,
+// solvers/featherstone/solver_featherstone.py:461-1066; kernels in solvers/featherstone/kernels.py).
+//
+// The reference spends ~16 launches per substep, walks every articulation with ONE thread (FK, RNEA forward /
+// backward), materialises a dense 6nj x 6nj mass matrix M (97 % zeros) plus J and P = M J in HBM and multiplies
+// them with one thread per articulation (kernels.py:1504-1538: 78x78x18 serial MACs).  Here one launch does the
+// whole step; a sub-warp group of L lanes owns one environment and keeps every intermediate in shared memory:
+//
+//   eval_rigid_fk                  :687-728     joint lanes, level by level (joints of equal tree depth in parallel)
+//   public->internal qd / joint_f  :924-975, :1069-1088, :893-921
+//   eval_rigid_id (RNEA forward)   :1241-1317   level-parallel; spatial inertia T^T I T by blocks (T = [[R,S],[0,R]])
+//   eval_body_contact (penalty)    semi_implicit/kernels_contact.py:381-556   body lanes, ordered by contact index
+//   eval_rigid_tau (RNEA backward) :1320-1418   level-parallel, children folded into the parent in descending joint order
+//   H = J^T M J                    :1422-1501, :1655-1687   never forms M, J or P: H[a][b] = sum over the joints i below
+//                                  both dofs of S_a . (I_s[i] S_b), accumulated in the reference's k-order
+//   dense_cholesky / dense_subs    :1690-1781   column-parallel factorisation, serial substitutions (order-preserving)
+//   integrate_generalized_joints   :1849-1893 (jcalc_integrate :464-630)
+//   eval_fk_with_velocity_conversion :1987-2149, internal->public qd :1015-1066
+//
+// Every sum is taken in the order of the reference's serial loops (structural zeros skipped, which is exact), so the
+// strict-fp build reproduces the CPU oracle bit for bit.  Tensor cores (north_star: "only for the small dense
+// mass-matrix factor/solve") would need TF32 or 3xTF32 splits and cannot meet bit-parity; with H at 18x18 the stage is
+// ~9 k MACs per env, latency- not throughput-bound, so it stays on the FP32 pipe.
 #include "nb2_internal.cuh"
+#include "nb2_math.cuh"
+
 namespace nb2 {
-nb2_status launch_featherstone_step(nb2_model*, const nb2_featherstone_params&, const nb2_state_view&, const nb2_state_view&,
-                                    const nb2_control_view&, int, float, cudaStream_t) {
-    set_error("nb2_featherstone_step: not implemented yet");
-    return NB2_ERR_UNSUPPORTED;
+
+enum { FJ_PRISMATIC = 0, FJ_REVOLUTE = 1, FJ_BALL = 2, FJ_FIXED = 3, FJ_FREE = 4, FJ_DISTANCE = 5, FJ_D6 = 6 };
+
+struct S6 {
+    float v[6];
+    NB2_DEV S6() {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) v[i] = 0.f;
+    }
+    NB2_DEV S6(V3 a, V3 b) { v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = b.x; v[4] = b.y; v[5] = b.z; }
+    NB2_DEV V3 top() const { return V3(v[0], v[1], v[2]); }
+    NB2_DEV V3 bot() const { return V3(v[3], v[4], v[5]); }
+};
+NB2_DEV S6 ld6(const float* p) {
+    S6 s;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s.v[i] = p[i];
+    return s;
 }
+NB2_DEV void st6(float* p, const S6& s) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) p[i] = s.v[i];
+}
+NB2_DEV S6 operator+(const S6& a, const S6& b) {
+    S6 r;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) r.v[i] = a.v[i] + b.v[i];
+    return r;
+}
+NB2_DEV S6 operator-(const S6& a, const S6& b) {
+    S6 r;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) r.v[i] = a.v[i] - b.v[i];
+    return r;
+}
+NB2_DEV S6 operator*(const S6& a, float s) {
+    S6 r;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) r.v[i] = a.v[i] * s;
+    return r;
+}
+NB2_DEV float dot6(const S6& a, const S6& b) {
+    return a.v[0] * b.v[0] + a.v[1] * b.v[1] + a.v[2] * b.v[2] + a.v[3] * b.v[3] + a.v[4] * b.v[4] + a.v[5] * b.v[5];
+}
+NB2_DEV S6 twist_xf(const Xf& t, const S6& x) {  // math/spatial.py:82-105
+    V3 w = qrot(t.q, x.bot());
+    V3 v = qrot(t.q, x.top()) + cross(t.p, w);
+    return S6(v, w);
+}
+NB2_DEV S6 scross(const S6& a, const S6& b) {
+    V3 w = cross(a.bot(), b.bot());
+    V3 v = cross(a.bot(), b.top()) + cross(a.top(), b.bot());
+    return S6(v, w);
+}
+NB2_DEV S6 scross_dual(const S6& a, const S6& b) {
+    V3 w = cross(a.bot(), b.bot()) + cross(a.top(), b.top());
+    V3 v = cross(a.bot(), b.top());
+    return S6(v, w);
+}
+NB2_DEV S6 m66v(const float* I, const S6& b) {  // dense 6x6 (row-major in shared memory) times vector, column order
+    S6 r;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) r.v[i] = I[6 * i] * b.v[0];
+#pragma unroll
+    for (int c = 1; c < 6; ++c)
+#pragma unroll
+        for (int i = 0; i < 6; ++i) r.v[i] += I[6 * i + c] * b.v[c];
+    return r;
+}
+NB2_DEV Q4 q_axis_angle(V3 axis, float angle) {
+    float half = angle * 0.5f;
+    float w = cos_w(half), s = sin_w(half);
+    V3 v = axis * s;
+    return Q4(v.x, v.y, v.z, w);
+}
+
+// transform_spatial_inertia (kernels.py:66-138) for I = blockdiag(m 1, Ic): T^T I T with T = [[R, S], [0, R]],
+// R / S from the inverse transform.  Sums follow the dense k-order of the reference with structural zeros dropped.
+NB2_DEV void spatial_inertia(const Xf& t, float mass, const M33& Ic, float* out) {
+    const Xf ti = xinv(t);
+    const M33 R = qmat(ti.q);
+    const V3 p = ti.p;
+    M33 S;  // skew(p) @ R
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        S.a[0 + j] = (-p.z) * R.a[3 + j] + p.y * R.a[6 + j];
+        S.a[3 + j] = p.z * R.a[0 + j] + (-p.x) * R.a[6 + j];
+        S.a[6 + j] = (-p.y) * R.a[0 + j] + p.x * R.a[3 + j];
+    }
+    float A[6][6];  // A = T^T I
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            A[i][j] = R.a[3 * j + i] * mass;
+            A[i][j + 3] = 0.0f;
+            A[i + 3][j] = S.a[3 * j + i] * mass;
+            float s = R.a[0 + i] * Ic.a[0 + j];
+            s += R.a[3 + i] * Ic.a[3 + j];
+            s += R.a[6 + i] * Ic.a[6 + j];
+            A[i + 3][j + 3] = s;
+        }
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            float s = A[i][0] * R.a[0 + j];
+            s += A[i][1] * R.a[3 + j];
+            s += A[i][2] * R.a[6 + j];
+            out[6 * i + j] = s;
+            float u = A[i][0] * S.a[0 + j];
+            u += A[i][1] * S.a[3 + j];
+            u += A[i][2] * S.a[6 + j];
+            if (i >= 3) {
+                u += A[i][3] * R.a[0 + j];
+                u += A[i][4] * R.a[3 + j];
+                u += A[i][5] * R.a[6 + j];
+            }
+            out[6 * i + j + 3] = u;
+        }
+}
+
+NB2_DEV float joint_force(float q, float qd, float tq, float tqd, float ke, float kd, float lo, float up, float lke, float lkd, float damping) {
+    float limit_f = 0.0f, damping_f = 0.0f;
+    float target_f = ke * (tq - q) + kd * (tqd - qd);
+    if (q < lo) {
+        limit_f = lke * (lo - q);
+        damping_f = -lkd * qd;
+        target_f = 0.0f;
+    } else if (q > up) {
+        limit_f = lke * (up - q);
+        damping_f = -lkd * qd;
+        target_f = 0.0f;
+    }
+    float passive_f = -damping * qd;
+    return limit_f + damping_f + target_f + passive_f;
+}
+
+NB2_DEV void axes3(V3 a0, V3 a1, V3 a2, float q0, float q1, V3& o0, V3& o1, V3& o2) {  // transform_3d_rotational_axes
+    Q4 q_0 = q_axis_angle(a0, q0);
+    V3 a1w = qrot(q_0, a1);
+    Q4 q_1 = q_axis_angle(a1w, q1);
+    V3 a2w = qrot(qmul(q_1, q_0), a2);
+    o0 = a0; o1 = a1w; o2 = a2w;
+}
+
+// jcalc_transform (kernels.py:142-238)
+NB2_DEV Xf joint_transform(const nb2_model_desc& d, int type, int axis_start, int lin, int ang, const float* jq, int qs) {
+    if (type == FJ_PRISMATIC) return Xf(ld3(d.joint_axis + 3 * axis_start) * jq[qs], Q4());
+    if (type == FJ_REVOLUTE) return Xf(V3(), q_axis_angle(ld3(d.joint_axis + 3 * axis_start), jq[qs]));
+    if (type == FJ_BALL) return Xf(V3(), Q4(jq[qs], jq[qs + 1], jq[qs + 2], jq[qs + 3]));
+    if (type == FJ_FREE || type == FJ_DISTANCE) return Xf(V3(jq[qs], jq[qs + 1], jq[qs + 2]), Q4(jq[qs + 3], jq[qs + 4], jq[qs + 5], jq[qs + 6]));
+    if (type == FJ_D6) {
+        V3 pos;
+        Q4 rot;
+        for (int k = 0; k < 3; ++k)
+            if (lin > k) pos += ld3(d.joint_axis + 3 * (axis_start + k)) * jq[qs + k];
+        const int ia = axis_start + lin, iq = qs + lin;
+        if (ang == 1) rot = q_axis_angle(ld3(d.joint_axis + 3 * ia), jq[iq]);
+        if (ang == 3) {
+            V3 w0, w1, w2;
+            axes3(ld3(d.joint_axis + 3 * ia), ld3(d.joint_axis + 3 * (ia + 1)), ld3(d.joint_axis + 3 * (ia + 2)), jq[iq], jq[iq + 1], w0, w1, w2);
+            rot = qmul(qmul(q_axis_angle(w2, jq[iq + 2]), q_axis_angle(w1, jq[iq + 1])), q_axis_angle(w0, jq[iq]));
+        }
+        return Xf(pos, rot);
+    }
+    return Xf();
+}
+
+struct FsSmem {
+    float *bq, *bqc, *vs, *as, *fb, *ft, *fe, *qdfk, *Is, *so, *fs, *S, *qd_in, *jf, *tau, *qdd, *qd_out, *H, *jq;
+};
+NB2_DEV size_t fs_smem_floats(const DevModel& M) {
+    return size_t(M.max_env_bodies) * (7 + 7 + 6 * 6 + 36 + 3) + size_t(M.max_env_joints) * 6 + size_t(M.max_env_dofs) * (6 + 5) +
+           size_t(M.max_env_H) + size_t(M.max_env_coords);
+}
+NB2_DEV FsSmem fs_carve(float* base, const DevModel& M) {
+    FsSmem s;
+    const int nb = M.max_env_bodies, nj = M.max_env_joints, nd = M.max_env_dofs;
+    float* p = base;
+    s.bq = p; p += nb * 7;
+    s.bqc = p; p += nb * 7;
+    s.vs = p; p += nb * 6;
+    s.as = p; p += nb * 6;
+    s.fb = p; p += nb * 6;
+    s.ft = p; p += nb * 6;
+    s.fe = p; p += nb * 6;
+    s.qdfk = p; p += nb * 6;
+    s.Is = p; p += nb * 36;
+    s.so = p; p += nb * 3;
+    s.fs = p; p += nj * 6;
+    s.S = p; p += nd * 6;
+    s.qd_in = p; p += nd;
+    s.jf = p; p += nd;
+    s.tau = p; p += nd;
+    s.qdd = p; p += nd;
+    s.qd_out = p; p += nd;
+    s.H = p; p += M.max_env_H;
+    s.jq = p;
+    return s;
+}
+
+template <int L>
+__global__ void __launch_bounds__(32, 12) featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view sin, nb2_state_view sout,
+                                                                    nb2_control_view ctl, int use_contacts, int update_mass, float dt) {
+    constexpr int G = 32 / L;
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31;
+    const int grp = lane / L, l = lane % L;
+    const int env = blockIdx.x * G + grp;
+    const bool live = env < M.env_count;
+    // groups run different trip counts (articulations / dofs per env), so barriers cover one group only
+    const unsigned gmask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << (grp * L));
+    const nb2_model_desc& d = M.d;
+    const FsSmem sm = fs_carve(smem + size_t(grp) * fs_smem_floats(M), M);
+
+    int b0 = 0, nb = 0, j0 = 0, nj = 0, a0 = 0, na = 0, d0 = 0, nd = 0, c0 = 0, ncoord = 0, slot0 = 0, nc = 0;
+    if (live) {
+        b0 = M.env_body_start[env];
+        nb = M.env_body_start[env + 1] - b0;
+        j0 = M.env_joint_start[env];
+        nj = M.env_joint_start[env + 1] - j0;
+        a0 = M.env_art_start[env];
+        na = M.env_art_start[env + 1] - a0;
+        d0 = d.joint_qd_start[j0];
+        nd = d.joint_qd_start[j0 + nj] - d0;
+        c0 = d.joint_q_start[j0];
+        ncoord = d.joint_q_start[j0 + nj] - c0;
+        slot0 = M.env_slot_start[env];
+        nc = use_contacts ? M.env_contact_count[env] : 0;
+    }
+    const size_t T = size_t(M.slot_total);
+    const float* cb = M.cb;
+
+    // ---- body_f_ext = body_f; zero scratch ------------------------------------------------------
+    for (int b = l; b < nb; b += L) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            sm.fe[6 * b + k] = sin.body_f[6 * (b0 + b) + k];
+            sm.ft[6 * b + k] = 0.f;
+            sm.fb[6 * b + k] = 0.f;
+        }
+    }
+    __syncwarp(gmask);
+    // ---- per joint: public -> internal joint_f, FREE/DISTANCE wrench into body_f_ext -------------
+    for (int j = l; j < nj; j += L) {
+        const int gj = j0 + j, type = d.joint_type[gj];
+        const int qd0 = d.joint_qd_start[gj], qd1 = d.joint_qd_start[gj + 1];
+        if (type == FJ_FREE || type == FJ_DISTANCE) {
+            const int child = d.joint_child[gj] - b0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) sm.fe[6 * child + k] += ctl.joint_f[qd0 + k];  // one inbound joint per body
+            for (int i = qd0; i < qd1; ++i) sm.jf[i - d0] = 0.0f;
+        } else {
+            for (int i = qd0; i < qd1; ++i) sm.jf[i - d0] = ctl.joint_f[i];
+        }
+    }
+    // ---- eval_rigid_fk: level-parallel ------------------------------------------------------------
+    for (int lvl = 0; lvl <= M.max_depth; ++lvl) {
+        for (int j = l; j < nj; j += L) {
+            const int gj = j0 + j;
+            if (M.joint_depth[gj] != lvl) continue;
+            const int parent = d.joint_parent[gj], child = d.joint_child[gj] - b0;
+            Xf X_wpj = ldx(d.joint_X_p + 7 * gj);
+            if (parent >= 0) X_wpj = xmul(ldx(sm.bq + 7 * (parent - b0)), X_wpj);
+            const Xf X_j = joint_transform(d, d.joint_type[gj], d.joint_qd_start[gj], d.joint_dof_dim[2 * gj], d.joint_dof_dim[2 * gj + 1],
+                                           sin.joint_q, d.joint_q_start[gj]);
+            const Xf X_wc = xmul(xmul(X_wpj, X_j), xinv(ldx(d.joint_X_c + 7 * gj)));
+            const Xf X_sm = xmul(X_wc, Xf(ld3(d.body_com + 3 * (b0 + child)), Q4()));
+            stx(sm.bq + 7 * child, X_wc);
+            stx(sm.bqc + 7 * child, X_sm);
+            stx(sin.body_q + 7 * (b0 + child), X_wc);  // the reference refreshes state_in.body_q (solver_featherstone.py:511)
+        }
+        __syncwarp(gmask);
+    }
+    // ---- public -> internal joint_qd ------------------------------------------------------------------
+    for (int j = l; j < nj; j += L) {
+        const int gj = j0 + j, type = d.joint_type[gj];
+        const int qd0 = d.joint_qd_start[gj], qd1 = d.joint_qd_start[gj + 1];
+        if (type != FJ_FREE && type != FJ_DISTANCE) {
+            for (int i = qd0; i < qd1; ++i) sm.qd_in[i - d0] = sin.joint_qd[i];
+            continue;
+        }
+        const int parent = d.joint_parent[gj], child = d.joint_child[gj] - b0;
+        Xf X_wpj = ldx(d.joint_X_p + 7 * gj);
+        if (parent >= 0) X_wpj = xmul(ldx(sm.bq + 7 * (parent - b0)), X_wpj);
+        const V3 x_com = xpoint(ldx(sm.bq + 7 * child), ld3(d.body_com + 3 * (b0 + child)));
+        const V3 r = qrot_inv(X_wpj.q, x_com - X_wpj.p);
+        const V3 v_com(sin.joint_qd[qd0], sin.joint_qd[qd0 + 1], sin.joint_qd[qd0 + 2]);
+        const V3 omega(sin.joint_qd[qd0 + 3], sin.joint_qd[qd0 + 4], sin.joint_qd[qd0 + 5]);
+        const V3 v_int = v_com - cross(omega, r);
+        float* o = sm.qd_in + (qd0 - d0);
+        o[0] = v_int.x; o[1] = v_int.y; o[2] = v_int.z; o[3] = omega.x; o[4] = omega.y; o[5] = omega.z;
+    }
+    __syncwarp(gmask);
+    // ---- eval_rigid_id: RNEA forward, level-parallel ----------------------------------------------------
+    for (int lvl = 0; lvl <= M.max_depth; ++lvl) {
+        for (int j = l; j < nj; j += L) {
+            const int gj = j0 + j;
+            if (M.joint_depth[gj] != lvl) continue;
+            const int type = d.joint_type[gj], parent = d.joint_parent[gj], child = d.joint_child[gj] - b0;
+            const int art = d.joint_articulation[gj];
+            const int root = d.articulation_start[art];
+            V3 solve_origin;
+            {
+                const int rt = d.joint_type[root];
+                if (rt == FJ_FREE || rt == FJ_DISTANCE) solve_origin = ld3(sm.bqc + 7 * (d.joint_child[root] - b0));
+            }
+            Xf X_wpj = ldx(d.joint_X_p + 7 * gj);
+            if (parent >= 0) X_wpj = xmul(ldx(sm.bq + 7 * (parent - b0)), X_wpj);
+            const Xf X_s(X_wpj.p - solve_origin, X_wpj.q);
+            const int qs = d.joint_q_start[gj], qds = d.joint_qd_start[gj];
+            const int lin = d.joint_dof_dim[2 * gj], ang = d.joint_dof_dim[2 * gj + 1];
+            const float* jqd = sm.qd_in - d0;  // indexed with global dof ids
+            float* Sout = sm.S - 6 * d0;
+            S6 v_j, c_app;
+            if (type == FJ_PRISMATIC) {
+                S6 S = twist_xf(X_s, S6(ld3(d.joint_axis + 3 * qds), V3()));
+                v_j = S * jqd[qds];
+                st6(Sout + 6 * qds, S);
+            } else if (type == FJ_REVOLUTE) {
+                S6 S = twist_xf(X_s, S6(V3(), ld3(d.joint_axis + 3 * qds)));
+                v_j = S * jqd[qds];
+                st6(Sout + 6 * qds, S);
+            } else if (type == FJ_D6) {
+                V3 c_ang;
+                for (int k = 0; k < 3; ++k)
+                    if (lin > k) {
+                        S6 S = twist_xf(X_s, S6(ld3(d.joint_axis + 3 * (qds + k)), V3()));
+                        v_j = v_j + S * jqd[qds + k];
+                        st6(Sout + 6 * (qds + k), S);
+                    }
+                const int iqd = qds + lin, iq = qs + lin;
+                if (ang == 1) {
+                    S6 S = twist_xf(X_s, S6(V3(), ld3(d.joint_axis + 3 * iqd)));
+                    v_j = v_j + S * jqd[iqd];
+                    st6(Sout + 6 * iqd, S);
+                }
+                if (ang == 3) {
+                    V3 w0, w1, w2;
+                    axes3(ld3(d.joint_axis + 3 * iqd), ld3(d.joint_axis + 3 * (iqd + 1)), ld3(d.joint_axis + 3 * (iqd + 2)), sin.joint_q[iq],
+                          sin.joint_q[iq + 1], w0, w1, w2);
+                    S6 S0 = twist_xf(X_s, S6(V3(), w0)), S1 = twist_xf(X_s, S6(V3(), w1)), S2 = twist_xf(X_s, S6(V3(), w2));
+                    const float q0 = jqd[iqd], q1 = jqd[iqd + 1], q2 = jqd[iqd + 2];
+                    v_j = v_j + (S0 * q0 + S1 * q1 + S2 * q2);
+                    st6(Sout + 6 * iqd, S0);
+                    st6(Sout + 6 * (iqd + 1), S1);
+                    st6(Sout + 6 * (iqd + 2), S2);
+                    c_ang += cross(w0, w1) * (q0 * q1);
+                    c_ang += cross(w0, w2) * (q0 * q2);
+                    c_ang += cross(w1, w2) * (q1 * q2);
+                }
+                c_app = twist_xf(X_s, S6(V3(), c_ang));
+            } else if (type == FJ_BALL) {
+                S6 S0 = twist_xf(X_s, S6(V3(), V3(1.f, 0.f, 0.f))), S1 = twist_xf(X_s, S6(V3(), V3(0.f, 1.f, 0.f))),
+                   S2 = twist_xf(X_s, S6(V3(), V3(0.f, 0.f, 1.f)));
+                st6(Sout + 6 * qds, S0);
+                st6(Sout + 6 * (qds + 1), S1);
+                st6(Sout + 6 * (qds + 2), S2);
+                v_j = S0 * jqd[qds] + S1 * jqd[qds + 1] + S2 * jqd[qds + 2];
+            } else if (type == FJ_FREE || type == FJ_DISTANCE) {
+                v_j = twist_xf(X_s, ld6(jqd + qds));
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    S6 e;
+                    e.v[k] = 1.0f;
+                    st6(Sout + 6 * (qds + k), twist_xf(X_s, e));
+                }
+            }
+            S6 v_par, a_par;
+            if (parent >= 0) {
+                v_par = ld6(sm.vs + 6 * (parent - b0));
+                a_par = ld6(sm.as + 6 * (parent - b0));
+            }
+            const S6 v_s = v_par + v_j;
+            const S6 a_s = a_par + scross(v_s, v_j) + c_app;
+            const Xf X_sm = ldx(sm.bqc + 7 * child);
+            const V3 x_com_s = X_sm.p - solve_origin;
+            st3(sm.so + 3 * child, solve_origin);
+            const float mass = d.body_mass[b0 + child];
+            int wi = d.body_world[b0 + child];
+            if (wi < 0) wi += d.gravity_count;
+            const V3 f_g = mass * ld3(d.gravity + 3 * wi);
+            const S6 f_g_s(f_g, cross(x_com_s, f_g));
+            float* Is = sm.Is + 36 * child;
+            spatial_inertia(Xf(x_com_s, X_sm.q), mass, ldm(d.body_inertia + 9 * (b0 + child)), Is);
+            const S6 f_b = m66v(Is, a_s) + scross_dual(v_s, m66v(Is, v_s));
+            const V3 om = v_s.bot();
+            const V3 v_com_world = v_s.top() + cross(om, x_com_s);
+            st6(sm.qdfk + 6 * child, S6(v_com_world, om));
+            st6(sm.vs + 6 * child, v_s);
+            st6(sm.as + 6 * child, a_s);
+            st6(sm.fb + 6 * child, f_b - f_g_s);
+        }
+        __syncwarp(gmask);
+    }
+    // ---- eval_body_contact (penalty), ordered per body over the env's contacts ---------------------------
+    if (use_contacts) {
+        for (int b = l; b < nb; b += L) {
+            V3 facc = ld3(sm.fe + 6 * b), tacc = ld3(sm.fe + 6 * b + 3);
+            for (int c = 0; c < nc; ++c) {
+                const int s = slot0 + c;
+                const int ba = __float_as_int(cb[CF_BODY_A * T + s]), bb = __float_as_int(cb[CF_BODY_B * T + s]);
+                if (ba != b && bb != b) continue;
+                const float ke = cb[CF_KE * T + s], kd = cb[CF_KD * T + s], kf = cb[CF_KF * T + s], ka = cb[CF_KA * T + s], mu = cb[CF_MU * T + s];
+                const V3 n = -V3(cb[CF_NX * T + s], cb[CF_NY * T + s], cb[CF_NZ * T + s]);
+                V3 bx_a(cb[CF_P0X * T + s], cb[CF_P0Y * T + s], cb[CF_P0Z * T + s]);
+                V3 bx_b(cb[CF_P1X * T + s], cb[CF_P1Y * T + s], cb[CF_P1Z * T + s]);
+                V3 r_a, r_b;
+                if (ba >= 0) {
+                    const Xf X = ldx(sm.bq + 7 * ba);
+                    bx_a = xpoint(X, bx_a) - cb[CF_MARGIN0 * T + s] * n;
+                    r_a = bx_a - xpoint(X, ld3(d.body_com + 3 * (b0 + ba)));
+                }
+                if (bb >= 0) {
+                    const Xf X = ldx(sm.bq + 7 * bb);
+                    bx_b = xpoint(X, bx_b) + cb[CF_MARGIN1 * T + s] * n;
+                    r_b = bx_b - xpoint(X, ld3(d.body_com + 3 * (b0 + bb)));
+                }
+                const float dd = dot(n, bx_a - bx_b);
+                if (dd >= ka) continue;
+                V3 bv_a, bv_b;
+                if (ba >= 0) bv_a = ld3(sm.qdfk + 6 * ba) + cross(ld3(sm.qdfk + 6 * ba + 3), r_a);
+                if (bb >= 0) bv_b = ld3(sm.qdfk + 6 * bb) + cross(ld3(sm.qdfk + 6 * bb + 3), r_b);
+                const V3 v = bv_a - bv_b;
+                const float vn = dot(n, v);
+                const V3 vt = v - n * vn;
+                const float fn = dd * ke;
+                const float fd = fmin_w(vn, 0.0f) * kd * (dd < 0.0f ? 1.0f : 0.0f);
+                V3 ft;
+                if (dd < 0.0f) {
+                    const float a2 = dot(vt, vt), delta = P.friction_smoothing;
+                    const float vs = (a2 <= delta * delta) ? 0.5f * a2 : delta * (sqrtf(a2) - 0.5f * delta);
+                    if (vs > 0.0f) {
+                        const V3 fr = vt / vs;
+                        ft = fr * fmin_w(kf * vs, -mu * (fn + fd));
+                    }
+                }
+                const V3 f_total = n * (fn + fd) + ft;
+                if (ba == b) { facc -= f_total; tacc -= cross(r_a, f_total); }
+                if (bb == b) { facc += f_total; tacc += cross(r_b, f_total); }
+            }
+            st3(sm.fe + 6 * b, facc);
+            st3(sm.fe + 6 * b + 3, tacc);
+        }
+        __syncwarp(gmask);
+    }
+    // ---- eval_rigid_tau: RNEA backward, deepest level first ----------------------------------------------------
+    for (int lvl = M.max_depth; lvl >= 0; --lvl) {
+        for (int j = l; j < nj; j += L) {
+            const int gj = j0 + j;
+            if (M.joint_depth[gj] != lvl) continue;
+            const int type = d.joint_type[gj], child = d.joint_child[gj] - b0;
+            const int ds = d.joint_qd_start[gj], cs = d.joint_q_start[gj], tqs = d.joint_target_q_start[gj];
+            const int lin = d.joint_dof_dim[2 * gj], ang = d.joint_dof_dim[2 * gj + 1];
+            const S6 f_b = ld6(sm.fb + 6 * child), f_t = ld6(sm.ft + 6 * child), fe = ld6(sm.fe + 6 * child);
+            const V3 x_com_s = ld3(sm.bqc + 7 * child) - ld3(sm.so + 3 * child);
+            const S6 f_ext0(fe.top(), fe.bot() + cross(x_com_s, fe.top()));
+            S6 f_ext;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) f_ext.v[k] = -f_ext0.v[k];
+            const S6 f_s = f_b + f_t + f_ext;
+            st6(sm.fs + 6 * j, f_s);
+            const float* S = sm.S - 6 * d0;
+            const float* jqd = sm.qd_in - d0;
+            const float* jf = sm.jf - d0;
+            float* tau = sm.tau - d0;
+            if (type == FJ_BALL) {
+                for (int k = 0; k < 3; ++k) {
+                    const int jj = ds + k;
+                    const float passive_f = -d.joint_damping[jj] * jqd[jj];
+                    tau[jj] = -dot6(ld6(S + 6 * jj), f_s) + jf[jj] + passive_f;
+                }
+            } else if (type == FJ_FREE || type == FJ_DISTANCE) {
+                for (int k = 0; k < 6; ++k) tau[ds + k] = -dot6(ld6(S + 6 * (ds + k)), f_s) + jf[ds + k];
+            } else if (type == FJ_PRISMATIC || type == FJ_REVOLUTE || type == FJ_D6) {
+                for (int k = 0; k < lin + ang; ++k) {
+                    const int jj = ds + k;
+                    const float drive = joint_force(sin.joint_q[cs + k], jqd[jj], ctl.joint_target_q[tqs + k], ctl.joint_target_qd[jj],
+                                                    d.joint_target_ke[jj], d.joint_target_kd[jj], d.joint_limit_lower[jj], d.joint_limit_upper[jj],
+                                                    d.joint_limit_ke[jj], d.joint_limit_kd[jj], d.joint_damping[jj]);
+                    tau[jj] = -dot6(ld6(S + 6 * jj), f_s) + drive + jf[jj];
+                }
+            }
+        }
+        __syncwarp(gmask);
+        // fold this level's f_s into the parents (serial reference order: descending joint index)
+        for (int b = l; b < nb; b += L) {
+            S6 acc = ld6(sm.ft + 6 * b);
+            bool any = false;
+            for (int j = nj - 1; j >= 0; --j) {
+                const int gj = j0 + j;
+                if (M.joint_depth[gj] != lvl || d.joint_parent[gj] - b0 != b) continue;
+                acc = acc + ld6(sm.fs + 6 * j);
+                any = true;
+            }
+            if (any) st6(sm.ft + 6 * b, acc);
+        }
+        __syncwarp(gmask);
+    }
+    // ---- H = J^T M J + Cholesky, per articulation -----------------------------------------------------------------
+    for (int a = 0; a < na; ++a) {
+        const int art = a0 + a;
+        const int aj0 = d.articulation_start[art], aj1 = d.articulation_start[art + 1];
+        const int anj = aj1 - aj0;
+        const int ad0 = d.joint_qd_start[aj0], n = d.joint_qd_start[aj1] - ad0;
+        float* H = sm.H + M.art_H_start[art];
+        float* Lg = M.fs_L + M.env_H_start[env] + M.art_H_start[art];
+        if (update_mass) {
+            for (int e = l; e < n * n; e += L) {
+                const int ra = e / n, cbb = e % n;
+                // joints owning dof ra / cbb
+                int ja = aj0, jb = aj0;
+                while (d.joint_qd_start[ja + 1] - ad0 <= ra) ++ja;
+                while (d.joint_qd_start[jb + 1] - ad0 <= cbb) ++jb;
+                const unsigned long long need = (1ull << (ja - aj0)) | (1ull << (jb - aj0));
+                const S6 Sa = ld6(sm.S + 6 * (ad0 - d0 + ra)), Sb = ld6(sm.S + 6 * (ad0 - d0 + cbb));
+                float sum = 0.0f;
+                for (int i = 0; i < anj; ++i) {
+                    if ((M.joint_anc_mask[aj0 + i] & need) != need) continue;
+                    // NB: the reference's spatial_mass indexes body_I_s by JOINT index (kernels.py:1476-1477)
+                    const float* Is = sm.Is + 36 * (aj0 + i - b0);
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) {
+                        float pr = 0.0f;  // P[6i+r, b] = sum_k M[6i+r, 6i+k] J[6i+k, b]
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) pr += Is[6 * r + k] * Sb.v[k];
+                        sum += Sa.v[r] * pr;
+                    }
+                }
+                H[e] = sum;
+            }
+            __syncwarp(gmask);
+            // dense_cholesky (kernels.py:1690-1719), in place on the lower triangle; columns in order, rows in parallel
+            for (int jn = 0; jn < n; ++jn) {
+                float sdiag = H[jn * n + jn] + d.joint_armature[ad0 + jn];
+                for (int k = 0; k < jn; ++k) {
+                    const float r = H[jn * n + k];
+                    sdiag -= r * r;
+                }
+                sdiag = sqrtf(sdiag);
+                const float invS = 1.0f / sdiag;
+                __syncwarp(gmask);
+                for (int i = jn + 1 + l; i < n; i += L) {
+                    float t = H[i * n + jn];
+                    for (int k = 0; k < jn; ++k) t -= H[i * n + k] * H[jn * n + k];
+                    H[i * n + jn] = t * invS;
+                }
+                if (l == 0) H[jn * n + jn] = sdiag;
+                __syncwarp(gmask);
+            }
+            for (int e = l; e < n * n; e += L) Lg[e] = H[e];
+        } else {
+            for (int e = l; e < n * n; e += L) H[e] = Lg[e];
+        }
+        __syncwarp(gmask);
+        // dense_subs (kernels.py:1754-1781): forward then backward substitution, serial (order-preserving)
+        if (l == 0) {
+            float* x = sm.qdd + (ad0 - d0);
+            const float* bvec = sm.tau + (ad0 - d0);
+            for (int i = 0; i < n; ++i) {
+                float t = bvec[i];
+                for (int j = 0; j < i; ++j) t -= H[i * n + j] * x[j];
+                x[i] = t / H[i * n + i];
+            }
+            for (int i = n - 1; i >= 0; --i) {
+                float t = x[i];
+                for (int j = i + 1; j < n; ++j) t -= H[j * n + i] * x[j];
+                x[i] = t / H[i * n + i];
+            }
+        }
+        __syncwarp(gmask);
+    }
+    // ---- integrate_generalized_joints (jcalc_integrate, kernels.py:464-630) ----------------------------------------
+    for (int j = l; j < nj; j += L) {
+        const int gj = j0 + j, type = d.joint_type[gj], parent = d.joint_parent[gj], child = d.joint_child[gj];
+        const int cs = d.joint_q_start[gj], ds = d.joint_qd_start[gj];
+        const float* q = sin.joint_q;
+        const float* qd = sm.qd_in - d0;
+        const float* qdd = sm.qdd - d0;
+        float* qn = sm.jq - c0;
+        float* qdn = sm.qd_out - d0;
+        if (type == FJ_FIXED) continue;
+        if (type == FJ_PRISMATIC || type == FJ_REVOLUTE) {
+            const float qd_new = qd[ds] + qdd[ds] * dt;
+            qdn[ds] = qd_new;
+            qn[cs] = q[cs] + qd_new * dt;
+        } else if (type == FJ_BALL) {
+            const V3 w_new = V3(qd[ds], qd[ds + 1], qd[ds + 2]) + V3(qdd[ds], qdd[ds + 1], qdd[ds + 2]) * dt;
+            const Q4 r(q[cs], q[cs + 1], q[cs + 2], q[cs + 3]);
+            const Q4 drdt = qscale(qmul(Q4(w_new.x, w_new.y, w_new.z, 0.0f), r), 0.5f);
+            const Q4 rn = qunit(qadd(r, qscale(drdt, dt)));
+            qn[cs] = rn.x; qn[cs + 1] = rn.y; qn[cs + 2] = rn.z; qn[cs + 3] = rn.w;
+            qdn[ds] = w_new.x; qdn[ds + 1] = w_new.y; qdn[ds + 2] = w_new.z;
+        } else if (type == FJ_FREE || type == FJ_DISTANCE) {
+            if (parent < 0) {
+                const V3 a_parent(qdd[ds], qdd[ds + 1], qdd[ds + 2]), alpha(qdd[ds + 3], qdd[ds + 4], qdd[ds + 5]);
+                const V3 v_parent(qd[ds], qd[ds + 1], qd[ds + 2]), omega(qd[ds + 3], qd[ds + 4], qd[ds + 5]);
+                const V3 pp(q[cs], q[cs + 1], q[cs + 2]);
+                const Q4 r(q[cs + 3], q[cs + 4], q[cs + 5], q[cs + 6]);
+                const V3 r_com_joint = xpoint(xinv(ldx(d.joint_X_c + 7 * gj)), ld3(d.body_com + 3 * child));
+                const V3 x_com = pp + qrot(r, r_com_joint);
+                const V3 v_com = v_parent + cross(omega, x_com);
+                const V3 a_com = a_parent + cross(alpha, x_com) + cross(omega, v_com);
+                const V3 omega_new = omega + alpha * dt;
+                const V3 v_com_new = v_com + a_com * dt;
+                const Q4 drdt = qscale(qmul(Q4(omega_new.x, omega_new.y, omega_new.z, 0.0f), r), 0.5f);
+                const Q4 r_new = qunit(qadd(r, qscale(drdt, dt)));
+                const V3 x_com_new = x_com + v_com_new * dt;
+                const V3 p_new = x_com_new - qrot(r_new, r_com_joint);
+                const V3 v_parent_new = v_com_new - cross(omega_new, x_com_new);
+                qn[cs] = p_new.x; qn[cs + 1] = p_new.y; qn[cs + 2] = p_new.z;
+                qn[cs + 3] = r_new.x; qn[cs + 4] = r_new.y; qn[cs + 5] = r_new.z; qn[cs + 6] = r_new.w;
+                qdn[ds] = v_parent_new.x; qdn[ds + 1] = v_parent_new.y; qdn[ds + 2] = v_parent_new.z;
+                qdn[ds + 3] = omega_new.x; qdn[ds + 4] = omega_new.y; qdn[ds + 5] = omega_new.z;
+            } else {
+                const V3 w_s = V3(qd[ds + 3], qd[ds + 4], qd[ds + 5]) + V3(qdd[ds + 3], qdd[ds + 4], qdd[ds + 5]) * dt;
+                const V3 v_s = V3(qd[ds], qd[ds + 1], qd[ds + 2]) + V3(qdd[ds], qdd[ds + 1], qdd[ds + 2]) * dt;
+                const V3 p_s(q[cs], q[cs + 1], q[cs + 2]);
+                const V3 dpdt = v_s + cross(w_s, p_s);
+                const Q4 r_s(q[cs + 3], q[cs + 4], q[cs + 5], q[cs + 6]);
+                const Q4 drdt = qscale(qmul(Q4(w_s.x, w_s.y, w_s.z, 0.0f), r_s), 0.5f);
+                const V3 pn = p_s + dpdt * dt;
+                const Q4 rn = qunit(qadd(r_s, qscale(drdt, dt)));
+                qn[cs] = pn.x; qn[cs + 1] = pn.y; qn[cs + 2] = pn.z; qn[cs + 3] = rn.x; qn[cs + 4] = rn.y; qn[cs + 5] = rn.z; qn[cs + 6] = rn.w;
+                qdn[ds] = v_s.x; qdn[ds + 1] = v_s.y; qdn[ds + 2] = v_s.z; qdn[ds + 3] = w_s.x; qdn[ds + 4] = w_s.y; qdn[ds + 5] = w_s.z;
+            }
+        } else if (type == FJ_D6) {
+            const int cnt = d.joint_dof_dim[2 * gj] + d.joint_dof_dim[2 * gj + 1];
+            for (int k = 0; k < cnt; ++k) {
+                const float qd_new = qd[ds + k] + qdd[ds + k] * dt;
+                qdn[ds + k] = qd_new;
+                qn[cs + k] = q[cs + k] + qd_new * dt;
+            }
+        }
+    }
+    __syncwarp(gmask);
+    for (int i = l; i < ncoord; i += L) sout.joint_q[c0 + i] = sm.jq[i];
+    // ---- eval_fk_with_velocity_conversion: level-parallel; reuses bq (poses) and vs (COM twists) ------------------------
+    for (int lvl = 0; lvl <= M.max_depth; ++lvl) {
+        for (int j = l; j < nj; j += L) {
+            const int gj = j0 + j;
+            if (M.joint_depth[gj] != lvl) continue;
+            const int type = d.joint_type[gj], parent = d.joint_parent[gj], child = d.joint_child[gj] - b0;
+            const int qs = d.joint_q_start[gj], qds = d.joint_qd_start[gj];
+            const int lin = d.joint_dof_dim[2 * gj], ang = d.joint_dof_dim[2 * gj + 1];
+            const float* jq = sm.jq - c0;
+            const float* jqd = sm.qd_out - d0;
+            const Xf X_j = joint_transform(d, type, qds, lin, ang, jq, qs);
+            V3 vj_lin, vj_ang;
+            if (type == FJ_PRISMATIC) vj_lin = ld3(d.joint_axis + 3 * qds) * jqd[qds];
+            if (type == FJ_REVOLUTE) vj_ang = ld3(d.joint_axis + 3 * qds) * jqd[qds];
+            if (type == FJ_BALL) vj_ang = V3(jqd[qds], jqd[qds + 1], jqd[qds + 2]);
+            if (type == FJ_FREE || type == FJ_DISTANCE) {
+                vj_lin = V3(jqd[qds], jqd[qds + 1], jqd[qds + 2]);
+                vj_ang = V3(jqd[qds + 3], jqd[qds + 4], jqd[qds + 5]);
+            }
+            if (type == FJ_D6) {
+                for (int k = 0; k < 3; ++k)
+                    if (lin > k) vj_lin += ld3(d.joint_axis + 3 * (qds + k)) * jqd[qds + k];
+                const int iq = qs + lin, iqd = qds + lin;
+                if (ang == 1) vj_ang = jqd[iqd] * ld3(d.joint_axis + 3 * iqd);
+                if (ang == 3) {
+                    V3 w0, w1, w2;
+                    axes3(ld3(d.joint_axis + 3 * iqd), ld3(d.joint_axis + 3 * (iqd + 1)), ld3(d.joint_axis + 3 * (iqd + 2)), jq[iq], jq[iq + 1], w0, w1, w2);
+                    vj_ang = w0 * jqd[iqd] + w1 * jqd[iqd + 1] + w2 * jqd[iqd + 2];
+                }
+            }
+            Xf X_wpj = ldx(d.joint_X_p + 7 * gj);
+            Xf X_wp;
+            if (parent >= 0) {
+                X_wp = ldx(sm.bq + 7 * (parent - b0));
+                X_wpj = xmul(X_wp, X_wpj);
+            }
+            const Xf X_wcj = xmul(X_wpj, X_j);
+            const Xf X_wc = xmul(X_wcj, xinv(ldx(d.joint_X_c + 7 * gj)));
+            const V3 x_child = X_wc.p;
+            V3 v_parent_origin, w_parent;
+            if (parent >= 0) {
+                const V3 pv = ld3(sm.vs + 6 * (parent - b0));
+                w_parent = ld3(sm.vs + 6 * (parent - b0) + 3);
+                v_parent_origin = cross(w_parent, x_child - xpoint(X_wp, ld3(d.body_com + 3 * parent))) + pv;
+            }
+            const V3 lin_w = xvec(X_wpj, vj_lin);
+            V3 ang_w = xvec(X_wpj, vj_ang);
+            V3 lin_o;
+            if (type == FJ_FREE || type == FJ_DISTANCE) {
+                const S6 vw = twist_xf(X_wpj, S6(vj_lin, vj_ang));
+                lin_o = cross(vw.bot(), x_child) + vw.top();
+                ang_w = vw.bot();
+            } else {
+                lin_o = lin_w + cross(ang_w, x_child - X_wcj.p);
+            }
+            const V3 v_o = v_parent_origin + lin_o, w_o = w_parent + ang_w;
+            const V3 v_com = cross(w_o, xvec(X_wc, ld3(d.body_com + 3 * (b0 + child)))) + v_o;
+            stx(sm.bq + 7 * child, X_wc);
+            st6(sm.vs + 6 * child, S6(v_com, w_o));
+            stx(sout.body_q + 7 * (b0 + child), X_wc);
+            st6(sout.body_qd + 6 * (b0 + child), S6(v_com, w_o));
+        }
+        __syncwarp(gmask);
+    }
+    // ---- internal -> public joint_qd ------------------------------------------------------------------------------
+    for (int j = l; j < nj; j += L) {
+        const int gj = j0 + j, type = d.joint_type[gj];
+        const int qd0 = d.joint_qd_start[gj], qd1 = d.joint_qd_start[gj + 1];
+        if (type != FJ_FREE && type != FJ_DISTANCE) {
+            for (int i = qd0; i < qd1; ++i) sout.joint_qd[i] = sm.qd_out[i - d0];
+            continue;
+        }
+        const int parent = d.joint_parent[gj], child = d.joint_child[gj] - b0;
+        Xf X_wpj = ldx(d.joint_X_p + 7 * gj);
+        if (parent >= 0) X_wpj = xmul(ldx(sm.bq + 7 * (parent - b0)), X_wpj);
+        const V3 x_com = xpoint(ldx(sm.bq + 7 * child), ld3(d.body_com + 3 * (b0 + child)));
+        const V3 r = qrot_inv(X_wpj.q, x_com - X_wpj.p);
+        const float* qi = sm.qd_out + (qd0 - d0);
+        const V3 v_int(qi[0], qi[1], qi[2]), omega(qi[3], qi[4], qi[5]);
+        const V3 v_com = v_int + cross(omega, r);
+        float* o = sout.joint_qd + qd0;
+        o[0] = v_com.x; o[1] = v_com.y; o[2] = v_com.z; o[3] = omega.x; o[4] = omega.y; o[5] = omega.z;
+    }
+}
+
+template <int L>
+static nb2_status launch_fs_L(nb2_model* m, const nb2_featherstone_params& p, const nb2_state_view& in, const nb2_state_view& out,
+                              const nb2_control_view& ctl, int use_contacts, int update_mass, float dt, cudaStream_t s) {
+    const DevModel& M = m->dev;
+    const int G = 32 / L;
+    const int blocks = (M.env_count + G - 1) / G;
+    const size_t per_env = size_t(M.max_env_bodies) * (7 + 7 + 6 * 6 + 36 + 3) + size_t(M.max_env_joints) * 6 + size_t(M.max_env_dofs) * (6 + 5) +
+                           size_t(M.max_env_H) + size_t(M.max_env_coords);
+    const size_t smem = per_env * G * sizeof(float);
+    if (smem > 220 * 1024) {
+        set_error("featherstone_step: environment too large for the fused shared-memory kernel");
+        return NB2_ERR_CAPACITY;
+    }
+    if (smem > 48 * 1024)
+        NB2_CUDA_CHECK(cudaFuncSetAttribute(featherstone_step_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    NB2_CUDA_CHECK(cudaFuncSetAttribute(featherstone_step_kernel<L>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    featherstone_step_kernel<L><<<blocks, 32, smem, s>>>(M, p, in, out, ctl, use_contacts, update_mass, dt);
+    count_launch();
+    NB2_CUDA_CHECK(cudaGetLastError());
+    return NB2_OK;
+}
+
+nb2_status launch_featherstone_step(nb2_model* m, const nb2_featherstone_params& p, const nb2_state_view& in, const nb2_state_view& out,
+                                    const nb2_control_view& ctl, int use_contacts, float dt, cudaStream_t s) {
+    const DevModel& M = m->dev;
+    if (M.d.joint_count == 0) {
+        set_error("nb2_featherstone_step: model has no joints (free rigid bodies need add_body(), which creates FREE joints)");
+        return NB2_ERR_UNSUPPORTED;
+    }
+    if (!m->host.featherstone_supported) {
+        set_error("nb2_featherstone_step: unsupported model: " + m->host.featherstone_reason);
+        return NB2_ERR_UNSUPPORTED;
+    }
+    if (!in.body_q || !in.body_f || !in.joint_q || !in.joint_qd || !out.body_q || !out.body_qd || !out.joint_q || !out.joint_qd ||
+        !ctl.joint_f || !ctl.joint_target_q || !ctl.joint_target_qd) {
+        set_error("nb2_featherstone_step: state / control arrays are NULL");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    if (in.joint_q == out.joint_q) {
+        set_error("nb2_featherstone_step: state_in must not alias state_out (in-place stepping is not implemented)");
+        return NB2_ERR_UNSUPPORTED;
+    }
+    const int interval = p.update_mass_matrix_interval > 0 ? p.update_mass_matrix_interval : 1;
+    const int update_mass = (m->featherstone_step_count % interval) == 0;
+    m->featherstone_step_count += 1;
+    switch (m->lanes_per_env) {
+        case 8: return launch_fs_L<8>(m, p, in, out, ctl, use_contacts, update_mass, dt, s);
+        case 16: return launch_fs_L<16>(m, p, in, out, ctl, use_contacts, update_mass, dt, s);
+        default: return launch_fs_L<32>(m, p, in, out, ctl, use_contacts, update_mass, dt, s);
+    }
+}
+
 nb2_status launch_eval_fk(nb2_model*, const float*, const float*, float*, float*, cudaStream_t) {
     set_error("nb2_eval_fk: not implemented yet");
     return NB2_ERR_UNSUPPORTED;
 }
+
 }  // namespace nb2

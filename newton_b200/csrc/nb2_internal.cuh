@@ -48,6 +48,13 @@ struct DevModel {
     int* env_contact_count;        // [E]
     int* env_contact_offset;       // [E+1] exclusive scan, written by the export path
     int max_env_bodies, max_env_joints, max_env_slots_shapes, max_env_pairs, max_env_contact_slots;
+    // articulated-body (Featherstone) tables
+    const int* joint_depth;            // [J] depth of each joint in its articulation tree (root = 0)
+    const unsigned long long* joint_anc_mask;  // [J] bit k set <=> articulation-local joint k is an ancestor-or-self
+    const int* art_H_start;            // [A+1] offset of each articulation's nd x nd block inside its env's H storage
+    const int* env_H_start;            // [E+1] global offset of the env's H/L storage (persistent L for update intervals)
+    float* fs_L;                       // persistent Cholesky factors [env_H_start[E]]
+    int max_depth, max_env_dofs, max_env_coords, max_env_H, max_env_arts;
 };
 
 struct HostTables {
@@ -55,6 +62,10 @@ struct HostTables {
     std::vector<int> global_shapes;
     std::vector<int2> pairs;
     std::vector<int> body_joint_start, body_joint_entry;
+    std::vector<int> joint_depth, art_H_start, env_H_start;
+    std::vector<unsigned long long> joint_anc_mask;
+    bool featherstone_supported = true;
+    std::string featherstone_reason;
 };
 
 }  // namespace nb2

@@ -1,4 +1,5 @@
+from .featherstone import SolverFeatherstone
 from .solver import SolverBase
 from .xpbd import SolverXPBD
 
-__all__ = ["SolverBase", "SolverXPBD"]
+__all__ = ["SolverBase", "SolverFeatherstone", "SolverXPBD"]

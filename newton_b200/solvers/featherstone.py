@@ -1,0 +1,48 @@
+"""``SolverFeatherstone`` - drop-in for the reference class
+(``newton/_src/solvers/featherstone/solver_featherstone.py:135-1066``).
+
+Same constructor kwargs (``:135-146``) and ``step`` signature (``:461-469``).  One fused CUDA kernel per call
+(``newton_b200/csrc/nb2_featherstone.cu``).  ``use_tile_gemm`` / ``fuse_cholesky`` select Warp tile kernels in
+the reference; here H = J^T M J and its Cholesky factor are always fused, so the flags are accepted and ignored.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+from .. import _abi, _lib
+from .solver import SolverBase
+
+
+class SolverFeatherstone(SolverBase):
+    def __init__(self, model, *, angular_damping: float = 0.05, update_mass_matrix_interval: int = 1,
+                 friction_smoothing: float = 1.0, use_tile_gemm: bool = False, fuse_cholesky: bool = True,
+                 deterministic=None):
+        super().__init__(model)
+        if getattr(model, "particle_count", 0):
+            raise NotImplementedError("particles are outside the hot-path scope")
+        self.angular_damping = angular_damping
+        self.update_mass_matrix_interval = update_mass_matrix_interval
+        self.friction_smoothing = friction_smoothing
+        self.use_tile_gemm = use_tile_gemm
+        self.fuse_cholesky = fuse_cholesky
+
+    def step(self, state_in, state_out, control, contacts, dt: float) -> None:
+        """Advance by ``dt`` (reference ``solver_featherstone.py:461-1066``): writes ``state_out.joint_q/joint_qd/
+        body_q/body_qd`` and, like the reference, refreshes ``state_in.body_q`` by forward kinematics."""
+        model = self.model
+        if control is None:
+            control = model.control(clone_variables=False)
+        use_contacts = 0
+        if contacts is not None and contacts.rigid_contact_max:
+            if getattr(contacts, "_nb2_blocks", None) is not self._native:
+                raise NotImplementedError(
+                    "contacts were not produced by newton_b200.CollisionPipeline.collide() on this model"
+                )
+            use_contacts = 1
+        p = _abi.FeatherstoneParams(self.angular_damping, int(self.update_mass_matrix_interval), self.friction_smoothing)
+        st = _lib.lib().nb2_featherstone_step(
+            self._native.handle, C.byref(p), C.byref(_abi.state_view(state_in)), C.byref(_abi.state_view(state_out)),
+            C.byref(_abi.control_view(control)), use_contacts, C.c_float(dt), _lib.current_stream_ptr(model),
+        )
+        _lib.check(st, "nb2_featherstone_step")

@@ -46,6 +46,8 @@ def lib():
         _LIB.orc_primitive_pair.restype = C.c_int
         _LIB.orc_convex_pair.restype = C.c_int
         _LIB.orc_version.restype = C.c_char_p
+        _LIB.orc_featherstone_new.restype = C.c_void_p
+        _LIB.orc_featherstone_free.argtypes = [C.c_void_p]
     return _LIB
 
 
@@ -123,6 +125,13 @@ class SolverFeatherstone:
         self.model = model
         self._desc = _abi.model_desc(model)
         self.params = _abi.FeatherstoneParams(angular_damping, update_mass_matrix_interval, friction_smoothing)
+        self._h = C.c_void_p(lib().orc_featherstone_new())
+
+    def __del__(self):
+        try:
+            lib().orc_featherstone_free(self._h)
+        except Exception:
+            pass
 
     def step(self, state_in, state_out, control, contacts, dt):
         if control is None:
@@ -133,7 +142,7 @@ class SolverFeatherstone:
             ctp = C.byref(ctv)
         else:
             ctp = None
-        lib().orc_featherstone_step(C.byref(self._desc), C.byref(self.params), C.byref(sv_in), C.byref(sv_out),
+        lib().orc_featherstone_step(self._h, C.byref(self._desc), C.byref(self.params), C.byref(sv_in), C.byref(sv_out),
                                     C.byref(cv), ctp, C.c_float(dt))
 
 

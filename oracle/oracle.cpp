@@ -138,10 +138,13 @@ void orc_xpbd_step(const nb2_model_desc* mp, const nb2_xpbd_params* p, const nb2
     }
 }
 
-void orc_featherstone_step(const nb2_model_desc* m, const nb2_featherstone_params* p, const nb2_state_view* state_in,
+// SolverFeatherstone keeps cross-step state (step counter, cached H / L): one handle per solver instance.
+void* orc_featherstone_new(void) { return new FsScratch(); }
+void orc_featherstone_free(void* h) { delete static_cast<FsScratch*>(h); }
+void orc_featherstone_step(void* h, const nb2_model_desc* m, const nb2_featherstone_params* p, const nb2_state_view* state_in,
                            const nb2_state_view* state_out, const nb2_control_view* control, const nb2_contacts_view* contacts,
                            float dt) {
-    featherstone_step(*m, *p, *state_in, *state_out, *control, contacts, dt);
+    featherstone_step(*static_cast<FsScratch*>(h), *m, *p, *state_in, *state_out, *control, contacts, dt);
 }
 
 // ---- unit-level hooks for known-answer tests ------------------------------------------------------

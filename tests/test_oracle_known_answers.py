@@ -231,3 +231,77 @@ def test_sphere_rests_on_ground(oracle_lib):
         s0, s1 = s1, s0
     assert s0.body_q[0, 2].item() == pytest.approx(0.5, abs=2e-3)
     assert abs(s0.body_qd[0, 2].item()) < 1e-2
+
+
+def _pendulum(sphere_radius=0.01):
+    """Single pendulum of reference tests/test_physics_verification.py:112-139 (g = -10 along Y, L = 1, theta0 = 0.05)."""
+    import newton_b200
+
+    b = ModelBuilder(gravity=(0.0, -10.0, 0.0), up_axis="y")
+    link = b.add_link()
+    b.add_shape_sphere(link, radius=sphere_radius)
+    j = b.add_joint_revolute(parent=-1, child=link, axis=(0.0, 0.0, 1.0), parent_xform=X.transform(),
+                             child_xform=X.transform((0.0, 1.0, 0.0)), armature=0.0)
+    b.add_articulation([j])
+    model = b.finalize()
+    model.joint_q[0] = 0.05
+    newton_b200.eval_fk(model, model.joint_q, model.joint_qd, model)
+    return model
+
+
+@pytest.mark.parametrize("solver_name,sim_dt,gen", [("featherstone", 1e-3, True), ("xpbd", 3e-4, False)])
+def test_pendulum_period(oracle_lib, solver_name, sim_dt, gen):
+    """theta(t) = theta0 cos(2 pi t / T), T = 2 pi sqrt(I_pivot / (m g d)); mean trajectory error < 1 % of the amplitude
+    (reference tests/test_physics_verification.py:105-185, same dt per solver as :1574-1582)."""
+    model = _pendulum()
+    solver = oracle_lib.SolverFeatherstone(model, angular_damping=0.0) if solver_name == "featherstone" else \
+        oracle_lib.SolverXPBD(model, iterations=20, angular_damping=0.0)  # reference :1552
+    mass = model.body_mass[0].item()
+    I_pivot = model.body_inertia[0, 2, 2].item() + mass * 1.0
+    T = 2.0 * np.pi * np.sqrt(I_pivot / (mass * 10.0 * 1.0))
+    n = int(3.5 * T / sim_dt)
+    s0, s1 = model.state(), model.state()
+    angles = np.empty(n)
+    for i in range(n):
+        s0.clear_forces()
+        solver.step(s0, s1, None, None, sim_dt)
+        s0, s1 = s1, s0
+        if gen:
+            angles[i] = s0.joint_q[0].item()
+        else:
+            bq = s0.body_q[0]
+            angles[i] = math.atan2(bq[0].item(), -bq[1].item())
+    t = np.arange(1, n + 1) * sim_dt
+    err = np.mean(np.abs(angles - 0.05 * np.cos(2.0 * np.pi / T * t))) / 0.05
+    assert err < 0.01, err
+
+
+def test_featherstone_double_pendulum_energy(oracle_lib):
+    """Config 1 (example_basic_pendulum scene, SolverFeatherstone, no damping): total energy drift < 1 % over 1 s."""
+    model = scenes.pendulum_model()
+    solver = oracle_lib.SolverFeatherstone(model, angular_damping=0.0)
+    s0, s1 = model.state(), model.state()
+    m = model.body_mass.numpy()
+    I = model.body_inertia.numpy()
+
+    def energy(s):
+        q, qd = s.body_q.numpy(), s.body_qd.numpy()
+        e = 0.0
+        for b in range(2):
+            R = X.quat_to_matrix(q[b, 3:].astype(np.float64))
+            Iw = R @ I[b] @ R.T
+            com = X.transform_point(q[b].astype(np.float64), model.body_com[b].numpy().astype(np.float64))
+            e += 0.5 * m[b] * qd[b, :3] @ qd[b, :3] + 0.5 * qd[b, 3:] @ Iw @ qd[b, 3:] + m[b] * 9.81 * com[2]
+        return e
+
+    solver.step(s0, s1, None, None, 1e-3)
+    s0, s1 = s1, s0
+    e0 = energy(s0)
+    for _ in range(1000):
+        s0.clear_forces()
+        solver.step(s0, s1, None, None, 1e-3)
+        s0, s1 = s1, s0
+    e1 = energy(s0)
+    assert abs(e1 - e0) / abs(e0) < 0.01
+    q = s0.body_q.numpy()
+    assert np.all(np.abs(q[:, 0]) < 1e-5) and np.all(q[:, 2] < 5.0 + 1e-4)  # stays in its plane, below the pivot
