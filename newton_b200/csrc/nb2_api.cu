@@ -69,6 +69,8 @@ static nb2_status build_tables(nb2_model* m, const nb2_model_desc& d) {
     if ((st = fetch(d.shape_contact_pairs, size_t(P) * 2, pairs))) return st;
     if ((st = fetch(d.articulation_start, size_t(d.articulation_count) + 1, art_start))) return st;
     if ((st = fetch(d.joint_articulation, size_t(J), jart))) return st;
+    std::vector<float> shape_scale;
+    if ((st = fetch(d.shape_scale, size_t(S) * 3, shape_scale))) return st;
 
     // ---- env partition ----------------------------------------------------------------------
     const bool implicit_single = (W == 1) && (bws[0] == B) && (jws[0] == J) && (sws[0] == S);
@@ -123,6 +125,21 @@ static nb2_status build_tables(nb2_model* m, const nb2_model_desc& d) {
         if (env < 0) continue;                           // static-vs-static global pair: no dynamic body involved
         int sa = s1, sb = s2;
         if (shape_type[sa] > shape_type[sb]) std::swap(sa, sb);  // narrow_phase.py:525-528
+        {   // shapes the narrow phase of this library covers: analytic primitives + convex primitives through MPR/GJK
+            const int ta = shape_type[sa], tb = shape_type[sb];
+            auto known = [](int t) { return t == 1 || (t >= 3 && t <= 7); };  // PLANE SPHERE CAPSULE ELLIPSOID CYLINDER BOX
+            if (!known(ta) || !known(tb)) {
+                set_error("shape pair (" + std::to_string(sa) + "," + std::to_string(sb) + "): geometry types " + std::to_string(ta) + "/" +
+                          std::to_string(tb) + " are outside the supported set (plane, sphere, capsule, ellipsoid, cylinder, box)");
+                return NB2_ERR_UNSUPPORTED;
+            }
+            // plane vs barrel cylinder can fall through to the generic convex path, which needs the reference's
+            // infinite-plane -> cube conversion (collision_core.py:752-766): not built
+            if (ta == 1 && tb == 6 && shape_scale[3 * sb + 2] != 0.0f) {
+                set_error("plane vs barrel cylinder (shape_scale.z != 0) is not supported");
+                return NB2_ERR_UNSUPPORTED;
+            }
+        }
         int64_t key = ((int64_t(sa) & 0xFFFFF) << 43) | ((int64_t(sb) & 0xFFFFF) << 23);
         recs.push_back({env, key, sa, sb});
     }

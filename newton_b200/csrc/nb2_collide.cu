@@ -409,8 +409,8 @@ __global__ void __launch_bounds__(32) collide_kernel(DevModel M, const float* __
                         }
                     }
                 } else {
-                    ConvexShape A{ta, sca, Xa, marg_a, d.shape_gap[sa], d.shape_collision_radius[sa]};
-                    ConvexShape Bc{tb, scb, Xb, marg_b, d.shape_gap[sb], d.shape_collision_radius[sb]};
+                    ConvexShape A{ta, sca, Xa, marg_a, d.shape_gap[sa]};
+                    ConvexShape Bc{tb, scb, Xb, marg_b, d.shape_gap[sb]};
                     vmask = convex_pair_contacts(A, Bc, cdist, cpos, cnorm, reff_a, reff_b);
                 }
             }

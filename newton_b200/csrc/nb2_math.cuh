@@ -6,10 +6,19 @@
 // registers; loads/stores of the reference's packed AoS elements (28-byte transforms, 24-byte spatial
 // vectors) are explicit so each kernel controls its own memory traffic.
 #pragma once
-#include <cuda_runtime.h>
 #include <stdint.h>
-
-#define NB2_DEV __device__ __forceinline__
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#define NB2_DEV __host__ __device__ __forceinline__
+#else
+// Host-only compilation (g++): lets the CPU oracle compile the single-source convex-contact routines of
+// nb2_convex.cuh with -ffp-contract=off, i.e. the arithmetic of the strict-fp CUDA build.
+#include <cmath>
+#define NB2_DEV inline
+#ifndef NB2_STRICT_FP
+#define NB2_STRICT_FP 1
+#endif
+#endif
 
 namespace nb2 {
 

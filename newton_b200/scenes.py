@@ -172,3 +172,38 @@ def shapes_on_plane_model(world_count: int = 1, device="cpu", seed: int | None =
         scene.end_world()
     scene.add_ground_plane()
     return _finish(scene, device)
+
+
+def convex_pile_model(world_count: int = 1, device="cpu", seed: int | None = 5):
+    """Overlapping convex primitives resting on each other - every pair class that has no analytic collider and
+    therefore runs through MPR/GJK + manifold (``narrow_phase.py:1041-1216``): box-box, capsule-box,
+    cylinder-cylinder, cylinder-box, ellipsoid-box, ellipsoid-sphere, ellipsoid-ellipsoid."""
+    rng = np.random.default_rng(seed) if seed is not None else None
+    scene = ModelBuilder()
+    for _ in range(world_count):
+        scene.begin_world()
+        jit = (lambda s=0.01: rng.uniform(-s, s, size=3)) if rng is not None else (lambda s=0.0: np.zeros(3))
+        yaw = (lambda: float(rng.uniform(-0.4, 0.4))) if rng is not None else (lambda: 0.0)
+        zq = lambda a: X.quat_from_axis_angle((0.0, 0.0, 1.0), a)
+        base = scene.add_body(xform=X.transform(np.array([0.0, 0.0, 0.25]) + jit(), zq(yaw())))
+        scene.add_shape_box(base, hx=1.5, hy=1.5, hz=0.25)
+        b = scene.add_body(xform=X.transform(np.array([-0.8, -0.8, 0.79]) + jit(), zq(yaw())))
+        scene.add_shape_box(b, hx=0.3, hy=0.3, hz=0.3)
+        b = scene.add_body(xform=X.transform(np.array([0.8, -0.8, 0.69]) + jit(),
+                                             X.quat_from_axis_angle((0.0, 1.0, 0.0), 0.5 * math.pi)))
+        scene.add_shape_capsule(b, radius=0.2, half_height=0.4)
+        c0 = scene.add_body(xform=X.transform(np.array([0.8, 0.8, 0.79]) + jit(), zq(yaw())))
+        scene.add_shape_cylinder(c0, radius=0.3, half_height=0.3)
+        c1 = scene.add_body(xform=X.transform(np.array([0.85, 0.8, 1.38]) + jit(), zq(yaw())))
+        scene.add_shape_cylinder(c1, radius=0.25, half_height=0.3)
+        e = scene.add_body(xform=X.transform(np.array([-0.8, 0.8, 0.69]) + jit(), zq(yaw())))
+        scene.add_shape_ellipsoid(e, rx=0.4, ry=0.3, rz=0.2)
+        sp = scene.add_body(xform=X.transform(np.array([-0.8, 0.8, 1.07]) + jit()))
+        scene.add_shape_sphere(sp, radius=0.2)
+        e2 = scene.add_body(xform=X.transform(np.array([0.0, 0.0, 0.69]) + jit(), zq(yaw())))
+        scene.add_shape_ellipsoid(e2, rx=0.3, ry=0.3, rz=0.2)
+        e3 = scene.add_body(xform=X.transform(np.array([0.05, 0.0, 1.07]) + jit(), zq(yaw())))
+        scene.add_shape_ellipsoid(e3, rx=0.25, ry=0.2, rz=0.2)
+        scene.end_world()
+    scene.add_ground_plane()
+    return _finish(scene, device)

@@ -180,6 +180,37 @@ def convex_pair(type_a, scale_a, xform_a, type_b, scale_b, xform_b, gap_sum=0.2)
     return cnt, dist, pos, n
 
 
+def _f32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+def mpr_core(type_a, scale_a, type_b, scale_b, pos_b, quat_b, extend=0.0):
+    """solve_mpr_core in A's frame: returns (collision, point_a, point_b, normal, penetration)."""
+    sa, sb, pb, qb = _f32(scale_a), _f32(scale_b), _f32(pos_b), _f32(quat_b)
+    out = np.zeros(10, dtype=np.float32)
+    hit = lib().orc_mpr_core(int(type_a), C.c_void_p(sa.ctypes.data), int(type_b), C.c_void_p(sb.ctypes.data),
+                             C.c_void_p(pb.ctypes.data), C.c_void_p(qb.ctypes.data), C.c_float(extend),
+                             C.c_void_p(out.ctypes.data))
+    return hit, out[0:3], out[3:6], out[6:9], float(out[9])
+
+
+def gjk_core(type_a, scale_a, type_b, scale_b, pos_b, quat_b, extend=0.0, eps=1e-4):
+    """solve_closest_distance_core in A's frame: returns (separated, point_a, point_b, normal, distance)."""
+    sa, sb, pb, qb = _f32(scale_a), _f32(scale_b), _f32(pos_b), _f32(quat_b)
+    out = np.zeros(10, dtype=np.float32)
+    sep = lib().orc_gjk_core(int(type_a), C.c_void_p(sa.ctypes.data), int(type_b), C.c_void_p(sb.ctypes.data),
+                             C.c_void_p(pb.ctypes.data), C.c_void_p(qb.ctypes.data), C.c_float(extend), C.c_float(eps),
+                             C.c_void_p(out.ctypes.data))
+    return sep, out[0:3], out[3:6], out[6:9], float(out[9])
+
+
+def support_map(geo_type, scale, direction):
+    s, d = _f32(scale), _f32(direction)
+    out = np.zeros(3, dtype=np.float32)
+    lib().orc_support_map(int(geo_type), C.c_void_p(s.ctypes.data), C.c_void_p(d.ctypes.data), C.c_void_p(out.ctypes.data))
+    return out
+
+
 def shape_aabbs(model, body_q):
     d = _abi.model_desc(model)
     lo = np.zeros((model.shape_count, 3), dtype=np.float32)

@@ -179,6 +179,22 @@ int orc_convex_pair(int type_a, const float* scale_a, const float* xform_a, int 
                             transform::load(xform_b), gap_sum, dist5, pos15, normal15);
 }
 
+// A-frame MPR / GJK cores and the support map, for the reference's direct solver tests (test_mpr.py, test_gjk.py).
+// out10 = point_a(3) point_b(3) normal(3) penetration|distance.  B's pose is relative to A.
+int orc_mpr_core(int type_a, const float* scale_a, int type_b, const float* scale_b, const float* pos_b, const float* quat_b, float extend,
+                 float* out10) {
+    return mpr_core_test(type_a, load3(scale_a), type_b, load3(scale_b), load3(pos_b), quat(quat_b[0], quat_b[1], quat_b[2], quat_b[3]),
+                         extend, out10);
+}
+int orc_gjk_core(int type_a, const float* scale_a, int type_b, const float* scale_b, const float* pos_b, const float* quat_b, float extend,
+                 float eps, float* out10) {
+    return gjk_core_test(type_a, load3(scale_a), type_b, load3(scale_b), load3(pos_b), quat(quat_b[0], quat_b[1], quat_b[2], quat_b[3]),
+                         extend, eps, out10);
+}
+void orc_support_map(int type, const float* scale, const float* dir, float* out3) {
+    store3(out3, support_map_test(type, load3(scale), load3(dir)));
+}
+
 const char* orc_version(void) { return "oracle-r1"; }
 
 }  // extern "C"

@@ -87,6 +87,23 @@ def test_shapes_on_plane_bit_exact(oracle_lib, cuda_lib):
     _assert_exact(*out, model)
 
 
+@pytest.mark.parametrize("world_count", [1, 7])
+def test_box_stacks_bit_exact(oracle_lib, cuda_lib, world_count):
+    """Config 2 scene (reduced stack count): box-box pairs through MPR + 4-point manifolds, plane-box analytic."""
+    model = scenes.box_stack_model(world_count, seed=0)
+    out = _both(model, 100, 1.0 / 60 / 4, {"iterations": 4}, oracle_lib)
+    _assert_exact(*out, model)
+    assert out[2][-1] == 20 * world_count  # 4 contacts on each of the 5 interfaces of every stack
+
+
+def test_convex_pile_bit_exact(oracle_lib, cuda_lib):
+    """Every pair class of the generic convex path (box-box, capsule-box, cylinder-cylinder, cylinder-box,
+    ellipsoid-box/sphere/ellipsoid) tumbling for 150 substeps: MPR, GJK fallback, manifold clipping, axial roll."""
+    model = scenes.convex_pile_model(4, seed=5)
+    out = _both(model, 150, 1.0 / 240, {"iterations": 4}, oracle_lib)
+    _assert_exact(*out, model)
+
+
 def test_implicit_single_world_and_no_contacts(oracle_lib, cuda_lib):
     """Model built without begin_world() (all entities in world -1) and step(contacts=None)."""
     b = ModelBuilder()

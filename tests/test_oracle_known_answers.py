@@ -305,3 +305,127 @@ def test_featherstone_double_pendulum_energy(oracle_lib):
     assert abs(e1 - e0) / abs(e0) < 0.01
     q = s0.body_q.numpy()
     assert np.all(np.abs(q[:, 0]) < 1e-5) and np.all(q[:, 2] < 5.0 + 1e-4)  # stays in its plane, below the pivot
+
+
+# ---- generic convex path: MPR / GJK cores + manifold ------------------------------------------------------------
+# (the oracle compiles newton_b200/csrc/nb2_convex.cuh for the host; these reference known answers pin that the
+#  algorithm written there is the reference's - see oracle/oracle_gjk.h)
+
+def test_mpr_box_support_tie_boundary(oracle_lib):
+    """newton/tests/test_mpr.py:173-190: witnesses stay valid just below / above the box support tie threshold."""
+    tie_eps = 1.0e-6  # _CENTERED_BOX_SUPPORT_TIE_EPSILON (support_function.py:41)
+    angles = tie_eps * np.array([0.5, 2.0], dtype=np.float32)
+    for a in angles:
+        q = [math.sin(0.5 * a), 0.0, 0.0, math.cos(0.5 * a)]
+        hit, pa, pb, n, pen = oracle_lib.mpr_core(GeoType.BOX, [0.5] * 3, GeoType.BOX, [0.5] * 3, [0.0, 0.999, 0.0], q)
+        assert hit == 1
+        assert np.linalg.norm(n) == pytest.approx(1.0, abs=1e-6)
+        np.testing.assert_allclose(n, [0.0, 1.0, 0.0], atol=1e-5)
+        assert pen == pytest.approx(0.5 + 0.5 * (math.cos(a) + math.sin(a)) - 0.999, abs=2e-5)
+        assert float(np.dot(pb - pa, n)) == pytest.approx(-pen, abs=1e-6)
+
+
+def test_gjk_cylinder_barrel_support(oracle_lib):
+    """newton/tests/test_gjk.py:128-158."""
+    r, hh, br = 0.5, 1.0, 2.0
+    eq = r + br - math.sqrt(br**2 - hh**2)
+    np.testing.assert_allclose(oracle_lib.support_map(GeoType.CYLINDER, (r, hh, 0.0), (1, 0, 0)), (r, 0, 0), atol=1e-6)
+    np.testing.assert_allclose(oracle_lib.support_map(GeoType.CYLINDER, (r, hh, br), (1, 0, 0)), (eq, 0, 0), atol=1e-6)
+    np.testing.assert_allclose(oracle_lib.support_map(GeoType.CYLINDER, (r, hh, br), (0, 0, 1)), (r, 0, hh), atol=1e-6)
+    d = np.array([1.0, 0.0, 0.25])
+    sz = br * d[2] / np.linalg.norm(d)
+    sr = r - math.sqrt(br**2 - hh**2) + math.sqrt(br**2 - sz**2)
+    np.testing.assert_allclose(oracle_lib.support_map(GeoType.CYLINDER, (r, hh, br), d), (sr, 0.0, sz), atol=1e-6)
+
+
+def test_gjk_distance_cases(oracle_lib):
+    """newton/tests/test_gjk.py:160-235 (COLLIDE_EPSILON 1e-6 as in the reference's kernel; B's pose relative to A)."""
+    q = [0, 0, 0, 1]
+    sep, _, _, _, dist = oracle_lib.gjk_core(GeoType.SPHERE, (1, 0, 0), GeoType.SPHERE, (1, 0, 0), [3, 0, 0], q, eps=1e-6)
+    assert sep == 1 and dist == pytest.approx(1.0, abs=1e-5)
+    sep, _, _, _, dist = oracle_lib.gjk_core(GeoType.SPHERE, (1, 0, 0), GeoType.SPHERE, (1, 0, 0), [2, 0, 0], q, eps=1e-6)
+    assert dist == pytest.approx(0.0, abs=1e-5)
+    sep, _, _, _, dist = oracle_lib.gjk_core(GeoType.SPHERE, (3, 0, 0), GeoType.SPHERE, (3, 0, 0), [4, 0, 0], q, eps=1e-6)
+    assert sep == 0 and dist == pytest.approx(0.0, abs=1e-5)  # overlapping -> "collision"
+    sep, _, _, n, dist = oracle_lib.gjk_core(GeoType.BOX, (1, 1, 1), GeoType.BOX, (1, 1, 1), [4.5, 0, 0], q, eps=1e-6)
+    assert sep == 1 and dist == pytest.approx(2.5, abs=1e-5)
+    np.testing.assert_allclose(n, [1, 0, 0], atol=1e-5)
+
+
+def _dist_to_box(p, pos, half):
+    d = np.abs(np.asarray(p) - np.asarray(pos)) - np.asarray(half)
+    return float(np.linalg.norm(np.maximum(d, 0.0)) + min(max(d[0], d[1], d[2]), 0.0))
+
+
+def test_narrow_phase_box_box_face(oracle_lib):
+    """newton/tests/test_narrow_phase.py:707-778: overlap 0.2 along X, normal A->B, midpoint surface reconstruction."""
+    cnt, dist, pos, n = oracle_lib.convex_pair(GeoType.BOX, (1, 1, 1), _xf([0, 0, 0]), GeoType.BOX, (1, 1, 1), _xf([1.8, 0, 0]))
+    assert cnt == 4  # full face manifold
+    for i in range(cnt):
+        assert np.linalg.norm(n[i]) == pytest.approx(1.0, abs=1e-5)
+        assert n[i][0] > 0.9
+        assert dist[i] == pytest.approx(-0.2, abs=1e-4)  # reference bar: places=1
+        # check_surface_reconstruction: centre +- n*d/2 lie on the two surfaces
+        assert abs(_dist_to_box(pos[i] - n[i] * dist[i] * 0.5, [0, 0, 0], [1, 1, 1])) < 1e-4
+        assert abs(_dist_to_box(pos[i] + n[i] * dist[i] * 0.5, [1.8, 0, 0], [1, 1, 1])) < 1e-4
+
+
+def test_narrow_phase_box_box_edge(oracle_lib):
+    """newton/tests/test_narrow_phase.py:780-799: box rotated 45 deg about Z at x = 1.2 -> edge contact, unit normal."""
+    a = math.pi / 4.0
+    cnt, dist, pos, n = oracle_lib.convex_pair(GeoType.BOX, (0.5,) * 3, _xf([0, 0, 0]), GeoType.BOX, (0.5,) * 3,
+                                               _xf([1.2, 0, 0], (0.0, 0.0, math.sin(a / 2), math.cos(a / 2))))
+    assert cnt > 0
+    assert np.linalg.norm(n[0]) == pytest.approx(1.0, abs=1e-5)
+    np.testing.assert_allclose(n[0], [1, 0, 0], atol=1e-4)
+    assert dist[0] == pytest.approx(1.2 - 0.5 - 0.5 * math.sqrt(2.0), abs=1e-4)  # edge x = 1.2 - 0.7071 vs face x = 0.5
+
+
+def test_narrow_phase_ellipsoids(oracle_lib):
+    """newton/tests/test_narrow_phase.py:1677-1950 (ellipsoid pairs always take the GJK/MPR route)."""
+    E = GeoType.ELLIPSOID
+    # separated: no contact or positive distance (:1677-1704)
+    cnt, dist, _, n = oracle_lib.convex_pair(E, (1.0, 0.5, 0.3), _xf([0, 0, 0]), E, (1.0, 0.5, 0.3), _xf([3.0, 0, 0]), gap_sum=0.0)
+    assert cnt == 0 or dist[0] > 0.0
+    # penetrating 0.2 along X (:1706-1741)
+    cnt, dist, _, n = oracle_lib.convex_pair(E, (1.0, 0.5, 0.3), _xf([0, 0, 0]), E, (1.0, 0.5, 0.3), _xf([1.8, 0, 0]))
+    assert cnt == 1 and dist[0] == pytest.approx(-0.2, abs=1e-3)
+    assert np.linalg.norm(n[0]) == pytest.approx(1.0, abs=1e-5) and n[0][0] > 0.99
+    # sphere-like ellipsoids behave like spheres (:1913-1950)
+    cnt, dist, _, n = oracle_lib.convex_pair(E, (1, 1, 1), _xf([0, 0, 0]), E, (1, 1, 1), _xf([1.8, 0, 0]))
+    assert cnt == 1 and dist[0] == pytest.approx(-0.2, abs=1e-3) and n[0][0] == pytest.approx(1.0, abs=1e-3)
+    # ellipsoid vs sphere: type-sorted so the sphere is shape A (:1743-1787), normal from the sphere to the ellipsoid
+    cnt, dist, _, n = oracle_lib.convex_pair(GeoType.SPHERE, (0.5, 0.5, 0.5), _xf([1.4, 0, 0]), E, (1.0, 0.5, 0.3), _xf([0, 0, 0]))
+    assert cnt == 1 and dist[0] == pytest.approx(-0.1, abs=1e-3) and n[0][0] < -0.99
+    # ellipsoid vs box / capsule produce unit normals (:1789-1880)
+    cnt, dist, _, n = oracle_lib.convex_pair(E, (1.0, 0.5, 0.3), _xf([0, 0, 0]), GeoType.BOX, (0.5, 0.5, 0.5), _xf([1.3, 0, 0]))
+    assert cnt >= 1 and dist[0] == pytest.approx(-0.2, abs=1e-3) and np.linalg.norm(n[0]) == pytest.approx(1.0, abs=1e-5)
+    cnt, dist, _, n = oracle_lib.convex_pair(GeoType.CAPSULE, (0.5, 1.0, 0.0), _xf([1.3, 0, 0]), E, (1.0, 0.5, 0.3), _xf([0, 0, 0]))
+    assert cnt >= 1 and np.linalg.norm(n[0]) == pytest.approx(1.0, abs=1e-5)
+
+
+def test_xpbd_aligned_box_stack_remains_stable(oracle_lib):
+    """newton/tests/test_solver_xpbd.py:1791-1840: an aligned five-box stack (up axis Y) stays upright for 180 frames;
+    MPR must keep four-point face manifolds as solver-scale quaternion drift crosses zero."""
+    b = ModelBuilder(up_axis="Y")
+    b.add_ground_plane()
+    for i in range(5):
+        body = b.add_body(xform=X.transform((0.0, 0.5 + i, 0.0)))
+        b.add_shape_box(body, hx=0.5, hy=0.5, hz=0.5)
+    model = b.finalize()
+    solver = oracle_lib.SolverXPBD(model, iterations=4)
+    s0, s1, ctl = model.state(), model.state(), model.control()
+    pipe = oracle_lib.CollisionPipeline(model)
+    contacts = pipe.contacts()
+    dt = 1.0 / 60.0 / 4
+    for _ in range(180 * 4):
+        s0.clear_forces()
+        pipe.collide(s0, contacts)
+        solver.step(s0, s1, ctl, contacts, dt)
+        s0, s1 = s1, s0
+    bq = s0.body_q.numpy()
+    assert np.all(np.isfinite(bq))
+    assert int(contacts.rigid_contact_count[0]) == 20  # 4-point manifolds on all five interfaces
+    np.testing.assert_allclose(bq[:, 1], 0.5 + np.arange(5), atol=2.0e-2)
+    assert float(np.max(np.linalg.norm(bq[:, (0, 2)], axis=1))) < 1.0e-2
+    assert float(np.max(np.linalg.norm(bq[:, 3:][:, (0, 2)], axis=1))) < 1.0e-3
