@@ -32,12 +32,55 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 ENVS_PER_GPU = 4096
-SUBSTEPS = 4
 ITERATIONS = 8
-FPS = 50
-DT = 1.0 / FPS / SUBSTEPS
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
+
+# The headline (default) workload is BASELINE.json configs[2]; the other two configs that fit one GPU are selectable
+# with --workload for the per-config numbers recorded in profiles/ (they are not the bench line the driver reads).
+WORKLOADS = {
+    "quadruped_xpbd": dict(
+        config="BASELINE.json configs[2]", scene="quadruped", solver="xpbd", envs=4096, substeps=4, fps=50, kernel="xpbd_step_kernel",
+        text="quadruped (Anymal-class, 13 bodies/18 dofs) envs, SolverXPBD iterations=8",
+        # state in (13 x 76 B) + out (13 x 52 B) + control (220 B) + one read of each 80-byte contact
+        alg_bytes=lambda n_c: 1884.0 + 80.0 * n_c),
+    "box_stacks_xpbd": dict(
+        config="BASELINE.json configs[1]", scene="stacks", solver="xpbd", envs=512, substeps=4, fps=60, kernel="xpbd_step_kernel",
+        text="5-box stack envs (box-box MPR manifolds + plane-box), SolverXPBD iterations=8",
+        alg_bytes=lambda n_c: 5 * 76.0 + 5 * 52.0 + 80.0 * n_c),
+    "quadruped_featherstone": dict(
+        config="BASELINE.json configs[3]", scene="quadruped", solver="featherstone", envs=4096, substeps=8, fps=50,
+        kernel="featherstone_step_kernel",
+        text="quadruped (Anymal-class, 13 bodies/18 dofs) envs, SolverFeatherstone (dense H = J^T M J, Cholesky), penalty contacts",
+        # joint_q/qd in+out (2 x 148 B) + body_f in (312) + body_q/qd out (676) + control (220) + 112-byte contacts
+        alg_bytes=lambda n_c: 296.0 + 312.0 + 676.0 + 220.0 + 112.0 * n_c),
+}
+WL = WORKLOADS["quadruped_xpbd"]
+SUBSTEPS = WL["substeps"]
+FPS = WL["fps"]
+DT = 1.0 / FPS / SUBSTEPS
+
+
+def select_workload(name):
+    global WL, SUBSTEPS, FPS, DT
+    WL = WORKLOADS[name]
+    SUBSTEPS, FPS = WL["substeps"], WL["fps"]
+    DT = 1.0 / FPS / SUBSTEPS
+
+
+def build_scene(envs, seed):
+    from newton_b200 import scenes
+
+    if WL["scene"] == "quadruped":
+        return scenes.quadruped_model(envs, device="cpu", seed=seed)
+    return scenes.box_stack_model(envs, device="cpu", seed=seed)
+
+
+def make_solver(pkg, model):
+    """pkg is newton_b200.solvers (product) or the oracle module (CPU checker)."""
+    if WL["solver"] == "xpbd":
+        return pkg.SolverXPBD(model, iterations=ITERATIONS)
+    return pkg.SolverFeatherstone(model)
 
 
 def parse_args():
@@ -46,16 +89,21 @@ def parse_args():
     p.add_argument("--steps", type=int, default=1000)
     p.add_argument("--warmup", type=int, default=20)
     p.add_argument("--impl", default="native", choices=["native", "reference"])
-    p.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU (weak scaling)")
+    p.add_argument("--envs", type=int, default=None, help="environments per GPU (weak scaling); default: the workload's")
+    p.add_argument("--workload", default="quadruped_xpbd", choices=sorted(WORKLOADS))
     p.add_argument("--fast-fp", action="store_true", help="use the FMA-contracted twin library (not bit-exact vs the oracle)")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    return p.parse_args()
+    a = p.parse_args()
+    select_workload(a.workload)
+    if a.envs is None:
+        a.envs = WL["envs"]
+    return a
 
 
 def workload_config(envs, n_gpus):
     return {
-        "workload": f"{envs * n_gpus} quadruped (Anymal-class, 13 bodies/18 dofs) envs, SolverXPBD iterations={ITERATIONS}, "
-                    f"{SUBSTEPS} substeps/frame @ {FPS} fps, explicit broad phase, ground plane; BASELINE.json configs[2]"
+        "workload": f"{envs * n_gpus} {WL['text']}, "
+                    f"{SUBSTEPS} substeps/frame @ {FPS} fps, explicit broad phase, ground plane; {WL['config']}"
                     + ("" if n_gpus == 1 else f" sharded {envs}/GPU (configs[4] layout)"),
         "envs_per_gpu": envs,
         "substeps_per_step": SUBSTEPS,
@@ -141,9 +189,9 @@ def run_native(args):
 
     envs = args.envs
     # every rank owns `envs` worlds (weak scaling); per-rank seed so shards differ like slices of one big scene
-    model = scenes.quadruped_model(envs, device="cpu", seed=1 + rank).to(dev)
+    model = build_scene(envs, seed=1 + rank).to(dev)
     pipeline = newton_b200.CollisionPipeline(model)
-    solver = newton_b200.solvers.SolverXPBD(model, iterations=ITERATIONS)
+    solver = make_solver(newton_b200.solvers, model)
     state_0, state_1 = model.state(), model.state()
     control = model.control()
     contacts = pipeline.contacts()
@@ -230,7 +278,7 @@ def run_native(args):
     h2d = h_target.numel() * 4 + h_jf.numel() * 4
     d2h = h_q.numel() * 4 + h_qd.numel() * 4
 
-    # ---- roofline of the dominant kernel (xpbd_step_kernel): CUDA events around single launches on this stream
+    # ---- roofline of the dominant kernel (the fused solver kernel): CUDA events around single launches on this stream
     n_c = float(contacts.rigid_contact_count.item()) / envs
     reps = 40
     evs = []
@@ -247,9 +295,9 @@ def run_native(args):
         evs.append((a, b))
     torch.cuda.synchronize()
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-    # algorithmic bytes per env-substep of the solver kernel: state in (988) + out (676) +
-    # control (220) + one read of each 80-byte contact; the matching contact write belongs to the collide kernel
-    alg_bytes_env = 1884.0 + 80.0 * n_c
+    # algorithmic bytes per env-substep of the solver kernel; the matching contact
+    # write belongs to the collide kernel
+    alg_bytes_env = WL["alg_bytes"](n_c)
     achieved = alg_bytes_env * envs / (kern_ms * 1e-3) / 1e9
     peaks = {}
     try:
@@ -259,7 +307,7 @@ def run_native(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     roofline = {
-        "bound": "hbm", "kernel": "xpbd_step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "bound": "hbm", "kernel": WL["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": None, "peak_source": "measured" if peaks else "fallback",
         "algorithmic_bytes_per_env_substep": alg_bytes_env, "kernel_ms": kern_ms, "contacts_per_env": n_c,
     }
@@ -297,12 +345,12 @@ def oracle_throughput(envs: int, frames: int, threads: int) -> dict:
     threads = max(1, min(threads, envs))
     per = envs // threads
     envs = per * threads
-    base = scenes.quadruped_model(envs, device="cpu", seed=1)
+    base = build_scene(envs, seed=1)
     shards = [base.shard(r, threads) for r in range(threads)] if threads > 1 else [base]
 
     def make(m):
-        return dict(m=m, pipe=oracle.CollisionPipeline(m), solver=oracle.SolverXPBD(m, iterations=ITERATIONS), s0=m.state(),
-                    s1=m.state(), ctrl=m.control())
+        return dict(m=m, pipe=oracle.CollisionPipeline(m), solver=make_solver(oracle, m), s0=m.state(), s1=m.state(),
+                    ctrl=m.control())
 
     ctx = [make(m) for m in shards]
     for c in ctx:

@@ -1,9 +1,12 @@
-"""Forward kinematics joint_q -> body_q (host side, NumPy).
+"""Forward kinematics joint_q -> body_q: ``newton.eval_fk``.
 
 Mirrors ``eval_single_articulation_fk`` of the reference (``newton/_src/sim/articulation.py:237-432``):
 ``X_wc = X_wp * X_pj * X_j(q) * X_cj^-1`` walked in joint order, body twists reported as COM twists.
-Called once before the simulation loop by the examples (``example_basic_urdf.py:87``); SURVEY.md
-§8(f) lists the batched device version as the first "next" row.
+Called once before the simulation loop by the examples (``example_basic_urdf.py:87``) and on resets.
+
+Models on a CUDA device run the ``eval_fk_kernel`` of the native library through ``nb2_eval_fk`` (one thread per
+articulation; SURVEY.md §8(f) first "next" row).  Models still on the host - the builder finalizes on the CPU
+before ``Model.to(device)`` - use the NumPy walk below, which is scene-construction code, not a simulation path.
 """
 
 from __future__ import annotations
@@ -20,6 +23,22 @@ def eval_fk(model, joint_q, joint_qd, state) -> None:
 
     ``state`` may be the model itself (as in ``newton.eval_fk(model, model.joint_q, model.joint_qd, model)``).
     """
+    if state.body_q.is_cuda:
+        import ctypes as C
+
+        from .. import _abi, _lib
+
+        nm = _lib.native_model(model)
+        jq = joint_q.contiguous()
+        jqd = joint_qd.contiguous()
+        with torch.cuda.device(nm.device_index):
+            _lib.check(
+                _lib.lib().nb2_eval_fk(nm.handle, C.c_void_p(_abi.ptr(jq)), C.c_void_p(_abi.ptr(jqd)),
+                                       C.c_void_p(_abi.ptr(state.body_q)), C.c_void_p(_abi.ptr(state.body_qd)),
+                                       _lib.current_stream_ptr(model)),
+                "nb2_eval_fk",
+            )
+        return
     q = joint_q.detach().cpu().numpy().astype(np.float64)
     qd = joint_qd.detach().cpu().numpy().astype(np.float64)
     jt = model.numpy("joint_type")

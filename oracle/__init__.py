@@ -211,6 +211,13 @@ def support_map(geo_type, scale, direction):
     return out
 
 
+def eval_fk(model, joint_q, joint_qd, state):
+    """newton.eval_fk: writes state.body_q / state.body_qd (state may be the model)."""
+    d = _abi.model_desc(model)
+    lib().orc_eval_fk(C.byref(d), C.c_void_p(_abi.ptr(joint_q)), C.c_void_p(_abi.ptr(joint_qd)),
+                      C.c_void_p(_abi.ptr(state.body_q)), C.c_void_p(_abi.ptr(state.body_qd)))
+
+
 def shape_aabbs(model, body_q):
     d = _abi.model_desc(model)
     lo = np.zeros((model.shape_count, 3), dtype=np.float32)

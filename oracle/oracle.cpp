@@ -195,6 +195,11 @@ void orc_support_map(int type, const float* scale, const float* dir, float* out3
     store3(out3, support_map_test(type, load3(scale), load3(dir)));
 }
 
+// newton.eval_fk(model, joint_q, joint_qd, state)
+void orc_eval_fk(const nb2_model_desc* m, const float* joint_q, const float* joint_qd, float* body_q, float* body_qd) {
+    eval_articulation_fk(*m, joint_q, joint_qd, body_q, body_qd);
+}
+
 const char* orc_version(void) { return "oracle-r1"; }
 
 }  // extern "C"

@@ -662,4 +662,63 @@ inline void featherstone_step(FsScratch& s, const nb2_model_desc& m, const nb2_f
     s.step += 1;
 }
 
+// ---- public newton.eval_fk (sim/articulation.py:237-424 eval_single_articulation_fk, all articulations, no mask) ------------
+// joint_qd in the PUBLIC convention (FREE/DISTANCE linear dofs = child COM velocity).
+inline void eval_articulation_fk(const nb2_model_desc& m, const float* joint_q, const float* joint_qd, float* body_q, float* body_qd) {
+    for (int a = 0; a < m.articulation_count; ++a)
+        for (int i = m.articulation_start[a]; i < m.articulation_start[a + 1]; ++i) {
+            if (m.joint_articulation[i] == -1) continue;
+            int parent = m.joint_parent[i], child = m.joint_child[i], type = m.joint_type[i];
+            int qs = m.joint_q_start[i], qds = m.joint_qd_start[i];
+            int lin = m.joint_dof_dim[2 * i], ang = m.joint_dof_dim[2 * i + 1];
+            transform X_j = jcalc_transform(m, type, qds, lin, ang, joint_q, qs);
+            vec3 vj_lin, vj_ang;
+            auto axis = [&](int k) { return load3(m.joint_axis + 3 * k); };
+            if (type == JT_PRISMATIC) vj_lin = axis(qds) * joint_qd[qds];
+            if (type == JT_REVOLUTE) vj_ang = axis(qds) * joint_qd[qds];
+            if (type == JT_BALL) vj_ang = vec3(joint_qd[qds], joint_qd[qds + 1], joint_qd[qds + 2]);
+            if (type == JT_FREE || type == JT_DISTANCE) {
+                vj_lin = vec3(joint_qd[qds], joint_qd[qds + 1], joint_qd[qds + 2]);
+                vj_ang = vec3(joint_qd[qds + 3], joint_qd[qds + 4], joint_qd[qds + 5]);
+            }
+            if (type == JT_D6) {
+                for (int k = 0; k < 3; ++k)
+                    if (lin > k) vj_lin += axis(qds + k) * joint_qd[qds + k];
+                int iq = qs + lin, iqd = qds + lin;
+                if (ang == 1) vj_ang = joint_qd[iqd] * axis(iqd);
+                if (ang == 3) {
+                    quat rot;
+                    compute_3d_rotational_dofs(axis(iqd), axis(iqd + 1), axis(iqd + 2), joint_q[iq], joint_q[iq + 1], joint_q[iq + 2],
+                                               joint_qd[iqd], joint_qd[iqd + 1], joint_qd[iqd + 2], rot, vj_ang);
+                }
+            }
+            transform X_wpj = transform::load(m.joint_X_p + 7 * i);
+            transform X_wp;
+            if (parent >= 0) {
+                X_wp = transform::load(body_q + 7 * parent);
+                X_wpj = X_wp * X_wpj;
+            }
+            transform X_wcj = X_wpj * X_j;
+            transform X_wc = X_wcj * transform_inverse(transform::load(m.joint_X_c + 7 * i));
+            vec3 x_child_origin = X_wc.p;
+            vec3 v_parent_origin, w_parent;
+            if (parent >= 0) {
+                spatial v_wp = spatial::load(body_qd + 6 * parent);
+                w_parent = v_wp.bot;
+                v_parent_origin = velocity_at_point(v_wp, x_child_origin - transform_point(X_wp, load3(m.body_com + 3 * parent)));
+            }
+            vec3 linear_joint_world = transform_vector(X_wpj, vj_lin);
+            vec3 angular_joint_world = transform_vector(X_wpj, vj_ang);
+            vec3 linear_joint_origin;
+            if (type == JT_FREE || type == JT_DISTANCE)  // com_twist_to_origin_twist
+                linear_joint_origin = linear_joint_world - cross(angular_joint_world, transform_vector(X_wc, load3(m.body_com + 3 * child)));
+            else
+                linear_joint_origin = linear_joint_world + cross(angular_joint_world, x_child_origin - X_wcj.p);
+            vec3 v_o = v_parent_origin + linear_joint_origin, w_o = w_parent + angular_joint_world;
+            X_wc.store(body_q + 7 * child);
+            vec3 v_com = cross(w_o, transform_vector(X_wc, load3(m.body_com + 3 * child))) + v_o;  // origin_twist_to_com_twist
+            spatial(v_com, w_o).store(body_qd + 6 * child);
+        }
+}
+
 }  // namespace orc

@@ -5,9 +5,14 @@ import newton_b200
 from newton_b200 import scenes, _lib
 E = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 its = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-model = scenes.quadruped_model(E, seed=1).to("cuda:0")
+scene = sys.argv[3] if len(sys.argv) > 3 else "quad"
+solver_name = sys.argv[4] if len(sys.argv) > 4 else "xpbd"
+model = (scenes.quadruped_model(E, seed=1) if scene == "quad" else scenes.box_stack_model(E, seed=0)).to("cuda:0")
 pipe = newton_b200.CollisionPipeline(model)
-solver = newton_b200.solvers.SolverXPBD(model, iterations=its)
+if solver_name == "xpbd":
+    solver = newton_b200.solvers.SolverXPBD(model, iterations=its)
+else:
+    solver = newton_b200.solvers.SolverFeatherstone(model)
 s0, s1, ctrl, contacts = model.state(), model.state(), model.control(), pipe.contacts()
 def frame():
     global s0, s1
@@ -27,7 +32,7 @@ a.record()
 for _ in range(N): g.replay()
 b.record(); torch.cuda.synchronize()
 ms = a.elapsed_time(b) / N
-print(f"envs={E} iters={its}: frame {ms*1e3:.1f} us  -> {E*4/ms*1e3/1e6:.2f} M env-steps/s  contacts/env={contacts.rigid_contact_count.item()/E:.1f}")
+print(f"scene={scene} solver={solver_name} envs={E} iters={its}: frame {ms*1e3:.1f} us  -> {E*4/ms*1e3/1e6:.2f} M env-steps/s  contacts/env={contacts.rigid_contact_count.item()/E:.1f}")
 # kernel-only timings
 def t(fn, n=100):
     for _ in range(10): fn()

@@ -121,3 +121,24 @@ def test_two_rank_gloo_state_gather(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-3000:]
     assert "GATHER_OK" in out.stdout
+
+
+def test_oracle_eval_fk_matches_host_walk(oracle_lib):
+    """The fp32 oracle restatement of newton.eval_fk (sim/articulation.py:237-424) against the independent float64
+    NumPy walk the builder uses: quadruped (FREE + 12 REVOLUTE per env) and the double pendulum, random velocities."""
+    import torch
+
+    import newton_b200
+    from newton_b200 import scenes
+
+    for model in (scenes.quadruped_model(3, seed=1), scenes.pendulum_model()):
+        g = torch.Generator().manual_seed(0)
+        model.joint_qd.copy_(torch.rand(model.joint_qd.shape, generator=g) - 0.5)
+        model.joint_q[-2:] += 0.3
+        newton_b200.eval_fk(model, model.joint_q, model.joint_qd, model)
+        host_q, host_qd = model.body_q.clone(), model.body_qd.clone()
+        model.body_q.zero_()
+        model.body_qd.zero_()
+        oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, model)
+        np.testing.assert_allclose(model.body_q.numpy(), host_q.numpy(), atol=2e-6)
+        np.testing.assert_allclose(model.body_qd.numpy(), host_qd.numpy(), atol=2e-6)

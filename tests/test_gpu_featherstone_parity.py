@@ -76,3 +76,17 @@ def test_mixed_joint_types(oracle_lib, cuda_lib):
     model.joint_qd.copy_(torch.rand(model.joint_qd.shape, generator=g) * 0.4 - 0.2)
     model.joint_f.copy_(torch.rand(model.joint_f.shape, generator=g) * 0.2 - 0.1)
     _compare(model, oracle_lib, 100, 1e-3, {"angular_damping": 0.0}, collide=False)
+
+
+def test_eval_fk_kernel_bit_exact(oracle_lib, cuda_lib):
+    """nb2_eval_fk (one thread per articulation) vs the oracle's newton.eval_fk, random joint velocities."""
+    for model in (scenes.quadruped_model(37, seed=3), scenes.pendulum_model()):
+        g = torch.Generator().manual_seed(1)
+        model.joint_qd.copy_(torch.rand(model.joint_qd.shape, generator=g) - 0.5)
+        mg = model.to("cuda:0")
+        mg.body_q.zero_()
+        mg.body_qd.zero_()
+        newton_b200.eval_fk(mg, mg.joint_q, mg.joint_qd, mg)
+        oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, model)
+        np.testing.assert_array_equal(mg.body_q.cpu().numpy(), model.body_q.numpy())
+        np.testing.assert_array_equal(mg.body_qd.cpu().numpy(), model.body_qd.numpy())
