@@ -62,5 +62,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(tag: str, defines: list[str], strict: bool = True, sources=None) -> str:
+    """Experiment helper: builds ``libnewton_b200_<tag>.so`` with extra ``-D`` flags (select it with ``NB2_LIB``)."""
+    lib_path = os.path.join(HERE, f"libnewton_b200_{tag}.so")
+    flags = NVCC_FLAGS + (STRICT_FLAGS if strict else []) + list(defines)
+    procs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(CSRC, src.replace(".cu", f".{tag}.o"))
+        objs.append(obj)
+        procs.append((src, subprocess.Popen([_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj], stdout=subprocess.PIPE,
+                                            stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(out)
+            raise RuntimeError(f"nvcc failed on {src} ({tag})")
+    subprocess.run([_nvcc(), "-shared", "-o", lib_path, *objs, "-lcudart"], check=True)
+    return lib_path
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose="-v" in sys.argv))

@@ -228,7 +228,7 @@ NB2_DEV FsSmem fs_carve(float* base, const DevModel& M) {
 }
 
 template <int L>
-__global__ void __launch_bounds__(32, 12) featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view sin, nb2_state_view sout,
+__global__ void __launch_bounds__(32, 14) featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view sin, nb2_state_view sout,
                                                                     nb2_control_view ctl, int use_contacts, int update_mass, float dt) {
     constexpr int G = 32 / L;
     extern __shared__ float smem[];

@@ -27,11 +27,28 @@ enum { BODY_KINEMATIC = 2 };
 enum { BR_Q = 0, BR_QD = 7, BR_COM = 13, BR_INVM = 16, BR_INVI = 17, BR_I = 26, BR_SIZE = 35 };
 enum { DR_SIZE = 13 };  // delta record: lin_a, ang_a, lin_b, ang_b, active
 
+// Code-size control.  The first kernel version inlined and unrolled everything: 9 400 SASS instructions (150 KB) and
+// 19 % of the stall samples on instruction fetch (profiles/r1a_xpbd_step_kernel.txt).  Measured on B200 (round-1c A/B,
+// profiles/r1c_xpbd_code_size_ab.txt): keeping the 3-row joint loops rolled (8 200 instr.) and/or turning the shared
+// helpers into real calls (6 900 instr.) changes the kernel time by < 1 % - the fetch stalls come from 14 one-warp CTAs
+// per SM each walking its own place in the code, not from the absolute size.  The rolled loops are kept (smaller, same
+// speed); -DNB2_XPBD_NOINLINE / -DNB2_XPBD_UNROLLED rebuild the other variants.
+#ifdef NB2_XPBD_NOINLINE
+#define NB2_HELPER __host__ __device__ __noinline__
+#else
+#define NB2_HELPER NB2_DEV
+#endif
+#ifdef NB2_XPBD_UNROLLED
+#define NB2_ROW_UNROLL _Pragma("unroll")
+#else
+#define NB2_ROW_UNROLL _Pragma("unroll 1")
+#endif
+
 struct BodyView {
     Xf X;
     V3 com;
     float inv_m;
-    M33 inv_I;
+    const float* rec;  // shared-memory record (inverse inertia is read from it on demand); nullptr = the static world
     V3 v, w;
 };
 
@@ -42,14 +59,23 @@ NB2_DEV BodyView load_body(const float* rec) {
     b.w = ld3(rec + BR_QD + 3);
     b.com = ld3(rec + BR_COM);
     b.inv_m = rec[BR_INVM];
-    b.inv_I = ldm(rec + BR_INVI);
+    b.rec = rec;
     return b;
 }
 NB2_DEV BodyView static_body() {  // body index -1: the world
     BodyView b;
     b.inv_m = 0.f;
-    b.inv_I = m33_zero();
+    b.rec = nullptr;
     return b;
+}
+
+// r^T I^-1 r with r = ang rotated into the body frame: the angular term of the generalized inverse mass.  For the static
+// world the reference multiplies by a zero inverse inertia; the sum is +-0 and adding it leaves the denominator unchanged.
+NB2_HELPER float ang_inv_mass(const float* rec, V3 ang) {
+    if (rec == nullptr) return 0.0f;
+    const Q4 q(rec[BR_Q + 3], rec[BR_Q + 4], rec[BR_Q + 5], rec[BR_Q + 6]);
+    const V3 r = qrot_inv(q, ang);
+    return dot(r, mv(ldm(rec + BR_INVI), r));
 }
 
 // shared denominators of compute_contact_constraint_delta / compute_positional_correction (kernels.py:2063-2075)
@@ -57,10 +83,8 @@ NB2_DEV float generalized_inv_mass(const BodyView& a, const BodyView& b, V3 lin_
     float denom = 0.0f;
     denom += len2(lin_a) * a.inv_m;
     denom += len2(lin_b) * b.inv_m;
-    V3 ra = qrot_inv(a.X.q, ang_a);
-    V3 rb = qrot_inv(b.X.q, ang_b);
-    denom += dot(ra, mv(a.inv_I, ra));
-    denom += dot(rb, mv(b.inv_I, rb));
+    denom += ang_inv_mass(a.rec, ang_a);
+    denom += ang_inv_mass(b.rec, ang_b);
     return denom;
 }
 NB2_DEV float contact_delta(float err, const BodyView& a, const BodyView& b, V3 lin_a, V3 lin_b, V3 ang_a, V3 ang_b, float relaxation,
@@ -81,10 +105,8 @@ NB2_DEV float positional_correction(float err, float derr, const BodyView& a, co
 NB2_DEV float angular_correction(float err, float derr, const BodyView& a, const BodyView& b, V3 ang_a, V3 ang_b, float compliance,
                                  float damping, float dt) {
     float denom = 0.0f;
-    V3 ra = qrot_inv(a.X.q, ang_a);
-    V3 rb = qrot_inv(b.X.q, ang_b);
-    denom += dot(ra, mv(a.inv_I, ra));
-    denom += dot(rb, mv(b.inv_I, rb));
+    denom += ang_inv_mass(a.rec, ang_a);
+    denom += ang_inv_mass(b.rec, ang_b);
     float alpha = compliance, gamma = compliance * damping;
     float dl = -(err + alpha * 0.0f + gamma * derr);
     if (denom + alpha > 0.0f) dl /= (dt + gamma) * denom + alpha / dt;
@@ -215,13 +237,13 @@ NB2_DEV bool solve_joint(const nb2_model_desc& d, const nb2_control_view& ctl, c
             else if (e > up) proj.set(dim, up);
             else if (s.stiffness.get(dim) > 0.0f) proj.set(dim, clamp_w(s.target_pos.get(dim), lo, up));
         }
-        const M33 frame_p = qmat(X_wp.q);
         const V3 r_p = xpoint(X_wp, proj) - wcom_p;
         const V3 r_c = x_c - wcom_c;
-#pragma unroll
+        NB2_ROW_UNROLL
         for (int dim = 0; dim < 3; ++dim) {
             float e = rel_p.get(dim);
-            V3 lc(frame_p.at(0, dim), frame_p.at(1, dim), frame_p.at(2, dim));
+            // column `dim` of quat_to_matrix(X_wp.q), i.e. the rotated basis vector
+            V3 lc = qrot(X_wp.q, V3(dim == 0 ? 1.f : 0.f, dim == 1 ? 1.f : 0.f, dim == 2 ? 1.f : 0.f));
             V3 lp = -lc, ap = -cross(r_p, lc), ac = cross(r_c, lc);
             float derr = dot(lp, vel_p) + dot(lc, vel_c) + dot(ap, omega_p) + dot(ac, omega_c);
             float err = 0.0f, compliance = P.joint_linear_compliance, damping = 0.0f;
@@ -279,7 +301,7 @@ NB2_DEV bool solve_joint(const nb2_model_desc& d, const nb2_control_view& ctl, c
         }
         const AxisSetup s = gather_axes(d, ctl, axis_start, target_start, lin_count, ang_count);
         const Q4 qc_inv = qconj(q_c);
-#pragma unroll
+        NB2_ROW_UNROLL
         for (int dim = 0; dim < 3; ++dim) {
             float e = dim == 0 ? err_0 : (dim == 1 ? err_1 : err_2);
             Q4 grad = dim == 0 ? g0 : (dim == 1 ? g1 : g2);
@@ -376,7 +398,7 @@ NB2_DEV void store_deltas(float* rec, const Deltas& dl, float active) {
 }
 
 // apply_body_deltas for one body held in shared memory (kernels.py:864-933), in place.
-NB2_DEV void apply_delta(float* rec, V3 dlin, V3 dang, float inv_weight, bool weighted, float dt) {
+NB2_HELPER void apply_delta(float* rec, V3 dlin, V3 dang, float inv_weight, bool weighted, float dt) {
     const float inv_m = rec[BR_INVM];
     if (inv_m == 0.0f) return;
     const M33 inv_I = ldm(rec + BR_INVI), I = ldm(rec + BR_I);
