@@ -32,7 +32,7 @@ NB2_DEV V3 support_box(V3 scale, V3 dir) {  // support_function.py:121-129
     return V3((dir.x >= -th ? 1.0f : -1.0f) * scale.x, (dir.y >= -th ? 1.0f : -1.0f) * scale.y, (dir.z >= -th ? 1.0f : -1.0f) * scale.z);
 }
 
-NB2_DEV V3 support_map(const ConvexGeom& g, V3 d) {  // support_function.py:133-352
+NB2_CALL V3 support_map(const ConvexGeom& g, V3 d) {  // support_function.py:133-352
     const float eps = 1.0e-12f;
     if (g.type == CG_BOX) return support_box(g.scale, d);
     if (g.type == CG_SPHERE) {
@@ -100,7 +100,7 @@ NB2_DEV V3 support_map(const ConvexGeom& g, V3 d) {  // support_function.py:133-
 }
 
 // shape_support with center_ties=True (support_function.py:397-431): MPR only
-NB2_DEV V3 support_ties(const ConvexGeom& g, V3 d) {
+NB2_CALL V3 support_ties(const ConvexGeom& g, V3 d) {
     if (g.type != CG_BOX) return support_map(g, d);
     V3 r = support_box(g.scale, d);
     const V3 c = cmul(vabs(d), g.scale);
@@ -118,7 +118,7 @@ NB2_DEV V3 mvert_a(const MVert& v) { return v.B + v.BtoA; }
 
 // minkowski_support (mpr.py:110-150); TIES selects the MPR flavour of the shape support
 template <bool TIES>
-NB2_DEV MVert mink_support(const ConvexGeom& ga, const ConvexGeom& gb, V3 dir, Q4 qb, V3 pb, float extend) {
+NB2_CALL MVert mink_support(const ConvexGeom& ga, const ConvexGeom& gb, V3 dir, Q4 qb, V3 pb, float extend) {
     MVert v;
     V3 pa = TIES ? support_ties(ga, dir) : support_map(ga, dir);
     const V3 nd = -dir;
@@ -259,7 +259,7 @@ struct Simplex {
 };
 NB2_DEV void bc_clear(float* bc) { bc[0] = bc[1] = bc[2] = bc[3] = 0.0f; }
 
-NB2_DEV V3 closest_segment(const Simplex& s, int i0, int i1, float* bc, unsigned& mask) {  // :104-150
+NB2_CALL V3 closest_segment(const Simplex& s, int i0, int i1, float* bc, unsigned& mask) {  // :104-150
     const float EPS = 1e-8f;
     const V3 a = s.D[i0], b = s.D[i1];
     const V3 edge = b - a;
@@ -283,7 +283,7 @@ NB2_DEV V3 closest_segment(const Simplex& s, int i0, int i1, float* bc, unsigned
     return l0 * a + l1 * b;
 }
 
-NB2_DEV V3 closest_triangle(const Simplex& s, int i0, int i1, int i2, float* bc, unsigned& mask) {  // :152-230
+NB2_CALL V3 closest_triangle(const Simplex& s, int i0, int i1, int i2, float* bc, unsigned& mask) {  // :152-230
     const float EPS = 1e-8f;
     const V3 a = s.D[i0], b = s.D[i1], c = s.D[i2];
     const V3 u = a - b, w = a - c;
@@ -491,7 +491,7 @@ NB2_DEV float len2p(P2 a, P2 b) {
     return dx * dx + dy * dy;
 }
 
-NB2_DEV int trim_in_place(P2 s0, P2 s1, P2* loop, int loop_count) {  // multicontact.py:339-411
+NB2_CALL int trim_in_place(P2 s0, P2 s1, P2* loop, int loop_count) {  // multicontact.py:339-411
     if (loop_count < 3) return loop_count;
     P2 ia{0.f, 0.f}, ib{0.f, 0.f};
     int change_a = -1, change_b = -1;
@@ -586,7 +586,7 @@ NB2_DEV int trim_all_in_place(P2* trim, int trim_count, P2* loop, int loop_count
     return cur;
 }
 
-NB2_DEV void calipers_quad(const P2* hull, int n, int out[4]) {  // approx_max_quadrilateral_area_with_calipers :486-560
+NB2_CALL void calipers_quad(const P2* hull, int n, int out[4]) {  // approx_max_quadrilateral_area_with_calipers :486-560
     int p1 = 0, p3 = 1;
     float max_d2 = len2p(hull[p1], hull[p3]);
     const float tie = 1.0e-3f;
@@ -680,7 +680,7 @@ NB2_DEV V3 ray_plane(V3 o, V3 dir, float pd, V3 pn) {  // :107-127
 }
 
 // post_process_axial_on_discrete_contact (collision_core.py:174-277)
-NB2_DEV void post_process_contact(V3& center, float& dist, V3 normal, float reff_a, float reff_b, int ta, V3 sca, V3 pos_a, Q4 rot_a, int tb,
+NB2_CALL void post_process_contact(V3& center, float& dist, V3 normal, float reff_a, float reff_b, int ta, V3 sca, V3 pos_a, Q4 rot_a, int tb,
                                   V3 scb, V3 pos_b, Q4 rot_b) {
     if (ta == CG_SPHERE || ta == CG_CAPSULE) {
         center = center + normal * (reff_a * 0.5f);

@@ -10,11 +10,13 @@
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
 #define NB2_DEV __host__ __device__ __forceinline__
+#define NB2_CALL __host__ __device__ __noinline__  // one shared copy of a big routine (code size matters for 1-warp CTAs)
 #else
 // Host-only compilation (g++): lets the CPU oracle compile the single-source convex-contact routines of
 // nb2_convex.cuh with -ffp-contract=off, i.e. the arithmetic of the strict-fp CUDA build.
 #include <cmath>
 #define NB2_DEV inline
+#define NB2_CALL inline
 #ifndef NB2_STRICT_FP
 #define NB2_STRICT_FP 1
 #endif
