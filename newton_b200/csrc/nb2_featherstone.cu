@@ -195,11 +195,14 @@ NB2_DEV Xf joint_transform(const nb2_model_desc& d, int type, int axis_start, in
 }
 
 struct FsSmem {
-    float *bq, *bqc, *vs, *as, *fb, *ft, *fe, *qdfk, *Is, *so, *fs, *S, *qd_in, *jf, *tau, *qdd, *qd_out, *H, *jq;
+    float *bq, *bqc, *vs, *as, *fb, *ft, *fe, *qdfk, *Is, *so, *fs, *S, *qd_in, *jf, *tau, *qdd, *qd_out, *H, *jq, *P;
+    int* dofj;
+    unsigned long long *anc, *desc;  // ancestor-or-self / descendant-or-self bit masks of the env's joints (8-byte aligned)
 };
 NB2_DEV size_t fs_smem_floats(const DevModel& M) {
-    return size_t(M.max_env_bodies) * (7 + 7 + 6 * 6 + 36 + 3) + size_t(M.max_env_joints) * 6 + size_t(M.max_env_dofs) * (6 + 5) +
-           size_t(M.max_env_H) + size_t(M.max_env_coords);
+    const size_t n = size_t(M.max_env_bodies) * (7 + 7 + 6 * 6 + 36 + 3 + 6) + size_t(M.max_env_joints) * 6 +
+                     size_t(M.max_env_dofs) * (6 + 5 + 1) + size_t(M.max_env_H) + size_t(M.max_env_coords);
+    return ((n + 1) & ~size_t(1)) + 4 * size_t(M.max_env_joints);  // even float count, then two u64 per joint
 }
 NB2_DEV FsSmem fs_carve(float* base, const DevModel& M) {
     FsSmem s;
@@ -223,7 +226,12 @@ NB2_DEV FsSmem fs_carve(float* base, const DevModel& M) {
     s.qdd = p; p += nd;
     s.qd_out = p; p += nd;
     s.H = p; p += M.max_env_H;
-    s.jq = p;
+    s.jq = p; p += M.max_env_coords;
+    s.P = p; p += nb * 6;
+    s.dofj = reinterpret_cast<int*>(p); p += nd;
+    p = base + (((p - base) + 1) & ~ptrdiff_t(1));
+    s.anc = reinterpret_cast<unsigned long long*>(p);
+    s.desc = s.anc + nj;
     return s;
 }
 
@@ -534,17 +542,32 @@ __global__ void __launch_bounds__(32, 14) featherstone_step_kernel(DevModel M, n
         float* H = sm.H + M.art_H_start[art];
         float* Lg = M.fs_L + M.env_H_start[env] + M.art_H_start[art];
         if (update_mass) {
-            for (int e = l; e < n * n; e += L) {
-                const int ra = e / n, cbb = e % n;
-                // joints owning dof ra / cbb
-                int ja = aj0, jb = aj0;
-                while (d.joint_qd_start[ja + 1] - ad0 <= ra) ++ja;
-                while (d.joint_qd_start[jb + 1] - ad0 <= cbb) ++jb;
-                const unsigned long long need = (1ull << (ja - aj0)) | (1ull << (jb - aj0));
-                const S6 Sa = ld6(sm.S + 6 * (ad0 - d0 + ra)), Sb = ld6(sm.S + 6 * (ad0 - d0 + cbb));
-                float sum = 0.0f;
-                for (int i = 0; i < anj; ++i) {
-                    if ((M.joint_anc_mask[aj0 + i] & need) != need) continue;
+            // H = J^T (M J), lower triangle only (all dense_cholesky reads), one column at a time:
+            //   P[:, b] = M J[:, b]  -> the 6-vectors I_i S_b of the bodies below joint(b), staged in shared memory
+            //   H[a, b] = sum_i sum_r S_a[r] P[6i+r, b] over bodies below joint(a) AND joint(b), in (i, r) order -
+            // the summation order of the reference's dense_gemm pair (kernels.py:1504-1538) minus its exact-zero terms, so
+            // the result is bit-identical while M J is formed once per column instead of once per entry.
+            for (int e = l; e < n * n; e += L) H[e] = 0.0f;
+            for (int i = l; i < anj; i += L) sm.anc[i] = M.joint_anc_mask[aj0 + i];
+            for (int i = l; i < n; i += L) {  // dof -> articulation-local joint
+                int ja = aj0;
+                while (d.joint_qd_start[ja + 1] - ad0 <= i) ++ja;
+                sm.dofj[ad0 - d0 + i] = ja - aj0;
+            }
+            __syncwarp(gmask);
+            // descendant-or-self sets (bit i = body i hangs below joint j): the bodies whose block of M J touches dof row a
+            for (int j = l; j < anj; j += L) {
+                unsigned long long m = 0ull;
+                for (int i = 0; i < anj; ++i) m |= ((sm.anc[i] >> j) & 1ull) << i;
+                sm.desc[j] = m;
+            }
+            __syncwarp(gmask);
+            const int* dofj = sm.dofj + (ad0 - d0);
+            for (int cbb = 0; cbb < n; ++cbb) {
+                const int jb = dofj[cbb];
+                const S6 Sb = ld6(sm.S + 6 * (ad0 - d0 + cbb));
+                for (int i = l; i < anj; i += L) {
+                    if (((sm.anc[i] >> jb) & 1ull) == 0ull) continue;
                     // NB: the reference's spatial_mass indexes body_I_s by JOINT index (kernels.py:1476-1477)
                     const float* Is = sm.Is + 36 * (aj0 + i - b0);
 #pragma unroll
@@ -552,10 +575,28 @@ __global__ void __launch_bounds__(32, 14) featherstone_step_kernel(DevModel M, n
                         float pr = 0.0f;  // P[6i+r, b] = sum_k M[6i+r, 6i+k] J[6i+k, b]
 #pragma unroll
                         for (int k = 0; k < 6; ++k) pr += Is[6 * r + k] * Sb.v[k];
-                        sum += Sa.v[r] * pr;
+                        sm.P[6 * i + r] = pr;
                     }
                 }
-                H[e] = sum;
+                __syncwarp(gmask);
+                for (int ra = cbb + l; ra < n; ra += L) {
+                    const int ja = dofj[ra];
+                    float sum = 0.0f;
+                    // rows come after columns in dof order, so joint(a) is never a proper ancestor of joint(b): the bodies below
+                    // both joints are desc(ja) when jb is an ancestor-or-self of ja, none otherwise
+                    if ((sm.anc[ja] >> jb) & 1ull) {
+                        const S6 Sa = ld6(sm.S + 6 * (ad0 - d0 + ra));
+                        unsigned long long m = sm.desc[ja];
+                        while (m) {  // ascending body order = the reference's summation order
+                            const int i = __ffsll((long long)m) - 1;
+                            m &= m - 1ull;
+#pragma unroll
+                            for (int r = 0; r < 6; ++r) sum += Sa.v[r] * sm.P[6 * i + r];
+                        }
+                    }
+                    H[ra * n + cbb] = sum;
+                }
+                __syncwarp(gmask);
             }
             __syncwarp(gmask);
             // dense_cholesky (kernels.py:1690-1719), in place on the lower triangle; columns in order, rows in parallel
@@ -582,14 +623,22 @@ __global__ void __launch_bounds__(32, 14) featherstone_step_kernel(DevModel M, n
         }
         __syncwarp(gmask);
         // dense_subs (kernels.py:1754-1781): forward then backward substitution, serial (order-preserving)
-        if (l == 0) {
+        {   // forward substitution, column-oriented: as soon as x[j] is final every later row subtracts L[i,j] x[j] - each row
+            // still performs its subtractions in ascending j and divides last, i.e. the serial loop's arithmetic
             float* x = sm.qdd + (ad0 - d0);
             const float* bvec = sm.tau + (ad0 - d0);
-            for (int i = 0; i < n; ++i) {
-                float t = bvec[i];
-                for (int j = 0; j < i; ++j) t -= H[i * n + j] * x[j];
-                x[i] = t / H[i * n + i];
+            for (int i = l; i < n; i += L) x[i] = bvec[i];
+            __syncwarp(gmask);
+            for (int j = 0; j < n; ++j) {
+                if (l == j % L) x[j] = x[j] / H[j * n + j];
+                __syncwarp(gmask);
+                const float xj = x[j];
+                for (int i = j + 1 + ((l - (j + 1)) % L + L) % L; i < n; i += L) x[i] -= H[i * n + j] * xj;  // rows > j owned by this lane
             }
+            __syncwarp(gmask);
+        }
+        if (l == 0) {  // backward substitution: every row needs ALL later unknowns before its first (ascending-order) subtraction
+            float* x = sm.qdd + (ad0 - d0);
             for (int i = n - 1; i >= 0; --i) {
                 float t = x[i];
                 for (int j = i + 1; j < n; ++j) t -= H[j * n + i] * x[j];
@@ -754,8 +803,7 @@ static nb2_status launch_fs_L(nb2_model* m, const nb2_featherstone_params& p, co
     const DevModel& M = m->dev;
     const int G = 32 / L;
     const int blocks = (M.env_count + G - 1) / G;
-    const size_t per_env = size_t(M.max_env_bodies) * (7 + 7 + 6 * 6 + 36 + 3) + size_t(M.max_env_joints) * 6 + size_t(M.max_env_dofs) * (6 + 5) +
-                           size_t(M.max_env_H) + size_t(M.max_env_coords);
+    const size_t per_env = fs_smem_floats(M);
     const size_t smem = per_env * G * sizeof(float);
     if (smem > 220 * 1024) {
         set_error("featherstone_step: environment too large for the fused shared-memory kernel");

@@ -8,6 +8,7 @@ its = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 scene = sys.argv[3] if len(sys.argv) > 3 else "quad"
 solver_name = sys.argv[4] if len(sys.argv) > 4 else "xpbd"
 model = (scenes.quadruped_model(E, seed=1) if scene == "quad" else scenes.box_stack_model(E, seed=0)).to("cuda:0")
+DT = 0.005 if solver_name == "xpbd" else 0.0025
 pipe = newton_b200.CollisionPipeline(model)
 if solver_name == "xpbd":
     solver = newton_b200.solvers.SolverXPBD(model, iterations=its)
@@ -17,7 +18,7 @@ s0, s1, ctrl, contacts = model.state(), model.state(), model.control(), pipe.con
 def frame():
     global s0, s1
     for _ in range(4):
-        s0.clear_forces(); pipe.collide(s0, contacts); solver.step(s0, s1, ctrl, contacts, 0.005); s0, s1 = s1, s0
+        s0.clear_forces(); pipe.collide(s0, contacts); solver.step(s0, s1, ctrl, contacts, DT); s0, s1 = s1, s0
 st = torch.cuda.Stream()
 with torch.cuda.stream(st):
     for _ in range(60): frame()
@@ -39,4 +40,4 @@ def t(fn, n=100):
     torch.cuda.synchronize(); a.record()
     for _ in range(n): fn()
     b.record(); torch.cuda.synchronize(); return a.elapsed_time(b)/n*1e3
-print("collide(+export) us:", t(lambda: pipe.collide(s0, contacts)), " xpbd_step us:", t(lambda: solver.step(s0, s1, ctrl, contacts, 0.005)))
+print("collide(+export) us:", t(lambda: pipe.collide(s0, contacts)), " xpbd_step us:", t(lambda: solver.step(s0, s1, ctrl, contacts, DT)))
