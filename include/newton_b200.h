@@ -142,6 +142,7 @@ typedef struct nb2_contacts_view {
     float* margin0;
     float* margin1;
     int32_t* tids;
+    float* force; /* optional Contacts.force, spatial_vector[rigid_contact_max] (sim/contacts.py:264-276), may be NULL */
 } nb2_contacts_view;
 
 /* Constructor kwargs of reference SolverXPBD (solvers/xpbd/solver_xpbd.py:99-116). */
@@ -155,6 +156,8 @@ typedef struct nb2_xpbd_params {
     int32_t rigid_contact_con_weighting;
     float angular_damping;
     int32_t enable_restitution;
+    /* SolverXPBD.compute_body_velocity_from_position_delta (solver_xpbd.py:171, attribute, default False) */
+    int32_t compute_body_velocity_from_position_delta;
 } nb2_xpbd_params;
 
 /* Constructor kwargs of reference SolverFeatherstone (solvers/featherstone/solver_featherstone.py:135-146). */
@@ -193,12 +196,22 @@ int32_t nb2_model_rigid_contact_max(const nb2_model* model);
 nb2_status nb2_collide(nb2_model* model, const float* body_q, const nb2_contacts_view* contacts, void* cuda_stream);
 
 /* Reference SolverXPBD.step(state_in, state_out, control, contacts, dt) (solver_xpbd.py:329-862).
- * `use_contacts` = 0 mirrors `contacts=None`.  Contacts come from the last nb2_collide() on this model.
- * Writes state_out.body_q/body_qd; like the reference it may also overwrite state_in.body_q/body_qd
+ * `use_contacts` bit 0: 0 mirrors `contacts=None`; contacts come from the last nb2_collide() on this model.
+ * `use_contacts` bit 1 (NB2_XPBD_CONTACT_IMPULSE): accumulate the weighted per-contact impulses the reference keeps
+ * when `contacts.force` is allocated (solver_xpbd.py:370-375, kernels.py:2402-2461) for nb2_xpbd_update_contacts.
+ * Writes state_out.body_q/body_qd, and state_out.body_parent_f when that pointer is non-NULL
+ * (kernels.py:2497-2544); like the reference it may also overwrite state_in.body_q/body_qd
  * (ping-pong scratch, solver_xpbd.py:290-300). */
+#define NB2_XPBD_USE_CONTACTS 1
+#define NB2_XPBD_CONTACT_IMPULSE 2
 nb2_status nb2_xpbd_step(nb2_model* model, const nb2_xpbd_params* params, const nb2_state_view* state_in,
                          const nb2_state_view* state_out, const nb2_control_view* control, int32_t use_contacts,
                          float dt, void* cuda_stream);
+
+/* Reference SolverXPBD.update_contacts(contacts) (solver_xpbd.py:864-925, convert_contact_impulse_to_force
+ * kernels.py:2464-2494): contacts->force[i] = accumulated impulse of exported contact i / dt of the last
+ * nb2_xpbd_step that ran with NB2_XPBD_CONTACT_IMPULSE; rows at and beyond the contact count are zeroed. */
+nb2_status nb2_xpbd_update_contacts(nb2_model* model, const nb2_contacts_view* contacts, void* cuda_stream);
 
 /* Reference SolverBase.integrate_bodies (solvers/solver.py:267-307; kernel :112-170). */
 nb2_status nb2_integrate_bodies(nb2_model* model, const nb2_state_view* state_in, const nb2_state_view* state_out,

@@ -135,6 +135,7 @@ class ContactsView(C.Structure):
         ("margin0", C.c_void_p),
         ("margin1", C.c_void_p),
         ("tids", C.c_void_p),
+        ("force", C.c_void_p),
     ]
 
 
@@ -149,6 +150,7 @@ class XPBDParams(C.Structure):
         ("rigid_contact_con_weighting", C.c_int32),
         ("angular_damping", C.c_float),
         ("enable_restitution", C.c_int32),
+        ("compute_body_velocity_from_position_delta", C.c_int32),
     ]
 
 
@@ -199,4 +201,6 @@ def contacts_view(contacts) -> ContactsView:
     v.rigid_contact_count = ptr(contacts.rigid_contact_count)
     for short in ("shape0", "shape1", "point0", "point1", "offset0", "offset1", "normal", "margin0", "margin1", "tids"):
         setattr(v, short, ptr(getattr(contacts, "rigid_contact_" + short)))
+    force = getattr(contacts, "force", None)
+    v.force = ptr(force) if force is not None else None
     return v

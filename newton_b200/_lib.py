@@ -19,7 +19,7 @@ STATUS = {0: "NB2_OK", 1: "NB2_ERR_INVALID_ARGUMENT", 2: "NB2_ERR_UNSUPPORTED", 
 # every symbol include/newton_b200.h declares
 EXPORTED_SYMBOLS = (
     "nb2_model_create", "nb2_model_destroy", "nb2_model_notify_changed", "nb2_model_rigid_contact_max", "nb2_collide",
-    "nb2_xpbd_step", "nb2_integrate_bodies", "nb2_featherstone_step", "nb2_eval_fk", "nb2_last_error",
+    "nb2_xpbd_step", "nb2_xpbd_update_contacts", "nb2_integrate_bodies", "nb2_featherstone_step", "nb2_eval_fk", "nb2_last_error",
     "nb2_kernel_launch_count", "nb2_version",
 )
 
@@ -52,6 +52,8 @@ def lib():
         L.nb2_xpbd_step.argtypes = [P, C.POINTER(_abi.XPBDParams), C.POINTER(_abi.StateView), C.POINTER(_abi.StateView),
                                     C.POINTER(_abi.ControlView), C.c_int32, C.c_float, P]
         L.nb2_xpbd_step.restype = C.c_int
+        L.nb2_xpbd_update_contacts.argtypes = [P, C.POINTER(_abi.ContactsView), P]
+        L.nb2_xpbd_update_contacts.restype = C.c_int
         L.nb2_integrate_bodies.argtypes = [P, C.POINTER(_abi.StateView), C.POINTER(_abi.StateView), C.c_float, C.c_float, P]
         L.nb2_integrate_bodies.restype = C.c_int
         L.nb2_featherstone_step.argtypes = [P, C.POINTER(_abi.FeatherstoneParams), C.POINTER(_abi.StateView),

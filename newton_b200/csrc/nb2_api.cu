@@ -330,6 +330,18 @@ static nb2_status upload_tables(nb2_model* m) {
         m->allocations.push_back(p);
         dv.fs_L = static_cast<float*>(p);
     }
+    {
+        size_t n = std::max<size_t>(size_t(dv.slot_total) * 6, 1) * sizeof(float);
+        NB2_CUDA_CHECK(cudaMalloc(&p, n));
+        NB2_CUDA_CHECK(cudaMemset(p, 0, n));
+        m->allocations.push_back(p);
+        dv.contact_impulse = static_cast<float*>(p);
+        n = std::max<size_t>(size_t(dv.d.joint_count) * 6, 1) * sizeof(float);
+        NB2_CUDA_CHECK(cudaMalloc(&p, n));
+        NB2_CUDA_CHECK(cudaMemset(p, 0, n));
+        m->allocations.push_back(p);
+        dv.joint_impulse = static_cast<float*>(p);
+    }
     size_t cb_bytes = std::max<size_t>(size_t(dv.slot_total) * CF_COUNT, 1) * sizeof(float);
     NB2_CUDA_CHECK(cudaMalloc(&p, cb_bytes));
     NB2_CUDA_CHECK(cudaMemset(p, 0, cb_bytes));
@@ -416,12 +428,21 @@ nb2_status nb2_xpbd_step(nb2_model* model, const nb2_xpbd_params* params, const 
         set_error("nb2_xpbd_step: iterations must be >= 0 and dt > 0");
         return NB2_ERR_INVALID_ARGUMENT;
     }
-    if (params->enable_restitution) {
-        set_error("nb2_xpbd_step: enable_restitution is not implemented yet");
-        return NB2_ERR_UNSUPPORTED;
-    }
+    if ((use_contacts & NB2_XPBD_CONTACT_IMPULSE) && (use_contacts & NB2_XPBD_USE_CONTACTS)) model->xpbd_impulse_dt = dt;
     return launch_xpbd_step(model, *params, *state_in, *state_out, *control, use_contacts, dt,
                             static_cast<cudaStream_t>(cuda_stream));
+}
+
+nb2_status nb2_xpbd_update_contacts(nb2_model* model, const nb2_contacts_view* contacts, void* cuda_stream) {
+    if (!model || !contacts || !contacts->force || !contacts->rigid_contact_count) {
+        set_error("nb2_xpbd_update_contacts: NULL argument (contacts.force must be allocated)");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    if (!(model->xpbd_impulse_dt > 0.0f)) {
+        set_error("nb2_xpbd_update_contacts: no contact impulse data available, run nb2_xpbd_step with NB2_XPBD_CONTACT_IMPULSE first");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    return launch_xpbd_update_contacts(model, *contacts, static_cast<cudaStream_t>(cuda_stream));
 }
 
 nb2_status nb2_integrate_bodies(nb2_model* model, const nb2_state_view* state_in, const nb2_state_view* state_out,

@@ -55,6 +55,9 @@ struct DevModel {
     const int* env_H_start;            // [E+1] global offset of the env's H/L storage (persistent L for update intervals)
     float* fs_L;                       // persistent Cholesky factors [env_H_start[E]]
     int max_depth, max_env_dofs, max_env_coords, max_env_H, max_env_arts;
+    // XPBD reporting scratch (row a17): weighted contact impulses (6 planes of slot_total) and per-joint child-side impulses
+    float* contact_impulse;
+    float* joint_impulse;  // [6 * joint_count]
 };
 
 struct HostTables {
@@ -77,6 +80,7 @@ struct nb2_model {
     std::vector<void*> allocations;
     int lanes_per_env = 32;  // sub-warp group width used by the fused kernels
     int featherstone_step_count = 0;
+    float xpbd_impulse_dt = 0.0f;  // dt of the last nb2_xpbd_step that accumulated contact impulses (0 = none yet)
 };
 
 namespace nb2 {
@@ -85,6 +89,7 @@ void count_launch(int n = 1);
 nb2_status launch_collide(nb2_model* m, const float* body_q, const nb2_contacts_view* contacts, cudaStream_t s);
 nb2_status launch_xpbd_step(nb2_model* m, const nb2_xpbd_params& p, const nb2_state_view& in, const nb2_state_view& out,
                             const nb2_control_view& ctl, int use_contacts, float dt, cudaStream_t s);
+nb2_status launch_xpbd_update_contacts(nb2_model* m, const nb2_contacts_view& contacts, cudaStream_t s);
 nb2_status launch_integrate_bodies(nb2_model* m, const nb2_state_view& in, const nb2_state_view& out, float angular_damping,
                                    float dt, cudaStream_t s);
 nb2_status launch_featherstone_step(nb2_model* m, const nb2_featherstone_params& p, const nb2_state_view& in,

@@ -429,9 +429,16 @@ NB2_HELPER void apply_delta(float* rec, V3 dlin, V3 dang, float inv_weight, bool
     st3(rec + BR_QD + 3, w1);
 }
 
-template <int L>
+// EX = false: the plain step.  EX = true adds the reporting / post-processing paths of row a17 (restitution, velocity from
+// position delta, weighted contact impulses for Contacts.force, joint impulses for State.body_parent_f); it is a second
+// instantiation so the plain step pays neither registers nor shared memory for them.
+template <int L, bool EX>
 __global__ void __launch_bounds__(32, 16) xpbd_step_kernel(DevModel M, nb2_xpbd_params P, nb2_state_view sin, nb2_state_view sout,
-                                                        nb2_control_view ctl, int use_contacts, float dt) {
+                                                        nb2_control_view ctl, int use_contacts_flags, float dt) {
+    const int use_contacts = use_contacts_flags & NB2_XPBD_USE_CONTACTS;
+    const bool want_cimp = EX && use_contacts && (use_contacts_flags & NB2_XPBD_CONTACT_IMPULSE);
+    const bool want_jimp = EX && sout.body_parent_f != nullptr;
+    const bool want_init = EX && (P.enable_restitution || P.compute_body_velocity_from_position_delta);
     constexpr int G = 32 / L;
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31;
@@ -440,10 +447,12 @@ __global__ void __launch_bounds__(32, 16) xpbd_step_kernel(DevModel M, nb2_xpbd_
     const bool live = env < M.env_count;
     const nb2_model_desc& d = M.d;
     const int rec_cap = max(M.max_env_contact_slots, M.max_env_joints);
-    const int per_env = M.max_env_bodies * BR_SIZE + rec_cap * DR_SIZE + M.max_env_contact_slots;
+    const int per_env = M.max_env_bodies * BR_SIZE + rec_cap * DR_SIZE + M.max_env_contact_slots + (EX ? M.max_env_bodies * 14 : 0);
     float* bodies = smem + size_t(grp) * per_env;
     float* drec = bodies + M.max_env_bodies * BR_SIZE;
     int* cpair = reinterpret_cast<int*>(drec + rec_cap * DR_SIZE);
+    float* init_qd = reinterpret_cast<float*>(cpair + M.max_env_contact_slots);  // EX only: state_in poses + twists (13/body)
+    float* bcnt = init_qd + M.max_env_bodies * 13;                                 // EX only: active contacts per body
 
     int b0 = 0, nb = 0, j0 = 0, nj = 0, slot0 = 0, nc = 0;
     if (live) {
@@ -472,10 +481,17 @@ __global__ void __launch_bounds__(32, 16) xpbd_step_kernel(DevModel M, nb2_xpbd_
             rec[BR_I + k] = d.body_inertia[9 * gb + k];
         }
     }
+    if (want_init)
+        for (int b = l; b < nb; b += L)
+#pragma unroll
+            for (int k = 0; k < 13; ++k) init_qd[b * 13 + k] = bodies[b * BR_SIZE + BR_Q + k];  // q (7) then qd (6) are adjacent
     for (int c = l; c < nc; c += L) {
         const size_t T = size_t(M.slot_total);
         int ba = __float_as_int(M.cb[CF_BODY_A * T + slot0 + c]), bb = __float_as_int(M.cb[CF_BODY_B * T + slot0 + c]);
         cpair[c] = (ba & 0xffff) | (bb << 16);
+        if (want_cimp)
+#pragma unroll
+            for (int k = 0; k < 6; ++k) M.contact_impulse[k * T + slot0 + c] = 0.0f;
     }
     __syncwarp();
     // ---- apply_joint_forces: per-joint wrenches, then ordered per-body accumulation into a body_f copy ----
@@ -484,6 +500,12 @@ __global__ void __launch_bounds__(32, 16) xpbd_step_kernel(DevModel M, nb2_xpbd_
         bool act = joint_force_wrench(d, ctl.joint_f, j0 + j, b0, bodies, w);
         if (!act) w = Deltas();
         store_deltas(drec + j * DR_SIZE, w, act ? 1.0f : 0.0f);
+        if (want_jimp) {  // child-side wrench * dt opens the joint's impulse accumulator (kernels.py:1018-1019, 1074-1075)
+            float* ji = M.joint_impulse + 6 * size_t(j0 + j);
+            const V3 a = V3() + w.lin_c * dt, t = V3() + w.ang_c * dt;
+            st3(ji, a);
+            st3(ji + 3, t);
+        }
     }
     __syncwarp();
     // ---- integrate_bodies (solver.py:64-107) ----------------------------------------------------
@@ -627,8 +649,31 @@ __global__ void __launch_bounds__(32, 16) xpbd_step_kernel(DevModel M, nb2_xpbd_
                     if (bb == b) { dlin += ld3(r + 6); dang += ld3(r + 9); cnt += 1.0f; }
                 }
                 apply_delta(bodies + b * BR_SIZE, dlin, dang, cnt, P.rigid_contact_con_weighting != 0, dt);
+                if (want_cimp) bcnt[b] = cnt;
             }
             __syncwarp();
+            if (want_cimp) {  // accumulate_weighted_contact_impulse (kernels.py:2402-2461)
+                for (int c = l; c < nc; c += L) {
+                    const float* r = drec + c * DR_SIZE;
+                    if (r[12] == 0.0f) continue;  // inactive this iteration: the reference adds an exact zero
+                    const int pr = cpair[c];
+                    const int ba = int(short(pr & 0xffff)), bb = pr >> 16;
+                    float weight = 1.0f;
+                    if (P.rigid_contact_con_weighting) {
+                        const float n_a = ba >= 0 ? bcnt[ba] : 0.0f, n_b = bb >= 0 ? bcnt[bb] : 0.0f;
+                        const float n_sum = n_a + n_b;
+                        if (n_sum > 0.0f) {
+                            if (n_a == 0.0f) weight = 1.0f / n_b;
+                            else if (n_b == 0.0f) weight = 1.0f / n_a;
+                            else weight = 2.0f / n_sum;
+                        }
+                    }
+                    float* ci = M.contact_impulse + slot0 + c;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) ci[k * T] = ci[k * T] + r[k] * weight;  // (lin_delta_a, ang_delta_a) * weight
+                }
+                __syncwarp();
+            }
         }
         if (d.joint_count > 0) {
             // solve_body_joints (kernels.py:1513-2044)
@@ -637,6 +682,11 @@ __global__ void __launch_bounds__(32, 16) xpbd_step_kernel(DevModel M, nb2_xpbd_
                 bool act = solve_joint(d, ctl, P, j0 + j, b0, bodies, dt, dl);
                 if (!act) dl = Deltas();
                 store_deltas(drec + j * DR_SIZE, dl, act ? 1.0f : 0.0f);
+                if (want_jimp && act) {  // kernels.py:2043-2044
+                    float* ji = M.joint_impulse + 6 * size_t(j0 + j);
+                    st3(ji, ld3(ji) + dl.lin_c);
+                    st3(ji + 3, ld3(ji + 3) + dl.ang_c);
+                }
             }
             __syncwarp();
             for (int b = l; b < nb; b += L) {
@@ -654,6 +704,131 @@ __global__ void __launch_bounds__(32, 16) xpbd_step_kernel(DevModel M, nb2_xpbd_
             __syncwarp();
         }
     }
+    if (EX) {
+        // ---- State.body_parent_f (convert_joint_impulse_to_parent_f, kernels.py:2497-2544): joints in index order per child ----
+        if (sout.body_parent_f != nullptr) {
+            __syncwarp();
+            const float inv_dt = 1.0f / dt;
+            for (int b = l; b < nb; b += L) {
+                const int gb = b0 + b;
+                V3 f, t;
+                for (int k = M.body_joint_start[gb]; k < M.body_joint_start[gb + 1]; ++k) {
+                    const int e = M.body_joint_entry[k];
+                    if (!(e & 1)) continue;
+                    const int gj = j0 + (e >> 1);
+                    if (!d.joint_enabled[gj] || d.joint_type[gj] == JT_FREE) continue;
+                    const float* ji = M.joint_impulse + 6 * size_t(gj);
+                    f += ld3(ji) * inv_dt;
+                    t += ld3(ji + 3) * inv_dt;
+                }
+                st3(sout.body_parent_f + 6 * gb, f);
+                st3(sout.body_parent_f + 6 * gb + 3, t);
+            }
+        }
+        // ---- update_body_velocities (kernels.py:2547-2579); kinematic bodies keep their input state (copy_kinematic) -----------
+        if (P.compute_body_velocity_from_position_delta) {
+            for (int b = l; b < nb; b += L) {
+                if ((d.body_flags[b0 + b] & BODY_KINEMATIC) != 0) continue;
+                float* rec = bodies + b * BR_SIZE;
+                const Xf pose = ldx(rec + BR_Q), prev = ldx(init_qd + b * 13);
+                const V3 com = ld3(rec + BR_COM);
+                const V3 x_com = pose.p + qrot(pose.q, com), x_prev = prev.p + qrot(prev.q, com);
+                const V3 v = (x_com - x_prev) / dt;
+                const Q4 dq = qmul(pose.q, qconj(prev.q));
+                V3 omega = (2.0f / dt) * V3(dq.x, dq.y, dq.z);
+                if (dq.w < 0.0f) omega = -omega;
+                st3(rec + BR_QD, v);
+                st3(rec + BR_QD + 3, omega);
+            }
+            __syncwarp();
+        }
+        // ---- apply_rigid_restitution (kernels.py:2582-2728) + apply_body_delta_velocities (:936-942) ------------------------------
+        if (P.enable_restitution && use_contacts) {
+            for (int c = l; c < nc; c += L) {
+                const int s = slot0 + c;
+                const int pr = cpair[c];
+                const int ba = int(short(pr & 0xffff)), bb = pr >> 16;
+                Deltas dl;
+                float active = 0.0f;
+                if (ba != bb) {
+                    const int sa = __float_as_int(cb[CF_SHAPE0 * T + s]), sb = __float_as_int(cb[CF_SHAPE1 * T + s]);
+                    float restitution = 0.0f;
+                    restitution += d.shape_material_restitution[sa];
+                    restitution += d.shape_material_restitution[sb];
+                    restitution /= 2.0f;
+                    const float* ra_rec = ba >= 0 ? bodies + ba * BR_SIZE : nullptr;
+                    const float* rb_rec = bb >= 0 ? bodies + bb * BR_SIZE : nullptr;
+                    const Xf Xa = ba >= 0 ? ldx(init_qd + ba * 13) : Xf(), Xb = bb >= 0 ? ldx(init_qd + bb * 13) : Xf();
+                    const V3 com_a = ba >= 0 ? ld3(ra_rec + BR_COM) : V3(), com_b = bb >= 0 ? ld3(rb_rec + BR_COM) : V3();
+                    const V3 p0(cb[CF_P0X * T + s], cb[CF_P0Y * T + s], cb[CF_P0Z * T + s]);
+                    const V3 p1(cb[CF_P1X * T + s], cb[CF_P1Y * T + s], cb[CF_P1Z * T + s]);
+                    const V3 o0(cb[CF_O0X * T + s], cb[CF_O0Y * T + s], cb[CF_O0Z * T + s]);
+                    const V3 o1(cb[CF_O1X * T + s], cb[CF_O1Y * T + s], cb[CF_O1Z * T + s]);
+                    const V3 n(cb[CF_NX * T + s], cb[CF_NY * T + s], cb[CF_NZ * T + s]);
+                    const V3 bx_a = xpoint(Xa, p0 + o0), bx_b = xpoint(Xb, p1 + o1);  // contact_surface_point
+                    if (dot(n, bx_b - bx_a) < 0.0f) {
+                        const V3 r_a = bx_a - xpoint(Xa, com_a), r_b = bx_b - xpoint(Xb, com_b);
+                        V3 v_a, v_b, v_a_new, v_b_new, rxn_a, rxn_b;
+                        float inv_mass = 0.0f, m_inv_a = 0.0f, m_inv_b = 0.0f;
+                        M33 I_inv_a = m33_zero(), I_inv_b = m33_zero();
+                        if (ba >= 0) {
+                            int wi = d.body_world[b0 + ba];
+                            if (wi < 0) wi += d.gravity_count;
+                            m_inv_a = ra_rec[BR_INVM];
+                            I_inv_a = ldm(ra_rec + BR_INVI);
+                            v_a = (cross(ld3(init_qd + ba * 13 + 10), r_a) + ld3(init_qd + ba * 13 + 7)) + ld3(d.gravity + 3 * wi) * dt;
+                            v_a_new = cross(ld3(ra_rec + BR_QD + 3), r_a) + ld3(ra_rec + BR_QD);
+                            rxn_a = qrot_inv(Xa.q, cross(r_a, n));
+                            inv_mass += m_inv_a + dot(rxn_a, mv(I_inv_a, rxn_a));
+                        }
+                        if (bb >= 0) {
+                            int wi = d.body_world[b0 + bb];
+                            if (wi < 0) wi += d.gravity_count;
+                            m_inv_b = rb_rec[BR_INVM];
+                            I_inv_b = ldm(rb_rec + BR_INVI);
+                            v_b = (cross(ld3(init_qd + bb * 13 + 10), r_b) + ld3(init_qd + bb * 13 + 7)) + ld3(d.gravity + 3 * wi) * dt;
+                            v_b_new = cross(ld3(rb_rec + BR_QD + 3), r_b) + ld3(rb_rec + BR_QD);
+                            rxn_b = qrot_inv(Xb.q, cross(r_b, n));
+                            inv_mass += m_inv_b + dot(rxn_b, mv(I_inv_b, rxn_b));
+                        }
+                        const float rel_old = dot(n, v_b - v_a), rel_new = dot(n, v_b_new - v_a_new);
+                        if (inv_mass != 0.0f && rel_old < 0.0f) {
+                            const float dv = (-rel_new - restitution * rel_old) / inv_mass;
+                            active = 1.0f;
+                            if (ba >= 0) {
+                                const float dv_a = -dv;
+                                dl.lin_p = n * m_inv_a * dv_a;
+                                dl.ang_p = qrot(Xa.q, mv(I_inv_a, rxn_a) * dv_a);
+                            }
+                            if (bb >= 0) {
+                                dl.lin_c = n * m_inv_b * dv;
+                                dl.ang_c = qrot(Xb.q, mv(I_inv_b, rxn_b) * dv);
+                            }
+                        }
+                    }
+                }
+                store_deltas(drec + c * DR_SIZE, dl, active);
+            }
+            __syncwarp();
+            for (int b = l; b < nb; b += L) {
+                if ((d.body_flags[b0 + b] & BODY_KINEMATIC) != 0) continue;
+                V3 dlin, dang;
+                for (int c = 0; c < nc; ++c) {
+                    const int pr = cpair[c];
+                    const int ba = int(short(pr & 0xffff)), bb = pr >> 16;
+                    if (ba != b && bb != b) continue;
+                    const float* r = drec + c * DR_SIZE;
+                    if (r[12] == 0.0f) continue;
+                    if (ba == b) { dlin += ld3(r + 0); dang += ld3(r + 3); }
+                    if (bb == b) { dlin += ld3(r + 6); dang += ld3(r + 9); }
+                }
+                float* rec = bodies + b * BR_SIZE;
+                st3(rec + BR_QD, ld3(rec + BR_QD) + dlin);
+                st3(rec + BR_QD + 3, ld3(rec + BR_QD + 3) + dang);
+            }
+            __syncwarp();
+        }
+    }
     // ---- write back -------------------------------------------------------------------------------------
     for (int b = l; b < nb; b += L) {
         const int gb = b0 + b;
@@ -662,6 +837,21 @@ __global__ void __launch_bounds__(32, 16) xpbd_step_kernel(DevModel M, nb2_xpbd_
         for (int k = 0; k < 7; ++k) sout.body_q[7 * gb + k] = rec[BR_Q + k];
 #pragma unroll
         for (int k = 0; k < 6; ++k) sout.body_qd[6 * gb + k] = rec[BR_QD + k];
+    }
+}
+
+// SolverXPBD.update_contacts (solver_xpbd.py:864-925): force[i] = weighted impulse of exported contact i / dt
+__global__ void __launch_bounds__(128) xpbd_update_contacts_kernel(DevModel M, nb2_contacts_view out, float inv_dt) {
+    const int env = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (env >= M.env_count) return;
+    const int lane = threadIdx.x & 31;
+    const int n = M.env_contact_count[env], base = M.env_contact_offset[env], slot0 = M.env_slot_start[env];
+    const size_t T = size_t(M.slot_total);
+    for (int c = lane; c < n; c += 32) {
+        const int o = base + c;
+        if (o >= out.rigid_contact_max) break;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) out.force[6 * size_t(o) + k] = M.contact_impulse[k * T + slot0 + c] * inv_dt;
     }
 }
 
@@ -698,25 +888,26 @@ __global__ void __launch_bounds__(256) integrate_bodies_kernel(nb2_model_desc d,
     st3(sout.body_qd + 6 * b + 3, w1);
 }
 
-template <int L>
+template <int L, bool EX>
 static nb2_status launch_xpbd_L(nb2_model* m, const nb2_xpbd_params& p, const nb2_state_view& in, const nb2_state_view& out,
                                 const nb2_control_view& ctl, int use_contacts, float dt, cudaStream_t s) {
     const DevModel& M = m->dev;
     const int G = 32 / L;
     const int blocks = (M.env_count + G - 1) / G;
     const int rec_cap = std::max(M.max_env_contact_slots, M.max_env_joints);
-    const size_t per_env = size_t(M.max_env_bodies) * BR_SIZE + size_t(rec_cap) * DR_SIZE + size_t(M.max_env_contact_slots);
+    const size_t per_env = size_t(M.max_env_bodies) * BR_SIZE + size_t(rec_cap) * DR_SIZE + size_t(M.max_env_contact_slots) +
+                           (EX ? size_t(M.max_env_bodies) * 14 : 0);
     const size_t smem = per_env * G * sizeof(float);
     if (smem > 220 * 1024 || M.max_env_bodies > 32000) {
         set_error("xpbd_step: environment too large for the fused shared-memory kernel (bodies/contacts per env)");
         return NB2_ERR_CAPACITY;
     }
     if (smem > 48 * 1024)
-        NB2_CUDA_CHECK(cudaFuncSetAttribute(xpbd_step_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        NB2_CUDA_CHECK(cudaFuncSetAttribute(xpbd_step_kernel<L, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     // one-warp CTAs: ask for the largest shared-memory carve-out so ~16 CTAs (one wave of 4096 envs on 148 SMs) fit per SM
-    NB2_CUDA_CHECK(cudaFuncSetAttribute(xpbd_step_kernel<L>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    NB2_CUDA_CHECK(cudaFuncSetAttribute(xpbd_step_kernel<L, EX>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         cudaSharedmemCarveoutMaxShared));
-    xpbd_step_kernel<L><<<blocks, 32, smem, s>>>(M, p, in, out, ctl, use_contacts, dt);
+    xpbd_step_kernel<L, EX><<<blocks, 32, smem, s>>>(M, p, in, out, ctl, use_contacts, dt);
     count_launch();
     NB2_CUDA_CHECK(cudaGetLastError());
     return NB2_OK;
@@ -734,11 +925,31 @@ nb2_status launch_xpbd_step(nb2_model* m, const nb2_xpbd_params& p, const nb2_st
         set_error("nb2_xpbd_step: control arrays are NULL");
         return NB2_ERR_INVALID_ARGUMENT;
     }
-    switch (m->lanes_per_env) {
-        case 8: return launch_xpbd_L<8>(m, p, in, out, ctl, use_contacts, dt, s);
-        case 16: return launch_xpbd_L<16>(m, p, in, out, ctl, use_contacts, dt, s);
-        default: return launch_xpbd_L<32>(m, p, in, out, ctl, use_contacts, dt, s);
+    if (p.enable_restitution && !M.d.shape_material_restitution) {
+        set_error("nb2_xpbd_step: enable_restitution needs model.shape_material_restitution");
+        return NB2_ERR_INVALID_ARGUMENT;
     }
+    const bool ex = p.enable_restitution || p.compute_body_velocity_from_position_delta || out.body_parent_f != nullptr ||
+                    ((use_contacts & NB2_XPBD_CONTACT_IMPULSE) && (use_contacts & NB2_XPBD_USE_CONTACTS));
+#define NB2_XPBD_DISPATCH(LANES)                                                                        \
+    return ex ? launch_xpbd_L<LANES, true>(m, p, in, out, ctl, use_contacts, dt, s)                     \
+              : launch_xpbd_L<LANES, false>(m, p, in, out, ctl, use_contacts, dt, s)
+    switch (m->lanes_per_env) {
+        case 8: NB2_XPBD_DISPATCH(8);
+        case 16: NB2_XPBD_DISPATCH(16);
+        default: NB2_XPBD_DISPATCH(32);
+    }
+#undef NB2_XPBD_DISPATCH
+}
+
+nb2_status launch_xpbd_update_contacts(nb2_model* m, const nb2_contacts_view& contacts, cudaStream_t s) {
+    const DevModel& M = m->dev;
+    NB2_CUDA_CHECK(cudaMemsetAsync(contacts.force, 0, size_t(contacts.rigid_contact_max) * 6 * sizeof(float), s));
+    if (M.env_count == 0) return NB2_OK;
+    xpbd_update_contacts_kernel<<<(M.env_count + 3) / 4, 128, 0, s>>>(M, contacts, 1.0f / m->xpbd_impulse_dt);
+    count_launch();
+    NB2_CUDA_CHECK(cudaGetLastError());
+    return NB2_OK;
 }
 
 nb2_status launch_integrate_bodies(nb2_model* m, const nb2_state_view& in, const nb2_state_view& out, float angular_damping, float dt,

@@ -51,6 +51,7 @@ class CollisionPipeline:
         view = None
         if contacts is not None:
             contacts._nb2_blocks = self._native
+            contacts._nb2_exported = bool(self.export_contacts)
             if self.export_contacts:
                 view = C.byref(_abi.contacts_view(contacts))
         st = _lib.lib().nb2_collide(self._native.handle, C.c_void_p(_abi.ptr(state.body_q)), view,

@@ -33,12 +33,15 @@ class SolverXPBD(SolverBase):
         self.rigid_contact_con_weighting = rigid_contact_con_weighting
         self.angular_damping = angular_damping
         self.enable_restitution = enable_restitution
+        self.compute_body_velocity_from_position_delta = False  # reference attribute (solver_xpbd.py:171)
+        self._contact_impulse_capacity = None  # rigid_contact_max of the Contacts the last step accumulated impulses for
 
     def _params(self) -> _abi.XPBDParams:
         return _abi.XPBDParams(
             int(self.iterations), self.joint_linear_relaxation, self.joint_angular_relaxation,
             self.joint_linear_compliance, self.joint_angular_compliance, self.rigid_contact_relaxation,
             1 if self.rigid_contact_con_weighting else 0, self.angular_damping, 1 if self.enable_restitution else 0,
+            1 if self.compute_body_velocity_from_position_delta else 0,
         )
 
     def step(self, state_in, state_out, control, contacts, dt: float) -> None:
@@ -54,9 +57,32 @@ class SolverXPBD(SolverBase):
                     "foreign Contacts arrays into the env-major contact blocks is not implemented yet"
                 )
             use_contacts = 1
+            if getattr(contacts, "force", None) is not None:  # the reference keeps impulses when contacts.force exists
+                if not getattr(contacts, "_nb2_exported", False):
+                    raise NotImplementedError("contacts.force needs CollisionPipeline(export_contacts=True)")
+                use_contacts |= 2
+                self._contact_impulse_capacity = contacts.rigid_contact_max
         p = self._params()
         st = _lib.lib().nb2_xpbd_step(
             self._native.handle, C.byref(p), C.byref(_abi.state_view(state_in)), C.byref(_abi.state_view(state_out)),
             C.byref(_abi.control_view(control)), use_contacts, C.c_float(dt), _lib.current_stream_ptr(model),
         )
         _lib.check(st, "nb2_xpbd_step")
+
+    def update_contacts(self, contacts, state=None) -> None:
+        """Populate ``contacts.force`` from the impulses of the last :meth:`step` (reference ``solver_xpbd.py:864-925``)."""
+        if getattr(contacts, "force", None) is None:
+            raise ValueError(
+                "contacts.force is not allocated. Call model.request_contact_attributes('force') before creating the "
+                "Contacts object."
+            )
+        if self._contact_impulse_capacity is None:
+            raise ValueError("No contact impulse data available. Call step() before update_contacts().")
+        if contacts.rigid_contact_max != self._contact_impulse_capacity:
+            raise ValueError(
+                f"Contacts capacity mismatch: update_contacts() received rigid_contact_max={contacts.rigid_contact_max}, "
+                f"but step() used {self._contact_impulse_capacity}. Pass the same Contacts instance to both."
+            )
+        st = _lib.lib().nb2_xpbd_update_contacts(self._native.handle, C.byref(_abi.contacts_view(contacts)),
+                                                 _lib.current_stream_ptr(self.model))
+        _lib.check(st, "nb2_xpbd_update_contacts")

@@ -90,25 +90,47 @@ class SolverXPBD:
                  joint_angular_compliance=0.0, rigid_contact_relaxation=0.8, rigid_contact_con_weighting=True,
                  angular_damping=0.0, enable_restitution=False, deterministic=None):
         _check_cpu(model)
-        if enable_restitution:
-            raise NotImplementedError("oracle: enable_restitution")
         self.model = model
         self._desc = _abi.model_desc(model)
-        self.params = _abi.XPBDParams(iterations, joint_linear_relaxation, joint_angular_relaxation,
-                                      joint_linear_compliance, joint_angular_compliance, rigid_contact_relaxation,
-                                      1 if rigid_contact_con_weighting else 0, angular_damping, 0)
+        self.compute_body_velocity_from_position_delta = False  # attribute, solver_xpbd.py:171
+        self._args = (iterations, joint_linear_relaxation, joint_angular_relaxation, joint_linear_compliance,
+                      joint_angular_compliance, rigid_contact_relaxation, 1 if rigid_contact_con_weighting else 0,
+                      angular_damping, 1 if enable_restitution else 0)
+        self._contact_impulse = None
+        self._last_dt = None
+
+    @property
+    def params(self):
+        return _abi.XPBDParams(*self._args, 1 if self.compute_body_velocity_from_position_delta else 0)
 
     def step(self, state_in, state_out, control, contacts, dt):
         if control is None:
             control = self.model.control(clone_variables=False)
         sv_in, sv_out, cv = _abi.state_view(state_in), _abi.state_view(state_out), _abi.control_view(control)
+        imp = None
         if contacts is not None:
             ctv = _abi.contacts_view(contacts)
             ctp = C.byref(ctv)
+            if getattr(contacts, "force", None) is not None:
+                self._contact_impulse = np.zeros((contacts.rigid_contact_max, 6), dtype=np.float32)
+                imp = C.c_void_p(self._contact_impulse.ctypes.data)
         else:
             ctp = None
-        lib().orc_xpbd_step(C.byref(self._desc), C.byref(self.params), C.byref(sv_in), C.byref(sv_out), C.byref(cv), ctp,
-                            C.c_float(dt))
+        p = self.params
+        lib().orc_xpbd_step(C.byref(self._desc), C.byref(p), C.byref(sv_in), C.byref(sv_out), C.byref(cv), ctp,
+                            C.c_float(dt), imp)
+        self._last_dt = dt
+
+    def update_contacts(self, contacts, state=None):
+        """``SolverXPBD.update_contacts`` (solver_xpbd.py:864-925)."""
+        if getattr(contacts, "force", None) is None:
+            raise ValueError("contacts.force is not allocated")
+        if self._contact_impulse is None:
+            raise ValueError("No contact impulse data available. Call step() before update_contacts().")
+        if contacts.rigid_contact_max != self._contact_impulse.shape[0]:
+            raise ValueError("Contacts capacity mismatch")
+        ctv = _abi.contacts_view(contacts)
+        lib().orc_xpbd_update_contacts(C.byref(ctv), C.c_void_p(self._contact_impulse.ctypes.data), C.c_float(self._last_dt))
 
     def integrate_bodies(self, model, state_in, state_out, dt, angular_damping=0.0):
         sv_in, sv_out = _abi.state_view(state_in), _abi.state_view(state_out)

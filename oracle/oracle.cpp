@@ -79,16 +79,33 @@ void orc_integrate_bodies(const nb2_model_desc* m, const nb2_state_view* in, con
 }
 
 // SolverXPBD.step, rigid-body part (reference solver_xpbd.py:329-862).
+// contact_impulse: optional [rigid_contact_max x 6] accumulator the reference allocates when contacts.force exists
+// (solver_xpbd.py:370-375); it is zeroed here, like the per-step wp.zeros.
 void orc_xpbd_step(const nb2_model_desc* mp, const nb2_xpbd_params* p, const nb2_state_view* state_in,
-                   const nb2_state_view* state_out, const nb2_control_view* control, const nb2_contacts_view* contacts, float dt) {
+                   const nb2_state_view* state_out, const nb2_control_view* control, const nb2_contacts_view* contacts, float dt,
+                   float* contact_impulse) {
     const nb2_model_desc& m = *mp;
     if (m.body_count == 0) return;
     std::vector<float> inv_m, inv_I;
     effective_inv_mass(m, inv_m, inv_I);
     const size_t B = size_t(m.body_count);
     std::vector<float> body_deltas(B * 6, 0.f), inv_weight(B, 0.f);
+    std::vector<float> contact_impulse_iter;
+    if (!contacts) contact_impulse = nullptr;
+    if (contact_impulse) {
+        std::fill(contact_impulse, contact_impulse + size_t(contacts->rigid_contact_max) * 6, 0.f);
+        contact_impulse_iter.assign(size_t(contacts->rigid_contact_max) * 6, 0.f);
+    }
+    std::vector<float> joint_impulse;
+    if (state_out->body_parent_f && m.joint_count > 0) joint_impulse.assign(size_t(m.joint_count) * 6, 0.f);
+    float* jimp = joint_impulse.empty() ? nullptr : joint_impulse.data();
+    std::vector<float> body_q_init, body_qd_init;
+    if (p->compute_body_velocity_from_position_delta || p->enable_restitution) {  // solver_xpbd.py:414-416
+        body_q_init.assign(state_in->body_q, state_in->body_q + B * 7);
+        body_qd_init.assign(state_in->body_qd, state_in->body_qd + B * 6);
+    }
     std::vector<float> body_f_tmp(state_in->body_f, state_in->body_f + B * 6);
-    if (m.joint_count) apply_joint_forces(m, state_in->body_q, control->joint_f, dt, body_f_tmp.data());
+    if (m.joint_count) apply_joint_forces(m, state_in->body_q, control->joint_f, dt, body_f_tmp.data(), jimp);
     integrate_bodies(m, state_in->body_q, state_in->body_qd, body_f_tmp.data(), p->angular_damping, dt, state_out->body_q,
                      state_out->body_qd);
     float* body_q = state_out->body_q;
@@ -114,28 +131,56 @@ void orc_xpbd_step(const nb2_model_desc* mp, const nb2_xpbd_params* p, const nb2
                 std::fill(inv_weight.begin(), inv_weight.end(), 0.f);
                 w = inv_weight.data();
             }
+            float* it_imp = nullptr;
+            if (contact_impulse) {
+                std::fill(contact_impulse_iter.begin(), contact_impulse_iter.end(), 0.f);
+                it_imp = contact_impulse_iter.data();
+            }
             solve_body_contact_positions(m, body_q, body_qd, inv_m.data(), inv_I.data(), *contacts, p->rigid_contact_relaxation,
-                                         dt, body_deltas.data(), w);
+                                         dt, body_deltas.data(), w, it_imp);
+            if (contact_impulse) accumulate_weighted_contact_impulse(m, *contacts, it_imp, w, contact_impulse);
             apply(w);
         }
         if (m.joint_count) {
             std::fill(body_deltas.begin(), body_deltas.end(), 0.f);
             solve_body_joints(m, body_q, body_qd, inv_m.data(), inv_I.data(), *control, p->joint_linear_compliance,
                               p->joint_angular_compliance, p->joint_angular_relaxation, p->joint_linear_relaxation, dt,
-                              body_deltas.data());
+                              body_deltas.data(), jimp);
             apply(nullptr);
         }
+    }
+    if (state_out->body_parent_f) {  // solver_xpbd.py:745-760
+        std::fill(state_out->body_parent_f, state_out->body_parent_f + B * 6, 0.f);
+        if (jimp) convert_joint_impulse_to_parent_f(m, jimp, dt, state_out->body_parent_f);
     }
     if (body_q != state_out->body_q) {
         std::memcpy(state_out->body_q, body_q, B * 7 * sizeof(float));
         std::memcpy(state_out->body_qd, body_qd, B * 6 * sizeof(float));
     }
+    if (p->compute_body_velocity_from_position_delta)  // solver_xpbd.py:768-780
+        update_body_velocities(m, state_out->body_q, body_q_init.data(), dt, state_out->body_qd);
+    if (p->enable_restitution && contacts) {  // solver_xpbd.py:782-850
+        std::fill(body_deltas.begin(), body_deltas.end(), 0.f);
+        apply_rigid_restitution(m, state_out->body_q, state_out->body_qd, body_q_init.data(), body_qd_init.data(), inv_m.data(),
+                                inv_I.data(), *contacts, dt, body_deltas.data());
+        for (size_t i = 0; i < B * 6; ++i) state_out->body_qd[i] += body_deltas[i];  // apply_body_delta_velocities (kernels.py:936-942)
+    }
     // copy_kinematic_body_state_kernel (kernels.py:19-32)
+    const float* q_src = body_q_init.empty() ? state_in->body_q : body_q_init.data();
+    const float* qd_src = body_qd_init.empty() ? state_in->body_qd : body_qd_init.data();
     for (int i = 0; i < m.body_count; ++i) {
         if ((m.body_flags[i] & BODY_KINEMATIC) == 0) continue;
-        std::memcpy(state_out->body_q + 7 * i, state_in->body_q + 7 * i, 7 * sizeof(float));
-        std::memcpy(state_out->body_qd + 6 * i, state_in->body_qd + 6 * i, 6 * sizeof(float));
+        std::memcpy(state_out->body_q + 7 * i, q_src + 7 * i, 7 * sizeof(float));
+        std::memcpy(state_out->body_qd + 6 * i, qd_src + 6 * i, 6 * sizeof(float));
     }
+}
+
+// SolverXPBD.update_contacts (solver_xpbd.py:864-925; convert_contact_impulse_to_force kernels.py:2464-2494)
+void orc_xpbd_update_contacts(const nb2_contacts_view* c, const float* contact_impulse, float dt) {
+    int count = c->rigid_contact_count[0];
+    float inv_dt = 1.0f / dt;
+    for (int tid = 0; tid < c->rigid_contact_max; ++tid)
+        for (int k = 0; k < 6; ++k) c->force[6 * tid + k] = tid < count ? contact_impulse[6 * tid + k] * inv_dt : 0.0f;
 }
 
 // SolverFeatherstone keeps cross-step state (step counter, cached H / L): one handle per solver instance.

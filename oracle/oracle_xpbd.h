@@ -61,8 +61,8 @@ inline void integrate_bodies(const nb2_model_desc& m, const float* body_q, const
 }
 
 // reference solvers/xpbd/kernels.py:945-1075
-inline void apply_joint_forces(const nb2_model_desc& m, const float* body_q, const float* joint_f, float dt, float* body_f) {
-    (void)dt;
+inline void apply_joint_forces(const nb2_model_desc& m, const float* body_q, const float* joint_f, float dt, float* body_f,
+                               float* joint_impulse = nullptr) {
     for (int tid = 0; tid < m.joint_count; ++tid) {
         int type = m.joint_type[tid];
         if (!m.joint_enabled[tid]) continue;
@@ -93,6 +93,7 @@ inline void apply_joint_forces(const nb2_model_desc& m, const float* body_q, con
             t_total = vec3(joint_f[qd_start + 3], joint_f[qd_start + 4], joint_f[qd_start + 5]);
             atomic_add(body_f, id_c, spatial(f_total, t_total));
             if (id_p >= 0) atomic_sub(body_f, id_p, spatial(f_total, t_total));
+            if (joint_impulse) atomic_add(joint_impulse, tid, spatial(f_total, t_total) * dt);  // kernels.py:1018-1019
             continue;
         } else if (type == JT_BALL) {
             t_total = vec3(joint_f[qd_start + 0], joint_f[qd_start + 1], joint_f[qd_start + 2]);
@@ -115,6 +116,7 @@ inline void apply_joint_forces(const nb2_model_desc& m, const float* body_q, con
         spatial child_wrench(f_total, t_total + cross(r_c, f_total));
         if (id_p >= 0) atomic_sub(body_f, id_p, spatial(f_total, t_total + cross(r_p, f_total)));
         atomic_add(body_f, id_c, child_wrench);
+        if (joint_impulse) atomic_add(joint_impulse, tid, child_wrench * dt);  // kernels.py:1074-1075
     }
 }
 
@@ -172,7 +174,8 @@ inline float compute_angular_correction(float err, float derr, const transform& 
 // reference solvers/xpbd/kernels.py:2164-2399 (+ sim/contacts.py:70-115)
 inline void solve_body_contact_positions(const nb2_model_desc& m, const float* body_q, const float* body_qd,
                                          const float* body_m_inv, const float* body_I_inv, const nb2_contacts_view& c,
-                                         float relaxation, float dt, float* deltas, float* contact_inv_weight) {
+                                         float relaxation, float dt, float* deltas, float* contact_inv_weight,
+                                         float* contact_impulse = nullptr) {
     int count = c.rigid_contact_count[0];
     for (int tid = 0; tid < c.rigid_contact_max; ++tid) {
         if (tid >= count) break;
@@ -299,6 +302,152 @@ inline void solve_body_contact_positions(const nb2_model_desc& m, const float* b
         }
         if (body_a >= 0) atomic_add(deltas, body_a, spatial(lin_delta_a, ang_delta_a));
         if (body_b >= 0) atomic_add(deltas, body_b, spatial(lin_delta_b, ang_delta_b));
+        if (contact_impulse) atomic_add(contact_impulse, tid, spatial(lin_delta_a, ang_delta_a));  // kernels.py:2398-2399
+    }
+}
+
+// reference solvers/xpbd/kernels.py:2402-2461
+inline void accumulate_weighted_contact_impulse(const nb2_model_desc& m, const nb2_contacts_view& c, const float* contact_impulse_iter,
+                                                const float* constraint_inv_weight, float* contact_impulse) {
+    int count = c.rigid_contact_count[0];
+    for (int tid = 0; tid < c.rigid_contact_max; ++tid) {
+        if (tid >= count) break;
+        spatial impulse = spatial::load(contact_impulse_iter + 6 * tid);
+        float weight = 1.0f;
+        if (constraint_inv_weight) {
+            float n_a = 0.0f, n_b = 0.0f;
+            int shape_a = c.shape0[tid];
+            if (shape_a >= 0) {
+                int body_a = m.shape_body[shape_a];
+                if (body_a >= 0) n_a = constraint_inv_weight[body_a];
+            }
+            int shape_b = c.shape1[tid];
+            if (shape_b >= 0) {
+                int body_b = m.shape_body[shape_b];
+                if (body_b >= 0) n_b = constraint_inv_weight[body_b];
+            }
+            float n_sum = n_a + n_b;
+            if (n_sum > 0.0f) {
+                if (n_a == 0.0f) weight = 1.0f / n_b;
+                else if (n_b == 0.0f) weight = 1.0f / n_a;
+                else weight = 2.0f / n_sum;
+            }
+        }
+        atomic_add(contact_impulse, tid, spatial(impulse.top * weight, impulse.bot * weight));
+    }
+}
+
+// reference solvers/xpbd/kernels.py:2547-2579
+inline void update_body_velocities(const nb2_model_desc& m, const float* poses, const float* poses_prev, float dt, float* qd_out) {
+    for (int tid = 0; tid < m.body_count; ++tid) {
+        transform pose = transform::load(poses + 7 * tid), pose_prev = transform::load(poses_prev + 7 * tid);
+        vec3 com = load3(m.body_com + 3 * tid);
+        vec3 x_com = pose.p + quat_rotate(pose.q, com);
+        vec3 x_com_prev = pose_prev.p + quat_rotate(pose_prev.q, com);
+        vec3 v = (x_com - x_com_prev) / dt;
+        quat dq = pose.q * quat_inverse(pose_prev.q);
+        vec3 omega = (2.0f / dt) * vec3(dq.x, dq.y, dq.z);
+        if (dq.w < 0.0f) omega = -omega;
+        spatial(v, omega).store(qd_out + 6 * tid);
+    }
+}
+
+// reference solvers/xpbd/kernels.py:2582-2728
+inline void apply_rigid_restitution(const nb2_model_desc& m, const float* body_q, const float* body_qd, const float* body_q_prev,
+                                    const float* body_qd_prev, const float* body_m_inv, const float* body_I_inv,
+                                    const nb2_contacts_view& c, float dt, float* deltas) {
+    (void)body_q;
+    int count = c.rigid_contact_count[0];
+    for (int tid = 0; tid < c.rigid_contact_max; ++tid) {
+        if (tid >= count) break;
+        int shape_a = c.shape0[tid], shape_b = c.shape1[tid];
+        if (shape_a == shape_b) continue;
+        int body_a = -1, body_b = -1, mat_nonzero = 0;
+        float restitution = 0.0f;
+        if (shape_a >= 0) {
+            mat_nonzero += 1;
+            restitution += m.shape_material_restitution[shape_a];
+            body_a = m.shape_body[shape_a];
+        }
+        if (shape_b >= 0) {
+            mat_nonzero += 1;
+            restitution += m.shape_material_restitution[shape_b];
+            body_b = m.shape_body[shape_b];
+        }
+        if (mat_nonzero > 0) restitution /= float(mat_nonzero);
+        if (body_a == body_b) continue;
+        float m_inv_a = 0.f, m_inv_b = 0.f, inv_mass = 0.f;
+        mat33 I_inv_a, I_inv_b;
+        transform X_wb_a_prev, X_wb_b_prev;
+        vec3 com_a(0.f), com_b(0.f), v_a(0.f), v_b(0.f), v_a_new(0.f), v_b_new(0.f);
+        if (body_a >= 0) {
+            X_wb_a_prev = transform::load(body_q_prev + 7 * body_a);
+            m_inv_a = body_m_inv[body_a];
+            I_inv_a = mat33::load(body_I_inv + 9 * body_a);
+            com_a = load3(m.body_com + 3 * body_a);
+        }
+        if (body_b >= 0) {
+            X_wb_b_prev = transform::load(body_q_prev + 7 * body_b);
+            m_inv_b = body_m_inv[body_b];
+            I_inv_b = mat33::load(body_I_inv + 9 * body_b);
+            com_b = load3(m.body_com + 3 * body_b);
+        }
+        // contact_surface_point (sim/contacts.py:96-115): X_wb * (point + offset)
+        vec3 bx_a = transform_point(X_wb_a_prev, load3(c.point0 + 3 * tid) + load3(c.offset0 + 3 * tid));
+        vec3 bx_b = transform_point(X_wb_b_prev, load3(c.point1 + 3 * tid) + load3(c.offset1 + 3 * tid));
+        vec3 n = load3(c.normal + 3 * tid);
+        float d = dot(n, bx_b - bx_a);
+        if (d >= 0.0f) continue;
+        vec3 r_a = bx_a - transform_point(X_wb_a_prev, com_a);
+        vec3 r_b = bx_b - transform_point(X_wb_b_prev, com_b);
+        vec3 rxn_a(0.f), rxn_b(0.f);
+        auto gravity_of = [&](int body) {
+            int w = m.body_world[body];
+            if (w < 0) w += m.gravity_count;  // Warp negative indexing: world -1 -> last slot
+            return load3(m.gravity + 3 * w);
+        };
+        if (body_a >= 0) {
+            v_a = velocity_at_point(spatial::load(body_qd_prev + 6 * body_a), r_a) + gravity_of(body_a) * dt;
+            v_a_new = velocity_at_point(spatial::load(body_qd + 6 * body_a), r_a);
+            rxn_a = quat_rotate_inv(X_wb_a_prev.q, cross(r_a, n));
+            float inv_mass_a = m_inv_a + dot(rxn_a, I_inv_a * rxn_a);
+            inv_mass += inv_mass_a;
+        }
+        if (body_b >= 0) {
+            v_b = velocity_at_point(spatial::load(body_qd_prev + 6 * body_b), r_b) + gravity_of(body_b) * dt;
+            v_b_new = velocity_at_point(spatial::load(body_qd + 6 * body_b), r_b);
+            rxn_b = quat_rotate_inv(X_wb_b_prev.q, cross(r_b, n));
+            float inv_mass_b = m_inv_b + dot(rxn_b, I_inv_b * rxn_b);
+            inv_mass += inv_mass_b;
+        }
+        if (inv_mass == 0.0f) continue;
+        float rel_vel_old = dot(n, v_b - v_a);
+        float rel_vel_new = dot(n, v_b_new - v_a_new);
+        if (rel_vel_old >= 0.0f) continue;
+        float dv = (-rel_vel_new - restitution * rel_vel_old) / inv_mass;
+        if (body_a >= 0) {
+            float dv_a = -dv;
+            vec3 dq = quat_rotate(X_wb_a_prev.q, I_inv_a * rxn_a * dv_a);
+            atomic_add(deltas, body_a, spatial(n * m_inv_a * dv_a, dq));
+        }
+        if (body_b >= 0) {
+            float dv_b = dv;
+            vec3 dq = quat_rotate(X_wb_b_prev.q, I_inv_b * rxn_b * dv_b);
+            atomic_add(deltas, body_b, spatial(n * m_inv_b * dv_b, dq));
+        }
+    }
+}
+
+// reference solvers/xpbd/kernels.py:2497-2544 (body_parent_f is zeroed by the caller)
+inline void convert_joint_impulse_to_parent_f(const nb2_model_desc& m, const float* joint_impulse, float dt, float* body_parent_f) {
+    for (int tid = 0; tid < m.joint_count; ++tid) {
+        if (!m.joint_enabled[tid]) continue;
+        if (m.joint_type[tid] == JT_FREE) continue;
+        int id_c = m.joint_child[tid];
+        if (id_c < 0) continue;
+        float inv_dt = 1.0f / dt;
+        spatial impulse = spatial::load(joint_impulse + 6 * tid);
+        atomic_add(body_parent_f, id_c, spatial(impulse.top * inv_dt, impulse.bot * inv_dt));
     }
 }
 
@@ -409,7 +558,7 @@ inline AxisSetup gather_axes(const nb2_model_desc& m, const nb2_control_view& ct
 inline void solve_body_joints(const nb2_model_desc& m, const float* body_q, const float* body_qd, const float* body_inv_m,
                               const float* body_inv_I, const nb2_control_view& ctl, float joint_linear_compliance,
                               float joint_angular_compliance, float angular_relaxation, float linear_relaxation, float dt,
-                              float* deltas) {
+                              float* deltas, float* joint_impulse = nullptr) {
     for (int tid = 0; tid < m.joint_count; ++tid) {
         int type = m.joint_type[tid];
         if (!m.joint_enabled[tid]) continue;
@@ -615,6 +764,7 @@ inline void solve_body_joints(const nb2_model_desc& m, const float* body_q, cons
         }
         if (id_p >= 0) atomic_add(deltas, id_p, spatial(lin_delta_p, ang_delta_p));
         if (id_c >= 0) atomic_add(deltas, id_c, spatial(lin_delta_c, ang_delta_c));
+        if (joint_impulse) atomic_add(joint_impulse, tid, spatial(lin_delta_c, ang_delta_c));  // kernels.py:2043-2044
     }
 }
 

@@ -7,9 +7,11 @@ import torch
 
 
 def simulate(model, pipeline_cls, solver_cls, *, substeps, dt, solver_kwargs=None, collide=True, control=None,
-             record_contacts=False):
+             record_contacts=False, solver_attrs=None, update_contacts=False):
     """`collide -> step -> swap` loop exactly as the reference examples run it (example_basic_urdf.py:117-135)."""
     solver = solver_cls(model, **(solver_kwargs or {}))
+    for k, v in (solver_attrs or {}).items():
+        setattr(solver, k, v)
     pipe = pipeline_cls(model) if (collide and pipeline_cls is not None) else None
     s0, s1 = model.state(), model.state()
     ctrl = control if control is not None else model.control()
@@ -23,6 +25,8 @@ def simulate(model, pipeline_cls, solver_cls, *, substeps, dt, solver_kwargs=Non
                 counts.append(int(contacts.rigid_contact_count.item()))
         solver.step(s0, s1, ctrl, contacts, dt)
         s0, s1 = s1, s0
+    if update_contacts:
+        solver.update_contacts(contacts, s0)
     return s0, contacts, counts
 
 
@@ -36,6 +40,8 @@ def canonical_contacts(contacts, model):
     out = {"shape0": s0[order], "shape1": s1[order]}
     for name in ("point0", "point1", "offset0", "offset1", "normal", "margin0", "margin1"):
         out[name] = g(getattr(contacts, "rigid_contact_" + name))[order]
+    if getattr(contacts, "force", None) is not None:
+        out["force"] = g(contacts.force)[order]
     return n, out
 
 

@@ -25,15 +25,16 @@ pytestmark = pytest.mark.gpu
 TOL_STATE_REL = 1e-5  # north_star tolerance (used for the fast-fp twin; the product library must be exact)
 
 
-def _both(model_cpu, substeps, dt, solver_kwargs, oracle, control_fn=None):
+def _both(model_cpu, substeps, dt, solver_kwargs, oracle, control_fn=None, **sim_kw):
     ctrl_cpu = control_fn(model_cpu) if control_fn else None
     ref_state, ref_contacts, ref_counts = simulate(model_cpu, oracle.CollisionPipeline, oracle.SolverXPBD, substeps=substeps,
-                                                   dt=dt, solver_kwargs=solver_kwargs, record_contacts=True, control=ctrl_cpu)
+                                                   dt=dt, solver_kwargs=solver_kwargs, record_contacts=True, control=ctrl_cpu,
+                                                   **sim_kw)
     model_gpu = model_cpu.to("cuda:0")
     ctrl_gpu = control_fn(model_gpu) if control_fn else None
     gpu_state, gpu_contacts, gpu_counts = simulate(model_gpu, newton_b200.CollisionPipeline, newton_b200.solvers.SolverXPBD,
                                                    substeps=substeps, dt=dt, solver_kwargs=solver_kwargs,
-                                                   record_contacts=True, control=ctrl_gpu)
+                                                   record_contacts=True, control=ctrl_gpu, **sim_kw)
     torch.cuda.synchronize()
     return ref_state, ref_contacts, ref_counts, gpu_state, gpu_contacts, gpu_counts
 
@@ -102,6 +103,64 @@ def test_convex_pile_bit_exact(oracle_lib, cuda_lib):
     model = scenes.convex_pile_model(4, seed=5)
     out = _both(model, 150, 1.0 / 240, {"iterations": 4}, oracle_lib)
     _assert_exact(*out, model)
+
+
+def _bouncy_scene(worlds):
+    """Spheres, a box and a capsule with restitution dropped on each other and on the plane."""
+    from newton_b200.sim.builder import ShapeConfig
+
+    rng = np.random.default_rng(11)
+    scene = ModelBuilder()
+    ground = ShapeConfig(restitution=0.6, mu=0.4)
+    for _ in range(worlds):
+        scene.begin_world()
+        for i, e in enumerate((0.9, 0.5, 0.2)):
+            cfg = ShapeConfig(restitution=e, mu=0.3)
+            b = scene.add_body(xform=X.transform(np.array([0.6 * i, 0.0, 0.45 + 0.2 * i]) + rng.uniform(-0.02, 0.02, 3)))
+            scene.add_shape_sphere(b, radius=0.2, cfg=cfg)
+        b = scene.add_body(xform=X.transform(np.array([0.3, 0.05, 1.2]) + rng.uniform(-0.02, 0.02, 3),
+                                             X.quat_from_axis_angle((1.0, 0.0, 0.0), 0.4)))
+        scene.add_shape_box(b, hx=0.25, hy=0.2, hz=0.1, cfg=ShapeConfig(restitution=0.7, mu=0.5))
+        b = scene.add_body(xform=X.transform(np.array([-0.7, 0.0, 0.5]), X.quat_from_axis_angle((0.0, 1.0, 0.0), 1.0)))
+        scene.add_shape_capsule(b, radius=0.15, half_height=0.3, cfg=ShapeConfig(restitution=0.8, mu=0.5))
+        scene.end_world()
+    scene.add_ground_plane(cfg=ground)
+    return scene.finalize()
+
+
+def test_restitution_bit_exact(oracle_lib, cuda_lib):
+    """enable_restitution=True (apply_rigid_restitution + apply_body_delta_velocities, kernels.py:2582-2728, 936-942)."""
+    model = _bouncy_scene(6)
+    out = _both(model, 200, 1.0 / 400, {"iterations": 4, "enable_restitution": True}, oracle_lib)
+    _assert_exact(*out, model)
+    assert float(out[3].body_qd.abs().max()) > 0.1  # things are still moving: the restitution pass was exercised
+
+
+def test_velocity_from_position_delta_bit_exact(oracle_lib, cuda_lib):
+    """SolverXPBD.compute_body_velocity_from_position_delta (update_body_velocities, kernels.py:2547-2579)."""
+    model = _drop(scenes.quadruped_model(5, seed=7), 5, 0.5)
+    out = _both(model, 60, 0.005, {"iterations": 4}, oracle_lib, solver_attrs={"compute_body_velocity_from_position_delta": True})
+    _assert_exact(*out, model)
+
+
+def test_contact_force_and_parent_force_bit_exact(oracle_lib, cuda_lib):
+    """Contacts.force via update_contacts() and State.body_parent_f (row a17 reporting kernels), quadrupeds on the ground
+    with non-zero joint_f, plus box stacks (body-body contacts, two dynamic bodies per contact)."""
+
+    def ctrl(model):
+        c = model.control()
+        g = torch.Generator().manual_seed(3)
+        c.joint_f.copy_((torch.rand(c.joint_f.shape, generator=g) * 2.0 - 1.0).to(c.joint_f.device))
+        return c
+
+    for model, control_fn in ((_drop(scenes.quadruped_model(4, seed=2), 4, 0.47), ctrl), (scenes.box_stack_model(3, seed=1), None)):
+        model.request_contact_attributes("force")
+        model.request_state_attributes("body_parent_f")
+        out = _both(model, 50, 0.005, {"iterations": 6}, oracle_lib, control_fn=control_fn, update_contacts=True)
+        _assert_exact(*out, model)
+        rs, gs = out[0], out[3]
+        np.testing.assert_array_equal(gs.body_parent_f.cpu().numpy(), rs.body_parent_f.numpy())
+        assert np.abs(canonical_contacts(out[1], model)[1]["force"]).max() > 1.0
 
 
 def test_implicit_single_world_and_no_contacts(oracle_lib, cuda_lib):

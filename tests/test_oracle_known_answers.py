@@ -429,3 +429,155 @@ def test_xpbd_aligned_box_stack_remains_stable(oracle_lib):
     np.testing.assert_allclose(bq[:, 1], 0.5 + np.arange(5), atol=2.0e-2)
     assert float(np.max(np.linalg.norm(bq[:, (0, 2)], axis=1))) < 1.0e-2
     assert float(np.max(np.linalg.norm(bq[:, 3:][:, (0, 2)], axis=1))) < 1.0e-3
+
+
+# ---- XPBD row a17: restitution, contact forces, joint reaction (body_parent_f) --------------------------------------------------
+
+@pytest.mark.parametrize("e", [0.5, 0.8])
+def test_xpbd_restitution_rebound_height(oracle_lib, e):
+    """newton/tests/test_physics_verification.py:612-676 (test_restitution, SolverXPBD(iterations=10,
+    enable_restitution=True)): a sphere dropped from 1 m rebounds to e^2 * h within 1 %."""
+    from newton_b200.sim.builder import ShapeConfig
+
+    g, h_drop, radius = -10.0, 1.0, 0.05
+    cfg = ShapeConfig(mu=0.0, restitution=e, ke=1e4, kd=100.0, kf=0.0, margin=0.001, gap=0.0)
+    b = ModelBuilder(up_axis="Y", gravity=g)
+    b.add_ground_plane(cfg=cfg)
+    body = b.add_body(xform=X.transform((0.0, radius + h_drop, 0.0)))
+    b.add_shape_sphere(body, radius=radius, cfg=cfg)
+    model = b.finalize()
+    pipe = oracle_lib.CollisionPipeline(model)
+    contacts = pipe.contacts()
+    solver = oracle_lib.SolverXPBD(model, iterations=10, angular_damping=0.0, enable_restitution=True)
+    s0, s1 = model.state(), model.state()
+    sim_dt = 1e-3
+    ys = []
+    for _ in range(int(3.0 * math.sqrt(2.0 * h_drop / abs(g)) / sim_dt)):
+        s0.clear_forces()
+        pipe.collide(s0, contacts)
+        solver.step(s0, s1, None, contacts, sim_dt)
+        s0, s1 = s1, s0
+        ys.append(float(s0.body_q[0, 1]))
+    y = np.array(ys)
+    assert y.min() > -0.01
+    impact = next(i for i in range(1, len(y) - 1) if y[i] < y[i - 1] and y[i] <= y[i + 1])
+    h_rebound = y[impact:].max() - radius
+    assert h_rebound == pytest.approx(e * e * h_drop, rel=0.01)
+
+
+def test_xpbd_contact_force_static_equilibrium(oracle_lib):
+    """newton/tests/test_solver_xpbd.py:848-1035: time-averaged ``contacts.force`` of resting bodies equals their weight
+    (sphere, heavy sphere, 4-contact box with 1/N weighting, two-cube base of a 3-cube pyramid carrying 1.5 mg each)."""
+    from newton_b200.sim.builder import ShapeConfig
+
+    grav = 9.81
+    b = ModelBuilder()
+    b.add_ground_plane()
+    masses = {}
+
+    def body(pos, density, **shape):
+        b.default_shape_cfg.density = density
+        i = b.add_body(xform=X.transform(pos))
+        if "radius" in shape:
+            b.add_shape_sphere(i, radius=shape["radius"])
+            masses[i] = density * 4.0 / 3.0 * math.pi * shape["radius"] ** 3
+        else:
+            b.add_shape_box(i, hx=shape["h"], hy=shape["h"], hz=shape["h"])
+            masses[i] = density * (2.0 * shape["h"]) ** 3
+        return i
+
+    sphere = body((0.0, 0.0, 0.25), 1000.0, radius=0.25)
+    heavy = body((10.0, 0.0, 0.5), 2000.0, radius=0.5)
+    box = body((20.0, 0.0, 0.5), 1000.0, h=0.5)
+    left = body((29.5, 0.0, 0.5), 1000.0, h=0.5)
+    right = body((30.5, 0.0, 0.5), 1000.0, h=0.5)
+    body((30.0, 0.0, 1.5), 1000.0, h=0.5)
+    model = b.finalize()
+    model.request_contact_attributes("force")
+    solver = oracle_lib.SolverXPBD(model, iterations=32, rigid_contact_con_weighting=True)
+    s0, s1, ctl = model.state(), model.state(), model.control()
+    pipe = oracle_lib.CollisionPipeline(model)
+    contacts = pipe.contacts()
+    assert contacts.force is not None
+    sub_dt = 1.0 / 60.0 / 8
+    acc = {i: np.zeros(3) for i in (sphere, heavy, box, left, right)}
+    shape_body = model.shape_body.numpy()
+    avg_steps = 60
+    for frame in range(200 + avg_steps):
+        for _ in range(8):
+            s0.clear_forces()
+            pipe.collide(s0, contacts)
+            solver.step(s0, s1, ctl, contacts, sub_dt)
+            s0, s1 = s1, s0
+        if frame < 200:
+            continue
+        solver.update_contacts(contacts, s0)
+        nc = int(contacts.rigid_contact_count[0])
+        f = contacts.force.numpy()[:nc, :3]
+        sh0, sh1 = contacts.rigid_contact_shape0.numpy()[:nc], contacts.rigid_contact_shape1.numpy()[:nc]
+        for ci in range(nc):  # contacts.force = force on body0 by body1; ground is shape 0
+            if sh0[ci] == 0:
+                other, fo = sh1[ci], f[ci]
+            elif sh1[ci] == 0:
+                other, fo = sh0[ci], -f[ci]
+            else:
+                continue
+            ob = shape_body[other]
+            if ob in acc:
+                acc[ob] += fo
+    for i in acc:
+        acc[i] /= avg_steps
+    assert acc[sphere][2] == pytest.approx(-masses[sphere] * grav, rel=0.05)
+    assert acc[heavy][2] == pytest.approx(-masses[heavy] * grav, rel=0.05)
+    assert acc[box][2] == pytest.approx(-masses[box] * grav, rel=0.10)  # N contacts must not report N * mg
+    for i in (sphere, heavy):
+        assert abs(acc[i][0]) < 0.5 and abs(acc[i][1]) < 0.5
+    assert -acc[left][2] == pytest.approx(1.5 * masses[left] * grav, rel=0.15)
+    assert -acc[right][2] == pytest.approx(1.5 * masses[right] * grav, rel=0.15)
+
+
+@pytest.mark.parametrize("joint_kind", ["revolute", "ball", "fixed"])
+@pytest.mark.parametrize("parent_kinematic", [False, True])
+def test_xpbd_parent_force_single_body(oracle_lib, joint_kind, parent_kinematic):
+    """newton/tests/test_solver_xpbd.py:1120-1280: a body hanging 1 m below a joint to the world / a kinematic body:
+    the time-averaged ``body_parent_f`` is its weight along +Z within 1 %, lateral force and torque ~ 0."""
+    from newton_b200 import BodyFlags
+
+    b = ModelBuilder(gravity=-9.81)
+    if parent_kinematic:
+        parent = b.add_body(xform=X.transform((0.0, 0.0, 0.0)))
+        b.add_shape_box(parent, hx=0.05, hy=0.05, hz=0.05)
+        b.body_flags[parent] = int(BodyFlags.KINEMATIC)
+    else:
+        parent = -1
+    child = b.add_link()
+    b.add_shape_box(child, hx=0.1, hy=0.1, hz=0.1)
+    kw = dict(parent_xform=X.transform((0.0, 0.0, 0.0)), child_xform=X.transform((0.0, 0.0, 1.0)))
+    if joint_kind == "revolute":
+        j = b.add_joint_revolute(parent, child, axis=(0.0, 1.0, 0.0), **kw)
+    elif joint_kind == "ball":
+        j = b.add_joint_ball(parent, child, **kw)
+    else:
+        j = b.add_joint_fixed(parent, child, **kw)
+    b.add_articulation([j])
+    model = b.finalize()
+    model.request_state_attributes("body_parent_f")
+    import newton_b200
+
+    newton_b200.eval_fk(model, model.joint_q, model.joint_qd, model)
+    solver = oracle_lib.SolverXPBD(model, iterations=8)
+    s0, s1 = model.state(), model.state()
+    assert s0.body_parent_f is not None
+    sub_dt = 1.0 / 60.0 / 8
+    avg = np.zeros(6)
+    for frame in range(60 + 30):
+        for _ in range(8):
+            solver.step(s0, s1, None, None, sub_dt)
+            s0, s1 = s1, s0
+        if frame >= 60:
+            avg += s0.body_parent_f.numpy()[child]
+    avg /= 30
+    weight = float(model.body_mass[child]) * 9.81
+    assert avg[2] == pytest.approx(weight, rel=0.01)
+    np.testing.assert_allclose(avg[:2], 0.0, atol=0.1)
+    np.testing.assert_allclose(avg[3:], 0.0, atol=0.1)
