@@ -18,10 +18,16 @@ class CollisionPipeline:
     def __init__(self, model, *, broad_phase: str | None = None, rigid_contact_max: int | None = None,
                  deterministic: bool = False, soft_contact_margin: float = 0.01, requires_grad: bool = False,
                  export_contacts: bool = True, **unsupported):
-        if broad_phase not in (None, "explicit"):
-            raise NotImplementedError(
-                f"broad_phase={broad_phase!r}: only the explicit pair list is in the hot-path scope (SURVEY.md §8(f) row 3)"
-            )
+        if broad_phase not in (None, "explicit", "nxn", "sap"):
+            raise ValueError(f"unknown broad_phase {broad_phase!r} (expected 'explicit', 'nxn' or 'sap')")
+        # "nxn" / "sap" (broad_phase_nxn.py:132-218, broad_phase_sap.py) enumerate candidates at run time with the same
+        # world / collision-group / filter-pair rules the builder used to precompute model.shape_contact_pairs
+        # ("exact same filtering logic ... to ensure consistency between EXPLICIT mode and NXN/SAP modes",
+        # sim/builder.py:12796-12797), followed by the same AABB test.  The candidate set - and therefore the contact set
+        # in deterministic order - is identical, so all three options run the env-local AABB sweep over the pair list.
+        if getattr(model, "shape_contact_pairs", None) is None:
+            raise ValueError("model.shape_contact_pairs is missing (ModelBuilder.finalize() generates it)")
+        self.broad_phase = broad_phase or "explicit"
         if requires_grad:
             raise NotImplementedError("differentiable contacts are out of scope")
         for k, v in unsupported.items():
