@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(32, 16) xpbd_step_kernel(DevModel M, nb2_xpbd_
     const float* cb = M.cb;
     for (int it = 0; it < P.iterations; ++it) {
         if (use_contacts) {
-            // solve_body_contact_positions (kernels.py:2164-2399)
+            // ---- [iteration] solve_body_contact_positions (kernels.py:2164-2399)
             for (int c = l; c < nc; c += L) {
                 const int s = slot0 + c;
                 const int pr = cpair[c];
@@ -635,7 +635,7 @@ __global__ void __launch_bounds__(32, 16) xpbd_step_kernel(DevModel M, nb2_xpbd_
                 store_deltas(drec + c * DR_SIZE, dl, active);
             }
             __syncwarp();
-            // ordered per-body sum (contact order; side A before side B) + weighted apply
+            // ---- [iteration] ordered per-body sum (contact order; side A before side B) + weighted apply
             for (int b = l; b < nb; b += L) {
                 V3 dlin, dang;
                 float cnt = 0.0f;
@@ -676,7 +676,7 @@ __global__ void __launch_bounds__(32, 16) xpbd_step_kernel(DevModel M, nb2_xpbd_
             }
         }
         if (d.joint_count > 0) {
-            // solve_body_joints (kernels.py:1513-2044)
+            // ---- [iteration] solve_body_joints (kernels.py:1513-2044) + ordered per-body apply
             for (int j = l; j < nj; j += L) {
                 Deltas dl;
                 bool act = solve_joint(d, ctl, P, j0 + j, b0, bodies, dt, dl);

@@ -7,7 +7,8 @@ base = cu.split("/")[-1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 lines = open(cu).read().splitlines()
-marks = [(i + 1, l.strip()[:90]) for i, l in enumerate(lines) if re.match(r"\s*// ----", l)]
+marks = [(i + 1, l.strip()[:90]) for i, l in enumerate(lines)
+         if re.match(r"\s*// ----", l) or re.match(r"^(NB2_DEV|NB2_HELPER|NB2_CALL|__global__|static|template)\b.*\(", l)]
 def section(ln):
     name = "(before first section)"
     for m, t in marks:
