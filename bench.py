@@ -42,18 +42,27 @@ WORKLOADS = {
     "quadruped_xpbd": dict(
         config="BASELINE.json configs[2]", scene="quadruped", solver="xpbd", envs=4096, substeps=4, fps=50, kernel="xpbd_step_kernel",
         text="quadruped (Anymal-class, 13 bodies/18 dofs) envs, SolverXPBD iterations=8",
-        # state in (13 x 76 B) + out (13 x 52 B) + control (220 B) + one read of each 80-byte contact
-        alg_bytes=lambda n_c: 1884.0 + 80.0 * n_c),
+        # B_state 1884 (state in 13 x 76 B + out 13 x 52 B + control 220 B) + one read of each 80-byte
+        # contact + B_model 4001 (per-env model constants: the reference layout replicates them per world and the kernel
+        # reads them every substep)
+        alg_bytes=lambda n_c: 1884.0 + 80.0 * n_c + 4001.0,
+        # dram__bytes_read + write of one launch, ncu --set full (profiles/r1d_xpbd_step_kernel.txt)
+        traffic=27.5e6),
+    "quadruped_xpbd_stock": dict(
+        config="BASELINE.json configs[2] scene with the stock example's loop (example_basic_urdf.py:28-33: 100 fps, 10 substeps, "
+               "iterations=2)", scene="quadruped", solver="xpbd", envs=4096, substeps=10, fps=100, iterations=2,
+        kernel="xpbd_step_kernel", text="quadruped (Anymal-class, 13 bodies/18 dofs) envs, SolverXPBD iterations=2",
+        alg_bytes=lambda n_c: 1884.0 + 80.0 * n_c + 4001.0, traffic=None),
     "box_stacks_xpbd": dict(
         config="BASELINE.json configs[1]", scene="stacks", solver="xpbd", envs=512, substeps=4, fps=60, kernel="xpbd_step_kernel",
         text="5-box stack envs (box-box MPR manifolds + plane-box), SolverXPBD iterations=8",
-        alg_bytes=lambda n_c: 5 * 76.0 + 5 * 52.0 + 80.0 * n_c),
+        alg_bytes=lambda n_c: 5 * 76.0 + 5 * 52.0 + 80.0 * n_c + 5 * 100.0, traffic=None),
     "quadruped_featherstone": dict(
-        config="BASELINE.json configs[3]", scene="quadruped", solver="featherstone", envs=4096, substeps=8, fps=50,
+        config="BASELINE.json configs[3]", scene="quadruped", solver="featherstone", envs=4096, substeps=10, fps=100,
         kernel="featherstone_step_kernel",
         text="quadruped (Anymal-class, 13 bodies/18 dofs) envs, SolverFeatherstone (dense H = J^T M J, Cholesky), penalty contacts",
-        # joint_q/qd in+out (2 x 148 B) + body_f in (312) + body_q/qd out (676) + control (220) + 112-byte contacts
-        alg_bytes=lambda n_c: 296.0 + 312.0 + 676.0 + 220.0 + 112.0 * n_c),
+        # joint_q/qd in+out (2 x 148 B) + body_f in (312) + body_q/qd out (676) + control (220) + 112-byte contacts + B_model
+        alg_bytes=lambda n_c: 296.0 + 312.0 + 676.0 + 220.0 + 112.0 * n_c + 4001.0, traffic=None),
 }
 WL = WORKLOADS["quadruped_xpbd"]
 SUBSTEPS = WL["substeps"]
@@ -79,7 +88,7 @@ def build_scene(envs, seed):
 def make_solver(pkg, model):
     """pkg is newton_b200.solvers (product) or the oracle module (CPU checker)."""
     if WL["solver"] == "xpbd":
-        return pkg.SolverXPBD(model, iterations=ITERATIONS)
+        return pkg.SolverXPBD(model, iterations=WL.get("iterations", ITERATIONS))
     return pkg.SolverFeatherstone(model)
 
 
@@ -107,7 +116,7 @@ def workload_config(envs, n_gpus):
                     + ("" if n_gpus == 1 else f" sharded {envs}/GPU (configs[4] layout)"),
         "envs_per_gpu": envs,
         "substeps_per_step": SUBSTEPS,
-        "iterations": ITERATIONS,
+        "iterations": WL.get("iterations", ITERATIONS) if WL["solver"] == "xpbd" else None,
         "dt": DT,
         "parallelism": f"env-sharded x{n_gpus}" if n_gpus > 1 else "single GPU",
         "l2": "flushed between timed steps (256 MiB memset outside the timed events)",
@@ -207,7 +216,7 @@ def run_native(args):
     # settle the robots on the ground first (untimed) so the timed frames carry the steady-state contact load
     stream = torch.cuda.Stream(device=dev)
     with torch.cuda.stream(stream):
-        for _ in range(60):
+        for _ in range(int(round(1.2 * FPS))):  # 1.2 s of simulated time
             simulate()
     torch.cuda.synchronize()
     launches_before = _lib.kernel_launch_count()
@@ -249,7 +258,9 @@ def run_native(args):
             b.record()
         barrier()
         clocks = sampler.stop() if sampler else None
-        ms = sum(a.elapsed_time(b) for a, b in ev)
+        per_step = [a.elapsed_time(b) for a, b in ev]
+        timed.last_per_step = per_step
+        ms = sum(per_step)
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -259,6 +270,12 @@ def run_native(args):
     total_ms, clocks = timed(step_device, args.steps, max(args.warmup, 3), sampler)
     env_steps = envs * world * SUBSTEPS * args.steps
     value = env_steps / (total_ms * 1e-3)
+    frame_ms = np.asarray(timed.last_per_step)  # rank-local per-frame device times (SURVEY.md §8(d) extras)
+    extras = {
+        "us_per_substep": float(total_ms / args.steps / SUBSTEPS * 1e3),
+        "p50_frame_ms": float(np.percentile(frame_ms, 50)), "p95_frame_ms": float(np.percentile(frame_ms, 95)),
+        "realtime_factor": float((1.0 / FPS) / (total_ms / args.steps * 1e-3)),
+    }
 
     # ---- e2e: host buffers through the public API (H2D of the step's control inputs, D2H of the resulting state)
     h_target = model.joint_target_q.cpu().pin_memory()
@@ -308,7 +325,8 @@ def run_native(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     roofline = {
         "bound": "hbm", "kernel": WL["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": "measured" if peaks else "fallback",
+        "frac": achieved / peak, "traffic": WL.get("traffic") if envs == WL["envs"] else None,
+        "peak_source": "measured" if peaks else "fallback",
         "algorithmic_bytes_per_env_substep": alg_bytes_env, "kernel_ms": kern_ms, "contacts_per_env": n_c,
     }
 
@@ -325,7 +343,7 @@ def run_native(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches_per_step * args.steps),
-            "gpu_launches_per_step": int(launches_per_step),
+            "gpu_launches_per_step": int(launches_per_step), "frame_stats": extras,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
         }
         print(json.dumps(out))
@@ -370,7 +388,7 @@ def oracle_throughput(envs: int, frames: int, threads: int) -> dict:
         for t in ts:
             t.join()
 
-    run_all(15)  # settle onto the ground (untimed) so the timed frames carry contacts
+    run_all(max(1, int(round(0.4 * FPS))))  # settle onto the ground (untimed, 0.4 s simulated) so the timed frames carry contacts
     t0 = time.perf_counter()
     run_all(frames)
     dt = time.perf_counter() - t0

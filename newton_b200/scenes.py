@@ -207,3 +207,38 @@ def convex_pile_model(world_count: int = 1, device="cpu", seed: int | None = 5):
         scene.end_world()
     scene.add_ground_plane()
     return _finish(scene, device)
+
+
+def mixed_worlds_model(repeats: int = 2, device="cpu", seed: int | None = 9):
+    """Heterogeneous worlds in one model - a quadruped, a 3-box stack, an empty world, a lone pendulum link, repeated -
+    so the per-env sizes differ (partial lane groups, envs without joints / shapes / contacts)."""
+    rng = np.random.default_rng(seed) if seed is not None else None
+    quad = quadruped_builder()
+    scene = ModelBuilder()
+    for r in range(repeats):
+        scene.begin_world()
+        q0 = scene.joint_coord_count
+        scene.add_builder(quad)
+        if rng is not None:
+            for k in range(7, quad.joint_coord_count):
+                scene.joint_q[q0 + k] += float(rng.normal(0.0, 0.02))
+            scene.joint_target_q[q0:q0 + quad.joint_coord_count] = scene.joint_q[q0:q0 + quad.joint_coord_count]
+        scene.joint_q[q0 + 2] = 0.5
+        scene.end_world()
+        scene.begin_world()
+        for i in range(3):
+            b = scene.add_body(xform=X.transform((0.0, 0.0, 0.4 + 0.8 * i), X.quat_from_axis_angle((0.0, 0.0, 1.0), 0.1 * (i + r))))
+            scene.add_shape_box(b, hx=0.4, hy=0.4, hz=0.4)
+        scene.end_world()
+        scene.begin_world()  # empty world
+        scene.end_world()
+        scene.begin_world()
+        link = scene.add_link()
+        scene.add_shape_capsule(link, radius=0.05, half_height=0.3)
+        j = scene.add_joint_revolute(parent=-1, child=link, axis=(0.0, 1.0, 0.0), parent_xform=X.transform((0.0, 0.0, 1.5)),
+                                     child_xform=X.transform((0.0, 0.0, 0.4)))
+        scene.add_articulation([j])
+        scene.joint_q[-1] = 0.7 + 0.1 * r
+        scene.end_world()
+    scene.add_ground_plane()
+    return _finish(scene, device)

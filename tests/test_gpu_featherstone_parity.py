@@ -90,3 +90,16 @@ def test_eval_fk_kernel_bit_exact(oracle_lib, cuda_lib):
         oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, model)
         np.testing.assert_array_equal(mg.body_q.cpu().numpy(), model.body_q.numpy())
         np.testing.assert_array_equal(mg.body_qd.cpu().numpy(), model.body_qd.numpy())
+
+
+def test_heterogeneous_worlds_bit_exact(oracle_lib, cuda_lib):
+    """Featherstone over worlds of different sizes (18-dof quadruped, three free boxes, an empty world, a 1-dof link)."""
+    model = scenes.mixed_worlds_model(3)
+    ref, _, rc = simulate(model, oracle_lib.CollisionPipeline, oracle_lib.SolverFeatherstone, substeps=80, dt=1.0 / 480,
+                          record_contacts=True)
+    mg = model.to("cuda:0")
+    gpu, _, gc = simulate(mg, newton_b200.CollisionPipeline, newton_b200.solvers.SolverFeatherstone, substeps=80, dt=1.0 / 480,
+                          record_contacts=True)
+    assert rc == gc
+    for name in ("joint_q", "joint_qd", "body_q", "body_qd"):
+        np.testing.assert_array_equal(getattr(gpu, name).cpu().numpy(), getattr(ref, name).numpy(), err_msg=name)

@@ -163,6 +163,13 @@ def test_contact_force_and_parent_force_bit_exact(oracle_lib, cuda_lib):
         assert np.abs(canonical_contacts(out[1], model)[1]["force"]).max() > 1.0
 
 
+def test_heterogeneous_worlds_bit_exact(oracle_lib, cuda_lib):
+    """Worlds of different sizes in one model (quadruped / box stack / empty / single link): partial lane groups."""
+    model = scenes.mixed_worlds_model(3)
+    out = _both(model, 100, 1.0 / 240, {"iterations": 4}, oracle_lib)
+    _assert_exact(*out, model)
+
+
 def test_implicit_single_world_and_no_contacts(oracle_lib, cuda_lib):
     """Model built without begin_world() (all entities in world -1) and step(contacts=None)."""
     b = ModelBuilder()

@@ -581,3 +581,26 @@ def test_xpbd_parent_force_single_body(oracle_lib, joint_kind, parent_kinematic)
     assert avg[2] == pytest.approx(weight, rel=0.01)
     np.testing.assert_allclose(avg[:2], 0.0, atol=0.1)
     np.testing.assert_allclose(avg[3:], 0.0, atol=0.1)
+
+
+@pytest.mark.parametrize("solver_name", ["featherstone", "xpbd"])
+def test_example_basic_pendulum_final_state(oracle_lib, solver_name):
+    """BASELINE config 1: ``example_basic_pendulum.py`` (2 box links, 2 revolute joints about Y, fps 100, 10 substeps,
+    100 frames) and its ``test_final`` (:113-137): links stay in the x = 0 swing plane, |y| < 1, 0 < z < 5, bounded
+    velocities.  Run with SolverFeatherstone (the config) and with the example's own SolverXPBD."""
+    model = scenes.pendulum_model()
+    solver = oracle_lib.SolverFeatherstone(model) if solver_name == "featherstone" else oracle_lib.SolverXPBD(model)
+    pipe = oracle_lib.CollisionPipeline(model)
+    contacts = pipe.contacts()
+    s0, s1, ctl = model.state(), model.state(), model.control()
+    for _ in range(100 * 10):
+        s0.clear_forces()
+        pipe.collide(s0, contacts)
+        solver.step(s0, s1, ctl, contacts, 1.0 / 100 / 10)
+        s0, s1 = s1, s0
+    q, qd = s0.body_q.numpy(), s0.body_qd.numpy()
+    for b in (0, 1):
+        assert abs(q[b, 0]) < 1e-5 and abs(q[b, 1]) < 1.0 and 0.0 < q[b, 2] < 5.0
+        assert abs(qd[b, 0]) < 1e-4
+        assert abs(qd[b, 1]) < 10.0 and abs(qd[b, 2]) < 5.0 and abs(qd[b, 3]) < 10.0 and abs(qd[b, 4]) < 10.0
+    assert np.abs(qd).max() > 0.1  # it is swinging
