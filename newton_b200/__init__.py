@@ -1,7 +1,7 @@
 """newton_b200 - B200-native batched rigid-body stepper behind Newton's solver API."""
 from .sim import (  # noqa: F401
     MAXVAL, BodyFlags, Contacts, Control, GeoType, JointDofConfig, JointType, Model, ModelBuilder,
-    ModelFlags, ShapeConfig, ShapeFlags, State, StateFlags, eval_fk,
+    ModelFlags, ShapeConfig, ShapeFlags, State, StateFlags, eval_fk, eval_ik,
 )
 from .sim.collide import CollisionPipeline  # noqa: F401,E402
 from . import solvers  # noqa: F401,E402

@@ -19,7 +19,7 @@ STATUS = {0: "NB2_OK", 1: "NB2_ERR_INVALID_ARGUMENT", 2: "NB2_ERR_UNSUPPORTED", 
 # every symbol include/newton_b200.h declares
 EXPORTED_SYMBOLS = (
     "nb2_model_create", "nb2_model_destroy", "nb2_model_notify_changed", "nb2_model_rigid_contact_max", "nb2_collide",
-    "nb2_xpbd_step", "nb2_xpbd_update_contacts", "nb2_integrate_bodies", "nb2_featherstone_step", "nb2_eval_fk", "nb2_last_error",
+    "nb2_xpbd_step", "nb2_xpbd_update_contacts", "nb2_integrate_bodies", "nb2_featherstone_step", "nb2_eval_fk", "nb2_eval_ik", "nb2_last_error",
     "nb2_kernel_launch_count", "nb2_version",
 )
 
@@ -61,6 +61,8 @@ def lib():
         L.nb2_featherstone_step.restype = C.c_int
         L.nb2_eval_fk.argtypes = [P, P, P, P, P, P]
         L.nb2_eval_fk.restype = C.c_int
+        L.nb2_eval_ik.argtypes = [P, P, P, P, P, P]
+        L.nb2_eval_ik.restype = C.c_int
         L.nb2_last_error.restype = C.c_char_p
         L.nb2_kernel_launch_count.restype = C.c_int64
         L.nb2_version.restype = C.c_char_p

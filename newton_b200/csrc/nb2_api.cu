@@ -202,8 +202,13 @@ static nb2_status build_tables(nb2_model* m, const nb2_model_desc& d) {
     }
     // ---- articulation tables for the Featherstone kernel ----------------------------------------
     {
-        std::vector<int> janc, jqd, bflags;
+        std::vector<int> janc, jqd, bflags, jtype, jdim;
         if ((st = fetch(d.joint_ancestor, size_t(J), janc))) return st;
+        if ((st = fetch(d.joint_type, size_t(J), jtype))) return st;
+        if ((st = fetch(d.joint_dof_dim, size_t(J) * 2, jdim))) return st;
+        h.ik_supported = true;
+        for (int j = 0; j < J; ++j)
+            if (jtype[j] == 6 && jdim[2 * j + 1] > 1) h.ik_supported = false;  // D6 with 2-3 angular axes
         if ((st = fetch(d.body_flags, size_t(B), bflags))) return st;
         for (int b = 0; b < B; ++b)
             if (bflags[b] & 2) {
@@ -472,6 +477,19 @@ nb2_status nb2_eval_fk(nb2_model* model, const float* joint_q, const float* join
         return NB2_ERR_INVALID_ARGUMENT;
     }
     return launch_eval_fk(model, joint_q, joint_qd, body_q, body_qd, static_cast<cudaStream_t>(cuda_stream));
+}
+
+nb2_status nb2_eval_ik(nb2_model* model, const float* body_q, const float* body_qd, float* joint_q, float* joint_qd,
+                       void* cuda_stream) {
+    if (!model || !body_q || !body_qd || !joint_q || !joint_qd) {
+        set_error("nb2_eval_ik: NULL argument");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    if (!model->host.ik_supported) {
+        set_error("nb2_eval_ik: D6 joints with two or three angular axes are not supported");
+        return NB2_ERR_UNSUPPORTED;
+    }
+    return launch_eval_ik(model, body_q, body_qd, joint_q, joint_qd, static_cast<cudaStream_t>(cuda_stream));
 }
 
 const char* nb2_last_error(void) { return g_last_error.c_str(); }

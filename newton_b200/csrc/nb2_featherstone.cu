@@ -918,4 +918,90 @@ nb2_status launch_eval_fk(nb2_model* m, const float* joint_q, const float* joint
     return NB2_OK;
 }
 
+// ---- public newton.eval_ik (sim/articulation.py:640-932 eval_articulation_ik): one thread per joint -----------------------------
+NB2_DEV float twist_angle_signed(V3 axis, Q4 q) {  // wp.quat_twist_angle_signed, see oracle_featherstone.h
+    float proj = dot(V3(q.x, q.y, q.z), axis), w = q.w;
+    if (w < 0.0f) {
+        proj = -proj;
+        w = -w;
+    }
+    return 2.0f * atan2_w(proj, w);
+}
+
+__global__ void __launch_bounds__(128) eval_ik_kernel(DevModel M, const float* __restrict__ body_q, const float* __restrict__ body_qd,
+                                                      float* __restrict__ joint_q, float* __restrict__ joint_qd) {
+    const nb2_model_desc& d = M.d;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d.joint_count || d.joint_articulation[j] < 0) return;
+    const int parent = d.joint_parent[j], child = d.joint_child[j], type = d.joint_type[j];
+    const Xf X_pj = ldx(d.joint_X_p + 7 * j), X_cj = ldx(d.joint_X_c + 7 * j);
+    V3 w_p, v_p, pv, pw;
+    Xf X_wpj = X_pj, X_wp;
+    if (parent >= 0) {
+        X_wp = ldx(body_q + 7 * parent);
+        X_wpj = xmul(X_wp, X_pj);
+        pv = ld3(body_qd + 6 * parent);
+        pw = ld3(body_qd + 6 * parent + 3);
+        w_p = pw;
+        v_p = cross(pw, X_wpj.p - xpoint(X_wp, ld3(d.body_com + 3 * parent))) + pv;
+    }
+    const Xf X_wc = ldx(body_q + 7 * child);
+    const Xf X_wcj = xmul(X_wc, X_cj);
+    const V3 cv = ld3(body_qd + 6 * child), w_c = ld3(body_qd + 6 * child + 3);
+    const V3 v_c = cross(w_c, X_wcj.p - xpoint(X_wc, ld3(d.body_com + 3 * child))) + cv;
+    const V3 x_err = X_wcj.p - X_wpj.p, v_err = v_c - v_p, w_err = w_c - w_p;
+    const Q4 q_p = X_wpj.q, q_c = X_wcj.q;
+    const int q_start = d.joint_q_start[j], qd_start = d.joint_qd_start[j];
+    const int lin = d.joint_dof_dim[2 * j], ang = d.joint_dof_dim[2 * j + 1];
+    if (type == FJ_PRISMATIC) {
+        const V3 axis_p = qrot(q_p, ld3(d.joint_axis + 3 * qd_start));
+        joint_q[q_start] = dot(x_err, axis_p);
+        joint_qd[qd_start] = dot(v_err, axis_p);
+    } else if (type == FJ_REVOLUTE) {
+        const Q4 q_pc = qmul(qconj(q_p), q_c);
+        const V3 ax = ld3(d.joint_axis + 3 * qd_start);
+        joint_q[q_start] = twist_angle_signed(ax, q_pc);
+        joint_qd[qd_start] = dot(w_err, xvec(X_wpj, ax));
+    } else if (type == FJ_BALL) {
+        const Q4 q_pc = qmul(qconj(q_p), q_c);
+        joint_q[q_start] = q_pc.x; joint_q[q_start + 1] = q_pc.y; joint_q[q_start + 2] = q_pc.z; joint_q[q_start + 3] = q_pc.w;
+        const V3 av = xvec(xinv(X_wpj), w_err);
+        st3(joint_qd + qd_start, av);
+    } else if (type == FJ_FREE || type == FJ_DISTANCE) {
+        const Q4 q_pc = qmul(qconj(q_p), q_c);
+        const V3 x_err_c = qrot_inv(q_p, x_err);
+        const V3 x_com_w = xpoint(X_wc, ld3(d.body_com + 3 * child));
+        V3 v_com_err = cv;
+        if (parent >= 0) v_com_err = v_com_err - (cross(pw, x_com_w - xpoint(X_wp, ld3(d.body_com + 3 * parent))) + pv);
+        const V3 v_err_c = qrot_inv(q_p, v_com_err), w_err_c = qrot_inv(q_p, w_err);
+        st3(joint_q + q_start, x_err_c);
+        joint_q[q_start + 3] = q_pc.x; joint_q[q_start + 4] = q_pc.y; joint_q[q_start + 5] = q_pc.z; joint_q[q_start + 6] = q_pc.w;
+        st3(joint_qd + qd_start, v_err_c);
+        st3(joint_qd + qd_start + 3, w_err_c);
+    } else if (type == FJ_D6) {
+        const V3 x_err_c = qrot_inv(q_p, x_err), v_err_c = qrot_inv(q_p, v_err);
+        for (int k = 0; k < 3; ++k)
+            if (lin > k) {
+                const V3 ax = ld3(d.joint_axis + 3 * (qd_start + k));
+                joint_q[q_start + k] = dot(x_err_c, ax);
+                joint_qd[qd_start + k] = dot(v_err_c, ax);
+            }
+        if (ang == 1) {
+            const Q4 q_pc = qmul(qconj(q_p), q_c);
+            const V3 ax = ld3(d.joint_axis + 3 * (qd_start + lin));
+            joint_q[q_start + lin] = twist_angle_signed(ax, q_pc);
+            joint_qd[qd_start + lin] = dot(w_err, xvec(X_wpj, ax));
+        }
+    }
+}
+
+nb2_status launch_eval_ik(nb2_model* m, const float* body_q, const float* body_qd, float* joint_q, float* joint_qd, cudaStream_t s) {
+    const int J = m->dev.d.joint_count;
+    if (J == 0) return NB2_OK;
+    eval_ik_kernel<<<(J + 127) / 128, 128, 0, s>>>(m->dev, body_q, body_qd, joint_q, joint_qd);
+    count_launch();
+    NB2_CUDA_CHECK(cudaGetLastError());
+    return NB2_OK;
+}
+
 }  // namespace nb2

@@ -68,6 +68,7 @@ struct HostTables {
     std::vector<int> joint_depth, art_H_start, env_H_start;
     std::vector<unsigned long long> joint_anc_mask;
     bool featherstone_supported = true;
+    bool ik_supported = true;  // false when a D6 joint has 2-3 angular axes
     std::string featherstone_reason;
 };
 
@@ -97,6 +98,7 @@ nb2_status launch_featherstone_step(nb2_model* m, const nb2_featherstone_params&
                                     cudaStream_t s);
 nb2_status launch_eval_fk(nb2_model* m, const float* joint_q, const float* joint_qd, float* body_q, float* body_qd,
                           cudaStream_t s);
+nb2_status launch_eval_ik(nb2_model* m, const float* body_q, const float* body_qd, float* joint_q, float* joint_qd, cudaStream_t s);
 }  // namespace nb2
 
 #define NB2_CUDA_CHECK(expr)                                                                          \

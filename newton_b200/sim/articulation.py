@@ -118,3 +118,21 @@ def eval_fk(model, joint_q, joint_qd, state) -> None:
 
     state.body_q.copy_(torch.from_numpy(body_q.astype(np.float32)))
     state.body_qd.copy_(torch.from_numpy(body_qd.astype(np.float32)))
+
+
+def eval_ik(model, state, joint_q, joint_qd) -> None:
+    """``newton.eval_ik`` (reference ``sim/articulation.py:883-932``): ``state.body_q`` / ``body_qd`` -> generalized
+    ``joint_q`` / ``joint_qd`` for every articulated joint, through ``nb2_eval_ik`` (one thread per joint).  CUDA models only;
+    like every simulation call of this package there is no CPU path (the oracle under ``oracle/`` is the CPU checker)."""
+    import ctypes as C
+
+    from .. import _abi, _lib
+
+    nm = _lib.native_model(model)  # raises for CPU models
+    with torch.cuda.device(nm.device_index):
+        _lib.check(
+            _lib.lib().nb2_eval_ik(nm.handle, C.c_void_p(_abi.ptr(state.body_q)), C.c_void_p(_abi.ptr(state.body_qd)),
+                                   C.c_void_p(_abi.ptr(joint_q)), C.c_void_p(_abi.ptr(joint_qd)),
+                                   _lib.current_stream_ptr(model)),
+            "nb2_eval_ik",
+        )

@@ -240,6 +240,15 @@ def eval_fk(model, joint_q, joint_qd, state):
                       C.c_void_p(_abi.ptr(state.body_q)), C.c_void_p(_abi.ptr(state.body_qd)))
 
 
+def eval_ik(model, state, joint_q, joint_qd):
+    """newton.eval_ik: body_q / body_qd -> joint_q / joint_qd (sim/articulation.py:640-932)."""
+    d = _abi.model_desc(model)
+    n = lib().orc_eval_ik(C.byref(d), C.c_void_p(_abi.ptr(state.body_q)), C.c_void_p(_abi.ptr(state.body_qd)),
+                          C.c_void_p(_abi.ptr(joint_q)), C.c_void_p(_abi.ptr(joint_qd)))
+    if n:
+        raise NotImplementedError("oracle eval_ik: D6 joints with 2-3 angular axes")
+
+
 def shape_aabbs(model, body_q):
     d = _abi.model_desc(model)
     lo = np.zeros((model.shape_count, 3), dtype=np.float32)

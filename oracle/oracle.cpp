@@ -245,6 +245,11 @@ void orc_eval_fk(const nb2_model_desc* m, const float* joint_q, const float* joi
     eval_articulation_fk(*m, joint_q, joint_qd, body_q, body_qd);
 }
 
+// newton.eval_ik(model, state, joint_q, joint_qd); returns the number of joints it cannot invert (D6 with 2-3 angular axes)
+int orc_eval_ik(const nb2_model_desc* m, const float* body_q, const float* body_qd, float* joint_q, float* joint_qd) {
+    return eval_articulation_ik(*m, body_q, body_qd, joint_q, joint_qd);
+}
+
 const char* orc_version(void) { return "oracle-r1"; }
 
 }  // extern "C"

@@ -721,4 +721,86 @@ inline void eval_articulation_fk(const nb2_model_desc& m, const float* joint_q, 
         }
 }
 
+// wp.quat_twist_angle_signed(axis, q): signed rotation angle of q's twist about `axis`.  Warp built-in (warp-lang >= 1.16,
+// not vendored; PARITY UNPINNED): restated as 2*atan2(q.xyz . axis, q.w) folded into (-pi, pi], which equals the
+// legacy `2*acos(twist.w)*sign(twist.xyz . axis)` form of warp.sim away from the branch cut.
+inline float quat_twist_angle_signed(vec3 axis, quat q) {
+    float proj = dot(vec3(q.x, q.y, q.z), axis), w = q.w;
+    if (w < 0.0f) { proj = -proj; w = -w; }
+    return 2.0f * atan2_w(proj, w);
+}
+
+// ---- public newton.eval_ik (sim/articulation.py:640-932 eval_articulation_ik; one joint per thread, no mask) ---------------
+// D6 joints with 2 or 3 angular axes (invert_{2,3}d_rotational_dofs) are not restated: returns the number of such joints.
+inline int eval_articulation_ik(const nb2_model_desc& m, const float* body_q, const float* body_qd, float* joint_q, float* joint_qd) {
+    int unsupported = 0;
+    for (int a = 0; a < m.articulation_count; ++a)
+        for (int j = m.articulation_start[a]; j < m.articulation_start[a + 1]; ++j) {
+            const int parent = m.joint_parent[j], child = m.joint_child[j], type = m.joint_type[j];
+            transform X_pj = transform::load(m.joint_X_p + 7 * j), X_cj = transform::load(m.joint_X_c + 7 * j);
+            vec3 w_p, v_p;
+            spatial v_wp;
+            transform X_wpj = X_pj, X_wp;
+            if (parent >= 0) {
+                X_wp = transform::load(body_q + 7 * parent);
+                X_wpj = X_wp * X_pj;
+                v_wp = spatial::load(body_qd + 6 * parent);
+                w_p = v_wp.bot;
+                v_p = velocity_at_point(v_wp, X_wpj.p - transform_point(X_wp, load3(m.body_com + 3 * parent)));
+            }
+            transform X_wc = transform::load(body_q + 7 * child);
+            transform X_wcj = X_wc * X_cj;
+            spatial v_wc = spatial::load(body_qd + 6 * child);
+            vec3 w_c = v_wc.bot;
+            vec3 v_c = velocity_at_point(v_wc, X_wcj.p - transform_point(X_wc, load3(m.body_com + 3 * child)));
+            vec3 x_err = X_wcj.p - X_wpj.p, v_err = v_c - v_p, w_err = w_c - w_p;
+            quat q_p = X_wpj.q, q_c = X_wcj.q;
+            int q_start = m.joint_q_start[j], qd_start = m.joint_qd_start[j];
+            int lin = m.joint_dof_dim[2 * j], ang = m.joint_dof_dim[2 * j + 1];
+            auto axis = [&](int k) { return load3(m.joint_axis + 3 * k); };
+            if (type == JT_PRISMATIC) {
+                vec3 axis_p = quat_rotate(q_p, axis(qd_start));
+                joint_q[q_start] = dot(x_err, axis_p);
+                joint_qd[qd_start] = dot(v_err, axis_p);
+            } else if (type == JT_REVOLUTE) {
+                quat q_pc = quat_inverse(q_p) * q_c;
+                vec3 ax = axis(qd_start);
+                joint_q[q_start] = quat_twist_angle_signed(ax, q_pc);
+                joint_qd[qd_start] = dot(w_err, transform_vector(X_wpj, ax));
+            } else if (type == JT_BALL) {
+                quat q_pc = quat_inverse(q_p) * q_c;
+                joint_q[q_start] = q_pc.x; joint_q[q_start + 1] = q_pc.y; joint_q[q_start + 2] = q_pc.z; joint_q[q_start + 3] = q_pc.w;
+                vec3 ang_vel = transform_vector(transform_inverse(X_wpj), w_err);
+                joint_qd[qd_start] = ang_vel.x; joint_qd[qd_start + 1] = ang_vel.y; joint_qd[qd_start + 2] = ang_vel.z;
+            } else if (type == JT_FREE || type == JT_DISTANCE) {
+                quat q_pc = quat_inverse(q_p) * q_c;
+                vec3 x_err_c = quat_rotate_inv(q_p, x_err);
+                vec3 x_child_com_world = transform_point(X_wc, load3(m.body_com + 3 * child));
+                vec3 v_com_err = v_wc.top;
+                if (parent >= 0)
+                    v_com_err = v_com_err - velocity_at_point(v_wp, x_child_com_world - transform_point(X_wp, load3(m.body_com + 3 * parent)));
+                vec3 v_err_c = quat_rotate_inv(q_p, v_com_err), w_err_c = quat_rotate_inv(q_p, w_err);
+                joint_q[q_start] = x_err_c.x; joint_q[q_start + 1] = x_err_c.y; joint_q[q_start + 2] = x_err_c.z;
+                joint_q[q_start + 3] = q_pc.x; joint_q[q_start + 4] = q_pc.y; joint_q[q_start + 5] = q_pc.z; joint_q[q_start + 6] = q_pc.w;
+                joint_qd[qd_start] = v_err_c.x; joint_qd[qd_start + 1] = v_err_c.y; joint_qd[qd_start + 2] = v_err_c.z;
+                joint_qd[qd_start + 3] = w_err_c.x; joint_qd[qd_start + 4] = w_err_c.y; joint_qd[qd_start + 5] = w_err_c.z;
+            } else if (type == JT_D6) {
+                vec3 x_err_c = quat_rotate_inv(q_p, x_err), v_err_c = quat_rotate_inv(q_p, v_err);
+                for (int k = 0; k < 3; ++k)
+                    if (lin > k) {
+                        joint_q[q_start + k] = dot(x_err_c, axis(qd_start + k));
+                        joint_qd[qd_start + k] = dot(v_err_c, axis(qd_start + k));
+                    }
+                if (ang == 1) {
+                    quat q_pc = quat_inverse(q_p) * q_c;
+                    vec3 ax = axis(qd_start + lin);
+                    joint_q[q_start + lin] = quat_twist_angle_signed(ax, q_pc);
+                    joint_qd[qd_start + lin] = dot(w_err, transform_vector(X_wpj, ax));
+                }
+                if (ang > 1) unsupported += 1;
+            }
+        }
+    return unsupported;
+}
+
 }  // namespace orc

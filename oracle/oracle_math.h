@@ -58,6 +58,7 @@ inline vec3 vabs(vec3 a) { return vec3(std::fabs(a.x), std::fabs(a.y), std::fabs
 inline float asin_w(float x) { return (float)std::asin((double)x); }
 inline float acos_w(float x) { return (float)std::acos((double)x); }
 inline float sin_w(float x) { return (float)std::sin((double)x); }
+inline float atan2_w(float y, float x) { return (float)std::atan2((double)y, (double)x); }
 inline float cos_w(float x) { return (float)std::cos((double)x); }
 inline float clampf(float x, float a, float b) { return minf(maxf(a, x), b); }
 inline float nonzero(float x) { return x != 0.0f ? 1.0f : 0.0f; }

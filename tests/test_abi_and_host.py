@@ -142,3 +142,20 @@ def test_oracle_eval_fk_matches_host_walk(oracle_lib):
         oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, model)
         np.testing.assert_allclose(model.body_q.numpy(), host_q.numpy(), atol=2e-6)
         np.testing.assert_allclose(model.body_qd.numpy(), host_qd.numpy(), atol=2e-6)
+
+
+def test_oracle_eval_ik_inverts_eval_fk(oracle_lib):
+    """newton.eval_ik (sim/articulation.py:640-932) is the inverse of eval_fk on generalized coordinates and velocities
+    (FREE root in the public COM-velocity convention, revolute legs, the world-anchored pendulum): round trip to 1e-6."""
+    import torch
+
+    from newton_b200 import scenes
+
+    for model in (scenes.quadruped_model(3, seed=1), scenes.pendulum_model(), scenes.mixed_worlds_model(1)):
+        g = torch.Generator().manual_seed(0)
+        model.joint_qd.copy_(torch.rand(model.joint_qd.shape, generator=g) - 0.5)
+        oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, model)
+        q, qd = torch.zeros_like(model.joint_q), torch.zeros_like(model.joint_qd)
+        oracle_lib.eval_ik(model, model, q, qd)
+        np.testing.assert_allclose(q.numpy(), model.joint_q.numpy(), atol=1e-6)
+        np.testing.assert_allclose(qd.numpy(), model.joint_qd.numpy(), atol=1e-6)

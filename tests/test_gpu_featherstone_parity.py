@@ -103,3 +103,24 @@ def test_heterogeneous_worlds_bit_exact(oracle_lib, cuda_lib):
     assert rc == gc
     for name in ("joint_q", "joint_qd", "body_q", "body_qd"):
         np.testing.assert_array_equal(getattr(gpu, name).cpu().numpy(), getattr(ref, name).numpy(), err_msg=name)
+
+
+def test_eval_ik_kernel_bit_exact(oracle_lib, cuda_lib):
+    """nb2_eval_ik vs the oracle's newton.eval_ik on states produced by 40 XPBD substeps (maximal-coordinate solver:
+    the joint coordinates are only recoverable through eval_ik), plus the fk -> ik round trip on the device."""
+    for model in (scenes.quadruped_model(9, seed=3), scenes.mixed_worlds_model(2)):
+        state, _, _ = simulate(model, oracle_lib.CollisionPipeline, oracle_lib.SolverXPBD, substeps=40, dt=0.004,
+                               solver_kwargs={"iterations": 3})
+        q_ref, qd_ref = torch.zeros_like(model.joint_q), torch.zeros_like(model.joint_qd)
+        oracle_lib.eval_ik(model, state, q_ref, qd_ref)
+        mg = model.to("cuda:0")
+        sg = mg.state()
+        sg.body_q.copy_(state.body_q)
+        sg.body_qd.copy_(state.body_qd)
+        q, qd = torch.zeros_like(mg.joint_q), torch.zeros_like(mg.joint_qd)
+        newton_b200.eval_ik(mg, sg, q, qd)
+        np.testing.assert_array_equal(q.cpu().numpy(), q_ref.numpy())
+        np.testing.assert_array_equal(qd.cpu().numpy(), qd_ref.numpy())
+        newton_b200.eval_fk(mg, mg.joint_q, mg.joint_qd, sg)
+        newton_b200.eval_ik(mg, sg, q, qd)
+        np.testing.assert_allclose(q.cpu().numpy(), mg.joint_q.cpu().numpy(), atol=1e-6)
