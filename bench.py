@@ -226,16 +226,30 @@ def run_native(args):
     launches_per_step = _lib.kernel_launch_count() - launches_before  # kernels captured in one frame graph
     assert SUBSTEPS % 2 == 0  # state_0/state_1 swap parity: the graph ends where it began
 
-    gathered_q = gathered_qd = None
+    gathered_q = gathered_qd = snap_q = snap_qd = None
+    pending = []  # NCCL work handles of the previous frame's gather
     if world > 1:  # end-of-frame state gather over NVLink; part of every timed step
         gathered_q = torch.empty((world * state_0.body_q.shape[0], 7), dtype=torch.float32, device=dev)
         gathered_qd = torch.empty((world * state_0.body_qd.shape[0], 6), dtype=torch.float32, device=dev)
+        snap_q, snap_qd = torch.empty_like(state_0.body_q), torch.empty_like(state_0.body_qd)
+
+    def drain():
+        for w in pending:
+            w.wait()  # stream-level wait (no host sync)
+        pending.clear()
 
     def step_device():
+        """One frame.  N > 1: the frame's body_q / body_qd are snapshotted (2.8 MB D2D) and all-gathered on NCCL's stream
+        while the next frame computes (SURVEY.md §8(e): "on a dedicated stream, overlapped with the next frame");
+        the snapshot buffers are recycled only after the previous gather has finished, and the last gather is drained
+        inside the timed region."""
         graph.replay()
         if world > 1:
-            dist.all_gather_into_tensor(gathered_q, state_0.body_q)
-            dist.all_gather_into_tensor(gathered_qd, state_0.body_qd)
+            drain()
+            snap_q.copy_(state_0.body_q)
+            snap_qd.copy_(state_0.body_qd)
+            pending.append(dist.all_gather_into_tensor(gathered_q, snap_q, async_op=True))
+            pending.append(dist.all_gather_into_tensor(gathered_qd, snap_qd, async_op=True))
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
@@ -256,9 +270,14 @@ def run_native(args):
             a.record()
             fn()
             b.record()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        drain()  # the last frame's gather is part of the job
+        d1.record()
         barrier()
         clocks = sampler.stop() if sampler else None
         per_step = [a.elapsed_time(b) for a, b in ev]
+        per_step[-1] += d0.elapsed_time(d1)
         timed.last_per_step = per_step
         ms = sum(per_step)
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
