@@ -290,7 +290,16 @@ __global__ void __launch_bounds__(32, 14) featherstone_step_kernel(DevModel M, n
             for (int i = qd0; i < qd1; ++i) sm.jf[i - d0] = ctl.joint_f[i];
         }
     }
-    // ---- eval_rigid_fk: level-parallel ------------------------------------------------------------
+    // ---- eval_rigid_fk: joint-local transforms for all joints at once, then the tree recurrence level by level ----------------
+    // (scratch: X_j(q) and X_cj^-1 live in the spatial-inertia block of the joint's body, which is unused until the RNEA pass)
+    for (int j = l; j < nj; j += L) {
+        const int gj = j0 + j;
+        const Xf X_j = joint_transform(d, d.joint_type[gj], d.joint_qd_start[gj], d.joint_dof_dim[2 * gj], d.joint_dof_dim[2 * gj + 1],
+                                       sin.joint_q, d.joint_q_start[gj]);
+        stx(sm.Is + 36 * j, X_j);
+        stx(sm.Is + 36 * j + 7, xinv(ldx(d.joint_X_c + 7 * gj)));
+    }
+    __syncwarp(gmask);
     for (int lvl = 0; lvl <= M.max_depth; ++lvl) {
         for (int j = l; j < nj; j += L) {
             const int gj = j0 + j;
@@ -298,9 +307,7 @@ __global__ void __launch_bounds__(32, 14) featherstone_step_kernel(DevModel M, n
             const int parent = d.joint_parent[gj], child = d.joint_child[gj] - b0;
             Xf X_wpj = ldx(d.joint_X_p + 7 * gj);
             if (parent >= 0) X_wpj = xmul(ldx(sm.bq + 7 * (parent - b0)), X_wpj);
-            const Xf X_j = joint_transform(d, d.joint_type[gj], d.joint_qd_start[gj], d.joint_dof_dim[2 * gj], d.joint_dof_dim[2 * gj + 1],
-                                           sin.joint_q, d.joint_q_start[gj]);
-            const Xf X_wc = xmul(xmul(X_wpj, X_j), xinv(ldx(d.joint_X_c + 7 * gj)));
+            const Xf X_wc = xmul(xmul(X_wpj, ldx(sm.Is + 36 * j)), ldx(sm.Is + 36 * j + 7));
             const Xf X_sm = xmul(X_wc, Xf(ld3(d.body_com + 3 * (b0 + child)), Q4()));
             stx(sm.bq + 7 * child, X_wc);
             stx(sm.bqc + 7 * child, X_sm);
@@ -328,80 +335,92 @@ __global__ void __launch_bounds__(32, 14) featherstone_step_kernel(DevModel M, n
         o[0] = v_int.x; o[1] = v_int.y; o[2] = v_int.z; o[3] = omega.x; o[4] = omega.y; o[5] = omega.z;
     }
     __syncwarp(gmask);
-    // ---- eval_rigid_id: RNEA forward, level-parallel ----------------------------------------------------
-    for (int lvl = 0; lvl <= M.max_depth; ++lvl) {
+    // ---- eval_rigid_id (RNEA forward).  Only v_s / a_s recur down the tree; everything else - motion subspaces S, joint
+    // velocities v_j, bias terms, spatial inertias - needs the FK poses alone and runs for all joints at once. ---------------
+    for (int j = l; j < nj; j += L) {  // A: per-joint quantities (v_j parked in vs[child], c_app in as[child])
+        const int gj = j0 + j;
+        const int type = d.joint_type[gj], parent = d.joint_parent[gj], child = d.joint_child[gj] - b0;
+        const int art = d.joint_articulation[gj];
+        const int root = d.articulation_start[art];
+        V3 solve_origin;
+        {
+            const int rt = d.joint_type[root];
+            if (rt == FJ_FREE || rt == FJ_DISTANCE) solve_origin = ld3(sm.bqc + 7 * (d.joint_child[root] - b0));
+        }
+        Xf X_wpj = ldx(d.joint_X_p + 7 * gj);
+        if (parent >= 0) X_wpj = xmul(ldx(sm.bq + 7 * (parent - b0)), X_wpj);
+        const Xf X_s(X_wpj.p - solve_origin, X_wpj.q);
+        const int qs = d.joint_q_start[gj], qds = d.joint_qd_start[gj];
+        const int lin = d.joint_dof_dim[2 * gj], ang = d.joint_dof_dim[2 * gj + 1];
+        const float* jqd = sm.qd_in - d0;  // indexed with global dof ids
+        float* Sout = sm.S - 6 * d0;
+        S6 v_j, c_app;
+        if (type == FJ_PRISMATIC) {
+            S6 S = twist_xf(X_s, S6(ld3(d.joint_axis + 3 * qds), V3()));
+            v_j = S * jqd[qds];
+            st6(Sout + 6 * qds, S);
+        } else if (type == FJ_REVOLUTE) {
+            S6 S = twist_xf(X_s, S6(V3(), ld3(d.joint_axis + 3 * qds)));
+            v_j = S * jqd[qds];
+            st6(Sout + 6 * qds, S);
+        } else if (type == FJ_D6) {
+            V3 c_ang;
+            for (int k = 0; k < 3; ++k)
+                if (lin > k) {
+                    S6 S = twist_xf(X_s, S6(ld3(d.joint_axis + 3 * (qds + k)), V3()));
+                    v_j = v_j + S * jqd[qds + k];
+                    st6(Sout + 6 * (qds + k), S);
+                }
+            const int iqd = qds + lin, iq = qs + lin;
+            if (ang == 1) {
+                S6 S = twist_xf(X_s, S6(V3(), ld3(d.joint_axis + 3 * iqd)));
+                v_j = v_j + S * jqd[iqd];
+                st6(Sout + 6 * iqd, S);
+            }
+            if (ang == 3) {
+                V3 w0, w1, w2;
+                axes3(ld3(d.joint_axis + 3 * iqd), ld3(d.joint_axis + 3 * (iqd + 1)), ld3(d.joint_axis + 3 * (iqd + 2)), sin.joint_q[iq],
+                      sin.joint_q[iq + 1], w0, w1, w2);
+                S6 S0 = twist_xf(X_s, S6(V3(), w0)), S1 = twist_xf(X_s, S6(V3(), w1)), S2 = twist_xf(X_s, S6(V3(), w2));
+                const float q0 = jqd[iqd], q1 = jqd[iqd + 1], q2 = jqd[iqd + 2];
+                v_j = v_j + (S0 * q0 + S1 * q1 + S2 * q2);
+                st6(Sout + 6 * iqd, S0);
+                st6(Sout + 6 * (iqd + 1), S1);
+                st6(Sout + 6 * (iqd + 2), S2);
+                c_ang += cross(w0, w1) * (q0 * q1);
+                c_ang += cross(w0, w2) * (q0 * q2);
+                c_ang += cross(w1, w2) * (q1 * q2);
+            }
+            c_app = twist_xf(X_s, S6(V3(), c_ang));
+        } else if (type == FJ_BALL) {
+            S6 S0 = twist_xf(X_s, S6(V3(), V3(1.f, 0.f, 0.f))), S1 = twist_xf(X_s, S6(V3(), V3(0.f, 1.f, 0.f))),
+               S2 = twist_xf(X_s, S6(V3(), V3(0.f, 0.f, 1.f)));
+            st6(Sout + 6 * qds, S0);
+            st6(Sout + 6 * (qds + 1), S1);
+            st6(Sout + 6 * (qds + 2), S2);
+            v_j = S0 * jqd[qds] + S1 * jqd[qds + 1] + S2 * jqd[qds + 2];
+        } else if (type == FJ_FREE || type == FJ_DISTANCE) {
+            v_j = twist_xf(X_s, ld6(jqd + qds));
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                S6 e;
+                e.v[k] = 1.0f;
+                st6(Sout + 6 * (qds + k), twist_xf(X_s, e));
+            }
+        }
+        st6(sm.vs + 6 * child, v_j);
+        st6(sm.as + 6 * child, c_app);
+        st3(sm.so + 3 * child, solve_origin);
+        const Xf X_sm = ldx(sm.bqc + 7 * child);
+        spatial_inertia(Xf(X_sm.p - solve_origin, X_sm.q), d.body_mass[b0 + child], ldm(d.body_inertia + 9 * (b0 + child)), sm.Is + 36 * child);
+    }
+    __syncwarp(gmask);
+    for (int lvl = 0; lvl <= M.max_depth; ++lvl) {  // B: v_s = v_parent + v_j, a_s = a_parent + v_s x v_j + c_app
         for (int j = l; j < nj; j += L) {
             const int gj = j0 + j;
             if (M.joint_depth[gj] != lvl) continue;
-            const int type = d.joint_type[gj], parent = d.joint_parent[gj], child = d.joint_child[gj] - b0;
-            const int art = d.joint_articulation[gj];
-            const int root = d.articulation_start[art];
-            V3 solve_origin;
-            {
-                const int rt = d.joint_type[root];
-                if (rt == FJ_FREE || rt == FJ_DISTANCE) solve_origin = ld3(sm.bqc + 7 * (d.joint_child[root] - b0));
-            }
-            Xf X_wpj = ldx(d.joint_X_p + 7 * gj);
-            if (parent >= 0) X_wpj = xmul(ldx(sm.bq + 7 * (parent - b0)), X_wpj);
-            const Xf X_s(X_wpj.p - solve_origin, X_wpj.q);
-            const int qs = d.joint_q_start[gj], qds = d.joint_qd_start[gj];
-            const int lin = d.joint_dof_dim[2 * gj], ang = d.joint_dof_dim[2 * gj + 1];
-            const float* jqd = sm.qd_in - d0;  // indexed with global dof ids
-            float* Sout = sm.S - 6 * d0;
-            S6 v_j, c_app;
-            if (type == FJ_PRISMATIC) {
-                S6 S = twist_xf(X_s, S6(ld3(d.joint_axis + 3 * qds), V3()));
-                v_j = S * jqd[qds];
-                st6(Sout + 6 * qds, S);
-            } else if (type == FJ_REVOLUTE) {
-                S6 S = twist_xf(X_s, S6(V3(), ld3(d.joint_axis + 3 * qds)));
-                v_j = S * jqd[qds];
-                st6(Sout + 6 * qds, S);
-            } else if (type == FJ_D6) {
-                V3 c_ang;
-                for (int k = 0; k < 3; ++k)
-                    if (lin > k) {
-                        S6 S = twist_xf(X_s, S6(ld3(d.joint_axis + 3 * (qds + k)), V3()));
-                        v_j = v_j + S * jqd[qds + k];
-                        st6(Sout + 6 * (qds + k), S);
-                    }
-                const int iqd = qds + lin, iq = qs + lin;
-                if (ang == 1) {
-                    S6 S = twist_xf(X_s, S6(V3(), ld3(d.joint_axis + 3 * iqd)));
-                    v_j = v_j + S * jqd[iqd];
-                    st6(Sout + 6 * iqd, S);
-                }
-                if (ang == 3) {
-                    V3 w0, w1, w2;
-                    axes3(ld3(d.joint_axis + 3 * iqd), ld3(d.joint_axis + 3 * (iqd + 1)), ld3(d.joint_axis + 3 * (iqd + 2)), sin.joint_q[iq],
-                          sin.joint_q[iq + 1], w0, w1, w2);
-                    S6 S0 = twist_xf(X_s, S6(V3(), w0)), S1 = twist_xf(X_s, S6(V3(), w1)), S2 = twist_xf(X_s, S6(V3(), w2));
-                    const float q0 = jqd[iqd], q1 = jqd[iqd + 1], q2 = jqd[iqd + 2];
-                    v_j = v_j + (S0 * q0 + S1 * q1 + S2 * q2);
-                    st6(Sout + 6 * iqd, S0);
-                    st6(Sout + 6 * (iqd + 1), S1);
-                    st6(Sout + 6 * (iqd + 2), S2);
-                    c_ang += cross(w0, w1) * (q0 * q1);
-                    c_ang += cross(w0, w2) * (q0 * q2);
-                    c_ang += cross(w1, w2) * (q1 * q2);
-                }
-                c_app = twist_xf(X_s, S6(V3(), c_ang));
-            } else if (type == FJ_BALL) {
-                S6 S0 = twist_xf(X_s, S6(V3(), V3(1.f, 0.f, 0.f))), S1 = twist_xf(X_s, S6(V3(), V3(0.f, 1.f, 0.f))),
-                   S2 = twist_xf(X_s, S6(V3(), V3(0.f, 0.f, 1.f)));
-                st6(Sout + 6 * qds, S0);
-                st6(Sout + 6 * (qds + 1), S1);
-                st6(Sout + 6 * (qds + 2), S2);
-                v_j = S0 * jqd[qds] + S1 * jqd[qds + 1] + S2 * jqd[qds + 2];
-            } else if (type == FJ_FREE || type == FJ_DISTANCE) {
-                v_j = twist_xf(X_s, ld6(jqd + qds));
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    S6 e;
-                    e.v[k] = 1.0f;
-                    st6(Sout + 6 * (qds + k), twist_xf(X_s, e));
-                }
-            }
+            const int parent = d.joint_parent[gj], child = d.joint_child[gj] - b0;
+            const S6 v_j = ld6(sm.vs + 6 * child), c_app = ld6(sm.as + 6 * child);
             S6 v_par, a_par;
             if (parent >= 0) {
                 v_par = ld6(sm.vs + 6 * (parent - b0));
@@ -409,26 +428,28 @@ __global__ void __launch_bounds__(32, 14) featherstone_step_kernel(DevModel M, n
             }
             const S6 v_s = v_par + v_j;
             const S6 a_s = a_par + scross(v_s, v_j) + c_app;
-            const Xf X_sm = ldx(sm.bqc + 7 * child);
-            const V3 x_com_s = X_sm.p - solve_origin;
-            st3(sm.so + 3 * child, solve_origin);
-            const float mass = d.body_mass[b0 + child];
-            int wi = d.body_world[b0 + child];
-            if (wi < 0) wi += d.gravity_count;
-            const V3 f_g = mass * ld3(d.gravity + 3 * wi);
-            const S6 f_g_s(f_g, cross(x_com_s, f_g));
-            float* Is = sm.Is + 36 * child;
-            spatial_inertia(Xf(x_com_s, X_sm.q), mass, ldm(d.body_inertia + 9 * (b0 + child)), Is);
-            const S6 f_b = m66v(Is, a_s) + scross_dual(v_s, m66v(Is, v_s));
-            const V3 om = v_s.bot();
-            const V3 v_com_world = v_s.top() + cross(om, x_com_s);
-            st6(sm.qdfk + 6 * child, S6(v_com_world, om));
             st6(sm.vs + 6 * child, v_s);
             st6(sm.as + 6 * child, a_s);
-            st6(sm.fb + 6 * child, f_b - f_g_s);
         }
         __syncwarp(gmask);
     }
+    for (int j = l; j < nj; j += L) {  // C: body forces
+        const int gj = j0 + j, child = d.joint_child[gj] - b0;
+        const S6 v_s = ld6(sm.vs + 6 * child), a_s = ld6(sm.as + 6 * child);
+        const V3 x_com_s = ld3(sm.bqc + 7 * child) - ld3(sm.so + 3 * child);
+        const float mass = d.body_mass[b0 + child];
+        int wi = d.body_world[b0 + child];
+        if (wi < 0) wi += d.gravity_count;
+        const V3 f_g = mass * ld3(d.gravity + 3 * wi);
+        const S6 f_g_s(f_g, cross(x_com_s, f_g));
+        const float* Is = sm.Is + 36 * child;
+        const S6 f_b = m66v(Is, a_s) + scross_dual(v_s, m66v(Is, v_s));
+        const V3 om = v_s.bot();
+        const V3 v_com_world = v_s.top() + cross(om, x_com_s);
+        st6(sm.qdfk + 6 * child, S6(v_com_world, om));
+        st6(sm.fb + 6 * child, f_b - f_g_s);
+    }
+    __syncwarp(gmask);
     // ---- eval_body_contact (penalty), ordered per body over the env's contacts ---------------------------
     if (use_contacts) {
         for (int b = l; b < nb; b += L) {
@@ -480,13 +501,32 @@ __global__ void __launch_bounds__(32, 14) featherstone_step_kernel(DevModel M, n
         }
         __syncwarp(gmask);
     }
-    // ---- eval_rigid_tau: RNEA backward, deepest level first ----------------------------------------------------
+    // ---- eval_rigid_tau (RNEA backward).  The drive / limit / damping terms do not depend on the force recursion: they are
+    // evaluated for all dofs at once and parked in tau[]; the level loop only adds -S.f_s in the reference's order. ---------
+    for (int j = l; j < nj; j += L) {
+        const int gj = j0 + j, type = d.joint_type[gj];
+        const int ds = d.joint_qd_start[gj], cs = d.joint_q_start[gj], tqs = d.joint_target_q_start[gj];
+        const int lin = d.joint_dof_dim[2 * gj], ang = d.joint_dof_dim[2 * gj + 1];
+        const float* jqd = sm.qd_in - d0;
+        float* tau = sm.tau - d0;
+        if (type == FJ_BALL) {
+            for (int k = 0; k < 3; ++k) tau[ds + k] = -d.joint_damping[ds + k] * jqd[ds + k];  // passive_f
+        } else if (type == FJ_PRISMATIC || type == FJ_REVOLUTE || type == FJ_D6) {
+            for (int k = 0; k < lin + ang; ++k) {
+                const int jj = ds + k;
+                tau[jj] = joint_force(sin.joint_q[cs + k], jqd[jj], ctl.joint_target_q[tqs + k], ctl.joint_target_qd[jj], d.joint_target_ke[jj],
+                                      d.joint_target_kd[jj], d.joint_limit_lower[jj], d.joint_limit_upper[jj], d.joint_limit_ke[jj],
+                                      d.joint_limit_kd[jj], d.joint_damping[jj]);
+            }
+        }
+    }
+    __syncwarp(gmask);
     for (int lvl = M.max_depth; lvl >= 0; --lvl) {
         for (int j = l; j < nj; j += L) {
             const int gj = j0 + j;
             if (M.joint_depth[gj] != lvl) continue;
             const int type = d.joint_type[gj], child = d.joint_child[gj] - b0;
-            const int ds = d.joint_qd_start[gj], cs = d.joint_q_start[gj], tqs = d.joint_target_q_start[gj];
+            const int ds = d.joint_qd_start[gj];
             const int lin = d.joint_dof_dim[2 * gj], ang = d.joint_dof_dim[2 * gj + 1];
             const S6 f_b = ld6(sm.fb + 6 * child), f_t = ld6(sm.ft + 6 * child), fe = ld6(sm.fe + 6 * child);
             const V3 x_com_s = ld3(sm.bqc + 7 * child) - ld3(sm.so + 3 * child);
@@ -497,35 +537,34 @@ __global__ void __launch_bounds__(32, 14) featherstone_step_kernel(DevModel M, n
             const S6 f_s = f_b + f_t + f_ext;
             st6(sm.fs + 6 * j, f_s);
             const float* S = sm.S - 6 * d0;
-            const float* jqd = sm.qd_in - d0;
             const float* jf = sm.jf - d0;
             float* tau = sm.tau - d0;
             if (type == FJ_BALL) {
                 for (int k = 0; k < 3; ++k) {
                     const int jj = ds + k;
-                    const float passive_f = -d.joint_damping[jj] * jqd[jj];
-                    tau[jj] = -dot6(ld6(S + 6 * jj), f_s) + jf[jj] + passive_f;
+                    tau[jj] = -dot6(ld6(S + 6 * jj), f_s) + jf[jj] + tau[jj];  // + passive_f
                 }
             } else if (type == FJ_FREE || type == FJ_DISTANCE) {
                 for (int k = 0; k < 6; ++k) tau[ds + k] = -dot6(ld6(S + 6 * (ds + k)), f_s) + jf[ds + k];
             } else if (type == FJ_PRISMATIC || type == FJ_REVOLUTE || type == FJ_D6) {
                 for (int k = 0; k < lin + ang; ++k) {
                     const int jj = ds + k;
-                    const float drive = joint_force(sin.joint_q[cs + k], jqd[jj], ctl.joint_target_q[tqs + k], ctl.joint_target_qd[jj],
-                                                    d.joint_target_ke[jj], d.joint_target_kd[jj], d.joint_limit_lower[jj], d.joint_limit_upper[jj],
-                                                    d.joint_limit_ke[jj], d.joint_limit_kd[jj], d.joint_damping[jj]);
-                    tau[jj] = -dot6(ld6(S + 6 * jj), f_s) + drive + jf[jj];
+                    tau[jj] = -dot6(ld6(S + 6 * jj), f_s) + tau[jj] + jf[jj];  // + drive + joint_f
                 }
             }
         }
         __syncwarp(gmask);
-        // fold this level's f_s into the parents (serial reference order: descending joint index)
+        // fold this level's f_s into the parents (serial reference order: descending joint index); the body's joint list is
+        // ascending, so walk it backwards and take the joints it is the parent of
         for (int b = l; b < nb; b += L) {
+            const int gb = b0 + b;
             S6 acc = ld6(sm.ft + 6 * b);
             bool any = false;
-            for (int j = nj - 1; j >= 0; --j) {
-                const int gj = j0 + j;
-                if (M.joint_depth[gj] != lvl || d.joint_parent[gj] - b0 != b) continue;
+            for (int k = M.body_joint_start[gb + 1] - 1; k >= M.body_joint_start[gb]; --k) {
+                const int e = M.body_joint_entry[k];
+                if (e & 1) continue;  // the body is this joint's child
+                const int j = e >> 1;
+                if (M.joint_depth[j0 + j] != lvl) continue;
                 acc = acc + ld6(sm.fs + 6 * j);
                 any = true;
             }
@@ -542,18 +581,28 @@ __global__ void __launch_bounds__(32, 14) featherstone_step_kernel(DevModel M, n
         float* H = sm.H + M.art_H_start[art];
         float* Lg = M.fs_L + M.env_H_start[env] + M.art_H_start[art];
         if (update_mass) {
-            // H = J^T (M J), lower triangle only (all dense_cholesky reads), one column at a time:
-            //   P[:, b] = M J[:, b]  -> the 6-vectors I_i S_b of the bodies below joint(b), staged in shared memory
-            //   H[a, b] = sum_i sum_r S_a[r] P[6i+r, b] over bodies below joint(a) AND joint(b), in (i, r) order -
-            // the summation order of the reference's dense_gemm pair (kernels.py:1504-1538) minus its exact-zero terms, so
+            // H = J^T (M J), lower triangle only (all dense_cholesky reads).  Columns are processed in batches of equal
+            // (tree depth of their joint, dof index inside the joint): such joints are never ancestors of one another, so
+            // every body lies below at most one of them and one 6-vector per body holds P[:, b] = I_i S_b for the whole batch:
+            //   stage 1  P_i = I_i S_b           for the bodies below the batch's joints (one lane per body)
+            //   stage 2  H[a, b] = sum_i sum_r S_a[r] P_i[r] over the bodies below joint(a), in (i, r) order, a >= b
+            // - the summation order of the reference's dense_gemm pair (kernels.py:1504-1538) minus its exact-zero terms, so
             // the result is bit-identical while M J is formed once per column instead of once per entry.
+            int* jdof0 = reinterpret_cast<int*>(sm.fe);  // tables in the (now dead) external-force block: 3 ints per joint
+            int* jndof = jdof0 + anj;
+            int* jdepth = jndof + anj;
             for (int e = l; e < n * n; e += L) H[e] = 0.0f;
-            for (int i = l; i < anj; i += L) sm.anc[i] = M.joint_anc_mask[aj0 + i];
-            for (int i = l; i < n; i += L) {  // dof -> articulation-local joint
-                int ja = aj0;
-                while (d.joint_qd_start[ja + 1] - ad0 <= i) ++ja;
-                sm.dofj[ad0 - d0 + i] = ja - aj0;
+            int my_maxdep = 0;
+            for (int i = l; i < anj; i += L) {
+                sm.anc[i] = M.joint_anc_mask[aj0 + i];
+                jdof0[i] = d.joint_qd_start[aj0 + i] - ad0;
+                jndof[i] = d.joint_qd_start[aj0 + i + 1] - d.joint_qd_start[aj0 + i];
+                jdepth[i] = M.joint_depth[aj0 + i];
+                my_maxdep = max(my_maxdep, jdepth[i]);
+                for (int k = 0; k < jndof[i]; ++k) sm.dofj[ad0 - d0 + jdof0[i] + k] = i;
             }
+#pragma unroll
+            for (int o = L / 2; o > 0; o >>= 1) my_maxdep = max(my_maxdep, __shfl_xor_sync(gmask, my_maxdep, o, L));
             __syncwarp(gmask);
             // descendant-or-self sets (bit i = body i hangs below joint j): the bodies whose block of M J touches dof row a
             for (int j = l; j < anj; j += L) {
@@ -563,40 +612,54 @@ __global__ void __launch_bounds__(32, 14) featherstone_step_kernel(DevModel M, n
             }
             __syncwarp(gmask);
             const int* dofj = sm.dofj + (ad0 - d0);
-            for (int cbb = 0; cbb < n; ++cbb) {
-                const int jb = dofj[cbb];
-                const S6 Sb = ld6(sm.S + 6 * (ad0 - d0 + cbb));
-                for (int i = l; i < anj; i += L) {
-                    if (((sm.anc[i] >> jb) & 1ull) == 0ull) continue;
-                    // NB: the reference's spatial_mass indexes body_I_s by JOINT index (kernels.py:1476-1477)
-                    const float* Is = sm.Is + 36 * (aj0 + i - b0);
+            for (int dep = 0; dep <= my_maxdep; ++dep) {
+                for (int kk = 0; kk < 6; ++kk) {
+                    // does any joint of this depth own a dof number kk?  (uniform across the group: same tables)
+                    bool any = false;
+                    for (int j = 0; j < anj && !any; ++j) any = jdepth[j] == dep && jndof[j] > kk;
+                    if (!any) break;  // dof counts only shrink the batch: no joint with > kk dofs => none with > kk+1
+                    for (int i = l; i < anj; i += L) {  // stage 1
+                        if (jdepth[i] < dep) continue;
+                        int jb = -1;  // ancestor-or-self of body i at depth dep
+                        for (unsigned long long m = sm.anc[i]; m; m &= m - 1ull) {
+                            const int a = __ffsll((long long)m) - 1;
+                            if (jdepth[a] == dep) jb = a;
+                        }
+                        if (jb < 0 || jndof[jb] <= kk) continue;
+                        const S6 Sb = ld6(sm.S + 6 * (ad0 - d0 + jdof0[jb] + kk));
+                        // NB: the reference's spatial_mass indexes body_I_s by JOINT index (kernels.py:1476-1477)
+                        const float* Is = sm.Is + 36 * (aj0 + i - b0);
 #pragma unroll
-                    for (int r = 0; r < 6; ++r) {
-                        float pr = 0.0f;  // P[6i+r, b] = sum_k M[6i+r, 6i+k] J[6i+k, b]
+                        for (int r = 0; r < 6; ++r) {
+                            float pr = 0.0f;  // P[6i+r, b] = sum_k M[6i+r, 6i+k] J[6i+k, b]
 #pragma unroll
-                        for (int k = 0; k < 6; ++k) pr += Is[6 * r + k] * Sb.v[k];
-                        sm.P[6 * i + r] = pr;
+                            for (int k = 0; k < 6; ++k) pr += Is[6 * r + k] * Sb.v[k];
+                            sm.P[6 * i + r] = pr;
+                        }
                     }
-                }
-                __syncwarp(gmask);
-                for (int ra = cbb + l; ra < n; ra += L) {
-                    const int ja = dofj[ra];
-                    float sum = 0.0f;
-                    // rows come after columns in dof order, so joint(a) is never a proper ancestor of joint(b): the bodies below
-                    // both joints are desc(ja) when jb is an ancestor-or-self of ja, none otherwise
-                    if ((sm.anc[ja] >> jb) & 1ull) {
+                    __syncwarp(gmask);
+                    for (int ra = l; ra < n; ra += L) {  // stage 2
+                        const int ja = dofj[ra];
+                        if (jdepth[ja] < dep) continue;
+                        int jb = -1;
+                        for (unsigned long long m = sm.anc[ja]; m; m &= m - 1ull) {
+                            const int a = __ffsll((long long)m) - 1;
+                            if (jdepth[a] == dep) jb = a;
+                        }
+                        if (jb < 0 || jndof[jb] <= kk) continue;
+                        const int cbb = jdof0[jb] + kk;
+                        if (ra < cbb) continue;  // upper triangle (only possible inside joint(b) itself)
                         const S6 Sa = ld6(sm.S + 6 * (ad0 - d0 + ra));
-                        unsigned long long m = sm.desc[ja];
-                        while (m) {  // ascending body order = the reference's summation order
+                        float sum = 0.0f;
+                        for (unsigned long long m = sm.desc[ja]; m; m &= m - 1ull) {  // ascending body order
                             const int i = __ffsll((long long)m) - 1;
-                            m &= m - 1ull;
 #pragma unroll
                             for (int r = 0; r < 6; ++r) sum += Sa.v[r] * sm.P[6 * i + r];
                         }
+                        H[ra * n + cbb] = sum;
                     }
-                    H[ra * n + cbb] = sum;
+                    __syncwarp(gmask);
                 }
-                __syncwarp(gmask);
             }
             __syncwarp(gmask);
             // dense_cholesky (kernels.py:1690-1719), in place on the lower triangle; columns in order, rows in parallel
