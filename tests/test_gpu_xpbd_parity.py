@@ -287,3 +287,37 @@ print("ERR", rel_err(gs.body_q.cpu().numpy(), rs.body_q.numpy()), rel_err(gs.bod
     eq, eqd = [float(x) for x in out.stdout.strip().split("ERR")[1].split()]
     assert eq < TOL_STATE_REL
     assert eqd < 2e-3
+
+
+@pytest.mark.parametrize("solver_name", ["xpbd", "featherstone"])
+def test_full_size_batch_matches_single_env_oracle(oracle_lib, cuda_lib, solver_name):
+    """BASELINE.json's full batch (4096 quadruped envs on one GPU) through a size-independent property: environments never
+    interact, so 4096 copies of one environment must each reproduce, bit for bit, what the oracle computes for that single
+    environment - which checks grid sizing, slot offsets and indexing at scale at the cost of a 1-env oracle run."""
+    envs = 4096
+    if solver_name == "xpbd":
+        kw, dt, n, pkg_o, pkg_g = {"iterations": 8}, 0.005, 24, oracle_lib.SolverXPBD, newton_b200.solvers.SolverXPBD
+    else:
+        kw, dt, n, pkg_o, pkg_g = {}, 0.001, 40, oracle_lib.SolverFeatherstone, newton_b200.solvers.SolverFeatherstone
+    one = _drop(scenes.quadruped_model(1, seed=None), 1, 0.47)
+    ref, _, rc = simulate(one, oracle_lib.CollisionPipeline, pkg_o, substeps=n, dt=dt, solver_kwargs=kw, record_contacts=True)
+    big = _drop(scenes.quadruped_model(envs, seed=None), envs, 0.47).to("cuda:0")
+    out, _, gc = simulate(big, newton_b200.CollisionPipeline, pkg_g, substeps=n, dt=dt, solver_kwargs=kw, record_contacts=True)
+    assert gc == [c * envs for c in rc] and rc[-1] > 0
+    q = out.body_q.cpu().numpy().reshape(envs, -1, 7)
+    qd = out.body_qd.cpu().numpy().reshape(envs, -1, 6)
+    np.testing.assert_array_equal(q, np.broadcast_to(ref.body_q.numpy()[None], q.shape))
+    np.testing.assert_array_equal(qd, np.broadcast_to(ref.body_qd.numpy()[None], qd.shape))
+
+
+def test_full_size_box_stacks_match_single_env_oracle(oracle_lib, cuda_lib):
+    """Config 2 at its full size (512 stacks): every stack equals the oracle's single stack, 20 manifold contacts each."""
+    envs = 512
+    kw = {"iterations": 8}
+    ref, _, rc = simulate(scenes.box_stack_model(1, seed=None), oracle_lib.CollisionPipeline, oracle_lib.SolverXPBD, substeps=24,
+                          dt=1.0 / 240, solver_kwargs=kw, record_contacts=True)
+    out, _, gc = simulate(scenes.box_stack_model(envs, seed=None).to("cuda:0"), newton_b200.CollisionPipeline,
+                          newton_b200.solvers.SolverXPBD, substeps=24, dt=1.0 / 240, solver_kwargs=kw, record_contacts=True)
+    assert gc == [c * envs for c in rc] and rc[-1] == 20
+    q = out.body_q.cpu().numpy().reshape(envs, -1, 7)
+    np.testing.assert_array_equal(q, np.broadcast_to(ref.body_q.numpy()[None], q.shape))
