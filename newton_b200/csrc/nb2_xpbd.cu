@@ -432,8 +432,11 @@ NB2_HELPER void apply_delta(float* rec, V3 dlin, V3 dang, float inv_weight, bool
 // EX = false: the plain step.  EX = true adds the reporting / post-processing paths of row a17 (restitution, velocity from
 // position delta, weighted contact impulses for Contacts.force, joint impulses for State.body_parent_f); it is a second
 // instantiation so the plain step pays neither registers nor shared memory for them.
+#ifndef NB2_XPBD_MINBLOCKS
+#define NB2_XPBD_MINBLOCKS 16  // resident one-warp CTAs per SM the register allocation must allow (4096 envs need 13.8)
+#endif
 template <int L, bool EX>
-__global__ void __launch_bounds__(32, 16) xpbd_step_kernel(DevModel M, nb2_xpbd_params P, nb2_state_view sin, nb2_state_view sout,
+__global__ void __launch_bounds__(32, NB2_XPBD_MINBLOCKS) xpbd_step_kernel(DevModel M, nb2_xpbd_params P, nb2_state_view sin, nb2_state_view sout,
                                                         nb2_control_view ctl, int use_contacts_flags, float dt) {
     const int use_contacts = use_contacts_flags & NB2_XPBD_USE_CONTACTS;
     const bool want_cimp = EX && use_contacts && (use_contacts_flags & NB2_XPBD_CONTACT_IMPULSE);
