@@ -604,3 +604,157 @@ def test_example_basic_pendulum_final_state(oracle_lib, solver_name):
         assert abs(qd[b, 0]) < 1e-4
         assert abs(qd[b, 1]) < 10.0 and abs(qd[b, 2]) < 5.0 and abs(qd[b, 3]) < 10.0 and abs(qd[b, 4]) < 10.0
     assert np.abs(qd).max() > 0.1  # it is swinging
+
+
+# ---- more closed-form checks of newton/tests/test_physics_verification.py (both solvers where the reference runs both) ------------
+
+def _solver(oracle_lib, name, model):
+    if name == "featherstone":
+        return oracle_lib.SolverFeatherstone(model, angular_damping=0.0)
+    return oracle_lib.SolverXPBD(model, iterations=20, angular_damping=0.0)
+
+
+@pytest.mark.parametrize("solver_name", ["featherstone", "xpbd"])
+def test_projectile_motion(oracle_lib, solver_name):
+    """test_physics_verification.py:289-353: ballistic flight, position / velocity against the closed form at six instants."""
+    import newton_b200
+
+    g, p0, v0 = -10.0, np.array([0.0, 10.0, 0.0]), np.array([5.0, 10.0, 0.0])
+    b = ModelBuilder(up_axis="Y", gravity=g)
+    body = b.add_body(xform=X.transform(p0))
+    b.add_shape_sphere(body, radius=0.1)
+    model = b.finalize()
+    s0, s1 = model.state(), model.state()
+    if solver_name == "featherstone":
+        s0.joint_qd[:3] = torch_f32(v0)
+        newton_b200.eval_fk(model, s0.joint_q, s0.joint_qd, s0)
+    else:
+        s0.body_qd[0, :3] = torch_f32(v0)
+    solver = _solver(oracle_lib, solver_name, model)
+    dt = 1e-3
+    for i in range(1, 101):
+        s0.clear_forces()
+        solver.step(s0, s1, None, None, dt)
+        s0, s1 = s1, s0
+        if i in (10, 20, 30, 50, 70, 100):
+            t = i * dt
+            pos, vel = s0.body_q.numpy()[0, :3], s0.body_qd.numpy()[0, :3]
+            exp_p = p0 + v0 * t + np.array([0.0, 0.5 * g * t * t, 0.0])
+            exp_v = v0 + np.array([0.0, g * t, 0.0])
+            np.testing.assert_allclose(pos, exp_p, atol=max(2.0 * 0.5 * abs(g) * dt * t, 1e-3))
+            np.testing.assert_allclose(vel, exp_v, atol=max(abs(g) * dt, 1e-3))
+
+
+def torch_f32(a):
+    import torch
+
+    return torch.tensor(np.asarray(a), dtype=torch.float32)
+
+
+def test_joint_actuation_featherstone(oracle_lib):
+    """test_physics_verification.py:356-447: constant joint_f on a revolute / prismatic joint without gravity:
+    omega = tau t / I_zz and v = F t / m within one step's increment."""
+    import newton_b200
+    from newton_b200.sim.builder import JointDofConfig  # noqa: F401
+
+    b = ModelBuilder(up_axis="Y", gravity=0.0)
+    link_rev = b.add_link()
+    b.add_shape_box(link_rev, hx=0.2, hy=0.2, hz=0.2)
+    j_rev = b.add_joint_revolute(parent=-1, child=link_rev, axis=(0.0, 0.0, 1.0), armature=0.0)
+    b.add_articulation([j_rev])
+    link_pri = b.add_link()
+    b.add_shape_sphere(link_pri, radius=0.1)
+    j_pri = b.add_joint_prismatic(parent=-1, child=link_pri, axis=(1.0, 0.0, 0.0), parent_xform=X.transform((0.0, 5.0, 0.0)), armature=0.0)
+    b.add_articulation([j_pri])
+    model = b.finalize()
+    newton_b200.eval_fk(model, model.joint_q, model.joint_qd, model)
+    I_zz = float(model.body_inertia[0, 2, 2])
+    mass = float(model.body_mass[1])
+    solver = oracle_lib.SolverFeatherstone(model, angular_damping=0.0)
+    s0, s1, ctl = model.state(), model.state(), model.control()
+    qd_start = model.joint_qd_start.numpy()
+    ctl.joint_f[qd_start[0]] = 5.0
+    ctl.joint_f[qd_start[1]] = 5.0
+    dt, n = 1e-3, 300
+    for _ in range(n):
+        s0.clear_forces()
+        solver.step(s0, s1, ctl, None, dt)
+        s0, s1 = s1, s0
+    t = n * dt
+    assert float(s0.joint_qd[qd_start[0]]) == pytest.approx(5.0 * t / I_zz, abs=max(5.0 / I_zz * dt, 1e-3))
+    assert float(s0.joint_qd[qd_start[1]]) == pytest.approx(5.0 * t / mass, abs=max(5.0 / mass * dt, 1e-3))
+
+
+@pytest.mark.parametrize("solver_name", ["featherstone", "xpbd"])
+def test_momentum_conservation(oracle_lib, solver_name):
+    """test_physics_verification.py:450-537: four free boxes without gravity keep linear and angular momentum (drift < 5e-4)."""
+    import newton_b200
+
+    positions = [(0.0, 0.0, 0.0), (100.0, 0.0, 0.0), (0.0, 100.0, 0.0), (0.0, 0.0, 100.0)]
+    velocities = np.array([(1.0, 0.0, 0.0, 0.0, 0.0, 0.5), (0.0, -1.0, 0.0, 0.3, 0.0, 0.0), (0.0, 0.0, 1.5, 0.0, -0.2, 0.0),
+                           (-0.5, 0.5, -0.5, 0.0, 0.0, -0.3)], dtype=np.float32)
+    b = ModelBuilder(up_axis="Y", gravity=0.0)
+    for p in positions:
+        body = b.add_body(xform=X.transform(p))
+        b.add_shape_box(body, hx=0.5, hy=0.5, hz=0.5)
+    model = b.finalize()
+    s0, s1 = model.state(), model.state()
+    if solver_name == "featherstone":
+        s0.joint_qd.copy_(torch_f32(velocities.reshape(-1)))
+        newton_b200.eval_fk(model, s0.joint_q, s0.joint_qd, s0)
+    else:
+        s0.body_qd.copy_(torch_f32(velocities))
+    masses, inertias = model.body_mass.numpy(), model.body_inertia.numpy()
+
+    def momenta(state):
+        q, qd = state.body_q.numpy().astype(np.float64), state.body_qd.numpy().astype(np.float64)
+        p, L = np.zeros(3), np.zeros(3)
+        for i in range(4):
+            R = X.quat_to_matrix(q[i, 3:])
+            p += masses[i] * qd[i, :3]
+            L += np.cross(q[i, :3], masses[i] * qd[i, :3]) + (R @ inertias[i] @ R.T) @ qd[i, 3:]
+        return p, L
+
+    p0, L0 = momenta(s0)
+    assert np.linalg.norm(p0) > 0.1 and np.linalg.norm(L0) > 0.1
+    solver = _solver(oracle_lib, solver_name, model)
+    for _ in range(1000):
+        s0.clear_forces()
+        solver.step(s0, s1, None, None, 1e-3)
+        s0, s1 = s1, s0
+    p1, L1 = momenta(s0)
+    assert np.linalg.norm(p1 - p0) / np.linalg.norm(p0) < 5e-4
+    assert np.linalg.norm(L1 - L0) / np.linalg.norm(L0) < 5e-4
+    assert np.linalg.norm(s0.body_q.numpy()[:, :3] - np.array(positions)) > 0.1
+
+
+def test_torque_free_precession_featherstone(oracle_lib):
+    """test_physics_verification.py:540-603: anisotropic body on a 3-angular-axis D6 joint, no torque: world angular
+    momentum drifts < 5e-3 over 20 steps of 10 ms while the body precesses."""
+    import newton_b200
+    from newton_b200.sim.builder import JointDofConfig
+
+    b = ModelBuilder(gravity=0.0)
+    link = b.add_link(mass=1.0, com=(0.0, 0.0, 0.0), inertia=np.diag([0.2, 0.5, 0.4]))
+    j = b.add_joint_d6(parent=-1, child=link, angular_axes=[JointDofConfig.create_unlimited(a) for a in "xyz"])
+    b.add_articulation([j])
+    model = b.finalize()
+    s0, s1 = model.state(), model.state()
+    s0.joint_qd[:3] = torch_f32([0.7, -0.5, 0.9])
+    newton_b200.eval_fk(model, s0.joint_q, s0.joint_qd, s0)
+    I_body = model.body_inertia.numpy()[0].astype(np.float64)
+
+    def L_world(state):
+        q = state.body_q.numpy()[0].astype(np.float64)
+        R = X.quat_to_matrix(q[3:])
+        return (R @ I_body @ R.T) @ state.body_qd.numpy()[0, 3:].astype(np.float64)
+
+    L0, quat0 = L_world(s0), s0.body_q.numpy()[0, 3:].copy()
+    assert np.linalg.norm(L0) > 0.1
+    solver = oracle_lib.SolverFeatherstone(model, angular_damping=0.0)
+    for _ in range(20):
+        s0.clear_forces()
+        solver.step(s0, s1, None, None, 1e-2)
+        s0, s1 = s1, s0
+    assert np.linalg.norm(L_world(s0) - L0) / np.linalg.norm(L0) < 5e-3
+    assert 2.0 * math.acos(min(abs(float(np.dot(quat0, s0.body_q.numpy()[0, 3:]))), 1.0)) > 0.1
