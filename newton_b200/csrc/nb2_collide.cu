@@ -516,13 +516,40 @@ __global__ void __launch_bounds__(1024) contact_scan_kernel(const int* __restric
     }
 }
 
+// SELF_SCAN (batches up to 8192 environments): one pass - every CTA (4 environments, one warp each) first sums the contact
+// counts of all environments before its own (E/128 coalesced int loads per thread out of L2; exact integer arithmetic, so
+// the offsets equal the scan's) and then scatters its environments' contact blocks; this saves the single-CTA scan launch
+// (6 us of a 40 us collide stage at 4096 envs).  The sum is O(E^2 / 128) over the grid, so larger batches keep the
+// separate contact_scan_kernel and read its offsets.
+template <bool SELF_SCAN>
 __global__ void __launch_bounds__(128) contact_export_kernel(DevModel M, nb2_contacts_view out) {
-    const int env = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    __shared__ int warp_part[4];
+    const int env0 = blockIdx.x * 4;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int env = env0 + wid;
+    int dst0;
+    if (SELF_SCAN) {
+        int part = 0;
+        for (int i = threadIdx.x; i < env0; i += 128) part += M.env_contact_count[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) warp_part[wid] = part;
+        __syncthreads();
+        dst0 = warp_part[0] + warp_part[1] + warp_part[2] + warp_part[3];
+        for (int e = env0; e < env && e < M.env_count; ++e) dst0 += M.env_contact_count[e];
+    } else {
+        dst0 = env < M.env_count ? M.env_contact_offset[env] : 0;
+    }
     if (env >= M.env_count) return;
-    const int lane = threadIdx.x & 31;
     const int n = M.env_contact_count[env];
+    if (SELF_SCAN && lane == 0) {
+        M.env_contact_offset[env] = dst0;
+        if (env == M.env_count - 1) {
+            M.env_contact_offset[M.env_count] = dst0 + n;
+            out.rigid_contact_count[0] = dst0 + n;
+        }
+    }
     const int src0 = M.env_slot_start[env];
-    const int dst0 = M.env_contact_offset[env];
     const size_t T = size_t(M.slot_total);
     const float* cb = M.cb;
     for (int c = lane; c < n; c += 32) {
@@ -578,9 +605,14 @@ nb2_status launch_collide(nb2_model* m, const float* body_q, const nb2_contacts_
             set_error("nb2_collide: contacts view has NULL arrays");
             return NB2_ERR_INVALID_ARGUMENT;
         }
-        contact_scan_kernel<<<1, 1024, 0, s>>>(M.env_contact_count, M.env_count, M.env_contact_offset, contacts->rigid_contact_count);
-        contact_export_kernel<<<(M.env_count + 3) / 4, 128, 0, s>>>(M, *contacts);
-        count_launch(2);
+        if (M.env_count <= 8192) {
+            contact_export_kernel<true><<<(M.env_count + 3) / 4, 128, 0, s>>>(M, *contacts);
+            count_launch();
+        } else {
+            contact_scan_kernel<<<1, 1024, 0, s>>>(M.env_contact_count, M.env_count, M.env_contact_offset, contacts->rigid_contact_count);
+            contact_export_kernel<false><<<(M.env_count + 3) / 4, 128, 0, s>>>(M, *contacts);
+            count_launch(2);
+        }
         NB2_CUDA_CHECK(cudaGetLastError());
     }
     return NB2_OK;
