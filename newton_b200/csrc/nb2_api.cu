@@ -136,6 +136,13 @@ static nb2_status build_tables(nb2_model* m, const nb2_model_desc& d) {
             }
             // plane vs barrel cylinder can fall through to the generic convex path, which needs the reference's
             // infinite-plane -> cube conversion (collision_core.py:752-766): not built
+            {   // narrow_phase.py:642-655 + the analytic chain of narrow_phase.py:657-864: everything else is MPR / GJK
+                const bool early = ta >= 5 || (ta == 4 && tb > 4);
+                const bool analytic = !early && ((ta == 1 && (tb == 3 || tb == 4 || tb == 5 || tb == 6 || tb == 7)) ||
+                                                 (ta == 3 && (tb == 3 || tb == 4 || tb == 7 || (tb == 6 && shape_scale[3 * sb + 2] == 0.0f))) ||
+                                                 (ta == 4 && tb == 4));
+                if (!analytic && ta != 1) m->has_convex_pairs = true;
+            }
             if (ta == 1 && tb == 6 && shape_scale[3 * sb + 2] != 0.0f) {
                 set_error("plane vs barrel cylinder (shape_scale.z != 0) is not supported");
                 return NB2_ERR_UNSUPPORTED;

@@ -277,7 +277,9 @@ struct __align__(4) SlotRec {
     float hi[3];
 };
 
-template <int L>
+// CONVEX = false is instantiated for models none of whose pairs can reach the generic convex path (decided per pair type at
+// nb2_model_create): the analytic-only kernel carries neither the MPR / GJK / manifold code nor its registers and stack.
+template <int L, bool CONVEX>
 __global__ void __launch_bounds__(32) collide_kernel(DevModel M, const float* __restrict__ body_q) {
     constexpr int G = 32 / L;  // environments per warp
     extern __shared__ unsigned char smem_raw[];
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(32) collide_kernel(DevModel M, const float* __
                             if (dd <= gap_sum) vmask |= 1u << i;
                         }
                     }
-                } else {
+                } else if (CONVEX) {
                     ConvexShape A{ta, sca, Xa, marg_a, d.shape_gap[sa]};
                     ConvexShape Bc{tb, scb, Xb, marg_b, d.shape_gap[sb]};
                     vmask = convex_pair_contacts(A, Bc, cdist, cpos, cnorm, reff_a, reff_b);
@@ -571,7 +573,7 @@ __global__ void __launch_bounds__(128) contact_export_kernel(DevModel M, nb2_con
     }
 }
 
-template <int L>
+template <int L, bool CONVEX>
 static nb2_status launch_collide_L(nb2_model* m, const float* body_q, cudaStream_t s) {
     const DevModel& M = m->dev;
     const int G = 32 / L;
@@ -582,8 +584,8 @@ static nb2_status launch_collide_L(nb2_model* m, const float* body_q, cudaStream
         return NB2_ERR_CAPACITY;
     }
     if (smem > 48 * 1024)
-        NB2_CUDA_CHECK(cudaFuncSetAttribute(collide_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    collide_kernel<L><<<blocks, 32, smem, s>>>(M, body_q);
+        NB2_CUDA_CHECK(cudaFuncSetAttribute(collide_kernel<L, CONVEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    collide_kernel<L, CONVEX><<<blocks, 32, smem, s>>>(M, body_q);
     count_launch();
     NB2_CUDA_CHECK(cudaGetLastError());
     return NB2_OK;
@@ -593,11 +595,14 @@ nb2_status launch_collide(nb2_model* m, const float* body_q, const nb2_contacts_
     const DevModel& M = m->dev;
     if (M.env_count == 0 || M.d.shape_count == 0) return NB2_OK;
     nb2_status st;
+#define NB2_COLLIDE_DISPATCH(LANES) \
+    st = m->has_convex_pairs ? launch_collide_L<LANES, true>(m, body_q, s) : launch_collide_L<LANES, false>(m, body_q, s)
     switch (m->lanes_per_env) {
-        case 8: st = launch_collide_L<8>(m, body_q, s); break;
-        case 16: st = launch_collide_L<16>(m, body_q, s); break;
-        default: st = launch_collide_L<32>(m, body_q, s); break;
+        case 8: NB2_COLLIDE_DISPATCH(8); break;
+        case 16: NB2_COLLIDE_DISPATCH(16); break;
+        default: NB2_COLLIDE_DISPATCH(32); break;
     }
+#undef NB2_COLLIDE_DISPATCH
     if (st != NB2_OK) return st;
     if (contacts) {
         if (!contacts->rigid_contact_count || !contacts->shape0 || !contacts->shape1 || !contacts->point0 || !contacts->point1 ||

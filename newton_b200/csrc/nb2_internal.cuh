@@ -81,6 +81,7 @@ struct nb2_model {
     std::vector<void*> allocations;
     int lanes_per_env = 32;  // sub-warp group width used by the fused kernels
     int featherstone_step_count = 0;
+    bool has_convex_pairs = false;  // some pair's types have no analytic collider -> collide_kernel<L, true>
     float xpbd_impulse_dt = 0.0f;  // dt of the last nb2_xpbd_step that accumulated contact impulses (0 = none yet)
 };
 
