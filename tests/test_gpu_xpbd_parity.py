@@ -321,3 +321,13 @@ def test_full_size_box_stacks_match_single_env_oracle(oracle_lib, cuda_lib):
     assert gc == [c * envs for c in rc] and rc[-1] == 20
     q = out.body_q.cpu().numpy().reshape(envs, -1, 7)
     np.testing.assert_array_equal(q, np.broadcast_to(ref.body_q.numpy()[None], q.shape))
+
+
+def test_ramp_scene_bit_exact(oracle_lib, cuda_lib):
+    """The reference's GJK/MPR multi-contact ramp scene (test_rigid_contact.py:236-432; see tests/test_oracle_known_answers.py):
+    dynamic cubes / capsule / cylinder against static box walls and a tilted plane, implicit single world."""
+    from tests.test_oracle_known_answers import _ramp_scene
+
+    model, _ = _ramp_scene()
+    out = _both(model, 200, 1.0 / 600, {"iterations": 2}, oracle_lib)
+    _assert_exact(*out, model)

@@ -758,3 +758,68 @@ def test_torque_free_precession_featherstone(oracle_lib):
         s0, s1 = s1, s0
     assert np.linalg.norm(L_world(s0) - L0) / np.linalg.norm(L0) < 5e-3
     assert 2.0 * math.acos(min(abs(float(np.dot(quat0, s0.body_q.numpy()[0, 3:]))), 1.0)) > 0.1
+
+
+def _ramp_scene():
+    """Scene of newton/tests/test_rigid_contact.py:236-432 (objects resting on a 30-degree ramp against an end wall), minus
+    the two cones and the two convex-hull cubes (shape types outside this library's scope; they sit furthest up the ramp)."""
+    L, TH, ANG, WALL_H, CUBE = 10.0, 0.5, math.radians(30.0), 2.0, 0.99
+    W = CUBE * 2.01
+    b = ModelBuilder()
+    b.default_shape_cfg.ke, b.default_shape_cfg.kd, b.default_shape_cfg.kf = 2e4, 500.0, 0.5
+    centre = np.array([0.0, L / 2 * math.cos(ANG), L / 2 * math.sin(ANG)])
+    rq = X.quat_from_axis_angle((1.0, 0.0, 0.0), ANG)
+    b.add_shape_plane(body=-1, xform=X.transform(centre, rq), width=0.0, length=0.0)
+    fwd, up, right = (X.quat_rotate(rq, np.array(v)) for v in ((0.0, -1.0, 0.0), (0.0, 0.0, 1.0), (1.0, 0.0, 0.0)))
+    gh, gt = 0.3, 0.1
+    for sgn in (1.0, -1.0):
+        c = centre + sgn * (W / 2 + gt / 2) * right + (gh / 2) * up
+        b.add_shape_box(-1, xform=X.transform(c, rq), hx=gt / 2, hy=L / 2, hz=gh / 2)
+    shift = 0.6 * L
+    tmp = centre + 0.5 * CUBE * (up + shift * fwd)
+    b.add_shape_box(-1, xform=X.transform((0.0, tmp[1] - CUBE / 2 * 1.4 - TH / 2, tmp[2])), hx=W / 2, hy=TH / 2, hz=WALL_H / 2)
+
+    def at(side, k):
+        return centre + 0.5 * CUBE * (up + side * right + (shift - k) * fwd)
+
+    for side in (1.0, -1.0):
+        body = b.add_body(xform=X.transform(at(side, 0.0), rq))
+        b.add_shape_box(body, hx=CUBE / 2, hy=CUBE / 2, hz=CUBE / 2)
+    for side in (1.0, -1.0):
+        body = b.add_body(xform=X.transform(at(side, 2.01), rq))
+        b.add_shape_sphere(body, radius=CUBE / 2)
+    z_to_x = X.quat_between_vectors((0.0, 0.0, 1.0), (1.0, 0.0, 0.0))
+    lying = X.quat_mul(rq, z_to_x)
+    body = b.add_body(xform=X.transform(at(0.0, 4.02), lying))
+    b.add_shape_capsule(body, radius=CUBE / 2, half_height=CUBE / 2)
+    body = b.add_body(xform=X.transform(at(0.0, 6.03), lying))
+    b.add_shape_cylinder(body, radius=CUBE / 2, half_height=CUBE)
+    for side in (1.0, -1.0):
+        body = b.add_body(xform=X.transform(at(side, 8.04), rq))
+        b.add_shape_box(body, hx=CUBE / 2, hy=CUBE / 2, hz=CUBE / 2)
+    b.add_ground_plane()
+    return b.finalize(), CUBE
+
+
+def test_shapes_on_ramp_multicontact_stay_put(oracle_lib):
+    """test_rigid_contact.py:236-510 (test_shape_collisions_gjk_mpr_multicontact): with correct MPR / GJK manifolds - cube
+    vs static box walls, capsule / cylinder vs cube, the axial rolling post-process - nothing on the ramp moves more than
+    0.15 cube sizes or turns more than 10 degrees in 100 frames x 10 substeps of SolverXPBD(iterations=2)."""
+    model, cube = _ramp_scene()
+    solver = oracle_lib.SolverXPBD(model, iterations=2)
+    pipe = oracle_lib.CollisionPipeline(model)
+    contacts = pipe.contacts()
+    s0, s1, ctl = model.state(), model.state(), model.control()
+    q_init = s0.body_q.numpy().copy()
+    dt = 1.0 / 60.0 / 10
+    for _ in range(100 * 10):
+        s0.clear_forces()
+        pipe.collide(s0, contacts)
+        solver.step(s0, s1, ctl, contacts, dt)
+        s0, s1 = s1, s0
+    q = s0.body_q.numpy()
+    for i in range(model.body_count):
+        disp = np.linalg.norm(q[i, :3] - q_init[i, :3])
+        ang = 2.0 * math.acos(min(abs(float(np.dot(q[i, 3:], q_init[i, 3:]))), 1.0))
+        assert disp < 0.15 * cube, f"body {i} moved {disp:.4f}"
+        assert ang < math.radians(10.0), f"body {i} turned {math.degrees(ang):.2f} deg"
