@@ -331,3 +331,17 @@ def test_ramp_scene_bit_exact(oracle_lib, cuda_lib):
     model, _ = _ramp_scene()
     out = _both(model, 200, 1.0 / 600, {"iterations": 2}, oracle_lib)
     _assert_exact(*out, model)
+
+
+@pytest.mark.parametrize("solver_name", ["xpbd", "featherstone"])
+def test_run_to_run_determinism(cuda_lib, solver_name):
+    """newton/tests/determinism/test_solver_determinism.py:205-229: two runs from the same state are bit-equal (ordered sums
+    instead of float atomics make this hold by construction, on any batch size)."""
+    cls = newton_b200.solvers.SolverXPBD if solver_name == "xpbd" else newton_b200.solvers.SolverFeatherstone
+    kw = {"iterations": 4} if solver_name == "xpbd" else {}
+    model = _drop(scenes.quadruped_model(257, seed=4), 257, 0.47).to("cuda:0")
+    runs = [simulate(model, newton_b200.CollisionPipeline, cls, substeps=30, dt=0.002, solver_kwargs=kw, record_contacts=True)
+            for _ in range(2)]
+    assert runs[0][2] == runs[1][2]
+    for name in ("body_q", "body_qd"):
+        assert torch.equal(getattr(runs[0][0], name), getattr(runs[1][0], name)), name

@@ -823,3 +823,50 @@ def test_shapes_on_ramp_multicontact_stay_put(oracle_lib):
         ang = 2.0 * math.acos(min(abs(float(np.dot(q[i, 3:], q_init[i, 3:]))), 1.0))
         assert disp < 0.15 * cube, f"body {i} moved {disp:.4f}"
         assert ang < math.radians(10.0), f"body {i} turned {math.degrees(ang):.2f} deg"
+
+
+@pytest.mark.parametrize("solver_name", ["xpbd", "featherstone"])
+def test_shapes_dropped_on_plane_come_to_rest(oracle_lib, solver_name):
+    """newton/tests/test_rigid_contact.py:28-235 (test_shapes_on_plane), primitive shapes only (the triangle mesh is out of
+    scope): spheres, lying capsules, boxes and upright cylinders of two sizes dropped from 0.5 m come to rest on the plane
+    at their resting heights, upright, |v| and |w| < 0.2 - for SolverXPBD and for SolverFeatherstone (penalty contacts,
+    angular_damping 0.15, friction_smoothing 2.0), 120 frames x 30 substeps."""
+    b = ModelBuilder()
+    cfg = b.default_shape_cfg
+    cfg.ke, cfg.kd, cfg.kf, cfg.gap = 1e4, 1000.0, 0.0, 0.1
+    expected = []
+    z_to_y = X.quat_between_vectors((0.0, 0.0, 1.0), (0.0, 1.0, 0.0))
+    for i, s in enumerate((0.5, 1.0)):
+        y = 1.5 * i
+        body = b.add_body(xform=X.transform((0.0, y, 0.5)))
+        b.add_shape_sphere(body, radius=0.1 * s)
+        expected.append((0.0, y, 0.1 * s))
+        body = b.add_body(xform=X.transform((2.0, y, 0.5)))
+        b.add_shape_capsule(body, xform=X.transform((0.0, 0.0, 0.0), z_to_y), radius=0.1 * s, half_height=0.3 * s)
+        expected.append((2.0, y, 0.1 * s))
+        body = b.add_body(xform=X.transform((4.0, y, 0.5)))
+        b.add_shape_box(body, hx=0.2 * s, hy=0.25 * s, hz=0.3 * s)
+        expected.append((4.0, y, 0.3 * s))
+        body = b.add_body(xform=X.transform((5.0, y, 0.5)))
+        b.add_shape_cylinder(body, radius=0.1 * s, half_height=0.3 * s)
+        expected.append((5.0, y, 0.3 * s))
+    b.add_ground_plane()
+    model = b.finalize()
+    if solver_name == "featherstone":
+        solver = oracle_lib.SolverFeatherstone(model, angular_damping=0.15, friction_smoothing=2.0)
+    else:
+        solver = oracle_lib.SolverXPBD(model)
+    pipe = oracle_lib.CollisionPipeline(model)
+    contacts = pipe.contacts()
+    s0, s1, ctl = model.state(), model.state(), model.control()
+    dt = 1.0 / 60.0 / 30
+    for _ in range(120 * 30):
+        s0.clear_forces()
+        pipe.collide(s0, contacts)
+        solver.step(s0, s1, ctl, contacts, dt)
+        s0, s1 = s1, s0
+    q, qd = s0.body_q.numpy(), s0.body_qd.numpy()
+    assert np.isfinite(q).all() and np.isfinite(qd).all()
+    assert np.abs(qd[:, :3]).max() < 0.2 and np.abs(qd[:, 3:]).max() < 0.2
+    np.testing.assert_allclose(q[:, :3], np.array(expected), atol=0.25)
+    np.testing.assert_allclose(q[:, 3:], np.tile([0.0, 0.0, 0.0, 1.0], (model.body_count, 1)), atol=1e-1)
