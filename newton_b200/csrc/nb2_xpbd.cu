@@ -15,6 +15,8 @@
 //     solve_body_joints             kernels.py:1513-2044  joint lanes -> smem delta records
 //     apply_body_deltas             kernels.py:864-933    body lanes, ordered sum over the body's joints (CSR)
 //   copy_kinematic_body_state      kernels.py:19-32       implicit: kinematic bodies are never modified
+#include <cstdlib>
+
 #include "nb2_internal.cuh"
 #include "nb2_math.cuh"
 
@@ -166,14 +168,26 @@ struct Deltas {
 };
 
 // solve_body_joints for one joint (kernels.py:1513-2044).  `bodies` = this env's shared-memory records.
+// Per-joint quantities that do not change over the Jacobi iterations, staged once per substep in shared memory when it
+// fits next to the body records without costing a resident CTA: the two joint frames and the angular AxisSetup.
+enum { JC_XP = 0, JC_XC = 7, JC_ANG = 14, JC_SIZE = 33 };  // odd stride: consecutive joints (lanes) hit different banks
+NB2_DEV void store_axis_setup(float* p, const AxisSetup& s) {
+    st3(p, s.lim_lo); st3(p + 3, s.lim_up); st3(p + 6, s.target_pos); st3(p + 9, s.stiffness); st3(p + 12, s.target_vel); st3(p + 15, s.damping);
+}
+NB2_DEV AxisSetup load_axis_setup(const float* p) {
+    AxisSetup s;
+    s.lim_lo = ld3(p); s.lim_up = ld3(p + 3); s.target_pos = ld3(p + 6); s.stiffness = ld3(p + 9); s.target_vel = ld3(p + 12); s.damping = ld3(p + 15);
+    return s;
+}
+
 NB2_DEV bool solve_joint(const nb2_model_desc& d, const nb2_control_view& ctl, const nb2_xpbd_params& P, int j, int body0,
-                         const float* bodies, float dt, Deltas& out) {
+                         const float* bodies, const float* jc, float dt, Deltas& out) {
     const int type = d.joint_type[j];
     if (!d.joint_enabled[j] || type == JT_FREE) return false;
     const int id_c = d.joint_child[j] - body0;
     const int id_p_raw = d.joint_parent[j];
     const int id_p = id_p_raw >= 0 ? id_p_raw - body0 : -1;
-    const Xf X_pj = ldx(d.joint_X_p + 7 * j), X_cj = ldx(d.joint_X_c + 7 * j);
+    const Xf X_pj = jc ? ldx(jc + JC_XP) : ldx(d.joint_X_p + 7 * j), X_cj = jc ? ldx(jc + JC_XC) : ldx(d.joint_X_c + 7 * j);
     BodyView bp = static_body();
     Xf X_wp = X_pj;
     Xf pose_p = X_pj;
@@ -299,7 +313,7 @@ NB2_DEV bool solve_joint(const nb2_model_desc& d, const nb2_control_view& ctl, c
             g1 = qscale(g1, scale);
             g2 = qscale(g2, scale);
         }
-        const AxisSetup s = gather_axes(d, ctl, axis_start, target_start, lin_count, ang_count);
+        const AxisSetup s = jc ? load_axis_setup(jc + JC_ANG) : gather_axes(d, ctl, axis_start, target_start, lin_count, ang_count);
         const Q4 qc_inv = qconj(q_c);
         NB2_ROW_UNROLL
         for (int dim = 0; dim < 3; ++dim) {
@@ -437,7 +451,7 @@ NB2_HELPER void apply_delta(float* rec, V3 dlin, V3 dang, float inv_weight, bool
 #endif
 template <int L, bool EX>
 __global__ void __launch_bounds__(32, NB2_XPBD_MINBLOCKS) xpbd_step_kernel(DevModel M, nb2_xpbd_params P, nb2_state_view sin, nb2_state_view sout,
-                                                        nb2_control_view ctl, int use_contacts_flags, float dt) {
+                                                        nb2_control_view ctl, int use_contacts_flags, float dt, int joint_cache_floats) {
     const int use_contacts = use_contacts_flags & NB2_XPBD_USE_CONTACTS;
     const bool want_cimp = EX && use_contacts && (use_contacts_flags & NB2_XPBD_CONTACT_IMPULSE);
     const bool want_jimp = EX && sout.body_parent_f != nullptr;
@@ -456,6 +470,8 @@ __global__ void __launch_bounds__(32, NB2_XPBD_MINBLOCKS) xpbd_step_kernel(DevMo
     int* cpair = reinterpret_cast<int*>(drec + rec_cap * DR_SIZE);
     float* init_qd = reinterpret_cast<float*>(cpair + M.max_env_contact_slots);  // EX only: state_in poses + twists (13/body)
     float* bcnt = init_qd + M.max_env_bodies * 13;                                 // EX only: active contacts per body
+    // joint cache: the launch passes a non-zero stride only when the block still fits 14-16 CTAs per SM
+    float* jcache = joint_cache_floats ? smem + size_t(G) * per_env + size_t(grp) * joint_cache_floats : nullptr;
 
     int b0 = 0, nb = 0, j0 = 0, nj = 0, slot0 = 0, nc = 0;
     if (live) {
@@ -497,6 +513,15 @@ __global__ void __launch_bounds__(32, NB2_XPBD_MINBLOCKS) xpbd_step_kernel(DevMo
             for (int k = 0; k < 6; ++k) M.contact_impulse[k * T + slot0 + c] = 0.0f;
     }
     __syncwarp();
+    if (jcache)
+        for (int j = l; j < nj; j += L) {
+            const int gj = j0 + j;
+            float* jc = jcache + j * JC_SIZE;
+            stx(jc + JC_XP, ldx(d.joint_X_p + 7 * gj));
+            stx(jc + JC_XC, ldx(d.joint_X_c + 7 * gj));
+            store_axis_setup(jc + JC_ANG, gather_axes(d, ctl, d.joint_qd_start[gj], d.joint_target_q_start[gj], d.joint_dof_dim[2 * gj],
+                                                      d.joint_dof_dim[2 * gj + 1]));
+        }
     // ---- apply_joint_forces: per-joint wrenches, then ordered per-body accumulation into a body_f copy ----
     for (int j = l; j < nj; j += L) {
         Deltas w;
@@ -682,7 +707,7 @@ __global__ void __launch_bounds__(32, NB2_XPBD_MINBLOCKS) xpbd_step_kernel(DevMo
             // ---- [iteration] solve_body_joints (kernels.py:1513-2044) + ordered per-body apply
             for (int j = l; j < nj; j += L) {
                 Deltas dl;
-                bool act = solve_joint(d, ctl, P, j0 + j, b0, bodies, dt, dl);
+                bool act = solve_joint(d, ctl, P, j0 + j, b0, bodies, jcache ? jcache + j * JC_SIZE : nullptr, dt, dl);
                 if (!act) dl = Deltas();
                 store_deltas(drec + j * DR_SIZE, dl, act ? 1.0f : 0.0f);
                 if (want_jimp && act) {  // kernels.py:2043-2044
@@ -900,17 +925,28 @@ static nb2_status launch_xpbd_L(nb2_model* m, const nb2_xpbd_params& p, const nb
     const int rec_cap = std::max(M.max_env_contact_slots, M.max_env_joints);
     const size_t per_env = size_t(M.max_env_bodies) * BR_SIZE + size_t(rec_cap) * DR_SIZE + size_t(M.max_env_contact_slots) +
                            (EX ? size_t(M.max_env_bodies) * 14 : 0);
-    const size_t smem = per_env * G * sizeof(float);
+    size_t smem = per_env * G * sizeof(float);
     if (smem > 220 * 1024 || M.max_env_bodies > 32000) {
         set_error("xpbd_step: environment too large for the fused shared-memory kernel (bodies/contacts per env)");
         return NB2_ERR_CAPACITY;
     }
+    // per-joint invariants (32 floats / joint) ride along when the block stays within a 14-CTA/SM share of shared memory
+    // (227 KB / 14 minus the 1 KB per-CTA reservation): residency - one wave for 4096 quadruped envs - is worth more
+    int joint_cache_floats = 0;
+    {
+        const size_t cache = size_t(M.max_env_joints) * JC_SIZE;
+        static const bool enabled = std::getenv("NB2_XPBD_NO_JOINT_CACHE") == nullptr;  // A/B switch (profiles/r1f_xpbd_ab.txt)
+        if (enabled && M.d.joint_count > 0 && smem + cache * G * sizeof(float) <= 15 * 1024) {
+            joint_cache_floats = int(cache);
+            smem += cache * G * sizeof(float);
+        }
+    }
     if (smem > 48 * 1024)
         NB2_CUDA_CHECK(cudaFuncSetAttribute(xpbd_step_kernel<L, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     // one-warp CTAs: ask for the largest shared-memory carve-out so ~16 CTAs (one wave of 4096 envs on 148 SMs) fit per SM
-    NB2_CUDA_CHECK(cudaFuncSetAttribute(xpbd_step_kernel<L, EX>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                        cudaSharedmemCarveoutMaxShared));
-    xpbd_step_kernel<L, EX><<<blocks, 32, smem, s>>>(M, p, in, out, ctl, use_contacts, dt);
+    static const int carveout = std::getenv("NB2_XPBD_CARVEOUT") ? std::atoi(std::getenv("NB2_XPBD_CARVEOUT")) : int(cudaSharedmemCarveoutMaxShared);
+    NB2_CUDA_CHECK(cudaFuncSetAttribute(xpbd_step_kernel<L, EX>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
+    xpbd_step_kernel<L, EX><<<blocks, 32, smem, s>>>(M, p, in, out, ctl, use_contacts, dt, joint_cache_floats);
     count_launch();
     NB2_CUDA_CHECK(cudaGetLastError());
     return NB2_OK;
