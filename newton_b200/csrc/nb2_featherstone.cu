@@ -982,13 +982,8 @@ nb2_status launch_eval_fk(nb2_model* m, const float* joint_q, const float* joint
 }
 
 // ---- public newton.eval_ik (sim/articulation.py:640-932 eval_articulation_ik): one thread per joint -----------------------------
-NB2_DEV float twist_angle_signed(V3 axis, Q4 q) {  // wp.quat_twist_angle_signed, see oracle_featherstone.h
-    float proj = dot(V3(q.x, q.y, q.z), axis), w = q.w;
-    if (w < 0.0f) {
-        proj = -proj;
-        w = -w;
-    }
-    return 2.0f * atan2_w(proj, w);
+NB2_DEV float twist_angle_signed(V3 axis, Q4 q) {  // wp.quat_twist_angle_signed: 2 atan2(q.xyz . axis, q.w), range (-2 pi, 2 pi]
+    return 2.0f * atan2_w(dot(V3(q.x, q.y, q.z), axis), q.w);
 }
 
 __global__ void __launch_bounds__(128) eval_ik_kernel(DevModel M, const float* __restrict__ body_q, const float* __restrict__ body_qd,

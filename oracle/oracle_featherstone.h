@@ -722,12 +722,12 @@ inline void eval_articulation_fk(const nb2_model_desc& m, const float* joint_q, 
 }
 
 // wp.quat_twist_angle_signed(axis, q): signed rotation angle of q's twist about `axis`.  Warp built-in (warp-lang >= 1.16,
-// not vendored; PARITY UNPINNED): restated as 2*atan2(q.xyz . axis, q.w) folded into (-pi, pi], which equals the
-// legacy `2*acos(twist.w)*sign(twist.xyz . axis)` form of warp.sim away from the branch cut.
+// not vendored): restated as 2*atan2(q.xyz . axis, q.w), range (-2 pi, 2 pi].  The unfolded range is pinned by the
+// reference's own test - newton/tests/test_kinematics.py:95-111 expects eval_ik(eval_fk(+-4.0 rad)) == +-4.0 to 1e-6,
+// which a fold into (-pi, pi] would break; operation order inside the built-in remains unpinned at the ulp level.
 inline float quat_twist_angle_signed(vec3 axis, quat q) {
-    float proj = dot(vec3(q.x, q.y, q.z), axis), w = q.w;
-    if (w < 0.0f) { proj = -proj; w = -w; }
-    return 2.0f * atan2_w(proj, w);
+    float proj = dot(vec3(q.x, q.y, q.z), axis);
+    return 2.0f * atan2_w(proj, q.w);
 }
 
 // ---- public newton.eval_ik (sim/articulation.py:640-932 eval_articulation_ik; one joint per thread, no mask) ---------------

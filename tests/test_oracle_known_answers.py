@@ -959,3 +959,77 @@ def test_body_force_at_com_offset_causes_no_rotation(oracle_lib, solver_name, co
     expected = 10.0 / float(model.body_mass[0]) * 0.05
     assert np.abs(qd[3:]).max() < 1e-3
     assert float(np.dot(direction, qd[:3])) == pytest.approx(expected, rel=5e-2)
+
+
+# ---- newton/tests/test_kinematics.py: eval_fk / eval_ik ----------------------------------------------------------------------
+
+def test_fk_ik_revolute_small_and_large_angles(oracle_lib):
+    """test_kinematics.py:95-111: eval_ik(eval_fk(q)) == q to 1e-6 for q in {+-4.0, +-5e-4, +-1e-4} rad - pins the range and
+    small-angle behaviour of wp.quat_twist_angle_signed."""
+    import torch
+
+    b = ModelBuilder(gravity=0.0)
+    child = b.add_link()
+    j = b.add_joint_revolute(parent=-1, child=child, axis=(0.0, 0.0, 1.0))
+    b.add_articulation([j])
+    model = b.finalize()
+    state = model.state()
+    q_ik, qd_ik = torch.zeros_like(model.joint_q), torch.zeros_like(model.joint_qd)
+    for angle in (-4.0, -5.0e-4, -1.0e-4, 1.0e-4, 5.0e-4, 4.0):
+        state.joint_q[0] = angle
+        oracle_lib.eval_fk(model, state.joint_q, state.joint_qd, state)
+        oracle_lib.eval_ik(model, state, q_ik, qd_ik)
+        assert float(q_ik[0]) == pytest.approx(float(np.float32(angle)), abs=1e-6)
+
+
+def test_fk_ik_two_link_arm_analytic(oracle_lib):
+    """test_kinematics.py:114-188: planar 2-link arm (L1 = 1.0, L2 = 0.8): FK positions against the closed form, IK recovers
+    the joint angles, tolerance 1e-4."""
+    import torch
+
+    L1, L2 = 1.0, 0.8
+    b = ModelBuilder(up_axis="Y", gravity=0.0)
+    link0 = b.add_link()
+    b.add_shape_sphere(link0, radius=0.01)
+    link1 = b.add_link()
+    b.add_shape_sphere(link1, radius=0.01)
+    j0 = b.add_joint_revolute(parent=-1, child=link0, axis=(0.0, 0.0, 1.0), child_xform=X.transform((0.0, L1, 0.0)))
+    j1 = b.add_joint_revolute(parent=link0, child=link1, axis=(0.0, 0.0, 1.0), child_xform=X.transform((0.0, L2, 0.0)))
+    b.add_articulation([j0, j1])
+    model = b.finalize()
+    for t1, t2 in ((0.0, 0.0), (0.3, 0.0), (0.0, -0.5), (math.pi / 4, math.pi / 4), (0.3, -0.2)):
+        state = model.state()
+        state.joint_q[0], state.joint_q[1] = t1, t2
+        oracle_lib.eval_fk(model, state.joint_q, state.joint_qd, state)
+        q = state.body_q.numpy()
+        np.testing.assert_allclose(q[0, :3], [L1 * math.sin(t1), -L1 * math.cos(t1), 0.0], atol=1e-4)
+        np.testing.assert_allclose(q[1, :3], [L1 * math.sin(t1) + L2 * math.sin(t1 + t2), -L1 * math.cos(t1) - L2 * math.cos(t1 + t2), 0.0],
+                                   atol=1e-4)
+        q_ik, qd_ik = torch.zeros_like(model.joint_q), torch.zeros_like(model.joint_qd)
+        oracle_lib.eval_ik(model, state, q_ik, qd_ik)
+        np.testing.assert_allclose(q_ik.numpy(), [t1, t2], atol=1e-4)
+
+
+def test_fk_descendant_velocity_matches_finite_difference(oracle_lib):
+    """test_kinematics.py:191-257: the COM twist eval_fk reports for the tip of a 2-revolute chain with offset anchors and an
+    offset parent COM agrees with the finite difference of its origin position (5e-3)."""
+    b = ModelBuilder(up_axis="Y", gravity=0.0)
+    link0, link1 = b.add_link(), b.add_link()
+    b.body_com[link0] = np.array([0.35, 0.0, 0.0])
+    j0 = b.add_joint_revolute(parent=-1, child=link0, axis=(0.0, 0.0, 1.0))
+    j1 = b.add_joint_revolute(parent=link0, child=link1, axis=(0.0, 0.0, 1.0), parent_xform=X.transform((1.0, 0.0, 0.0)),
+                              child_xform=X.transform((0.2, 0.0, -0.15)))
+    b.add_articulation([j0, j1])
+    model = b.finalize()
+    s0, s1 = model.state(), model.state()
+    q, qd = np.array([0.7, -0.35], dtype=np.float32), np.array([1.1, -0.45], dtype=np.float32)
+    dt = 1.0e-4
+    s0.joint_q.copy_(torch_f32(q)); s0.joint_qd.copy_(torch_f32(qd))
+    s1.joint_q.copy_(torch_f32(q + qd * dt)); s1.joint_qd.copy_(torch_f32(qd))
+    oracle_lib.eval_fk(model, s0.joint_q, s0.joint_qd, s0)
+    oracle_lib.eval_fk(model, s1.joint_q, s1.joint_qd, s1)
+    bq, bq1, bqd = s0.body_q.numpy(), s1.body_q.numpy(), s0.body_qd.numpy()
+    fd = (bq1[link1, :3] - bq[link1, :3]) / dt
+    com_world = X.quat_rotate(bq[link1, 3:].astype(np.float64), model.body_com.numpy()[link1].astype(np.float64))
+    origin_vel = bqd[link1, :3] - np.cross(bqd[link1, 3:], com_world)
+    np.testing.assert_allclose(fd, origin_vel, atol=5e-3)
