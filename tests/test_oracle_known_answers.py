@@ -1033,3 +1033,75 @@ def test_fk_descendant_velocity_matches_finite_difference(oracle_lib):
     com_world = X.quat_rotate(bq[link1, 3:].astype(np.float64), model.body_com.numpy()[link1].astype(np.float64))
     origin_vel = bqd[link1, :3] - np.cross(bqd[link1, 3:], com_world)
     np.testing.assert_allclose(fd, origin_vel, atol=5e-3)
+
+
+def _free_or_distance(b, kind, parent, child, parent_xform, child_xform):
+    if kind == "free":
+        return b.add_joint_free(child, parent=parent, parent_xform=parent_xform, child_xform=child_xform)
+    return b.add_joint_distance(parent, child, parent_xform=parent_xform, child_xform=child_xform, min_distance=-1.0, max_distance=-1.0)
+
+
+@pytest.mark.parametrize("kind", ["free", "distance"])
+def test_fk_free_root_descendant_velocity_matches_finite_difference(oracle_lib, kind):
+    """test_kinematics.py:377-517: FREE / DISTANCE-rooted chain with offset COMs on the root and on a revolute descendant
+    with non-trivial anchors; the root joint_qd is (v_com_world, omega_world).  The origin velocities recovered from
+    eval_fk's body_qd agree with forward differences of body_q for both bodies (5e-3)."""
+    b = ModelBuilder(up_axis="Y", gravity=0.0)
+    base, child = b.add_link(), b.add_link()
+    b.body_com[base] = np.array([0.15, -0.1, 0.05])
+    b.body_com[child] = np.array([0.3, 0.1, -0.15])
+    j0 = _free_or_distance(b, kind, -1, base, X.transform((0.0, 0.0, 0.0)), X.transform((0.0, 0.0, 0.0)))
+    j1 = b.add_joint_revolute(parent=base, child=child, axis=(0.0, 0.0, 1.0), parent_xform=X.transform((0.75, 0.25, -0.1)),
+                              child_xform=X.transform((0.2, -0.05, 0.15)))
+    b.add_articulation([j0, j1])
+    model = b.finalize()
+    q, qd = model.joint_q.numpy().astype(np.float64), model.joint_qd.numpy().astype(np.float64)
+    root_rot = X.quat_from_axis_angle(np.array([0.3, 1.0, -0.2]) / np.linalg.norm([0.3, 1.0, -0.2]), 0.55)
+    q[0:3], q[3:7], q[7] = [0.2, -0.1, 0.15], root_rot, 0.35
+    v_com, omega = np.array([0.6, -0.3, 0.2]), np.array([0.4, 0.25, -0.5])
+    qd[0:3], qd[3:6], qd[6] = v_com, omega, -0.7
+    dt = 1.0e-4
+    com_local = np.array([0.15, -0.1, 0.05])
+    rot_next = X.quat_mul(X.quat_from_axis_angle(omega / np.linalg.norm(omega), np.linalg.norm(omega) * dt), root_rot)
+    com_next = q[0:3] + X.quat_rotate(root_rot, com_local) + v_com * dt
+    q_next = q.copy()
+    q_next[0:3], q_next[3:7], q_next[7] = com_next - X.quat_rotate(rot_next, com_local), rot_next, q[7] + qd[6] * dt
+    s0, s1 = model.state(), model.state()
+    s0.joint_q.copy_(torch_f32(q)); s0.joint_qd.copy_(torch_f32(qd))
+    s1.joint_q.copy_(torch_f32(q_next)); s1.joint_qd.copy_(torch_f32(qd))
+    oracle_lib.eval_fk(model, s0.joint_q, s0.joint_qd, s0)
+    oracle_lib.eval_fk(model, s1.joint_q, s1.joint_qd, s1)
+    bq, bq1, bqd = s0.body_q.numpy(), s1.body_q.numpy(), s0.body_qd.numpy()
+    for body in (base, child):
+        fd = (bq1[body, :3] - bq[body, :3]) / dt
+        com_w = X.quat_rotate(bq[body, 3:].astype(np.float64), model.body_com.numpy()[body].astype(np.float64))
+        np.testing.assert_allclose(fd, bqd[body, :3] - np.cross(bqd[body, 3:], com_w), atol=5e-3)
+
+
+@pytest.mark.parametrize("kind", ["free", "distance"])
+def test_ik_free_descendant_recovers_joint_state(oracle_lib, kind):
+    """test_kinematics.py:520-575: a FREE / DISTANCE joint hanging off a revolute-jointed parent with offset COMs and anchors:
+    eval_ik(eval_fk(q, qd)) recovers q and qd to 1e-5."""
+    import torch
+
+    b = ModelBuilder(up_axis="Y", gravity=0.0)
+    base, child = b.add_link(), b.add_link()
+    b.body_com[base] = np.array([0.25, -0.1, 0.0])
+    b.body_com[child] = np.array([0.3, 0.15, -0.2])
+    j0 = b.add_joint_revolute(parent=-1, child=base, axis=(0.0, 0.0, 1.0))
+    j1 = _free_or_distance(b, kind, base, child, X.transform((1.0, 0.2, 0.3)), X.transform((0.1, -0.05, 0.2)))
+    b.add_articulation([j0, j1])
+    model = b.finalize()
+    state = model.state()
+    q, qd = state.joint_q.numpy().copy(), state.joint_qd.numpy().copy()
+    q[0] = 0.35
+    q[1:4] = [0.4, -0.2, 0.3]
+    q[4:8] = X.quat_from_axis_angle(np.array([1.0, 2.0, -1.0]) / math.sqrt(6.0), 0.45)
+    qd[0] = 0.9
+    qd[1:7] = [0.2, -0.15, 0.1, 0.4, -0.3, 0.25]
+    state.joint_q.copy_(torch_f32(q)); state.joint_qd.copy_(torch_f32(qd))
+    oracle_lib.eval_fk(model, state.joint_q, state.joint_qd, state)
+    rq, rqd = torch.zeros_like(state.joint_q), torch.zeros_like(state.joint_qd)
+    oracle_lib.eval_ik(model, state, rq, rqd)
+    np.testing.assert_allclose(rq.numpy(), q, atol=1e-5)
+    np.testing.assert_allclose(rqd.numpy(), qd, atol=1e-5)
