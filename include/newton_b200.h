@@ -195,6 +195,14 @@ int32_t nb2_model_rigid_contact_max(const nb2_model* model);
  * deterministic (env, sort-key) order and `rigid_contact_count[0]` is set. */
 nb2_status nb2_collide(nb2_model* model, const float* body_q, const nb2_contacts_view* contacts, void* cuda_stream);
 
+/* Load a reference-layout `Contacts` buffer that nb2_collide did NOT produce (e.g. written by the reference's own
+ * CollisionPipeline, sim/collide.py:1765-2207, or by user code) into the model's env-major contact blocks, so that the next
+ * nb2_xpbd_step / nb2_featherstone_step consumes it.  Contacts keep their array order inside each environment (stable sort
+ * by world), i.e. the per-body summation order of the reference's serial device; contacts between two static shapes are
+ * skipped; an environment's contacts beyond its block capacity (5 per candidate pair) are dropped.  The first call (and any
+ * call with a larger rigid_contact_max) allocates scratch and is therefore not CUDA-graph capturable; later calls are. */
+nb2_status nb2_contacts_import(nb2_model* model, const nb2_contacts_view* contacts, void* cuda_stream);
+
 /* Reference SolverXPBD.step(state_in, state_out, control, contacts, dt) (solver_xpbd.py:329-862).
  * `use_contacts` bit 0: 0 mirrors `contacts=None`; contacts come from the last nb2_collide() on this model.
  * `use_contacts` bit 1 (NB2_XPBD_CONTACT_IMPULSE): accumulate the weighted per-contact impulses the reference keeps

@@ -75,6 +75,7 @@ static nb2_status build_tables(nb2_model* m, const nb2_model_desc& d) {
 
     // ---- env partition ----------------------------------------------------------------------
     const bool implicit_single = (W == 1) && (bws[0] == B) && (jws[0] == J) && (sws[0] == S);
+    m->implicit_single = implicit_single;
     int E;
     h.global_shapes.clear();
     if (implicit_single) {  // model built without begin_world(): everything lives in world -1 (builder.py:11276)
@@ -427,6 +428,15 @@ nb2_status nb2_collide(nb2_model* model, const float* body_q, const nb2_contacts
         return NB2_ERR_INVALID_ARGUMENT;
     }
     return launch_collide(model, body_q, contacts, static_cast<cudaStream_t>(cuda_stream));
+}
+
+nb2_status nb2_contacts_import(nb2_model* model, const nb2_contacts_view* c, void* cuda_stream) {
+    if (!model || !c || !c->rigid_contact_count || !c->shape0 || !c->shape1 || !c->point0 || !c->point1 || !c->offset0 || !c->offset1 ||
+        !c->normal || !c->margin0 || !c->margin1 || c->rigid_contact_max < 0) {
+        set_error("nb2_contacts_import: NULL argument / contacts view has NULL arrays");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    return launch_contacts_import(model, *c, static_cast<cudaStream_t>(cuda_stream));
 }
 
 nb2_status nb2_xpbd_step(nb2_model* model, const nb2_xpbd_params* params, const nb2_state_view* state_in,

@@ -15,6 +15,8 @@
 // every contact its slot in key order - the order `CollisionPipeline(deterministic=True)` produces by radix sort.
 // Contacts land in env-major SoA "contact blocks" that the solver kernels read directly; an optional export pass
 // (scan + scatter) compacts them into the reference `Contacts` arrays.
+#include <cub/device/device_radix_sort.cuh>
+
 #include "nb2_gjk.cuh"
 #include "nb2_internal.cuh"
 #include "nb2_math.cuh"
@@ -571,6 +573,119 @@ __global__ void __launch_bounds__(128) contact_export_kernel(DevModel M, nb2_con
         out.margin1[o] = cb[CF_MARGIN1 * T + s];
         if (out.tids) out.tids[o] = 0;
     }
+}
+
+// ---- import of a foreign reference-layout Contacts buffer into the contact blocks (nb2_contacts_import) ----------------------
+__global__ void __launch_bounds__(256) import_keys_kernel(DevModel M, nb2_contacts_view in, int implicit_single, int* __restrict__ keys,
+                                                          int* __restrict__ idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= in.rigid_contact_max) return;
+    const nb2_model_desc& d = M.d;
+    const int n = min(in.rigid_contact_count[0], in.rigid_contact_max);
+    int key = M.env_count;  // sentinel: sorts behind every environment
+    if (i < n) {
+        const int s0 = in.shape0[i], s1 = in.shape1[i];
+        if (s0 >= 0 && s1 >= 0 && s0 != s1 && s0 < d.shape_count && s1 < d.shape_count) {
+            const bool dynamic = d.shape_body[s0] >= 0 || d.shape_body[s1] >= 0;  // static-vs-static contacts move nothing
+            int env = 0;
+            if (!implicit_single) {
+                const int w0 = d.shape_world[s0], w1 = d.shape_world[s1];
+                env = w0 >= 0 ? w0 : w1;
+            }
+            if (dynamic && env >= 0 && env < M.env_count) key = env;
+        }
+    }
+    keys[i] = key;
+    idx[i] = i;
+}
+
+NB2_DEV int lower_bound_int(const int* a, int n, int v) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(128) import_scatter_kernel(DevModel M, nb2_contacts_view in, const int* __restrict__ keys_sorted,
+                                                             const int* __restrict__ idx_sorted) {
+    const int env = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (env >= M.env_count) return;
+    const int lane = threadIdx.x & 31;
+    const nb2_model_desc& d = M.d;
+    const int first = lower_bound_int(keys_sorted, in.rigid_contact_max, env);
+    const int last = lower_bound_int(keys_sorted, in.rigid_contact_max, env + 1);
+    const int slot0 = M.env_slot_start[env], cap = M.env_slot_start[env + 1] - slot0;
+    const int n = min(last - first, cap);  // beyond the block capacity: dropped, like every other overflow of this path
+    if (lane == 0) M.env_contact_count[env] = n;
+    const int bs = M.env_body_start[env];
+    float* cb = M.cb;
+    const size_t T = size_t(M.slot_total);
+    for (int c = lane; c < n; c += 32) {
+        const int i = idx_sorted[first + c], slot = slot0 + c;
+        const int sa = in.shape0[i], sb = in.shape1[i];
+        const int body0 = d.shape_body[sa], body1 = d.shape_body[sb];
+        cb[CF_BODY_A * T + slot] = __int_as_float(body0 >= 0 ? body0 - bs : -1);
+        cb[CF_BODY_B * T + slot] = __int_as_float(body1 >= 0 ? body1 - bs : -1);
+        cb[CF_SHAPE0 * T + slot] = __int_as_float(sa);
+        cb[CF_SHAPE1 * T + slot] = __int_as_float(sb);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            cb[(CF_P0X + k) * T + slot] = in.point0[3 * i + k];
+            cb[(CF_P1X + k) * T + slot] = in.point1[3 * i + k];
+            cb[(CF_O0X + k) * T + slot] = in.offset0[3 * i + k];
+            cb[(CF_O1X + k) * T + slot] = in.offset1[3 * i + k];
+            cb[(CF_NX + k) * T + slot] = in.normal[3 * i + k];
+        }
+        cb[CF_MARGIN0 * T + slot] = in.margin0[i];
+        cb[CF_MARGIN1 * T + slot] = in.margin1[i];
+        // pair-averaged coefficients, exactly as the collide kernel's write-out computes them
+        cb[CF_MU * T + slot] = (d.shape_material_mu[sa] + d.shape_material_mu[sb]) / 2.0f;
+        cb[CF_MU_TORSIONAL * T + slot] = (d.shape_material_mu_torsional[sa] + d.shape_material_mu_torsional[sb]) / 2.0f;
+        cb[CF_MU_ROLLING * T + slot] = (d.shape_material_mu_rolling[sa] + d.shape_material_mu_rolling[sb]) / 2.0f;
+        cb[CF_KE * T + slot] = 0.5f * (d.shape_material_ke[sa] + d.shape_material_ke[sb]);
+        cb[CF_KD * T + slot] = 0.5f * (d.shape_material_kd[sa] + d.shape_material_kd[sb]);
+        cb[CF_KF * T + slot] = 0.5f * (d.shape_material_kf[sa] + d.shape_material_kf[sb]);
+        cb[CF_KA * T + slot] = 0.5f * (d.shape_material_ka[sa] + d.shape_material_ka[sb]);
+    }
+}
+
+nb2_status launch_contacts_import(nb2_model* m, const nb2_contacts_view& in, cudaStream_t s) {
+    const DevModel& M = m->dev;
+    if (M.env_count == 0) return NB2_OK;
+    const int C = in.rigid_contact_max;
+    int end_bit = 1;
+    while ((1 << end_bit) <= M.env_count) ++end_bit;  // keys are 0..env_count
+    if (C > m->import_capacity) {  // (re)allocate scratch: not capturable, see the header
+        size_t temp = 0;
+        NB2_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, temp, (const int*)nullptr, (int*)nullptr, (const int*)nullptr, (int*)nullptr, C, 0,
+                                                       end_bit, s));
+        int* buf = nullptr;
+        NB2_CUDA_CHECK(cudaMalloc(&buf, size_t(C) * 4 * sizeof(int)));
+        m->allocations.push_back(buf);
+        void* tmp = nullptr;
+        NB2_CUDA_CHECK(cudaMalloc(&tmp, std::max<size_t>(temp, 16)));
+        m->allocations.push_back(tmp);
+        m->import_keys = buf;
+        m->import_keys_sorted = buf + C;
+        m->import_idx = buf + 2 * size_t(C);
+        m->import_idx_sorted = buf + 3 * size_t(C);
+        m->import_temp = tmp;
+        m->import_temp_bytes = temp;
+        m->import_capacity = C;
+    }
+    if (C > 0) {
+        import_keys_kernel<<<(C + 255) / 256, 256, 0, s>>>(M, in, m->implicit_single ? 1 : 0, m->import_keys, m->import_idx);
+        size_t temp = m->import_temp_bytes;
+        NB2_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(m->import_temp, temp, m->import_keys, m->import_keys_sorted, m->import_idx,
+                                                       m->import_idx_sorted, C, 0, end_bit, s));  // stable: array order kept per env
+    }
+    import_scatter_kernel<<<(M.env_count + 3) / 4, 128, 0, s>>>(M, in, m->import_keys_sorted, m->import_idx_sorted);
+    count_launch(2);
+    NB2_CUDA_CHECK(cudaGetLastError());
+    return NB2_OK;
 }
 
 template <int L, bool CONVEX>

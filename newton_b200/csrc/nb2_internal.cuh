@@ -81,6 +81,12 @@ struct nb2_model {
     std::vector<void*> allocations;
     int lanes_per_env = 32;  // sub-warp group width used by the fused kernels
     int featherstone_step_count = 0;
+    // scratch of nb2_contacts_import (allocated on first use, sized by the imported buffer's capacity)
+    int import_capacity = 0;
+    int *import_keys = nullptr, *import_keys_sorted = nullptr, *import_idx = nullptr, *import_idx_sorted = nullptr;
+    void* import_temp = nullptr;
+    size_t import_temp_bytes = 0;
+    bool implicit_single = false;  // model built without begin_world(): one environment holding every entity
     bool has_convex_pairs = false;  // some pair's types have no analytic collider -> collide_kernel<L, true>
     float xpbd_impulse_dt = 0.0f;  // dt of the last nb2_xpbd_step that accumulated contact impulses (0 = none yet)
 };
@@ -91,6 +97,7 @@ void count_launch(int n = 1);
 nb2_status launch_collide(nb2_model* m, const float* body_q, const nb2_contacts_view* contacts, cudaStream_t s);
 nb2_status launch_xpbd_step(nb2_model* m, const nb2_xpbd_params& p, const nb2_state_view& in, const nb2_state_view& out,
                             const nb2_control_view& ctl, int use_contacts, float dt, cudaStream_t s);
+nb2_status launch_contacts_import(nb2_model* m, const nb2_contacts_view& contacts, cudaStream_t s);
 nb2_status launch_xpbd_update_contacts(nb2_model* m, const nb2_contacts_view& contacts, cudaStream_t s);
 nb2_status launch_integrate_bodies(nb2_model* m, const nb2_state_view& in, const nb2_state_view& out, float angular_damping,
                                    float dt, cudaStream_t s);

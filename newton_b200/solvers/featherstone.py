@@ -33,13 +33,7 @@ class SolverFeatherstone(SolverBase):
         model = self.model
         if control is None:
             control = model.control(clone_variables=False)
-        use_contacts = 0
-        if contacts is not None and contacts.rigid_contact_max:
-            if getattr(contacts, "_nb2_blocks", None) is not self._native:
-                raise NotImplementedError(
-                    "contacts were not produced by newton_b200.CollisionPipeline.collide() on this model"
-                )
-            use_contacts = 1
+        use_contacts = 1 if self._prepare_contacts(contacts) else 0
         p = _abi.FeatherstoneParams(self.angular_damping, int(self.update_mass_matrix_interval), self.friction_smoothing)
         st = _lib.lib().nb2_featherstone_step(
             self._native.handle, C.byref(p), C.byref(_abi.state_view(state_in)), C.byref(_abi.state_view(state_out)),

@@ -19,6 +19,19 @@ class SolverBase:
     def step(self, state_in, state_out, control, contacts, dt: float) -> None:
         raise NotImplementedError()
 
+    def _prepare_contacts(self, contacts) -> bool:
+        """True when ``contacts`` should be consumed.  Contacts produced by ``newton_b200.CollisionPipeline.collide()`` on this
+        model already sit in the native env-major contact blocks; any other ``Contacts`` buffer with the reference's
+        attributes (the reference's own ``CollisionPipeline``, hand-written contacts ...) is loaded through
+        ``nb2_contacts_import`` first - per world, in array order."""
+        if contacts is None or not contacts.rigid_contact_max:
+            return False
+        if getattr(contacts, "_nb2_blocks", None) is not self._native:
+            st = _lib.lib().nb2_contacts_import(self._native.handle, C.byref(_abi.contacts_view(contacts)),
+                                                _lib.current_stream_ptr(self.model))
+            _lib.check(st, "nb2_contacts_import")
+        return True
+
     def notify_model_changed(self, flags: int) -> None:
         """Reference ``solver.py:394-429``: the kernels read the Model arrays live; refresh borrowed pointers."""
         self._native.notify_model_changed(int(flags))

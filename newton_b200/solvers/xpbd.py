@@ -51,15 +51,12 @@ class SolverXPBD(SolverBase):
             control = model.control(clone_variables=False)
         use_contacts = 0
         if contacts is not None:
-            if getattr(contacts, "_nb2_blocks", None) is not self._native:
-                raise NotImplementedError(
-                    "contacts were not produced by newton_b200.CollisionPipeline.collide() on this model; importing "
-                    "foreign Contacts arrays into the env-major contact blocks is not implemented yet"
-                )
-            use_contacts = 1
-            if getattr(contacts, "force", None) is not None:  # the reference keeps impulses when contacts.force exists
-                if not getattr(contacts, "_nb2_exported", False):
-                    raise NotImplementedError("contacts.force needs CollisionPipeline(export_contacts=True)")
+            foreign = getattr(contacts, "_nb2_blocks", None) is not self._native
+            use_contacts = 1 if self._prepare_contacts(contacts) else 0
+            if use_contacts and getattr(contacts, "force", None) is not None:  # the reference keeps impulses when contacts.force exists
+                if foreign or not getattr(contacts, "_nb2_exported", False):
+                    raise NotImplementedError(
+                        "contacts.force needs contacts produced by newton_b200.CollisionPipeline(export_contacts=True)")
                 use_contacts |= 2
                 self._contact_impulse_capacity = contacts.rigid_contact_max
         p = self._params()

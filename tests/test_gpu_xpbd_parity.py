@@ -345,3 +345,51 @@ def test_run_to_run_determinism(cuda_lib, solver_name):
     assert runs[0][2] == runs[1][2]
     for name in ("body_q", "body_qd"):
         assert torch.equal(getattr(runs[0][0], name), getattr(runs[1][0], name)), name
+
+
+@pytest.mark.parametrize("solver_name", ["xpbd", "featherstone"])
+def test_foreign_contacts_import(oracle_lib, cuda_lib, solver_name):
+    """nb2_contacts_import: a reference-layout Contacts buffer that newton_b200's collide did not produce.  (a) A plain copy
+    of the exported arrays must step exactly like the native contact blocks; (b) the same contacts in the order the ORACLE
+    pipeline emits them (global sort-key order: all box-box contacts before the plane contacts) must reproduce the oracle's
+    step bit for bit - the per-world stable sort keeps each body's summation order."""
+    model = scenes.mixed_worlds_model(2)
+    mg = model.to("cuda:0")
+    if solver_name == "xpbd":
+        mk_g = lambda: newton_b200.solvers.SolverXPBD(mg, iterations=4)  # noqa: E731
+        mk_o = lambda: oracle_lib.SolverXPBD(model, iterations=4)  # noqa: E731
+        dt = 1.0 / 240
+    else:
+        mk_g = lambda: newton_b200.solvers.SolverFeatherstone(mg)  # noqa: E731
+        mk_o = lambda: oracle_lib.SolverFeatherstone(model)  # noqa: E731
+        dt = 1.0 / 480
+    pipe = newton_b200.CollisionPipeline(mg)
+    native = pipe.contacts()
+    s_in = mg.state()
+    pipe.collide(s_in, native)
+    assert int(native.rigid_contact_count.item()) > 20
+    # (a) copy of the exported buffer, no native tag
+    copy = pipe.contacts()
+    for name, value in vars(native).items():
+        if isinstance(value, torch.Tensor):
+            getattr(copy, name).copy_(value)
+    out_native, out_copy = mg.state(), mg.state()
+    mk_g().step(mg.state(), out_native, None, native, dt)
+    mk_g().step(mg.state(), out_copy, None, copy, dt)
+    assert torch.equal(out_native.body_q, out_copy.body_q) and torch.equal(out_native.body_qd, out_copy.body_qd)
+    # (b) the oracle pipeline's buffer (different global order), moved to the device as a foreign buffer
+    opipe = oracle_lib.CollisionPipeline(model)
+    oc = opipe.contacts()
+    o_in = model.state()
+    opipe.collide(o_in, oc)
+    foreign = pipe.contacts()
+    for name, value in vars(oc).items():
+        if isinstance(value, torch.Tensor) and getattr(foreign, name, None) is not None:
+            n = min(value.shape[0], getattr(foreign, name).shape[0])
+            getattr(foreign, name)[:n].copy_(value[:n])
+    o_out = model.state()
+    mk_o().step(model.state(), o_out, None, oc, dt)
+    g_out = mg.state()
+    mk_g().step(mg.state(), g_out, None, foreign, dt)
+    np.testing.assert_array_equal(g_out.body_q.cpu().numpy(), o_out.body_q.numpy())
+    np.testing.assert_array_equal(g_out.body_qd.cpu().numpy(), o_out.body_qd.numpy())
