@@ -195,6 +195,13 @@ int32_t nb2_model_rigid_contact_max(const nb2_model* model);
  * deterministic (env, sort-key) order and `rigid_contact_count[0]` is set. */
 nb2_status nb2_collide(nb2_model* model, const float* body_q, const nb2_contacts_view* contacts, void* cuda_stream);
 
+/* Reference CollisionPipeline(deterministic=True): ContactSorter.sort_full by make_contact_sort_key (sim/collide.py:2054-2073,
+ * geometry/contact_sort.py, contact_data.py:59-87).  nb2_collide exports contacts in (world, sort key) order; this call
+ * reorders the exported arrays of the SAME `contacts` buffer into the reference's global key order (stable radix sort on
+ * (shape0, shape1); the emission order inside a pair is the sub-key order).  The contact blocks the solvers read are not
+ * touched; nb2_xpbd_update_contacts follows the new order.  First call allocates scratch (not graph-capturable). */
+nb2_status nb2_contacts_sort(nb2_model* model, const nb2_contacts_view* contacts, void* cuda_stream);
+
 /* Load a reference-layout `Contacts` buffer that nb2_collide did NOT produce (e.g. written by the reference's own
  * CollisionPipeline, sim/collide.py:1765-2207, or by user code) into the model's env-major contact blocks, so that the next
  * nb2_xpbd_step / nb2_featherstone_step consumes it.  Contacts keep their array order inside each environment (stable sort

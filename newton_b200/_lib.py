@@ -18,7 +18,7 @@ STATUS = {0: "NB2_OK", 1: "NB2_ERR_INVALID_ARGUMENT", 2: "NB2_ERR_UNSUPPORTED", 
 
 # every symbol include/newton_b200.h declares
 EXPORTED_SYMBOLS = (
-    "nb2_model_create", "nb2_model_destroy", "nb2_model_notify_changed", "nb2_model_rigid_contact_max", "nb2_collide", "nb2_contacts_import",
+    "nb2_model_create", "nb2_model_destroy", "nb2_model_notify_changed", "nb2_model_rigid_contact_max", "nb2_collide", "nb2_contacts_sort", "nb2_contacts_import",
     "nb2_xpbd_step", "nb2_xpbd_update_contacts", "nb2_integrate_bodies", "nb2_featherstone_step", "nb2_eval_fk", "nb2_eval_ik", "nb2_last_error",
     "nb2_kernel_launch_count", "nb2_version",
 )
@@ -49,6 +49,8 @@ def lib():
         L.nb2_model_rigid_contact_max.restype = C.c_int32
         L.nb2_collide.argtypes = [P, P, C.POINTER(_abi.ContactsView), P]
         L.nb2_collide.restype = C.c_int
+        L.nb2_contacts_sort.argtypes = [P, C.POINTER(_abi.ContactsView), P]
+        L.nb2_contacts_sort.restype = C.c_int
         L.nb2_contacts_import.argtypes = [P, C.POINTER(_abi.ContactsView), P]
         L.nb2_contacts_import.restype = C.c_int
         L.nb2_xpbd_step.argtypes = [P, C.POINTER(_abi.XPBDParams), C.POINTER(_abi.StateView), C.POINTER(_abi.StateView),

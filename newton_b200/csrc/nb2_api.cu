@@ -427,7 +427,17 @@ nb2_status nb2_collide(nb2_model* model, const float* body_q, const nb2_contacts
         set_error("nb2_collide: NULL argument");
         return NB2_ERR_INVALID_ARGUMENT;
     }
+    model->dev.export_rank = nullptr;  // a fresh export is in (world, key) order until nb2_contacts_sort runs
     return launch_collide(model, body_q, contacts, static_cast<cudaStream_t>(cuda_stream));
+}
+
+nb2_status nb2_contacts_sort(nb2_model* model, const nb2_contacts_view* c, void* cuda_stream) {
+    if (!model || !c || !c->rigid_contact_count || !c->shape0 || !c->shape1 || !c->point0 || !c->point1 || !c->offset0 || !c->offset1 ||
+        !c->normal || !c->margin0 || !c->margin1 || c->rigid_contact_max < 0) {
+        set_error("nb2_contacts_sort: NULL argument / contacts view has NULL arrays");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    return launch_contacts_sort(model, *c, static_cast<cudaStream_t>(cuda_stream));
 }
 
 nb2_status nb2_contacts_import(nb2_model* model, const nb2_contacts_view* c, void* cuda_stream) {

@@ -575,6 +575,98 @@ __global__ void __launch_bounds__(128) contact_export_kernel(DevModel M, nb2_con
     }
 }
 
+// ---- deterministic=True: reorder the exported arrays into the reference's global sort-key order (nb2_contacts_sort) -----------
+__global__ void __launch_bounds__(256) sort_keys_kernel(nb2_contacts_view c, unsigned long long shape_radix, unsigned long long* __restrict__ keys,
+                                                        int* __restrict__ idx, float* __restrict__ stage) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.rigid_contact_max) return;
+    const int n = min(c.rigid_contact_count[0], c.rigid_contact_max);
+    idx[i] = i;
+    if (i >= n) {
+        keys[i] = ~0ull;
+        return;
+    }
+    // make_contact_sort_key orders by (shape_a, shape_b, sub_key); the export already lists a pair's contacts in sub-key order
+    keys[i] = (unsigned long long)(unsigned)c.shape0[i] * shape_radix + (unsigned long long)(unsigned)c.shape1[i];
+    float* st = stage + size_t(i) * 20;
+    st[0] = __int_as_float(c.shape0[i]);
+    st[1] = __int_as_float(c.shape1[i]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        st[2 + k] = c.point0[3 * i + k];
+        st[5 + k] = c.point1[3 * i + k];
+        st[8 + k] = c.offset0[3 * i + k];
+        st[11 + k] = c.offset1[3 * i + k];
+        st[14 + k] = c.normal[3 * i + k];
+    }
+    st[17] = c.margin0[i];
+    st[18] = c.margin1[i];
+    st[19] = c.tids ? __int_as_float(c.tids[i]) : 0.0f;
+}
+
+__global__ void __launch_bounds__(256) sort_gather_kernel(nb2_contacts_view c, const int* __restrict__ idx_sorted, const float* __restrict__ stage,
+                                                          int* __restrict__ rank) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= c.rigid_contact_max) return;
+    const int n = min(c.rigid_contact_count[0], c.rigid_contact_max);
+    if (p >= n) return;
+    const int i = idx_sorted[p];  // exported index that lands at position p
+    rank[i] = p;
+    const float* st = stage + size_t(i) * 20;
+    c.shape0[p] = __float_as_int(st[0]);
+    c.shape1[p] = __float_as_int(st[1]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        c.point0[3 * p + k] = st[2 + k];
+        c.point1[3 * p + k] = st[5 + k];
+        c.offset0[3 * p + k] = st[8 + k];
+        c.offset1[3 * p + k] = st[11 + k];
+        c.normal[3 * p + k] = st[14 + k];
+    }
+    c.margin0[p] = st[17];
+    c.margin1[p] = st[18];
+    if (c.tids) c.tids[p] = __float_as_int(st[19]);
+}
+
+nb2_status launch_contacts_sort(nb2_model* m, const nb2_contacts_view& c, cudaStream_t s) {
+    const int C = c.rigid_contact_max;
+    if (C == 0) return NB2_OK;
+    int bits = 1;
+    while ((1ull << bits) <= (unsigned long long)m->dev.d.shape_count) ++bits;  // shape ids are 0 .. shape_count - 1
+    const unsigned long long radix = 1ull << bits;
+    const int end_bit = 2 * bits < 64 ? 2 * bits : 64;
+    if (C > m->sort_capacity) {
+        size_t temp = 0;
+        NB2_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, temp, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                                       (const int*)nullptr, (int*)nullptr, C, 0, end_bit, s));
+        void *k = nullptr, *ix = nullptr, *st = nullptr, *tmp = nullptr, *rk = nullptr;
+        NB2_CUDA_CHECK(cudaMalloc(&k, size_t(C) * 2 * sizeof(unsigned long long)));
+        NB2_CUDA_CHECK(cudaMalloc(&ix, size_t(C) * 2 * sizeof(int)));
+        NB2_CUDA_CHECK(cudaMalloc(&st, size_t(C) * 20 * sizeof(float)));
+        NB2_CUDA_CHECK(cudaMalloc(&rk, size_t(C) * sizeof(int)));
+        NB2_CUDA_CHECK(cudaMalloc(&tmp, std::max<size_t>(temp, 16)));
+        for (void* p : {k, ix, st, rk, tmp}) m->allocations.push_back(p);
+        m->sort_keys = static_cast<unsigned long long*>(k);
+        m->sort_keys_sorted = m->sort_keys + C;
+        m->sort_idx = static_cast<int*>(ix);
+        m->sort_idx_sorted = m->sort_idx + C;
+        m->sort_stage = static_cast<float*>(st);
+        m->sort_rank = static_cast<int*>(rk);
+        m->sort_temp = tmp;
+        m->sort_temp_bytes = temp;
+        m->sort_capacity = C;
+    }
+    sort_keys_kernel<<<(C + 255) / 256, 256, 0, s>>>(c, radix, m->sort_keys, m->sort_idx, m->sort_stage);
+    size_t temp = m->sort_temp_bytes;
+    NB2_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(m->sort_temp, temp, m->sort_keys, m->sort_keys_sorted, m->sort_idx, m->sort_idx_sorted, C, 0,
+                                                   end_bit, s));  // stable
+    sort_gather_kernel<<<(C + 255) / 256, 256, 0, s>>>(c, m->sort_idx_sorted, m->sort_stage, m->sort_rank);
+    m->dev.export_rank = m->sort_rank;
+    count_launch(2);
+    NB2_CUDA_CHECK(cudaGetLastError());
+    return NB2_OK;
+}
+
 // ---- import of a foreign reference-layout Contacts buffer into the contact blocks (nb2_contacts_import) ----------------------
 __global__ void __launch_bounds__(256) import_keys_kernel(DevModel M, nb2_contacts_view in, int implicit_single, int* __restrict__ keys,
                                                           int* __restrict__ idx) {

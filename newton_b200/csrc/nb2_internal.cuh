@@ -58,6 +58,8 @@ struct DevModel {
     // XPBD reporting scratch (row a17): weighted contact impulses (6 planes of slot_total) and per-joint child-side impulses
     float* contact_impulse;
     float* joint_impulse;  // [6 * joint_count]
+    // exported index -> position after nb2_contacts_sort (nullptr: export order is the final order)
+    const int* export_rank;
 };
 
 struct HostTables {
@@ -86,6 +88,14 @@ struct nb2_model {
     int *import_keys = nullptr, *import_keys_sorted = nullptr, *import_idx = nullptr, *import_idx_sorted = nullptr;
     void* import_temp = nullptr;
     size_t import_temp_bytes = 0;
+    // scratch of nb2_contacts_sort (deterministic=True export order)
+    int sort_capacity = 0;
+    unsigned long long *sort_keys = nullptr, *sort_keys_sorted = nullptr;
+    int *sort_idx = nullptr, *sort_idx_sorted = nullptr;
+    float* sort_stage = nullptr;  // 20 words per contact: a copy of the exported arrays to gather from
+    int* sort_rank = nullptr;     // exported index -> sorted position
+    void* sort_temp = nullptr;
+    size_t sort_temp_bytes = 0;
     bool implicit_single = false;  // model built without begin_world(): one environment holding every entity
     bool has_convex_pairs = false;  // some pair's types have no analytic collider -> collide_kernel<L, true>
     float xpbd_impulse_dt = 0.0f;  // dt of the last nb2_xpbd_step that accumulated contact impulses (0 = none yet)
@@ -97,6 +107,7 @@ void count_launch(int n = 1);
 nb2_status launch_collide(nb2_model* m, const float* body_q, const nb2_contacts_view* contacts, cudaStream_t s);
 nb2_status launch_xpbd_step(nb2_model* m, const nb2_xpbd_params& p, const nb2_state_view& in, const nb2_state_view& out,
                             const nb2_control_view& ctl, int use_contacts, float dt, cudaStream_t s);
+nb2_status launch_contacts_sort(nb2_model* m, const nb2_contacts_view& contacts, cudaStream_t s);
 nb2_status launch_contacts_import(nb2_model* m, const nb2_contacts_view& contacts, cudaStream_t s);
 nb2_status launch_xpbd_update_contacts(nb2_model* m, const nb2_contacts_view& contacts, cudaStream_t s);
 nb2_status launch_integrate_bodies(nb2_model* m, const nb2_state_view& in, const nb2_state_view& out, float angular_damping,

@@ -876,8 +876,9 @@ __global__ void __launch_bounds__(128) xpbd_update_contacts_kernel(DevModel M, n
     const int n = M.env_contact_count[env], base = M.env_contact_offset[env], slot0 = M.env_slot_start[env];
     const size_t T = size_t(M.slot_total);
     for (int c = lane; c < n; c += 32) {
-        const int o = base + c;
+        int o = base + c;
         if (o >= out.rigid_contact_max) break;
+        if (M.export_rank) o = M.export_rank[o];  // the buffer was reordered by nb2_contacts_sort
 #pragma unroll
         for (int k = 0; k < 6; ++k) out.force[6 * size_t(o) + k] = M.contact_impulse[k * T + slot0 + c] * inv_dt;
     }

@@ -36,7 +36,8 @@ class CollisionPipeline:
         self.model = model
         self.device = model.device
         self._native = _lib.native_model(model)
-        # Contacts are always produced in deterministic (env, sort-key) order, so `deterministic` is a no-op.
+        # Contacts are always produced in a deterministic (world, sort-key) order.  deterministic=True additionally reorders
+        # the exported arrays into the reference's global sort-key order (ContactSorter.sort_full, collide.py:2054-2073).
         self.deterministic = deterministic
         self.export_contacts = export_contacts
         native_max = self._native.rigid_contact_max
@@ -63,3 +64,6 @@ class CollisionPipeline:
         st = _lib.lib().nb2_collide(self._native.handle, C.c_void_p(_abi.ptr(state.body_q)), view,
                                     _lib.current_stream_ptr(self.model))
         _lib.check(st, "nb2_collide")
+        if self.deterministic and view is not None:
+            st = _lib.lib().nb2_contacts_sort(self._native.handle, view, _lib.current_stream_ptr(self.model))
+            _lib.check(st, "nb2_contacts_sort")

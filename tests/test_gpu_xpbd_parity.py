@@ -393,3 +393,32 @@ def test_foreign_contacts_import(oracle_lib, cuda_lib, solver_name):
     mk_g().step(mg.state(), g_out, None, foreign, dt)
     np.testing.assert_array_equal(g_out.body_q.cpu().numpy(), o_out.body_q.numpy())
     np.testing.assert_array_equal(g_out.body_qd.cpu().numpy(), o_out.body_qd.numpy())
+
+
+def test_deterministic_export_matches_reference_order(oracle_lib, cuda_lib):
+    """CollisionPipeline(deterministic=True): the exported arrays are in the reference's global sort-key order
+    (ContactSorter.sort_full, collide.py:2054-2073) - compared element by element with the oracle's sorted buffer, no
+    canonicalisation - and Contacts.force follows that order."""
+    for model in (scenes.mixed_worlds_model(2), scenes.box_stack_model(3, seed=1)):
+        model.request_contact_attributes("force")
+        mg = model.to("cuda:0")
+        opipe, gpipe = oracle_lib.CollisionPipeline(model, deterministic=True), newton_b200.CollisionPipeline(mg, deterministic=True)
+        oc, gc = opipe.contacts(), gpipe.contacts()
+        osolver, gsolver = oracle_lib.SolverXPBD(model, iterations=4), newton_b200.solvers.SolverXPBD(mg, iterations=4)
+        o0, o1, g0, g1 = model.state(), model.state(), mg.state(), mg.state()
+        for _ in range(20):
+            opipe.collide(o0, oc)
+            osolver.step(o0, o1, None, oc, 1.0 / 240)
+            o0, o1 = o1, o0
+            gpipe.collide(g0, gc)
+            gsolver.step(g0, g1, None, gc, 1.0 / 240)
+            g0, g1 = g1, g0
+        osolver.update_contacts(oc)
+        gsolver.update_contacts(gc)
+        n = int(oc.rigid_contact_count.item())
+        assert n == int(gc.rigid_contact_count.item()) and n > 10
+        for name in ("shape0", "shape1", "point0", "point1", "offset0", "offset1", "normal", "margin0", "margin1"):
+            np.testing.assert_array_equal(getattr(gc, "rigid_contact_" + name)[:n].cpu().numpy(),
+                                          getattr(oc, "rigid_contact_" + name)[:n].numpy(), err_msg=name)
+        np.testing.assert_array_equal(gc.force[:n].cpu().numpy(), oc.force[:n].numpy())
+        np.testing.assert_array_equal(g0.body_q.cpu().numpy(), o0.body_q.numpy())
