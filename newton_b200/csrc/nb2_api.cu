@@ -129,24 +129,19 @@ static nb2_status build_tables(nb2_model* m, const nb2_model_desc& d) {
         if (shape_type[sa] > shape_type[sb]) std::swap(sa, sb);  // narrow_phase.py:525-528
         {   // shapes the narrow phase of this library covers: analytic primitives + convex primitives through MPR/GJK
             const int ta = shape_type[sa], tb = shape_type[sb];
-            auto known = [](int t) { return t == 1 || (t >= 3 && t <= 7); };  // PLANE SPHERE CAPSULE ELLIPSOID CYLINDER BOX
+            auto known = [](int t) { return t == 1 || (t >= 3 && t <= 7) || t == 9; };  // PLANE SPHERE CAPSULE ELLIPSOID CYLINDER BOX CONE
             if (!known(ta) || !known(tb)) {
                 set_error("shape pair (" + std::to_string(sa) + "," + std::to_string(sb) + "): geometry types " + std::to_string(ta) + "/" +
-                          std::to_string(tb) + " are outside the supported set (plane, sphere, capsule, ellipsoid, cylinder, box)");
+                          std::to_string(tb) + " are outside the supported set (plane, sphere, capsule, ellipsoid, cylinder, box, cone)");
                 return NB2_ERR_UNSUPPORTED;
             }
-            // plane vs barrel cylinder can fall through to the generic convex path, which needs the reference's
-            // infinite-plane -> cube conversion (collision_core.py:752-766): not built
             {   // narrow_phase.py:642-655 + the analytic chain of narrow_phase.py:657-864: everything else is MPR / GJK
-                const bool early = ta >= 5 || (ta == 4 && tb > 4);
-                const bool analytic = !early && ((ta == 1 && (tb == 3 || tb == 4 || tb == 5 || tb == 6 || tb == 7)) ||
-                                                 (ta == 3 && (tb == 3 || tb == 4 || tb == 7 || (tb == 6 && shape_scale[3 * sb + 2] == 0.0f))) ||
-                                                 (ta == 4 && tb == 4));
-                if (!analytic && ta != 1) m->has_convex_pairs = true;
-            }
-            if (ta == 1 && tb == 6 && shape_scale[3 * sb + 2] != 0.0f) {
-                set_error("plane vs barrel cylinder (shape_scale.z != 0) is not supported");
-                return NB2_ERR_UNSUPPORTED;
+                // (a plane that gets there - cone, barrel cylinder lying on its side - is replaced by a box proxy)
+                const bool early = ta >= 5 || tb == 9 || (ta == 4 && tb > 4);
+                const bool barrel = tb == 6 && shape_scale[3 * sb + 2] != 0.0f;
+                const bool analytic = !early && ((ta == 1 && (tb == 3 || tb == 4 || tb == 5 || (tb == 6 && !barrel) || tb == 7)) ||
+                                                 (ta == 3 && (tb == 3 || tb == 4 || tb == 7 || (tb == 6 && !barrel))) || (ta == 4 && tb == 4));
+                if (!analytic) m->has_convex_pairs = true;
             }
         }
         int64_t key = ((int64_t(sa) & 0xFFFFF) << 43) | ((int64_t(sb) & 0xFFFFF) << 23);

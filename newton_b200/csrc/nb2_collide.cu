@@ -251,6 +251,11 @@ NB2_DEV void shape_aabb(int type, V3 scale, const Xf& X, float gap_eff, float co
         V3 r0 = qrot(X.q, V3(1.f, 0.f, 0.f)), r1 = qrot(X.q, V3(0.f, 1.f, 0.f)), r2 = qrot(X.q, V3(0.f, 0.f, 1.f));
         he = V3(radius * sqrtf(r0.x * r0.x + r1.x * r1.x) + hh * fabsf(r2.x), radius * sqrtf(r0.y * r0.y + r1.y * r1.y) + hh * fabsf(r2.y),
                 radius * sqrtf(r0.z * r0.z + r1.z * r1.z) + hh * fabsf(r2.z));
+    } else if (type == GEO_CONE) {  // generic branch of compute_shape_aabbs: tight AABB from the support map
+        tight_aabb_from_support(ConvexGeom{CG_CONE, scale}, X.q, pos, lo, hi);
+        lo = lo - mvv;
+        hi = hi + mvv;
+        return;
     } else if (type == GEO_ELLIPSOID) {
         M33 R = qmat(X.q);
 #pragma unroll
@@ -413,8 +418,8 @@ __global__ void __launch_bounds__(32) collide_kernel(DevModel M, const float* __
                         }
                     }
                 } else if (CONVEX) {
-                    ConvexShape A{ta, sca, Xa, marg_a, d.shape_gap[sa]};
-                    ConvexShape Bc{tb, scb, Xb, marg_b, d.shape_gap[sb]};
+                    ConvexShape A{ta, sca, Xa, marg_a, d.shape_gap[sa], alo, ahi};
+                    ConvexShape Bc{tb, scb, Xb, marg_b, d.shape_gap[sb], blo, bhi};
                     vmask = convex_pair_contacts(A, Bc, cdist, cpos, cnorm, reff_a, reff_b);
                 }
             }

@@ -911,4 +911,57 @@ NB2_DEV int convex_contacts(const ConvexPairIn& in, float* odist, V3* opos, V3* 
     return count;
 }
 
+// compute_tight_aabb_from_support, generic branch (collision_core.py:454-548): six support evaluations along the world axes
+// expressed in the shape frame.  Used for the shapes compute_shape_aabbs has no closed form for (cones).
+NB2_DEV void tight_aabb_from_support(const ConvexGeom& g, Q4 q, V3 pos, V3& lo, V3& hi) {
+    const M33 R = qmat(q);
+    const V3 lx(R.at(0, 0), R.at(0, 1), R.at(0, 2)), ly(R.at(1, 0), R.at(1, 1), R.at(1, 2)), lz(R.at(2, 0), R.at(2, 1), R.at(2, 2));
+    const float max_x = dot(lx, support_map(g, lx)), max_y = dot(ly, support_map(g, ly)), max_z = dot(lz, support_map(g, lz));
+    const float min_x = dot(lx, support_map(g, -lx)), min_y = dot(ly, support_map(g, -ly)), min_z = dot(lz, support_map(g, -lz));
+    lo = V3(min_x, min_y, min_z) + pos;
+    hi = V3(max_x, max_y, max_z) + pos;
+}
+
+struct ConvexPairAabbs {  // the shapes' world AABBs as compute_shape_aabbs wrote them (external_aabb=True path)
+    V3 lo_a, hi_a, lo_b, hi_b;
+};
+
+// narrow_phase_kernel_gjk_mpr + find_contacts (narrow_phase.py:1098-1216, collision_core.py:700-790): an infinite plane that
+// reaches the generic path (plane-cone, plane-barrel-cylinder) is first tested against the other shape's bounding sphere and
+// then replaced by a box proxy whose top face is the plane (convert_infinite_plane_to_cube, collision_core.py:566-626).
+NB2_DEV int convex_contacts_any(ConvexPairIn in, const ConvexPairAabbs& bb, float* odist, V3* opos, V3* onorm, float& reff_a, float& reff_b) {
+    reff_a = 0.0f;
+    reff_b = 0.0f;
+    // geom_data keeps HALF extents for finite planes (collide.py:452-453); infinite planes stay (0, 0)
+    if (in.type_a == CG_PLANE) in.scale_a = V3(in.scale_a.x * 0.5f, in.scale_a.y * 0.5f, 0.0f);
+    if (in.type_b == CG_PLANE) in.scale_b = V3(in.scale_b.x * 0.5f, in.scale_b.y * 0.5f, 0.0f);
+    const bool inf_a = in.type_a == CG_PLANE && in.scale_a.x == 0.0f && in.scale_a.y == 0.0f;
+    const bool inf_b = in.type_b == CG_PLANE && in.scale_b.x == 0.0f && in.scale_b.y == 0.0f;
+    if (inf_a && inf_b) return 0;
+    if (inf_a || inf_b) {
+        const V3 ca = 0.5f * (bb.lo_a + bb.hi_a), cb = 0.5f * (bb.lo_b + bb.hi_b);  // compute_bounding_sphere_from_aabb
+        const float ra = len(0.5f * (bb.hi_a - bb.lo_a)), rb = len(0.5f * (bb.hi_b - bb.lo_b));
+        const Xf plane = inf_a ? in.Xa : in.Xb;
+        const V3 other_center = inf_a ? cb : ca;
+        const float other_radius = inf_a ? rb : ra;
+        const V3 n = qrot(plane.q, V3(0.f, 0.f, 1.f));
+        if (dot(other_center - plane.p, n) > other_radius) return 0;  // check_infinite_plane_bsphere_overlap
+        const V3 other_pos = inf_a ? in.Xb.p : in.Xa.p;
+        const float size = (other_radius + in.gap_sum) * 10.0f;  // lateral_size == depth
+        const float dist_n = dot(other_pos - plane.p, n);
+        const V3 surface = other_pos - n * dist_n;
+        const V3 adjusted = surface - n * size;
+        if (inf_a) {
+            in.type_a = CG_BOX;
+            in.scale_a = V3(size, size, size);
+            in.Xa.p = adjusted;
+        } else {
+            in.type_b = CG_BOX;
+            in.scale_b = V3(size, size, size);
+            in.Xb.p = adjusted;
+        }
+    }
+    return convex_contacts(in, odist, opos, onorm, reff_a, reff_b);
+}
+
 }  // namespace nb2

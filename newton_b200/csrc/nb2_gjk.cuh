@@ -9,15 +9,11 @@ struct ConvexShape {
     V3 scale;
     Xf X;
     float margin, gap;
+    V3 lo, hi;  // world AABB (margin + gap included), as the broad phase used it
 };
 // Returns a bit mask of valid entries in dist/pos/normal (up to 5 manifold contacts, emission order = sort_sub_key order).
-// Pairs with a PLANE reach the generic path only for cones / barrel cylinders (narrow_phase.py:1098-1165 converts the
-// infinite plane to a cube first); that conversion is not built, nb2_model_create rejects such models (nb2_api.cu).
 NB2_DEV unsigned convex_pair_contacts(const ConvexShape& a, const ConvexShape& b, float* dist, V3* pos, V3* normal, float& reff_a,
                                       float& reff_b) {
-    reff_a = 0.0f;
-    reff_b = 0.0f;
-    if (a.type == CG_PLANE || b.type == CG_PLANE) return 0u;
     ConvexPairIn in;
     in.type_a = a.type;
     in.type_b = b.type;
@@ -28,7 +24,8 @@ NB2_DEV unsigned convex_pair_contacts(const ConvexShape& a, const ConvexShape& b
     in.margin_a = a.margin;
     in.margin_b = b.margin;
     in.gap_sum = a.gap + b.gap;
-    const int n = convex_contacts(in, dist, pos, normal, reff_a, reff_b);
+    ConvexPairAabbs bb{a.lo, a.hi, b.lo, b.hi};
+    const int n = convex_contacts_any(in, bb, dist, pos, normal, reff_a, reff_b);
     return (1u << n) - 1u;
 }
 }  // namespace nb2

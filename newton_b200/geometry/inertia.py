@@ -41,6 +41,15 @@ def compute_inertia_cylinder(density, r, hh, barrel_radius=0.0):
     return m, np.zeros(3), np.diag([Ia, Ia, Ib])
 
 
+def compute_inertia_cone(density, r, hh):
+    """Solid cone along z, base at -hh, apex at +hh (reference ``inertia.py:195-223``): COM a quarter height above the base."""
+    h = 2.0 * hh
+    m = density * math.pi * r * r * h / 3.0
+    Ia = 3.0 / 20.0 * m * r * r + 3.0 / 80.0 * m * h * h
+    Ib = 3.0 / 10.0 * m * r * r
+    return m, np.array([0.0, 0.0, -h / 4.0]), np.diag([Ia, Ia, Ib])
+
+
 def compute_inertia_ellipsoid(density, rx, ry, rz):
     m = density * (4.0 / 3.0) * math.pi * rx * ry * rz
     return (
@@ -75,6 +84,7 @@ def compute_inertia_shape(geo_type, scale, density, is_solid=True, thickness=0.0
         GeoType.CAPSULE: lambda s: compute_inertia_capsule(density, s[0], s[1]),
         GeoType.CYLINDER: lambda s: compute_inertia_cylinder(density, s[0], s[1], s[2] if len(s) > 2 else 0.0),
         GeoType.ELLIPSOID: lambda s: compute_inertia_ellipsoid(density, s[0], s[1], s[2]),
+        GeoType.CONE: lambda s: compute_inertia_cone(density, s[0], s[1]),
     }
     if geo_type not in fns:
         raise NotImplementedError(f"inertia of shape type {geo_type} is outside the hot-path scope")

@@ -618,6 +618,10 @@ class ModelBuilder:
         return self.add_shape(body=body, type=GeoType.CYLINDER, xform=xform, cfg=cfg,
                               scale=(radius, half_height, 0.0), label=label)
 
+    def add_shape_cone(self, body, *, xform=None, radius=1.0, half_height=0.5, cfg=None, label=None) -> int:
+        """Cone along +z, apex up (reference ``sim/builder.py`` ``add_shape_cone``; support map ``support_function.py:316-336``)."""
+        return self.add_shape(body=body, type=GeoType.CONE, xform=xform, cfg=cfg, scale=(radius, half_height, 0.0), label=label)
+
     # ------------------------------------------------------------------ URDF (primitive geometry only)
     def add_urdf(self, source: str, *, xform=None, floating=None, enable_self_collisions=True,
                  ignore_inertial_definitions=False, scale=1.0):

@@ -7,6 +7,7 @@
 //   write_contact                  reference sim/collide.py:166-254
 //   deterministic sort key         reference geometry/contact_data.py:59-87
 #pragma once
+#include "../newton_b200/csrc/nb2_convex.cuh"  // single-source support maps (cone AABB), see oracle_gjk.h
 #include <algorithm>
 #include <vector>
 
@@ -322,6 +323,13 @@ inline void compute_shape_aabbs(const nb2_model_desc& m, const float* body_q, st
                     radius * std::sqrt(r0.z * r0.z + r1.z * r1.z) + half_height * std::fabs(r2.z));
             lo = pos - he - margin_vec;
             hi = pos + he + margin_vec;
+        } else if (geo_type == GEO_CONE) {
+            // generic branch (collide.py:447-468): compute_tight_aabb_from_support, single-source with the CUDA build
+            nb2::V3 l, h;
+            nb2::tight_aabb_from_support(nb2::ConvexGeom{nb2::CG_CONE, nb2::V3(scale.x, scale.y, scale.z)},
+                                         nb2::Q4(orientation.x, orientation.y, orientation.z, orientation.w), nb2::V3(pos.x, pos.y, pos.z), l, h);
+            lo = vec3(l.x, l.y, l.z) - margin_vec;
+            hi = vec3(h.x, h.y, h.z) + margin_vec;
         } else if (geo_type == GEO_ELLIPSOID) {
             // tight AABB from the support map (collide.py:447-468): extent_i = |R_i * diag(scale)|
             mat33 R = quat_to_matrix(orientation);

@@ -22,9 +22,9 @@ inline nb2::Xf to_nb2(const transform& t) { return nb2::Xf(to_nb2(t.p), nb2::Q4(
 
 // One pair through compute_gjk_mpr_contacts; contacts come back already gap-tested, in sort_sub_key order.
 inline int convex_pair(int type_a, vec3 scale_a, const transform& Xa, float margin_a, int type_b, vec3 scale_b, const transform& Xb,
-                       float margin_b, float gap_sum, float* dist, vec3* pos, vec3* normal, float& reff_a, float& reff_b) {
+                       float margin_b, float gap_sum, float* dist, vec3* pos, vec3* normal, float& reff_a, float& reff_b,
+                       vec3 lo_a = vec3(), vec3 hi_a = vec3(), vec3 lo_b = vec3(), vec3 hi_b = vec3()) {
     reff_a = reff_b = 0.0f;
-    if (type_a == GEO_PLANE || type_b == GEO_PLANE) return 0;  // infinite-plane -> cube conversion not built (see nb2_gjk.cuh)
     nb2::ConvexPairIn in;
     in.type_a = type_a;
     in.type_b = type_b;
@@ -36,7 +36,8 @@ inline int convex_pair(int type_a, vec3 scale_a, const transform& Xa, float marg
     in.margin_b = margin_b;
     in.gap_sum = gap_sum;
     nb2::V3 p[5], n[5];
-    int cnt = nb2::convex_contacts(in, dist, p, n, reff_a, reff_b);
+    nb2::ConvexPairAabbs bb{to_nb2(lo_a), to_nb2(hi_a), to_nb2(lo_b), to_nb2(hi_b)};
+    int cnt = nb2::convex_contacts_any(in, bb, dist, p, n, reff_a, reff_b);
     for (int i = 0; i < cnt; ++i) {
         pos[i] = from_nb2(p[i]);
         normal[i] = from_nb2(n[i]);
@@ -57,7 +58,7 @@ inline void gjk_mpr_pairs(const nb2_model_desc& m, const float* body_q, CollideR
         vec3 pos[5], normal[5];
         const float gap_sum = m.shape_gap[shape_a] + m.shape_gap[shape_b];
         int cnt = convex_pair(m.shape_type[shape_a], A.scale, A.X_ws, A.margin, m.shape_type[shape_b], B.scale, B.X_ws, B.margin, gap_sum,
-                              dist, pos, normal, ra, rb);
+                              dist, pos, normal, ra, rb, A.aabb_lower, A.aabb_upper, B.aabb_lower, B.aabb_upper);
         for (int i = 0; i < cnt; ++i) {
             RawContact rc;
             // emission order == sort_sub_key order; dropped manifold points only leave holes in the sub-key sequence
@@ -93,7 +94,24 @@ inline int convex_pair_test(int type_a, vec3 scale_a, const transform& Xa, int t
                             float* dist5, float* pos15, float* normal15) {
     float ra, rb;
     vec3 pos[5], normal[5];
-    int cnt = convex_pair(type_a, scale_a, Xa, 0.0f, type_b, scale_b, Xb, 0.0f, gap_sum, dist5, pos, normal, ra, rb);
+    // AABBs as the stand-alone NarrowPhase computes them (narrow_phase.py:1120-1150): tight support AABB +- the shape's gap;
+    // only the bounding-sphere radius of the shape facing an infinite plane depends on them
+    auto aabb = [&](int type, vec3 scale, const transform& X, vec3& lo, vec3& hi) {
+        if (type == GEO_PLANE) {
+            lo = X.p - vec3(1.0e6f);
+            hi = X.p + vec3(1.0e6f);
+            return;
+        }
+        nb2::V3 l, h;
+        nb2::tight_aabb_from_support(nb2::ConvexGeom{type, to_nb2(scale)}, nb2::Q4(X.q.x, X.q.y, X.q.z, X.q.w), to_nb2(X.p), l, h);
+        const vec3 g(0.5f * gap_sum);
+        lo = from_nb2(l) - g;
+        hi = from_nb2(h) + g;
+    };
+    vec3 lo_a, hi_a, lo_b, hi_b;
+    aabb(type_a, scale_a, Xa, lo_a, hi_a);
+    aabb(type_b, scale_b, Xb, lo_b, hi_b);
+    int cnt = convex_pair(type_a, scale_a, Xa, 0.0f, type_b, scale_b, Xb, 0.0f, gap_sum, dist5, pos, normal, ra, rb, lo_a, hi_a, lo_b, hi_b);
     for (int i = 0; i < cnt; ++i) {
         store3(pos15 + 3 * i, pos[i]);
         store3(normal15 + 3 * i, normal[i]);

@@ -762,7 +762,7 @@ def test_torque_free_precession_featherstone(oracle_lib):
 
 def _ramp_scene():
     """Scene of newton/tests/test_rigid_contact.py:236-432 (objects resting on a 30-degree ramp against an end wall), minus
-    the two cones and the two convex-hull cubes (shape types outside this library's scope; they sit furthest up the ramp)."""
+    the two convex-hull cubes (convex meshes are outside this library's scope; they sit furthest up the ramp)."""
     L, TH, ANG, WALL_H, CUBE = 10.0, 0.5, math.radians(30.0), 2.0, 0.99
     W = CUBE * 2.01
     b = ModelBuilder()
@@ -796,6 +796,12 @@ def _ramp_scene():
     b.add_shape_cylinder(body, radius=CUBE / 2, half_height=CUBE)
     for side in (1.0, -1.0):
         body = b.add_body(xform=X.transform(at(side, 8.04), rq))
+        b.add_shape_box(body, hx=CUBE / 2, hy=CUBE / 2, hz=CUBE / 2)
+    for side in (1.0, -1.0):  # cones, axis along the ramp normal: plane-cone goes through the plane -> box proxy + MPR
+        body = b.add_body(xform=X.transform(at(side, 10.05), rq))
+        b.add_shape_cone(body, radius=CUBE / 2, half_height=CUBE / 2)
+    for side in (1.0, -1.0):
+        body = b.add_body(xform=X.transform(at(side, 12.06), rq))
         b.add_shape_box(body, hx=CUBE / 2, hy=CUBE / 2, hz=CUBE / 2)
     b.add_ground_plane()
     return b.finalize(), CUBE
@@ -1105,3 +1111,24 @@ def test_ik_free_descendant_recovers_joint_state(oracle_lib, kind):
     oracle_lib.eval_ik(model, state, rq, rqd)
     np.testing.assert_allclose(rq.numpy(), q, atol=1e-5)
     np.testing.assert_allclose(rqd.numpy(), qd, atol=1e-5)
+
+
+
+def test_narrow_phase_barrel_cylinder_and_cone(oracle_lib):
+    """newton/tests/test_narrow_phase.py:1268-1327: barrel cylinders through the generic path - a sphere against the curved
+    barrel, an infinite plane against a barrel lying on its side (plane -> box proxy, collision_core.py:566-626) and against
+    its cap (>= 3 manifold points, all penetrating); plus cones resting on a plane on their base / on their side."""
+    s = math.sqrt(0.5)
+    cnt, dist, _, _ = oracle_lib.convex_pair(GeoType.SPHERE, (0.25, 0, 0), _xf([1.7, 0, 0]), GeoType.CYLINDER, (0.5, 1.0, 1.0), I7)
+    assert cnt > 0 and dist[0] < 0.0
+    cnt, dist, _, n = oracle_lib.convex_pair(GeoType.PLANE, (0, 0, 0), I7, GeoType.CYLINDER, (0.5, 1.0, 1.0), _xf([0, 0, 1.45], (0, s, 0, s)))
+    assert cnt > 0 and dist[0] < 0.0
+    assert dist[0] == pytest.approx(1.45 - 1.5, abs=1e-3)  # equatorial radius 0.5 + 1.0 - sqrt(1.0^2 - 1.0^2)
+    np.testing.assert_allclose(n[0], [0, 0, 1], atol=1e-4)
+    cnt, dist, _, _ = oracle_lib.convex_pair(GeoType.PLANE, (0, 0, 0), I7, GeoType.CYLINDER, (0.5, 1.0, 1.5), _xf([0, 0, 0.99]))
+    assert cnt >= 3 and np.all(dist[:cnt] < 0.0)
+    cnt, dist, pos, n = oracle_lib.convex_pair(GeoType.PLANE, (0, 0, 0), I7, GeoType.CONE, (0.5, 0.5, 0), _xf([0, 0, 0.49]))
+    assert cnt >= 3 and np.allclose(dist[:cnt], -0.01, atol=1e-4)  # base disc 1 cm into the plane
+    assert np.allclose(np.linalg.norm(pos[:cnt, :2], axis=1), 0.5, atol=5e-3)  # manifold points on the base rim
+    cnt, dist, _, n = oracle_lib.convex_pair(GeoType.PLANE, (0, 0, 0), I7, GeoType.CONE, (0.5, 0.5, 0), _xf([0, 0, 0.3], (0, s, 0, s)))
+    assert cnt >= 1 and dist[0] == pytest.approx(-0.2, abs=1e-3)  # axis horizontal: the base rim reaches 0.5 below the centre
