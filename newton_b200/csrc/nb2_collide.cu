@@ -251,8 +251,10 @@ NB2_DEV void shape_aabb(int type, V3 scale, const Xf& X, float gap_eff, float co
         V3 r0 = qrot(X.q, V3(1.f, 0.f, 0.f)), r1 = qrot(X.q, V3(0.f, 1.f, 0.f)), r2 = qrot(X.q, V3(0.f, 0.f, 1.f));
         he = V3(radius * sqrtf(r0.x * r0.x + r1.x * r1.x) + hh * fabsf(r2.x), radius * sqrtf(r0.y * r0.y + r1.y * r1.y) + hh * fabsf(r2.y),
                 radius * sqrtf(r0.z * r0.z + r1.z * r1.z) + hh * fabsf(r2.z));
-    } else if (type == GEO_CONE) {  // generic branch of compute_shape_aabbs: tight AABB from the support map
-        tight_aabb_from_support(ConvexGeom{CG_CONE, scale}, X.q, pos, lo, hi);
+    } else if (type == GEO_CONE || type == GEO_PLANE) {  // generic branch of compute_shape_aabbs: tight AABB from the support map
+        // (finite planes: geom_scale holds HALF extents, collide.py:452-453)
+        const ConvexGeom g{type, type == GEO_PLANE ? V3(scale.x * 0.5f, scale.y * 0.5f, 0.0f) : scale};
+        tight_aabb_from_support(g, X.q, pos, lo, hi);
         lo = lo - mvv;
         hi = hi + mvv;
         return;

@@ -323,10 +323,12 @@ inline void compute_shape_aabbs(const nb2_model_desc& m, const float* body_q, st
                     radius * std::sqrt(r0.z * r0.z + r1.z * r1.z) + half_height * std::fabs(r2.z));
             lo = pos - he - margin_vec;
             hi = pos + he + margin_vec;
-        } else if (geo_type == GEO_CONE) {
-            // generic branch (collide.py:447-468): compute_tight_aabb_from_support, single-source with the CUDA build
+        } else if (geo_type == GEO_CONE || geo_type == GEO_PLANE) {
+            // generic branch (collide.py:447-468): compute_tight_aabb_from_support, single-source with the CUDA build;
+            // finite planes carry HALF extents in geom_scale (collide.py:452-453)
+            if (geo_type == GEO_PLANE) geom_scale = vec3(scale.x * 0.5f, scale.y * 0.5f, 0.0f);
             nb2::V3 l, h;
-            nb2::tight_aabb_from_support(nb2::ConvexGeom{nb2::CG_CONE, nb2::V3(scale.x, scale.y, scale.z)},
+            nb2::tight_aabb_from_support(nb2::ConvexGeom{geo_type, nb2::V3(geom_scale.x, geom_scale.y, geom_scale.z)},
                                          nb2::Q4(orientation.x, orientation.y, orientation.z, orientation.w), nb2::V3(pos.x, pos.y, pos.z), l, h);
             lo = vec3(l.x, l.y, l.z) - margin_vec;
             hi = vec3(h.x, h.y, h.z) + margin_vec;

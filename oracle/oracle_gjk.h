@@ -57,7 +57,9 @@ inline void gjk_mpr_pairs(const nb2_model_desc& m, const float* body_q, CollideR
         float dist[5], ra, rb;
         vec3 pos[5], normal[5];
         const float gap_sum = m.shape_gap[shape_a] + m.shape_gap[shape_b];
-        int cnt = convex_pair(m.shape_type[shape_a], A.scale, A.X_ws, A.margin, m.shape_type[shape_b], B.scale, B.X_ws, B.margin, gap_sum,
+        // raw model scales: convex_contacts_any applies the geom_data halving of finite planes itself
+        int cnt = convex_pair(m.shape_type[shape_a], load3(m.shape_scale + 3 * shape_a), A.X_ws, A.margin, m.shape_type[shape_b],
+                              load3(m.shape_scale + 3 * shape_b), B.X_ws, B.margin, gap_sum,
                               dist, pos, normal, ra, rb, A.aabb_lower, A.aabb_upper, B.aabb_lower, B.aabb_upper);
         for (int i = 0; i < cnt; ++i) {
             RawContact rc;

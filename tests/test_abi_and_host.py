@@ -159,3 +159,25 @@ def test_oracle_eval_ik_inverts_eval_fk(oracle_lib):
         oracle_lib.eval_ik(model, model, q, qd)
         np.testing.assert_allclose(q.numpy(), model.joint_q.numpy(), atol=1e-6)
         np.testing.assert_allclose(qd.numpy(), model.joint_qd.numpy(), atol=1e-6)
+
+
+def test_oracle_aabbs_of_finite_plane_and_cone(oracle_lib):
+    """compute_shape_aabbs' generic branch (collide.py:447-468, tight AABB from the support map): a tilted finite plane
+    (width 4, length 2 -> half extents 2 x 1) and a cone, each expanded by margin + gap."""
+    from newton_b200.sim.builder import ModelBuilder
+    from newton_b200.utils import xform as X
+
+    b = ModelBuilder()
+    rot = X.quat_from_axis_angle((1.0, 0.0, 0.0), 0.3)
+    b.add_shape_plane(body=-1, xform=X.transform((1.0, 2.0, 0.5), rot), width=4.0, length=2.0)
+    body = b.add_body(xform=X.transform((0.0, 0.0, 1.0)))
+    b.add_shape_cone(body, radius=0.3, half_height=0.4)
+    model = b.finalize()
+    lo, hi = oracle_lib.shape_aabbs(model, model.body_q)
+    g = float(model.shape_gap[0] + model.shape_margin[0])
+    corners = np.array([[sx * 2.0, sy * 1.0, 0.0] for sx in (-1, 1) for sy in (-1, 1)]) @ X.quat_to_matrix(rot).T + np.array([1.0, 2.0, 0.5])
+    np.testing.assert_allclose(lo[0], corners.min(0) - g, atol=1e-5)
+    np.testing.assert_allclose(hi[0], corners.max(0) + g, atol=1e-5)
+    g = float(model.shape_gap[1] + model.shape_margin[1])
+    np.testing.assert_allclose(lo[1], [-0.3 - g, -0.3 - g, 0.6 - g], atol=1e-5)
+    np.testing.assert_allclose(hi[1], [0.3 + g, 0.3 + g, 1.4 + g], atol=1e-5)
