@@ -242,3 +242,24 @@ def mixed_worlds_model(repeats: int = 2, device="cpu", seed: int | None = 9):
         scene.end_world()
     scene.add_ground_plane()
     return _finish(scene, device)
+
+
+def platform_model(world_count: int = 1, device="cpu"):
+    """A finite plane (2 x 2 platform at z = 0.5) over the ground: one sphere and one cone land on the platform, a second
+    sphere starts beyond the platform's extent - its AABB never overlaps the finite plane's tight AABB - and falls to the
+    ground; a capsule leans on the platform edge region.  Exercises finite-plane AABBs, plane-cone (box proxy) and cones."""
+    scene = ModelBuilder()
+    for w in range(world_count):
+        scene.begin_world()
+        scene.add_shape_plane(body=-1, xform=X.transform((0.0, 0.0, 0.5)), width=2.0, length=2.0)
+        b = scene.add_body(xform=X.transform((0.2 + 0.01 * w, 0.1, 0.9)))
+        scene.add_shape_sphere(b, radius=0.2)
+        b = scene.add_body(xform=X.transform((2.5, 0.0, 0.9)))
+        scene.add_shape_sphere(b, radius=0.2)
+        b = scene.add_body(xform=X.transform((-0.4, -0.3, 0.95), X.quat_from_axis_angle((1.0, 0.0, 0.0), 0.2 + 0.05 * w)))
+        scene.add_shape_cone(b, radius=0.25, half_height=0.3)
+        b = scene.add_body(xform=X.transform((0.3, -0.6, 1.0), X.quat_from_axis_angle((0.0, 1.0, 0.0), 1.2)))
+        scene.add_shape_capsule(b, radius=0.1, half_height=0.3)
+        scene.end_world()
+    scene.add_ground_plane()
+    return _finish(scene, device)

@@ -422,3 +422,13 @@ def test_deterministic_export_matches_reference_order(oracle_lib, cuda_lib):
                                           getattr(oc, "rigid_contact_" + name)[:n].numpy(), err_msg=name)
         np.testing.assert_array_equal(gc.force[:n].cpu().numpy(), oc.force[:n].numpy())
         np.testing.assert_array_equal(g0.body_q.cpu().numpy(), o0.body_q.numpy())
+
+
+def test_finite_plane_platform_bit_exact(oracle_lib, cuda_lib):
+    """Finite plane with tight support AABB (a sphere beyond its extent falls past it), plane-cone through the box proxy,
+    per-world static shapes."""
+    model = scenes.platform_model(3)
+    out = _both(model, 240, 1.0 / 240, {"iterations": 4}, oracle_lib)
+    _assert_exact(*out, model)
+    z = out[3].body_q.cpu().numpy().reshape(3, 4, 7)[:, :, 2]
+    assert np.all(np.abs(z[:, 0] - 0.7) < 0.02) and np.all(np.abs(z[:, 1] - 0.2) < 0.02)  # on the platform / on the ground
