@@ -9,9 +9,9 @@
 //   build_manifold / polygon clipping / rotating calipers    geometry/multicontact.py:27-958
 //   post_process_axial_on_discrete_contact                   geometry/collision_core.py:174-277
 //
-// SINGLE SOURCE: this header compiles for the device (libnewton_b200.so) and, with g++ -ffp-contract=off, for the
-// host, where the CPU oracle uses it for the same rows (DESIGN.md §5 explains why this ~900-line branchy routine is
-// not restated twice and how it is pinned: the reference's box-box / GJK / MPR known-answer tests).
+// HOST + DEVICE: this header compiles for the device (libnewton_b200.so) and, with g++ -ffp-contract=off, for the
+// host.  The host compilation exists only for tests/test_oracle_convex_independence.py, which compares it bit for bit with
+// the oracle's own, separately written restatement (oracle/oracle_convex.h); nothing in the product runs it on the CPU.
 #pragma once
 #include "nb2_math.cuh"
 

@@ -12,8 +12,9 @@
 #define NB2_DEV __host__ __device__ __forceinline__
 #define NB2_CALL __host__ __device__ __noinline__  // one shared copy of a big routine (code size matters for 1-warp CTAs)
 #else
-// Host-only compilation (g++): lets the CPU oracle compile the single-source convex-contact routines of
-// nb2_convex.cuh with -ffp-contract=off, i.e. the arithmetic of the strict-fp CUDA build.
+// Host-only compilation (g++): lets the test suite compile the convex-contact routines of nb2_convex.cuh
+//  with -ffp-contract=off, i.e. the arithmetic of the strict-fp CUDA build, and compare them
+// with the oracle's own restatement on the CPU.
 #include <cmath>
 #define NB2_DEV inline
 #define NB2_CALL inline

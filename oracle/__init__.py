@@ -185,8 +185,14 @@ def primitive_pair(type_a, scale_a, xform_a, type_b, scale_b, xform_b, plane_box
     return bool(ok), dist, pos, n
 
 
-def convex_pair(type_a, scale_a, xform_a, type_b, scale_b, xform_b, gap_sum=0.2):
-    """GJK/MPR + manifold for one convex pair: returns (count, dist[5], pos[5,3], normal[5,3])."""
+IMPLS = {"oracle": 0, "product_host": 1}
+
+
+def convex_pair(type_a, scale_a, xform_a, type_b, scale_b, xform_b, gap_sum=0.2, impl="oracle", margin_a=0.0, margin_b=0.0):
+    """GJK/MPR + manifold for one convex pair: returns (count, dist[5], pos[5,3], normal[5,3]).
+
+    ``impl``: "oracle" = oracle_convex.h (the oracle's own restatement), "product_host" = the product's
+    nb2_convex.cuh compiled for the host (only for the bit-equality test between the two)."""
     sa = np.asarray(scale_a, dtype=np.float32)
     sb = np.asarray(scale_b, dtype=np.float32)
     xa = np.asarray(xform_a, dtype=np.float32)
@@ -197,7 +203,7 @@ def convex_pair(type_a, scale_a, xform_a, type_b, scale_b, xform_b, gap_sum=0.2)
     cnt = lib().orc_convex_pair(
         int(type_a), C.c_void_p(sa.ctypes.data), C.c_void_p(xa.ctypes.data), int(type_b), C.c_void_p(sb.ctypes.data),
         C.c_void_p(xb.ctypes.data), C.c_float(gap_sum), C.c_void_p(dist.ctypes.data), C.c_void_p(pos.ctypes.data),
-        C.c_void_p(n.ctypes.data),
+        C.c_void_p(n.ctypes.data), C.c_int(IMPLS[impl]), C.c_float(margin_a), C.c_float(margin_b),
     )
     return cnt, dist, pos, n
 
@@ -206,31 +212,40 @@ def _f32(a):
     return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
 
 
-def mpr_core(type_a, scale_a, type_b, scale_b, pos_b, quat_b, extend=0.0):
+def mpr_core(type_a, scale_a, type_b, scale_b, pos_b, quat_b, extend=0.0, impl="oracle"):
     """solve_mpr_core in A's frame: returns (collision, point_a, point_b, normal, penetration)."""
     sa, sb, pb, qb = _f32(scale_a), _f32(scale_b), _f32(pos_b), _f32(quat_b)
     out = np.zeros(10, dtype=np.float32)
     hit = lib().orc_mpr_core(int(type_a), C.c_void_p(sa.ctypes.data), int(type_b), C.c_void_p(sb.ctypes.data),
                              C.c_void_p(pb.ctypes.data), C.c_void_p(qb.ctypes.data), C.c_float(extend),
-                             C.c_void_p(out.ctypes.data))
+                             C.c_void_p(out.ctypes.data), C.c_int(IMPLS[impl]))
     return hit, out[0:3], out[3:6], out[6:9], float(out[9])
 
 
-def gjk_core(type_a, scale_a, type_b, scale_b, pos_b, quat_b, extend=0.0, eps=1e-4):
+def gjk_core(type_a, scale_a, type_b, scale_b, pos_b, quat_b, extend=0.0, eps=1e-4, impl="oracle"):
     """solve_closest_distance_core in A's frame: returns (separated, point_a, point_b, normal, distance)."""
     sa, sb, pb, qb = _f32(scale_a), _f32(scale_b), _f32(pos_b), _f32(quat_b)
     out = np.zeros(10, dtype=np.float32)
     sep = lib().orc_gjk_core(int(type_a), C.c_void_p(sa.ctypes.data), int(type_b), C.c_void_p(sb.ctypes.data),
                              C.c_void_p(pb.ctypes.data), C.c_void_p(qb.ctypes.data), C.c_float(extend), C.c_float(eps),
-                             C.c_void_p(out.ctypes.data))
+                             C.c_void_p(out.ctypes.data), C.c_int(IMPLS[impl]))
     return sep, out[0:3], out[3:6], out[6:9], float(out[9])
 
 
-def support_map(geo_type, scale, direction):
+def support_map(geo_type, scale, direction, impl="oracle"):
     s, d = _f32(scale), _f32(direction)
     out = np.zeros(3, dtype=np.float32)
-    lib().orc_support_map(int(geo_type), C.c_void_p(s.ctypes.data), C.c_void_p(d.ctypes.data), C.c_void_p(out.ctypes.data))
+    lib().orc_support_map(int(geo_type), C.c_void_p(s.ctypes.data), C.c_void_p(d.ctypes.data), C.c_void_p(out.ctypes.data),
+                          C.c_int(IMPLS[impl]))
     return out
+
+
+def tight_aabb(geo_type, scale, xform, impl="oracle"):
+    """compute_tight_aabb_from_support (collision_core.py:454-548): returns (lower, upper)."""
+    s, x = _f32(scale), _f32(xform)
+    out = np.zeros(6, dtype=np.float32)
+    lib().orc_tight_aabb(int(geo_type), C.c_void_p(s.ctypes.data), C.c_void_p(x.ctypes.data), C.c_void_p(out.ctypes.data), C.c_int(IMPLS[impl]))
+    return out[:3], out[3:]
 
 
 def eval_fk(model, joint_q, joint_qd, state):

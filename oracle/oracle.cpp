@@ -219,25 +219,41 @@ void orc_compute_shape_aabbs(const nb2_model_desc* m, const float* body_q, float
 
 // Convex pair through MPR/GJK + manifold (oracle_gjk.h): returns contact count, fills up to 5 contacts.
 int orc_convex_pair(int type_a, const float* scale_a, const float* xform_a, int type_b, const float* scale_b,
-                    const float* xform_b, float gap_sum, float* dist5, float* pos15, float* normal15) {
+                    const float* xform_b, float gap_sum, float* dist5, float* pos15, float* normal15, int impl, float margin_a, float margin_b) {
     return convex_pair_test(type_a, load3(scale_a), transform::load(xform_a), type_b, load3(scale_b),
-                            transform::load(xform_b), gap_sum, dist5, pos15, normal15);
+                            transform::load(xform_b), gap_sum, dist5, pos15, normal15, impl, margin_a, margin_b);
 }
 
 // A-frame MPR / GJK cores and the support map, for the reference's direct solver tests (test_mpr.py, test_gjk.py).
 // out10 = point_a(3) point_b(3) normal(3) penetration|distance.  B's pose is relative to A.
 int orc_mpr_core(int type_a, const float* scale_a, int type_b, const float* scale_b, const float* pos_b, const float* quat_b, float extend,
-                 float* out10) {
+                 float* out10, int impl) {
     return mpr_core_test(type_a, load3(scale_a), type_b, load3(scale_b), load3(pos_b), quat(quat_b[0], quat_b[1], quat_b[2], quat_b[3]),
-                         extend, out10);
+                         extend, out10, impl);
 }
 int orc_gjk_core(int type_a, const float* scale_a, int type_b, const float* scale_b, const float* pos_b, const float* quat_b, float extend,
-                 float eps, float* out10) {
+                 float eps, float* out10, int impl) {
     return gjk_core_test(type_a, load3(scale_a), type_b, load3(scale_b), load3(pos_b), quat(quat_b[0], quat_b[1], quat_b[2], quat_b[3]),
-                         extend, eps, out10);
+                         extend, eps, out10, impl);
 }
-void orc_support_map(int type, const float* scale, const float* dir, float* out3) {
-    store3(out3, support_map_test(type, load3(scale), load3(dir)));
+void orc_support_map(int type, const float* scale, const float* dir, float* out3, int impl) {
+    store3(out3, support_map_test(type, load3(scale), load3(dir), impl));
+}
+
+// compute_tight_aabb_from_support for one shape: out6 = lower(3) upper(3); impl 0 = oracle_convex.h, 1 = nb2_convex.cuh on the host
+void orc_tight_aabb(int type, const float* scale, const float* xform, float* out6, int impl) {
+    transform X = transform::load(xform);
+    vec3 lo, hi;
+    if (impl == 0) {
+        cvx::compute_tight_aabb_from_support(cvx_geom(type, load3(scale)), X.q, X.p, lo, hi);
+    } else {
+        nb2::V3 l, h;
+        nb2::tight_aabb_from_support(nb2::ConvexGeom{type, to_nb2(load3(scale))}, nb2::Q4(X.q.x, X.q.y, X.q.z, X.q.w), to_nb2(X.p), l, h);
+        lo = from_nb2(l);
+        hi = from_nb2(h);
+    }
+    store3(out6, lo);
+    store3(out6 + 3, hi);
 }
 
 // newton.eval_fk(model, joint_q, joint_qd, state)

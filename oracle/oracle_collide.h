@@ -7,7 +7,7 @@
 //   write_contact                  reference sim/collide.py:166-254
 //   deterministic sort key         reference geometry/contact_data.py:59-87
 #pragma once
-#include "../newton_b200/csrc/nb2_convex.cuh"  // single-source support maps (cone AABB), see oracle_gjk.h
+#include "oracle_convex.h"  // support maps for the generic AABB branch
 #include <algorithm>
 #include <vector>
 
@@ -324,14 +324,16 @@ inline void compute_shape_aabbs(const nb2_model_desc& m, const float* body_q, st
             lo = pos - he - margin_vec;
             hi = pos + he + margin_vec;
         } else if (geo_type == GEO_CONE || geo_type == GEO_PLANE) {
-            // generic branch (collide.py:447-468): compute_tight_aabb_from_support, single-source with the CUDA build;
+            // generic branch (collide.py:447-468): compute_tight_aabb_from_support;
             // finite planes carry HALF extents in geom_scale (collide.py:452-453)
             if (geo_type == GEO_PLANE) geom_scale = vec3(scale.x * 0.5f, scale.y * 0.5f, 0.0f);
-            nb2::V3 l, h;
-            nb2::tight_aabb_from_support(nb2::ConvexGeom{geo_type, nb2::V3(geom_scale.x, geom_scale.y, geom_scale.z)},
-                                         nb2::Q4(orientation.x, orientation.y, orientation.z, orientation.w), nb2::V3(pos.x, pos.y, pos.z), l, h);
-            lo = vec3(l.x, l.y, l.z) - margin_vec;
-            hi = vec3(h.x, h.y, h.z) + margin_vec;
+            cvx::GenericShapeData sd;
+            sd.shape_type = geo_type;
+            sd.scale = geom_scale;
+            vec3 l, h;
+            cvx::compute_tight_aabb_from_support(sd, orientation, pos, l, h);
+            lo = l - margin_vec;
+            hi = h + margin_vec;
         } else if (geo_type == GEO_ELLIPSOID) {
             // tight AABB from the support map (collide.py:447-468): extent_i = |R_i * diag(scale)|
             mat33 R = quat_to_matrix(orientation);

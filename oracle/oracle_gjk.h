@@ -2,18 +2,18 @@
 //
 // Generic convex-convex contacts (MPR / GJK + manifold; reference geometry/narrow_phase.py:1041-1216,
 // collision_core.py:337-450, collision_convex.py:107-231, mpr.py:188-403, simplex_solver.py:322-495,
-// multicontact.py:779-956).
+// multicontact.py:779-956) as the oracle's collide pipeline runs them.
 //
-// SINGLE SOURCE: unlike the rest of the oracle, these ~900 lines are NOT restated a second time.  The routine is
-// written once as host+device code in newton_b200/csrc/nb2_convex.cuh and compiled here by g++ with
-// -ffp-contract=off (the strict-fp arithmetic of the product build).  Consequently GPU-vs-oracle equality on these
-// rows only proves that the device compilation computes what the host compilation does; that the algorithm is the
-// reference's is pinned separately by the reference's own known answers for this path
-// (tests/test_oracle_known_answers.py: box-box face / edge / separated cases from
-// newton/tests/test_collision_primitives.py + test_narrow_phase.py, 5-box stack from test_solver_xpbd.py).
+// TWO implementations are reachable from here:
+//   impl 0 (default, what orc_collide uses): oracle_convex.h, the oracle's own restatement written from the reference;
+//   impl 1: the PRODUCT's host+device routine newton_b200/csrc/nb2_convex.cuh compiled by g++ with -ffp-contract=off.
+// tests/test_oracle_known_answers.py pins impl 0 with the reference's known answers; tests/test_abi_and_host.py checks
+// impl 0 == impl 1 bit for bit on randomised pairs of every shape-type combination (CPU only), and the GPU parity
+// tests compare the CUDA compilation with impl 0.
 #pragma once
 #include "../newton_b200/csrc/nb2_convex.cuh"
 #include "oracle_collide.h"
+#include "oracle_convex.h"
 namespace orc {
 
 inline nb2::V3 to_nb2(vec3 v) { return nb2::V3(v.x, v.y, v.z); }
@@ -23,8 +23,18 @@ inline nb2::Xf to_nb2(const transform& t) { return nb2::Xf(to_nb2(t.p), nb2::Q4(
 // One pair through compute_gjk_mpr_contacts; contacts come back already gap-tested, in sort_sub_key order.
 inline int convex_pair(int type_a, vec3 scale_a, const transform& Xa, float margin_a, int type_b, vec3 scale_b, const transform& Xb,
                        float margin_b, float gap_sum, float* dist, vec3* pos, vec3* normal, float& reff_a, float& reff_b,
-                       vec3 lo_a = vec3(), vec3 hi_a = vec3(), vec3 lo_b = vec3(), vec3 hi_b = vec3()) {
+                       vec3 lo_a = vec3(), vec3 hi_a = vec3(), vec3 lo_b = vec3(), vec3 hi_b = vec3(), int impl = 0) {
     reff_a = reff_b = 0.0f;
+    if (impl == 0) {
+        cvx::ContactOut out[5];
+        int cnt = cvx::gjk_mpr_pair(type_a, scale_a, Xa, margin_a, lo_a, hi_a, type_b, scale_b, Xb, margin_b, lo_b, hi_b, gap_sum, out, reff_a, reff_b);
+        for (int i = 0; i < cnt; ++i) {
+            dist[i] = out[i].distance;
+            pos[i] = out[i].center;
+            normal[i] = out[i].normal;
+        }
+        return cnt;
+    }
     nb2::ConvexPairIn in;
     in.type_a = type_a;
     in.type_b = type_b;
@@ -71,7 +81,19 @@ inline void gjk_mpr_pairs(const nb2_model_desc& m, const float* body_q, CollideR
 }
 
 // Direct solver cores in A's frame (what newton/tests/test_mpr.py and test_gjk.py launch).
-inline int mpr_core_test(int type_a, vec3 scale_a, int type_b, vec3 scale_b, vec3 pos_b, quat quat_b, float extend, float* out11) {
+inline cvx::GenericShapeData cvx_geom(int type, vec3 scale) {
+    cvx::GenericShapeData g;
+    g.shape_type = type;
+    g.scale = scale;
+    return g;
+}
+inline int mpr_core_test(int type_a, vec3 scale_a, int type_b, vec3 scale_b, vec3 pos_b, quat quat_b, float extend, float* out11, int impl = 0) {
+    if (impl == 0) {
+        cvx::MprResult r = cvx::solve_mpr_core(cvx_geom(type_a, scale_a), cvx_geom(type_b, scale_b), quat_b, pos_b, extend);
+        const float o[10] = {r.point_a.x, r.point_a.y, r.point_a.z, r.point_b.x, r.point_b.y, r.point_b.z, r.normal.x, r.normal.y, r.normal.z, r.penetration};
+        for (int i = 0; i < 10; ++i) out11[i] = o[i];
+        return r.collision ? 1 : 0;
+    }
     nb2::ConvexGeom ga{type_a, to_nb2(scale_a)}, gb{type_b, to_nb2(scale_b)};
     nb2::V3 pa, pb, n;
     float pen;
@@ -81,7 +103,13 @@ inline int mpr_core_test(int type_a, vec3 scale_a, int type_b, vec3 scale_b, vec
     return hit ? 1 : 0;
 }
 inline int gjk_core_test(int type_a, vec3 scale_a, int type_b, vec3 scale_b, vec3 pos_b, quat quat_b, float extend, float eps,
-                         float* out11) {
+                         float* out11, int impl = 0) {
+    if (impl == 0) {
+        cvx::GjkResult r = cvx::solve_closest_distance_core(cvx_geom(type_a, scale_a), cvx_geom(type_b, scale_b), quat_b, pos_b, extend, 30, eps);
+        const float o[10] = {r.point_a.x, r.point_a.y, r.point_a.z, r.point_b.x, r.point_b.y, r.point_b.z, r.normal.x, r.normal.y, r.normal.z, r.distance};
+        for (int i = 0; i < 10; ++i) out11[i] = o[i];
+        return r.separated ? 1 : 0;
+    }
     nb2::ConvexGeom ga{type_a, to_nb2(scale_a)}, gb{type_b, to_nb2(scale_b)};
     nb2::V3 pa, pb, n;
     float dist;
@@ -90,10 +118,13 @@ inline int gjk_core_test(int type_a, vec3 scale_a, int type_b, vec3 scale_b, vec
     for (int i = 0; i < 10; ++i) out11[i] = o[i];
     return separated ? 1 : 0;
 }
-inline vec3 support_map_test(int type, vec3 scale, vec3 dir) { return from_nb2(nb2::support_map(nb2::ConvexGeom{type, to_nb2(scale)}, to_nb2(dir))); }
+inline vec3 support_map_test(int type, vec3 scale, vec3 dir, int impl = 0) {
+    if (impl == 0) return cvx::support_map(cvx_geom(type, scale), dir);
+    return from_nb2(nb2::support_map(nb2::ConvexGeom{type, to_nb2(scale)}, to_nb2(dir)));
+}
 
 inline int convex_pair_test(int type_a, vec3 scale_a, const transform& Xa, int type_b, vec3 scale_b, const transform& Xb, float gap_sum,
-                            float* dist5, float* pos15, float* normal15) {
+                            float* dist5, float* pos15, float* normal15, int impl = 0, float margin_a = 0.0f, float margin_b = 0.0f) {
     float ra, rb;
     vec3 pos[5], normal[5];
     // AABBs as the stand-alone NarrowPhase computes them (narrow_phase.py:1120-1150): tight support AABB +- the shape's gap;
@@ -104,16 +135,16 @@ inline int convex_pair_test(int type_a, vec3 scale_a, const transform& Xa, int t
             hi = X.p + vec3(1.0e6f);
             return;
         }
-        nb2::V3 l, h;
-        nb2::tight_aabb_from_support(nb2::ConvexGeom{type, to_nb2(scale)}, nb2::Q4(X.q.x, X.q.y, X.q.z, X.q.w), to_nb2(X.p), l, h);
+        vec3 l, h;
+        cvx::compute_tight_aabb_from_support(cvx_geom(type, scale), X.q, X.p, l, h);
         const vec3 g(0.5f * gap_sum);
-        lo = from_nb2(l) - g;
-        hi = from_nb2(h) + g;
+        lo = l - g;
+        hi = h + g;
     };
     vec3 lo_a, hi_a, lo_b, hi_b;
     aabb(type_a, scale_a, Xa, lo_a, hi_a);
     aabb(type_b, scale_b, Xb, lo_b, hi_b);
-    int cnt = convex_pair(type_a, scale_a, Xa, 0.0f, type_b, scale_b, Xb, 0.0f, gap_sum, dist5, pos, normal, ra, rb, lo_a, hi_a, lo_b, hi_b);
+    int cnt = convex_pair(type_a, scale_a, Xa, margin_a, type_b, scale_b, Xb, margin_b, gap_sum, dist5, pos, normal, ra, rb, lo_a, hi_a, lo_b, hi_b, impl);
     for (int i = 0; i < cnt; ++i) {
         store3(pos15 + 3 * i, pos[i]);
         store3(normal15 + 3 * i, normal[i]);
