@@ -247,6 +247,43 @@ nb2_status nb2_eval_fk(nb2_model* model, const float* joint_q, const float* join
 nb2_status nb2_eval_ik(nb2_model* model, const float* body_q, const float* body_qd, float* joint_q, float* joint_qd,
                        void* cuda_stream);
 
+/* Reference newton.eval_fk(model, joint_q, joint_qd, state, mask=..., indices=...) (sim/articulation.py:420-475, 500-574):
+ * `articulation_mask` ([articulation_count] bytes, 0 = skip) and `articulation_indices` ([index_count] int32; entries outside
+ * [0, articulation_count) are ignored) may each be NULL; the reference rejects passing both and so does this call. */
+nb2_status nb2_eval_fk_masked(nb2_model* model, const float* joint_q, const float* joint_qd, float* body_q, float* body_qd,
+                              const uint8_t* articulation_mask, const int32_t* articulation_indices, int32_t index_count,
+                              void* cuda_stream);
+
+/* --- ArticulationView attribute access -------------------------------------------------------
+ * Reference newton.selection.ArticulationView (utils/selection.py): `_get_attribute_array` (:1232-1357) views an attribute
+ * array as [world, articulation, value, trailing...] through an offset and two strides; `_get_attribute_values`
+ * (:1359-1378) gathers index-selected values into a contiguous staging array (`_gather_indexed_{3,4}d_kernel` :185-203);
+ * `_set_attribute_values` (:1380-1439) writes values under a per-world or per-(world, articulation) mask
+ * (`set_articulation_attribute_{3,4}d[_per_world]_kernel` :85-152).  The layout counts VALUES (one transform, one float ...);
+ * `row_words` is the number of 32-bit words per value, so float / int32 / vec3 / transform / spatial_vector / int[2] ...
+ * attributes all go through the same word-copy kernels.  A view addresses the words
+ *     attrib[(offset + w*stride_between_worlds + a*stride_within_worlds + sel(k)) * row_words + t],
+ *     sel(k) = indices ? indices[k] : slice_start + k,   w < world_count, a < count_per_world, k < value_count, t < row_words
+ * and `values` is the contiguous [world_count, count_per_world, value_count, row_words] array. */
+typedef struct nb2_view_layout {
+    int32_t world_count, count_per_world, value_count, row_words;
+    int32_t offset, stride_between_worlds, stride_within_worlds, slice_start;
+    const int32_t* indices; /* device pointer, [value_count] values relative to the articulation's first value, or NULL */
+} nb2_view_layout;
+
+/* values[w, a, k, :] = attrib[view(w, a, k), :]   (reference selection.py:1359-1378) */
+nb2_status nb2_view_gather(const void* attrib, const nb2_view_layout* layout, void* values, void* cuda_stream);
+/* attrib[view(w, a, k), :] = values[w, a, k, :] where the mask selects (w, a): mask_ndim 0 = everything (mask may be NULL),
+ * 1 = mask[world_count], 2 = mask[world_count, count_per_world]; one byte per entry (reference selection.py:1380-1439) */
+nb2_status nb2_view_scatter(void* attrib, const nb2_view_layout* layout, const void* values, const uint8_t* mask,
+                            int32_t mask_ndim, void* cuda_stream);
+/* Model articulation mask from a view mask: model_mask[0..articulation_count) is cleared, then
+ * model_mask[articulation_ids[w, a]] = 1 where the view mask selects (w, a)
+ * (reference get_model_articulation_mask :1727-1753, set_model_articulation_mask[_per_world]_kernel :35-61). */
+nb2_status nb2_view_articulation_mask(const uint8_t* mask, int32_t mask_ndim, const int32_t* articulation_ids,
+                                      int32_t world_count, int32_t count_per_world, uint8_t* model_mask,
+                                      int32_t articulation_count, void* cuda_stream);
+
 /* --- diagnostics ---------------------------------------------------------------------------- */
 const char* nb2_last_error(void);
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches claim). */

@@ -166,6 +166,22 @@ _COUNT_FIELDS = ("world_count", "body_count", "joint_count", "joint_dof_count", 
                  "articulation_count")
 
 
+class ViewLayout(C.Structure):
+    """``nb2_view_layout`` (include/newton_b200.h): how an ArticulationView addresses an attribute array."""
+
+    _fields_ = [
+        ("world_count", C.c_int32),
+        ("count_per_world", C.c_int32),
+        ("value_count", C.c_int32),
+        ("row_words", C.c_int32),
+        ("offset", C.c_int32),
+        ("stride_between_worlds", C.c_int32),
+        ("stride_within_worlds", C.c_int32),
+        ("slice_start", C.c_int32),
+        ("indices", C.c_void_p),
+    ]
+
+
 def model_desc(model) -> ModelDesc:
     """Fill a :class:`ModelDesc` with the addresses of ``model``'s arrays (borrowed, not copied)."""
     d = ModelDesc()

@@ -19,8 +19,8 @@ STATUS = {0: "NB2_OK", 1: "NB2_ERR_INVALID_ARGUMENT", 2: "NB2_ERR_UNSUPPORTED", 
 # every symbol include/newton_b200.h declares
 EXPORTED_SYMBOLS = (
     "nb2_model_create", "nb2_model_destroy", "nb2_model_notify_changed", "nb2_model_rigid_contact_max", "nb2_collide", "nb2_contacts_sort", "nb2_contacts_import",
-    "nb2_xpbd_step", "nb2_xpbd_update_contacts", "nb2_integrate_bodies", "nb2_featherstone_step", "nb2_eval_fk", "nb2_eval_ik", "nb2_last_error",
-    "nb2_kernel_launch_count", "nb2_version",
+    "nb2_xpbd_step", "nb2_xpbd_update_contacts", "nb2_integrate_bodies", "nb2_featherstone_step", "nb2_eval_fk", "nb2_eval_ik", "nb2_eval_fk_masked",
+    "nb2_view_gather", "nb2_view_scatter", "nb2_view_articulation_mask", "nb2_last_error", "nb2_kernel_launch_count", "nb2_version",
 )
 
 
@@ -67,6 +67,14 @@ def lib():
         L.nb2_eval_fk.restype = C.c_int
         L.nb2_eval_ik.argtypes = [P, P, P, P, P, P]
         L.nb2_eval_ik.restype = C.c_int
+        L.nb2_eval_fk_masked.argtypes = [P, P, P, P, P, P, P, C.c_int32, P]
+        L.nb2_eval_fk_masked.restype = C.c_int
+        L.nb2_view_gather.argtypes = [P, C.POINTER(_abi.ViewLayout), P, P]
+        L.nb2_view_gather.restype = C.c_int
+        L.nb2_view_scatter.argtypes = [P, C.POINTER(_abi.ViewLayout), P, P, C.c_int32, P]
+        L.nb2_view_scatter.restype = C.c_int
+        L.nb2_view_articulation_mask.argtypes = [P, C.c_int32, P, C.c_int32, C.c_int32, P, C.c_int32, P]
+        L.nb2_view_articulation_mask.restype = C.c_int
         L.nb2_last_error.restype = C.c_char_p
         L.nb2_kernel_launch_count.restype = C.c_int64
         L.nb2_version.restype = C.c_char_p

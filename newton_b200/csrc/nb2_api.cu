@@ -501,6 +501,25 @@ nb2_status nb2_eval_fk(nb2_model* model, const float* joint_q, const float* join
     return launch_eval_fk(model, joint_q, joint_qd, body_q, body_qd, static_cast<cudaStream_t>(cuda_stream));
 }
 
+nb2_status nb2_eval_fk_masked(nb2_model* model, const float* joint_q, const float* joint_qd, float* body_q, float* body_qd,
+                              const uint8_t* articulation_mask, const int32_t* articulation_indices, int32_t index_count,
+                              void* cuda_stream) {
+    if (!model || !joint_q || !joint_qd || !body_q || !body_qd) {
+        set_error("nb2_eval_fk_masked: NULL argument");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    if (articulation_mask && articulation_indices) {
+        set_error("nb2_eval_fk_masked: cannot specify both mask and indices");  // sim/articulation.py:529-530
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    if (articulation_indices && index_count < 0) {
+        set_error("nb2_eval_fk_masked: negative index_count");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    return launch_eval_fk(model, joint_q, joint_qd, body_q, body_qd, static_cast<cudaStream_t>(cuda_stream), articulation_mask,
+                          articulation_indices, index_count);
+}
+
 nb2_status nb2_eval_ik(nb2_model* model, const float* body_q, const float* body_qd, float* joint_q, float* joint_qd,
                        void* cuda_stream) {
     if (!model || !body_q || !body_qd || !joint_q || !joint_qd) {

@@ -914,11 +914,16 @@ nb2_status launch_featherstone_step(nb2_model* m, const nb2_featherstone_params&
 // ---- public newton.eval_fk (sim/articulation.py:237-475): one thread walks one articulation in joint order ------------
 // A set-up / reset call (example_basic_urdf.py:87), not part of the substep loop: the serial walk keeps the reference's
 // exact operation order; articulations are independent, so the grid is one thread per articulation.
+// `mask` / `indices` are the reference's optional articulation_mask / articulation_indices (eval_articulation_fk :420-475).
 __global__ void __launch_bounds__(128) eval_fk_kernel(DevModel M, const float* __restrict__ joint_q, const float* __restrict__ joint_qd,
-                                                      float* __restrict__ body_q, float* __restrict__ body_qd) {
+                                                      float* __restrict__ body_q, float* __restrict__ body_qd,
+                                                      const uint8_t* __restrict__ mask, const int* __restrict__ indices, int count) {
     const nb2_model_desc& d = M.d;
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= d.articulation_count) return;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= count) return;
+    const int a = indices ? indices[tid] : tid;
+    if (a < 0 || a >= d.articulation_count) return;
+    if (mask && !mask[a]) return;
     for (int i = d.articulation_start[a]; i < d.articulation_start[a + 1]; ++i) {
         if (d.joint_articulation[i] == -1) continue;
         const int type = d.joint_type[i], parent = d.joint_parent[i], child = d.joint_child[i];
@@ -972,10 +977,11 @@ __global__ void __launch_bounds__(128) eval_fk_kernel(DevModel M, const float* _
     }
 }
 
-nb2_status launch_eval_fk(nb2_model* m, const float* joint_q, const float* joint_qd, float* body_q, float* body_qd, cudaStream_t s) {
-    const int A = m->dev.d.articulation_count;
-    if (A == 0) return NB2_OK;
-    eval_fk_kernel<<<(A + 127) / 128, 128, 0, s>>>(m->dev, joint_q, joint_qd, body_q, body_qd);
+nb2_status launch_eval_fk(nb2_model* m, const float* joint_q, const float* joint_qd, float* body_q, float* body_qd, cudaStream_t s,
+                          const uint8_t* mask, const int* indices, int index_count) {
+    const int A = indices ? index_count : m->dev.d.articulation_count;
+    if (A <= 0 || m->dev.d.articulation_count == 0) return NB2_OK;
+    eval_fk_kernel<<<(A + 127) / 128, 128, 0, s>>>(m->dev, joint_q, joint_qd, body_q, body_qd, mask, indices, A);
     count_launch();
     NB2_CUDA_CHECK(cudaGetLastError());
     return NB2_OK;

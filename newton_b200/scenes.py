@@ -263,3 +263,47 @@ def platform_model(world_count: int = 1, device="cpu"):
         scene.end_world()
     scene.add_ground_plane()
     return _finish(scene, device)
+
+
+def ant_builder(floating: bool = True) -> ModelBuilder:
+    """Ant-class articulation with the topology the reference's selection tests use (``nv_ant.xml`` through
+    ``newton/tests/test_selection.py:253-271``): 9 links, 9 joints (root + 4 x {hip, ankle}), 13 shapes
+    (torso sphere, 3 capsules per leg), 14 dofs / 15 coords with a FREE root, 8 / 8 with a FIXED root.
+    Built from primitives here instead of parsing the MJCF asset."""
+    b = ModelBuilder()
+    b.default_shape_cfg.mu = 1.0
+    inertia = np.eye(3) * 0.01
+    torso = b.add_link(xform=X.transform((0.0, 0.0, 0.75)), mass=1.0, inertia=inertia, label="ant/torso")
+    b.add_shape_sphere(torso, radius=0.25, label="ant/torso_geom")
+    root = (b.add_joint_free(child=torso, label="ant/root") if floating
+            else b.add_joint_fixed(-1, torso, parent_xform=X.transform((0.0, 0.0, 0.75)), label="ant/root"))
+    joints = [root]
+    for k, name in enumerate(("front_left", "front_right", "back_left", "back_right")):
+        ang = math.pi / 4 + k * math.pi / 2
+        d = np.array([math.cos(ang), math.sin(ang), 0.0])
+        rot = X.quat_from_axis_angle(np.array([0.0, 0.0, 1.0]), ang)
+        leg = b.add_link(xform=X.transform(0.28 * d + (0.0, 0.0, 0.75), rot), mass=0.2, inertia=inertia, label=f"ant/{name}_leg")
+        side = X.quat_from_axis_angle(np.array([0.0, 1.0, 0.0]), math.pi / 2)  # capsule axis +Z -> leg's +X
+        b.add_shape_capsule(leg, xform=X.transform((-0.14, 0.0, 0.0), side), radius=0.08, half_height=0.14, label=f"ant/{name}_aux_geom")
+        b.add_shape_capsule(leg, xform=X.transform((0.14, 0.0, 0.0), side), radius=0.08, half_height=0.14, label=f"ant/{name}_leg_geom")
+        foot = b.add_link(xform=X.transform(0.56 * d + (0.0, 0.0, 0.75), rot), mass=0.1, inertia=inertia, label=f"ant/{name}_foot")
+        b.add_shape_capsule(foot, xform=X.transform((0.2, 0.0, 0.0), side), radius=0.08, half_height=0.2, label=f"ant/{name}_ankle_geom")
+        joints.append(b.add_joint_revolute(torso, leg, parent_xform=X.transform(0.28 * d, rot), axis=(0.0, 0.0, 1.0),
+                                           limit_lower=-0.7, limit_upper=0.7, label=f"ant/hip_{k + 1}"))
+        joints.append(b.add_joint_revolute(leg, foot, parent_xform=X.transform((0.28, 0.0, 0.0)), axis=(0.0, 1.0, 0.0),
+                                           limit_lower=0.2, limit_upper=1.2, label=f"ant/ankle_{k + 1}"))
+    b.add_articulation(joints, label="ant")
+    return b
+
+
+def ants_model(world_count: int, per_world: int = 1, floating: bool = True, device="cpu", ground: bool = True):
+    """``world_count`` worlds of ``per_world`` ants each, stacked in z (reference ``test_selection.py:328-335``)."""
+    ant = ant_builder(floating)
+    world = ModelBuilder()
+    for i in range(per_world):
+        world.add_builder(ant, xform=X.transform((0.0, 0.0, 1.0 + 1.5 * i)))
+    scene = ModelBuilder()
+    scene.replicate(world, world_count)
+    if ground:
+        scene.add_ground_plane(cfg=ant.default_shape_cfg)
+    return _finish(scene, device)

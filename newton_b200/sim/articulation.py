@@ -18,11 +18,15 @@ from ..utils import xform as X
 from .enums import JointType
 
 
-def eval_fk(model, joint_q, joint_qd, state) -> None:
-    """Write ``state.body_q`` / ``state.body_qd`` from generalized coordinates.
+def eval_fk(model, joint_q, joint_qd, state, mask=None, indices=None) -> None:
+    """Write ``state.body_q`` / ``state.body_qd`` from generalized coordinates (reference ``sim/articulation.py:500-574``).
 
     ``state`` may be the model itself (as in ``newton.eval_fk(model, model.joint_q, model.joint_qd, model)``).
+    ``mask`` (bool ``[articulation_count]``) or ``indices`` (int ``[n]``) restrict the update to some articulations;
+    bodies of the others keep their values.
     """
+    if mask is not None and indices is not None:
+        raise ValueError("Cannot specify both mask and indices parameters")
     if state.body_q.is_cuda:
         import ctypes as C
 
@@ -31,14 +35,32 @@ def eval_fk(model, joint_q, joint_qd, state) -> None:
         nm = _lib.native_model(model)
         jq = joint_q.contiguous()
         jqd = joint_qd.contiguous()
+        if mask is not None:
+            if mask.dtype != torch.bool or mask.numel() != model.articulation_count:
+                raise ValueError(f"Expected Boolean mask with shape ({model.articulation_count},)")
+            mask = mask.contiguous()
+        if indices is not None:
+            indices = torch.as_tensor(indices, dtype=torch.int32, device=state.body_q.device).contiguous()
         with torch.cuda.device(nm.device_index):
-            _lib.check(
-                _lib.lib().nb2_eval_fk(nm.handle, C.c_void_p(_abi.ptr(jq)), C.c_void_p(_abi.ptr(jqd)),
-                                       C.c_void_p(_abi.ptr(state.body_q)), C.c_void_p(_abi.ptr(state.body_qd)),
-                                       _lib.current_stream_ptr(model)),
-                "nb2_eval_fk",
-            )
+            if mask is None and indices is None:
+                st = _lib.lib().nb2_eval_fk(nm.handle, C.c_void_p(_abi.ptr(jq)), C.c_void_p(_abi.ptr(jqd)),
+                                            C.c_void_p(_abi.ptr(state.body_q)), C.c_void_p(_abi.ptr(state.body_qd)),
+                                            _lib.current_stream_ptr(model))
+            else:
+                st = _lib.lib().nb2_eval_fk_masked(
+                    nm.handle, C.c_void_p(_abi.ptr(jq)), C.c_void_p(_abi.ptr(jqd)), C.c_void_p(_abi.ptr(state.body_q)),
+                    C.c_void_p(_abi.ptr(state.body_qd)), C.c_void_p(None if mask is None else mask.data_ptr()),
+                    C.c_void_p(None if indices is None else indices.data_ptr()), 0 if indices is None else indices.numel(),
+                    _lib.current_stream_ptr(model))
+            _lib.check(st, "nb2_eval_fk")
         return
+    enabled = None
+    if mask is not None:
+        enabled = np.asarray(mask.detach().cpu().numpy(), dtype=bool)
+    elif indices is not None:
+        enabled = np.zeros(model.articulation_count, dtype=bool)
+        ids = np.asarray(torch.as_tensor(indices).cpu().numpy(), dtype=np.int64)
+        enabled[ids[(ids >= 0) & (ids < model.articulation_count)]] = True
     q = joint_q.detach().cpu().numpy().astype(np.float64)
     qd = joint_qd.detach().cpu().numpy().astype(np.float64)
     jt = model.numpy("joint_type")
@@ -56,7 +78,7 @@ def eval_fk(model, joint_q, joint_qd, state) -> None:
     body_qd = state.body_qd.detach().cpu().numpy().astype(np.float64)
 
     for i in range(model.joint_count):
-        if art[i] == -1:
+        if art[i] == -1 or (enabled is not None and not enabled[art[i]]):
             continue
         t = jt[i]
         Xj = X.transform_identity()

@@ -836,6 +836,8 @@ class ModelBuilder:
         m.joint_dof_count, m.joint_coord_count = self.joint_dof_count, self.joint_coord_count
         m.articulation_count = self.articulation_count
         m.body_label, m.joint_label, m.shape_label = list(self.body_label), list(self.joint_label), list(self.shape_label)
+        m.articulation_label = list(self.articulation_label)
+        m.body_shapes = {b: list(s) for b, s in self.body_shapes.items()}
 
         def arr(values, trailing, dtype):
             np_dtype = {F32: np.float32, I32: np.int32, torch.bool: np.bool_}[dtype]

@@ -18,6 +18,8 @@ any object exposing the same attributes whose arrays provide ``data_ptr()`` or `
 
 from __future__ import annotations
 
+import enum
+
 import numpy as np
 import torch
 
@@ -209,8 +211,31 @@ _SHAPE_FIELDS = {
 }
 
 
+class AttributeFrequency(enum.IntEnum):
+    """What an attribute array is indexed by (reference ``Model.AttributeFrequency``, ``sim/model.py:344-381``)."""
+
+    ONCE = 0
+    JOINT = 1
+    JOINT_DOF = 2
+    JOINT_COORD = 3
+    JOINT_CONSTRAINT = 4
+    BODY = 5
+    SHAPE = 6
+    ARTICULATION = 7
+    EQUALITY_CONSTRAINT = 8
+    PARTICLE = 9
+    EDGE = 10
+    TRIANGLE = 11
+    TETRAHEDRON = 12
+    SPRING = 13
+    CONSTRAINT_MIMIC = 14
+    WORLD = 15
+
+
 class Model:
     """Static model description (reference ``sim/model.py:299``; field docs at ``:1060-1307``)."""
+
+    AttributeFrequency = AttributeFrequency
 
     def __init__(self, device="cpu"):
         self.device = torch.device(device)
@@ -234,6 +259,8 @@ class Model:
         self.body_label: list[str] = []
         self.joint_label: list[str] = []
         self.shape_label: list[str] = []
+        self.articulation_label: list[str] = []
+        self.body_shapes: dict[int, list[int]] = {-1: []}
         self.particle_grid = None
         for group in (_BODY_FIELDS, _JOINT_FIELDS, _DOF_FIELDS, _COORD_FIELDS, _SHAPE_FIELDS):
             for name in group:
@@ -286,6 +313,24 @@ class Model:
                 c.joint_target_qd = self.joint_target_qd
                 c.joint_act = self.joint_act
         return c
+
+    def get_attribute_frequency(self, name: str) -> AttributeFrequency:
+        """Frequency of a Model / State / Control attribute (reference ``sim/model.py:2224-2241``)."""
+        if name in _BODY_FIELDS or name in ("body_f", "body_parent_f"):
+            return AttributeFrequency.BODY
+        if name in _JOINT_FIELDS:
+            return AttributeFrequency.JOINT
+        if name in _DOF_FIELDS:
+            return AttributeFrequency.JOINT_DOF
+        if name in _COORD_FIELDS:
+            return AttributeFrequency.JOINT_COORD
+        if name == "joint_target_q":
+            return AttributeFrequency.JOINT_COORD if self.use_coord_layout_targets else AttributeFrequency.JOINT_DOF
+        if name in _SHAPE_FIELDS:
+            return AttributeFrequency.SHAPE
+        if name in ("articulation_start", "articulation_end", "articulation_world"):
+            return AttributeFrequency.ARTICULATION
+        raise KeyError(f"Attribute frequency of '{name}' is not known")
 
     def request_contact_attributes(self, *attributes: str) -> None:
         self._requested_contact_attributes.update(attributes)

@@ -7,6 +7,38 @@ import ctypes as C
 from .. import _abi, _lib
 
 
+def normalize_reset_world_mask(world_mask, *, world_count: int, device, allow_legacy: bool = False):
+    """Validate a reset mask and return it in the canonical ``(world_count + 1,)`` shape, last entry = world ``-1``
+    (reference ``core/reset.py:21-60``).  ``allow_legacy`` also accepts the deprecated ``(world_count,)`` shape."""
+    import warnings
+
+    import torch
+
+    if world_mask is None:
+        return None
+    if not isinstance(world_mask, torch.Tensor):
+        raise TypeError("'world_mask' must be a torch tensor or None.")
+    if world_mask.dtype != torch.bool:
+        raise TypeError("'world_mask' must have dtype bool.")
+    if world_mask.dim() != 1:
+        raise ValueError("'world_mask' must be one-dimensional.")
+    want = torch.device(device)
+    if world_mask.device.type != want.type or (world_mask.device.index or 0) != (want.index or 0):
+        raise ValueError(f"'world_mask' device {world_mask.device} does not match expected device {device}.")
+    mask_size = world_mask.shape[0]
+    if mask_size == world_count + 1:
+        return world_mask
+    if allow_legacy and mask_size == world_count:
+        warnings.warn("world_mask with shape (world_count,) is deprecated; use shape (world_count + 1,), "
+                      "where the final entry selects global entities in world -1.", DeprecationWarning, stacklevel=4)
+        normalized = torch.zeros(world_count + 1, dtype=torch.bool, device=world_mask.device)
+        normalized[:world_count] = world_mask
+        return normalized
+    if allow_legacy:
+        raise ValueError(f"world_mask has size {mask_size}, expected {world_count} or {world_count + 1}.")
+    raise ValueError(f"'world_mask' length {mask_size} must equal model.world_count + 1 ({world_count + 1}).")
+
+
 class SolverBase:
     def __init__(self, model):
         self.model = model
@@ -40,8 +72,9 @@ class SolverBase:
         raise NotImplementedError()
 
     def reset(self, state, world_mask=None, flags=None) -> None:
-        """Reference ``solver.py:344-375``: XPBD / Featherstone keep no per-world solver state to reset."""
-        return None
+        """Reference ``solver.py:344-375``: the base implementation validates the mask and resets nothing; neither
+        ``SolverXPBD`` nor ``SolverFeatherstone`` overrides it upstream (they keep no per-world solver state)."""
+        normalize_reset_world_mask(world_mask, world_count=int(self.model.world_count), device=self.model.device, allow_legacy=True)
 
     @classmethod
     def register_custom_attributes(cls, builder) -> None:

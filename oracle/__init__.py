@@ -103,6 +103,9 @@ class SolverXPBD:
     def params(self):
         return _abi.XPBDParams(*self._args, 1 if self.compute_body_velocity_from_position_delta else 0)
 
+    def reset(self, state, world_mask=None, flags=None):
+        """SolverBase.reset (solvers/solver.py:344-375): no-op for XPBD."""
+
     def step(self, state_in, state_out, control, contacts, dt):
         if control is None:
             control = self.model.control(clone_variables=False)
@@ -154,6 +157,9 @@ class SolverFeatherstone:
             lib().orc_featherstone_free(self._h)
         except Exception:
             pass
+
+    def reset(self, state, world_mask=None, flags=None):
+        """SolverBase.reset (solvers/solver.py:344-375): no-op for Featherstone."""
 
     def step(self, state_in, state_out, control, contacts, dt):
         if control is None:
@@ -248,11 +254,21 @@ def tight_aabb(geo_type, scale, xform, impl="oracle"):
     return out[:3], out[3:]
 
 
-def eval_fk(model, joint_q, joint_qd, state):
-    """newton.eval_fk: writes state.body_q / state.body_qd (state may be the model)."""
+def eval_fk(model, joint_q, joint_qd, state, mask=None, indices=None):
+    """newton.eval_fk: writes state.body_q / state.body_qd (state may be the model); optional articulation mask / indices."""
+    if mask is not None and indices is not None:
+        raise ValueError("Cannot specify both mask and indices parameters")
     d = _abi.model_desc(model)
-    lib().orc_eval_fk(C.byref(d), C.c_void_p(_abi.ptr(joint_q)), C.c_void_p(_abi.ptr(joint_qd)),
-                      C.c_void_p(_abi.ptr(state.body_q)), C.c_void_p(_abi.ptr(state.body_qd)))
+    if mask is None and indices is None:
+        lib().orc_eval_fk(C.byref(d), C.c_void_p(_abi.ptr(joint_q)), C.c_void_p(_abi.ptr(joint_qd)),
+                          C.c_void_p(_abi.ptr(state.body_q)), C.c_void_p(_abi.ptr(state.body_qd)))
+        return
+    m = None if mask is None else np.ascontiguousarray(np.asarray(mask.cpu() if hasattr(mask, "cpu") else mask), dtype=np.uint8)
+    ix = None if indices is None else np.ascontiguousarray(np.asarray(indices.cpu() if hasattr(indices, "cpu") else indices), dtype=np.int32)
+    lib().orc_eval_fk_masked(C.byref(d), C.c_void_p(_abi.ptr(joint_q)), C.c_void_p(_abi.ptr(joint_qd)),
+                             C.c_void_p(_abi.ptr(state.body_q)), C.c_void_p(_abi.ptr(state.body_qd)),
+                             C.c_void_p(None if m is None else m.ctypes.data), C.c_void_p(None if ix is None else ix.ctypes.data),
+                             C.c_int(0 if ix is None else ix.size))
 
 
 def eval_ik(model, state, joint_q, joint_qd):

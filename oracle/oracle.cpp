@@ -21,6 +21,7 @@
 #include "oracle_collide.h"
 #include "oracle_featherstone.h"
 #include "oracle_gjk.h"
+#include "../newton_b200/csrc/nb2_selection.cuh"
 #include "oracle_xpbd.h"
 
 using namespace orc;
@@ -259,6 +260,24 @@ void orc_tight_aabb(int type, const float* scale, const float* xform, float* out
 // newton.eval_fk(model, joint_q, joint_qd, state)
 void orc_eval_fk(const nb2_model_desc* m, const float* joint_q, const float* joint_qd, float* body_q, float* body_qd) {
     eval_articulation_fk(*m, joint_q, joint_qd, body_q, body_qd);
+}
+// ... with the optional articulation mask / index list (sim/articulation.py:420-475)
+void orc_eval_fk_masked(const nb2_model_desc* m, const float* joint_q, const float* joint_qd, float* body_q, float* body_qd,
+                        const uint8_t* articulation_mask, const int* articulation_indices, int index_count) {
+    eval_articulation_fk(*m, joint_q, joint_qd, body_q, body_qd, articulation_mask, articulation_indices, index_count);
+}
+
+// The index arithmetic of the PRODUCT's ArticulationView copy kernels (newton_b200/csrc/nb2_selection.cuh) run on the host over
+// every word, so that tests/test_selection.py can compare it with the NumPy restatement (oracle/selection.py) without a GPU.
+// gather != 0: values <- attrib; else attrib <- values under the mask.  `wide` selects the 64-bit instantiation.
+void orc_view_copy_product_host(uint32_t* attrib, const nb2_view_layout* layout, uint32_t* values, const uint8_t* mask, int mask_ndim,
+                                int gather, int wide) {
+    const long long n = (long long)layout->world_count * layout->count_per_world * layout->value_count * layout->row_words;
+    for (long long i = 0; i < n; ++i) {
+        const nb2::ViewElem e = wide ? nb2::view_elem<long long>(*layout, layout->indices, i) : nb2::view_elem<unsigned>(*layout, layout->indices, (unsigned)i);
+        if (gather) values[i] = attrib[e.word];
+        else if (nb2::view_selected(*layout, mask, mask_ndim, e)) attrib[e.word] = values[i];
+    }
 }
 
 // newton.eval_ik(model, state, joint_q, joint_qd); returns the number of joints it cannot invert (D6 with 2-3 angular axes)

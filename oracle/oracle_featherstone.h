@@ -662,10 +662,15 @@ inline void featherstone_step(FsScratch& s, const nb2_model_desc& m, const nb2_f
     s.step += 1;
 }
 
-// ---- public newton.eval_fk (sim/articulation.py:237-424 eval_single_articulation_fk, all articulations, no mask) ------------
-// joint_qd in the PUBLIC convention (FREE/DISTANCE linear dofs = child COM velocity).
-inline void eval_articulation_fk(const nb2_model_desc& m, const float* joint_q, const float* joint_qd, float* body_q, float* body_qd) {
-    for (int a = 0; a < m.articulation_count; ++a)
+// ---- public newton.eval_fk (sim/articulation.py:237-424 eval_single_articulation_fk; launch :420-475 with the optional ----
+// articulation_mask / articulation_indices).  joint_qd in the PUBLIC convention (FREE/DISTANCE linear dofs = child COM velocity).
+inline void eval_articulation_fk(const nb2_model_desc& m, const float* joint_q, const float* joint_qd, float* body_q, float* body_qd,
+                                 const uint8_t* articulation_mask = nullptr, const int* articulation_indices = nullptr, int index_count = 0) {
+    const int dim = articulation_indices ? index_count : m.articulation_count;
+    for (int tid = 0; tid < dim; ++tid) {
+        const int a = articulation_indices ? articulation_indices[tid] : tid;
+        if (a < 0 || a >= m.articulation_count) continue;        // :462-463 bounds check
+        if (articulation_mask && !articulation_mask[a]) continue;  // :466-468
         for (int i = m.articulation_start[a]; i < m.articulation_start[a + 1]; ++i) {
             if (m.joint_articulation[i] == -1) continue;
             int parent = m.joint_parent[i], child = m.joint_child[i], type = m.joint_type[i];
@@ -719,6 +724,7 @@ inline void eval_articulation_fk(const nb2_model_desc& m, const float* joint_q, 
             vec3 v_com = cross(w_o, transform_vector(X_wc, load3(m.body_com + 3 * child))) + v_o;  // origin_twist_to_com_twist
             spatial(v_com, w_o).store(body_qd + 6 * child);
         }
+    }
 }
 
 // wp.quat_twist_angle_signed(axis, q): signed rotation angle of q's twist about `axis`.  Warp built-in (warp-lang >= 1.16,
