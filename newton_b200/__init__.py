@@ -5,3 +5,4 @@ from .sim import (  # noqa: F401
 )
 from .sim.collide import CollisionPipeline  # noqa: F401,E402
 from . import solvers  # noqa: F401,E402
+from . import selection  # noqa: F401,E402

@@ -240,6 +240,7 @@ static nb2_status build_tables(nb2_model* m, const nb2_model_desc& d) {
                 if (anc >= j || (anc >= 0 && anc < j0)) {
                     h.featherstone_supported = false;
                     h.featherstone_reason = "joints must be stored parent-before-child inside their articulation";
+                    h.fk_levels = false;  // eval_fk then walks the joints serially, in array order, like the reference
                     anc = -1;
                 }
                 h.joint_depth[j] = anc >= 0 ? h.joint_depth[anc] + 1 : 0;
@@ -250,6 +251,14 @@ static nb2_status build_tables(nb2_model* m, const nb2_model_desc& d) {
                     h.featherstone_reason = "joints outside an articulation";
                 }
             }
+        }
+        {  // a body driven by two joints ("undefined semantics" upstream): only the serial walk reproduces the array-order result
+            std::vector<char> driven(size_t(B), 0);
+            for (int j = 0; j < J; ++j)
+                if (jart[j] >= 0 && jchild[j] >= 0) {
+                    if (driven[jchild[j]]) h.fk_levels = false;
+                    driven[jchild[j]] = 1;
+                }
         }
         int e = 0, max_env_H = 0, max_env_arts = 0;
         for (int ee = 0; ee < E; ++ee) {

@@ -911,77 +911,113 @@ nb2_status launch_featherstone_step(nb2_model* m, const nb2_featherstone_params&
     }
 }
 
-// ---- public newton.eval_fk (sim/articulation.py:237-475): one thread walks one articulation in joint order ------------
-// A set-up / reset call (example_basic_urdf.py:87), not part of the substep loop: the serial walk keeps the reference's
-// exact operation order; articulations are independent, so the grid is one thread per articulation.
-// `mask` / `indices` are the reference's optional articulation_mask / articulation_indices (eval_articulation_fk :420-475).
-__global__ void __launch_bounds__(128) eval_fk_kernel(DevModel M, const float* __restrict__ joint_q, const float* __restrict__ joint_qd,
-                                                      float* __restrict__ body_q, float* __restrict__ body_qd,
-                                                      const uint8_t* __restrict__ mask, const int* __restrict__ indices, int count) {
-    const nb2_model_desc& d = M.d;
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= count) return;
-    const int a = indices ? indices[tid] : tid;
-    if (a < 0 || a >= d.articulation_count) return;
-    if (mask && !mask[a]) return;
-    for (int i = d.articulation_start[a]; i < d.articulation_start[a + 1]; ++i) {
-        if (d.joint_articulation[i] == -1) continue;
-        const int type = d.joint_type[i], parent = d.joint_parent[i], child = d.joint_child[i];
-        const int qs = d.joint_q_start[i], qds = d.joint_qd_start[i];
-        const int lin = d.joint_dof_dim[2 * i], ang = d.joint_dof_dim[2 * i + 1];
-        const Xf X_j = joint_transform(d, type, qds, lin, ang, joint_q, qs);
-        V3 vj_lin, vj_ang;
-        if (type == FJ_PRISMATIC) vj_lin = ld3(d.joint_axis + 3 * qds) * joint_qd[qds];
-        if (type == FJ_REVOLUTE) vj_ang = ld3(d.joint_axis + 3 * qds) * joint_qd[qds];
-        if (type == FJ_BALL) vj_ang = V3(joint_qd[qds], joint_qd[qds + 1], joint_qd[qds + 2]);
-        if (type == FJ_FREE || type == FJ_DISTANCE) {
-            vj_lin = V3(joint_qd[qds], joint_qd[qds + 1], joint_qd[qds + 2]);
-            vj_ang = V3(joint_qd[qds + 3], joint_qd[qds + 4], joint_qd[qds + 5]);
-        }
-        if (type == FJ_D6) {
-            for (int k = 0; k < 3; ++k)
-                if (lin > k) vj_lin += ld3(d.joint_axis + 3 * (qds + k)) * joint_qd[qds + k];
-            const int iq = qs + lin, iqd = qds + lin;
-            if (ang == 1) vj_ang = joint_qd[iqd] * ld3(d.joint_axis + 3 * iqd);
-            if (ang == 3) {
-                V3 w0, w1, w2;
-                axes3(ld3(d.joint_axis + 3 * iqd), ld3(d.joint_axis + 3 * (iqd + 1)), ld3(d.joint_axis + 3 * (iqd + 2)), joint_q[iq], joint_q[iq + 1],
-                      w0, w1, w2);
-                vj_ang = w0 * joint_qd[iqd] + w1 * joint_qd[iqd + 1] + w2 * joint_qd[iqd + 2];
-            }
-        }
-        Xf X_wpj = ldx(d.joint_X_p + 7 * i);
-        Xf X_wp;
-        if (parent >= 0) {
-            X_wp = ldx(body_q + 7 * parent);
-            X_wpj = xmul(X_wp, X_wpj);
-        }
-        const Xf X_wcj = xmul(X_wpj, X_j);
-        const Xf X_wc = xmul(X_wcj, xinv(ldx(d.joint_X_c + 7 * i)));
-        const V3 x_child = X_wc.p;
-        V3 v_parent_origin, w_parent;
-        if (parent >= 0) {
-            const V3 pv = ld3(body_qd + 6 * parent);
-            w_parent = ld3(body_qd + 6 * parent + 3);
-            v_parent_origin = cross(w_parent, x_child - xpoint(X_wp, ld3(d.body_com + 3 * parent))) + pv;
-        }
-        const V3 lin_w = xvec(X_wpj, vj_lin), ang_w = xvec(X_wpj, vj_ang);
-        const V3 com_c = xvec(X_wc, ld3(d.body_com + 3 * child));
-        V3 lin_o;
-        if (type == FJ_FREE || type == FJ_DISTANCE) lin_o = lin_w - cross(ang_w, com_c);  // COM twist -> origin twist
-        else lin_o = lin_w + cross(ang_w, x_child - X_wcj.p);
-        const V3 v_o = v_parent_origin + lin_o, w_o = w_parent + ang_w;
-        const V3 v_com = cross(w_o, com_c) + v_o;
-        stx(body_q + 7 * child, X_wc);
-        st6(body_qd + 6 * child, S6(v_com, w_o));
+// ---- public newton.eval_fk (sim/articulation.py:237-475) ------------------------------------------------------------------
+// A set-up / reset call (example_basic_urdf.py:87; ArticulationView.eval_fk on the done worlds of an RL loop), not part of the
+// substep loop.  fk_joint is one iteration of the reference's joint loop (eval_single_articulation_fk :237-418): it reads the
+// parent's freshly written pose / twist and writes the child's.
+__device__ __forceinline__ void fk_joint(const nb2_model_desc& d, int i, const float* __restrict__ joint_q, const float* __restrict__ joint_qd,
+                                         float* body_q, float* body_qd) {
+    const int type = d.joint_type[i], parent = d.joint_parent[i], child = d.joint_child[i];
+    const int qs = d.joint_q_start[i], qds = d.joint_qd_start[i];
+    const int lin = d.joint_dof_dim[2 * i], ang = d.joint_dof_dim[2 * i + 1];
+    const Xf X_j = joint_transform(d, type, qds, lin, ang, joint_q, qs);
+    V3 vj_lin, vj_ang;
+    if (type == FJ_PRISMATIC) vj_lin = ld3(d.joint_axis + 3 * qds) * joint_qd[qds];
+    if (type == FJ_REVOLUTE) vj_ang = ld3(d.joint_axis + 3 * qds) * joint_qd[qds];
+    if (type == FJ_BALL) vj_ang = V3(joint_qd[qds], joint_qd[qds + 1], joint_qd[qds + 2]);
+    if (type == FJ_FREE || type == FJ_DISTANCE) {
+        vj_lin = V3(joint_qd[qds], joint_qd[qds + 1], joint_qd[qds + 2]);
+        vj_ang = V3(joint_qd[qds + 3], joint_qd[qds + 4], joint_qd[qds + 5]);
     }
+    if (type == FJ_D6) {
+        for (int k = 0; k < 3; ++k)
+            if (lin > k) vj_lin += ld3(d.joint_axis + 3 * (qds + k)) * joint_qd[qds + k];
+        const int iq = qs + lin, iqd = qds + lin;
+        if (ang == 1) vj_ang = joint_qd[iqd] * ld3(d.joint_axis + 3 * iqd);
+        if (ang == 3) {
+            V3 w0, w1, w2;
+            axes3(ld3(d.joint_axis + 3 * iqd), ld3(d.joint_axis + 3 * (iqd + 1)), ld3(d.joint_axis + 3 * (iqd + 2)), joint_q[iq], joint_q[iq + 1],
+                  w0, w1, w2);
+            vj_ang = w0 * joint_qd[iqd] + w1 * joint_qd[iqd + 1] + w2 * joint_qd[iqd + 2];
+        }
+    }
+    Xf X_wpj = ldx(d.joint_X_p + 7 * i);
+    Xf X_wp;
+    if (parent >= 0) {
+        X_wp = ldx(body_q + 7 * parent);
+        X_wpj = xmul(X_wp, X_wpj);
+    }
+    const Xf X_wcj = xmul(X_wpj, X_j);
+    const Xf X_wc = xmul(X_wcj, xinv(ldx(d.joint_X_c + 7 * i)));
+    const V3 x_child = X_wc.p;
+    V3 v_parent_origin, w_parent;
+    if (parent >= 0) {
+        const V3 pv = ld3(body_qd + 6 * parent);
+        w_parent = ld3(body_qd + 6 * parent + 3);
+        v_parent_origin = cross(w_parent, x_child - xpoint(X_wp, ld3(d.body_com + 3 * parent))) + pv;
+    }
+    const V3 lin_w = xvec(X_wpj, vj_lin), ang_w = xvec(X_wpj, vj_ang);
+    const V3 com_c = xvec(X_wc, ld3(d.body_com + 3 * child));
+    V3 lin_o;
+    if (type == FJ_FREE || type == FJ_DISTANCE) lin_o = lin_w - cross(ang_w, com_c);  // COM twist -> origin twist
+    else lin_o = lin_w + cross(ang_w, x_child - X_wcj.p);
+    const V3 v_o = v_parent_origin + lin_o, w_o = w_parent + ang_w;
+    const V3 v_com = cross(w_o, com_c) + v_o;
+    stx(body_q + 7 * child, X_wc);
+    st6(body_qd + 6 * child, S6(v_com, w_o));
+}
+
+// Which articulation a work item handles: `mask` / `indices` are the reference's optional articulation_mask /
+// articulation_indices (eval_articulation_fk :420-475); -1 = nothing to do.
+__device__ __forceinline__ int fk_articulation(const nb2_model_desc& d, int item, int count, const uint8_t* mask, const int* indices) {
+    if (item >= count) return -1;
+    const int a = indices ? indices[item] : item;
+    if (a < 0 || a >= d.articulation_count) return -1;
+    if (mask && !mask[a]) return -1;
+    return a;
+}
+
+// One WARP per articulation, joints of equal tree depth in parallel (lane = joint), depth levels in order with __syncwarp()
+// between them (it orders the lanes' global writes and reads): a 13-joint quadruped takes 4 dependent steps instead of 13.
+// Every joint runs exactly the arithmetic of the serial walk on the same parent values, so the results are bit-identical to it.
+// Requires parent-before-child joint order and one driving joint per body (nb2_model::fk_levels, checked at model creation).
+__global__ void __launch_bounds__(128) eval_fk_levels_kernel(DevModel M, const float* __restrict__ joint_q, const float* __restrict__ joint_qd,
+                                                             float* body_q, float* body_qd, const uint8_t* __restrict__ mask,
+                                                             const int* __restrict__ indices, int count) {
+    const nb2_model_desc& d = M.d;
+    const int lane = threadIdx.x & 31;
+    const int a = fk_articulation(d, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, count, mask, indices);  // warp-uniform
+    if (a < 0) return;
+    const int j0 = d.articulation_start[a], j1 = d.articulation_start[a + 1];
+    int deepest = 0;
+    for (int i = j0 + lane; i < j1; i += 32) deepest = max(deepest, M.joint_depth[i]);
+    for (int o = 16; o > 0; o >>= 1) deepest = max(deepest, __shfl_xor_sync(0xffffffffu, deepest, o));
+    for (int level = 0; level <= deepest; ++level) {
+        for (int i = j0 + lane; i < j1; i += 32)
+            if (M.joint_depth[i] == level && d.joint_articulation[i] != -1) fk_joint(d, i, joint_q, joint_qd, body_q, body_qd);
+        __syncwarp();
+    }
+}
+
+// Fallback for models whose joint order the level schedule cannot honour: one thread walks one articulation in joint order.
+__global__ void __launch_bounds__(128) eval_fk_kernel(DevModel M, const float* __restrict__ joint_q, const float* __restrict__ joint_qd,
+                                                      float* body_q, float* body_qd, const uint8_t* __restrict__ mask,
+                                                      const int* __restrict__ indices, int count) {
+    const nb2_model_desc& d = M.d;
+    const int a = fk_articulation(d, blockIdx.x * blockDim.x + threadIdx.x, count, mask, indices);
+    if (a < 0) return;
+    for (int i = d.articulation_start[a]; i < d.articulation_start[a + 1]; ++i)
+        if (d.joint_articulation[i] != -1) fk_joint(d, i, joint_q, joint_qd, body_q, body_qd);
 }
 
 nb2_status launch_eval_fk(nb2_model* m, const float* joint_q, const float* joint_qd, float* body_q, float* body_qd, cudaStream_t s,
                           const uint8_t* mask, const int* indices, int index_count) {
     const int A = indices ? index_count : m->dev.d.articulation_count;
     if (A <= 0 || m->dev.d.articulation_count == 0) return NB2_OK;
-    eval_fk_kernel<<<(A + 127) / 128, 128, 0, s>>>(m->dev, joint_q, joint_qd, body_q, body_qd, mask, indices, A);
+    if (m->host.fk_levels)
+        eval_fk_levels_kernel<<<(A + 3) / 4, 128, 0, s>>>(m->dev, joint_q, joint_qd, body_q, body_qd, mask, indices, A);
+    else
+        eval_fk_kernel<<<(A + 127) / 128, 128, 0, s>>>(m->dev, joint_q, joint_qd, body_q, body_qd, mask, indices, A);
     count_launch();
     NB2_CUDA_CHECK(cudaGetLastError());
     return NB2_OK;

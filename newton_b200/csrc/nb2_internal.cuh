@@ -71,6 +71,7 @@ struct HostTables {
     std::vector<unsigned long long> joint_anc_mask;
     bool featherstone_supported = true;
     bool ik_supported = true;  // false when a D6 joint has 2-3 angular axes
+    bool fk_levels = true;     // eval_fk may schedule joints by tree depth (parent-before-child order, one driving joint per body)
     std::string featherstone_reason;
 };
 

@@ -155,6 +155,12 @@ def _uniform_stride(starts, what: str) -> int | None:
     return strides[0]
 
 
+class _Plan:
+    """Cached addressing of one attribute array through a view (see ``ArticulationView._plan``)."""
+
+    __slots__ = ("shape", "numel", "indices", "abi", "view", "view_ptr")
+
+
 class ArticulationView:
     """Selection of identical articulations across worlds (reference ``selection.py:500-561`` for the contract).
 
@@ -168,6 +174,7 @@ class ArticulationView:
                  include_joint_types=None, exclude_joint_types=None, include_loop_closing_joints: bool = False, verbose: bool | None = None):
         self.model = model
         self.device = model.device
+        self._plans: dict = {}
         for parameter_name, indices in (("include_joints", include_joints), ("include_links", include_links)):
             if (isinstance(indices, list) and all(isinstance(index, int) for index in indices)
                     and any(indices[i] < indices[i - 1] for i in range(1, len(indices)))):
@@ -398,13 +405,22 @@ class ArticulationView:
         return self.link_labels
 
     # ------------------------------------------------------------------ generic attribute API
-    def _resolve_layout(self, name: str, source, _slice):
-        """Everything ``nb2_view_layout`` needs for ``source.<name>`` (reference ``_get_attribute_array``, :1232-1357)."""
+    def _plan(self, name: str, source, _slice):
+        """How ``source.<name>`` is addressed (reference ``_get_attribute_array``, :1232-1357): the attribute tensor plus a cached
+        :class:`_Plan` (view shape, ``nb2_view_layout``, strided-view arguments).  Cached per array like the reference's
+        ``lru_cache``, keyed by what the plan depends on - name, slice, base pointer, shape."""
         attrib = source
         for part in name.split("."):
             attrib = getattr(attrib, part)
         if not isinstance(attrib, torch.Tensor):
             raise AttributeError(f"Attribute '{name}' is not an array")
+        key = (name, _slice, attrib.data_ptr(), tuple(attrib.shape))
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self._plans[key] = self._make_plan(name, attrib, _slice)
+        return attrib, plan
+
+    def _make_plan(self, name: str, attrib, _slice) -> "_Plan":
         frequency = self.model.get_attribute_frequency(name)
         layout = self.frequency_layouts.get(frequency)
         if layout is None:
@@ -414,50 +430,58 @@ class ArticulationView:
         elif not isinstance(_slice, (type(None), int, slice)):
             raise ValueError(f"Invalid slice type: expected slice or int, got {type(_slice)}")
         indices = None
-        drop_value_dim = False
+        drop = False  # an int slice drops the value dimension, like NumPy / Warp indexing
         if _slice is None:
             if layout.indices is not None:
                 indices, start, count = layout.indices, 0, len(layout.indices)
             else:
                 start, count = layout.slice.start, layout.slice.stop - layout.slice.start
         elif isinstance(_slice, int):
-            start, count, drop_value_dim = _slice, 1, True
+            start, count, drop = _slice, 1, True
         else:
             start, count = _slice.start, _slice.stop - _slice.start
-        return attrib, layout, indices, start, count, drop_value_dim
-
-    def _abi_layout(self, attrib, layout, indices, start, count) -> _abi.ViewLayout:
-        row_words = int(np.prod(attrib.shape[1:], dtype=np.int64)) if attrib.dim() > 1 else 1
-        if attrib.element_size() != 4:
-            raise NotImplementedError(f"ArticulationView copies 32-bit attributes only (got {attrib.dtype})")  # reference overloads: float/int
-        return _abi.ViewLayout(self.world_count, self.count_per_world, count, row_words, layout.offset, layout.stride_between_worlds,
-                               layout.stride_within_worlds, start, None if indices is None else indices.data_ptr())
-
-    def _view_shape(self, attrib, count, drop_value_dim):
-        lead = (self.world_count, self.count_per_world) if drop_value_dim else (self.world_count, self.count_per_world, count)
-        return (*lead, *attrib.shape[1:])
+        plan = _Plan()
+        trailing = tuple(attrib.shape[1:])
+        lead = (self.world_count, self.count_per_world) if drop else (self.world_count, self.count_per_world, count)
+        plan.shape = (*lead, *trailing)
+        plan.numel = int(np.prod(plan.shape, dtype=np.int64))
+        plan.indices = indices  # keeps the device index array alive
+        plan.abi = None
+        if attrib.element_size() == 4:  # the copy kernels move 32-bit words (reference overloads: float / int / transform / spatial_vector)
+            row_words = int(np.prod(trailing, dtype=np.int64)) if trailing else 1
+            plan.abi = _abi.ViewLayout(self.world_count, self.count_per_world, count, row_words, layout.offset, layout.stride_between_worlds,
+                                       layout.stride_within_worlds, start, None if indices is None else indices.data_ptr())
+        plan.view = None
+        if indices is None:  # contiguous selection: a strided view of the array itself
+            vs = attrib.stride(0) if attrib.dim() > 0 else 1
+            lead_strides = (layout.stride_between_worlds * vs, layout.stride_within_worlds * vs) + (() if drop else (vs,))
+            plan.view = (plan.shape, (*lead_strides, *attrib.stride()[1:]), attrib.storage_offset() + (layout.offset + start) * vs)
+            plan.view_ptr = attrib.data_ptr() + (layout.offset + start) * vs * attrib.element_size()
+        return plan
 
     def _get_attribute_array(self, name: str, source, _slice=None):
         """Zero-copy strided view for contiguous selections, else ``None`` (the caller gathers)."""
-        attrib, layout, indices, start, count, drop = self._resolve_layout(name, source, _slice)
-        if indices is not None:
+        attrib, plan = self._plan(name, source, _slice)
+        if plan.view is None:
             return None
-        vs = attrib.stride(0) if attrib.dim() > 0 else 1
-        shape = self._view_shape(attrib, count, drop)
-        lead = (layout.stride_between_worlds * vs, layout.stride_within_worlds * vs) + (() if drop else (vs,))
-        strides = (*lead, *attrib.stride()[1:])
-        if attrib.numel() == 0 or count == 0:
-            return attrib.new_empty(shape)
-        return torch.as_strided(attrib, shape, strides, attrib.storage_offset() + (layout.offset + start) * vs)
+        if attrib.numel() == 0 or plan.numel == 0:
+            return attrib.new_empty(plan.shape)
+        return torch.as_strided(attrib, *plan.view)
 
     def _get_attribute_values(self, name: str, source, _slice=None):
-        view = self._get_attribute_array(name, source, _slice)
-        if view is not None:
-            return view
-        attrib, layout, indices, start, count, drop = self._resolve_layout(name, source, _slice)
-        staging = attrib.new_empty(self._view_shape(attrib, count, drop))
-        self._launch_copy(attrib, self._abi_layout(attrib, layout, indices, start, count), staging, None, gather=True)
+        attrib, plan = self._plan(name, source, _slice)
+        if plan.view is not None:
+            return self._get_attribute_array(name, source, _slice)
+        staging = attrib.new_empty(plan.shape)
+        if plan.numel:
+            self._launch_copy(attrib, self._copy_layout(attrib, plan), staging, None, gather=True)
         return staging
+
+    @staticmethod
+    def _copy_layout(attrib, plan):
+        if plan.abi is None:
+            raise NotImplementedError(f"ArticulationView copies 32-bit attributes only (got {attrib.dtype})")
+        return plan.abi
 
     def _launch_copy(self, attrib, abi_layout, values, mask, gather: bool):
         if not attrib.is_cuda:
@@ -477,21 +501,20 @@ class ArticulationView:
 
     def _set_attribute_values(self, name: str, target, values, mask=None, _slice=None):
         """Masked write (reference ``_set_attribute_values``, :1380-1439)."""
-        attrib, layout, indices, start, count, drop = self._resolve_layout(name, target, _slice)
-        shape = self._view_shape(attrib, count, drop)
+        attrib, plan = self._plan(name, target, _slice)
         if not isinstance(values, torch.Tensor) or values.dtype != attrib.dtype or values.device != attrib.device:
             values = torch.as_tensor(np.asarray(values) if not isinstance(values, torch.Tensor) else values, dtype=attrib.dtype,
                                      device=attrib.device)
-        if int(np.prod(values.shape, dtype=np.int64)) != int(np.prod(shape, dtype=np.int64)):
-            raise ValueError(f"Expected values with shape {tuple(shape)}, got {tuple(values.shape)}")
-        view = self._get_attribute_array(name, target, _slice)
-        if view is not None and values.data_ptr() == view.data_ptr() and values.stride() == view.stride():
+        if values.numel() != plan.numel:
+            raise ValueError(f"Expected values with shape {plan.shape}, got {tuple(values.shape)}")
+        if plan.view is not None and values.data_ptr() == plan.view_ptr and values.stride() == plan.view[1]:
             return  # in-place modification of the view returned by get_*: nothing to copy
-        values = values.reshape(shape).contiguous()
+        if not values.is_contiguous():
+            values = values.contiguous()
         mask = None if mask is None else self._resolve_mask(mask)
-        if values.numel() == 0:
+        if plan.numel == 0:
             return
-        self._launch_copy(attrib, self._abi_layout(attrib, layout, indices, start, count), values, mask, gather=False)
+        self._launch_copy(attrib, self._copy_layout(attrib, plan), values, mask, gather=False)
 
     def get_attribute(self, name: str, source):
         """``[world, articulation, value, ...]`` values of ``source.<name>`` (Model, State or Control)."""

@@ -207,3 +207,35 @@ def test_reset_mask_validation_on_solver(cuda_lib):
         solver.reset(state, world_mask=torch.ones(7, dtype=torch.bool, device="cuda:0"))
     with pytest.raises(ValueError):
         solver.reset(state, world_mask=torch.ones(4, dtype=torch.bool))  # wrong device
+
+
+def test_eval_fk_child_before_parent_order_uses_serial_walk(cuda_lib, oracle_lib):
+    """Joints stored child-before-parent: the reference's serial walk then reads the parent's OLD pose for the first joint.  The
+    level-parallel kernel cannot reproduce that, so model creation must fall back to the serial kernel (nb2_model::fk_levels)."""
+    import oracle
+    from newton_b200 import ModelBuilder
+    from newton_b200.utils import xform as X
+
+    b = ModelBuilder()
+    inertia = np.eye(3) * 0.1
+    for _ in range(3):  # three chains so that several threads / warps run
+        b1 = b.add_link(mass=1.0, inertia=inertia, xform=X.transform((0.3, 0.1, 0.2)))
+        b2 = b.add_link(mass=1.0, inertia=inertia)
+        j_child = b.add_joint_revolute(b1, b2, axis=(0, 1, 0), parent_xform=X.transform((0.0, 0.0, 0.5)))
+        j_root = b.add_joint_revolute(-1, b1, axis=(0, 0, 1), parent_xform=X.transform((1.0, 0.0, 0.0)))
+        b.add_articulation([j_child, j_root])
+    cpu = b.finalize()
+    cpu.joint_q.copy_(torch.tensor([0.3, -0.7, 0.1, 0.9, -0.4, 0.5]))
+    cpu.joint_qd.copy_(torch.tensor([1.0, 2.0, -1.0, 0.5, 0.25, -2.0]))
+    gpu = cpu.to("cuda:0")
+    ref, out = cpu.state(), gpu.state()
+    oracle.eval_fk(cpu, ref.joint_q, ref.joint_qd, ref)
+    newton_b200.eval_fk(gpu, out.joint_q, out.joint_qd, out)
+    assert np.array_equal(out.body_q.cpu().numpy().view(np.uint32), ref.body_q.numpy().view(np.uint32))
+    assert np.array_equal(out.body_qd.cpu().numpy().view(np.uint32), ref.body_qd.numpy().view(np.uint32))
+    # ... and that really is the stale-parent result: a second pass (parents now up to date) changes the children
+    again = cpu.state()
+    again.body_q.copy_(ref.body_q)
+    again.body_qd.copy_(ref.body_qd)
+    oracle.eval_fk(cpu, again.joint_q, again.joint_qd, again)
+    assert not np.array_equal(again.body_q.numpy(), ref.body_q.numpy())
