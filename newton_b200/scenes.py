@@ -19,7 +19,7 @@ import math
 import numpy as np
 import torch
 
-from .sim.articulation import eval_fk
+from .utils.host_fk import host_fk  # noqa: F401  (re-exported: scenes.host_fk)
 from .sim.builder import ModelBuilder
 from .utils import xform as X
 
@@ -85,7 +85,7 @@ def quadruped_builder() -> ModelBuilder:
 def _finish(scene: ModelBuilder, device, run_fk=True):
     model = scene.finalize(device="cpu")
     if run_fk and model.joint_count:
-        eval_fk(model, model.joint_q, model.joint_qd, model)
+        host_fk(model, model.joint_q, model.joint_qd, model)
     return model.to(device) if str(device) != "cpu" else model
 
 

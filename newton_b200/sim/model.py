@@ -349,7 +349,8 @@ class Model:
         out = Model(device)
         for k, v in self.__dict__.items():
             if isinstance(v, torch.Tensor):
-                setattr(out, k, v.to(out.device).contiguous())
+                moved = v.to(out.device).contiguous()
+                setattr(out, k, moved.clone() if moved.data_ptr() == v.data_ptr() else moved)  # same device: still a copy
             elif k != "device":
                 setattr(out, k, v.copy() if isinstance(v, (list, set, dict)) else v)
         # re-establish the aliasing of joint_target_q_start

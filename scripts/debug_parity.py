@@ -9,7 +9,7 @@ its=int(sys.argv[2]) if len(sys.argv)>2 else 2
 N=int(sys.argv[3]) if len(sys.argv)>3 else 100
 model = scenes.quadruped_model(W, seed=1)
 model.joint_q.view(W, -1)[:, 2] = 0.48
-newton_b200.eval_fk(model, model.joint_q, model.joint_qd, model)
+scenes.host_fk(model, model.joint_q, model.joint_qd, model)
 kw={"iterations":its}
 mg = model.to("cuda:0")
 for n in [1,2,5,10,20,50,100][:]:

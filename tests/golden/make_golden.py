@@ -27,7 +27,7 @@ def _standing_quadrupeds():
 
     m = scenes.quadruped_model(2, seed=1)
     m.joint_q.view(2, -1)[:, 2] = 0.46  # feet in contact from the first substep
-    newton_b200.eval_fk(m, m.joint_q, m.joint_qd, m)
+    scenes.host_fk(m, m.joint_q, m.joint_qd, m)
     return m
 
 

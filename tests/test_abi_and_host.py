@@ -83,7 +83,7 @@ def test_sharded_oracle_equals_monolithic(oracle_lib):
 
     m = scenes.quadruped_model(4, seed=7)
     m.joint_q.view(4, -1)[:, 2] = 0.48
-    newton_b200.eval_fk(m, m.joint_q, m.joint_qd, m)
+    scenes.host_fk(m, m.joint_q, m.joint_qd, m)
     kw = {"iterations": 3}
     full, _, _ = simulate(m, oracle_lib.CollisionPipeline, oracle_lib.SolverXPBD, substeps=40, dt=0.005, solver_kwargs=kw)
     parts = [simulate(m.shard(r, 2), oracle_lib.CollisionPipeline, oracle_lib.SolverXPBD, substeps=40, dt=0.005, solver_kwargs=kw)[0]
@@ -105,7 +105,7 @@ def test_two_rank_gloo_state_gather(tmp_path):
         "r, w = dist.get_rank(), dist.get_world_size()\n"
         "m = scenes.quadruped_model(4, seed=7)\n"
         "m.joint_q.view(4, -1)[:, 2] = 0.48\n"
-        "newton_b200.eval_fk(m, m.joint_q, m.joint_qd, m)\n"
+        "scenes.host_fk(m, m.joint_q, m.joint_qd, m)\n"
         "kw = {'iterations': 2}\n"
         "s, _, _ = simulate(m.shard(r, w), oracle.CollisionPipeline, oracle.SolverXPBD, substeps=20, dt=0.005, solver_kwargs=kw)\n"
         "out = torch.empty((w * s.body_q.shape[0], 7))\n"
@@ -135,7 +135,7 @@ def test_oracle_eval_fk_matches_host_walk(oracle_lib):
         g = torch.Generator().manual_seed(0)
         model.joint_qd.copy_(torch.rand(model.joint_qd.shape, generator=g) - 0.5)
         model.joint_q[-2:] += 0.3
-        newton_b200.eval_fk(model, model.joint_q, model.joint_qd, model)
+        scenes.host_fk(model, model.joint_q, model.joint_qd, model)
         host_q, host_qd = model.body_q.clone(), model.body_qd.clone()
         model.body_q.zero_()
         model.body_qd.zero_()

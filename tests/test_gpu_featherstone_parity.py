@@ -42,7 +42,7 @@ def test_config4_quadruped_with_penalty_contacts(oracle_lib, cuda_lib, world_cou
     penalty contacts against the ground, floating base (solve origin at the root COM)."""
     model = scenes.quadruped_model(world_count, seed=1)
     model.joint_q.view(world_count, -1)[:, 2] = 0.47
-    newton_b200.eval_fk(model, model.joint_q, model.joint_qd, model)
+    scenes.host_fk(model, model.joint_q, model.joint_qd, model)
     _compare(model, oracle_lib, 100, 1e-3, {"angular_damping": 0.05, "update_mass_matrix_interval": interval})
 
 

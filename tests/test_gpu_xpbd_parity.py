@@ -54,7 +54,7 @@ def _assert_exact(rs, rc, rcounts, gs, gc, gcounts, model, need_contacts=True):
 
 def _drop(model, worlds, z):
     model.joint_q.view(worlds, -1)[:, 2] = z
-    newton_b200.eval_fk(model, model.joint_q, model.joint_qd, model)
+    scenes.host_fk(model, model.joint_q, model.joint_qd, model)
     return model
 
 
@@ -273,7 +273,7 @@ from newton_b200 import scenes
 from tests.helpers import simulate, rel_err
 m = scenes.quadruped_model(8, seed=1)
 m.joint_q.view(8, -1)[:, 2] = 0.48
-newton_b200.eval_fk(m, m.joint_q, m.joint_qd, m)
+scenes.host_fk(m, m.joint_q, m.joint_qd, m)
 kw = {"iterations": 8}
 rs, _, rc = simulate(m, oracle.CollisionPipeline, oracle.SolverXPBD, substeps=100, dt=0.005, solver_kwargs=kw, record_contacts=True)
 gs, _, gc = simulate(m.to("cuda:0"), newton_b200.CollisionPipeline, newton_b200.solvers.SolverXPBD, substeps=100, dt=0.005, solver_kwargs=kw, record_contacts=True)

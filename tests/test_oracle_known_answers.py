@@ -16,6 +16,7 @@ import pytest
 from newton_b200 import GeoType, scenes
 from newton_b200.sim.builder import ModelBuilder
 from newton_b200.utils import xform as X
+from newton_b200.utils.host_fk import host_fk
 
 I7 = [0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0]
 
@@ -245,7 +246,7 @@ def _pendulum(sphere_radius=0.01):
     b.add_articulation([j])
     model = b.finalize()
     model.joint_q[0] = 0.05
-    newton_b200.eval_fk(model, model.joint_q, model.joint_qd, model)
+    host_fk(model, model.joint_q, model.joint_qd, model)
     return model
 
 
@@ -564,7 +565,7 @@ def test_xpbd_parent_force_single_body(oracle_lib, joint_kind, parent_kinematic)
     model.request_state_attributes("body_parent_f")
     import newton_b200
 
-    newton_b200.eval_fk(model, model.joint_q, model.joint_qd, model)
+    host_fk(model, model.joint_q, model.joint_qd, model)
     solver = oracle_lib.SolverXPBD(model, iterations=8)
     s0, s1 = model.state(), model.state()
     assert s0.body_parent_f is not None
@@ -627,7 +628,7 @@ def test_projectile_motion(oracle_lib, solver_name):
     s0, s1 = model.state(), model.state()
     if solver_name == "featherstone":
         s0.joint_qd[:3] = torch_f32(v0)
-        newton_b200.eval_fk(model, s0.joint_q, s0.joint_qd, s0)
+        host_fk(model, s0.joint_q, s0.joint_qd, s0)
     else:
         s0.body_qd[0, :3] = torch_f32(v0)
     solver = _solver(oracle_lib, solver_name, model)
@@ -667,7 +668,7 @@ def test_joint_actuation_featherstone(oracle_lib):
     j_pri = b.add_joint_prismatic(parent=-1, child=link_pri, axis=(1.0, 0.0, 0.0), parent_xform=X.transform((0.0, 5.0, 0.0)), armature=0.0)
     b.add_articulation([j_pri])
     model = b.finalize()
-    newton_b200.eval_fk(model, model.joint_q, model.joint_qd, model)
+    host_fk(model, model.joint_q, model.joint_qd, model)
     I_zz = float(model.body_inertia[0, 2, 2])
     mass = float(model.body_mass[1])
     solver = oracle_lib.SolverFeatherstone(model, angular_damping=0.0)
@@ -701,7 +702,7 @@ def test_momentum_conservation(oracle_lib, solver_name):
     s0, s1 = model.state(), model.state()
     if solver_name == "featherstone":
         s0.joint_qd.copy_(torch_f32(velocities.reshape(-1)))
-        newton_b200.eval_fk(model, s0.joint_q, s0.joint_qd, s0)
+        host_fk(model, s0.joint_q, s0.joint_qd, s0)
     else:
         s0.body_qd.copy_(torch_f32(velocities))
     masses, inertias = model.body_mass.numpy(), model.body_inertia.numpy()
@@ -741,7 +742,7 @@ def test_torque_free_precession_featherstone(oracle_lib):
     model = b.finalize()
     s0, s1 = model.state(), model.state()
     s0.joint_qd[:3] = torch_f32([0.7, -0.5, 0.9])
-    newton_b200.eval_fk(model, s0.joint_q, s0.joint_qd, s0)
+    host_fk(model, s0.joint_q, s0.joint_qd, s0)
     I_body = model.body_inertia.numpy()[0].astype(np.float64)
 
     def L_world(state):
@@ -893,7 +894,7 @@ def test_body_force_floating_body(oracle_lib, solver_name, angular, use_control)
     body = b.add_body(xform=X.transform((1.0, 2.0, 3.0), rot))
     b.add_shape_box(body, hx=0.5, hy=0.5, hz=0.5)
     model = b.finalize()
-    newton_b200.eval_fk(model, model.joint_q, model.joint_qd, model)
+    host_fk(model, model.joint_q, model.joint_qd, model)
     solver = _solver(oracle_lib, solver_name, model) if solver_name == "featherstone" else oracle_lib.SolverXPBD(model, angular_damping=0.0)
     s0, s1 = model.state(), model.state()
     ctl = model.control() if use_control else None
@@ -951,7 +952,7 @@ def test_body_force_at_com_offset_causes_no_rotation(oracle_lib, solver_name, co
     b.add_shape_box(body, hx=0.1, hy=0.1, hz=0.1)
     b.body_com[body] = np.array(com)
     model = b.finalize()
-    newton_b200.eval_fk(model, model.joint_q, model.joint_qd, model)
+    host_fk(model, model.joint_q, model.joint_qd, model)
     solver = _solver(oracle_lib, solver_name, model) if solver_name == "featherstone" else oracle_lib.SolverXPBD(model, angular_damping=0.0)
     s0, s1 = model.state(), model.state()
     direction = np.array([0.0, 1.0, 0.0], dtype=np.float32)
