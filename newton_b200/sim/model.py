@@ -332,6 +332,32 @@ class Model:
             return AttributeFrequency.ARTICULATION
         raise KeyError(f"Attribute frequency of '{name}' is not known")
 
+    def set_gravity(self, gravity, world: int | None = None) -> None:
+        """Runtime gravity change (reference ``sim/model.py:1908-1951``): one vector for every world (and the global slot), one
+        per local world, one per local world plus the global slot, or - with ``world`` - a single world (``-1`` = global).
+        Call ``solver.notify_model_changed(ModelFlags.MODEL_PROPERTIES)`` afterwards, as with the reference."""
+        gravity_np = np.asarray(gravity, dtype=np.float32)
+        current = self.gravity.detach().cpu().numpy().copy()
+        if world is not None:
+            if gravity_np.shape != (3,):
+                raise ValueError("Expected single gravity vector (3,) when world is specified")
+            if world < -1 or world >= self.world_count:
+                raise IndexError(f"world {world} out of range; expected -1 or [0, {self.world_count})")
+            current[world] = gravity_np
+        elif gravity_np.ndim == 1:
+            if gravity_np.shape != (3,):
+                raise ValueError(f"Expected gravity with shape (3,), got {gravity_np.shape}")
+            current[:] = gravity_np
+        else:
+            local_shape, full_shape = (self.world_count, 3), (self.gravity.shape[0], 3)
+            if gravity_np.shape == full_shape:
+                current[:] = gravity_np
+            elif gravity_np.shape == local_shape:
+                current[: self.world_count] = gravity_np
+            else:
+                raise ValueError(f"Expected gravity with shape {local_shape} or {full_shape}, got {gravity_np.shape}")
+        self.gravity.copy_(torch.from_numpy(current))  # in place: the native model borrows this array's pointer
+
     def request_contact_attributes(self, *attributes: str) -> None:
         self._requested_contact_attributes.update(attributes)
 

@@ -106,6 +106,10 @@ class SolverXPBD:
     def reset(self, state, world_mask=None, flags=None):
         """SolverBase.reset (solvers/solver.py:344-375): no-op for XPBD."""
 
+    def notify_model_changed(self, flags):
+        """SolverBase.notify_model_changed (solvers/solver.py:394-429): the kernels read the Model arrays on every step."""
+        self._desc = _abi.model_desc(self.model)
+
     def step(self, state_in, state_out, control, contacts, dt):
         if control is None:
             control = self.model.control(clone_variables=False)
@@ -160,6 +164,10 @@ class SolverFeatherstone:
 
     def reset(self, state, world_mask=None, flags=None):
         """SolverBase.reset (solvers/solver.py:344-375): no-op for Featherstone."""
+
+    def notify_model_changed(self, flags):
+        """SolverBase.notify_model_changed (solvers/solver.py:394-429): the kernels read the Model arrays on every step."""
+        self._desc = _abi.model_desc(self.model)
 
     def step(self, state_in, state_out, control, contacts, dt):
         if control is None:

@@ -1,0 +1,502 @@
+"""More of the reference's own closed-form / known-answer checks for the hot path, run on the CPU oracle.
+
+* ``newton/tests/test_up_axis.py``          - one step of free fall along the configured up axis, both solvers
+* ``newton/tests/test_control_force.py``    - ``Control.joint_f`` on a FREE root, on a 3-prismatic D6 joint, with a child-frame
+                                              moment arm (XPBD ``apply_joint_forces``)
+* ``newton/tests/test_runtime_gravity.py``  - ``Model.set_gravity`` (all worlds / one world / array / global slot / implicit
+                                              world / invalid world), per-world gravity in the solvers, global-world bodies
+"""
+
+import numpy as np
+import pytest
+import torch
+
+from newton_b200 import ModelFlags
+from newton_b200.sim.builder import JointDofConfig, ModelBuilder
+from newton_b200.utils import xform as X
+from newton_b200.utils.host_fk import host_fk
+
+
+def _solver(oracle_lib, name, model):
+    cls = oracle_lib.SolverFeatherstone if name == "featherstone" else oracle_lib.SolverXPBD
+    return cls(model, angular_damping=0.0)
+
+
+def _quat_between_z_and(axis):
+    return {"y": X.quat_from_axis_angle(np.array([1.0, 0.0, 0.0]), -np.pi / 2), "z": np.array([0.0, 0.0, 0.0, 1.0])}[axis]
+
+
+def _quat_rpy(r, p, y):
+    """wp.quat_rpy (roll about x, pitch about y, yaw about z)."""
+    cy, sy, cr, sr, cp, sp = np.cos(y * 0.5), np.sin(y * 0.5), np.cos(r * 0.5), np.sin(r * 0.5), np.cos(p * 0.5), np.sin(p * 0.5)
+    return np.array([sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy, cr * cp * cy + sr * sp * sy])
+
+
+# ---- test_up_axis.py:16-37 -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("solver_name", ["featherstone", "xpbd"])
+@pytest.mark.parametrize("axis", ["y", "z"])
+def test_gravity_follows_up_axis(oracle_lib, solver_name, axis):
+    g = [0.0, 0.0, 0.0]
+    g["xyz".index(axis)] = -9.81
+    builder = ModelBuilder(up_axis=axis, gravity=tuple(g))
+    b = builder.add_body()
+    builder.add_shape_capsule(b, xform=X.transform((0.0, 0.0, 0.0), _quat_between_z_and(axis)))
+    model = builder.finalize()
+    s0, s1 = model.state(), model.state()
+    _solver(oracle_lib, solver_name, model).step(s0, s1, model.control(), None, 1.0 / 10.0)
+    assert s1.body_qd.numpy()[0, "xyz".index(axis)] == pytest.approx(-0.981, abs=1e-5)
+
+
+# ---- test_control_force.py:48-84 -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("solver_name", ["featherstone", "xpbd"])
+def test_control_force_floating_body_angular(oracle_lib, solver_name):
+    builder = ModelBuilder(up_axis="y", gravity=(0.0, 0.0, 0.0))
+    b = builder.add_body()
+    builder.add_shape_box(b)
+    builder.joint_q = [1.0, 2.0, 3.0, *_quat_rpy(-1.3, 0.8, 2.4)]
+    model = builder.finalize()
+    solver = _solver(oracle_lib, solver_name, model)
+    s0, s1 = model.state(), model.state()
+    oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, s0)
+    control = model.control()
+    control.joint_f.copy_(torch.tensor([0.0, 0.0, 0.0, 0.0, 0.0, 100.0]))
+    for _ in range(4):
+        solver.step(s0, s1, control, None, 1.0 / 10.0)
+        s0, s1 = s1, s0
+    qd = s0.body_qd.numpy()[0]
+    assert 0.04 < qd[5] < 0.4
+    assert np.abs(qd[:5]).max() <= 2e-6
+
+
+# ---- test_control_force.py:87-136 ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("solver_name", ["featherstone", "xpbd"])
+def test_control_force_3d_articulation(oracle_lib, solver_name):
+    builder = ModelBuilder(gravity=(0.0, 0.0, 0.0))
+    builder.default_shape_cfg.density = 100.0
+    b = builder.add_link()
+    builder.add_shape_sphere(b)
+    j = builder.add_joint_d6(-1, b, linear_axes=[JointDofConfig(axis=a, armature=0.0) for a in ((1, 0, 0), (0, 1, 0), (0, 0, 1))])
+    builder.add_articulation([j])
+    model = builder.finalize()
+    assert model.joint_dof_count == 3
+    for dim in range(3):
+        solver = _solver(oracle_lib, solver_name, model)
+        s0, s1 = model.state(), model.state()
+        control = model.control()
+        f = np.zeros(3, dtype=np.float32)
+        f[dim] = 100.0
+        control.joint_f.copy_(torch.from_numpy(f))
+        for _ in range(4):
+            solver.step(s0, s1, control, None, 1.0 / 10.0)
+            s0, s1 = s1, s0
+        if solver_name == "xpbd":  # maximal-coordinate solver: recover joint_qd from body_qd
+            assert oracle_lib.eval_ik(model, s0, s0.joint_q, s0.joint_qd) in (0, None)
+        qd = s0.joint_qd.numpy()
+        assert 0.009 < qd[dim] < 0.4
+        assert np.abs(np.delete(qd, dim)).max() <= 1e-6
+
+
+# ---- test_control_force.py:139-197 (regression of the reference's issue #1261) ---------------------------------------------
+def test_control_force_child_xform_moment_arm_xpbd(oracle_lib):
+    offset_y = 2.0
+    builder = ModelBuilder(gravity=(0.0, 0.0, 0.0))
+    builder.default_shape_cfg.density = 100.0
+    b = builder.add_link()
+    builder.add_shape_sphere(b)
+    axes = ((1, 0, 0), (0, 1, 0), (0, 0, 1))
+    j = builder.add_joint_d6(-1, b, child_xform=X.transform((0.0, offset_y, 0.0)),
+                             linear_axes=[JointDofConfig(axis=a, armature=0.0) for a in axes],
+                             angular_axes=[JointDofConfig(axis=a, armature=0.0) for a in axes])
+    builder.add_articulation([j])
+    model = builder.finalize()
+    solver = _solver(oracle_lib, "xpbd", model)
+    s0, s1 = model.state(), model.state()
+    control = model.control()
+    f = np.zeros(model.joint_dof_count, dtype=np.float32)
+    f[0] = 100.0  # force along X at the joint anchor, 2 m above the COM
+    control.joint_f.copy_(torch.from_numpy(f))
+    for _ in range(4):
+        solver.step(s0, s1, control, None, 1.0 / 10.0)
+        s0, s1 = s1, s0
+    qd = s0.body_qd.numpy()[0]
+    assert qd[0] > 0.001
+    assert qd[5] < -0.001  # cross((0, offset_y, 0), (F, 0, 0)) = (0, 0, -F offset_y)
+
+
+# ---- test_runtime_gravity.py -----------------------------------------------------------------------------------------------
+def _box_world():
+    w = ModelBuilder(gravity=(0.0, 0.0, -9.81))
+    w.default_shape_cfg.density = 1000.0
+    b = w.add_body()
+    w.add_shape_box(b, hx=0.5, hy=0.5, hz=0.5)
+    return w
+
+
+def _run(solver, model, s0, s1, n, dt=0.01):
+    control = model.control()
+    for _ in range(n):
+        s0.clear_forces()
+        solver.step(s0, s1, control, None, dt)
+        s0, s1 = s1, s0
+    return s0, s1
+
+
+def test_runtime_gravity_bodies_xpbd(oracle_lib):
+    """:124-163"""
+    model = _box_world().finalize()
+    solver = oracle_lib.SolverXPBD(model)
+    s0, s1 = _run(solver, model, model.state(), model.state(), 10)
+    assert s0.body_qd.numpy()[0, 2] < -0.5
+    model.set_gravity((9.81, 0.0, 0.0))
+    solver.notify_model_changed(ModelFlags.MODEL_PROPERTIES)
+    s0, s1 = _run(solver, model, s0, s1, 20)
+    assert s0.body_qd.numpy()[0, 0] > 0.5
+
+
+@pytest.mark.parametrize("solver_name", ["xpbd", "featherstone"])
+def test_per_world_gravity_bodies(oracle_lib, solver_name):
+    """:266-318 (the reference runs it with XPBD; the Featherstone oracle reads the same gravity[body_world])."""
+    main = ModelBuilder(gravity=(0.0, 0.0, -9.81))
+    main.replicate(_box_world(), 3)
+    model = main.finalize()
+    solver = oracle_lib.SolverXPBD(model) if solver_name == "xpbd" else oracle_lib.SolverFeatherstone(model, angular_damping=0.0)
+    assert model.gravity.shape[0] == 4
+    model.set_gravity((0.0, 0.0, 0.0), world=0)
+    model.set_gravity((0.0, 0.0, -4.905), world=1)
+    model.set_gravity((0.0, 0.0, -9.81), world=2)
+    solver.notify_model_changed(ModelFlags.MODEL_PROPERTIES)
+    s0, _ = _run(solver, model, model.state(), model.state(), 10)
+    vz = s0.body_qd.numpy()[:, 2]
+    assert vz[0] == pytest.approx(0.0, abs=5e-5)
+    assert vz[2] < vz[1] < 0.0 and vz[2] < -0.5
+    assert vz[1] == pytest.approx(-0.4905, abs=1e-5) and vz[2] == pytest.approx(-0.981, abs=1e-5)
+
+
+def test_global_gravity_bodies_xpbd(oracle_lib):
+    """:362-381 - a body of the global world -1 falls with the LAST gravity entry (negative-index wrap)."""
+    builder = ModelBuilder(gravity=(0.0, 0.0, -2.0))
+    global_body = builder.add_body(mass=1.0, inertia=np.eye(3))
+    builder.begin_world(gravity=(0.0, 0.0, -5.0))
+    local_body = builder.add_body(mass=1.0, inertia=np.eye(3))
+    builder.end_world()
+    model = builder.finalize()
+    assert model.numpy("body_world").tolist() == [-1, 0]
+    np.testing.assert_allclose(model.numpy("gravity"), ((0.0, 0.0, -5.0), (0.0, 0.0, -2.0)), atol=1e-6)
+    s_in, s_out = model.state(), model.state()
+    oracle_lib.SolverXPBD(model).step(s_in, s_out, model.control(), None, 0.1)
+    qd = s_out.body_qd.numpy()
+    assert qd[global_body, 2] == pytest.approx(-0.2, abs=1e-6)
+    assert qd[local_body, 2] == pytest.approx(-0.5, abs=1e-6)
+
+
+def test_set_gravity_spellings():
+    """:461-489, :513-538, :559-579, :582-595, :603-613 (bodies instead of particles)."""
+    builder = ModelBuilder(gravity=(0.0, 0.0, -9.81))
+    for _ in range(2):
+        builder.begin_world()
+        builder.add_body(mass=1.0, inertia=np.eye(3))
+        builder.end_world()
+    model = builder.finalize()
+    g = model.numpy("gravity")
+    assert len(g) == 3 and np.allclose(g[:, 2], -9.81, atol=1e-4)
+    ptr = model.gravity.data_ptr()
+    model.set_gravity((0.0, 0.0, 0.0), world=0)
+    assert model.gravity.data_ptr() == ptr  # updated in place: the native model keeps borrowing the same array
+    g = model.numpy("gravity")
+    assert g[0, 2] == 0.0 and g[1, 2] == pytest.approx(-9.81, abs=1e-4) and g[-1, 2] == pytest.approx(-9.81, abs=1e-4)
+    curriculum = np.array([[0.0, 0.0, s * -9.81] for s in np.linspace(0.0, 1.0, 2)], dtype=np.float32)
+    model.set_gravity(curriculum)
+    g = model.numpy("gravity")
+    np.testing.assert_allclose(g[:2], curriculum, atol=1e-6)
+    assert g[-1, 2] == pytest.approx(-9.81, abs=1e-4)  # local-world-only input keeps the global entry
+
+    builder = ModelBuilder(gravity=(0.0, 0.0, -9.81))
+    builder.begin_world(gravity=(0.0, 0.0, -1.0))
+    builder.add_body(mass=1.0, inertia=np.eye(3))
+    builder.end_world()
+    model = builder.finalize()
+    np.testing.assert_allclose(model.numpy("gravity"), ((0.0, 0.0, -1.0), (0.0, 0.0, -9.81)), atol=1e-6)
+    model.set_gravity((0.0, 0.0, -2.0), world=-1)
+    np.testing.assert_allclose(model.numpy("gravity"), ((0.0, 0.0, -1.0), (0.0, 0.0, -2.0)), atol=1e-6)
+    model.set_gravity(np.array(((0.0, 0.0, -3.0),), dtype=np.float32))
+    np.testing.assert_allclose(model.numpy("gravity"), ((0.0, 0.0, -3.0), (0.0, 0.0, -2.0)), atol=1e-6)
+    model.set_gravity(np.array(((0.0, 0.0, -4.0), (0.0, 0.0, -5.0)), dtype=np.float32))
+    np.testing.assert_allclose(model.numpy("gravity"), ((0.0, 0.0, -4.0), (0.0, 0.0, -5.0)), atol=1e-6)
+    model.set_gravity((0.0, 0.0, -6.0))
+    np.testing.assert_allclose(model.numpy("gravity"), ((0.0, 0.0, -6.0), (0.0, 0.0, -6.0)), atol=1e-6)
+    with pytest.raises(IndexError):
+        model.set_gravity((0.0, 0.0, 0.0), world=1)
+    with pytest.raises(IndexError):
+        model.set_gravity((0.0, 0.0, 0.0), world=-2)
+    with pytest.raises(ValueError):
+        model.set_gravity((0.0, 0.0), world=0)
+    with pytest.raises(ValueError):
+        model.set_gravity(np.zeros((5, 3)))
+
+    implicit = ModelBuilder()
+    implicit.add_body(mass=1.0, inertia=np.eye(3))
+    model = implicit.finalize()
+    assert model.world_count == 1 and tuple(model.gravity.shape) == (1, 3)
+    model.set_gravity((0.0, 0.0, -2.0), world=0)
+    np.testing.assert_allclose(model.numpy("gravity"), ((0.0, 0.0, -2.0),), atol=1e-6)
+    model.set_gravity(np.array(((0.0, 0.0, -3.0),), dtype=np.float32))
+    np.testing.assert_allclose(model.numpy("gravity"), ((0.0, 0.0, -3.0),), atol=1e-6)
+
+
+def test_implicit_world_gravity_drives_the_solver(oracle_lib):
+    """:582-600 with a body: gravity[0] is shared by world 0 and the global world of an implicit single-world model."""
+    implicit = ModelBuilder()
+    implicit.add_body(mass=1.0, inertia=np.eye(3))
+    model = implicit.finalize()
+    model.set_gravity((0.0, 0.0, -4.0))
+    s_in, s_out = model.state(), model.state()
+    oracle_lib.SolverXPBD(model).step(s_in, s_out, model.control(), None, 0.1)
+    assert s_out.body_qd.numpy()[0, 2] == pytest.approx(-0.4, abs=1e-6)
+
+
+# ---- test_rigid_friction_ramp.py (XPBD rows of its solver matrix: SolverXPBD(iterations=10)) ------------------------------------
+import math  # noqa: E402
+
+import newton_b200  # noqa: E402
+
+SIM_DT, SIM_SUBSTEPS = 1.0 / 60.0, 30
+
+
+def _simulate_frames(oracle_lib, solver, pipe, contacts, model, s0, s1, frames):
+    control = model.control()
+    for _ in range(frames * SIM_SUBSTEPS):
+        s0.clear_forces()
+        pipe.collide(s0, contacts)
+        solver.step(s0, s1, control, contacts, SIM_DT / SIM_SUBSTEPS)
+        s0, s1 = s1, s0
+    return s0, s1
+
+
+def test_xpbd_friction_ramp_grid(oracle_lib):
+    """:113-223 - a 5 x 5 grid of slabs on tilted ramps, mu in {0.1 .. 1.0} x angle in {3 .. 40 deg}: below the critical angle
+    atan(mu) (minus 2 deg) a slab stays put (|v| < 0.1 m/s, drift < 2 cm over 0.25 s after settling), above it (plus 2 deg) it
+    slides (>= 2 cm).  Box-on-box contacts: MPR manifolds + the XPBD friction projection."""
+    mus, angles = (0.10, 0.30, 0.50, 0.70, 1.00), (3.0, 10.0, 20.0, 30.0, 40.0)
+    builder = ModelBuilder(up_axis="z", gravity=(0.0, 0.0, -9.81))
+    box_ids = []
+    for row, mu in enumerate(mus):
+        ids = []
+        for col, angle_deg in enumerate(angles):
+            cfg = newton_b200.ShapeConfig()
+            cfg.collision_group = col + len(mus) * row + 1
+            cfg.mu, cfg.ke, cfg.kd, cfg.kf, cfg.gap = mu, 1.0e5, 1.0e3, 0.0, 0.0
+            q = X.quat_from_axis_angle(np.array([1.0, 0.0, 0.0]), math.radians(angle_deg))
+            center = np.array([col * 2.5, row * 6.0, 2.0])
+            builder.add_shape_box(-1, xform=X.transform(center, q), hx=0.5, hy=2.5, hz=0.05, cfg=cfg)
+            up = X.quat_rotate(q, np.array([0.0, 0.0, 1.0]))
+            body = builder.add_body(xform=X.transform(center + (0.05 + 0.05 + 0.001) * up, q), label=f"box_r{row}_c{col}")
+            builder.add_shape_box(body, hx=0.2, hy=0.2, hz=0.05, cfg=cfg)
+            ids.append(body)
+        box_ids.append(ids)
+    model = builder.finalize()
+    solver = oracle_lib.SolverXPBD(model, iterations=10)
+    pipe = oracle_lib.CollisionPipeline(model)
+    contacts = pipe.contacts()
+    s0, s1 = _simulate_frames(oracle_lib, solver, pipe, contacts, model, model.state(), model.state(), 30)
+    settle_q = s0.body_q.numpy().copy()
+    s0, s1 = _simulate_frames(oracle_lib, solver, pipe, contacts, model, s0, s1, 15)
+    final_q, final_qd = s0.body_q.numpy(), s0.body_qd.numpy()
+    assert np.isfinite(final_q).all() and np.isfinite(final_qd).all()
+    failures, static_cells, sliding_cells = [], 0, 0
+    for row, mu in enumerate(mus):
+        crit = math.degrees(math.atan(mu))
+        for col, theta in enumerate(angles):
+            bid = box_ids[row][col]
+            v = float(np.linalg.norm(final_qd[bid, :3]))
+            disp = float(np.linalg.norm(final_q[bid, :3] - settle_q[bid, :3]))
+            tag = f"(mu={mu:.2f}, theta={theta:.1f}, crit={crit:.1f})"
+            if theta < crit - 2.0:
+                static_cells += 1
+                if v >= 0.10 or disp >= 0.02:
+                    failures.append(f"{tag}: expected static, |v|={v:.4f} disp={disp:.4f}")
+            elif theta > crit + 2.0:
+                sliding_cells += 1
+                if disp < 0.02:
+                    failures.append(f"{tag}: expected sliding, disp={disp:.4f}")
+    assert static_cells == 15 and sliding_cells == 10  # no cell of this grid falls inside the +-2 deg dead band
+    assert not failures, "\n".join(failures)
+
+
+def test_xpbd_friction_stopping_distance(oracle_lib):
+    """:226-367 - a box launched at v0 = 2 m/s on a patch of matching mu stops after d = v0^2 / (2 mu g), within 1 %, and then
+    stays at rest (drift < 0.05 m/s)."""
+    mus, v0, g = (0.20, 0.40, 0.70), 2.0, 9.81
+    builder = ModelBuilder(up_axis="z", gravity=(0.0, 0.0, -g))
+    box_ids = []
+    for i, mu in enumerate(mus):
+        cfg = newton_b200.ShapeConfig()
+        cfg.collision_group = i + 1
+        cfg.mu, cfg.ke, cfg.kd, cfg.kf, cfg.gap = mu, 1.0e5, 0.0, 0.0, 0.0
+        y = i * 5.0
+        builder.add_shape_box(-1, xform=X.transform((5.0 - 0.5, y, -0.05)), hx=5.0, hy=0.6, hz=0.05, cfg=cfg)
+        body = builder.add_body(xform=X.transform((0.0, y, 0.25 + 0.001)), label=f"box_mu{mu:.2f}")
+        builder.add_shape_box(body, hx=0.25, hy=0.25, hz=0.25, cfg=cfg)
+        box_ids.append(body)
+    model = builder.finalize()
+    solver = oracle_lib.SolverXPBD(model, iterations=10)
+    pipe = oracle_lib.CollisionPipeline(model)
+    contacts = pipe.contacts()
+    s0, s1 = _simulate_frames(oracle_lib, solver, pipe, contacts, model, model.state(), model.state(), 30)
+    initial_q = s0.body_q.numpy().copy()
+    s0.body_qd[box_ids] = torch.tensor([v0, 0.0, 0.0, 0.0, 0.0, 0.0])
+    frames = int(math.ceil(1.5 * v0 / (min(mus) * g) / SIM_DT))
+    s0, s1 = _simulate_frames(oracle_lib, solver, pipe, contacts, model, s0, s1, frames)
+    final_q = s0.body_q.numpy().copy()
+    s0, s1 = _simulate_frames(oracle_lib, solver, pipe, contacts, model, s0, s1, 15)
+    rest_q = s0.body_q.numpy()
+    assert np.isfinite(final_q).all() and np.isfinite(rest_q).all()
+    for bid, mu in zip(box_ids, mus):
+        d_expected = v0 * v0 / (2.0 * mu * g)
+        d = float(np.linalg.norm(final_q[bid, :2] - initial_q[bid, :2]))
+        assert abs(d - d_expected) / d_expected <= 0.01, (mu, d, d_expected)
+        assert float(np.linalg.norm(rest_q[bid, :2] - final_q[bid, :2])) / (15 * SIM_DT) < 0.05, mu
+
+
+# ---- test_joint_controllers.py:35-101, 627-665 (revolute PD targets; XPBD(iterations=5) and Featherstone rows) --------------------
+@pytest.mark.parametrize("solver_name", ["featherstone", "xpbd"])
+@pytest.mark.parametrize("pos_target,vel_target,expected_pos,expected_vel,ke,kd",
+                         [(math.pi / 2.0, 0.0, math.pi / 2.0, 0.0, 2000.0, 500.0), (0.0, math.pi / 2.0, None, math.pi / 2.0, 0.0, 500.0)])
+def test_revolute_joint_controller(oracle_lib, solver_name, pos_target, vel_target, expected_pos, expected_vel, ke, kd):
+    builder = ModelBuilder(up_axis="y", gravity=(0.0, 0.0, 0.0))
+    b = builder.add_link(inertia=np.eye(3), mass=1.0)
+    cfg = newton_b200.ShapeConfig()
+    cfg.density = 1.0
+    builder.add_shape_box(b, hx=0.2, hy=0.2, hz=0.2, cfg=cfg)
+    j = builder.add_joint_revolute(-1, b, parent_xform=X.transform((0.0, 2.0, 0.0)), child_xform=X.transform((0.0, 2.0, 0.0)), axis=(0.0, 0.0, 1.0),
+                                   target_pos=pos_target, target_vel=vel_target, armature=0.0, limit_ke=0.0, limit_kd=0.0, target_ke=ke, target_kd=kd)
+    builder.add_articulation([j])
+    model = builder.finalize()
+    solver = oracle_lib.SolverFeatherstone(model, angular_damping=0.0) if solver_name == "featherstone" else \
+        oracle_lib.SolverXPBD(model, angular_damping=0.0, iterations=5)
+    s0, s1 = model.state(), model.state()
+    oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, s0)
+    control = model.control()
+    control.joint_target_q.copy_(torch.tensor([pos_target], dtype=torch.float32))
+    control.joint_target_qd.copy_(torch.tensor([vel_target], dtype=torch.float32))
+    for _ in range(100):
+        s0.clear_forces()
+        solver.step(s0, s1, control, None, 1.0 / 60.0)
+        s0, s1 = s1, s0
+    if solver_name == "xpbd":
+        oracle_lib.eval_ik(model, s0, s0.joint_q, s0.joint_qd)
+    if expected_pos is not None:
+        assert float(s0.joint_q[0]) == pytest.approx(expected_pos, abs=1e-2)
+    if expected_vel is not None:
+        assert float(s0.joint_qd[0]) == pytest.approx(expected_vel, abs=1e-2)
+
+
+# ---- test_joint_damping.py:17-146, 190-212 (Featherstone rows) ---------------------------------------------------------------------
+def _damped_spin(oracle_lib, kind, damping):
+    builder = ModelBuilder(gravity=(0.0, 0.0, 0.0), up_axis="y")
+    body = builder.add_link(mass=1.0, inertia=np.eye(3), lock_inertia=True)
+    if kind == "revolute":
+        joint = builder.add_joint_revolute(-1, body, axis=(0.0, 0.0, 1.0), target_ke=0.0, target_kd=0.0, damping=damping, limit_lower=-1.0e6,
+                                           limit_upper=1.0e6, limit_ke=0.0, limit_kd=0.0, armature=0.0, friction=0.0)
+    else:
+        joint = builder.add_joint_ball(-1, body, damping=damping, armature=0.0, friction=0.0)
+    builder.add_articulation([joint])
+    builder.joint_qd[0] = 1.0
+    model = builder.finalize()
+    solver = oracle_lib.SolverFeatherstone(model, angular_damping=0.0)
+    s0, s1 = model.state(), model.state()
+    control = model.control()
+    oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, s0)
+    n = 1 if kind == "revolute" else 3
+    initial = float(np.linalg.norm(s0.joint_qd.numpy()[:n]))
+    for _ in range(8):
+        solver.step(s0, s1, control, None, 0.01)
+        s0, s1 = s1, s0
+    return model, initial, float(np.linalg.norm(s0.joint_qd.numpy()[:n]))
+
+
+@pytest.mark.parametrize("kind", ["revolute", "ball"])
+def test_featherstone_joint_damping_decays_velocity(oracle_lib, kind):
+    _, undamped_initial, undamped_final = _damped_spin(oracle_lib, kind, 0.0)
+    model, damped_initial, damped_final = _damped_spin(oracle_lib, kind, 3.0)
+    assert undamped_final == pytest.approx(undamped_initial, abs=1e-5, rel=1e-5)
+    assert damped_final < damped_initial * 0.85
+    if kind == "ball":
+        np.testing.assert_allclose(model.numpy("joint_damping")[:3], [3.0, 3.0, 3.0])  # add_joint_ball(damping=...) reaches every axis
+
+
+# ---- test_body_velocity.py:124-371, 848-951 (free body with an offset centre of mass; XPBD and Featherstone rows) -----------------------
+COM_OFFSETS = [(0.5, 0.0, 0.0), (0.0, 0.3, 0.0), (0.0, 0.0, 0.4), (0.2, 0.3, 0.1)]
+AXES = [(0.0, 0.0, 1.0), (0.0, 1.0, 0.0), (1.0, 0.0, 0.0)]
+BODY_VELOCITY_SOLVERS = [("featherstone", True, 1e-3), ("xpbd", False, 1e-4)]  # (name, state set through joint_qd, CoM tolerance [m])
+
+
+def _com_world(state, model, body=0):
+    q = state.body_q.numpy()[body].astype(np.float64)
+    return q[:3] + X.quat_rotate(q[3:], model.numpy("body_com")[body].astype(np.float64))
+
+
+def _free_body_run(oracle_lib, solver_name, generalized, com, velocity, initial_pos):
+    builder = ModelBuilder(gravity=(0.0, 0.0, 0.0))
+    b = builder.add_body(xform=X.transform(initial_pos))
+    builder.add_shape_box(b, hx=0.1, hy=0.1, hz=0.1)
+    builder.body_com[b] = np.asarray(com, dtype=np.float64)
+    model = builder.finalize()
+    solver = _solver(oracle_lib, solver_name, model)
+    s0, s1 = model.state(), model.state()
+    oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, s0)
+    v = torch.tensor(velocity, dtype=torch.float32)
+    if generalized:  # Featherstone integrates joint_qd; body_qd follows through FK
+        s0.joint_qd.copy_(v)
+        oracle_lib.eval_fk(model, s0.joint_q, s0.joint_qd, s0)
+    else:  # XPBD integrates body_qd
+        s0.body_qd.copy_(v.reshape(1, 6))
+    q0, com0 = s0.body_q.numpy()[0].copy(), _com_world(s0, model)
+    for _ in range(10):
+        solver.step(s0, s1, None, None, 0.01)
+        s0, s1 = s1, s0
+    return q0, com0, s0.body_q.numpy()[0].copy(), _com_world(s0, model)
+
+
+@pytest.mark.parametrize("solver_name,generalized,tol", BODY_VELOCITY_SOLVERS)
+@pytest.mark.parametrize("com", COM_OFFSETS)
+@pytest.mark.parametrize("omega", AXES)
+def test_angular_velocity_keeps_com_stationary(oracle_lib, solver_name, generalized, tol, com, omega):
+    q0, com0, q1, com1 = _free_body_run(oracle_lib, solver_name, generalized, com, (0.0, 0.0, 0.0, *omega), (1.0, 2.0, 3.0))
+    assert np.linalg.norm(com1 - com0) < tol
+    assert abs(np.dot(q0[3:], q1[3:])) < 0.9999  # it did rotate
+
+
+@pytest.mark.parametrize("solver_name,generalized,tol", BODY_VELOCITY_SOLVERS)
+@pytest.mark.parametrize("com", COM_OFFSETS)
+@pytest.mark.parametrize("direction", AXES)
+def test_linear_velocity_moves_com(oracle_lib, solver_name, generalized, tol, com, direction):
+    v = tuple(0.7 * d for d in direction[::-1])  # (0.7, 0, 0), (0, 0.7, 0), (0, 0, 0.7)
+    _, com0, _, com1 = _free_body_run(oracle_lib, solver_name, generalized, com, (*v, 0.0, 0.0, 0.0), (0.0, 0.0, 1.0))
+    assert np.linalg.norm((com1 - com0) - np.array(v) * 0.1) < tol
+
+
+@pytest.mark.parametrize("solver_name,generalized,tol", BODY_VELOCITY_SOLVERS)
+@pytest.mark.parametrize("com", COM_OFFSETS)
+def test_combined_velocity_com_follows_linear_part(oracle_lib, solver_name, generalized, tol, com):
+    q0, com0, q1, com1 = _free_body_run(oracle_lib, solver_name, generalized, com, (0.1, 0.0, 0.0, 0.0, 0.0, 1.0), (0.0, 0.0, 1.0))
+    assert np.linalg.norm((com1 - com0) - np.array([0.1, 0.0, 0.0]) * 0.1) < tol
+    assert abs(np.dot(q0[3:], q1[3:])) < 0.9999
+
+
+def test_featherstone_root_free_joint_under_rotated_parent_xform_reports_parent_frame_qd(oracle_lib):
+    """:374-405 - joint_qd of a root FREE joint lives in the (rotated) parent joint frame, body_qd in the world frame at the COM."""
+    builder = ModelBuilder(gravity=(0.0, 0.0, -10.0), up_axis="z")
+    parent_xform = X.transform((0.5, 0.6, 0.7), X.quat_from_axis_angle(np.array([1.0, 0.0, 0.0]), np.pi / 2.0))
+    body = builder.add_link(mass=1.0, inertia=np.eye(3))
+    builder.add_articulation([builder.add_joint_free(parent=-1, child=body, parent_xform=parent_xform)])
+    model = builder.finalize()
+    solver = oracle_lib.SolverFeatherstone(model, angular_damping=0.0)
+    s0, s1 = model.state(), model.state()
+    oracle_lib.eval_fk(model, s0.joint_q, s0.joint_qd, s0)
+    dt = 1e-2
+    pipe = oracle_lib.CollisionPipeline(model)
+    solver.step(s0, s1, model.control(), pipe.contacts(), dt)
+    np.testing.assert_allclose(s1.joint_qd.numpy()[0:3], (0.0, -10.0 * dt, 0.0), atol=1e-5)  # world -Z is the parent frame's -Y
+    np.testing.assert_allclose(s1.joint_qd.numpy()[3:6], (0.0, 0.0, 0.0), atol=1e-5)
+    np.testing.assert_allclose(s1.body_qd.numpy()[body, 0:3], (0.0, 0.0, -10.0 * dt), atol=1e-5)
+    np.testing.assert_allclose(s1.body_qd.numpy()[body, 3:6], (0.0, 0.0, 0.0), atol=1e-5)
