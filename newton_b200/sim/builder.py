@@ -838,6 +838,7 @@ class ModelBuilder:
         m.body_label, m.joint_label, m.shape_label = list(self.body_label), list(self.joint_label), list(self.shape_label)
         m.articulation_label = list(self.articulation_label)
         m.body_shapes = {b: list(s) for b, s in self.body_shapes.items()}
+        m.shape_collision_filter_pairs = set(self.shape_collision_filter_pairs)  # reference Model.shape_collision_filter_pairs
 
         def arr(values, trailing, dtype):
             np_dtype = {F32: np.float32, I32: np.int32, torch.bool: np.bool_}[dtype]

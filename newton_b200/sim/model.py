@@ -261,6 +261,7 @@ class Model:
         self.shape_label: list[str] = []
         self.articulation_label: list[str] = []
         self.body_shapes: dict[int, list[int]] = {-1: []}
+        self.shape_collision_filter_pairs: set[tuple[int, int]] = set()
         self.particle_grid = None
         for group in (_BODY_FIELDS, _JOINT_FIELDS, _DOF_FIELDS, _COORD_FIELDS, _SHAPE_FIELDS):
             for name in group:

@@ -57,12 +57,25 @@ def _check_cpu(model):
 
 
 class CollisionPipeline:
-    """Oracle for reference ``CollisionPipeline`` (``sim/collide.py:1104-2207``), ``broad_phase="explicit"``."""
+    """Oracle for reference ``CollisionPipeline`` (``sim/collide.py:1104-2207``).
+
+    ``broad_phase="explicit"`` sweeps ``model.shape_contact_pairs``.  ``"nxn"`` / ``"sap"`` first enumerate the pairs the NxN kernel's
+    filter admits (``oracle/broad_phase.py``, a restatement of ``broad_phase_nxn.py:124-216``) and REQUIRE that set to equal the
+    explicit list - which is what lets the same AABB sweep stand in for them; the contact order does not depend on the broad
+    phase because the export is in deterministic key order."""
 
     def __init__(self, model, *, broad_phase=None, rigid_contact_max=None, deterministic=True):
         _check_cpu(model)
-        if broad_phase not in (None, "explicit"):
-            raise NotImplementedError("oracle implements the explicit broad phase")
+        if broad_phase not in (None, "explicit", "nxn", "sap"):
+            raise ValueError(f"unknown broad_phase {broad_phase!r}")
+        if broad_phase in ("nxn", "sap"):
+            from . import broad_phase as _bp
+
+            explicit = {tuple(p) for p in model.numpy("shape_contact_pairs").tolist()}
+            dynamic = _bp.model_nxn_pairs(model, getattr(model, "shape_collision_filter_pairs", ()))
+            if explicit != dynamic:
+                raise AssertionError(f"explicit pair list and the {broad_phase} filter disagree: "
+                                     f"{sorted(explicit ^ dynamic)[:8]} ...")
         self.model = model
         self.deterministic = deterministic
         self._desc = _abi.model_desc(model)

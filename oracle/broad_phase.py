@@ -1,0 +1,102 @@
+"""oracle/broad_phase.py - TEST INFRASTRUCTURE ONLY (see oracle/README.md).
+
+Restatement of WHICH shape pairs the reference's dynamic broad phases may emit, independent of AABBs: the filter half of
+``_nxn_broadphase_kernel`` (``newton/_src/geometry/broad_phase_nxn.py:124-216``) over the world map of
+``precompute_world_map`` (``geometry/broad_phase_common.py:271-380``) - the SAP broad phase applies the same per-pair filter
+(``broad_phase_sap.py``) to the pairs its sweep finds.  ``CollisionPipeline(broad_phase="nxn" | "sap")`` of the product runs
+its AABB sweep over ``model.shape_contact_pairs`` (the explicit list) on the strength of the reference's statement that the
+builder computes that list with "the exact same filtering logic as the broad phase kernels" (``sim/builder.py:12796-12797``);
+:func:`nxn_filter_pairs` is the other side of that equation, and ``tests/test_oracle_known_answers_more.py`` checks the two
+sets are equal for every scene of the test-suite.  Python loops: small cases only.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+COLLIDE_SHAPES = 2  # ShapeFlags.COLLIDE_SHAPES (geometry/flags.py:35)
+BODY_FLAG_KINEMATIC = 2  # BodyFlags.KINEMATIC (sim/enums.py:139)
+
+
+def test_group_pair(group_a: int, group_b: int) -> bool:
+    """broad_phase_common.py:221-238"""
+    if group_a == 0 or group_b == 0:
+        return False
+    if group_a > 0:
+        return group_a == group_b or group_b < 0
+    return group_a != group_b
+
+
+def test_world_and_group_pair(world_a: int, world_b: int, group_a: int, group_b: int) -> bool:
+    """broad_phase_common.py:242-268"""
+    if world_a != -1 and world_b != -1 and world_a != world_b:
+        return False
+    return test_group_pair(group_a, group_b)
+
+
+def precompute_world_map(shape_world, shape_flags=None):
+    """broad_phase_common.py:271-380: per regular world its colliding shapes followed by the shared (world -1) ones, then one
+    dedicated segment holding only the shared shapes.  Returns (index_map, slice_ends)."""
+    shape_world = np.asarray(shape_world)
+    colliding = np.ones(len(shape_world), dtype=bool) if shape_flags is None else (np.asarray(shape_flags) & COLLIDE_SHAPES) != 0
+    if (shape_world < -1).any():
+        raise ValueError("Invalid world IDs")
+    valid = np.flatnonzero(colliding)
+    worlds = shape_world[valid]
+    shared = valid[worlds == -1]
+    index_map, slice_ends = [], []
+    for w in np.unique(worlds[worlds >= 0]):
+        index_map.extend(valid[worlds == w].tolist())
+        index_map.extend(shared.tolist())
+        slice_ends.append(len(index_map))
+    index_map.extend(shared.tolist())
+    slice_ends.append(len(index_map))
+    return np.asarray(index_map, dtype=np.int64), np.asarray(slice_ends, dtype=np.int64)
+
+
+def is_shape_pair_immovable_filtered(a, b, shape_body, body_flags, include_static_kinematic_pairs: bool) -> bool:
+    """broad_phase_common.py:166-201"""
+    if include_static_kinematic_pairs or len(shape_body) == 0:
+        return False
+    body_a, body_b = int(shape_body[a]), int(shape_body[b])
+    static_a, static_b = body_a < 0, body_b < 0
+    if static_a and static_b:
+        return True
+    if len(body_flags) == 0:
+        return False
+    immovable_a = static_a or (int(body_flags[body_a]) & BODY_FLAG_KINEMATIC) != 0
+    immovable_b = static_b or (int(body_flags[body_b]) & BODY_FLAG_KINEMATIC) != 0
+    return immovable_a and immovable_b
+
+
+def nxn_filter_pairs(shape_world, shape_flags, collision_group, filter_pairs=(), shape_body=(), body_flags=(),
+                     include_static_kinematic_pairs: bool = True) -> set[tuple[int, int]]:
+    """Every (shape1 < shape2) the NxN kernel would test for AABB overlap and not reject (broad_phase_nxn.py:141-216)."""
+    index_map, slice_ends = precompute_world_map(shape_world, shape_flags)
+    excluded = {(min(a, b), max(a, b)) for a, b in filter_pairs}
+    num_regular_worlds = len(slice_ends) - 1
+    out: set[tuple[int, int]] = set()
+    start = 0
+    for segment, end in enumerate(slice_ends):
+        members = index_map[start:end]
+        dedicated = segment >= num_regular_worlds
+        for i in range(len(members)):
+            for j in range(i + 1, len(members)):
+                s1, s2 = int(min(members[i], members[j])), int(max(members[i], members[j]))
+                w1, w2 = int(shape_world[s1]), int(shape_world[s2])
+                if w1 == -1 and w2 == -1 and not dedicated:
+                    continue  # shared-vs-shared pairs are emitted once, by the dedicated segment
+                if not test_world_and_group_pair(w1, w2, int(collision_group[s1]), int(collision_group[s2])):
+                    continue
+                if is_shape_pair_immovable_filtered(s1, s2, shape_body, body_flags, include_static_kinematic_pairs):
+                    continue
+                if (s1, s2) in excluded:
+                    continue
+                out.add((s1, s2))
+        start = end
+    return out
+
+
+def model_nxn_pairs(model, filter_pairs=(), include_static_kinematic_pairs: bool = True) -> set[tuple[int, int]]:
+    return nxn_filter_pairs(model.numpy("shape_world"), model.numpy("shape_flags"), model.numpy("shape_collision_group"), filter_pairs,
+                            model.numpy("shape_body"), model.numpy("body_flags") if model.body_count else (), include_static_kinematic_pairs)

@@ -500,3 +500,233 @@ def test_featherstone_root_free_joint_under_rotated_parent_xform_reports_parent_
     np.testing.assert_allclose(s1.joint_qd.numpy()[3:6], (0.0, 0.0, 0.0), atol=1e-5)
     np.testing.assert_allclose(s1.body_qd.numpy()[body, 0:3], (0.0, 0.0, -10.0 * dt), atol=1e-5)
     np.testing.assert_allclose(s1.body_qd.numpy()[body, 3:6], (0.0, 0.0, 0.0), atol=1e-5)
+
+
+# ---- test_collision_plane_halfspace_aabb.py (half-space AABB of infinite planes, sim/collide.py:352-377) ---------------------------
+TILT = math.radians(0.05)
+FAR_X = -600.0
+
+
+def _surface_z(normal, plane_d, x):
+    return (-plane_d - normal[0] * x) / normal[2]
+
+
+def _collide_once(oracle_lib, builder):
+    model = builder.finalize()
+    pipe = oracle_lib.CollisionPipeline(model)
+    contacts = pipe.contacts()
+    state = model.state()
+    pipe.collide(state, contacts)
+    lo, hi = oracle_lib.shape_aabbs(model, state.body_q)
+    return int(contacts.rigid_contact_count.item()), lo, hi
+
+
+def _sphere_on_plane(oracle_lib, tilted, z_offset=0.0):
+    builder = ModelBuilder()
+    normal = (math.sin(TILT), 0.0, math.cos(TILT)) if tilted else (0.0, 0.0, 1.0)
+    builder.add_shape_plane(plane=(*normal, 0.0), width=0.0, length=0.0)
+    center_z = _surface_z(normal, 0.001, FAR_X) + 0.5 / normal[2]  # resting, 1 mm into the surface
+    body = builder.add_body(xform=X.transform((FAR_X, 0.0, center_z + z_offset)))
+    builder.add_shape_sphere(body, radius=0.5)
+    return _collide_once(oracle_lib, builder)
+
+
+def test_plane_halfspace_aabb_sphere_cases(oracle_lib):
+    """:106-147"""
+    normal = (math.sin(TILT), 0.0, math.cos(TILT))
+    count, _, hi = _sphere_on_plane(oracle_lib, tilted=True)
+    assert count > 0  # resting contact 600 m from the anchor of a 0.05-degree floor survives the broad phase
+    assert hi[0][2] > _surface_z(normal, 0.0, FAR_X)  # the clamped bound clears the surface it can reach
+    count, _, hi = _sphere_on_plane(oracle_lib, tilted=False)
+    assert count > 0 and hi[0][2] < 1.0  # an exactly aligned ground is clamped at its surface
+    count, _, hi = _sphere_on_plane(oracle_lib, tilted=False, z_offset=50.0)
+    assert count == 0 and hi[0][2] < 1.0  # ... and prunes a shape hovering 50 m above it
+
+
+@pytest.mark.parametrize("plane_d", [0.0, -25.0])
+@pytest.mark.parametrize("tilt_deg", [0.0, 0.05, 0.081, 0.1, 1.0])
+@pytest.mark.parametrize("offset", [-100.0, -600.0])
+def test_plane_halfspace_aabb_resting_box_tilt_table(oracle_lib, plane_d, tilt_deg, offset):
+    """:150-196"""
+    builder = ModelBuilder()
+    tilt = math.radians(tilt_deg)
+    normal = (math.sin(tilt), 0.0, math.cos(tilt))
+    builder.add_shape_plane(plane=(*normal, plane_d), width=0.0, length=0.0)
+    half = 0.5
+    support = half * (abs(normal[0]) + abs(normal[2]))
+    center_z = (-plane_d + support - 0.001 - normal[0] * offset) / normal[2]
+    body = builder.add_body(xform=X.transform((offset, 0.0, center_z)))
+    builder.add_shape_box(body, hx=half, hy=half, hz=half)
+    count, _, hi = _collide_once(oracle_lib, builder)
+    assert count > 0, "resting box lost its ground contact (fall-through)"
+    if tilt_deg == 0.0:
+        assert hi[0][2] < _surface_z(normal, plane_d, 0.0) + 1.0
+    else:
+        assert hi[0][2] > _surface_z(normal, plane_d, offset)
+
+
+def test_plane_halfspace_aabb_non_z_normal_still_clamps(oracle_lib):
+    """:199-217 - a +X plane built through quat_between_vectors carries ~1 ulp of lateral residue; the clamp must still engage."""
+    builder = ModelBuilder()
+    builder.add_shape_plane(plane=(1.0, 0.0, 0.0, 0.0), width=0.0, length=0.0)
+    builder.add_body(mass=1.0, inertia=np.eye(3))
+    _, _, hi = _collide_once(oracle_lib, builder)
+    assert hi[0][0] < 1.0
+
+
+# ---- test_cone_orientation.py (cone mass properties as the builder computes them; host-side input construction) -------------------
+def _cone_model(axis="z"):
+    builder = ModelBuilder()
+    body = builder.add_body()
+    cfg = newton_b200.ShapeConfig()
+    cfg.density = 1000.0
+    rot = {"x": X.quat_from_axis_angle(np.array([0.0, 1.0, 0.0]), np.pi / 2), "y": X.quat_from_axis_angle(np.array([1.0, 0.0, 0.0]), -np.pi / 2),
+           "z": np.array([0.0, 0.0, 0.0, 1.0])}[axis]
+    builder.add_shape_cone(body, xform=X.transform((0.0, 0.0, 0.0), rot), radius=1.0, half_height=2.0, cfg=cfg)
+    return builder.finalize()
+
+
+def test_cone_mass_properties():
+    """:22-43, :81-164 - COM a quarter of the height above the base (apex along +axis), m = rho pi r^2 h / 3, I_xx = I_yy != I_zz."""
+    model = _cone_model()
+    np.testing.assert_allclose(model.numpy("body_com")[0], (0.0, 0.0, -1.0), atol=1e-6)
+    assert float(model.body_mass[0]) == pytest.approx(1000.0 * np.pi * 1.0 * 4.0 / 3.0, abs=1e-3 * 4189.0 * 1e-3 + 1e-2)
+    inertia = model.numpy("body_inertia")[0]
+    assert inertia[0, 0] == pytest.approx(inertia[1, 1], rel=1e-6) and abs(inertia[0, 0] - inertia[2, 2]) > 1e-2
+    assert np.abs(inertia - np.diag(np.diag(inertia))).max() < 1e-3
+    for axis, expected in (("x", (-1.0, 0.0, 0.0)), ("y", (0.0, -1.0, 0.0)), ("z", (0.0, 0.0, -1.0))):
+        np.testing.assert_allclose(_cone_model(axis).numpy("body_com")[0], expected, atol=1e-5)
+
+
+# ---- test_collision_pipeline.py:85-262, 331-386 (head-on collision of two free bodies, XPBD defaults, primitive pairs) ----------------
+from newton_b200 import GeoType  # noqa: E402
+
+VX, VYZ, ANG = 1, 2, 4
+HEAD_ON = [  # (shape a, shape b, checks on a, checks on b) - the rows of collision_pipeline_contact_tests without meshes
+    (GeoType.SPHERE, GeoType.SPHERE, VYZ, VX | VYZ | ANG),
+    (GeoType.SPHERE, GeoType.BOX, VYZ, VX | VYZ | ANG),
+    (GeoType.SPHERE, GeoType.CAPSULE, VYZ, VX | VYZ | ANG),
+    (GeoType.SPHERE, GeoType.CYLINDER, VYZ, VX | VYZ | ANG),
+    (GeoType.SPHERE, GeoType.CONE, VYZ, VYZ),
+    (GeoType.BOX, GeoType.BOX, VYZ, VX | VYZ),
+    (GeoType.CAPSULE, GeoType.CAPSULE, VYZ, VX | VYZ),
+]
+
+
+def _add_head_on_shape(builder, shape_type, body):
+    if shape_type == GeoType.BOX:
+        builder.add_shape_box(body)
+    elif shape_type == GeoType.SPHERE:
+        builder.add_shape_sphere(body, radius=0.5)
+    elif shape_type == GeoType.CAPSULE:
+        builder.add_shape_capsule(body, radius=0.25, half_height=0.3)
+    elif shape_type == GeoType.CYLINDER:
+        builder.add_shape_cylinder(body, radius=0.25, half_height=0.4)
+    elif shape_type == GeoType.CONE:  # flat base towards the incoming body
+        builder.add_shape_cone(body, xform=X.transform((0.0, 0.0, 0.0), X.quat_from_axis_angle(np.array([0.0, 1.0, 0.0]), -np.pi / 2.0)),
+                               radius=0.25, half_height=0.4)
+
+
+@pytest.mark.parametrize("broad_phase", ["explicit", "nxn", "sap"])
+@pytest.mark.parametrize("type_a,type_b,level_a,level_b", HEAD_ON)
+def test_head_on_collision_transfers_momentum_along_x(oracle_lib, type_a, type_b, level_a, level_b, broad_phase):
+    builder = ModelBuilder(gravity=(0.0, 0.0, 0.0))
+    builder.rigid_gap = 0.005
+    body_a = builder.add_body(xform=X.transform((-1.0, 0.0, 0.0)))
+    _add_head_on_shape(builder, type_a, body_a)
+    builder.joint_qd[0] = 5.0
+    builder.body_qd[-1] = np.array([5.0, 0.0, 0.0, 0.0, 0.0, 0.0])
+    body_b = builder.add_body(xform=X.transform((1.0, 0.0, 0.0)))
+    _add_head_on_shape(builder, type_b, body_b)
+    model = builder.finalize()
+    pipe = oracle_lib.CollisionPipeline(model, broad_phase=broad_phase)
+    contacts = pipe.contacts()
+    solver = oracle_lib.SolverXPBD(model)
+    s0, s1, control = model.state(), model.state(), model.control()
+    dt = 1.0 / 60.0 / 10
+    for _ in range(100):
+        pipe.collide(s0, contacts)  # once per frame, like the reference test
+        for _ in range(10):
+            s0.clear_forces()
+            solver.step(s0, s1, control, contacts, dt)
+            s0, s1 = s1, s0
+    qd = s0.body_qd.numpy()
+    for body, level in ((body_a, level_a), (body_b, level_b)):
+        if level & VX:
+            assert 0.03 < qd[body, 0] <= 5.0, (body, qd[body])
+        if level & VYZ:
+            assert abs(qd[body, 1]) < 3e-3 and abs(qd[body, 2]) < 3e-3, (body, qd[body])
+        if level & ANG:
+            assert np.abs(qd[body, 3:]).max() < 3e-3, (body, qd[body])
+
+
+# ---- explicit pair list == what the NxN / SAP broad phases may emit (sim/builder.py:12796-12797 vs broad_phase_nxn.py:124-216) -------
+def _friction_grid_model():
+    builder = ModelBuilder(up_axis="z", gravity=(0.0, 0.0, -9.81))
+    for cell in range(6):
+        cfg = newton_b200.ShapeConfig()
+        cfg.collision_group = cell + 1
+        builder.add_shape_box(-1, xform=X.transform((cell * 2.5, 0.0, 2.0)), hx=0.5, hy=2.5, hz=0.05, cfg=cfg)
+        body = builder.add_body(xform=X.transform((cell * 2.5, 0.0, 2.2)))
+        builder.add_shape_box(body, hx=0.2, hy=0.2, hz=0.05, cfg=cfg)
+    return builder.finalize()
+
+
+def _group_zoo_model():
+    """Positive / negative / zero collision groups, a visual-only shape, an explicit filter pair, global + per-world shapes."""
+    builder = ModelBuilder()
+    builder.add_ground_plane()
+    world = ModelBuilder()
+    for k, group in enumerate((1, 1, 2, -1, -2, 0, -1)):
+        cfg = newton_b200.ShapeConfig()
+        cfg.collision_group = group
+        if k == 1:
+            cfg.has_shape_collision = False  # visual only: no COLLIDE_SHAPES flag
+        body = world.add_body(xform=X.transform((0.3 * k, 0.0, 0.5)))
+        world.add_shape_sphere(body, radius=0.2, cfg=cfg)
+    world.add_shape_collision_filter_pair(2, 3)
+    builder.replicate(world, 3)
+    cfg = newton_b200.ShapeConfig()
+    cfg.collision_group = -3
+    builder.add_shape_box(-1, xform=X.transform((0.0, 0.0, -1.0)), cfg=cfg)  # a second global shape, after the worlds
+    return builder.finalize()
+
+
+SCENES = {
+    "quadrupeds": lambda: scenes_mod().quadruped_model(3), "box_stacks": lambda: scenes_mod().box_stack_model(2),
+    "convex_pile": lambda: scenes_mod().convex_pile_model(2), "mixed_worlds": lambda: scenes_mod().mixed_worlds_model(2),
+    "platform": lambda: scenes_mod().platform_model(2), "ants": lambda: scenes_mod().ants_model(2, 2),
+    "shapes_on_plane": lambda: scenes_mod().shapes_on_plane_model(2), "pendulum": lambda: scenes_mod().pendulum_model(),
+    "friction_grid": _friction_grid_model, "group_zoo": _group_zoo_model,
+}
+
+
+def scenes_mod():
+    from newton_b200 import scenes
+
+    return scenes
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+def test_explicit_pair_list_equals_nxn_filter(oracle_lib, name):
+    from oracle import broad_phase as bp
+
+    model = SCENES[name]()
+    explicit = [tuple(p) for p in model.numpy("shape_contact_pairs").tolist()]
+    assert all(a < b for a, b in explicit) and len(set(explicit)) == len(explicit)
+    assert set(explicit) == bp.model_nxn_pairs(model, model.shape_collision_filter_pairs)
+    if name == "group_zoo":
+        assert len(explicit) > 0 and model.shape_collision_filter_pairs
+        # ... and with the immovable filter on (include_static_kinematic_pairs=False) only static-static pairs disappear
+        pruned = bp.model_nxn_pairs(model, model.shape_collision_filter_pairs, include_static_kinematic_pairs=False)
+        body = model.numpy("shape_body")
+        assert set(explicit) - pruned == {p for p in explicit if body[p[0]] < 0 and body[p[1]] < 0}
+
+
+def test_world_map_layout(oracle_lib):
+    """precompute_world_map docstring example (broad_phase_common.py:271-306): regular worlds each followed by the shared shapes,
+    then the dedicated shared-only segment; visual-only shapes dropped."""
+    from oracle import broad_phase as bp
+
+    index_map, slice_ends = bp.precompute_world_map([-1, 0, 0, 1, -1, 1], [2, 2, 0, 2, 2, 2])
+    assert index_map.tolist() == [1, 0, 4, 3, 5, 0, 4, 0, 4] and slice_ends.tolist() == [3, 7, 9]
