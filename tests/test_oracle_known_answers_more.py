@@ -730,3 +730,33 @@ def test_world_map_layout(oracle_lib):
 
     index_map, slice_ends = bp.precompute_world_map([-1, 0, 0, 1, -1, 1], [2, 2, 0, 2, 2, 2])
     assert index_map.tolist() == [1, 0, 4, 3, 5, 0, 4, 0, 4] and slice_ends.tolist() == [3, 7, 9]
+
+
+def test_nxn_filter_equals_reference_brute_force(oracle_lib):
+    """The segment-wise enumeration of the NxN kernel (world map + dedicated shared segment) admits exactly the pairs of the
+    reference's own host check ``find_overlapping_pairs_np`` (newton/tests/test_broad_phase.py:92-149) when every AABB overlaps:
+    i < j, both with COLLIDE_SHAPES, test_world_and_group_pair - each pair once, shared-vs-shared pairs included."""
+    from oracle import broad_phase as bp
+
+    rng = np.random.default_rng(4)
+    for trial in range(30):
+        n = int(rng.integers(1, 40))
+        worlds = rng.integers(-1, 4, size=n)
+        if trial % 3 == 0:
+            worlds = np.sort(worlds)
+        groups = rng.integers(-3, 4, size=n)
+        flags = np.where(rng.random(n) < 0.8, 3, 1)  # bit 1 = COLLIDE_SHAPES
+        expected = set()
+        for i in range(n):
+            for j in range(i + 1, n):
+                if (flags[i] & 2) == 0 or (flags[j] & 2) == 0:
+                    continue
+                wi, wj, gi, gj = int(worlds[i]), int(worlds[j]), int(groups[i]), int(groups[j])
+                if wi != -1 and wj != -1 and wi != wj:
+                    continue
+                if gi == 0 or gj == 0:
+                    continue
+                if not ((gi == gj or gj < 0) if gi > 0 else gi != gj):
+                    continue
+                expected.add((i, j))
+        assert bp.nxn_filter_pairs(worlds, flags, groups) == expected, trial

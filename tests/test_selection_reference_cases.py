@@ -265,3 +265,27 @@ def test_link_subset_writes(host_copies, oracle_lib, use_mask, two_per_view):
         view.set_attribute(name, target, values, mask)
         assert np.array_equal(getattr(target, name).numpy(), expected), name
         assert (expected != before).any()
+
+
+# ---- newton/tests/test_match_labels.py ----------------------------------------------------------------------------------------
+def test_match_labels_known_answers():
+    from newton_b200.selection import match_labels
+
+    assert match_labels(["alpha", "beta", "gamma"], "beta") == [1]
+    assert match_labels(["arm_left", "arm_right", "leg_left"], "arm_*") == [0, 1]
+    assert match_labels(["alpha", "beta", "gamma"], "delta") == []
+    assert match_labels(["a", "b", "c"], "*") == [0, 1, 2]
+    labels = ["/World/envs/env_0/Object_A", "/World/envs/env_12/Object_B", "/World/envs/env_12/Object_D", "/World/envs/env_x/Object_A"]
+    assert match_labels(labels, re.compile(r"/World/envs/env_[0-9]+/Object_(A|B)")) == [0, 1]
+    assert match_labels(["robot", "robot_arm"], re.compile(r"robot")) == [0]  # full match
+    assert match_labels(labels[:2], r"/World/envs/env_[0-9]+/Object_(A|B)") == []  # a regex-looking string stays a glob
+    assert match_labels(["alpha", "beta", "gamma", "delta"], ["alpha", "gamma"]) == [0, 2]
+    assert match_labels(["a", "b", "c"], [2, 0]) == [2, 0]
+    assert match_labels(["arm_left", "arm_right", "leg_left", "leg_right"], ["arm_*", "leg_left"]) == [0, 1, 2]
+    assert match_labels(["a", "b", "c"], []) == []
+    with pytest.raises(TypeError):
+        match_labels(["a", "b"], [1.5])
+    with pytest.raises(TypeError):
+        match_labels(["a", "b"], [None])
+    assert match_labels(["a", "b"], [99]) == [99]  # indices pass through unchecked
+    assert match_labels(["arm_left", "arm_right", "leg_left", "leg_right"], ["arm_*", "*_left"]) == [0, 1, 2]  # no duplicates
