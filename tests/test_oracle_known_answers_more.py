@@ -760,3 +760,99 @@ def test_nxn_filter_equals_reference_brute_force(oracle_lib):
                     continue
                 expected.add((i, j))
         assert bp.nxn_filter_pairs(worlds, flags, groups) == expected, trial
+
+
+# ---- test_environment_group_collision.py (world / collision-group filtering in the explicit pair list) ---------------------------------
+def _cfg(group, collide=True):
+    cfg = newton_b200.ShapeConfig()
+    cfg.collision_group = group
+    cfg.has_shape_collision = collide
+    return cfg
+
+
+def test_shapes_of_different_worlds_are_not_paired():
+    """:20-75"""
+    builder = ModelBuilder()
+    bodies = [builder.add_body() for _ in range(3)]
+    for k, x in enumerate((0.0, 0.8)):
+        builder.begin_world()
+        builder.add_shape_box(bodies[k], xform=X.transform((x, 0.0, 0.0)), hx=0.5, hy=0.5, hz=0.5, cfg=_cfg(1))
+        builder.end_world()
+    builder.add_shape_box(bodies[2], xform=X.transform((0.4, 1.0, 0.0)), hx=0.5, hy=0.5, hz=0.5, cfg=_cfg(-1))  # global, collides with all
+    model = builder.finalize()
+    pairs = {tuple(sorted(p)) for p in model.numpy("shape_contact_pairs").tolist()}
+    assert model.shape_contact_pair_count == 2 and pairs == {(0, 2), (1, 2)}
+
+
+def test_add_world_assigns_world_indices_and_keeps_groups():
+    """:116-169"""
+    robot = ModelBuilder()
+    robot.add_body(label="base")
+    robot.add_shape_box(0, hx=0.5, hy=0.5, hz=0.5, cfg=_cfg(1))
+    robot.add_body(label="link1")
+    robot.add_shape_capsule(1, radius=0.1, half_height=0.5, cfg=_cfg(2))
+    main = ModelBuilder()
+    main.add_shape_box(-1, xform=X.transform((0.0, -1.0, 0.0)), hx=10, hy=0.1, hz=10, cfg=_cfg(-1))
+    main.add_world(robot)
+    main.add_world(robot)
+    model = main.finalize()
+    assert model.numpy("shape_world").tolist() == [-1, 0, 0, 1, 1]
+    assert model.numpy("body_world").tolist() == [0, 0, 1, 1]
+    assert model.numpy("shape_collision_group").tolist() == [-1, 1, 2, 1, 2]
+
+
+def test_mixed_collision_and_world_groups_known_pairs(oracle_lib):
+    """:171-259"""
+    from oracle import broad_phase as bp
+
+    builder = ModelBuilder()
+    bodies = [builder.add_body() for _ in range(7)]
+    builder.begin_world()
+    builder.add_shape_sphere(bodies[0], xform=X.transform((-1.0, 0.0, 0.0)), radius=0.5, cfg=_cfg(1))
+    builder.add_shape_sphere(bodies[1], xform=X.transform((0.0, 0.0, 0.0)), radius=0.5, cfg=_cfg(2))
+    builder.add_shape_sphere(bodies[2], xform=X.transform((1.0, 0.0, 0.0)), radius=0.5, cfg=_cfg(-1))
+    builder.end_world()
+    builder.begin_world()
+    builder.add_shape_sphere(bodies[3], xform=X.transform((-1.0, 2.0, 0.0)), radius=0.5, cfg=_cfg(1))
+    builder.add_shape_sphere(bodies[4], xform=X.transform((0.0, 2.0, 0.0)), radius=0.5, cfg=_cfg(2))
+    builder.end_world()
+    builder.add_shape_sphere(bodies[5], xform=X.transform((0.0, 2.0, 0.0)), radius=0.5, cfg=_cfg(2, collide=False))  # global, visual only
+    builder.add_shape_sphere(bodies[6], xform=X.transform((0.0, 4.0, 0.0)), radius=0.5, cfg=_cfg(1))  # global
+    model = builder.finalize()
+    pairs = {tuple(sorted(p)) for p in model.numpy("shape_contact_pairs").tolist()}
+    assert pairs == {(0, 2), (1, 2), (0, 6), (2, 6), (3, 6)}
+    assert pairs == bp.model_nxn_pairs(model, model.shape_collision_filter_pairs)
+
+
+def test_collision_filter_pairs_are_canonical_after_merging_builders():
+    """:261-316 - child shapes created before the parent's: the parent/child filter pairs must still be (low, high)."""
+    builder = ModelBuilder()
+    child = builder.add_link()
+    builder.add_shape_box(child, hx=0.5, hy=0.5, hz=0.5)
+    builder.add_shape_box(child, hx=0.5, hy=0.5, hz=0.5)
+    parent = builder.add_link(xform=X.transform((2.0, 0.0, 0.0)))
+    builder.add_shape_box(parent, hx=0.5, hy=0.5, hz=0.5)
+    builder.add_shape_box(parent, hx=0.5, hy=0.5, hz=0.5)
+    joint = builder.add_joint_revolute(parent, child, axis=(0.0, 0.0, 1.0), collision_filter_parent=True)
+    builder.add_articulation([joint])
+    sub = ModelBuilder()
+    sub.add_shape_box(sub.add_body(), hx=0.5, hy=0.5, hz=0.5)
+    builder.add_shape_box(child, hx=0.5, hy=0.5, hz=0.5)  # index 4
+    builder.add_builder(sub)
+    model = builder.finalize()
+    pairs = {tuple(sorted(p)) for p in model.numpy("shape_contact_pairs").tolist()}
+    for parent_shape in (2, 3):
+        for child_shape in (0, 1, 4):
+            assert (min(parent_shape, child_shape), max(parent_shape, child_shape)) not in pairs
+    assert all(a < b for a, b in model.shape_collision_filter_pairs)
+
+
+@pytest.mark.parametrize("world_a,world_b,col_a,col_b,expected", [
+    (0, 0, 1, 1, True), (1, 1, -1, 2, True), (2, 2, 0, 1, False), (0, 1, 1, 1, False), (2, 3, -1, -1, False),
+    (-1, 0, 1, 1, True), (1, -1, 2, 2, True), (-1, -1, 1, 2, False), (-1, -1, -1, 1, True)])
+def test_world_and_group_pair_table(oracle_lib, world_a, world_b, col_a, col_b, expected):
+    """:321-356"""
+    from oracle import broad_phase as bp
+
+    assert bp.test_world_and_group_pair(world_a, world_b, col_a, col_b) == expected
+    assert ModelBuilder._test_group_pair(col_a, col_b) == bp.test_group_pair(col_a, col_b)
