@@ -31,6 +31,11 @@ class SolverFeatherstone(SolverBase):
         """Advance by ``dt`` (reference ``solver_featherstone.py:461-1066``): writes ``state_out.joint_q/joint_qd/
         body_q/body_qd`` and, like the reference, refreshes ``state_in.body_q`` by forward kinematics."""
         model = self.model
+        if getattr(state_out, "body_parent_f", None) is not None:
+            # reference: compute_body_parent_f (featherstone/kernels.py:2371-2416) after the RNEA backward pass.  The fused kernel
+            # does not export that sum yet; refusing is better than leaving zeros in an array the caller asked to be filled.
+            raise NotImplementedError("SolverFeatherstone: State.body_parent_f is not produced by the CUDA path yet "
+                                      "(SolverXPBD reports it); do not request the attribute for this solver")
         if control is None:
             control = model.control(clone_variables=False)
         use_contacts = 1 if self._prepare_contacts(contacts) else 0

@@ -447,6 +447,19 @@ inline void featherstone_step(FsScratch& s, const nb2_model_desc& m, const nb2_f
             if (parent >= 0) (sv6::load(s.body_ft_s.data() + 6 * parent) + f_s).store(s.body_ft_s.data() + 6 * parent);
         }
     }
+    // ---- State.body_parent_f when requested (solver_featherstone.py:691-697, 741-758; compute_body_parent_f kernels.py:2371-2416):
+    // the wrench the inbound joint transmits = the RNEA backward-pass sum, moved from the solve origin to the body's COM
+    if (sout.body_parent_f) {
+        std::fill(sout.body_parent_f, sout.body_parent_f + size_t(B) * 6, 0.f);
+        if (A > 0)
+            for (int b = 0; b < B; ++b) {
+                sv6 f_s = sv6::load(s.body_f_s.data() + 6 * b) + sv6::load(s.body_ft_s.data() + 6 * b) + sv6::load(s.body_f_ext.data() + 6 * b);
+                vec3 f_lin = f_s.top(), f_ang_at_origin = f_s.bot();
+                vec3 r_com = load3(s.body_q_com.data() + 7 * b) - load3(s.body_solve_origin.data() + 3 * b);
+                vec3 f_ang_at_com = f_ang_at_origin - cross(r_com, f_lin);
+                sv6(f_lin, f_ang_at_com).store(sout.body_parent_f + 6 * b);
+            }
+    }
     // ---- mass matrix: J, M, P = M J, H = J^T P, L = chol(H + diag(armature)) (solver_featherstone.py:767-921)
     if (s.step % (p.update_mass_matrix_interval > 0 ? p.update_mass_matrix_interval : 1) == 0) {
         for (int a = 0; a < A; ++a) {

@@ -856,3 +856,358 @@ def test_world_and_group_pair_table(oracle_lib, world_a, world_b, col_a, col_b, 
 
     assert bp.test_world_and_group_pair(world_a, world_b, col_a, col_b) == expected
     assert ModelBuilder._test_group_pair(col_a, col_b) == bp.test_group_pair(col_a, col_b)
+
+
+# ---- test_solver_xpbd.py: joint projection under large errors, contact-force reporting edge cases, articulation drift -----------------
+def _xf_point(q7, p):
+    return q7[:3].astype(np.float64) + X.quat_rotate(q7[3:].astype(np.float64), np.asarray(p, dtype=np.float64))
+
+
+def test_xpbd_distance_joint_limits(oracle_lib):
+    """:151-181 - one step projects the anchor distance into [min, max] from separated and from coincident anchors."""
+    def solve(initial_distance, min_distance, max_distance):
+        builder = ModelBuilder(gravity=(0.0, 0.0, 0.0))
+        body = builder.add_link(xform=X.transform((initial_distance, 0.0, 0.0)))
+        builder.add_shape_sphere(body, radius=0.1)
+        joint = builder.add_joint_distance(-1, body, parent_xform=X.transform((0.0, 0.0, 0.0), X.quat_from_axis_angle(np.array([0.0, 0.0, 1.0]), np.pi / 2)),
+                                           min_distance=min_distance, max_distance=max_distance)
+        builder.add_articulation([joint])
+        model = builder.finalize()
+        s_in, s_out = model.state(), model.state()
+        oracle_lib.SolverXPBD(model, iterations=10).step(s_in, s_out, None, None, 1.0 / 60.0)
+        return s_out.body_q.numpy()[body, :3]
+
+    assert np.linalg.norm(solve(0.25, 1.0, -1.0)) >= 0.99
+    np.testing.assert_allclose(solve(0.0, 1.0, -1.0), (0.0, 1.0, 0.0), atol=0.01)  # coincident anchors: pushed along the joint's x axis
+    assert np.linalg.norm(solve(2.0, -1.0, 1.0)) <= 1.01
+
+
+def _two_capsules(builder):
+    shape_xform = X.transform((0.0, 0.0, 0.0), X.quat_from_axis_angle(np.array([0.0, 1.0, 0.0]), 0.5 * np.pi))
+    parent = builder.add_link()
+    builder.add_shape_capsule(parent, xform=shape_xform, radius=0.0625, half_height=0.25)
+    return parent, shape_xform
+
+
+def test_xpbd_ball_joint_recovers_from_large_anchor_separation(oracle_lib):
+    """:184-248"""
+    half_extent = 0.0625 + 0.25
+    builder = ModelBuilder(gravity=(0.0, 0.0, 0.0))
+    parent, shape_xform = _two_capsules(builder)
+    child = builder.add_link(xform=X.transform((2.0 * half_extent, 0.0, 0.0)))
+    builder.add_shape_capsule(child, xform=shape_xform, radius=0.0625, half_height=0.25)
+    root = builder.add_joint_free(child=parent)
+    ball = builder.add_joint_ball(parent, child, parent_xform=X.transform((half_extent, 0.0, 0.0)), child_xform=X.transform((-half_extent, 0.0, 0.0)))
+    builder.add_articulation([root, ball])
+    model = builder.finalize()
+    s0, s1 = model.state(), model.state()
+    oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, s0)
+    s0.body_q[child, :3] += torch.tensor([1.0, 1.0, 0.0])
+    oracle_lib.SolverXPBD(model, iterations=2).step(s0, s1, None, None, 1.0 / 240.0)
+    q = s1.body_q.numpy()
+    gap = np.linalg.norm(_xf_point(q[child], (-half_extent, 0.0, 0.0)) - _xf_point(q[parent], (half_extent, 0.0, 0.0)))
+    assert gap < 0.5
+
+
+def test_xpbd_prismatic_joint_recovers_from_large_transverse_separation(oracle_lib):
+    """:251-321"""
+    builder = ModelBuilder(gravity=(0.0, 0.0, 0.0))
+    parent, shape_xform = _two_capsules(builder)
+    child = builder.add_link()
+    builder.add_shape_capsule(child, xform=shape_xform, radius=0.0625, half_height=0.25)
+    root = builder.add_joint_free(child=parent)
+    slider = builder.add_joint_prismatic(parent, child, axis=(1.0, 0.0, 0.0), limit_lower=-2.0, limit_upper=2.0)
+    builder.add_articulation([root, slider])
+    model = builder.finalize()
+    s0, s1 = model.state(), model.state()
+    oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, s0)
+    s0.body_q[child, :3] += torch.tensor([0.5, 1.0, 1.0])
+    oracle_lib.SolverXPBD(model, iterations=2).step(s0, s1, None, None, 1.0 / 240.0)
+    q = s1.body_q.numpy().astype(np.float64)
+    rel = X.quat_rotate(X.quat_inverse(q[parent, 3:]), q[child, :3] - q[parent, :3])
+    assert np.hypot(rel[1], rel[2]) < 0.5 and -2.0 <= rel[0] <= 2.0
+
+
+def test_xpbd_prismatic_joint_retains_extension_in_parent_moment_arm(oracle_lib):
+    """:324-363 - the correction's torque on the parent must use the moment arm out to the (valid) joint extension."""
+    builder = ModelBuilder(gravity=(0.0, 0.0, 0.0))
+    parent = builder.add_link()
+    builder.add_shape_sphere(parent, radius=0.25)
+    child = builder.add_link()
+    builder.add_shape_sphere(child, radius=0.25)
+    root = builder.add_joint_free(child=parent)
+    slider = builder.add_joint_prismatic(parent, child, axis=(1.0, 0.0, 0.0), limit_lower=-2.0, limit_upper=2.0, damping=0.0)
+    builder.add_articulation([root, slider])
+    model = builder.finalize()
+    s0, s1 = model.state(), model.state()
+    oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, s0)
+    s0.body_q[child, :2] += torch.tensor([0.5, 0.1])
+    oracle_lib.SolverXPBD(model, iterations=2, angular_damping=0.0).step(s0, s1, None, None, 1.0 / 240.0)
+    assert abs(float(s1.body_q[parent, 5])) > 0.01
+
+
+def test_xpbd_contact_force_is_zero_without_contact_or_touch(oracle_lib):
+    """:1038-1108"""
+    builder = ModelBuilder()
+    body = builder.add_body(xform=X.transform((0.0, 0.0, 5.0)))
+    builder.add_shape_sphere(body, radius=0.25)
+    model = builder.finalize()
+    model.request_contact_attributes("force")
+    solver = oracle_lib.SolverXPBD(model, iterations=2)
+    s_in, s_out = model.state(), model.state()
+    pipe = oracle_lib.CollisionPipeline(model)
+    contacts = pipe.contacts()
+    pipe.collide(s_in, contacts)
+    solver.step(s_in, s_out, model.control(), contacts, 1.0 / 60.0)
+    solver.update_contacts(contacts, s_out)
+    n = int(contacts.rigid_contact_count.item())
+    assert n == 0 or np.abs(contacts.force.numpy()[:n]).max() <= 1e-6
+
+    builder = ModelBuilder()
+    builder.default_shape_cfg.gap = 1.0  # a contact pair is generated 0.5 m above the surface ...
+    builder.add_ground_plane()
+    body = builder.add_body(xform=X.transform((0.0, 0.0, 0.25 + 0.5)))
+    builder.add_shape_sphere(body, radius=0.25)
+    model = builder.finalize()
+    model.set_gravity((0.0, 0.0, 0.0))
+    model.request_contact_attributes("force")
+    solver = oracle_lib.SolverXPBD(model, iterations=2)
+    s_in, s_out = model.state(), model.state()
+    pipe = oracle_lib.CollisionPipeline(model)
+    contacts = pipe.contacts()
+    pipe.collide(s_in, contacts)
+    n = int(contacts.rigid_contact_count.item())
+    assert n > 0
+    solver.step(s_in, s_out, model.control(), contacts, 1.0 / 60.0)
+    solver.update_contacts(contacts, s_out)
+    np.testing.assert_allclose(contacts.force.numpy()[:n, :3], 0.0, atol=1e-6)  # ... but reports no force
+
+
+def test_xpbd_update_contacts_requires_force_attribute(oracle_lib):
+    """:1111-1132"""
+    builder = ModelBuilder()
+    builder.add_ground_plane()
+    body = builder.add_body(xform=X.transform((0.0, 0.0, 0.25)))
+    builder.add_shape_sphere(body, radius=0.25)
+    model = builder.finalize()
+    solver = oracle_lib.SolverXPBD(model, iterations=2)
+    s_in, s_out = model.state(), model.state()
+    pipe = oracle_lib.CollisionPipeline(model)
+    contacts = pipe.contacts()
+    pipe.collide(s_in, contacts)
+    solver.step(s_in, s_out, model.control(), contacts, 1.0 / 60.0)
+    assert contacts.force is None
+    with pytest.raises(ValueError):
+        solver.update_contacts(contacts)
+
+
+def test_xpbd_articulation_contact_drift(oracle_lib):
+    """:750-845 (the reference's issue #2030) - a quadruped lying on its side must not creep: contacts are solved before joints in
+    every iteration; solving joints first leaves ~6 mm/s of lateral drift.  < 1 cm over 3 s after 2 s of settling."""
+    from newton_b200 import scenes
+
+    builder = ModelBuilder()
+    builder.default_joint_cfg.armature = 0.01
+    builder.default_joint_cfg.target_ke = 2000.0
+    builder.default_joint_cfg.target_kd = 1.0
+    builder.default_shape_cfg.ke, builder.default_shape_cfg.kd, builder.default_shape_cfg.kf, builder.default_shape_cfg.mu = 1.0e4, 1.0e2, 1.0e2, 1.0
+    rot = X.quat_from_axis_angle(np.array([1.0, 0.0, 0.0]), np.pi * 0.5)
+    builder.add_urdf(scenes.quadruped_urdf(), xform=X.transform((0.0, 0.0, 0.3), rot), floating=True, enable_self_collisions=False,
+                     ignore_inertial_definitions=True)
+    for i in range(builder.body_count):
+        builder.body_inertia[i] = builder.body_inertia[i] + np.eye(3) * 0.01
+        builder.body_inv_inertia[i] = np.linalg.inv(builder.body_inertia[i])
+    builder.joint_q[-12:] = [0.2, 0.4, -0.6, -0.2, -0.4, 0.6, -0.2, 0.4, -0.6, 0.2, -0.4, 0.6]
+    builder.joint_target_q[-12:] = builder.joint_q[-12:]
+    builder.add_ground_plane()
+    model = builder.finalize()
+    solver = oracle_lib.SolverXPBD(model)
+    s0, s1, control = model.state(), model.state(), model.control()
+    pipe = oracle_lib.CollisionPipeline(model)
+    contacts = pipe.contacts()
+    oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, s0)
+
+    def run(frames, s0, s1):
+        for _ in range(frames * 10):
+            s0.clear_forces()
+            pipe.collide(s0, contacts)
+            solver.step(s0, s1, control, contacts, 1.0 / 1000.0)
+            s0, s1 = s1, s0
+        return s0, s1
+
+    s0, s1 = run(200, s0, s1)
+    x0, y0 = float(s0.body_q[0, 0]), float(s0.body_q[0, 1])
+    s0, s1 = run(300, s0, s1)
+    drift = float(np.hypot(float(s0.body_q[0, 0]) - x0, float(s0.body_q[0, 1]) - y0))
+    assert np.isfinite(s0.body_q.numpy()).all() and drift < 0.01, drift
+
+
+# ---- test_solver_xpbd.py:1283-1526 (State.body_parent_f beyond the single-body cases of test_oracle_known_answers.py) ------------------
+def test_xpbd_parent_force_chain_weight_propagation(oracle_lib):
+    """:1283-1357 - two links hanging from two revolute joints: the upper joint carries both weights, the lower one only its link
+    (time-averaged over one second after two seconds of settling, 10 %)."""
+    g = 9.81
+    builder = ModelBuilder(gravity=(0.0, 0.0, -g), up_axis="z")
+    link0 = builder.add_link()
+    builder.add_shape_box(link0, hx=0.1, hy=0.1, hz=0.1)
+    joint0 = builder.add_joint_revolute(-1, link0, child_xform=X.transform((0.0, 0.0, 1.0)), axis=(0.0, 1.0, 0.0))
+    link1 = builder.add_link()
+    builder.add_shape_box(link1, hx=0.1, hy=0.1, hz=0.1)
+    joint1 = builder.add_joint_revolute(link0, link1, parent_xform=X.transform((0.0, 0.0, -1.0)), child_xform=X.transform((0.0, 0.0, 1.0)),
+                                        axis=(0.0, 1.0, 0.0))
+    builder.add_articulation([joint0, joint1])
+    model = builder.finalize()
+    model.request_state_attributes("body_parent_f")
+    solver = oracle_lib.SolverXPBD(model, iterations=32)
+    s_in, s_out = model.state(), model.state()
+    oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, s_in)
+    masses = model.numpy("body_mass")
+    sub_dt = 1.0 / 60.0 / 8
+    for _ in range(120 * 8):
+        solver.step(s_in, s_out, None, None, sub_dt)
+        s_in, s_out = s_out, s_in
+    avg = np.zeros((2, 6))
+    for _ in range(60):
+        for _ in range(8):
+            solver.step(s_in, s_out, None, None, sub_dt)
+            s_in, s_out = s_out, s_in
+        avg += s_in.body_parent_f.numpy()
+    avg /= 60
+    assert avg[0, 2] == pytest.approx(float(masses[0] + masses[1]) * g, rel=0.10)
+    assert avg[1, 2] == pytest.approx(float(masses[1]) * g, rel=0.10)
+
+
+def test_xpbd_parent_force_allocation_and_free_body(oracle_lib):
+    """:1360-1416 - not requested: stays None and step() runs; a FREE-jointed body reports a zero parent wrench."""
+    builder = ModelBuilder()
+    link = builder.add_link()
+    builder.add_shape_sphere(link, radius=0.1)
+    builder.add_articulation([builder.add_joint_revolute(-1, link, axis=(0.0, 1.0, 0.0))])
+    model = builder.finalize()
+    s_in, s_out = model.state(), model.state()
+    assert s_in.body_parent_f is None and s_out.body_parent_f is None
+    oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, s_in)
+    oracle_lib.SolverXPBD(model, iterations=2).step(s_in, s_out, None, None, 1.0 / 60.0)
+    assert s_out.body_parent_f is None
+
+    builder = ModelBuilder()
+    link = builder.add_link()
+    builder.add_shape_sphere(link, radius=0.1)
+    builder.add_articulation([builder.add_joint_free(child=link)])
+    model = builder.finalize()
+    model.request_state_attributes("body_parent_f")
+    s_in, s_out = model.state(), model.state()
+    oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, s_in)
+    oracle_lib.SolverXPBD(model, iterations=2).step(s_in, s_out, None, None, 1.0 / 60.0)
+    np.testing.assert_allclose(s_out.body_parent_f.numpy()[0], 0.0, atol=1e-6)
+
+
+def test_xpbd_parent_force_centripetal_zero_g(oracle_lib):
+    """:1419-1526 - two bodies on a hinge spinning rigidly at 5 rad/s without gravity: the time-averaged reaction on the child is
+    the centripetal force m omega^2 r (10 %), with negligible torque about its COM."""
+    omega = 5.0
+    builder = ModelBuilder(gravity=(0.0, 0.0, 0.0), up_axis="z")
+    body_1 = builder.add_link()
+    builder.add_shape_box(body_1, hx=0.25, hy=0.05, hz=0.05)
+    body_2 = builder.add_link()
+    builder.add_shape_box(body_2, hx=0.25, hy=0.05, hz=0.05)
+    joint_free = builder.add_joint_free(child=body_1)
+    joint_rev = builder.add_joint_revolute(body_1, body_2, parent_xform=X.transform((0.5, 0.0, 0.0)), child_xform=X.transform((-0.5, 0.0, 0.0)),
+                                           axis=(0.0, 1.0, 0.0))
+    builder.add_articulation([joint_free, joint_rev])
+    model = builder.finalize()
+    model.request_state_attributes("body_parent_f")
+    solver = oracle_lib.SolverXPBD(model, iterations=16, joint_linear_relaxation=1.0, joint_angular_relaxation=1.0, joint_linear_compliance=0.0,
+                                   joint_angular_compliance=0.0, angular_damping=0.0, enable_restitution=False)
+    s_in, s_out = model.state(), model.state()
+    oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, s_in)
+    s_in.body_qd[body_1] = torch.tensor([0.0, 0.0, 0.5 * omega, 0.0, omega, 0.0])
+    s_in.body_qd[body_2] = torch.tensor([0.0, 0.0, -0.5 * omega, 0.0, omega, 0.0])
+    sub_dt = 1.0 / 240.0 / 4
+    f_lin, f_tau = [], []
+    for _ in range(240):
+        for _ in range(4):
+            solver.step(s_in, s_out, None, None, sub_dt)
+            s_in, s_out = s_out, s_in
+        pf = s_in.body_parent_f.numpy()[body_2]
+        f_lin.append(np.linalg.norm(pf[:3]))
+        f_tau.append(np.linalg.norm(pf[3:]))
+    expected = float(model.body_mass[body_2]) * omega * omega * 0.5
+    assert float(np.mean(f_lin)) == pytest.approx(expected, rel=0.10)
+    assert float(np.mean(f_tau)) < 0.10 * expected * 0.5
+
+
+def _quat_to_R(q):
+    x, y, z, w = (float(c) for c in q)
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+@pytest.mark.parametrize("joint_kind,ic", [
+    ("revolute", {"v_child": (0.0, 1.0, 0.0)}), ("revolute", {"w_child": (0.0, 0.0, 2.0)}),
+    ("revolute", {"w_parent": (0.0, 0.0, 2.0), "w_child": (0.0, 0.0, 2.0)}), ("ball", {"v_child": (0.0, 1.0, 0.0)}),
+    ("ball", {"w_child": (0.5, 0.5, 0.5)}), ("fixed", {"v_child": (0.0, 1.0, 0.0)}),
+    ("fixed", {"w_parent": (0.0, 0.0, 1.0), "w_child": (0.0, 0.0, 1.0)}), ("prismatic", {"v_child": (0.0, 1.0, 0.0)})])
+def test_xpbd_parent_force_obeys_newtons_second_law(oracle_lib, joint_kind, ic):
+    """:1589-1788 - two free-floating bodies, one joint, no gravity: body_parent_f[child] dt equals the change of the child's linear
+    and angular momentum over the step, and the pair's total linear momentum is conserved."""
+    builder = ModelBuilder(gravity=(0.0, 0.0, 0.0), up_axis="z")
+    parent = builder.add_link()
+    builder.add_shape_box(parent, hx=0.2, hy=0.1, hz=0.1)
+    child = builder.add_link()
+    builder.add_shape_box(child, hx=0.2, hy=0.1, hz=0.1)
+    j_free = builder.add_joint_free(child=parent)
+    pxf, cxf = X.transform((0.5, 0.0, 0.0)), X.transform((-0.5, 0.0, 0.0))
+    if joint_kind == "revolute":
+        j_inner = builder.add_joint_revolute(parent, child, parent_xform=pxf, child_xform=cxf, axis=(0.0, 0.0, 1.0))
+    elif joint_kind == "ball":
+        j_inner = builder.add_joint_ball(parent, child, parent_xform=pxf, child_xform=cxf)
+    elif joint_kind == "fixed":
+        j_inner = builder.add_joint_fixed(parent, child, parent_xform=pxf, child_xform=cxf)
+    else:
+        j_inner = builder.add_joint_prismatic(parent, child, parent_xform=pxf, child_xform=cxf, axis=(0.0, 0.0, 1.0))
+    builder.add_articulation([j_free, j_inner])
+    model = builder.finalize()
+    model.request_state_attributes("body_parent_f")
+    solver = oracle_lib.SolverXPBD(model, iterations=32, joint_linear_relaxation=1.0, joint_angular_relaxation=1.0, joint_linear_compliance=0.0,
+                                   joint_angular_compliance=0.0, angular_damping=0.0, enable_restitution=False)
+    s_in, s_out = model.state(), model.state()
+    oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, s_in)
+    for key, (body, sl) in {"v_parent": (parent, slice(0, 3)), "w_parent": (parent, slice(3, 6)), "v_child": (child, slice(0, 3)),
+                            "w_child": (child, slice(3, 6))}.items():
+        if key in ic:
+            s_in.body_qd[body, sl] = torch.tensor(ic[key])
+    q_before, qd_before = s_in.body_q.numpy().copy(), s_in.body_qd.numpy().copy()
+    dt = 1e-3
+    solver.step(s_in, s_out, None, None, dt)
+    q_out, qd_out = s_out.body_q.numpy(), s_out.body_qd.numpy()
+    mass, inertia = model.numpy("body_mass"), model.numpy("body_inertia")
+    f_expected = mass[child] * (qd_out[child, :3] - qd_before[child, :3]) / dt
+    r_in, r_out = _quat_to_R(q_before[child, 3:]), _quat_to_R(q_out[child, 3:])
+    tau_expected = ((r_out @ inertia[child] @ r_out.T) @ qd_out[child, 3:] - (r_in @ inertia[child] @ r_in.T) @ qd_before[child, 3:]) / dt
+    parent_f = s_out.body_parent_f.numpy()[child]
+    np.testing.assert_allclose(parent_f[:3], f_expected, rtol=1e-4, atol=1.0)
+    np.testing.assert_allclose(parent_f[3:], tau_expected, rtol=0.01, atol=1.0)
+    dp = sum(mass[i] * (qd_out[i, :3] - qd_before[i, :3]) for i in range(model.body_count))
+    np.testing.assert_allclose(dp, 0.0, atol=1e-5)
+
+
+def test_parent_force_static_pendulum_xpbd_and_featherstone_agree(oracle_lib):
+    """:1529-1586 without the MuJoCo leg - one step of a hanging link: both solvers report F_z = m g within 5 %."""
+    results = {}
+    for name in ("xpbd", "featherstone"):
+        builder = ModelBuilder(gravity=(0.0, 0.0, -9.81), up_axis="z")
+        link = builder.add_link()
+        builder.add_shape_box(link, hx=0.1, hy=0.1, hz=0.1)
+        builder.add_articulation([builder.add_joint_revolute(-1, link, child_xform=X.transform((0.0, 0.0, 1.0)), axis=(0.0, 1.0, 0.0))])
+        model = builder.finalize()
+        model.request_state_attributes("body_parent_f")
+        solver = oracle_lib.SolverXPBD(model, iterations=8) if name == "xpbd" else oracle_lib.SolverFeatherstone(model)
+        s0, s1 = model.state(), model.state()
+        oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, s0)
+        solver.step(s0, s1, None, None, 5e-3)
+        if s1.body_parent_f is None:
+            pytest.skip("the Featherstone oracle does not report body_parent_f")
+        results[name] = s1.body_parent_f.numpy()[0]
+        assert results[name][2] == pytest.approx(float(model.body_mass[0]) * 9.81, rel=0.05), name
