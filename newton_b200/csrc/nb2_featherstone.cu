@@ -235,7 +235,9 @@ NB2_DEV FsSmem fs_carve(float* base, const DevModel& M) {
     return s;
 }
 
-template <int L>
+// PF: also write State.body_parent_f (compute_body_parent_f, featherstone/kernels.py:2371-2416) - a second instantiation, so
+// that the plain step's code is untouched (the same arrangement as xpbd_step_kernel<L, EX>).
+template <int L, bool PF>
 __global__ void __launch_bounds__(32, 14) featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view sin, nb2_state_view sout,
                                                                     nb2_control_view ctl, int use_contacts, int update_mass, float dt) {
     constexpr int G = 32 / L;
@@ -572,6 +574,19 @@ __global__ void __launch_bounds__(32, 14) featherstone_step_kernel(DevModel M, n
         }
         __syncwarp(gmask);
     }
+    if constexpr (PF) {
+        // ---- State.body_parent_f: the wrench the inbound joint transmits = this joint's RNEA backward-pass sum f_s (still in
+        // sm.fs), moved from the solve origin to the child's COM; bodies without an inbound joint report zero ------------------
+        for (int b = l; b < nb; b += L) st6(sout.body_parent_f + 6 * (b0 + b), S6());
+        __syncwarp(gmask);
+        for (int j = l; j < nj; j += L) {
+            const int child = d.joint_child[j0 + j] - b0;
+            const S6 f_s = ld6(sm.fs + 6 * j);
+            const V3 r_com = ld3(sm.bqc + 7 * child) - ld3(sm.so + 3 * child);
+            st6(sout.body_parent_f + 6 * (b0 + child), S6(f_s.top(), f_s.bot() - cross(r_com, f_s.top())));
+        }
+        __syncwarp(gmask);
+    }
     // ---- H = J^T M J + Cholesky, per articulation -----------------------------------------------------------------
     for (int a = 0; a < na; ++a) {
         const int art = a0 + a;
@@ -860,8 +875,8 @@ __global__ void __launch_bounds__(32, 14) featherstone_step_kernel(DevModel M, n
     }
 }
 
-template <int L>
-static nb2_status launch_fs_L(nb2_model* m, const nb2_featherstone_params& p, const nb2_state_view& in, const nb2_state_view& out,
+template <int L, bool PF>
+static nb2_status launch_fs_LP(nb2_model* m, const nb2_featherstone_params& p, const nb2_state_view& in, const nb2_state_view& out,
                               const nb2_control_view& ctl, int use_contacts, int update_mass, float dt, cudaStream_t s) {
     const DevModel& M = m->dev;
     const int G = 32 / L;
@@ -873,12 +888,19 @@ static nb2_status launch_fs_L(nb2_model* m, const nb2_featherstone_params& p, co
         return NB2_ERR_CAPACITY;
     }
     if (smem > 48 * 1024)
-        NB2_CUDA_CHECK(cudaFuncSetAttribute(featherstone_step_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    NB2_CUDA_CHECK(cudaFuncSetAttribute(featherstone_step_kernel<L>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    featherstone_step_kernel<L><<<blocks, 32, smem, s>>>(M, p, in, out, ctl, use_contacts, update_mass, dt);
+        NB2_CUDA_CHECK(cudaFuncSetAttribute(featherstone_step_kernel<L, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    NB2_CUDA_CHECK(cudaFuncSetAttribute(featherstone_step_kernel<L, PF>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    featherstone_step_kernel<L, PF><<<blocks, 32, smem, s>>>(M, p, in, out, ctl, use_contacts, update_mass, dt);
     count_launch();
     NB2_CUDA_CHECK(cudaGetLastError());
     return NB2_OK;
+}
+
+template <int L>
+static nb2_status launch_fs_L(nb2_model* m, const nb2_featherstone_params& p, const nb2_state_view& in, const nb2_state_view& out,
+                              const nb2_control_view& ctl, int use_contacts, int update_mass, float dt, cudaStream_t s) {
+    if (out.body_parent_f) return launch_fs_LP<L, true>(m, p, in, out, ctl, use_contacts, update_mass, dt, s);
+    return launch_fs_LP<L, false>(m, p, in, out, ctl, use_contacts, update_mass, dt, s);
 }
 
 nb2_status launch_featherstone_step(nb2_model* m, const nb2_featherstone_params& p, const nb2_state_view& in, const nb2_state_view& out,
