@@ -54,6 +54,23 @@ def shard_model(model: Model, rank: int, world_size: int) -> Model:
     out.max_dofs_per_articulation = model.max_dofs_per_articulation
     out.body_label = model.body_label[b0:b1]
     out.joint_label = model.joint_label[j0:j1]
+    # host-side metadata that ArticulationView needs on a shard (labels, body -> shapes, excluded pairs), re-indexed like the arrays
+    out.articulation_label = list(getattr(model, "articulation_label", [])[a0:a1])
+    shape_label = getattr(model, "shape_label", [])
+    out.shape_label = list(shape_label[s0:s1]) + list(shape_label[g0:g1])
+
+    def shape_id(s):  # model shape index -> shard shape index, None when the shape is not on this shard
+        if s0 <= s < s1:
+            return s - s0
+        if g0 <= s < g1:
+            return s - g0 + n_local_shapes
+        return None
+
+    out.body_shapes = {-1: [shape_id(s) for s in getattr(model, "body_shapes", {}).get(-1, []) if shape_id(s) is not None]}
+    for b in range(b0, b1):
+        out.body_shapes[b - b0] = [shape_id(s) for s in getattr(model, "body_shapes", {}).get(b, []) if shape_id(s) is not None]
+    out.shape_collision_filter_pairs = {(shape_id(a), shape_id(b)) for a, b in getattr(model, "shape_collision_filter_pairs", ())
+                                        if shape_id(a) is not None and shape_id(b) is not None}
 
     def cut(name, lo, hi):
         return getattr(model, name)[lo:hi].clone()

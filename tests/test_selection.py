@@ -382,3 +382,26 @@ def test_state_assign():
     s1.body_parent_f = torch.zeros_like(s1.body_qd)
     with pytest.raises(ValueError):
         s0.assign(s1)
+
+
+def test_view_on_a_shard_addresses_the_same_rows(oracle_lib):
+    """Multi-GPU: each rank builds its ArticulationView on ``model.shard(rank, n)``; the view must address that rank's slice of the
+    monolithic view (labels, body -> shape lists and filter pairs travel with the shard)."""
+    from oracle import broad_phase as bp
+
+    model = scenes.ants_model(6, 2)
+    rng = np.random.default_rng(1)
+    model.joint_q.copy_(torch.from_numpy(rng.normal(size=tuple(model.joint_q.shape)).astype(np.float32)))
+    model.shape_margin.copy_(torch.from_numpy(rng.random(tuple(model.shape_margin.shape)).astype(np.float32)))
+    whole = ArticulationView(model, "ant", exclude_links=["front_right_leg"])
+    for rank in range(3):
+        shard = model.shard(rank, 3)
+        view = ArticulationView(shard, "ant", exclude_links=["front_right_leg"])
+        assert (view.world_count, view.count_per_world) == (2, 2) and view.link_names == whole.link_names and view.shape_names == whole.shape_names
+        assert torch.equal(view.get_dof_positions(shard), whole.get_dof_positions(model)[2 * rank : 2 * rank + 2])
+        lay = view.frequency_layouts[F.SHAPE]
+        wlay = whole.frequency_layouts[F.SHAPE]
+        assert (lay.stride_between_worlds, lay.stride_within_worlds) == (wlay.stride_between_worlds, wlay.stride_within_worlds)
+        assert torch.equal(lay.indices, wlay.indices)
+        explicit = {tuple(p) for p in shard.numpy("shape_contact_pairs").tolist()}
+        assert explicit == bp.model_nxn_pairs(shard, shard.shape_collision_filter_pairs)  # the shard's pair list is self-consistent too
