@@ -1211,3 +1211,37 @@ def test_parent_force_static_pendulum_xpbd_and_featherstone_agree(oracle_lib):
             pytest.skip("the Featherstone oracle does not report body_parent_f")
         results[name] = s1.body_parent_f.numpy()[0]
         assert results[name][2] == pytest.approx(float(model.body_mass[0]) * 9.81, rel=0.05), name
+
+
+# ---- test_narrow_phase.py:2739-3160 (box-box depth accuracy across the three MPR inflation branches) --------------------------------
+def _signed_distance_to_box(p, pos, half):
+    d = np.abs(np.asarray(p, dtype=np.float64) - np.asarray(pos)) - np.asarray(half)
+    return float(np.linalg.norm(np.maximum(d, 0.0)) + min(max(d[0], d[1], d[2]), 0.0))
+
+
+def _box_pair(oracle_lib, z, thickness, gap_sum=0.2):
+    I7 = np.array([0, 0, 0, 0, 0, 0, 1], dtype=np.float32)
+    xb = np.array([0, 0, z, 0, 0, 0, 1], dtype=np.float32)
+    return oracle_lib.convex_pair(GeoType.BOX, (0.5, 0.5, 0.5), I7, GeoType.BOX, (0.5, 0.5, 0.5), xb, gap_sum, "oracle", thickness, thickness)
+
+
+@pytest.mark.parametrize("thickness", [0.0, 2.5e-5, 0.005])  # margin_sum = 0 (inflate 1e-4), in (0, 1e-4) (inflate 2e-4), >= 1e-4 (no inflation)
+def test_box_box_depth_accuracy_over_inflation_branches(oracle_lib, thickness):
+    """The anti-flicker inflation of the MPR support points (collision_convex.py:154-161) must be taken back out of the reported
+    depth: overlap 0.01 -> -0.01, coincident faces -> 0, both to 5e-5 (the contact writer then subtracts the margins, which the
+    reference test adds back), and centre -+ n d / 2 must land on the two box surfaces to 5e-5."""
+    cnt, dist, pos, n = _box_pair(oracle_lib, 1.0 - 0.01, thickness)
+    assert cnt > 0 and float(dist[:cnt].min()) == pytest.approx(-0.01, abs=5e-5)
+    cnt, dist, pos, n = _box_pair(oracle_lib, 1.0, thickness, gap_sum=0.02)
+    assert cnt > 0 and float(dist[:cnt].min()) == pytest.approx(0.0, abs=5e-5)
+    cnt, dist, pos, n = _box_pair(oracle_lib, 1.0 - 0.05, thickness)
+    validated = 0
+    for i in range(cnt):
+        if dist[i] >= 0.0:
+            continue
+        a = pos[i].astype(np.float64) - n[i] * (dist[i] / 2.0)
+        b = pos[i].astype(np.float64) + n[i] * (dist[i] / 2.0)
+        assert _signed_distance_to_box(a, (0, 0, 0), (0.5,) * 3) == pytest.approx(0.0, abs=5e-5)
+        assert _signed_distance_to_box(b, (0, 0, 0.95), (0.5,) * 3) == pytest.approx(0.0, abs=5e-5)
+        validated += 1
+    assert validated > 0
