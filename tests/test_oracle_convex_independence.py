@@ -125,3 +125,56 @@ def test_tight_aabb_bit_equal(oracle_lib, name):
         x = np.concatenate([rng.uniform(-2, 2, 3), _rand_quat(rng)]).astype(np.float32)
         a, b = oracle.tight_aabb(T[name], s, x, "oracle"), oracle.tight_aabb(T[name], s, x, "product_host")
         assert np.array_equal(_bits(a[0]), _bits(b[0])) and np.array_equal(_bits(a[1]), _bits(b[1]))
+
+
+@pytest.mark.parametrize("name_a,name_b", list(itertools.product(T, T)))
+def test_degenerate_configurations_bit_equal(oracle_lib, name_a, name_b):
+    """Configurations a random sweep rarely produces: coincident centres (MPR's interior-point fallbacks), faces exactly touching or
+    1e-6 / 1e-4 apart, axis-aligned and quarter-turn orientations, millimetre- and hundred-metre-sized shapes, the three margin
+    regimes of the MPR inflation.  Also: whatever comes out is finite."""
+    import oracle
+
+    rng = np.random.default_rng(31 + 1000 * T[name_a] + T[name_b])
+    ta, tb = T[name_a], T[name_b]
+    axes = np.eye(3)
+
+    def scale(t, mode):
+        if t == T["plane"]:
+            return (rng.choice([0.0, 1.0]) * np.array([rng.choice([0.5, 2.0]), rng.choice([0.5, 2.0]), 0.0])).astype(np.float32)
+        base = {0: rng.choice([0.25, 0.5, 1.0], size=3), 1: rng.uniform(1e-3, 1e-2, 3), 2: rng.uniform(10.0, 100.0, 3)}[mode].astype(np.float32)
+        if t == T["cylinder"]:
+            base[2] = 0.0 if rng.random() < 0.7 else max(base[0], base[1]) * 1.5
+        return base
+
+    def quat(mode):
+        if mode == 0:
+            return np.array([0, 0, 0, 1], dtype=np.float32)
+        if mode == 1:
+            k, ax = rng.integers(0, 4), axes[rng.integers(0, 3)]
+            return np.array([*(ax * np.sin(k * np.pi / 4)), np.cos(k * np.pi / 4)], dtype=np.float32)
+        return _rand_quat(rng)
+
+    for _ in range(40):
+        mode = int(rng.integers(0, 3))
+        sa, sb = scale(ta, mode), scale(tb, mode)
+        size = float(max(np.abs(sa).max(), np.abs(sb).max(), 1e-3))
+        reach = float(sa.max() + sb.max())
+        kind = int(rng.integers(0, 4))
+        if kind == 0:
+            off = np.zeros(3)
+        elif kind == 1:
+            off = axes[rng.integers(0, 3)] * reach
+        elif kind == 2:
+            off = axes[rng.integers(0, 3)] * reach * (1.0 + rng.choice([-1e-6, 1e-6, -1e-4, 1e-4]))
+        else:
+            off = np.array([0.0, 0.0, 1.0]) * size * rng.uniform(0.5, 2.5)
+        xa = np.concatenate([np.zeros(3), quat(int(rng.integers(0, 3)))]).astype(np.float32)
+        xb = np.concatenate([off, quat(int(rng.integers(0, 3)))]).astype(np.float32)
+        gap = float(rng.choice([0.0, 0.01, 0.2])) * (size if mode else 1.0)
+        ma, mb = float(rng.choice([0.0, 2.5e-5, 0.005])), float(rng.choice([0.0, 2.5e-5, 0.005]))
+        r0 = oracle.convex_pair(ta, sa, xa, tb, sb, xb, gap, "oracle", ma, mb)
+        r1 = oracle.convex_pair(ta, sa, xa, tb, sb, xb, gap, "product_host", ma, mb)
+        assert r0[0] == r1[0], (sa, sb, xa, xb, gap, ma, mb)
+        for a, b in zip(r0[1:], r1[1:]):
+            assert np.array_equal(_bits(a), _bits(b)), (sa, sb, xa, xb, gap, ma, mb)
+        assert np.isfinite(r0[1][: r0[0]]).all() and np.isfinite(r0[2][: r0[0]]).all() and np.isfinite(r0[3][: r0[0]]).all()
