@@ -15,7 +15,7 @@ from __future__ import annotations
 import torch
 
 
-def eval_fk(model, joint_q, joint_qd, state, mask=None, indices=None) -> None:
+def eval_fk(model, joint_q, joint_qd, state, mask=None, indices=None, body_flag_filter: int = 3) -> None:
     """Write ``state.body_q`` / ``state.body_qd`` from generalized coordinates (reference ``sim/articulation.py:500-574``).
 
     ``state`` may be the model itself (as in ``newton.eval_fk(model, model.joint_q, model.joint_qd, model)``).
@@ -24,6 +24,8 @@ def eval_fk(model, joint_q, joint_qd, state, mask=None, indices=None) -> None:
     """
     if mask is not None and indices is not None:
         raise ValueError("Cannot specify both mask and indices parameters")
+    if int(body_flag_filter) != 3:  # BodyFlags.ALL; reference sim/articulation.py:421, 507-533
+        raise NotImplementedError("eval_fk(body_flag_filter=...) is not implemented in the CUDA path yet (the oracle restates it)")
     if state.body_q.is_cuda:
         import ctypes as C
 

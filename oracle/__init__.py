@@ -275,12 +275,13 @@ def tight_aabb(geo_type, scale, xform, impl="oracle"):
     return out[:3], out[3:]
 
 
-def eval_fk(model, joint_q, joint_qd, state, mask=None, indices=None):
-    """newton.eval_fk: writes state.body_q / state.body_qd (state may be the model); optional articulation mask / indices."""
+def eval_fk(model, joint_q, joint_qd, state, mask=None, indices=None, body_flag_filter=3):
+    """newton.eval_fk: writes state.body_q / state.body_qd (state may be the model); optional articulation mask / indices and
+    body-flag filter (BodyFlags.ALL = 3; bodies that do not match keep their values)."""
     if mask is not None and indices is not None:
         raise ValueError("Cannot specify both mask and indices parameters")
     d = _abi.model_desc(model)
-    if mask is None and indices is None:
+    if mask is None and indices is None and int(body_flag_filter) == 3:
         lib().orc_eval_fk(C.byref(d), C.c_void_p(_abi.ptr(joint_q)), C.c_void_p(_abi.ptr(joint_qd)),
                           C.c_void_p(_abi.ptr(state.body_q)), C.c_void_p(_abi.ptr(state.body_qd)))
         return
@@ -289,7 +290,7 @@ def eval_fk(model, joint_q, joint_qd, state, mask=None, indices=None):
     lib().orc_eval_fk_masked(C.byref(d), C.c_void_p(_abi.ptr(joint_q)), C.c_void_p(_abi.ptr(joint_qd)),
                              C.c_void_p(_abi.ptr(state.body_q)), C.c_void_p(_abi.ptr(state.body_qd)),
                              C.c_void_p(None if m is None else m.ctypes.data), C.c_void_p(None if ix is None else ix.ctypes.data),
-                             C.c_int(0 if ix is None else ix.size))
+                             C.c_int(0 if ix is None else ix.size), C.c_int(int(body_flag_filter)))
 
 
 def eval_ik(model, state, joint_q, joint_qd):

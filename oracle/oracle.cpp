@@ -263,8 +263,8 @@ void orc_eval_fk(const nb2_model_desc* m, const float* joint_q, const float* joi
 }
 // ... with the optional articulation mask / index list (sim/articulation.py:420-475)
 void orc_eval_fk_masked(const nb2_model_desc* m, const float* joint_q, const float* joint_qd, float* body_q, float* body_qd,
-                        const uint8_t* articulation_mask, const int* articulation_indices, int index_count) {
-    eval_articulation_fk(*m, joint_q, joint_qd, body_q, body_qd, articulation_mask, articulation_indices, index_count);
+                        const uint8_t* articulation_mask, const int* articulation_indices, int index_count, int body_flag_filter) {
+    eval_articulation_fk(*m, joint_q, joint_qd, body_q, body_qd, articulation_mask, articulation_indices, index_count, body_flag_filter);
 }
 
 // The index arithmetic of the PRODUCT's ArticulationView copy kernels (newton_b200/csrc/nb2_selection.cuh) run on the host over

@@ -677,8 +677,10 @@ inline void featherstone_step(FsScratch& s, const nb2_model_desc& m, const nb2_f
 
 // ---- public newton.eval_fk (sim/articulation.py:237-424 eval_single_articulation_fk; launch :420-475 with the optional ----
 // articulation_mask / articulation_indices).  joint_qd in the PUBLIC convention (FREE/DISTANCE linear dofs = child COM velocity).
+// body_flag_filter (:421): only bodies whose flags intersect the filter are written (BodyFlags.ALL = DYNAMIC | KINEMATIC = 3).
 inline void eval_articulation_fk(const nb2_model_desc& m, const float* joint_q, const float* joint_qd, float* body_q, float* body_qd,
-                                 const uint8_t* articulation_mask = nullptr, const int* articulation_indices = nullptr, int index_count = 0) {
+                                 const uint8_t* articulation_mask = nullptr, const int* articulation_indices = nullptr, int index_count = 0,
+                                 int body_flag_filter = 3) {
     const int dim = articulation_indices ? index_count : m.articulation_count;
     for (int tid = 0; tid < dim; ++tid) {
         const int a = articulation_indices ? articulation_indices[tid] : tid;
@@ -733,6 +735,7 @@ inline void eval_articulation_fk(const nb2_model_desc& m, const float* joint_q, 
             else
                 linear_joint_origin = linear_joint_world + cross(angular_joint_world, x_child_origin - X_wcj.p);
             vec3 v_o = v_parent_origin + linear_joint_origin, w_o = w_parent + angular_joint_world;
+            if ((m.body_flags[child] & body_flag_filter) == 0) continue;  // keeps its values; descendants read them (sim/articulation.py:421)
             X_wc.store(body_q + 7 * child);
             vec3 v_com = cross(w_o, transform_vector(X_wc, load3(m.body_com + 3 * child))) + v_o;  // origin_twist_to_com_twist
             spatial(v_com, w_o).store(body_qd + 6 * child);

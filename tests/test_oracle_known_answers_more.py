@@ -1245,3 +1245,192 @@ def test_box_box_depth_accuracy_over_inflation_branches(oracle_lib, thickness):
         assert _signed_distance_to_box(b, (0, 0, 0.95), (0.5,) * 3) == pytest.approx(0.0, abs=5e-5)
         validated += 1
     assert validated > 0
+
+
+# ---- test_kinematic_links.py:304-715 (kinematic bodies under XPBD(iterations=5): prescribed motion, immunity to wrenches, contact
+# response of dynamic bodies, runtime toggling) ---------------------------------------------------------------------------------------
+from newton_b200 import BodyFlags  # noqa: E402
+
+KINEMATIC_TEST_WRENCH = torch.tensor([20.0, -15.0, 10.0, 0.5, -0.4, 0.3])
+
+
+def _contact_defaults(builder):
+    builder.default_shape_cfg.ke, builder.default_shape_cfg.kd, builder.default_shape_cfg.kf = 1.0e4, 500.0, 0.5
+
+
+def _kin_solver(oracle_lib, model):
+    return oracle_lib.SolverXPBD(model, iterations=5, angular_damping=0.0)
+
+
+def _quat_close(qa, qb, min_dot):
+    assert abs(float(np.dot(qa, qb))) > min_dot
+
+
+def test_kinematic_free_base_prescribed_motion_xpbd(oracle_lib):
+    """:400-481"""
+    dt, steps, x0, vx = 1.0 / 240.0, 100, -0.3, 1.0
+
+    def run_once(apply_force):
+        builder = ModelBuilder(gravity=(0.0, 0.0, 0.0))
+        _contact_defaults(builder)
+        kin = builder.add_body(xform=X.transform((-0.3, 0.0, 0.0)), mass=1.0, is_kinematic=True, label="kinematic_free")
+        builder.add_shape_box(kin, hx=0.25, hy=0.15, hz=0.15)
+        probe = builder.add_body(xform=X.transform((0.45, 0.0, 0.0)), mass=1.0, label="probe")
+        builder.add_shape_sphere(probe, radius=0.1)
+        model = builder.finalize()
+        joint = int(np.flatnonzero(model.numpy("joint_child") == kin)[0])
+        qs, qds = int(model.joint_q_start[joint]), int(model.joint_qd_start[joint])
+        solver = _kin_solver(oracle_lib, model)
+        pipe = oracle_lib.CollisionPipeline(model)
+        contacts = pipe.contacts()
+        s0, s1 = model.state(), model.state()
+        p0 = s0.body_q.numpy()[probe, :3].copy()
+        max_speed = 0.0
+        for i in range(steps):
+            s0.joint_q[qs : qs + 7] = torch.tensor([x0 + vx * i * dt, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0])
+            s0.joint_qd[qds : qds + 6] = torch.tensor([vx, 0.0, 0.0, 0.0, 0.0, 0.0])
+            oracle_lib.eval_fk(model, s0.joint_q, s0.joint_qd, s0, body_flag_filter=int(BodyFlags.KINEMATIC))
+            s0.clear_forces()
+            if apply_force:
+                s0.body_f[kin] = KINEMATIC_TEST_WRENCH
+            pipe.collide(s0, contacts)
+            solver.step(s0, s1, None, contacts, dt)
+            s0, s1 = s1, s0
+            max_speed = max(max_speed, float(np.linalg.norm(s0.body_qd.numpy()[probe, :3])))
+        q, qd = s0.body_q.numpy(), s0.body_qd.numpy()
+        return dict(kin_pos=q[kin, :3].copy(), kin_quat=q[kin, 3:].copy(), kin_qd=qd[kin].copy(), probe_qd=qd[probe].copy(), probe_max_speed=max_speed,
+                    probe_displacement=float(np.linalg.norm(q[probe, :3] - p0)))
+
+    free, forced = run_once(False), run_once(True)
+    assert free["kin_pos"][0] == pytest.approx(x0 + vx * (steps - 1) * dt, abs=4e-2)
+    assert abs(free["kin_pos"][1]) < 2e-2 and abs(free["kin_pos"][2]) < 2e-2 and free["kin_qd"][0] > 2e-1
+    np.testing.assert_allclose(forced["kin_pos"], free["kin_pos"], atol=8e-3)  # the applied wrench does not perturb prescribed motion
+    _quat_close(forced["kin_quat"], free["kin_quat"], 0.9995)
+    assert np.linalg.norm(forced["kin_qd"] - free["kin_qd"]) < 4e-1
+    assert free["probe_max_speed"] > 3e-2  # the dynamic probe is pushed
+    assert np.linalg.norm(free["probe_qd"][:3]) > 5e-3 or free["probe_displacement"] > 1e-3
+
+
+def test_kinematic_revolute_root_pendulum_prescribed_motion_xpbd(oracle_lib):
+    """:484-575 - maximal-coordinate solvers get the root's body_q / body_qd prescribed directly."""
+    dt, steps, theta0, omega = 1.0 / 240.0, 120, -1.0, 2.0
+
+    def run_once(apply_force):
+        builder = ModelBuilder(gravity=(0.0, 0.0, 0.0))
+        _contact_defaults(builder)
+        root = builder.add_link(mass=1.0, inertia=np.eye(3) * 0.1, is_kinematic=True, label="kinematic_root")
+        pendulum = builder.add_link(mass=1.0, inertia=np.eye(3) * 0.1, label="pendulum")
+        j_root = builder.add_joint_revolute(-1, root, axis=(0.0, 1.0, 0.0), label="kinematic_root_joint")
+        j_pend = builder.add_joint_revolute(root, pendulum, axis=(0.0, 1.0, 0.0), parent_xform=X.transform((0.45, 0.0, 0.0)), label="pendulum_joint")
+        builder.add_articulation([j_root, j_pend])
+        builder.add_shape_box(root, xform=X.transform((0.6, 0.0, 0.0)), hx=0.15, hy=0.08, hz=0.08)
+        builder.add_shape_sphere(pendulum, xform=X.transform((0.3, 0.0, 0.0)), radius=0.1)
+        probe = builder.add_body(xform=X.transform((0.72, 0.0, 0.0)), mass=0.6, label="probe")
+        builder.add_shape_sphere(probe, radius=0.1)
+        model = builder.finalize()
+        solver = _kin_solver(oracle_lib, model)
+        pipe = oracle_lib.CollisionPipeline(model)
+        contacts = pipe.contacts()
+        s0, s1 = model.state(), model.state()
+        p0 = s0.body_q.numpy()[probe, :3].copy()
+        max_probe = max_pend = 0.0
+        for i in range(steps):
+            theta = theta0 + omega * i * dt
+            s0.body_q[root] = torch.tensor([0.0, 0.0, 0.0, 0.0, np.sin(theta / 2), 0.0, np.cos(theta / 2)], dtype=torch.float32)
+            s0.body_qd[root] = torch.tensor([0.0, 0.0, 0.0, 0.0, omega, 0.0])
+            s0.clear_forces()
+            if apply_force:
+                s0.body_f[root] = KINEMATIC_TEST_WRENCH
+            pipe.collide(s0, contacts)
+            solver.step(s0, s1, None, contacts, dt)
+            s0, s1 = s1, s0
+            qd = s0.body_qd.numpy()
+            max_probe, max_pend = max(max_probe, float(np.linalg.norm(qd[probe, :3]))), max(max_pend, float(np.linalg.norm(qd[pendulum])))
+        q, qd = s0.body_q.numpy(), s0.body_qd.numpy()
+        return dict(root_pos=q[root, :3].copy(), root_quat=q[root, 3:].copy(), root_qd=qd[root].copy(), probe_max_speed=max_probe,
+                    pendulum_max_speed=max_pend, probe_displacement=float(np.linalg.norm(q[probe, :3] - p0)))
+
+    free, forced = run_once(False), run_once(True)
+    theta_end = theta0 + omega * (steps - 1) * dt
+    _quat_close(free["root_quat"], np.array([0.0, np.sin(theta_end / 2), 0.0, np.cos(theta_end / 2)]), 0.99)
+    assert np.linalg.norm(free["root_qd"][3:]) > 5e-1
+    np.testing.assert_allclose(forced["root_pos"], free["root_pos"], atol=1.5e-2)
+    _quat_close(forced["root_quat"], free["root_quat"], 0.995)
+    assert np.linalg.norm(forced["root_qd"] - free["root_qd"]) < 8e-1
+    assert free["probe_max_speed"] > 2e-2 and free["probe_displacement"] > 1e-2 and free["pendulum_max_speed"] > 2e-2
+
+
+def test_kinematic_fixed_root_is_immune_to_forces_and_stops_the_probe_xpbd(oracle_lib):
+    """:578-638"""
+    dt, steps, probe_vx = 1.0 / 240.0, 140, 3.0
+
+    def run_once(apply_force):
+        builder = ModelBuilder(gravity=(0.0, 0.0, 0.0))
+        _contact_defaults(builder)
+        static = builder.add_link(xform=X.transform((0.0, 0.0, 0.0)), mass=1.0, inertia=np.eye(3) * 0.1, is_kinematic=True, label="static_root")
+        builder.add_articulation([builder.add_joint_fixed(-1, static, label="static_root_joint")])
+        builder.add_shape_box(static, hx=0.25, hy=0.25, hz=0.25)
+        probe = builder.add_body(xform=X.transform((-1.0, 0.0, 0.0)), mass=1.0, label="probe")
+        builder.add_shape_sphere(probe, radius=0.12)
+        model = builder.finalize()
+        joint = int(np.flatnonzero(model.numpy("joint_child") == probe)[0])
+        qds = int(model.joint_qd_start[joint])
+        solver = _kin_solver(oracle_lib, model)
+        pipe = oracle_lib.CollisionPipeline(model)
+        contacts = pipe.contacts()
+        s0, s1 = model.state(), model.state()
+        s0.joint_qd[qds : qds + 6] = torch.tensor([probe_vx, 0.0, 0.0, 0.0, 0.0, 0.0])
+        oracle_lib.eval_fk(model, s0.joint_q, s0.joint_qd, s0)
+        q_init = s0.body_q.numpy()[static].copy()
+        for _ in range(steps):
+            s0.clear_forces()
+            if apply_force:
+                s0.body_f[static] = KINEMATIC_TEST_WRENCH
+            pipe.collide(s0, contacts)
+            solver.step(s0, s1, None, contacts, dt)
+            s0, s1 = s1, s0
+        q, qd = s0.body_q.numpy(), s0.body_qd.numpy()
+        return dict(q_init=q_init, static_pos=q[static, :3].copy(), static_quat=q[static, 3:].copy(), static_qd=qd[static].copy(),
+                    probe_pos=q[probe, :3].copy(), probe_qd=qd[probe].copy())
+
+    free, forced = run_once(False), run_once(True)
+    np.testing.assert_allclose(free["static_pos"], free["q_init"][:3], atol=2e-3)
+    _quat_close(free["static_quat"], free["q_init"][3:], 0.9999)
+    assert np.linalg.norm(free["static_qd"]) < 4e-1
+    np.testing.assert_allclose(forced["static_pos"], free["static_pos"], atol=2e-3)
+    _quat_close(forced["static_quat"], free["static_quat"], 0.9999)
+    assert np.linalg.norm(forced["static_qd"] - free["static_qd"]) < 6e-2
+    assert free["probe_pos"][0] < 0.25 and abs(free["probe_qd"][0] - probe_vx) > 2.5e-1  # the probe hit the box
+
+
+def test_kinematic_runtime_toggle_xpbd(oracle_lib):
+    """:641-715 - body_flags edited at run time + notify_model_changed(BODY_PROPERTIES)."""
+    builder = ModelBuilder(gravity=(0.0, 0.0, 0.0))
+    body = builder.add_body(xform=X.transform((0.0, 0.0, 0.0)), mass=1.0, is_kinematic=True, label="toggle_body")
+    builder.add_shape_sphere(body, radius=0.1)
+    model = builder.finalize()
+    solver = _kin_solver(oracle_lib, model)
+    pipe = oracle_lib.CollisionPipeline(model)
+    contacts = pipe.contacts()
+    s0, s1 = model.state(), model.state()
+
+    def phase(s0, s1):
+        for _ in range(60):
+            s0.clear_forces()
+            s0.body_f[body] = torch.tensor([10.0, 0.0, 0.0, 0.0, 0.0, 0.0])
+            pipe.collide(s0, contacts)
+            solver.step(s0, s1, None, contacts, 1.0 / 240.0)
+            s0, s1 = s1, s0
+        return s0, s1
+
+    s0, s1 = phase(s0, s1)
+    assert np.linalg.norm(s0.body_q.numpy()[body, :3]) < 1e-3  # kinematic: does not move under the force
+    model.body_flags[body] = int(BodyFlags.DYNAMIC)
+    solver.notify_model_changed(ModelFlags.BODY_PROPERTIES)
+    s0, s1 = phase(s0, s1)
+    assert s0.body_q.numpy()[body, 0] > 0.05  # dynamic: accelerates
+    model.body_flags[body] = int(BodyFlags.KINEMATIC)
+    solver.notify_model_changed(ModelFlags.BODY_PROPERTIES)
+    before = s0.body_q.numpy()[body, :3].copy()
+    s0, s1 = phase(s0, s1)
+    assert np.linalg.norm(s0.body_q.numpy()[body, :3] - before) < 1e-3  # kinematic again: stays put
