@@ -17,7 +17,7 @@ from .model import Contacts
 class CollisionPipeline:
     def __init__(self, model, *, broad_phase: str | None = None, rigid_contact_max: int | None = None,
                  deterministic: bool = False, soft_contact_margin: float = 0.01, requires_grad: bool = False,
-                 export_contacts: bool = True, **unsupported):
+                 export_contacts: bool = True, include_static_kinematic_pairs: bool = True, **unsupported):
         if broad_phase not in (None, "explicit", "nxn", "sap"):
             raise ValueError(f"unknown broad_phase {broad_phase!r} (expected 'explicit', 'nxn' or 'sap')")
         # "nxn" / "sap" (broad_phase_nxn.py:132-218, broad_phase_sap.py) enumerate candidates at run time with the same
@@ -30,6 +30,10 @@ class CollisionPipeline:
         self.broad_phase = broad_phase or "explicit"
         if requires_grad:
             raise NotImplementedError("differentiable contacts are out of scope")
+        if not include_static_kinematic_pairs:
+            # reference default True (collide.py:1112): pairs of two immovable shapes are kept, as in the explicit pair list;
+            # False would prune them in the broad phase (broad_phase_common.py:166-201)
+            raise NotImplementedError("CollisionPipeline(include_static_kinematic_pairs=False) is not implemented")
         for k, v in unsupported.items():
             if v not in (None, False):
                 raise NotImplementedError(f"CollisionPipeline option {k!r} is outside the hot-path scope")
