@@ -14,6 +14,13 @@ from .. import _abi, _lib
 from .model import Contacts
 
 
+# reference constructor arguments (sim/collide.py:1104-1133) that only size or tune paths outside the primitive / convex scope;
+# accepted with any value so that a call site spelling out the reference defaults keeps working
+_IGNORED_OPTIONS = frozenset({"reduce_contacts", "max_triangle_pairs", "soft_contact_max", "shape_pairs_max", "verify_buffers",
+                              "contact_reduction_hashtable_size_factor", "contact_matching_pos_threshold",
+                              "contact_matching_normal_dot_threshold"})
+
+
 class CollisionPipeline:
     def __init__(self, model, *, broad_phase: str | None = None, rigid_contact_max: int | None = None,
                  deterministic: bool = False, soft_contact_margin: float = 0.01, requires_grad: bool = False,
@@ -35,8 +42,12 @@ class CollisionPipeline:
             # False would prune them in the broad phase (broad_phase_common.py:166-201)
             raise NotImplementedError("CollisionPipeline(include_static_kinematic_pairs=False) is not implemented")
         for k, v in unsupported.items():
+            if k in _IGNORED_OPTIONS:  # tuning / capacity knobs of machinery this pipeline does not have (mesh reduction, buffers)
+                continue
+            if k == "contact_matching" and v == "disabled":
+                continue
             if v not in (None, False):
-                raise NotImplementedError(f"CollisionPipeline option {k!r} is outside the hot-path scope")
+                raise NotImplementedError(f"CollisionPipeline option {k!r}={v!r} is outside the hot-path scope")
         self.model = model
         self.device = model.device
         self._native = _lib.native_model(model)

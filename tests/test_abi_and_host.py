@@ -181,3 +181,23 @@ def test_oracle_aabbs_of_finite_plane_and_cone(oracle_lib):
     g = float(model.shape_gap[1] + model.shape_margin[1])
     np.testing.assert_allclose(lo[1], [-0.3 - g, -0.3 - g, 0.6 - g], atol=1e-5)
     np.testing.assert_allclose(hi[1], [0.3 + g, 0.3 + g, 1.4 + g], atol=1e-5)
+
+
+def test_collision_pipeline_constructor_options():
+    """Spelling out the reference's constructor defaults (sim/collide.py:1104-1133) must not be rejected; options that would
+    change the result are refused.  (CPU model: an accepted call gets as far as the no-CPU-path error.)"""
+    m = scenes.quadruped_model(1, seed=None)
+    defaults = dict(reduce_contacts=True, rigid_contact_max=None, max_triangle_pairs=1000000, shape_pairs_filtered=None,
+                    include_static_kinematic_pairs=True, soft_contact_max=None, soft_contact_margin=0.01,
+                    enable_rigid_soft_full_surface_contact=False, requires_grad=None, broad_phase=None, narrow_phase=None,
+                    sdf_hydroelastic_config=None, shape_pairs_max=None, deterministic=False, contact_matching="disabled",
+                    contact_matching_pos_threshold=0.0005, contact_matching_normal_dot_threshold=0.995, contact_report=False,
+                    verify_buffers=True, contact_reduction_hashtable_size_factor=0.25, speculative_config=None)
+    with pytest.raises(_lib.Nb2Error):
+        newton_b200.CollisionPipeline(m, **defaults)
+    for bad in (dict(include_static_kinematic_pairs=False), dict(contact_matching="latest"), dict(contact_report=True),
+                dict(speculative_config=object()), dict(requires_grad=True), dict(narrow_phase=object())):
+        with pytest.raises(NotImplementedError):
+            newton_b200.CollisionPipeline(m, **bad)
+    with pytest.raises(ValueError):
+        newton_b200.CollisionPipeline(m, broad_phase="bvh")
