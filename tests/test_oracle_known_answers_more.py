@@ -1434,3 +1434,67 @@ def test_kinematic_runtime_toggle_xpbd(oracle_lib):
     before = s0.body_q.numpy()[body, :3].copy()
     s0, s1 = phase(s0, s1)
     assert np.linalg.norm(s0.body_q.numpy()[body, :3] - before) < 1e-3  # kinematic again: stays put
+
+
+# ---- test_parent_force.py (the SolverFeatherstone rows: State.body_parent_f from the RNEA backward pass, rtol 1e-4) -------------------
+def _hanging_link(joint_axis, child_offset, parent_xform=None):
+    builder = ModelBuilder(gravity=(0.0, 0.0, -9.81), up_axis="z")
+    link = builder.add_link()
+    builder.add_shape_box(link, hx=0.1, hy=0.1, hz=0.1)
+    joint = builder.add_joint_revolute(-1, link, parent_xform=parent_xform, child_xform=X.transform(child_offset), axis=joint_axis)
+    builder.add_articulation([joint])
+    model = builder.finalize()
+    model.request_state_attributes("body_parent_f")
+    return model
+
+
+@pytest.mark.parametrize("parent_xform", [None, X.transform((5.0, 3.0, -2.0)),
+                                          X.transform((1.0, 2.0, 3.0), X.quat_from_axis_angle(np.array([1.0, 0.0, 0.0]), np.pi * 0.5))])
+def test_featherstone_parent_force_static_pendulum(oracle_lib, parent_xform):
+    """:52-84 - the joint carries exactly the weight, whatever the joint frame."""
+    model = _hanging_link((0.0, 1.0, 0.0), (0.0, 0.0, 1.0), parent_xform)
+    s0, s1 = model.state(), model.state()
+    assert s0.body_parent_f is not None
+    oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, s0)
+    oracle_lib.SolverFeatherstone(model).step(s0, s1, None, None, 5e-3)
+    pf = s1.body_parent_f.numpy()[0]
+    np.testing.assert_allclose(pf[:3], [0.0, 0.0, float(model.body_mass[0]) * 9.81], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(pf[3:], 0.0, atol=1e-2)
+
+
+def test_featherstone_parent_force_centrifugal(oracle_lib):
+    """:87-114 - horizontal pendulum spinning about Z at 5 rad/s: weight in +Z plus m omega^2 r towards the axis."""
+    model = _hanging_link((0.0, 0.0, 1.0), (-1.0, 0.0, 0.0))
+    s0, s1 = model.state(), model.state()
+    s0.joint_qd[0] = 5.0
+    oracle_lib.eval_fk(model, s0.joint_q, s0.joint_qd, s0)
+    oracle_lib.SolverFeatherstone(model).step(s0, s1, None, None, 5e-3)
+    pf, mass = s1.body_parent_f.numpy()[0], float(model.body_mass[0])
+    np.testing.assert_allclose(pf[:3], [-mass * 25.0, 0.0, mass * 9.81], rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(pf[3:], 0.0, atol=1e-2)
+
+
+def test_featherstone_body_f_propagates_into_parent_force(oracle_lib):
+    """:117-193 - a force / torque on the second link of a chain shows up in the first joint's reaction (non-compliant directions)."""
+    builder = ModelBuilder(gravity=(0.0, 0.0, -9.81), up_axis="z")
+    link0 = builder.add_link()
+    builder.add_shape_box(link0, hx=0.1, hy=0.1, hz=0.1)
+    joint0 = builder.add_joint_revolute(-1, link0, child_xform=X.transform((0.0, 0.0, 1.0)), axis=(0.0, 1.0, 0.0))
+    link1 = builder.add_link()
+    builder.add_shape_box(link1, hx=0.1, hy=0.1, hz=0.1)
+    joint1 = builder.add_joint_revolute(link0, link1, parent_xform=X.transform((0.0, 0.0, -1.0)), child_xform=X.transform((0.0, 0.0, 1.0)),
+                                        axis=(0.0, 1.0, 0.0))
+    builder.add_articulation([joint0, joint1])
+    model = builder.finalize()
+    model.request_state_attributes("body_parent_f")
+    solver = oracle_lib.SolverFeatherstone(model)
+    total_weight = float(model.body_mass[0] + model.body_mass[1]) * 9.81
+    for wrench, f_expected, tau_expected in (((0.0, 10.0, 0.0, 0.0, 0.0, 0.0), (0.0, -10.0, total_weight), (-20.0, 0.0, 0.0)),
+                                             ((0.0, 0.0, 0.0, 5.0, 0.0, 0.0), (0.0, 0.0, total_weight), (-5.0, 0.0, 0.0))):
+        s0, s1 = model.state(), model.state()
+        oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, s0)
+        s0.body_f[1] = torch.tensor(wrench)
+        solver.step(s0, s1, None, None, 5e-3)
+        pf = s1.body_parent_f.numpy()[0]
+        np.testing.assert_allclose(pf[:3], f_expected, rtol=1e-4, atol=1e-3)
+        np.testing.assert_allclose(pf[3:], tau_expected, atol=1e-2)
