@@ -1498,3 +1498,36 @@ def test_featherstone_body_f_propagates_into_parent_force(oracle_lib):
         pf = s1.body_parent_f.numpy()[0]
         np.testing.assert_allclose(pf[:3], f_expected, rtol=1e-4, atol=1e-3)
         np.testing.assert_allclose(pf[3:], tau_expected, atol=1e-2)
+
+
+# ---- test_rigid_contact.py:775-843 (test_box_drop, XPBD(iterations=2)) ----------------------------------------------------------------
+def test_xpbd_box_drop_energy_bound(oracle_lib):
+    """Two boxes (one tilted 0.5 rad) dropped onto the ground and onto each other: contacts never inject energy - |v_z| stays below
+    sqrt(2 g h_max) - and after one second both rest above the ground near the origin."""
+    builder = ModelBuilder()
+    builder.add_ground_plane()
+    half = 0.5
+    body_1 = builder.add_body(xform=X.transform((0.0, 0.0, half * 1.2)))
+    builder.add_shape_box(body_1, hx=half, hy=half, hz=half)
+    body_2 = builder.add_body(xform=X.transform((0.0, 0.0, half * 4.2), X.quat_from_axis_angle(np.array([1.0, 0.0, 0.0]), 0.5)))
+    builder.add_shape_box(body_2, hx=half, hy=half, hz=half)
+    model = builder.finalize()
+    solver = oracle_lib.SolverXPBD(model, iterations=2)
+    s0, s1 = model.state(), model.state()
+    oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, s0)
+    pipe = oracle_lib.CollisionPipeline(model)
+    contacts = pipe.contacts()
+    v_max = np.sqrt(2 * 9.81 * half * 3.2)
+    worst = 0.0
+    for _ in range(60):
+        for _ in range(8):
+            s0.clear_forces()
+            pipe.collide(s0, contacts)
+            solver.step(s0, s1, None, contacts, 1.0 / 60.0 / 8)
+            s0, s1 = s1, s0
+        worst = max(worst, float(np.abs(s0.body_qd.numpy()[:, 2]).max()))
+    assert worst < v_max
+    q, qd = s0.body_q.numpy(), s0.body_qd.numpy()
+    for b in range(model.body_count):
+        assert abs(q[b, 0]) < 1.0 and abs(q[b, 1]) < 1.0 and q[b, 2] > half * 0.5
+        assert np.linalg.norm(qd[b, :3]) < 1.0
