@@ -31,9 +31,26 @@ def compute_inertia_capsule(density, r, hh):
     return m, np.zeros(3), np.diag([Ia, Ia, Ib])
 
 
+_BARREL_NODES, _BARREL_WEIGHTS = np.polynomial.legendre.leggauss(32)  # reference inertia.py:22
+
+
 def compute_inertia_cylinder(density, r, hh, barrel_radius=0.0):
+    """Solid cylinder along z; ``barrel_radius`` != 0: the side profile is the circular arc of that radius through the end rims
+    (reference ``inertia.py:151-192``: 32-point Gauss-Legendre over the disc stack r(z))."""
     if barrel_radius != 0.0:
-        raise NotImplementedError("barrel cylinders are outside the hot-path scope (SURVEY.md §8)")
+        if barrel_radius < hh:
+            raise ValueError("barrel_radius must be zero or at least half_height")
+        z = hh * _BARREL_NODES
+        w = hh * _BARREL_WEIGHTS
+        end_offset = math.sqrt(barrel_radius * barrel_radius - hh * hh)
+        profile_offset = np.sqrt(np.maximum(barrel_radius * barrel_radius - z * z, 0.0))
+        rz = r + (hh * hh - z * z) / (profile_offset + end_offset)
+        r2 = rz * rz
+        r4 = r2 * r2
+        m = float(density * np.pi * np.dot(w, r2))
+        Ib = float(0.5 * density * np.pi * np.dot(w, r4))
+        Ia = float(density * np.pi * np.dot(w, 0.25 * r4 + r2 * z * z))
+        return m, np.zeros(3), np.diag([Ia, Ia, Ib])
     h = 2.0 * hh
     m = density * math.pi * r * r * h
     Ia = 1.0 / 12.0 * m * (3.0 * r * r + h * h)

@@ -1531,3 +1531,64 @@ def test_xpbd_box_drop_energy_bound(oracle_lib):
     for b in range(model.body_count):
         assert abs(q[b, 0]) < 1.0 and abs(q[b, 1]) < 1.0 and q[b, 2] > half * 0.5
         assert np.linalg.norm(qd[b, :3]) < 1.0
+
+
+# ---- mass properties of every primitive against brute-force integration (the reference checks its closed forms against
+# compute_inertia_mesh of fine meshes, newton/tests/test_inertia.py:25-134, 307-409; here: a 160^3 midpoint grid) -------------------------
+def _grid_mass_properties(inside, bounds, n=160):
+    lo, hi = np.asarray(bounds[0], dtype=np.float64), np.asarray(bounds[1], dtype=np.float64)
+    axes = [lo[k] + (np.arange(n) + 0.5) * (hi[k] - lo[k]) / n for k in range(3)]
+    x, y, z = np.meshgrid(*axes, indexing="ij")
+    mask = inside(x, y, z)
+    dv = np.prod((hi - lo) / n)
+    pts = np.stack([x[mask], y[mask], z[mask]], axis=1)
+    mass = dv * len(pts)
+    com = pts.mean(axis=0)
+    d = pts - com
+    inertia = dv * (np.einsum("ij,ij->", d, d) * np.eye(3) - d.T @ d)
+    return mass, com, inertia
+
+
+def _barrel_profile(r, hh, rb):
+    return lambda z: r + (hh * hh - z * z) / (np.sqrt(np.maximum(rb * rb - z * z, 0.0)) + np.sqrt(rb * rb - hh * hh))
+
+
+PRIMITIVES = {
+    "sphere": (GeoType.SPHERE, (0.7, 0.0, 0.0), lambda x, y, z: x * x + y * y + z * z <= 0.49, 0.7),
+    "box": (GeoType.BOX, (0.3, 0.5, 0.7), lambda x, y, z: (np.abs(x) <= 0.3) & (np.abs(y) <= 0.5) & (np.abs(z) <= 0.7), (0.3, 0.5, 0.7)),
+    "capsule": (GeoType.CAPSULE, (0.4, 0.6, 0.0), lambda x, y, z: x * x + y * y + np.maximum(np.abs(z) - 0.6, 0.0) ** 2 <= 0.16, 1.0),
+    "cylinder": (GeoType.CYLINDER, (0.5, 0.8, 0.0), lambda x, y, z: (x * x + y * y <= 0.25) & (np.abs(z) <= 0.8), 0.8),
+    "barrel": (GeoType.CYLINDER, (0.4, 0.6, 1.0), lambda x, y, z: (np.abs(z) <= 0.6) & (x * x + y * y <= _barrel_profile(0.4, 0.6, 1.0)(z) ** 2), 0.8),
+    "cone": (GeoType.CONE, (0.6, 0.9, 0.0), lambda x, y, z: (np.abs(z) <= 0.9) & (x * x + y * y <= (0.6 * (0.9 - z) / 1.8) ** 2), 0.9),
+    "ellipsoid": (GeoType.ELLIPSOID, (0.7, 0.5, 0.3), lambda x, y, z: (x / 0.7) ** 2 + (y / 0.5) ** 2 + (z / 0.3) ** 2 <= 1.0, 0.7),
+}
+
+
+@pytest.mark.parametrize("name", list(PRIMITIVES))
+def test_primitive_mass_properties_against_brute_force(name):
+    from newton_b200.geometry.inertia import compute_inertia_shape
+
+    geo_type, scale, inside, extent = PRIMITIVES[name]
+    mass, com, inertia = compute_inertia_shape(geo_type, scale, 1000.0)
+    half = np.asarray(extent if isinstance(extent, tuple) else (extent,) * 3, dtype=np.float64)  # grid bounds (tight for the box)
+    m_ref, com_ref, i_ref = _grid_mass_properties(inside, (-half, half))
+    assert mass == pytest.approx(1000.0 * m_ref, rel=5e-3)
+    np.testing.assert_allclose(com, com_ref, atol=2e-3 * half.max())
+    np.testing.assert_allclose(np.asarray(inertia), 1000.0 * i_ref, rtol=1e-2, atol=1e-3 * np.trace(1000.0 * i_ref))
+
+
+def test_barrel_cylinder_body_can_be_built():
+    """A dynamic body carrying a barrel cylinder gets the barrel's mass properties (it used to be refused by the builder)."""
+    builder = ModelBuilder()
+    body = builder.add_body()
+    cfg = newton_b200.ShapeConfig()
+    cfg.density = 500.0
+    shape = builder.add_shape_cylinder(body, radius=0.4, half_height=0.6, cfg=cfg)
+    builder.shape_scale[shape] = (0.4, 0.6, 1.0)  # barrel radius in scale.z (sim/builder.py:7089)
+    plain = float(builder.finalize().body_mass[0])
+    from newton_b200.geometry.inertia import compute_inertia_cylinder
+
+    m_barrel, _, inertia = compute_inertia_cylinder(500.0, 0.4, 0.6, 1.0)
+    assert m_barrel > plain and inertia[2, 2] > 0.5 * plain * 0.16  # bulging sides: heavier, larger axial inertia than the straight one
+    with pytest.raises(ValueError):
+        compute_inertia_cylinder(500.0, 0.4, 0.6, 0.5)
