@@ -45,24 +45,22 @@ WORKLOADS = {
         # B_state 1884 (state in 13 x 76 B + out 13 x 52 B + control 220 B) + one read of each 80-byte
         # contact + B_model 4001 (per-env model constants: the reference layout replicates them per world and the kernel
         # reads them every substep)
-        alg_bytes=lambda n_c: 1884.0 + 80.0 * n_c + 4001.0,
-        # dram__bytes_read + write of one launch, ncu --set full (profiles/r1d_xpbd_step_kernel.txt)
-        traffic=27.5e6),
+        alg_bytes=lambda n_c: 1884.0 + 80.0 * n_c + 4001.0, model_bytes=4001.0),
     "quadruped_xpbd_stock": dict(
         config="BASELINE.json configs[2] scene with the stock example's loop (example_basic_urdf.py:28-33: 100 fps, 10 substeps, "
                "iterations=2)", scene="quadruped", solver="xpbd", envs=4096, substeps=10, fps=100, iterations=2,
         kernel="xpbd_step_kernel", text="quadruped (Anymal-class, 13 bodies/18 dofs) envs, SolverXPBD iterations=2",
-        alg_bytes=lambda n_c: 1884.0 + 80.0 * n_c + 4001.0, traffic=None),
+        alg_bytes=lambda n_c: 1884.0 + 80.0 * n_c + 4001.0, model_bytes=4001.0),
     "box_stacks_xpbd": dict(
         config="BASELINE.json configs[1]", scene="stacks", solver="xpbd", envs=512, substeps=4, fps=60, kernel="xpbd_step_kernel",
         text="5-box stack envs (box-box MPR manifolds + plane-box), SolverXPBD iterations=8",
-        alg_bytes=lambda n_c: 5 * 76.0 + 5 * 52.0 + 80.0 * n_c + 5 * 100.0, traffic=None),
+        alg_bytes=lambda n_c: 5 * 76.0 + 5 * 52.0 + 80.0 * n_c + 5 * 100.0, model_bytes=500.0),
     "quadruped_featherstone": dict(
         config="BASELINE.json configs[3]", scene="quadruped", solver="featherstone", envs=4096, substeps=10, fps=100,
         kernel="featherstone_step_kernel",
         text="quadruped (Anymal-class, 13 bodies/18 dofs) envs, SolverFeatherstone (dense H = J^T M J, Cholesky), penalty contacts",
         # joint_q/qd in+out (2 x 148 B) + body_f in (312) + body_q/qd out (676) + control (220) + 112-byte contacts + B_model
-        alg_bytes=lambda n_c: 296.0 + 312.0 + 676.0 + 220.0 + 112.0 * n_c + 4001.0, traffic=None),
+        alg_bytes=lambda n_c: 296.0 + 312.0 + 676.0 + 220.0 + 112.0 * n_c + 4001.0, model_bytes=4001.0),
 }
 WL = WORKLOADS["quadruped_xpbd"]
 SUBSTEPS = WL["substeps"]
@@ -343,17 +341,33 @@ def run_native(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    # measured DRAM traffic of ONE launch of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum of the committed
+    # `ncu --set full` capture for this workload (profiles/traffic.json names the report it was read from); null when no capture
+    # of the current kernel at this size is committed
+    traffic = traffic_src = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(f"{args.workload}:{envs}")
+        if t:
+            traffic, traffic_src = float(t["dram_bytes"]), t["source"]
+    except Exception:
+        pass
+    no_model = (alg_bytes_env - WL["model_bytes"]) * envs / (kern_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "kernel": WL["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": WL.get("traffic") if envs == WL["envs"] else None,
+        "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": "measured" if peaks else "fallback",
         "algorithmic_bytes_per_env_substep": alg_bytes_env, "kernel_ms": kern_ms, "contacts_per_env": n_c,
+        # SURVEY.md §8(d) asks for both: with the per-env model constants (read every substep; what DRAM traffic shows) and
+        # without them (state + control + contacts only)
+        "achieved_no_model_constants": no_model, "frac_no_model_constants": no_model / peak,
+        "algorithmic_bytes_no_model_constants": alg_bytes_env - WL["model_bytes"],
         "kernel_share_of_step": kern_ms * SUBSTEPS / (total_ms / args.steps),
     }
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
-        cpu_baseline = oracle_throughput(min(envs, 1024), frames=2, threads=os.cpu_count() or 1)
+        cpu_baseline = oracle_throughput(envs, frames=20, threads=os.cpu_count() or 1)
 
     if rank == 0:
         out = {
@@ -374,81 +388,115 @@ def run_native(args):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+ENVS_PER_SHARD = 32  # >= 32 environments per unit of CPU work; shards are handed to the threads dynamically
+
+
+class CpuArm:
+    """The reference's CPU path for the SAME workload (all `envs` environments of the stated config): the oracle - a C++
+    restatement of the reference's Warp-CPU kernels - running the substep loop of independent world shards on a persistent
+    pool of native threads (oracle.FramePool, created and settled BEFORE any timer; no Python inside the timed region)."""
+
+    def __init__(self, envs: int, threads: int):
+        import oracle
+
+        oracle.build()
+        base = build_scene(envs, seed=1)
+        n_shards = max(1, envs // ENVS_PER_SHARD)
+        while envs % n_shards:  # Model.shard splits the world range evenly
+            n_shards -= 1
+        self.envs, self.threads, self.n_shards = envs, max(1, min(threads, n_shards)), n_shards
+        models = [base.shard(r, n_shards) for r in range(n_shards)] if n_shards > 1 else [base]
+        self.pool = oracle.FramePool(models, lambda m: make_solver(oracle, m), substeps=SUBSTEPS, dt=DT, threads=self.threads)
+        # one more pool with a single thread over ONE shard: what the reference's Warp-CPU device gives (kernels run serially
+        # on one host thread, SURVEY.md §8(d))
+        self.single = oracle.FramePool(models[:1], lambda m: make_solver(oracle, m), substeps=SUBSTEPS, dt=DT, threads=1)
+        self.single_envs = envs // n_shards
+        self.settled = False
+
+    def settle(self):
+        """Same untimed lead-in as the native arm: 1.2 s of simulated time so the timed frames carry standing contacts."""
+        if not self.settled:
+            n = int(round(1.2 * FPS))
+            self.pool.run_frames(n)
+            self.single.run_frames(n)
+            self.settled = True
+
+    def frame(self) -> float:
+        """One frame (= one bench step) of all envs; returns seconds."""
+        return self.pool.run_frames(1)
+
+    def describe(self, value, seconds, frames, single_value) -> dict:
+        phys = None
+        try:
+            import psutil
+
+            phys = psutil.cpu_count(logical=False)
+        except Exception:
+            pass
+        return {
+            "value": value, "unit": UNIT, "cores": self.threads, "physical_cores": phys, "kind": "port",
+            "all_cores": value, "single_thread": single_value,
+            "sample": f"{self.envs} envs x {frames} frames x {SUBSTEPS} substeps of the bench workload (same scene, seed and solver "
+                      f"settings, settled 1.2 s first), oracle C++ port of the reference kernels; {self.n_shards} shards of "
+                      f"{self.envs // self.n_shards} envs on a persistent pool of {self.threads} native threads (no Python in the timed "
+                      f"region); single_thread = one shard of {self.single_envs} envs on one thread; the reference itself (Warp) "
+                      f"cannot run here",
+            "seconds": seconds,
+        }
+
+    def single_thread_value(self, frames: int) -> float:
+        sec = self.single.run_frames(frames)
+        return self.single_envs * SUBSTEPS * frames / sec
+
+    def close(self):
+        self.pool.close()
+        self.single.close()
+
+
 def oracle_throughput(envs: int, frames: int, threads: int) -> dict:
-    """Times the CPU oracle (restatement of the reference's Warp-CPU kernels) on `envs` environments split over
-    `threads` host threads (environments are independent; ctypes releases the GIL)."""
-    import oracle
-    from newton_b200 import scenes
-
-    oracle.build()
-    threads = max(1, min(threads, envs))
-    per = envs // threads
-    envs = per * threads
-    base = build_scene(envs, seed=1)
-    shards = [base.shard(r, threads) for r in range(threads)] if threads > 1 else [base]
-
-    def make(m):
-        return dict(m=m, pipe=oracle.CollisionPipeline(m), solver=make_solver(oracle, m), s0=m.state(), s1=m.state(),
-                    ctrl=m.control())
-
-    ctx = [make(m) for m in shards]
-    for c in ctx:
-        c["contacts"] = c["pipe"].contacts()
-
-    def run(c, n_frames):
-        for _ in range(n_frames * SUBSTEPS):
-            c["s0"].clear_forces()
-            c["pipe"].collide(c["s0"], c["contacts"])
-            c["solver"].step(c["s0"], c["s1"], c["ctrl"], c["contacts"], DT)
-            c["s0"], c["s1"] = c["s1"], c["s0"]
-
-    def run_all(n_frames):
-        ts = [threading.Thread(target=run, args=(c, n_frames)) for c in ctx]
-        for t in ts:
-            t.start()
-        for t in ts:
-            t.join()
-
-    run_all(max(1, int(round(0.4 * FPS))))  # settle onto the ground (untimed, 0.4 s simulated) so the timed frames carry contacts
-    t0 = time.perf_counter()
-    run_all(frames)
-    dt = time.perf_counter() - t0
-    return {
-        "value": envs * SUBSTEPS * frames / dt, "unit": UNIT, "cores": threads, "kind": "port",
-        "sample": f"{envs} envs x {frames} frames x {SUBSTEPS} substeps (same scene/solver settings), oracle C++ port of the "
-                  f"reference kernels, {threads} host threads; the reference itself (Warp) cannot run here",
-        "seconds": dt,
-    }
+    """cpu_baseline of the native arm: `frames` timed frames of the full workload on all host threads (bounded: 4096 envs x
+    20 frames x 4 substeps is ~20 s of CPU work)."""
+    arm = CpuArm(envs, threads)
+    arm.settle()
+    for _ in range(2):
+        arm.frame()
+    sec = sum(arm.frame() for _ in range(frames))
+    single = arm.single_thread_value(max(2, frames // 4))
+    out = arm.describe(envs * SUBSTEPS * frames / sec, sec, frames, single)
+    arm.close()
+    return out
 
 
 def run_reference(args):
+    """`--impl reference`: the same config, metric and unit as the native arm, K timed steps after W warm-up steps, one step =
+    one frame of ALL `envs` environments (4 substeps) on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    envs = min(args.envs, 1024)
-    frames = 2
-    steps = max(1, args.steps)
-    warm = max(0, min(args.warmup, 2))
-    # each "step" is a bounded sample: `frames` frames of `envs` envs; keep the total run within minutes
-    steps = min(steps, 5)
-    vals = []
-    for i in range(warm + steps):
-        r = oracle_throughput(envs, frames, threads)
-        if i >= warm:
-            vals.append(r)
-    value = float(np.mean([v["value"] for v in vals]))
-    sec = float(np.mean([v["seconds"] for v in vals]))
-    cb = dict(vals[-1])
-    cb["value"] = value
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    arm = CpuArm(args.envs, threads)
+    arm.settle()
+    for _ in range(warm):
+        arm.frame()
+    per_step = [arm.frame() for _ in range(steps)]
+    sec = float(sum(per_step))
+    value = args.envs * SUBSTEPS * steps / sec
+    single = arm.single_thread_value(max(2, min(steps, 5)))
+    cb = arm.describe(value, sec, steps, single)
+    arm.close()
+    cfg = workload_config(args.envs, 1)
+    cfg["l2"] = "n/a (CPU)"
+    cfg["parallelism"] = f"{cb['cores']} host threads, {arm.n_shards} world shards"
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(args.envs, args.gpus), "impl": "reference", "cpu_baseline": cb,
+        "ms_per_step": sec / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": cfg, "impl": "reference", "cpu_baseline": cb,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "reference arm = CPU oracle (C++ restatement of the reference's Warp kernels); the unmodified reference "
-                "needs NVIDIA Warp, which is not installed and cannot be installed offline (see DESIGN.md)",
+        "note": "reference arm = CPU oracle (C++ restatement of the reference's Warp kernels) on all host threads; the unmodified "
+                "reference needs NVIDIA Warp, which is not installed and cannot be installed offline (see DESIGN.md).  The "
+                "reference's own Warp-CPU device runs kernels on ONE host thread: that figure is cpu_baseline.single_thread",
     }
     print(json.dumps(out))
 

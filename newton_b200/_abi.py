@@ -15,25 +15,65 @@ c_float_p = C.c_void_p
 c_int_p = C.c_void_p
 
 
-def ptr(a) -> int | None:
-    """Raw address of an array-like (None for missing / empty arrays)."""
+_NP_KIND = {"f32": np.float32, "i32": np.int32, "bool": np.bool_, "u8": np.uint8}
+
+
+def _torch_kind(t):
+    import torch
+
+    return {torch.float32: "f32", torch.int32: "i32", torch.bool: "bool", torch.uint8: "u8"}.get(t)
+
+
+def ptr(a, kind: str | None = None, device=None, min_numel: int | None = None, name: str = "array") -> int | None:
+    """Raw address of an array-like (None for missing / empty arrays).
+
+    The C-ABI only sees addresses, so everything the native side assumes is checked here, before the call: element type
+    (``kind``: "f32", "i32", "bool"; bool and uint8 are interchangeable), the device of a torch tensor (``device``) and a
+    minimum element count (``min_numel``).  A mismatch raises ``ValueError`` instead of being reinterpreted or read out of
+    bounds on the device (a sticky CUDA error)."""
     if a is None:
         return None
     if hasattr(a, "data_ptr"):
         if a.numel() == 0:
             return None
         if not a.is_contiguous():
-            raise ValueError("arrays crossing the C-ABI must be contiguous")
+            raise ValueError(f"{name}: arrays crossing the C-ABI must be contiguous")
+        if kind is not None:
+            k = _torch_kind(a.dtype)
+            if k != kind and not ({k, kind} <= {"bool", "u8"}):
+                raise ValueError(f"{name}: expected dtype {kind}, got {a.dtype}")
+        if device is not None:
+            import torch
+
+            want = torch.device(device)
+            if a.device.type != want.type or (want.type == "cuda" and want.index is not None and a.device.index != want.index):
+                raise ValueError(f"{name}: lives on {a.device}, the model is on {want}")
+        if min_numel is not None and a.numel() < min_numel:
+            raise ValueError(f"{name}: {a.numel()} elements, the model needs at least {min_numel}")
         return a.data_ptr()
     if hasattr(a, "ptr"):  # wp.array
+        if min_numel is not None and hasattr(a, "size") and int(a.size) * _wp_width(a) < min_numel:
+            raise ValueError(f"{name}: too small for the model ({a.size} elements)")
         return a.ptr
     if isinstance(a, np.ndarray):
         if a.size == 0:
             return None
         if not a.flags["C_CONTIGUOUS"]:
-            raise ValueError("arrays crossing the C-ABI must be contiguous")
+            raise ValueError(f"{name}: arrays crossing the C-ABI must be contiguous")
+        if kind is not None and a.dtype != _NP_KIND[kind] and not ({a.dtype.type, _NP_KIND[kind]} <= {np.bool_, np.uint8}):
+            raise ValueError(f"{name}: expected dtype {kind}, got {a.dtype}")
+        if device is not None and str(device) != "cpu" and not str(device).startswith("cpu"):
+            raise ValueError(f"{name}: a host NumPy array cannot be passed to a model on {device}")
+        if min_numel is not None and a.size < min_numel:
+            raise ValueError(f"{name}: {a.size} elements, the model needs at least {min_numel}")
         return a.ctypes.data
     raise TypeError(f"cannot take the address of {type(a)}")
+
+
+def _wp_width(a) -> int:
+    """Scalars per element of a Warp array (transform 7, spatial_vector 6, vec3 3, mat33 9, scalars 1)."""
+    n = getattr(getattr(a, "dtype", None), "_length_", 1)
+    return int(n) if n else 1
 
 
 class ModelDesc(C.Structure):
@@ -182,41 +222,66 @@ class ViewLayout(C.Structure):
     ]
 
 
+# element type of every ModelDesc array ("f32" unless listed)
+_MODEL_KIND = {n: "i32" for n in (
+    "body_flags", "body_world", "body_world_start", "joint_type", "joint_parent", "joint_child", "joint_ancestor",
+    "joint_articulation", "joint_q_start", "joint_qd_start", "joint_target_q_start", "joint_dof_dim", "joint_world_start",
+    "articulation_start", "shape_body", "shape_type", "shape_flags", "shape_world", "shape_world_start", "shape_contact_pairs")}
+_MODEL_KIND["joint_enabled"] = "bool"
+
+
 def model_desc(model) -> ModelDesc:
     """Fill a :class:`ModelDesc` with the addresses of ``model``'s arrays (borrowed, not copied)."""
     d = ModelDesc()
     for n in _COUNT_FIELDS:
         setattr(d, n, int(getattr(model, n)))
     d.shape_pair_count = int(getattr(model, "shape_contact_pair_count", 0))
+    dev = getattr(model, "device", None)
     for name, _ in ModelDesc._fields_:
         if name in _COUNT_FIELDS or name in ("shape_pair_count", "gravity_count"):
             continue
-        setattr(d, name, ptr(getattr(model, name, None)))
+        setattr(d, name, ptr(getattr(model, name, None), _MODEL_KIND.get(name, "f32"), dev, None, "model." + name))
     g = model.gravity
     d.gravity_count = int(g.shape[0])
     return d
 
 
-def state_view(state) -> StateView:
+def state_view(state, model=None) -> StateView:
+    """``model`` (optional) supplies the device and the element counts every array must at least have."""
     v = StateView()
+    dev = getattr(model, "device", None)
+    nb = int(getattr(model, "body_count", 0)) if model is not None else None
+    need = {} if model is None else {
+        "body_q": 7 * nb, "body_qd": 6 * nb, "body_f": 6 * nb, "body_parent_f": 6 * nb,
+        "joint_q": int(model.joint_coord_count), "joint_qd": int(model.joint_dof_count)}
     for name, _ in StateView._fields_:
-        setattr(v, name, ptr(getattr(state, name, None)))
+        setattr(v, name, ptr(getattr(state, name, None), "f32", dev, need.get(name), "state." + name))
     return v
 
 
-def control_view(control) -> ControlView:
+def control_view(control, model=None) -> ControlView:
     v = ControlView()
+    dev = getattr(model, "device", None)
+    need = {}
+    if model is not None:
+        nd, nc = int(model.joint_dof_count), int(model.joint_coord_count)
+        need = {"joint_f": nd, "joint_target_qd": nd, "joint_act": nd,
+                "joint_target_q": nc if getattr(model, "use_coord_layout_targets", False) else nd}
     for name, _ in ControlView._fields_:
-        setattr(v, name, ptr(getattr(control, name, None)))
+        setattr(v, name, ptr(getattr(control, name, None), "f32", dev, need.get(name), "control." + name))
     return v
 
 
-def contacts_view(contacts) -> ContactsView:
+def contacts_view(contacts, model=None) -> ContactsView:
     v = ContactsView()
-    v.rigid_contact_max = int(contacts.rigid_contact_max)
-    v.rigid_contact_count = ptr(contacts.rigid_contact_count)
-    for short in ("shape0", "shape1", "point0", "point1", "offset0", "offset1", "normal", "margin0", "margin1", "tids"):
-        setattr(v, short, ptr(getattr(contacts, "rigid_contact_" + short)))
+    n = int(contacts.rigid_contact_max)
+    dev = getattr(model, "device", None)
+    v.rigid_contact_max = n
+    v.rigid_contact_count = ptr(contacts.rigid_contact_count, "i32", dev, 1, "contacts.rigid_contact_count")
+    for short, kind, width in (("shape0", "i32", 1), ("shape1", "i32", 1), ("point0", "f32", 3), ("point1", "f32", 3),
+                               ("offset0", "f32", 3), ("offset1", "f32", 3), ("normal", "f32", 3), ("margin0", "f32", 1),
+                               ("margin1", "f32", 1), ("tids", "i32", 1)):
+        setattr(v, short, ptr(getattr(contacts, "rigid_contact_" + short), kind, dev, n * width, "contacts.rigid_contact_" + short))
     force = getattr(contacts, "force", None)
-    v.force = ptr(force) if force is not None else None
+    v.force = ptr(force, "f32", dev, n * 6, "contacts.force") if force is not None else None
     return v

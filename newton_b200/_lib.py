@@ -115,6 +115,7 @@ class NativeModel:
         with torch.cuda.device(self.device_index):
             check(lib().nb2_model_create(C.byref(self.desc), self.device_index, C.byref(handle)), "nb2_model_create")
         self.handle = handle
+        self.contact_stamp = 0  # bumped whenever the contact blocks are overwritten (collide / import)
         self.rigid_contact_max = int(lib().nb2_model_rigid_contact_max(handle))
 
     def notify_model_changed(self, flags: int):

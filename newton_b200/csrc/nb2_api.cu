@@ -29,7 +29,7 @@ static nb2_status fetch(const T* dptr, size_t n, std::vector<T>& out) {
         set_error("nb2_model_create: required model array is NULL");
         return NB2_ERR_INVALID_ARGUMENT;
     }
-    NB2_CUDA_CHECK(cudaMemcpy(out.data(), dptr, n * sizeof(T), cudaMemcpyDeviceToHost));
+    NB2_CUDA_CHECK(cudaMemcpy(out.data(), dptr, n * sizeof(T), cudaMemcpyDefault));
     return NB2_OK;
 }
 
@@ -375,6 +375,19 @@ static nb2_status upload_tables(nb2_model* m) {
     return NB2_OK;
 }
 
+// Every entry point runs on the model's device and leaves the caller's current device as it found it (a process may drive
+// several GPUs; nb2_model_destroy is called from a garbage collector at arbitrary points).
+struct DeviceGuard {
+    int prev = -1, dev = -1;
+    explicit DeviceGuard(int device) : dev(device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+    }
+};
+
 }  // namespace nb2
 
 using namespace nb2;
@@ -387,7 +400,7 @@ nb2_status nb2_model_create(const nb2_model_desc* desc, int32_t device, nb2_mode
         return NB2_ERR_INVALID_ARGUMENT;
     }
     *out = nullptr;
-    NB2_CUDA_CHECK(cudaSetDevice(device));
+    DeviceGuard guard(device);
     nb2_model* m = new nb2_model();
     m->device = device;
     nb2_status st = build_tables(m, *desc);
@@ -403,7 +416,7 @@ nb2_status nb2_model_create(const nb2_model_desc* desc, int32_t device, nb2_mode
 
 void nb2_model_destroy(nb2_model* model) {
     if (!model) return;
-    cudaSetDevice(model->device);
+    DeviceGuard guard(model->device);
     free_allocations(model);
     delete model;
 }
@@ -415,8 +428,11 @@ nb2_status nb2_model_notify_changed(nb2_model* model, const nb2_model_desc* desc
         return NB2_ERR_INVALID_ARGUMENT;
     }
     // The kernels read the Model arrays live; only refresh the borrowed pointers (topology changes need a new model).
-    if (desc->body_count != model->dev.d.body_count || desc->joint_count != model->dev.d.joint_count ||
-        desc->shape_count != model->dev.d.shape_count || desc->shape_pair_count != model->dev.d.shape_pair_count) {
+    const nb2_model_desc& o = model->dev.d;
+    if (desc->body_count != o.body_count || desc->joint_count != o.joint_count || desc->shape_count != o.shape_count ||
+        desc->shape_pair_count != o.shape_pair_count || desc->world_count != o.world_count ||
+        desc->articulation_count != o.articulation_count || desc->joint_dof_count != o.joint_dof_count ||
+        desc->joint_coord_count != o.joint_coord_count || desc->gravity_count != o.gravity_count) {
         set_error("nb2_model_notify_changed: topology changed; create a new nb2_model");
         return NB2_ERR_UNSUPPORTED;
     }
@@ -432,6 +448,7 @@ nb2_status nb2_collide(nb2_model* model, const float* body_q, const nb2_contacts
         return NB2_ERR_INVALID_ARGUMENT;
     }
     model->dev.export_rank = nullptr;  // a fresh export is in (world, key) order until nb2_contacts_sort runs
+    DeviceGuard guard(model->device);
     return launch_collide(model, body_q, contacts, static_cast<cudaStream_t>(cuda_stream));
 }
 
@@ -441,6 +458,7 @@ nb2_status nb2_contacts_sort(nb2_model* model, const nb2_contacts_view* c, void*
         set_error("nb2_contacts_sort: NULL argument / contacts view has NULL arrays");
         return NB2_ERR_INVALID_ARGUMENT;
     }
+    DeviceGuard guard(model->device);
     return launch_contacts_sort(model, *c, static_cast<cudaStream_t>(cuda_stream));
 }
 
@@ -450,6 +468,7 @@ nb2_status nb2_contacts_import(nb2_model* model, const nb2_contacts_view* c, voi
         set_error("nb2_contacts_import: NULL argument / contacts view has NULL arrays");
         return NB2_ERR_INVALID_ARGUMENT;
     }
+    DeviceGuard guard(model->device);
     return launch_contacts_import(model, *c, static_cast<cudaStream_t>(cuda_stream));
 }
 
@@ -465,6 +484,7 @@ nb2_status nb2_xpbd_step(nb2_model* model, const nb2_xpbd_params* params, const 
         return NB2_ERR_INVALID_ARGUMENT;
     }
     if ((use_contacts & NB2_XPBD_CONTACT_IMPULSE) && (use_contacts & NB2_XPBD_USE_CONTACTS)) model->xpbd_impulse_dt = dt;
+    DeviceGuard guard(model->device);
     return launch_xpbd_step(model, *params, *state_in, *state_out, *control, use_contacts, dt,
                             static_cast<cudaStream_t>(cuda_stream));
 }
@@ -478,6 +498,7 @@ nb2_status nb2_xpbd_update_contacts(nb2_model* model, const nb2_contacts_view* c
         set_error("nb2_xpbd_update_contacts: no contact impulse data available, run nb2_xpbd_step with NB2_XPBD_CONTACT_IMPULSE first");
         return NB2_ERR_INVALID_ARGUMENT;
     }
+    DeviceGuard guard(model->device);
     return launch_xpbd_update_contacts(model, *contacts, static_cast<cudaStream_t>(cuda_stream));
 }
 
@@ -487,6 +508,7 @@ nb2_status nb2_integrate_bodies(nb2_model* model, const nb2_state_view* state_in
         set_error("nb2_integrate_bodies: NULL argument");
         return NB2_ERR_INVALID_ARGUMENT;
     }
+    DeviceGuard guard(model->device);
     return launch_integrate_bodies(model, *state_in, *state_out, angular_damping, dt, static_cast<cudaStream_t>(cuda_stream));
 }
 
@@ -497,6 +519,7 @@ nb2_status nb2_featherstone_step(nb2_model* model, const nb2_featherstone_params
         set_error("nb2_featherstone_step: NULL argument");
         return NB2_ERR_INVALID_ARGUMENT;
     }
+    DeviceGuard guard(model->device);
     return launch_featherstone_step(model, *params, *state_in, *state_out, *control, use_contacts, dt,
                                     static_cast<cudaStream_t>(cuda_stream));
 }
@@ -507,6 +530,7 @@ nb2_status nb2_eval_fk(nb2_model* model, const float* joint_q, const float* join
         set_error("nb2_eval_fk: NULL argument");
         return NB2_ERR_INVALID_ARGUMENT;
     }
+    DeviceGuard guard(model->device);
     return launch_eval_fk(model, joint_q, joint_qd, body_q, body_qd, static_cast<cudaStream_t>(cuda_stream));
 }
 
@@ -525,6 +549,7 @@ nb2_status nb2_eval_fk_masked(nb2_model* model, const float* joint_q, const floa
         set_error("nb2_eval_fk_masked: negative index_count");
         return NB2_ERR_INVALID_ARGUMENT;
     }
+    DeviceGuard guard(model->device);
     return launch_eval_fk(model, joint_q, joint_qd, body_q, body_qd, static_cast<cudaStream_t>(cuda_stream), articulation_mask,
                           articulation_indices, index_count);
 }
@@ -539,6 +564,7 @@ nb2_status nb2_eval_ik(nb2_model* model, const float* body_q, const float* body_
         set_error("nb2_eval_ik: D6 joints with two or three angular axes are not supported");
         return NB2_ERR_UNSUPPORTED;
     }
+    DeviceGuard guard(model->device);
     return launch_eval_ik(model, body_q, body_qd, joint_q, joint_qd, static_cast<cudaStream_t>(cuda_stream));
 }
 

@@ -40,15 +40,17 @@ def eval_fk(model, joint_q, joint_qd, state, mask=None, indices=None, body_flag_
             mask = mask.contiguous()
         if indices is not None:
             indices = torch.as_tensor(indices, dtype=torch.int32, device=state.body_q.device).contiguous()
+        dev, nb = model.device, int(model.body_count)
+        p_jq = C.c_void_p(_abi.ptr(jq, "f32", dev, int(model.joint_coord_count), "joint_q"))
+        p_jqd = C.c_void_p(_abi.ptr(jqd, "f32", dev, int(model.joint_dof_count), "joint_qd"))
+        p_bq = C.c_void_p(_abi.ptr(state.body_q, "f32", dev, 7 * nb, "state.body_q"))
+        p_bqd = C.c_void_p(_abi.ptr(state.body_qd, "f32", dev, 6 * nb, "state.body_qd"))
         with torch.cuda.device(nm.device_index):
             if mask is None and indices is None:
-                st = _lib.lib().nb2_eval_fk(nm.handle, C.c_void_p(_abi.ptr(jq)), C.c_void_p(_abi.ptr(jqd)),
-                                            C.c_void_p(_abi.ptr(state.body_q)), C.c_void_p(_abi.ptr(state.body_qd)),
-                                            _lib.current_stream_ptr(model))
+                st = _lib.lib().nb2_eval_fk(nm.handle, p_jq, p_jqd, p_bq, p_bqd, _lib.current_stream_ptr(model))
             else:
                 st = _lib.lib().nb2_eval_fk_masked(
-                    nm.handle, C.c_void_p(_abi.ptr(jq)), C.c_void_p(_abi.ptr(jqd)), C.c_void_p(_abi.ptr(state.body_q)),
-                    C.c_void_p(_abi.ptr(state.body_qd)), C.c_void_p(None if mask is None else mask.data_ptr()),
+                    nm.handle, p_jq, p_jqd, p_bq, p_bqd, C.c_void_p(None if mask is None else mask.data_ptr()),
                     C.c_void_p(None if indices is None else indices.data_ptr()), 0 if indices is None else indices.numel(),
                     _lib.current_stream_ptr(model))
             _lib.check(st, "nb2_eval_fk")
@@ -72,8 +74,11 @@ def eval_ik(model, state, joint_q, joint_qd) -> None:
     nm = _lib.native_model(model)  # raises for CPU models
     with torch.cuda.device(nm.device_index):
         _lib.check(
-            _lib.lib().nb2_eval_ik(nm.handle, C.c_void_p(_abi.ptr(state.body_q)), C.c_void_p(_abi.ptr(state.body_qd)),
-                                   C.c_void_p(_abi.ptr(joint_q)), C.c_void_p(_abi.ptr(joint_qd)),
-                                   _lib.current_stream_ptr(model)),
+            _lib.lib().nb2_eval_ik(
+                nm.handle, C.c_void_p(_abi.ptr(state.body_q, "f32", model.device, 7 * int(model.body_count), "state.body_q")),
+                C.c_void_p(_abi.ptr(state.body_qd, "f32", model.device, 6 * int(model.body_count), "state.body_qd")),
+                C.c_void_p(_abi.ptr(joint_q, "f32", model.device, int(model.joint_coord_count), "joint_q")),
+                C.c_void_p(_abi.ptr(joint_qd, "f32", model.device, int(model.joint_dof_count), "joint_qd")),
+                _lib.current_stream_ptr(model)),
             "nb2_eval_ik",
         )

@@ -71,12 +71,16 @@ class CollisionPipeline:
     def collide(self, state, contacts, *, soft_contact_margin=None, dt=None):
         """Populate ``contacts`` from ``state.body_q`` (reference ``collide.py:1765-2207``)."""
         view = None
+        # every collide() overwrites the model's single set of contact blocks: stamp them, so that a Contacts object filled by
+        # an EARLIER collide (or cleared / edited since) is recognised as stale by the solvers and re-imported from its arrays
+        self._native.contact_stamp += 1
         if contacts is not None:
             contacts._nb2_blocks = self._native
+            contacts._nb2_stamp = self._native.contact_stamp
             contacts._nb2_exported = bool(self.export_contacts)
             if self.export_contacts:
-                view = C.byref(_abi.contacts_view(contacts))
-        st = _lib.lib().nb2_collide(self._native.handle, C.c_void_p(_abi.ptr(state.body_q)), view,
+                view = C.byref(_abi.contacts_view(contacts, self.model))
+        st = _lib.lib().nb2_collide(self._native.handle, C.c_void_p(_abi.ptr(state.body_q, "f32", self.device, 7 * int(self.model.body_count), "state.body_q")), view,
                                     _lib.current_stream_ptr(self.model))
         _lib.check(st, "nb2_collide")
         if self.deterministic and view is not None:

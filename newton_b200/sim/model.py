@@ -136,11 +136,21 @@ class Contacts:
         self.rigid_contact_match_index = None
         self.clear_buffers = False
         self._nb2_blocks = None
+        self._nb2_stamp = -1  # generation of the native contact blocks this buffer mirrors (see CollisionPipeline.collide)
 
     def clear(self, bump_generation: bool = True) -> None:
         self.contact_counters.zero_()
         if bump_generation:
             self.contact_generation += 1
+        # the native env-major blocks no longer describe this buffer: the next solver.step() re-imports the (empty) arrays
+        self._nb2_blocks = None
+        self._nb2_stamp = -1
+
+    def invalidate_native(self) -> None:
+        """Call after editing the ``rigid_contact_*`` arrays by hand: the solvers then load them through
+        ``nb2_contacts_import`` instead of consuming the contact blocks ``collide()`` left on the device."""
+        self._nb2_blocks = None
+        self._nb2_stamp = -1
 
 
 # Every per-entity Model array, its trailing shape and dtype.  Used by finalize(), to(), shard().
@@ -378,6 +388,8 @@ class Model:
             if isinstance(v, torch.Tensor):
                 moved = v.to(out.device).contiguous()
                 setattr(out, k, moved.clone() if moved.data_ptr() == v.data_ptr() else moved)  # same device: still a copy
+            elif k.startswith("_nb2_"):
+                continue  # per-model native caches (the nb2_model handle borrows THIS model's array addresses and device)
             elif k != "device":
                 setattr(out, k, v.copy() if isinstance(v, (list, set, dict)) else v)
         # re-establish the aliasing of joint_target_q_start

@@ -26,24 +26,18 @@ class SolverFeatherstone(SolverBase):
         self.friction_smoothing = friction_smoothing
         self.use_tile_gemm = use_tile_gemm
         self.fuse_cholesky = fuse_cholesky
-        self._parent_f_validated = False  # see step(): set only by tests/pending_gpu_featherstone_parent_f.py
 
     def step(self, state_in, state_out, control, contacts, dt: float) -> None:
         """Advance by ``dt`` (reference ``solver_featherstone.py:461-1066``): writes ``state_out.joint_q/joint_qd/
-        body_q/body_qd`` and, like the reference, refreshes ``state_in.body_q`` by forward kinematics."""
+        body_q/body_qd`` (+ ``body_parent_f`` when requested: compute_body_parent_f, featherstone/kernels.py:2371-2416) and, like
+        the reference, refreshes ``state_in.body_q`` by forward kinematics."""
         model = self.model
-        if getattr(state_out, "body_parent_f", None) is not None and not self._parent_f_validated:
-            # reference: compute_body_parent_f (featherstone/kernels.py:2371-2416) after the RNEA backward pass.  The kernel has the
-            # code (featherstone_step_kernel<L, true>) but it has not run on a GPU against the oracle yet
-            # (tests/pending_gpu_featherstone_parent_f.py); until then refusing beats returning an unchecked array.
-            raise NotImplementedError("SolverFeatherstone: State.body_parent_f from the CUDA path is not validated yet "
-                                      "(SolverXPBD reports it); do not request the attribute for this solver")
         if control is None:
             control = model.control(clone_variables=False)
         use_contacts = 1 if self._prepare_contacts(contacts) else 0
         p = _abi.FeatherstoneParams(self.angular_damping, int(self.update_mass_matrix_interval), self.friction_smoothing)
         st = _lib.lib().nb2_featherstone_step(
-            self._native.handle, C.byref(p), C.byref(_abi.state_view(state_in)), C.byref(_abi.state_view(state_out)),
-            C.byref(_abi.control_view(control)), use_contacts, C.c_float(dt), _lib.current_stream_ptr(model),
+            self._native.handle, C.byref(p), C.byref(_abi.state_view(state_in, model)), C.byref(_abi.state_view(state_out, model)),
+            C.byref(_abi.control_view(control, model)), use_contacts, C.c_float(dt), _lib.current_stream_ptr(model),
         )
         _lib.check(st, "nb2_featherstone_step")

@@ -58,11 +58,21 @@ class SolverBase:
         ``nb2_contacts_import`` first - per world, in array order."""
         if contacts is None or not contacts.rigid_contact_max:
             return False
-        if getattr(contacts, "_nb2_blocks", None) is not self._native:
-            st = _lib.lib().nb2_contacts_import(self._native.handle, C.byref(_abi.contacts_view(contacts)),
+        if not self._contacts_are_native(contacts):
+            if getattr(contacts, "_nb2_blocks", None) is self._native and not getattr(contacts, "_nb2_exported", True):
+                raise ValueError("these Contacts were produced with export_contacts=False and the model's contact blocks have "
+                                 "been overwritten by a later collide(): nothing is left to import")
+            self._native.contact_stamp += 1  # the import overwrites the blocks: whatever was stamped before is stale now
+            st = _lib.lib().nb2_contacts_import(self._native.handle, C.byref(_abi.contacts_view(contacts, self.model)),
                                                 _lib.current_stream_ptr(self.model))
             _lib.check(st, "nb2_contacts_import")
         return True
+
+    def _contacts_are_native(self, contacts) -> bool:
+        """True when the model's contact blocks still hold exactly what ``contacts`` describes: produced by the LAST
+        ``collide()`` / import on this model and not cleared since (``Contacts._nb2_stamp`` vs ``NativeModel.contact_stamp``)."""
+        return (getattr(contacts, "_nb2_blocks", None) is self._native
+                and getattr(contacts, "_nb2_stamp", -1) == self._native.contact_stamp)
 
     def notify_model_changed(self, flags: int) -> None:
         """Reference ``solver.py:394-429``: the kernels read the Model arrays live; refresh borrowed pointers."""
@@ -83,7 +93,7 @@ class SolverBase:
     def integrate_bodies(self, model, state_in, state_out, dt: float, angular_damping: float = 0.0) -> None:
         """Semi-implicit Euler on all bodies (reference ``solver.py:267-307``, kernel ``:112-170``)."""
         st = _lib.lib().nb2_integrate_bodies(
-            self._native.handle, C.byref(_abi.state_view(state_in)), C.byref(_abi.state_view(state_out)),
+            self._native.handle, C.byref(_abi.state_view(state_in, self.model)), C.byref(_abi.state_view(state_out, self.model)),
             C.c_float(angular_damping), C.c_float(dt), _lib.current_stream_ptr(self.model),
         )
         _lib.check(st, "nb2_integrate_bodies")

@@ -51,7 +51,7 @@ class SolverXPBD(SolverBase):
             control = model.control(clone_variables=False)
         use_contacts = 0
         if contacts is not None:
-            foreign = getattr(contacts, "_nb2_blocks", None) is not self._native
+            foreign = not self._contacts_are_native(contacts)
             use_contacts = 1 if self._prepare_contacts(contacts) else 0
             if use_contacts and getattr(contacts, "force", None) is not None:  # the reference keeps impulses when contacts.force exists
                 if foreign or not getattr(contacts, "_nb2_exported", False):
@@ -61,8 +61,8 @@ class SolverXPBD(SolverBase):
                 self._contact_impulse_capacity = contacts.rigid_contact_max
         p = self._params()
         st = _lib.lib().nb2_xpbd_step(
-            self._native.handle, C.byref(p), C.byref(_abi.state_view(state_in)), C.byref(_abi.state_view(state_out)),
-            C.byref(_abi.control_view(control)), use_contacts, C.c_float(dt), _lib.current_stream_ptr(model),
+            self._native.handle, C.byref(p), C.byref(_abi.state_view(state_in, model)), C.byref(_abi.state_view(state_out, model)),
+            C.byref(_abi.control_view(control, model)), use_contacts, C.c_float(dt), _lib.current_stream_ptr(model),
         )
         _lib.check(st, "nb2_xpbd_step")
 
@@ -80,6 +80,6 @@ class SolverXPBD(SolverBase):
                 f"Contacts capacity mismatch: update_contacts() received rigid_contact_max={contacts.rigid_contact_max}, "
                 f"but step() used {self._contact_impulse_capacity}. Pass the same Contacts instance to both."
             )
-        st = _lib.lib().nb2_xpbd_update_contacts(self._native.handle, C.byref(_abi.contacts_view(contacts)),
+        st = _lib.lib().nb2_xpbd_update_contacts(self._native.handle, C.byref(_abi.contacts_view(contacts, self.model)),
                                                  _lib.current_stream_ptr(self.model))
         _lib.check(st, "nb2_xpbd_update_contacts")

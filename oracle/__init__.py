@@ -195,6 +195,64 @@ class SolverFeatherstone:
                                     C.byref(cv), ctp, C.c_float(dt))
 
 
+class _Shard(C.Structure):
+    _fields_ = [("model", C.c_void_p), ("state_0", _abi.StateView), ("state_1", _abi.StateView), ("control", _abi.ControlView),
+                ("contacts", _abi.ContactsView), ("featherstone", C.c_void_p)]
+
+
+class _Loop(C.Structure):
+    _fields_ = [("solver", C.c_int32), ("substeps", C.c_int32), ("dt", C.c_float), ("xpbd", _abi.XPBDParams),
+                ("featherstone", _abi.FeatherstoneParams)]
+
+
+class FramePool:
+    """bench.py's CPU arm: the reference substep loop (clear_forces -> collide -> solver.step -> swap) of many independent
+    world shards on a persistent pool of native threads (``orc_pool_*`` in oracle.cpp).  Threads are created here, before any
+    timer; :meth:`run_frames` returns the seconds measured inside the library around the parallel region only."""
+
+    def __init__(self, models, make_solver, *, substeps: int, dt: float, threads: int):
+        L = lib()
+        L.orc_pool_new.restype = C.c_void_p
+        L.orc_pool_free.argtypes = [C.c_void_p]
+        L.orc_pool_run_frames.restype = C.c_double
+        self.threads = int(threads)
+        self._keep = []
+        self._shards = (_Shard * len(models))()
+        solver0 = None
+        for i, m in enumerate(models):
+            pipe, solver = CollisionPipeline(m, deterministic=False), make_solver(m)
+            s0, s1, ctrl, contacts = m.state(), m.state(), m.control(), pipe.contacts()
+            self._keep.append((m, pipe, solver, s0, s1, ctrl, contacts))
+            sh = self._shards[i]
+            sh.model = C.addressof(solver._desc)
+            sh.state_0, sh.state_1 = _abi.state_view(s0), _abi.state_view(s1)
+            sh.control, sh.contacts = _abi.control_view(ctrl), _abi.contacts_view(contacts)
+            sh.featherstone = solver._h if isinstance(solver, SolverFeatherstone) else None
+            solver0 = solver0 or solver
+        self._loop = _Loop()
+        self._loop.substeps, self._loop.dt = int(substeps), float(dt)
+        if isinstance(solver0, SolverFeatherstone):
+            self._loop.solver, self._loop.featherstone = 1, solver0.params
+        else:
+            self._loop.solver, self._loop.xpbd = 0, solver0.params
+        self._h = C.c_void_p(L.orc_pool_new(self.threads))
+
+    def run_frames(self, frames: int) -> float:
+        return float(lib().orc_pool_run_frames(self._h, self._shards, C.c_int(len(self._shards)), C.byref(self._loop),
+                                               C.c_int(int(frames))))
+
+    def close(self):
+        if self._h is not None:
+            lib().orc_pool_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def primitive_pair(type_a, scale_a, xform_a, type_b, scale_b, xform_b, plane_box_margin=0.0):
     """One analytic collider call: returns (is_analytic, dist[4], pos[4,3], normal[3])."""
     sa = np.asarray(scale_a, dtype=np.float32)

@@ -285,6 +285,122 @@ int orc_eval_ik(const nb2_model_desc* m, const float* body_q, const float* body_
     return eval_articulation_ik(*m, body_q, body_qd, joint_q, joint_qd);
 }
 
-const char* orc_version(void) { return "oracle-r1"; }
+
+// ---- multi-threaded frame loop for bench.py's cpu_baseline / --impl reference legs -------------------------------------
+// The reference's Warp-CPU device runs one kernel after the other on ONE host thread; environments are independent, so the
+// "all host cores" figure SURVEY.md §8(d) asks for splits the batch into shards and runs the reference substep loop
+// (clear_forces -> collide -> solver.step -> swap; example_basic_urdf.py:117-135) of every shard on a persistent pool of native
+// threads - no Python, no GIL, no per-call marshalling inside the timed region.  Threads are created once (orc_pool_new), park
+// on a condition variable, and orc_pool_run_frames() returns the seconds between releasing them and the last one finishing.
+struct OrcShard {
+    const nb2_model_desc* model;
+    nb2_state_view state_0, state_1;
+    nb2_control_view control;
+    nb2_contacts_view contacts;
+    void* featherstone;  // orc_featherstone_new() handle, or NULL for XPBD
+};
+struct OrcLoop {
+    int32_t solver;  // 0 = XPBD, 1 = Featherstone
+    int32_t substeps;
+    float dt;
+    nb2_xpbd_params xpbd;
+    nb2_featherstone_params featherstone;
+};
+
+}  // extern "C"
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+
+namespace {
+struct OrcPool {
+    std::vector<std::thread> threads;
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    long generation = 0;
+    int remaining = 0;
+    bool quit = false;
+    OrcShard* shards = nullptr;
+    int shard_count = 0;
+    const OrcLoop* loop = nullptr;
+    int frames = 0;
+    std::atomic<int> next{0};
+};
+
+void run_shard_frames(OrcShard& s, const OrcLoop& L, int frames) {
+    const nb2_model_desc& m = *s.model;
+    for (int i = 0; i < frames * L.substeps; ++i) {
+        std::memset(s.state_0.body_f, 0, size_t(m.body_count) * 6 * sizeof(float));  // State.clear_forces (sim/state.py:189-200)
+        orc_collide(&m, s.state_0.body_q, &s.contacts, 0);
+        if (L.solver == 0) orc_xpbd_step(&m, &L.xpbd, &s.state_0, &s.state_1, &s.control, &s.contacts, L.dt, nullptr);
+        else orc_featherstone_step(s.featherstone, &m, &L.featherstone, &s.state_0, &s.state_1, &s.control, &s.contacts, L.dt);
+        std::swap(s.state_0, s.state_1);
+    }
+}
+
+void pool_worker(OrcPool* p) {
+    long seen = 0;
+    for (;;) {
+        {
+            std::unique_lock<std::mutex> lk(p->mu);
+            p->cv_go.wait(lk, [&] { return p->quit || p->generation != seen; });
+            if (p->quit) return;
+            seen = p->generation;
+        }
+        for (;;) {  // shards are handed out dynamically: a slow thread (SMT sibling, OS noise) does not hold the frame back
+            int i = p->next.fetch_add(1);
+            if (i >= p->shard_count) break;
+            run_shard_frames(p->shards[i], *p->loop, p->frames);
+        }
+        std::unique_lock<std::mutex> lk(p->mu);
+        if (--p->remaining == 0) p->cv_done.notify_all();
+    }
+}
+}  // namespace
+
+extern "C" {
+
+void* orc_pool_new(int threads) {
+    OrcPool* p = new OrcPool();
+    for (int i = 0; i < threads; ++i) p->threads.emplace_back(pool_worker, p);
+    return p;
+}
+void orc_pool_free(void* h) {
+    OrcPool* p = static_cast<OrcPool*>(h);
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        p->quit = true;
+    }
+    p->cv_go.notify_all();
+    for (auto& t : p->threads) t.join();
+    delete p;
+}
+// Runs `frames` frames of every shard on the pool (shard states are swapped in place, so consecutive calls continue the same
+// simulation).  Returns wall seconds from releasing the parked threads to the last shard finishing.
+double orc_pool_run_frames(void* h, OrcShard* shards, int shard_count, const OrcLoop* loop, int frames) {
+    OrcPool* p = static_cast<OrcPool*>(h);
+    auto t0 = std::chrono::steady_clock::now();
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        p->shards = shards;
+        p->shard_count = shard_count;
+        p->loop = loop;
+        p->frames = frames;
+        p->next = 0;
+        p->remaining = int(p->threads.size());
+        ++p->generation;
+    }
+    p->cv_go.notify_all();
+    {
+        std::unique_lock<std::mutex> lk(p->mu);
+        p->cv_done.wait(lk, [&] { return p->remaining == 0; });
+    }
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+const char* orc_version(void) { return "oracle-r2"; }
 
 }  // extern "C"
