@@ -100,6 +100,7 @@ def parse_args():
     p.add_argument("--workload", default="quadruped_xpbd", choices=sorted(WORKLOADS))
     p.add_argument("--fast-fp", action="store_true", help="use the FMA-contracted twin library (not bit-exact vs the oracle)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N > 1: end-of-frame state gather mechanism")
     a = p.parse_args()
     select_workload(a.workload)
     if a.envs is None:
@@ -226,23 +227,45 @@ def run_native(args):
 
     gathered_q = gathered_qd = snap_q = snap_qd = None
     pending = []  # NCCL work handles of the previous frame's gather
+    peer = None
+    gather_mode = "none"
     if world > 1:  # end-of-frame state gather over NVLink; part of every timed step
-        gathered_q = torch.empty((world * state_0.body_q.shape[0], 7), dtype=torch.float32, device=dev)
-        gathered_qd = torch.empty((world * state_0.body_qd.shape[0], 6), dtype=torch.float32, device=dev)
-        snap_q, snap_qd = torch.empty_like(state_0.body_q), torch.empty_like(state_0.body_qd)
+        if args.gather == "peer":
+            try:
+                from newton_b200.sim.sharding import PeerStateGather
+
+                peer = PeerStateGather([state_0.body_q, state_0.body_qd])
+                gather_mode = "peer writes on the copy engines (nb2_peer_gather_*: CUDA IPC + cudaMemcpyAsync + stream wait-value)"
+            except Exception as e:  # no P2P / IPC on this box: the NCCL path below still gives a valid number
+                peer = None
+                print(f"[bench] peer gather unavailable ({type(e).__name__}: {e}); falling back to NCCL", file=sys.stderr)
+            ok = torch.tensor([1 if peer is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                peer = None
+        if peer is None:
+            gather_mode = "NCCL all_gather_into_tensor"
+            gathered_q = torch.empty((world * state_0.body_q.shape[0], 7), dtype=torch.float32, device=dev)
+            gathered_qd = torch.empty((world * state_0.body_qd.shape[0], 6), dtype=torch.float32, device=dev)
+            snap_q, snap_qd = torch.empty_like(state_0.body_q), torch.empty_like(state_0.body_qd)
 
     def drain():
+        if peer is not None:
+            peer.wait()  # stream-level wait until every rank's slice of the last push has landed here
+            return
         for w in pending:
             w.wait()  # stream-level wait (no host sync)
         pending.clear()
 
     def step_device():
-        """One frame.  N > 1: the frame's body_q / body_qd are snapshotted (2.8 MB D2D) and all-gathered on NCCL's stream
-        while the next frame computes (SURVEY.md §8(e): "on a dedicated stream, overlapped with the next frame");
-        the snapshot buffers are recycled only after the previous gather has finished, and the last gather is drained
-        inside the timed region."""
+        """One frame.  N > 1: the frame's body_q / body_qd are snapshotted (2.8 MB D2D) and gathered on a side stream while the
+        next frame computes ("on a dedicated stream, overlapped with the next frame"); the snapshot is recycled
+        only after the previous gather has read it, and the last gather is drained inside the timed region."""
         graph.replay()
         if world > 1:
+            if peer is not None:
+                peer.push([state_0.body_q, state_0.body_qd])
+                return
             drain()
             snap_q.copy_(state_0.body_q)
             snap_qd.copy_(state_0.body_qd)
@@ -380,6 +403,8 @@ def run_native(args):
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step), "frame_stats": extras,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+            "comm": {"backend": "nccl" if world > 1 else None, "nranks": world, "gather": gather_mode,
+                     "gather_bytes_per_rank_per_step": int(state_0.body_q.numel() * 4 + state_0.body_qd.numel() * 4) if world > 1 else 0},
         }
         print(json.dumps(out))
     if world > 1:

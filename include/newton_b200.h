@@ -104,6 +104,18 @@ typedef struct nb2_model_desc {
     const float* shape_material_restitution;
     /* explicit broad-phase pairs [shape_pair_count, 2] (reference model.shape_contact_pairs) */
     const int32_t* shape_contact_pairs;
+    /* CONVEX_MESH shapes (GeoType 10; reference ModelBuilder.add_shape_convex_hull, sim/builder.py:7201-7241).  The reference keeps
+       one wp.Mesh per shape behind model.shape_source_ptr and reads mesh.points in support_map (geometry/support_function.py:
+       153-172); the C-ABI takes the same data as a vertex pool: shape s owns hull_points[shape_hull_start[s] ..
+       + shape_hull_count[s]) (UNSCALED vertices, vec3; count 0 for every other shape type; shapes may share a range).
+       shape_collision_aabb_lower / _upper: local AABB with the shape scale baked in (model.shape_collision_aabb_lower,
+       sim/builder.py:11605-11610, 11686-11687), read by compute_shape_aabbs (sim/collide.py:420-444) and as the Minkowski-centre
+       seed of MPR / GJK (narrow_phase.py:1102-1105).  All five may be NULL when the model has no CONVEX_MESH shape. */
+    const float* shape_collision_aabb_lower;
+    const float* shape_collision_aabb_upper;
+    const int32_t* shape_hull_start;
+    const int32_t* shape_hull_count;
+    const float* hull_points;
     /* gravity [world_count + 1] vec3, last slot = global world -1 (reference sim/model.py:1300-1307);
        gravity_count is the number of vec3 entries actually present (1 for implicit single-world models) */
     const float* gravity;
@@ -283,6 +295,24 @@ nb2_status nb2_view_scatter(void* attrib, const nb2_view_layout* layout, const v
 nb2_status nb2_view_articulation_mask(const uint8_t* mask, int32_t mask_ndim, const int32_t* articulation_ids,
                                       int32_t world_count, int32_t count_per_world, uint8_t* model_mask,
                                       int32_t articulation_count, void* cuda_stream);
+
+/* --- multi-GPU end-of-frame state gather without compute kernels --------------------------------------
+ * Replaces the `ncclAllGather(body_q, body_qd)` of the reference design (there is no reference code for it: upstream is
+ * single-GPU; the sharding follows sim/model.py:1081-1097 world ranges).  Every rank owns a receive buffer of
+ * 2 slots x world_size x bytes_per_rank bytes, exported through CUDA IPC and mapped by all peers of the node; a push writes
+ * the rank's slice into every peer's buffer with the copy engines (NVLink DMA) and publishes the frame's sequence number, a
+ * wait blocks a stream (not the host, not an SM) until all slices of that sequence have landed. */
+typedef struct nb2_peer_gather nb2_peer_gather;
+size_t nb2_peer_gather_handle_bytes(void);
+nb2_status nb2_peer_gather_create(int32_t device, int32_t rank, int32_t world_size, size_t bytes_per_rank, nb2_peer_gather** out);
+/* device address of receive slot `slot` (0 / 1): world_size slices at nb2_peer_gather_stride() bytes from one another */
+void* nb2_peer_gather_buffer(nb2_peer_gather* g, int32_t slot);
+size_t nb2_peer_gather_stride(const nb2_peer_gather* g);
+nb2_status nb2_peer_gather_export(nb2_peer_gather* g, void* handle_out);
+nb2_status nb2_peer_gather_connect(nb2_peer_gather* g, const void* all_handles);
+nb2_status nb2_peer_gather_push(nb2_peer_gather* g, const void* src, size_t bytes, int32_t sequence, void* cuda_stream);
+nb2_status nb2_peer_gather_wait(nb2_peer_gather* g, int32_t sequence, void* cuda_stream);
+void nb2_peer_gather_destroy(nb2_peer_gather* g);
 
 /* --- diagnostics ---------------------------------------------------------------------------- */
 const char* nb2_last_error(void);

@@ -136,6 +136,11 @@ class ModelDesc(C.Structure):
         ("shape_material_mu_rolling", C.c_void_p),
         ("shape_material_restitution", C.c_void_p),
         ("shape_contact_pairs", C.c_void_p),
+        ("shape_collision_aabb_lower", C.c_void_p),
+        ("shape_collision_aabb_upper", C.c_void_p),
+        ("shape_hull_start", C.c_void_p),
+        ("shape_hull_count", C.c_void_p),
+        ("hull_points", C.c_void_p),
         ("gravity", C.c_void_p),
         ("gravity_count", C.c_int32),
     ]
@@ -226,7 +231,8 @@ class ViewLayout(C.Structure):
 _MODEL_KIND = {n: "i32" for n in (
     "body_flags", "body_world", "body_world_start", "joint_type", "joint_parent", "joint_child", "joint_ancestor",
     "joint_articulation", "joint_q_start", "joint_qd_start", "joint_target_q_start", "joint_dof_dim", "joint_world_start",
-    "articulation_start", "shape_body", "shape_type", "shape_flags", "shape_world", "shape_world_start", "shape_contact_pairs")}
+    "articulation_start", "shape_body", "shape_type", "shape_flags", "shape_world", "shape_world_start", "shape_contact_pairs",
+    "shape_hull_start", "shape_hull_count")}
 _MODEL_KIND["joint_enabled"] = "bool"
 
 

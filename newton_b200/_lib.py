@@ -21,6 +21,8 @@ EXPORTED_SYMBOLS = (
     "nb2_model_create", "nb2_model_destroy", "nb2_model_notify_changed", "nb2_model_rigid_contact_max", "nb2_collide", "nb2_contacts_sort", "nb2_contacts_import",
     "nb2_xpbd_step", "nb2_xpbd_update_contacts", "nb2_integrate_bodies", "nb2_featherstone_step", "nb2_eval_fk", "nb2_eval_ik", "nb2_eval_fk_masked",
     "nb2_view_gather", "nb2_view_scatter", "nb2_view_articulation_mask", "nb2_last_error", "nb2_kernel_launch_count", "nb2_version",
+    "nb2_peer_gather_handle_bytes", "nb2_peer_gather_create", "nb2_peer_gather_buffer", "nb2_peer_gather_stride", "nb2_peer_gather_export",
+    "nb2_peer_gather_connect", "nb2_peer_gather_push", "nb2_peer_gather_wait", "nb2_peer_gather_destroy",
 )
 
 
@@ -75,6 +77,23 @@ def lib():
         L.nb2_view_scatter.restype = C.c_int
         L.nb2_view_articulation_mask.argtypes = [P, C.c_int32, P, C.c_int32, C.c_int32, P, C.c_int32, P]
         L.nb2_view_articulation_mask.restype = C.c_int
+        L.nb2_peer_gather_handle_bytes.restype = C.c_size_t
+        L.nb2_peer_gather_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_size_t, C.POINTER(P)]
+        L.nb2_peer_gather_create.restype = C.c_int
+        L.nb2_peer_gather_buffer.argtypes = [P, C.c_int32]
+        L.nb2_peer_gather_buffer.restype = P
+        L.nb2_peer_gather_stride.argtypes = [P]
+        L.nb2_peer_gather_stride.restype = C.c_size_t
+        L.nb2_peer_gather_export.argtypes = [P, P]
+        L.nb2_peer_gather_export.restype = C.c_int
+        L.nb2_peer_gather_connect.argtypes = [P, P]
+        L.nb2_peer_gather_connect.restype = C.c_int
+        L.nb2_peer_gather_push.argtypes = [P, P, C.c_size_t, C.c_int32, P]
+        L.nb2_peer_gather_push.restype = C.c_int
+        L.nb2_peer_gather_wait.argtypes = [P, C.c_int32, P]
+        L.nb2_peer_gather_wait.restype = C.c_int
+        L.nb2_peer_gather_destroy.argtypes = [P]
+        L.nb2_peer_gather_destroy.restype = None
         L.nb2_last_error.restype = C.c_char_p
         L.nb2_kernel_launch_count.restype = C.c_int64
         L.nb2_version.restype = C.c_char_p

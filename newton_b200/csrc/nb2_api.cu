@@ -115,7 +115,7 @@ static nb2_status build_tables(nb2_model* m, const nb2_model_desc& d) {
         return shape_world[s];
     };
     // ---- pairs: group by env, order shapes by type, sort by the deterministic contact key ----
-    struct PairRec { int env; int64_t key; int sa, sb; };
+    struct PairRec { int env; int64_t key; int sa, sb; int max_contacts; };
     std::vector<PairRec> recs;
     recs.reserve(P);
     for (int t = 0; t < P; ++t) {
@@ -125,15 +125,22 @@ static nb2_status build_tables(nb2_model* m, const nb2_model_desc& d) {
         int env = w1 >= 0 ? w1 : w2;
         if (w1 >= 0 && w2 >= 0 && w1 != w2) continue;  // cross-world pairs never collide
         if (env < 0) continue;                           // static-vs-static global pair: no dynamic body involved
-        int sa = s1, sb = s2;
+        int sa = s1, sb = s2, pair_max = 5;
         if (shape_type[sa] > shape_type[sb]) std::swap(sa, sb);  // narrow_phase.py:525-528
         {   // shapes the narrow phase of this library covers: analytic primitives + convex primitives through MPR/GJK
             const int ta = shape_type[sa], tb = shape_type[sb];
-            auto known = [](int t) { return t == 1 || (t >= 3 && t <= 7) || t == 9; };  // PLANE SPHERE CAPSULE ELLIPSOID CYLINDER BOX CONE
+            // PLANE SPHERE CAPSULE ELLIPSOID CYLINDER BOX CONE CONVEX_MESH
+            auto known = [](int t) { return t == 1 || (t >= 3 && t <= 7) || t == 9 || t == 10; };
             if (!known(ta) || !known(tb)) {
                 set_error("shape pair (" + std::to_string(sa) + "," + std::to_string(sb) + "): geometry types " + std::to_string(ta) + "/" +
-                          std::to_string(tb) + " are outside the supported set (plane, sphere, capsule, ellipsoid, cylinder, box, cone)");
+                          std::to_string(tb) + " are outside the supported set (plane, sphere, capsule, ellipsoid, cylinder, box, cone, "
+                          "convex mesh)");
                 return NB2_ERR_UNSUPPORTED;
+            }
+            if ((ta == 10 || tb == 10) &&
+                (!d.hull_points || !d.shape_hull_start || !d.shape_hull_count || !d.shape_collision_aabb_lower || !d.shape_collision_aabb_upper)) {
+                set_error("CONVEX_MESH shapes need model.hull_points / shape_hull_start / shape_hull_count / shape_collision_aabb_lower / _upper");
+                return NB2_ERR_INVALID_ARGUMENT;
             }
             {   // narrow_phase.py:642-655 + the analytic chain of narrow_phase.py:657-864: everything else is MPR / GJK
                 // (a plane that gets there - cone, barrel cylinder lying on its side - is replaced by a box proxy)
@@ -142,10 +149,11 @@ static nb2_status build_tables(nb2_model* m, const nb2_model_desc& d) {
                 const bool analytic = !early && ((ta == 1 && (tb == 3 || tb == 4 || tb == 5 || (tb == 6 && !barrel) || tb == 7)) ||
                                                  (ta == 3 && (tb == 3 || tb == 4 || tb == 7 || (tb == 6 && !barrel))) || (ta == 4 && tb == 4));
                 if (!analytic) m->has_convex_pairs = true;
+                pair_max = analytic ? 4 : 5;  // analytic colliders return <= 4 points (plane-box / plane-cylinder), manifolds <= 5
             }
         }
         int64_t key = ((int64_t(sa) & 0xFFFFF) << 43) | ((int64_t(sb) & 0xFFFFF) << 23);
-        recs.push_back({env, key, sa, sb});
+        recs.push_back({env, key, sa, sb, pair_max});
     }
     std::stable_sort(recs.begin(), recs.end(), [](const PairRec& a, const PairRec& b) {
         return a.env != b.env ? a.env < b.env : a.key < b.key;
@@ -165,7 +173,10 @@ static nb2_status build_tables(nb2_model* m, const nb2_model_desc& d) {
                     if (h.global_shapes[g] == s) return nloc + int(g);
                 return -1;
             };
+            int env_max = 0;
             for (; i < recs.size() && recs[i].env == e; ++i) {
+                env_max += recs[i].max_contacts;
+                m->max_env_contacts = std::max(m->max_env_contacts, env_max);
                 int a = slot_of(recs[i].sa), b = slot_of(recs[i].sb);
                 if (a < 0 || b < 0) {
                     set_error("contact pair references a shape outside its world");
@@ -448,6 +459,7 @@ nb2_status nb2_collide(nb2_model* model, const float* body_q, const nb2_contacts
         return NB2_ERR_INVALID_ARGUMENT;
     }
     model->dev.export_rank = nullptr;  // a fresh export is in (world, key) order until nb2_contacts_sort runs
+    model->contacts_imported = false;
     DeviceGuard guard(model->device);
     return launch_collide(model, body_q, contacts, static_cast<cudaStream_t>(cuda_stream));
 }
@@ -469,6 +481,7 @@ nb2_status nb2_contacts_import(nb2_model* model, const nb2_contacts_view* c, voi
         return NB2_ERR_INVALID_ARGUMENT;
     }
     DeviceGuard guard(model->device);
+    model->contacts_imported = true;
     return launch_contacts_import(model, *c, static_cast<cudaStream_t>(cuda_stream));
 }
 

@@ -23,7 +23,7 @@
 
 namespace nb2 {
 
-enum { GEO_PLANE = 1, GEO_SPHERE = 3, GEO_CAPSULE = 4, GEO_ELLIPSOID = 5, GEO_CYLINDER = 6, GEO_BOX = 7, GEO_CONE = 9 };
+enum { GEO_PLANE = 1, GEO_SPHERE = 3, GEO_CAPSULE = 4, GEO_ELLIPSOID = 5, GEO_CYLINDER = 6, GEO_BOX = 7, GEO_CONE = 9, GEO_CONVEX_MESH = 10 };
 #define NB2_MAXVAL 1.0e10f
 
 // ---- analytic colliders --------------------------------------------------------------------------
@@ -214,10 +214,21 @@ NB2_DEV void sphere_box(V3 sp, float sr, V3 bp, const M33& R, V3 half, float& di
 }
 
 // World AABB of one shape, expanded by margin + gap (compute_shape_aabbs).
-NB2_DEV void shape_aabb(int type, V3 scale, const Xf& X, float gap_eff, float coll_radius, V3& lo, V3& hi) {
+NB2_DEV void shape_aabb(int type, V3 scale, const Xf& X, float gap_eff, float coll_radius, V3 local_lo, V3 local_hi, V3& lo, V3& hi) {
     V3 pos = X.p;
     V3 mvv(gap_eff, gap_eff, gap_eff);
     V3 he;
+    if (type == GEO_CONVEX_MESH) {  // has_local_aabb (collide.py:420-444): the builder's scaled local AABB rotated into the world
+        const V3 center = (local_lo + local_hi) * 0.5f, half = (local_hi - local_lo) * 0.5f;
+        const V3 wc = qrot(X.q, center) + pos;
+        const V3 r0 = qrot(X.q, V3(1.f, 0.f, 0.f)), r1 = qrot(X.q, V3(0.f, 1.f, 0.f)), r2 = qrot(X.q, V3(0.f, 0.f, 1.f));
+        const V3 wh(fabsf(r0.x) * half.x + fabsf(r1.x) * half.y + fabsf(r2.x) * half.z,
+                    fabsf(r0.y) * half.x + fabsf(r1.y) * half.y + fabsf(r2.y) * half.z,
+                    fabsf(r0.z) * half.x + fabsf(r1.z) * half.y + fabsf(r2.z) * half.z);
+        lo = wc - wh - mvv;
+        hi = wc + wh + mvv;
+        return;
+    }
     if (type == GEO_PLANE && scale.x == 0.0f && scale.y == 0.0f) {
         V3 normal = qrot(X.q, V3(0.f, 0.f, 1.f));
         const float EXT = 1.0e6f;
@@ -319,7 +330,13 @@ __global__ void __launch_bounds__(32) collide_kernel(DevModel M, const float* __
         if (body != -1) X = xmul(ldx(body_q + 7 * body), X);
         float margin = d.shape_margin[sid];
         V3 lo, hi;
-        shape_aabb(d.shape_type[sid], ld3(d.shape_scale + 3 * sid), X, margin + d.shape_gap[sid], d.shape_collision_radius[sid], lo, hi);
+        const int stype = d.shape_type[sid];
+        V3 llo, lhi;
+        if (stype == GEO_CONVEX_MESH) {
+            llo = ld3(d.shape_collision_aabb_lower + 3 * sid);
+            lhi = ld3(d.shape_collision_aabb_upper + 3 * sid);
+        }
+        shape_aabb(stype, ld3(d.shape_scale + 3 * sid), X, margin + d.shape_gap[sid], d.shape_collision_radius[sid], llo, lhi, lo, hi);
         stx(slots[s].x, X);
         st3(slots[s].lo, lo);
         st3(slots[s].hi, hi);
@@ -422,6 +439,16 @@ __global__ void __launch_bounds__(32) collide_kernel(DevModel M, const float* __
                 } else if (CONVEX) {
                     ConvexShape A{ta, sca, Xa, marg_a, d.shape_gap[sa], alo, ahi};
                     ConvexShape Bc{tb, scb, Xb, marg_b, d.shape_gap[sb], blo, bhi};
+                    if (ta == GEO_CONVEX_MESH) {  // narrow_phase.py:1096-1105
+                        A.hull = d.hull_points + 3 * size_t(d.shape_hull_start[sa]);
+                        A.hull_count = d.shape_hull_count[sa];
+                        A.center = 0.5f * (ld3(d.shape_collision_aabb_lower + 3 * sa) + ld3(d.shape_collision_aabb_upper + 3 * sa));
+                    }
+                    if (tb == GEO_CONVEX_MESH) {
+                        Bc.hull = d.hull_points + 3 * size_t(d.shape_hull_start[sb]);
+                        Bc.hull_count = d.shape_hull_count[sb];
+                        Bc.center = 0.5f * (ld3(d.shape_collision_aabb_lower + 3 * sb) + ld3(d.shape_collision_aabb_upper + 3 * sb));
+                    }
                     vmask = convex_pair_contacts(A, Bc, cdist, cpos, cnorm, reff_a, reff_b);
                 }
             }

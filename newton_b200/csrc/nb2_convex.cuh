@@ -17,11 +17,20 @@
 
 namespace nb2 {
 
-enum { CG_PLANE = 1, CG_SPHERE = 3, CG_CAPSULE = 4, CG_ELLIPSOID = 5, CG_CYLINDER = 6, CG_BOX = 7, CG_CONE = 9 };
+enum { CG_PLANE = 1, CG_SPHERE = 3, CG_CAPSULE = 4, CG_ELLIPSOID = 5, CG_CYLINDER = 6, CG_BOX = 7, CG_CONE = 9, CG_CONVEX_MESH = 10 };
 
-struct ConvexGeom {  // GenericShapeData without mesh fields; centre is the local origin for every primitive
+// GenericShapeData (support_function.py:84-118).  `center` is the Minkowski-centre seed: the local origin for every primitive,
+// the centre of the scaled local AABB for a convex hull (narrow_phase.py:1102-1105).  `hull` / `hull_count` are the hull's
+// UNSCALED vertices (wp.Mesh.points of shape_source; the per-shape scale is applied by the support map) - null for primitives.
+struct ConvexGeom {
     int type;
     V3 scale;
+    V3 center;
+    const float* hull;
+    int hull_count;
+    NB2_DEV ConvexGeom() : type(0), hull(nullptr), hull_count(0) {}
+    NB2_DEV ConvexGeom(int t, V3 s) : type(t), scale(s), hull(nullptr), hull_count(0) {}
+    NB2_DEV ConvexGeom(int t, V3 s, V3 c, const float* h, int n) : type(t), scale(s), center(c), hull(h), hull_count(n) {}
 };
 
 NB2_DEV float rsqrt_rn(float v) { return 1.0f / sqrtf(v); }  // _support_rsqrt_rn, host flavour (support_function.py:44-53)
@@ -33,6 +42,20 @@ NB2_DEV V3 support_box(V3 scale, V3 dir) {  // support_function.py:121-129
 }
 
 NB2_CALL V3 support_map(const ConvexGeom& g, V3 d) {  // support_function.py:133-352
+    if (g.type == CG_CONVEX_MESH) {  // vertex scan, first maximum wins (support_function.py:153-172)
+        const V3 sd = cmul(d, g.scale);  // dot(scale * v, d) == dot(v, scale * d): one scaling per query instead of per vertex
+        float max_dot = -1.0e10f;
+        int best = 0;
+        for (int i = 0; i < g.hull_count; ++i) {
+            const float dv = dot(V3(g.hull[3 * i], g.hull[3 * i + 1], g.hull[3 * i + 2]), sd);
+            if (dv > max_dot) {
+                max_dot = dv;
+                best = i;
+            }
+        }
+        if (g.hull_count == 0) return V3();
+        return cmul(V3(g.hull[3 * best], g.hull[3 * best + 1], g.hull[3 * best + 2]), g.scale);
+    }
     const float eps = 1.0e-12f;
     if (g.type == CG_BOX) return support_box(g.scale, d);
     if (g.type == CG_SPHERE) {
@@ -144,8 +167,8 @@ NB2_DEV bool mpr_core(const ConvexGeom& ga, const ConvexGeom& gb, Q4 qb, V3 pb, 
     point_a = V3();
     point_b = V3();
     MVert v0;
-    v0.B = pb + qrot(qb, V3());  // primitive centres are the local origins
-    v0.BtoA = V3() - v0.B;
+    v0.B = pb + qrot(qb, gb.center);  // shape_center (support_function.py:563-594): zero for primitives, AABB centre for hulls
+    v0.BtoA = ga.center - v0.B;
     normal = v0.BtoA;
     if (len2(normal) < NUM_EPS) {
         v0.BtoA = V3();  // fallback() of non-triangle shapes
@@ -401,7 +424,7 @@ NB2_DEV bool gjk_core(const ConvexGeom& ga, const ConvexGeom& gb, Q4 qb, V3 pb, 
     bc_clear(s.bc);
     s.mask = 0u;
     int iter = 30;
-    V3 v = V3() - (pb + qrot(qb, V3()));
+    V3 v = ga.center - (pb + qrot(qb, gb.center));  // geometric_center(...).BtoA (simplex_solver.py:346-348)
     float dist_sq = len2(v);
     V3 last_dir(1.f, 0.f, 0.f);
     while (iter > 0) {
@@ -690,7 +713,8 @@ NB2_CALL void post_process_contact(V3& center, float& dist, V3 normal, float ref
         center = center - normal * (reff_b * 0.5f);
         dist = dist - reff_b;
     }
-    const bool disc_a = ta == CG_BOX || ta == CG_PLANE, disc_b = tb == CG_BOX || tb == CG_PLANE;
+    // is_discrete_shape (collision_core.py:40-48)
+    const bool disc_a = ta == CG_BOX || ta == CG_PLANE || ta == CG_CONVEX_MESH, disc_b = tb == CG_BOX || tb == CG_PLANE || tb == CG_CONVEX_MESH;
     const bool ax_a = ta == CG_CYLINDER || ta == CG_CONE, ax_b = tb == CG_CYLINDER || tb == CG_CONE;
     if ((disc_a && ax_b) || (disc_b && ax_a)) {
         V3 axis, spos, an;
@@ -732,13 +756,18 @@ struct ConvexPairIn {
     V3 scale_a, scale_b;
     Xf Xa, Xb;
     float margin_a, margin_b, gap_sum;
+    // CONVEX_MESH only: unscaled hull vertices (shape_source) and the centre of the scaled local AABB (Minkowski-centre seed)
+    const float* hull_a = nullptr;
+    const float* hull_b = nullptr;
+    int hull_count_a = 0, hull_count_b = 0;
+    V3 center_a, center_b;
 };
 
 // compute_gjk_mpr_contacts -> solve_convex_multi_contact -> build_manifold (+ the writer's own gap test).
 // Outputs up to 5 contacts (world centre, normal, signed distance) in emission order; returns their count.
 // radius_eff_* are the Minkowski radii the writer needs.
 NB2_DEV int convex_contacts(const ConvexPairIn& in, float* odist, V3* opos, V3* onorm, float& reff_a, float& reff_b) {
-    ConvexGeom ga{in.type_a, in.scale_a}, gb{in.type_b, in.scale_b};
+    ConvexGeom ga(in.type_a, in.scale_a, in.center_a, in.hull_a, in.hull_count_a), gb(in.type_b, in.scale_b, in.center_b, in.hull_b, in.hull_count_b);
     reff_a = 0.0f;
     reff_b = 0.0f;
     if (ga.type == CG_SPHERE || ga.type == CG_CAPSULE) {
@@ -916,6 +945,19 @@ NB2_DEV int convex_contacts(const ConvexPairIn& in, float* odist, V3* opos, V3* 
 NB2_DEV void tight_aabb_from_support(const ConvexGeom& g, Q4 q, V3 pos, V3& lo, V3& hi) {
     const M33 R = qmat(q);
     const V3 lx(R.at(0, 0), R.at(0, 1), R.at(0, 2)), ly(R.at(1, 0), R.at(1, 1), R.at(1, 2)), lz(R.at(2, 0), R.at(2, 1), R.at(2, 2));
+    if (g.type == CG_CONVEX_MESH) {  // single pass over the vertices (collision_core.py:492-523)
+        const V3 sx = cmul(lx, g.scale), sy = cmul(ly, g.scale), sz = cmul(lz, g.scale);
+        V3 mn(1.0e10f, 1.0e10f, 1.0e10f), mx(-1.0e10f, -1.0e10f, -1.0e10f);
+        for (int i = 0; i < g.hull_count; ++i) {
+            const V3 p(g.hull[3 * i], g.hull[3 * i + 1], g.hull[3 * i + 2]);
+            const V3 v(dot(p, sx), dot(p, sy), dot(p, sz));
+            mn = vmin(mn, v);
+            mx = vmax(mx, v);
+        }
+        lo = mn + pos;
+        hi = mx + pos;
+        return;
+    }
     const float max_x = dot(lx, support_map(g, lx)), max_y = dot(ly, support_map(g, ly)), max_z = dot(lz, support_map(g, lz));
     const float min_x = dot(lx, support_map(g, -lx)), min_y = dot(ly, support_map(g, -ly)), min_z = dot(lz, support_map(g, -lz));
     lo = V3(min_x, min_y, min_z) + pos;

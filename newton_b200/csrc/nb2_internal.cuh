@@ -99,6 +99,8 @@ struct nb2_model {
     size_t sort_temp_bytes = 0;
     bool implicit_single = false;  // model built without begin_world(): one environment holding every entity
     bool has_convex_pairs = false;  // some pair's types have no analytic collider -> collide_kernel<L, true>
+    int max_env_contacts = 0;       // max over envs of the sum of the pairs' own contact maxima (<= 4 analytic, <= 5 manifold)
+    bool contacts_imported = false; // the contact blocks hold an imported foreign buffer (any count up to the slot range)
     float xpbd_impulse_dt = 0.0f;  // dt of the last nb2_xpbd_step that accumulated contact impulses (0 = none yet)
 };
 

@@ -20,6 +20,8 @@
 #include "nb2_internal.cuh"
 #include "nb2_math.cuh"
 
+#define NB2_GPU __device__ __forceinline__
+
 namespace nb2 {
 
 enum { JT_PRISMATIC = 0, JT_REVOLUTE = 1, JT_BALL = 2, JT_FIXED = 3, JT_FREE = 4, JT_DISTANCE = 5, JT_D6 = 6, JT_ROD = 7 };
@@ -28,6 +30,7 @@ enum { BODY_KINEMATIC = 2 };
 // shared-memory body record (floats): odd stride -> consecutive bodies hit different banks
 enum { BR_Q = 0, BR_QD = 7, BR_COM = 13, BR_INVM = 16, BR_INVI = 17, BR_I = 26, BR_SIZE = 35 };
 enum { DR_SIZE = 13 };  // delta record: lin_a, ang_a, lin_b, ang_b, active
+enum { XF_JOINT_CACHE = 1, XF_TMA = 2, XF_PHASE_SYNC = 4, XF_PHASE_SYNC_FINE = 8 };  // kernel flags
 
 // Code-size control.  The first kernel version inlined and unrolled everything: 9 400 SASS instructions (150 KB) and
 // 19 % of the stall samples on instruction fetch (profiles/r1a_xpbd_step_kernel.txt).  Measured on B200 (round-1c A/B,
@@ -170,7 +173,11 @@ struct Deltas {
 // solve_body_joints for one joint (kernels.py:1513-2044).  `bodies` = this env's shared-memory records.
 // Per-joint quantities that do not change over the Jacobi iterations, staged once per substep in shared memory when it
 // fits next to the body records without costing a resident CTA: the two joint frames and the angular AxisSetup.
-enum { JC_XP = 0, JC_XC = 7, JC_ANG = 14, JC_SIZE = 33 };  // odd stride: consecutive joints (lanes) hit different banks
+// ... and the joint's integer header (type, enabled, dof counts, child / parent, axis and target offsets), so the
+// iteration loop issues no global loads for joint data at all.
+enum { JC_XP = 0, JC_XC = 7, JC_ANG = 14, JC_HDR = 32, JC_CHILD = 33, JC_PARENT = 34, JC_AXIS = 35, JC_TARGET = 36,
+       JC_SIZE = 37 };  // odd stride: consecutive joints (lanes) hit different banks
+NB2_DEV int jc_int(const float* jc, int k) { return reinterpret_cast<const int*>(jc)[k]; }
 NB2_DEV void store_axis_setup(float* p, const AxisSetup& s) {
     st3(p, s.lim_lo); st3(p + 3, s.lim_up); st3(p + 6, s.target_pos); st3(p + 9, s.stiffness); st3(p + 12, s.target_vel); st3(p + 15, s.damping);
 }
@@ -182,10 +189,13 @@ NB2_DEV AxisSetup load_axis_setup(const float* p) {
 
 NB2_DEV bool solve_joint(const nb2_model_desc& d, const nb2_control_view& ctl, const nb2_xpbd_params& P, int j, int body0,
                          const float* bodies, const float* jc, float dt, Deltas& out) {
-    const int type = d.joint_type[j];
-    if (!d.joint_enabled[j] || type == JT_FREE) return false;
-    const int id_c = d.joint_child[j] - body0;
-    const int id_p_raw = d.joint_parent[j];
+    // header: bits 0-3 type, bit 4 enabled, bits 8-11 / 12-15 linear / angular dof counts
+    const int hdr = jc ? jc_int(jc, JC_HDR)
+                       : (d.joint_type[j] | (d.joint_enabled[j] ? 16 : 0) | (d.joint_dof_dim[2 * j] << 8) | (d.joint_dof_dim[2 * j + 1] << 12));
+    const int type = hdr & 15;
+    if (!(hdr & 16) || type == JT_FREE) return false;
+    const int id_c = (jc ? jc_int(jc, JC_CHILD) : d.joint_child[j]) - body0;
+    const int id_p_raw = jc ? jc_int(jc, JC_PARENT) : d.joint_parent[j];
     const int id_p = id_p_raw >= 0 ? id_p_raw - body0 : -1;
     const Xf X_pj = jc ? ldx(jc + JC_XP) : ldx(d.joint_X_p + 7 * j), X_cj = jc ? ldx(jc + JC_XC) : ldx(d.joint_X_c + 7 * j);
     BodyView bp = static_body();
@@ -206,9 +216,9 @@ NB2_DEV bool solve_joint(const nb2_model_desc& d, const nb2_control_view& ctl, c
     const Xf rel_pose = xmul(xinv(X_wp), X_wc);
     const V3 rel_p = rel_pose.p;
     const V3 x_p = X_wp.p, x_c = X_wc.p;
-    const int axis_start = d.joint_qd_start[j];
-    const int target_start = d.joint_target_q_start[j];
-    const int lin_count = d.joint_dof_dim[2 * j], ang_count = d.joint_dof_dim[2 * j + 1];
+    const int axis_start = jc ? jc_int(jc, JC_AXIS) : d.joint_qd_start[j];
+    const int target_start = jc ? jc_int(jc, JC_TARGET) : d.joint_target_q_start[j];
+    const int lin_count = (hdr >> 8) & 15, ang_count = (hdr >> 12) & 15;
     const V3 wcom_p = xpoint(pose_p, bp.com);
     const V3 wcom_c = xpoint(pose_c, bc.com);
     const V3 vel_p = bp.v, omega_p = bp.w, vel_c = bc.v, omega_c = bc.w;
@@ -443,35 +453,99 @@ NB2_HELPER void apply_delta(float* rec, V3 dlin, V3 dang, float inv_weight, bool
     st3(rec + BR_QD + 3, w1);
 }
 
+// ---- 1-D TMA (cp.async.bulk) + mbarrier helpers ------------------------------------------------------------------------
+// The CTA's environments own one contiguous run of bodies, so each per-body array of the reference layout (28-byte transforms,
+// 24-byte twists, 12-byte centres of mass, 36-byte inertia tensors ...) is ONE contiguous byte range per CTA: a single elected
+// thread asks the TMA unit to copy every such run global -> shared (complete_tx on an mbarrier) while the other lanes set up the
+// contact and joint tables; at the end of the substep the packed body_q / body_qd runs go back shared -> global as two bulk
+// stores.  Bulk copies need 16-byte aligned addresses and sizes, which holds when the CTA's first body index and body count are
+// multiples of 4 (4 quadruped envs = 52 bodies): checked per CTA, plain loads / stores otherwise.
+NB2_GPU unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+NB2_GPU void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+NB2_GPU void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+NB2_GPU void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+NB2_GPU void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+NB2_GPU void bulk_s2g(void* dst_gmem, const void* src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+NB2_GPU void bulk_commit_and_drain() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+NB2_GPU void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Shared-memory plan of one CTA (NE environments), in floats.  Identical on host and device.
+struct XpbdPlan {
+    int bodies, jcache, cpair, extra, drec, mbar, total;  // offsets of the per-CTA regions
+    int rec_cap;                                           // delta records per env; the region doubles as the TMA staging area
+};
+__host__ __device__ inline XpbdPlan xpbd_plan(int NE, int MB, int MJ, int CC, bool ex, bool joint_cache) {
+    XpbdPlan o;
+    auto up4 = [](int x) { return (x + 3) & ~3; };
+    o.rec_cap = MB > MJ ? (MB > CC ? MB : CC) : (MJ > CC ? MJ : CC);
+    o.bodies = 0;
+    o.jcache = up4(o.bodies + NE * MB * BR_SIZE);
+    o.cpair = up4(o.jcache + (joint_cache ? NE * MJ * JC_SIZE : 0));
+    o.extra = up4(o.cpair + NE * CC);
+    o.drec = up4(o.extra + (ex ? NE * MB * 14 : 0));
+    o.mbar = up4(o.drec + NE * o.rec_cap * DR_SIZE);
+    o.total = o.mbar + 4;
+    return o;
+}
+// staging layout inside the drec region: nB bodies of the CTA, arrays back to back (each a multiple of 16 bytes when nB % 4 == 0)
+enum { ST_Q = 0, ST_QD = 7, ST_COM = 13, ST_INVM = 16, ST_I = 17, ST_INVI = 26, ST_PER_BODY = 35 };
+
 // EX = false: the plain step.  EX = true adds the reporting / post-processing paths of row a17 (restitution, velocity from
 // position delta, weighted contact impulses for Contacts.force, joint impulses for State.body_parent_f); it is a second
 // instantiation so the plain step pays neither registers nor shared memory for them.
-#ifndef NB2_XPBD_MINBLOCKS
-#define NB2_XPBD_MINBLOCKS 16  // resident one-warp CTAs per SM the register allocation must allow (4096 envs need 13.8)
+//
+// WARPS warps per CTA, each warp = 32/L environments.  All warps of a CTA walk the same code at about the same time, so the
+// 6 500-instruction iteration body (far larger than the 32 KB L1.5 instruction cache) is fetched once per CTA instead of once per
+// warp; one-warp CTAs each at their own PC were 18 % `stall_no_inst` (profiles/r1f_xpbd_step_kernel.txt).
+#ifndef NB2_XPBD_MIN_WARPS
+#define NB2_XPBD_MIN_WARPS 16  // resident warps per SM the register allocation must allow (16 -> 128 registers)
 #endif
-template <int L, bool EX>
-__global__ void __launch_bounds__(32, NB2_XPBD_MINBLOCKS) xpbd_step_kernel(DevModel M, nb2_xpbd_params P, nb2_state_view sin, nb2_state_view sout,
-                                                        nb2_control_view ctl, int use_contacts_flags, float dt, int joint_cache_floats) {
+template <int L, bool EX, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, (WARPS >= NB2_XPBD_MIN_WARPS ? 1 : NB2_XPBD_MIN_WARPS / WARPS))
+xpbd_step_kernel(DevModel M, nb2_xpbd_params P, nb2_state_view sin, nb2_state_view sout, nb2_control_view ctl, int use_contacts_flags,
+                 float dt, int flags, int contact_cap) {
     const int use_contacts = use_contacts_flags & NB2_XPBD_USE_CONTACTS;
     const bool want_cimp = EX && use_contacts && (use_contacts_flags & NB2_XPBD_CONTACT_IMPULSE);
     const bool want_jimp = EX && sout.body_parent_f != nullptr;
     const bool want_init = EX && (P.enable_restitution || P.compute_body_velocity_from_position_delta);
+    const bool joint_cache = (flags & XF_JOINT_CACHE) != 0;
     constexpr int G = 32 / L;
-    extern __shared__ float smem[];
-    const int lane = threadIdx.x & 31;
+    constexpr int NE = G * WARPS;
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane / L, l = lane % L;
-    const int env = blockIdx.x * G + grp;
+    const int slot = warp * G + grp;  // environment slot inside the CTA
+    const int env0 = blockIdx.x * NE;
+    const int env = env0 + slot;
     const bool live = env < M.env_count;
     const nb2_model_desc& d = M.d;
-    const int rec_cap = max(M.max_env_contact_slots, M.max_env_joints);
-    const int per_env = M.max_env_bodies * BR_SIZE + rec_cap * DR_SIZE + M.max_env_contact_slots + (EX ? M.max_env_bodies * 14 : 0);
-    float* bodies = smem + size_t(grp) * per_env;
-    float* drec = bodies + M.max_env_bodies * BR_SIZE;
-    int* cpair = reinterpret_cast<int*>(drec + rec_cap * DR_SIZE);
-    float* init_qd = reinterpret_cast<float*>(cpair + M.max_env_contact_slots);  // EX only: state_in poses + twists (13/body)
-    float* bcnt = init_qd + M.max_env_bodies * 13;                                 // EX only: active contacts per body
-    // joint cache: the launch passes a non-zero stride only when the block still fits 14-16 CTAs per SM
-    float* jcache = joint_cache_floats ? smem + size_t(G) * per_env + size_t(grp) * joint_cache_floats : nullptr;
+    const XpbdPlan plan = xpbd_plan(NE, M.max_env_bodies, M.max_env_joints, contact_cap, EX, joint_cache);
+    float* bodies = smem + plan.bodies + slot * M.max_env_bodies * BR_SIZE;
+    float* drec = smem + plan.drec + slot * plan.rec_cap * DR_SIZE;
+    int* cpair = reinterpret_cast<int*>(smem + plan.cpair) + slot * contact_cap;
+    float* init_qd = smem + plan.extra + slot * M.max_env_bodies * 14;  // EX only: state_in poses + twists (13/body)
+    float* bcnt = init_qd + M.max_env_bodies * 13;                       // EX only: active contacts per body
+    float* jcache = joint_cache ? smem + plan.jcache + slot * M.max_env_joints * JC_SIZE : nullptr;
+    float* stage = smem + plan.drec;  // CTA-wide staging area of the bulk copies (the delta records are not live then)
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem + plan.mbar);
 
     int b0 = 0, nb = 0, j0 = 0, nj = 0, slot0 = 0, nc = 0;
     if (live) {
@@ -480,30 +554,34 @@ __global__ void __launch_bounds__(32, NB2_XPBD_MINBLOCKS) xpbd_step_kernel(DevMo
         j0 = M.env_joint_start[env];
         nj = M.env_joint_start[env + 1] - j0;
         slot0 = M.env_slot_start[env];
-        nc = use_contacts ? M.env_contact_count[env] : 0;
+        nc = use_contacts ? min(M.env_contact_count[env], contact_cap) : 0;
     }
-    // ---- load body state + constants into shared memory ------------------------------------------
-    for (int b = l; b < nb; b += L) {
-        const int gb = b0 + b;
-        float* rec = bodies + b * BR_SIZE;
-#pragma unroll
-        for (int k = 0; k < 7; ++k) rec[BR_Q + k] = sin.body_q[7 * gb + k];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) rec[BR_QD + k] = sin.body_qd[6 * gb + k];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) rec[BR_COM + k] = d.body_com[3 * gb + k];
-        const bool kin = (d.body_flags[gb] & BODY_KINEMATIC) != 0;  // _update_effective_inv_mass_inertia (solver.py:173-187)
-        rec[BR_INVM] = kin ? 0.0f : d.body_inv_mass[gb];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            rec[BR_INVI + k] = kin ? 0.0f : d.body_inv_inertia[9 * gb + k];
-            rec[BR_I + k] = d.body_inertia[9 * gb + k];
+    // ---- body state + constants -> shared memory ------------------------------------------------------------------------------
+    // CTA-uniform decision: the CTA's body run [cb0, cb0 + cnb) must be 16-byte aligned in every array it is copied from / to
+    const int env_last = min(env0 + NE, M.env_count);
+    const int cb0 = M.env_body_start[env0], cnb = M.env_body_start[env_last] - cb0;
+    bool tma = (flags & XF_TMA) != 0 && cnb > 0 && (cb0 & 3) == 0 && (cnb & 3) == 0 && cnb * ST_PER_BODY <= NE * plan.rec_cap * DR_SIZE;
+    if (tma) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(sin.body_q) | reinterpret_cast<uintptr_t>(sin.body_qd) |
+                            reinterpret_cast<uintptr_t>(sout.body_q) | reinterpret_cast<uintptr_t>(sout.body_qd) |
+                            reinterpret_cast<uintptr_t>(d.body_com) | reinterpret_cast<uintptr_t>(d.body_inv_mass) |
+                            reinterpret_cast<uintptr_t>(d.body_inertia) | reinterpret_cast<uintptr_t>(d.body_inv_inertia);
+        tma = (a & 15) == 0;
+    }
+    if (tma) {
+        if (threadIdx.x == 0) mbar_init(mbar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(mbar, unsigned(cnb) * ST_PER_BODY * 4u);
+            bulk_g2s(stage + ST_Q * cnb, sin.body_q + 7 * size_t(cb0), unsigned(cnb) * 28u, mbar);
+            bulk_g2s(stage + ST_QD * cnb, sin.body_qd + 6 * size_t(cb0), unsigned(cnb) * 24u, mbar);
+            bulk_g2s(stage + ST_COM * cnb, d.body_com + 3 * size_t(cb0), unsigned(cnb) * 12u, mbar);
+            bulk_g2s(stage + ST_INVM * cnb, d.body_inv_mass + size_t(cb0), unsigned(cnb) * 4u, mbar);
+            bulk_g2s(stage + ST_I * cnb, d.body_inertia + 9 * size_t(cb0), unsigned(cnb) * 36u, mbar);
+            bulk_g2s(stage + ST_INVI * cnb, d.body_inv_inertia + 9 * size_t(cb0), unsigned(cnb) * 36u, mbar);
         }
     }
-    if (want_init)
-        for (int b = l; b < nb; b += L)
-#pragma unroll
-            for (int k = 0; k < 13; ++k) init_qd[b * 13 + k] = bodies[b * BR_SIZE + BR_Q + k];  // q (7) then qd (6) are adjacent
+    // (while the copies are in flight) contact -> body incidence and the joint cache
     for (int c = l; c < nc; c += L) {
         const size_t T = size_t(M.slot_total);
         int ba = __float_as_int(M.cb[CF_BODY_A * T + slot0 + c]), bb = __float_as_int(M.cb[CF_BODY_B * T + slot0 + c]);
@@ -512,15 +590,73 @@ __global__ void __launch_bounds__(32, NB2_XPBD_MINBLOCKS) xpbd_step_kernel(DevMo
 #pragma unroll
             for (int k = 0; k < 6; ++k) M.contact_impulse[k * T + slot0 + c] = 0.0f;
     }
-    __syncwarp();
     if (jcache)
         for (int j = l; j < nj; j += L) {
             const int gj = j0 + j;
             float* jc = jcache + j * JC_SIZE;
+            const int lin_count = d.joint_dof_dim[2 * gj], ang_count = d.joint_dof_dim[2 * gj + 1];
+            const int axis_start = d.joint_qd_start[gj], target_start = d.joint_target_q_start[gj];
             stx(jc + JC_XP, ldx(d.joint_X_p + 7 * gj));
             stx(jc + JC_XC, ldx(d.joint_X_c + 7 * gj));
-            store_axis_setup(jc + JC_ANG, gather_axes(d, ctl, d.joint_qd_start[gj], d.joint_target_q_start[gj], d.joint_dof_dim[2 * gj],
-                                                      d.joint_dof_dim[2 * gj + 1]));
+            store_axis_setup(jc + JC_ANG, gather_axes(d, ctl, axis_start, target_start, lin_count, ang_count));
+            jc[JC_HDR] = __int_as_float(d.joint_type[gj] | (d.joint_enabled[gj] ? 16 : 0) | (lin_count << 8) | (ang_count << 12));
+            jc[JC_CHILD] = __int_as_float(d.joint_child[gj]);
+            jc[JC_PARENT] = __int_as_float(d.joint_parent[gj]);
+            jc[JC_AXIS] = __int_as_float(axis_start);
+            jc[JC_TARGET] = __int_as_float(target_start);
+        }
+    if (tma) mbar_wait(mbar, 0);
+    for (int b = l; b < nb; b += L) {
+        const int gb = b0 + b;
+        float* rec = bodies + b * BR_SIZE;
+        const bool kin = (d.body_flags[gb] & BODY_KINEMATIC) != 0;  // _update_effective_inv_mass_inertia (solver.py:173-187)
+        if (tma) {
+            const int sb = gb - cb0;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) rec[BR_Q + k] = stage[ST_Q * cnb + 7 * sb + k];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) rec[BR_QD + k] = stage[ST_QD * cnb + 6 * sb + k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) rec[BR_COM + k] = stage[ST_COM * cnb + 3 * sb + k];
+            rec[BR_INVM] = kin ? 0.0f : stage[ST_INVM * cnb + sb];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                rec[BR_INVI + k] = kin ? 0.0f : stage[ST_INVI * cnb + 9 * sb + k];
+                rec[BR_I + k] = stage[ST_I * cnb + 9 * sb + k];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 7; ++k) rec[BR_Q + k] = sin.body_q[7 * gb + k];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) rec[BR_QD + k] = sin.body_qd[6 * gb + k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) rec[BR_COM + k] = d.body_com[3 * gb + k];
+            rec[BR_INVM] = kin ? 0.0f : d.body_inv_mass[gb];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                rec[BR_INVI + k] = kin ? 0.0f : d.body_inv_inertia[9 * gb + k];
+                rec[BR_I + k] = d.body_inertia[9 * gb + k];
+            }
+        }
+    }
+    if (want_init)
+        for (int b = l; b < nb; b += L)
+#pragma unroll
+            for (int k = 0; k < 13; ++k) init_qd[b * 13 + k] = bodies[b * BR_SIZE + BR_Q + k];  // q (7) then qd (6) are adjacent
+    if (tma) __syncthreads();  // every warp has unpacked its bodies: the staging area becomes the delta records
+    else __syncwarp();
+    // ---- contact -> body incidence as two bit masks per body lane (contact c touches this body on side A / side B) --------------
+    // Contact order is the summation order; a mask walk visits exactly the incident records in that order instead of rescanning
+    // all nc contacts per body per iteration.  One body per lane and <= 64 contacts; larger environments use the scan.
+    const bool use_masks = nb <= L && nc <= 64;
+    unsigned long long mask_a = 0ull, mask_b = 0ull;
+    if (use_masks && l < nb)
+        for (int c = 0; c < nc; ++c) {
+            const int pr = cpair[c];
+            const int ba = int(short(pr & 0xffff)), bb = pr >> 16;
+            if (ba == bb) continue;  // the contact pass writes an inactive record
+            if (ba == l) mask_a |= 1ull << c;
+            if (bb == l) mask_b |= 1ull << c;
         }
     // ---- apply_joint_forces: per-joint wrenches, then ordered per-body accumulation into a body_f copy ----
     for (int j = l; j < nj; j += L) {
@@ -554,9 +690,9 @@ __global__ void __launch_bounds__(32, NB2_XPBD_MINBLOCKS) xpbd_step_kernel(DevMo
         const Q4 r0(rec[BR_Q + 3], rec[BR_Q + 4], rec[BR_Q + 5], rec[BR_Q + 6]);
         const V3 v0 = ld3(rec + BR_QD), w0 = ld3(rec + BR_QD + 3);
         const V3 com = ld3(rec + BR_COM);
-        const float inv_mass = d.body_inv_mass[gb];
+        const float inv_mass = rec[BR_INVM];  // not kinematic here: the effective value is the model's
         const M33 inertia = ldm(rec + BR_I);
-        const M33 inv_inertia = ldm(d.body_inv_inertia + 9 * gb);
+        const M33 inv_inertia = ldm(rec + BR_INVI);
         int wi = d.body_world[gb];
         if (wi < 0) wi += d.gravity_count;
         const V3 g = ld3(d.gravity + 3 * wi);
@@ -578,6 +714,10 @@ __global__ void __launch_bounds__(32, NB2_XPBD_MINBLOCKS) xpbd_step_kernel(DevMo
     const size_t T = size_t(M.slot_total);
     const float* cb = M.cb;
     for (int it = 0; it < P.iterations; ++it) {
+        // CTA barriers are not needed for correctness (a warp owns its environments); they keep the CTA's warps on the same
+        // stretch of code so that the instruction stream is fetched once per CTA (see the kernel comment)
+        const bool sync_it = (flags & XF_PHASE_SYNC) && WARPS > 1, sync_fine = (flags & XF_PHASE_SYNC_FINE) && WARPS > 1;
+        if (sync_it) __syncthreads();
         if (use_contacts) {
             // ---- [iteration] solve_body_contact_positions (kernels.py:2164-2399)
             for (int c = l; c < nc; c += L) {
@@ -587,29 +727,37 @@ __global__ void __launch_bounds__(32, NB2_XPBD_MINBLOCKS) xpbd_step_kernel(DevMo
                 Deltas dl;
                 float active = 0.0f;
                 if (ba != bb) {
+                    // A side never consumed by a body (static world) and not reported: its arithmetic is skipped.  Identity
+                    // transform and zero centre of mass reduce xpoint(X, p) to (+0) + p and r to the contact point itself.
+                    const bool need_a = ba >= 0 || want_cimp, need_b = bb >= 0 || want_cimp;
                     BodyView A = ba >= 0 ? load_body(bodies + ba * BR_SIZE) : static_body();
                     BodyView B = bb >= 0 ? load_body(bodies + bb * BR_SIZE) : static_body();
                     const V3 p0(cb[CF_P0X * T + s], cb[CF_P0Y * T + s], cb[CF_P0Z * T + s]);
                     const V3 p1(cb[CF_P1X * T + s], cb[CF_P1Y * T + s], cb[CF_P1Z * T + s]);
                     const V3 n(cb[CF_NX * T + s], cb[CF_NY * T + s], cb[CF_NZ * T + s]);
-                    V3 bx_a = xpoint(A.X, p0), bx_b = xpoint(B.X, p1);
+                    V3 bx_a = ba >= 0 ? xpoint(A.X, p0) : V3() + p0, bx_b = bb >= 0 ? xpoint(B.X, p1) : V3() + p1;
                     const float dpen = dot(n, bx_b - bx_a) - (cb[CF_MARGIN0 * T + s] + cb[CF_MARGIN1 * T + s]);
                     if (dpen < 0.0f) {
                         active = 1.0f;
                         const float mu = cb[CF_MU * T + s], mu_t = cb[CF_MU_TORSIONAL * T + s], mu_r = cb[CF_MU_ROLLING * T + s];
-                        V3 r_a = bx_a - xpoint(A.X, A.com), r_b = bx_b - xpoint(B.X, B.com);
-                        V3 ang_a = -cross(r_a, n), ang_b = cross(r_b, n);
+                        const V3 wcom_a = ba >= 0 ? xpoint(A.X, A.com) : V3(), wcom_b = bb >= 0 ? xpoint(B.X, B.com) : V3();
+                        V3 r_a = bx_a - wcom_a, r_b = bx_b - wcom_b;
+                        V3 ang_a, ang_b;
+                        if (need_a) ang_a = -cross(r_a, n);
+                        if (need_b) ang_b = cross(r_b, n);
                         const float lambda_n = contact_delta(dpen, A, B, -n, n, ang_a, ang_b, P.rigid_contact_relaxation, dt);
-                        V3 lin_da = -n * lambda_n, lin_db = n * lambda_n, ang_da = ang_a * lambda_n, ang_db = ang_b * lambda_n;
+                        V3 lin_da, lin_db, ang_da, ang_db;
+                        if (need_a) { lin_da = -n * lambda_n; ang_da = ang_a * lambda_n; }
+                        if (need_b) { lin_db = n * lambda_n; ang_db = ang_b * lambda_n; }
                         if (mu > 0.0f) {
                             const V3 o0(cb[CF_O0X * T + s], cb[CF_O0Y * T + s], cb[CF_O0Z * T + s]);
                             const V3 o1(cb[CF_O1X * T + s], cb[CF_O1Y * T + s], cb[CF_O1Z * T + s]);
-                            bx_a = xpoint(A.X, p0 + o0);
-                            bx_b = xpoint(B.X, p1 + o1);
+                            bx_a = ba >= 0 ? xpoint(A.X, p0 + o0) : V3() + (p0 + o0);
+                            bx_b = bb >= 0 ? xpoint(B.X, p1 + o1) : V3() + (p1 + o1);
                             V3 delta = bx_b - bx_a;
                             V3 fd = delta - dot(n, delta) * n;
-                            r_a = bx_a - xpoint(A.X, A.com);
-                            r_b = bx_b - xpoint(B.X, B.com);
+                            r_a = bx_a - wcom_a;
+                            r_b = bx_b - wcom_b;
                             V3 rel_v_kin;
                             if (ba >= 0 && (d.body_flags[b0 + ba] & BODY_KINEMATIC) != 0) {
                                 V3 v_a = cross(A.w, r_a) + A.v;
@@ -621,16 +769,14 @@ __global__ void __launch_bounds__(32, NB2_XPBD_MINBLOCKS) xpbd_step_kernel(DevMo
                             }
                             fd += rel_v_kin * dt;
                             V3 perp = unit(fd);
-                            ang_a = -cross(r_a, perp);
-                            ang_b = cross(r_b, perp);
+                            if (need_a) ang_a = -cross(r_a, perp);
+                            if (need_b) ang_b = cross(r_b, perp);
                             float err = len(fd);
                             if (err > 0.0f) {
                                 float lambda_fr = contact_delta(err, A, B, -perp, perp, ang_a, ang_b, P.rigid_contact_relaxation, dt);
                                 lambda_fr = fmax_w(lambda_fr, -lambda_n * mu);
-                                lin_da -= perp * lambda_fr;
-                                lin_db += perp * lambda_fr;
-                                ang_da += ang_a * lambda_fr;
-                                ang_db += ang_b * lambda_fr;
+                                if (need_a) { lin_da -= perp * lambda_fr; ang_da += ang_a * lambda_fr; }
+                                if (need_b) { lin_db += perp * lambda_fr; ang_db += ang_b * lambda_fr; }
                             }
                         }
                         V3 dom = B.w - A.w;
@@ -639,8 +785,8 @@ __global__ void __launch_bounds__(32, NB2_XPBD_MINBLOCKS) xpbd_step_kernel(DevMo
                             if (fabsf(err) > 0.0f) {
                                 float lt = contact_delta(err, A, B, V3(), V3(), -n, n, P.rigid_contact_relaxation, dt);
                                 lt = clamp_w(lt, -lambda_n * mu_t, lambda_n * mu_t);
-                                ang_da -= n * lt;
-                                ang_db += n * lt;
+                                if (need_a) ang_da -= n * lt;
+                                if (need_b) ang_db += n * lt;
                             }
                         }
                         if (mu_r > 0.0f) {
@@ -650,8 +796,8 @@ __global__ void __launch_bounds__(32, NB2_XPBD_MINBLOCKS) xpbd_step_kernel(DevMo
                                 V3 rn = unit(dom);
                                 float lr = contact_delta(err, A, B, V3(), V3(), -rn, rn, P.rigid_contact_relaxation, dt);
                                 lr = fmax_w(lr, -lambda_n * mu_r);
-                                ang_da -= rn * lr;
-                                ang_db += rn * lr;
+                                if (need_a) ang_da -= rn * lr;
+                                if (need_b) ang_db += rn * lr;
                             }
                         }
                         dl.lin_p = lin_da;
@@ -663,18 +809,31 @@ __global__ void __launch_bounds__(32, NB2_XPBD_MINBLOCKS) xpbd_step_kernel(DevMo
                 store_deltas(drec + c * DR_SIZE, dl, active);
             }
             __syncwarp();
+            if (sync_fine) __syncthreads();
             // ---- [iteration] ordered per-body sum (contact order; side A before side B) + weighted apply
             for (int b = l; b < nb; b += L) {
                 V3 dlin, dang;
                 float cnt = 0.0f;
-                for (int c = 0; c < nc; ++c) {
-                    const int pr = cpair[c];
-                    const int ba = int(short(pr & 0xffff)), bb = pr >> 16;
-                    if (ba != b && bb != b) continue;
-                    const float* r = drec + c * DR_SIZE;
-                    if (r[12] == 0.0f) continue;
-                    if (ba == b) { dlin += ld3(r + 0); dang += ld3(r + 3); cnt += 1.0f; }
-                    if (bb == b) { dlin += ld3(r + 6); dang += ld3(r + 9); cnt += 1.0f; }
+                if (use_masks) {
+                    unsigned long long m = mask_a | mask_b;
+                    while (m) {
+                        const int c = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        const float* r = drec + c * DR_SIZE;
+                        if (r[12] == 0.0f) continue;
+                        if ((mask_a >> c) & 1ull) { dlin += ld3(r + 0); dang += ld3(r + 3); cnt += 1.0f; }
+                        if ((mask_b >> c) & 1ull) { dlin += ld3(r + 6); dang += ld3(r + 9); cnt += 1.0f; }
+                    }
+                } else {
+                    for (int c = 0; c < nc; ++c) {
+                        const int pr = cpair[c];
+                        const int ba = int(short(pr & 0xffff)), bb = pr >> 16;
+                        if (ba != b && bb != b) continue;
+                        const float* r = drec + c * DR_SIZE;
+                        if (r[12] == 0.0f) continue;
+                        if (ba == b) { dlin += ld3(r + 0); dang += ld3(r + 3); cnt += 1.0f; }
+                        if (bb == b) { dlin += ld3(r + 6); dang += ld3(r + 9); cnt += 1.0f; }
+                    }
                 }
                 apply_delta(bodies + b * BR_SIZE, dlin, dang, cnt, P.rigid_contact_con_weighting != 0, dt);
                 if (want_cimp) bcnt[b] = cnt;
@@ -704,6 +863,7 @@ __global__ void __launch_bounds__(32, NB2_XPBD_MINBLOCKS) xpbd_step_kernel(DevMo
             }
         }
         if (d.joint_count > 0) {
+            if (sync_fine) __syncthreads();
             // ---- [iteration] solve_body_joints (kernels.py:1513-2044) + ordered per-body apply
             for (int j = l; j < nj; j += L) {
                 Deltas dl;
@@ -717,6 +877,7 @@ __global__ void __launch_bounds__(32, NB2_XPBD_MINBLOCKS) xpbd_step_kernel(DevMo
                 }
             }
             __syncwarp();
+            if (sync_fine) __syncthreads();
             for (int b = l; b < nb; b += L) {
                 const int gb = b0 + b;
                 V3 dlin, dang;
@@ -858,6 +1019,26 @@ __global__ void __launch_bounds__(32, NB2_XPBD_MINBLOCKS) xpbd_step_kernel(DevMo
         }
     }
     // ---- write back -------------------------------------------------------------------------------------
+    if (tma) {
+        // pack the CTA's body_q / body_qd runs in the reference's AoS layout, then two bulk stores shared -> global
+        __syncthreads();  // all warps are done with their delta records: the region is the staging area again
+        for (int b = l; b < nb; b += L) {
+            const int sb = b0 + b - cb0;
+            const float* rec = bodies + b * BR_SIZE;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) stage[ST_Q * cnb + 7 * sb + k] = rec[BR_Q + k];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) stage[ST_QD * cnb + 6 * sb + k] = rec[BR_QD + k];
+        }
+        fence_async_smem();  // generic-proxy writes -> visible to the async proxy (TMA)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bulk_s2g(sout.body_q + 7 * size_t(cb0), stage + ST_Q * cnb, unsigned(cnb) * 28u);
+            bulk_s2g(sout.body_qd + 6 * size_t(cb0), stage + ST_QD * cnb, unsigned(cnb) * 24u);
+            bulk_commit_and_drain();  // shared memory must stay alive until the TMA unit has read it
+        }
+        return;
+    }
     for (int b = l; b < nb; b += L) {
         const int gb = b0 + b;
         const float* rec = bodies + b * BR_SIZE;
@@ -917,40 +1098,77 @@ __global__ void __launch_bounds__(256) integrate_bodies_kernel(nb2_model_desc d,
     st3(sout.body_qd + 6 * b + 3, w1);
 }
 
-template <int L, bool EX>
-static nb2_status launch_xpbd_L(nb2_model* m, const nb2_xpbd_params& p, const nb2_state_view& in, const nb2_state_view& out,
+static int env_int(const char* name, int fallback) {
+    const char* v = std::getenv(name);
+    return v ? std::atoi(v) : fallback;
+}
+
+template <int L, bool EX, int WARPS>
+static nb2_status launch_xpbd_W(nb2_model* m, const nb2_xpbd_params& p, const nb2_state_view& in, const nb2_state_view& out,
                                 const nb2_control_view& ctl, int use_contacts, float dt, cudaStream_t s) {
     const DevModel& M = m->dev;
-    const int G = 32 / L;
-    const int blocks = (M.env_count + G - 1) / G;
-    const int rec_cap = std::max(M.max_env_contact_slots, M.max_env_joints);
-    const size_t per_env = size_t(M.max_env_bodies) * BR_SIZE + size_t(rec_cap) * DR_SIZE + size_t(M.max_env_contact_slots) +
-                           (EX ? size_t(M.max_env_bodies) * 14 : 0);
-    size_t smem = per_env * G * sizeof(float);
-    if (smem > 220 * 1024 || M.max_env_bodies > 32000) {
+    constexpr int NE = (32 / L) * WARPS;
+    const int blocks = (M.env_count + NE - 1) / NE;
+    // contact records per env: the tightest bound the host knows (sum of the pairs' own maxima after nb2_collide; the
+    // whole slot range after nb2_contacts_import, whose buffers may hold anything)
+    const int contact_cap = m->contacts_imported ? M.max_env_contact_slots : std::min(M.max_env_contact_slots, m->max_env_contacts);
+    if (M.max_env_bodies > 32000) {
+        set_error("xpbd_step: environment too large for the fused shared-memory kernel (bodies per env)");
+        return NB2_ERR_CAPACITY;
+    }
+    // Budget: the CTAs of one SM share 227 KB (+1 KB reserved each); the batch wants >= ceil(envs / (G * 148)) resident warps per SM to
+    // stay a single wave.  The per-joint cache rides along when it does not cost that residency.
+    static const bool cache_enabled = std::getenv("NB2_XPBD_NO_JOINT_CACHE") == nullptr;  // A/B switch (profiles/r1f_xpbd_ab.txt)
+    static const int tma_enabled = env_int("NB2_XPBD_TMA", 1), phase_sync = env_int("NB2_XPBD_PHASE_SYNC", 0);
+    int flags = (tma_enabled ? XF_TMA : 0) | (phase_sync >= 1 ? XF_PHASE_SYNC : 0) | (phase_sync >= 2 ? XF_PHASE_SYNC_FINE : 0);
+    XpbdPlan plan = xpbd_plan(NE, M.max_env_bodies, M.max_env_joints, contact_cap, EX, false);
+    if (cache_enabled && M.d.joint_count > 0) {
+        const XpbdPlan with_cache = xpbd_plan(NE, M.max_env_bodies, M.max_env_joints, contact_cap, EX, true);
+        const int want_ctas = (14 + WARPS - 1) / WARPS;  // 14 warps per SM keep 4096 two-env warps in one wave
+        if ((size_t(with_cache.total) * sizeof(float) + 1024) * want_ctas <= 227 * 1024 || size_t(plan.total) * sizeof(float) * want_ctas > 227 * 1024) {
+            if (size_t(with_cache.total) * sizeof(float) <= 220 * 1024) {
+                plan = with_cache;
+                flags |= XF_JOINT_CACHE;
+            }
+        }
+    }
+    const size_t smem = size_t(plan.total) * sizeof(float);
+    if (smem > 220 * 1024) {
         set_error("xpbd_step: environment too large for the fused shared-memory kernel (bodies/contacts per env)");
         return NB2_ERR_CAPACITY;
     }
-    // per-joint invariants (32 floats / joint) ride along when the block stays within a 14-CTA/SM share of shared memory
-    // (227 KB / 14 minus the 1 KB per-CTA reservation): residency - one wave for 4096 quadruped envs - is worth more
-    int joint_cache_floats = 0;
-    {
-        const size_t cache = size_t(M.max_env_joints) * JC_SIZE;
-        static const bool enabled = std::getenv("NB2_XPBD_NO_JOINT_CACHE") == nullptr;  // A/B switch (profiles/r1f_xpbd_ab.txt)
-        if (enabled && M.d.joint_count > 0 && smem + cache * G * sizeof(float) <= 15 * 1024) {
-            joint_cache_floats = int(cache);
-            smem += cache * G * sizeof(float);
-        }
-    }
     if (smem > 48 * 1024)
-        NB2_CUDA_CHECK(cudaFuncSetAttribute(xpbd_step_kernel<L, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    // one-warp CTAs: ask for the largest shared-memory carve-out so ~16 CTAs (one wave of 4096 envs on 148 SMs) fit per SM
+        NB2_CUDA_CHECK(cudaFuncSetAttribute(xpbd_step_kernel<L, EX, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    // ask for the largest shared-memory carve-out so that ~14-16 warps' worth of CTAs fit per SM
     static const int carveout = std::getenv("NB2_XPBD_CARVEOUT") ? std::atoi(std::getenv("NB2_XPBD_CARVEOUT")) : int(cudaSharedmemCarveoutMaxShared);
-    NB2_CUDA_CHECK(cudaFuncSetAttribute(xpbd_step_kernel<L, EX>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
-    xpbd_step_kernel<L, EX><<<blocks, 32, smem, s>>>(M, p, in, out, ctl, use_contacts, dt, joint_cache_floats);
+    NB2_CUDA_CHECK(cudaFuncSetAttribute(xpbd_step_kernel<L, EX, WARPS>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
+    xpbd_step_kernel<L, EX, WARPS><<<blocks, 32 * WARPS, smem, s>>>(M, p, in, out, ctl, use_contacts, dt, flags, contact_cap);
     count_launch();
     NB2_CUDA_CHECK(cudaGetLastError());
     return NB2_OK;
+}
+
+// warps per CTA: the A/B variants are compiled only for the plain step of the 16-lane layout (the benchmark configuration)
+#ifndef NB2_XPBD_WARPS_DEFAULT
+#define NB2_XPBD_WARPS_DEFAULT 2
+#endif
+template <int L, bool EX>
+static nb2_status launch_xpbd_L(nb2_model* m, const nb2_xpbd_params& p, const nb2_state_view& in, const nb2_state_view& out,
+                                const nb2_control_view& ctl, int use_contacts, float dt, cudaStream_t s) {
+    static const int warps = env_int("NB2_XPBD_WARPS", NB2_XPBD_WARPS_DEFAULT);
+#ifdef NB2_XPBD_AB_VARIANTS
+    if constexpr (L == 16 && !EX) {
+        switch (warps) {
+            case 1: return launch_xpbd_W<L, EX, 1>(m, p, in, out, ctl, use_contacts, dt, s);
+            case 4: return launch_xpbd_W<L, EX, 4>(m, p, in, out, ctl, use_contacts, dt, s);
+            case 7: return launch_xpbd_W<L, EX, 7>(m, p, in, out, ctl, use_contacts, dt, s);
+            case 14: return launch_xpbd_W<L, EX, 14>(m, p, in, out, ctl, use_contacts, dt, s);
+            default: break;
+        }
+    }
+#endif
+    (void)warps;
+    return launch_xpbd_W<L, EX, NB2_XPBD_WARPS_DEFAULT>(m, p, in, out, ctl, use_contacts, dt, s);
 }
 
 nb2_status launch_xpbd_step(nb2_model* m, const nb2_xpbd_params& p, const nb2_state_view& in, const nb2_state_view& out,

@@ -209,6 +209,59 @@ def convex_pile_model(world_count: int = 1, device="cpu", seed: int | None = 5):
     return _finish(scene, device)
 
 
+def _hull_vertices(kind: str, rng=None) -> np.ndarray:
+    """Vertex sets for convex-hull shapes: an icosahedron, a box written as 8 hull vertices, a squashed random polytope and an
+    off-centre wedge (hull whose AABB centre is not the shape origin - exercises the Minkowski-centre seed)."""
+    if kind == "icosahedron":
+        g = (1.0 + math.sqrt(5.0)) / 2.0
+        v = [(-1, g, 0), (1, g, 0), (-1, -g, 0), (1, -g, 0), (0, -1, g), (0, 1, g), (0, -1, -g), (0, 1, -g), (g, 0, -1), (g, 0, 1),
+             (-g, 0, -1), (-g, 0, 1)]
+        return np.asarray(v, dtype=np.float32) / np.float32(math.sqrt(1.0 + g * g))
+    if kind == "box":
+        return np.asarray([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], dtype=np.float32)
+    if kind == "wedge":
+        return np.asarray([(0, -1, 0), (2, -1, 0), (0, 1, 0), (2, 1, 0), (0, -1, 1), (0, 1, 1)], dtype=np.float32) * np.float32(0.5)
+    r = rng if rng is not None else np.random.default_rng(11)
+    p = r.normal(size=(24, 3))
+    p /= np.linalg.norm(p, axis=1, keepdims=True)
+    return (p * np.array([1.0, 0.8, 0.5])).astype(np.float32)
+
+
+def hull_pile_model(world_count: int = 1, device="cpu", seed: int | None = 7):
+    """CONVEX_MESH shapes (reference ``ModelBuilder.add_shape_convex_hull``; Anymal-class robots ship convex collision hulls,
+    ``example_robot_anymal_c_walk.py:91-151``) against everything they can meet: hull-plane (box proxy), hull-box, hull-hull,
+    sphere-hull, capsule-hull, cylinder-hull - all through MPR / GJK + manifold with the vertex-scan support map."""
+    from .geometry.mesh import Mesh
+
+    rng = np.random.default_rng(seed) if seed is not None else None
+    meshes = {k: Mesh(_hull_vertices(k, np.random.default_rng(11))) for k in ("icosahedron", "box", "wedge", "polytope")}
+    scene = ModelBuilder()
+    for _ in range(world_count):
+        scene.begin_world()
+        jit = (lambda s=0.01: rng.uniform(-s, s, size=3)) if rng is not None else (lambda s=0.0: np.zeros(3))
+        yaw = (lambda: float(rng.uniform(-0.4, 0.4))) if rng is not None else (lambda: 0.0)
+        zq = lambda a: X.quat_from_axis_angle((0.0, 0.0, 1.0), a)
+        base = scene.add_body(xform=X.transform(np.array([0.0, 0.0, 0.2]) + jit(), zq(yaw())))
+        scene.add_shape_convex_hull(base, mesh=meshes["box"], scale=(1.6, 1.6, 0.2))  # slab written as a hull: hull-plane
+        b = scene.add_body(xform=X.transform(np.array([-0.9, -0.9, 0.72]) + jit(), zq(yaw())))
+        scene.add_shape_convex_hull(b, mesh=meshes["icosahedron"], scale=(0.35, 0.35, 0.35))  # hull-hull
+        b = scene.add_body(xform=X.transform(np.array([0.9, -0.9, 0.66]) + jit(), zq(yaw())))
+        scene.add_shape_box(b, hx=0.25, hy=0.25, hz=0.25)  # box-hull
+        b = scene.add_body(xform=X.transform(np.array([0.9, 0.9, 0.61]) + jit()))
+        scene.add_shape_sphere(b, radius=0.2)  # sphere-hull
+        b = scene.add_body(xform=X.transform(np.array([-0.9, 0.9, 0.61]) + jit(), X.quat_from_axis_angle((0.0, 1.0, 0.0), 0.5 * math.pi)))
+        scene.add_shape_capsule(b, radius=0.2, half_height=0.3)  # capsule-hull
+        b = scene.add_body(xform=X.transform(np.array([0.0, 0.0, 0.71]) + jit(), zq(yaw())))
+        scene.add_shape_cylinder(b, radius=0.25, half_height=0.3)  # cylinder-hull
+        b = scene.add_body(xform=X.transform(np.array([0.0, -0.9, 0.67]) + jit(), zq(yaw())))
+        scene.add_shape_convex_hull(b, mesh=meshes["polytope"], scale=(0.4, 0.4, 0.5))
+        b = scene.add_body(xform=X.transform(np.array([2.4, 0.0, 0.05]) + jit(), zq(yaw())))
+        scene.add_shape_convex_hull(b, mesh=meshes["wedge"], scale=(0.8, 0.8, 0.8))  # off-centre hull resting on the plane
+        scene.end_world()
+    scene.add_ground_plane()
+    return _finish(scene, device)
+
+
 def mixed_worlds_model(repeats: int = 2, device="cpu", seed: int | None = 9):
     """Heterogeneous worlds in one model - a quadruped, a 3-box stack, an empty world, a lone pendulum link, repeated -
     so the per-env sizes differ (partial lane groups, envs without joints / shapes / contacts)."""

@@ -140,7 +140,8 @@ class JointDofConfig:
 _PER_BODY = list(_BODY_FIELDS)
 _PER_JOINT = [n for n in _JOINT_FIELDS if n not in ("joint_ancestor",)]
 _PER_DOF = list(_DOF_FIELDS)
-_PER_SHAPE = [n for n in _SHAPE_FIELDS]
+_FINALIZE_SHAPE = ("shape_collision_aabb_lower", "shape_collision_aabb_upper", "shape_hull_start", "shape_hull_count")
+_PER_SHAPE = [n for n in _SHAPE_FIELDS if n not in _FINALIZE_SHAPE]
 
 
 class ModelBuilder:
@@ -161,6 +162,7 @@ class ModelBuilder:
         self.world_gravity: list[np.ndarray] = []
         for n in _PER_BODY + _PER_JOINT + _PER_DOF + _PER_SHAPE:
             setattr(self, n, [])
+        self.shape_source: list = []  # per shape: Mesh for CONVEX_MESH shapes, else None (reference ModelBuilder.shape_source)
         self.joint_q: list[float] = []
         self.joint_target_q: list[float] = []
         self.joint_q_start: list[int] = []
@@ -276,6 +278,7 @@ class ModelBuilder:
         for n in _PER_SHAPE:
             getattr(self, n).extend(getattr(builder, n))
         self.shape_label.extend(builder.shape_label)
+        self.shape_source.extend(builder.shape_source)
         for s in range(builder.shape_count):
             ss = s0 + s
             self.shape_world[ss] = w
@@ -531,12 +534,21 @@ class ModelBuilder:
         self.body_inv_mass[i] = 1.0 / new_mass if new_mass > 0.0 else 0.0
         self.body_inv_inertia[i] = np.linalg.inv(new_inertia) if new_inertia.any() else new_inertia
 
-    def add_shape(self, *, body, type, xform=None, cfg=None, scale=None, is_static=False, label=None) -> int:
+    def add_shape(self, *, body, type, xform=None, cfg=None, scale=None, is_static=False, label=None, src=None) -> int:
         """Reference ``sim/builder.py:6498-6715``."""
         cfg = cfg or self.default_shape_cfg
         tf = X.transform_identity() if xform is None else np.asarray(xform, dtype=np.float64)
-        scale = (1.0, 1.0, 1.0) if scale is None else tuple(abs(float(s)) for s in scale)
         type = GeoType(type)
+        if type == GeoType.CONVEX_MESH:
+            if src is None:
+                raise ValueError("CONVEX_MESH shapes need a Mesh (src=...)")
+            # mesh-backed shapes keep the sign of the scale (sim/builder.py:6524); mirrored hulls are not needed here
+            scale = (1.0, 1.0, 1.0) if scale is None else tuple(float(s) for s in scale)
+            if any(s <= 0.0 for s in scale):
+                raise NotImplementedError("convex hulls with zero / negative (mirroring) scale")
+        else:
+            scale = (1.0, 1.0, 1.0) if scale is None else tuple(abs(float(s)) for s in scale)
+        self.shape_source.append(src)
         shape = self.shape_count
         self.shape_body.append(body)
         if cfg.has_shape_collision:
@@ -560,7 +572,7 @@ class ModelBuilder:
         self.shape_material_mu_rolling.append(cfg.mu_rolling)
         self.shape_gap.append(cfg.gap if cfg.gap is not None else self.rigid_gap)
         self.shape_collision_group.append(cfg.collision_group)
-        self.shape_collision_radius.append(compute_shape_radius(type, scale))
+        self.shape_collision_radius.append(compute_shape_radius(type, scale, src))
         self.shape_world.append(self.current_world)
         if cfg.has_shape_collision and cfg.collision_filter_parent:
             for parent_body, jidx in self.joint_parents.get(body, ()):
@@ -576,7 +588,13 @@ class ModelBuilder:
                     if self.shape_flags[cs] & ShapeFlags.COLLIDE_SHAPES:
                         self.add_shape_collision_filter_pair(shape, cs)
         if not is_static and cfg.density > 0.0 and body >= 0 and not self.body_lock_inertia[body]:
-            m, c, inertia = compute_inertia_shape(type, scale, cfg.density, cfg.is_solid, cfg.margin)
+            if type == GeoType.CONVEX_MESH:
+                from ..geometry.mesh import compute_inertia_mesh
+
+                # mass properties of the SCALED hull (reference compute_inertia_shape, geometry/inertia.py:726-742)
+                m, c, inertia, _ = compute_inertia_mesh(cfg.density, src.vertices.astype(np.float64) * np.asarray(scale), src._triangles())
+            else:
+                m, c, inertia = compute_inertia_shape(type, scale, cfg.density, cfg.is_solid, cfg.margin)
             com_body = X.transform_point(tf, c)
             self._update_body_mass(body, m, inertia, com_body, tf[3:])
         return shape
@@ -617,6 +635,10 @@ class ModelBuilder:
     def add_shape_cylinder(self, body, *, xform=None, radius=1.0, half_height=0.5, cfg=None, label=None) -> int:
         return self.add_shape(body=body, type=GeoType.CYLINDER, xform=xform, cfg=cfg,
                               scale=(radius, half_height, 0.0), label=label)
+
+    def add_shape_convex_hull(self, body, *, xform=None, mesh=None, scale=None, cfg=None, label=None) -> int:
+        """Reference ``sim/builder.py:7201-7241``: the vertices of ``mesh`` are taken as the hull (GeoType.CONVEX_MESH)."""
+        return self.add_shape(body=body, type=GeoType.CONVEX_MESH, xform=xform, cfg=cfg, scale=scale, src=mesh, label=label)
 
     def add_shape_cone(self, body, *, xform=None, radius=1.0, half_height=0.5, cfg=None, label=None) -> int:
         """Cone along +z, apex up (reference ``sim/builder.py`` ``add_shape_cone``; support map ``support_function.py:316-336``)."""
@@ -823,6 +845,55 @@ class ModelBuilder:
                         pairs.append((a, b))
         return np.asarray(pairs, dtype=np.int32).reshape(-1, 2)
 
+    def _finalize_shape_sources(self, m, arr):
+        """Local AABBs (reference ``sim/builder.py:11560-11687``) and the convex-hull vertex pool.  Every distinct Mesh is stored
+        once, exact duplicate vertices removed keeping first-occurrence order so that support-map ties resolve as upstream
+        (``_deduplicate_convex_collision_mesh``, ``sim/builder.py:104-137``)."""
+        pool, ranges = [], {}
+        lo_all, hi_all, starts, counts = [], [], [], []
+        total = 0
+        for s in range(self.shape_count):
+            t, scale, src = self.shape_type[s], np.asarray(self.shape_scale[s], dtype=np.float64), self.shape_source[s]
+            start = count = 0
+            if t == GeoType.CONVEX_MESH:
+                if id(src) not in ranges:
+                    v = src.vertices
+                    _, first = np.unique(v, axis=0, return_index=True)
+                    v = v[np.sort(first)]
+                    ranges[id(src)] = (total, v.shape[0], v)
+                    pool.append(v)
+                    total += v.shape[0]
+                start, count, v = ranges[id(src)]
+                a, b = v.min(axis=0) * scale, v.max(axis=0) * scale
+                lo, hi = np.minimum(a, b), np.maximum(a, b)
+            elif t == GeoType.SPHERE:
+                lo, hi = -scale[[0, 0, 0]], scale[[0, 0, 0]]
+            elif t == GeoType.BOX or t == GeoType.ELLIPSOID:
+                lo, hi = -scale, scale
+            elif t == GeoType.CAPSULE:
+                hi = np.array([scale[0], scale[0], scale[1] + scale[0]])
+                lo = -hi
+            elif t == GeoType.CYLINDER:
+                r = scale[0]
+                if scale[2] > 0.0:
+                    r += scale[1] * scale[1] / (scale[2] + np.sqrt(scale[2] * scale[2] - scale[1] * scale[1]))
+                hi = np.array([r, r, scale[1]])
+                lo = -hi
+            elif t == GeoType.CONE:
+                hi = np.array([scale[0], scale[0], scale[1]])
+                lo = -hi
+            else:
+                lo, hi = -np.ones(3), np.ones(3)
+            lo_all.append(lo)
+            hi_all.append(hi)
+            starts.append(start)
+            counts.append(count)
+        m.shape_collision_aabb_lower = arr(lo_all, (3,), F32)
+        m.shape_collision_aabb_upper = arr(hi_all, (3,), F32)
+        m.shape_hull_start, m.shape_hull_count = arr(starts, (), I32), arr(counts, (), I32)
+        m.hull_points = arr(np.concatenate(pool) if pool else np.zeros((0, 3), np.float32), (3,), F32)
+        m.shape_source = list(self.shape_source)
+
     def finalize(self, device="cpu") -> Model:
         """Build the immutable :class:`Model` (reference ``sim/builder.py:11232-12650``)."""
         m = Model(device)
@@ -850,6 +921,7 @@ class ModelBuilder:
             for n in names:
                 trailing, dtype = group[n]
                 setattr(m, n, arr(getattr(self, n), trailing, dtype))
+        self._finalize_shape_sources(m, arr)
         m.joint_q = arr(self.joint_q, (), F32)
         if self.use_coord_layout_targets:
             m.joint_target_q = arr(self.joint_target_q, (), F32)

@@ -218,6 +218,12 @@ _SHAPE_FIELDS = {
     "shape_material_restitution": ((), F32),
     "shape_material_mu_torsional": ((), F32),
     "shape_material_mu_rolling": ((), F32),
+    # local AABB with the scale baked in (reference Model.shape_collision_aabb_lower / _upper) and, for CONVEX_MESH shapes, the
+    # range of Model.hull_points (unscaled hull vertices - the reference's wp.Mesh.points behind shape_source_ptr)
+    "shape_collision_aabb_lower": ((3,), F32),
+    "shape_collision_aabb_upper": ((3,), F32),
+    "shape_hull_start": ((), I32),
+    "shape_hull_count": ((), I32),
 }
 
 
@@ -276,6 +282,8 @@ class Model:
         for group in (_BODY_FIELDS, _JOINT_FIELDS, _DOF_FIELDS, _COORD_FIELDS, _SHAPE_FIELDS):
             for name in group:
                 setattr(self, name, None)
+        self.hull_points = None  # [V, 3] unscaled vertices of every distinct convex hull (see shape_hull_start / _count)
+        self.shape_source: list = []  # per shape: the host-side Mesh of a CONVEX_MESH shape, else None
         self.joint_target_q = None  # [coord] when use_coord_layout_targets else [dof]
         self.joint_q_start = None  # [J+1]
         self.joint_qd_start = None  # [J+1]

@@ -86,6 +86,9 @@ def shard_model(model: Model, rank: int, world_size: int) -> Model:
     out.joint_target_q = cut("joint_target_q", c0, c1)
     for n in _SHAPE_FIELDS:
         setattr(out, n, torch.cat([cut(n, s0, s1), cut(n, g0, g1)]))
+    out.hull_points = None if model.hull_points is None else model.hull_points.clone()  # the convex-hull vertex pool is shared: shape_hull_start keeps indexing it
+    src = getattr(model, "shape_source", None) or [None] * model.shape_count
+    out.shape_source = list(src[s0:s1]) + list(src[g0:g1])
 
     def rebase(t, off):
         return torch.where(t >= 0, t - off, t)
@@ -128,3 +131,110 @@ def shard_model(model: Model, rank: int, world_size: int) -> Model:
     out.shape_contact_pair_count = int(remap.shape[0])
     out.gravity = torch.cat([model.gravity[w0:w1], model.gravity[-1:]]).clone()
     return out
+
+
+class PeerStateGather:
+    """End-of-frame all-gather of per-rank state slices through NVLink peer WRITES on the copy engines (``nb2_peer_gather_*`` in
+    ``csrc/nb2_peer.cu``) instead of NCCL all-gather kernels, which would take SMs from a solver kernel that needs all of them to
+    stay one wave.  One process per GPU of one node; ``torch.distributed`` (any backend) is used once, at
+    construction, to exchange the CUDA IPC handles.
+
+    ``templates`` are this rank's tensors (e.g. ``state.body_q``, ``state.body_qd``); every rank must pass the same shapes.
+    ``push(tensors)`` snapshots them (device-to-device, on the current stream), then - on a side stream - writes the snapshot into
+    every rank's receive slot and publishes the sequence number; ``wait(seq)`` makes the current stream wait until all ranks'
+    slices of that push have arrived; ``gathered(seq)`` returns ``[world_size, *shape]`` views of the receive slot."""
+
+    def __init__(self, templates, group=None):
+        import ctypes as C
+
+        import torch.distributed as dist
+
+        from .. import _lib
+
+        self._C, self._lib = C, _lib.lib()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = templates[0].device
+        self.shapes = [tuple(t.shape) for t in templates]
+        self.dtypes = [t.dtype for t in templates]
+        self.offsets, off = [], 0
+        for t in templates:
+            self.offsets.append(off)
+            off += (t.numel() * t.element_size() + 15) & ~15
+        self.bytes = off
+        h = C.c_void_p()
+        _lib.check(self._lib.nb2_peer_gather_create(self.device.index, self.rank, self.world, self.bytes, C.byref(h)),
+                   "nb2_peer_gather_create")
+        self._h = h
+        nh = int(self._lib.nb2_peer_gather_handle_bytes())
+        mine = C.create_string_buffer(nh)
+        _lib.check(self._lib.nb2_peer_gather_export(h, mine), "nb2_peer_gather_export")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(mine.raw), group=group)
+        _lib.check(self._lib.nb2_peer_gather_connect(h, C.c_char_p(b"".join(handles))), "nb2_peer_gather_connect")
+        dist.barrier(group=group)  # every rank has mapped every buffer before the first push
+        self.stride = int(self._lib.nb2_peer_gather_stride(h))
+        self._snap = torch.empty(self.stride, dtype=torch.uint8, device=self.device)
+        self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._snap_free = None  # event: the previous push has finished reading the snapshot
+        self.sequence = 0
+
+    def _slot_view(self, slot: int):
+        """The receive slot as a flat uint8 tensor (zero-copy view of the library's cudaMalloc block)."""
+        ptr = int(self._lib.nb2_peer_gather_buffer(self._h, slot))
+        n = self.world * self.stride
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
+
+        return torch.as_tensor(_Raw(), device=self.device)
+
+    def push(self, tensors) -> int:
+        cur = torch.cuda.current_stream(self.device)
+        if self._snap_free is not None:
+            cur.wait_event(self._snap_free)
+        for t, off in zip(tensors, self.offsets):
+            n = t.numel() * t.element_size()
+            self._snap[off : off + n].copy_(t.contiguous().view(torch.uint8).view(-1), non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        self.sequence += 1
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(ready)
+            self._lib_check(self._lib.nb2_peer_gather_push(self._h, self._C.c_void_p(self._snap.data_ptr()), self.bytes, self.sequence,
+                                                           self._C.c_void_p(self._copy_stream.cuda_stream)), "nb2_peer_gather_push")
+            self._snap_free = torch.cuda.Event()
+            self._snap_free.record(self._copy_stream)
+        return self.sequence
+
+    def _lib_check(self, st, what):
+        from .. import _lib
+
+        _lib.check(st, what)
+
+    def wait(self, sequence: int | None = None) -> None:
+        seq = self.sequence if sequence is None else int(sequence)
+        if seq <= 0:
+            return
+        cur = torch.cuda.current_stream(self.device)
+        self._lib_check(self._lib.nb2_peer_gather_wait(self._h, seq, self._C.c_void_p(cur.cuda_stream)), "nb2_peer_gather_wait")
+
+    def gathered(self, sequence: int | None = None):
+        seq = self.sequence if sequence is None else int(sequence)
+        raw = self._slot_view(seq & 1).view(self.world, self.stride)
+        out = []
+        for shape, dtype, off in zip(self.shapes, self.dtypes, self.offsets):
+            n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+            out.append(raw[:, off : off + n].view(dtype).view(self.world, *shape))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            torch.cuda.synchronize(self.device)
+            self._lib.nb2_peer_gather_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

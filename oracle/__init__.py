@@ -238,8 +238,18 @@ class FramePool:
         self._h = C.c_void_p(L.orc_pool_new(self.threads))
 
     def run_frames(self, frames: int) -> float:
+        self._substeps_done = getattr(self, "_substeps_done", 0) + int(frames) * int(self._loop.substeps)
         return float(lib().orc_pool_run_frames(self._h, self._shards, C.c_int(len(self._shards)), C.byref(self._loop),
                                                C.c_int(int(frames))))
+
+    def current_states(self):
+        """The State holding the latest result of every shard (the library swaps its two views after every substep)."""
+        odd = getattr(self, "_substeps_done", 0) % 2 == 1
+        return [k[4] if odd else k[3] for k in self._keep]
+
+    def contacts(self):
+        """The Contacts buffer of every shard (what the last substep's collide produced)."""
+        return [k[6] for k in self._keep]
 
     def close(self):
         if self._h is not None:
@@ -295,6 +305,31 @@ def convex_pair(type_a, scale_a, xform_a, type_b, scale_b, xform_b, gap_sum=0.2,
 
 def _f32(a):
     return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+def convex_pair_hull(type_a, scale_a, xform_a, hull_a, type_b, scale_b, xform_b, hull_b, gap_sum=0.2, impl="oracle"):
+    """``convex_pair`` with CONVEX_MESH operands: ``hull_*`` = unscaled vertices ``[n, 3]`` (None for primitives)."""
+    sa, sb, xa, xb = _f32(scale_a), _f32(scale_b), _f32(xform_a), _f32(xform_b)
+    ha = None if hull_a is None else _f32(hull_a).reshape(-1, 3)
+    hb = None if hull_b is None else _f32(hull_b).reshape(-1, 3)
+    dist, pos, n = np.zeros(5, np.float32), np.zeros((5, 3), np.float32), np.zeros((5, 3), np.float32)
+    L = lib()
+    L.orc_convex_pair_hull.restype = C.c_int
+    cnt = L.orc_convex_pair_hull(
+        int(type_a), C.c_void_p(sa.ctypes.data), C.c_void_p(xa.ctypes.data), C.c_void_p(None if ha is None else ha.ctypes.data),
+        C.c_int(0 if ha is None else ha.shape[0]), int(type_b), C.c_void_p(sb.ctypes.data), C.c_void_p(xb.ctypes.data),
+        C.c_void_p(None if hb is None else hb.ctypes.data), C.c_int(0 if hb is None else hb.shape[0]), C.c_float(gap_sum),
+        C.c_void_p(dist.ctypes.data), C.c_void_p(pos.ctypes.data), C.c_void_p(n.ctypes.data), C.c_int(IMPLS[impl]))
+    return cnt, dist, pos, n
+
+
+def hull_support_aabb(scale, hull, direction, xform, impl="oracle"):
+    """CONVEX_MESH support point in ``direction`` and tight world AABB under ``xform``: returns (support, lower, upper)."""
+    s, h, d, x = _f32(scale), _f32(hull).reshape(-1, 3), _f32(direction), _f32(xform)
+    out = np.zeros(9, np.float32)
+    lib().orc_hull_support_aabb(C.c_void_p(s.ctypes.data), C.c_void_p(h.ctypes.data), C.c_int(h.shape[0]), C.c_void_p(d.ctypes.data),
+                                C.c_void_p(x.ctypes.data), C.c_void_p(out.ctypes.data), C.c_int(IMPLS[impl]))
+    return out[:3], out[3:6], out[6:]
 
 
 def mpr_core(type_a, scale_a, type_b, scale_b, pos_b, quat_b, extend=0.0, impl="oracle"):

@@ -225,6 +225,35 @@ int orc_convex_pair(int type_a, const float* scale_a, const float* xform_a, int 
                             transform::load(xform_b), gap_sum, dist5, pos15, normal15, impl, margin_a, margin_b);
 }
 
+// ... with CONVEX_MESH operands: hull_* = unscaled vertices [n x 3] (NULL / 0 for primitives); the local AABB (centre seed) is
+// derived from the vertices like ModelBuilder.finalize does
+int orc_convex_pair_hull(int type_a, const float* scale_a, const float* xform_a, const float* hull_a, int n_a, int type_b, const float* scale_b,
+                         const float* xform_b, const float* hull_b, int n_b, float gap_sum, float* dist5, float* pos15, float* normal15, int impl) {
+    return convex_pair_test(type_a, load3(scale_a), transform::load(xform_a), type_b, load3(scale_b), transform::load(xform_b), gap_sum, dist5,
+                            pos15, normal15, impl, 0.0f, 0.0f, hull_of_points(hull_a, n_a, load3(scale_a)), hull_of_points(hull_b, n_b, load3(scale_b)));
+}
+// support map + tight AABB of one hull: out9 = support(3) aabb_lower(3) aabb_upper(3)
+void orc_hull_support_aabb(const float* scale, const float* hull, int n, const float* dir, const float* xform, float* out9, int impl) {
+    const cvx::HullRef h = hull_of_points(hull, n, load3(scale));
+    transform X = transform::load(xform);
+    vec3 sup, lo, hi;
+    if (impl == 0) {
+        const cvx::GenericShapeData g = cvx_geom_hull(GEO_CONVEX_MESH, load3(scale), h);
+        sup = cvx::support_map(g, load3(dir));
+        cvx::compute_tight_aabb_from_support(g, X.q, X.p, lo, hi);
+    } else {
+        const nb2::ConvexGeom g = nb2_geom_hull(GEO_CONVEX_MESH, load3(scale), h);
+        sup = from_nb2(nb2::support_map(g, to_nb2(load3(dir))));
+        nb2::V3 l, u;
+        nb2::tight_aabb_from_support(g, nb2::Q4(X.q.x, X.q.y, X.q.z, X.q.w), to_nb2(X.p), l, u);
+        lo = from_nb2(l);
+        hi = from_nb2(u);
+    }
+    store3(out9, sup);
+    store3(out9 + 3, lo);
+    store3(out9 + 6, hi);
+}
+
 // A-frame MPR / GJK cores and the support map, for the reference's direct solver tests (test_mpr.py, test_gjk.py).
 // out10 = point_a(3) point_b(3) normal(3) penetration|distance.  B's pose is relative to A.
 int orc_mpr_core(int type_a, const float* scale_a, int type_b, const float* scale_b, const float* pos_b, const float* quat_b, float extend,

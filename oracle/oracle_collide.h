@@ -16,7 +16,7 @@
 
 namespace orc {
 
-enum { GEO_PLANE = 1, GEO_HFIELD = 2, GEO_SPHERE = 3, GEO_CAPSULE = 4, GEO_ELLIPSOID = 5, GEO_CYLINDER = 6, GEO_BOX = 7, GEO_MESH = 8, GEO_CONE = 9 };
+enum { GEO_PLANE = 1, GEO_HFIELD = 2, GEO_SPHERE = 3, GEO_CAPSULE = 4, GEO_ELLIPSOID = 5, GEO_CYLINDER = 6, GEO_BOX = 7, GEO_MESH = 8, GEO_CONE = 9, GEO_CONVEX_MESH = 10 };
 static const float MAXVAL = 1.0e10f;
 static const float MINVAL = 1e-15f;
 static const float CYLINDER_FLAT_MODE_COS = 0.92387953251128673848f;  // cos(22.5 deg), collision_primitive.py:44-45
@@ -323,6 +323,20 @@ inline void compute_shape_aabbs(const nb2_model_desc& m, const float* body_q, st
                     radius * std::sqrt(r0.z * r0.z + r1.z * r1.z) + half_height * std::fabs(r2.z));
             lo = pos - he - margin_vec;
             hi = pos + he + margin_vec;
+        } else if (geo_type == GEO_CONVEX_MESH) {
+            // has_local_aabb (collide.py:420-444): the builder's scaled local AABB, rotated into the world frame
+            vec3 local_lo = load3(m.shape_collision_aabb_lower + 3 * sid), local_hi = load3(m.shape_collision_aabb_upper + 3 * sid);
+            vec3 center = (local_lo + local_hi) * 0.5f;
+            vec3 half = (local_hi - local_lo) * 0.5f;
+            vec3 world_center = quat_rotate(orientation, center) + pos;
+            vec3 r0 = quat_rotate(orientation, vec3(1.f, 0.f, 0.f));
+            vec3 r1 = quat_rotate(orientation, vec3(0.f, 1.f, 0.f));
+            vec3 r2 = quat_rotate(orientation, vec3(0.f, 0.f, 1.f));
+            vec3 world_half(std::fabs(r0.x) * half.x + std::fabs(r1.x) * half.y + std::fabs(r2.x) * half.z,
+                            std::fabs(r0.y) * half.x + std::fabs(r1.y) * half.y + std::fabs(r2.y) * half.z,
+                            std::fabs(r0.z) * half.x + std::fabs(r1.z) * half.y + std::fabs(r2.z) * half.z);
+            lo = world_center - world_half - margin_vec;
+            hi = world_center + world_half + margin_vec;
         } else if (geo_type == GEO_CONE || geo_type == GEO_PLANE) {
             // generic branch (collide.py:447-468): compute_tight_aabb_from_support;
             // finite planes carry HALF extents in geom_scale (collide.py:452-453)

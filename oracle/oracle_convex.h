@@ -25,12 +25,15 @@
 namespace orc {
 namespace cvx {
 
-enum { T_PLANE = 1, T_SPHERE = 3, T_CAPSULE = 4, T_ELLIPSOID = 5, T_CYLINDER = 6, T_BOX = 7, T_CONE = 9 };
+enum { T_PLANE = 1, T_SPHERE = 3, T_CAPSULE = 4, T_ELLIPSOID = 5, T_CYLINDER = 6, T_BOX = 7, T_CONE = 9, T_CONVEX_MESH = 10 };
 
-struct GenericShapeData {  // support_function.py:107-118 (auxiliary / mesh pointer unused for primitives)
+struct GenericShapeData {  // support_function.py:107-118
     int shape_type = 0;
     vec3 scale;
-    vec3 center;  // zero for every primitive (_shape_center, support_function.py:449-461)
+    vec3 center;  // zero for every primitive (_shape_center, support_function.py:449-461); local AABB centre for CONVEX_MESH
+    // what `auxiliary` (the packed wp.Mesh pointer) leads to for CONVEX_MESH: mesh.points, unscaled
+    const float* mesh_points = nullptr;
+    int mesh_point_count = 0;
 };
 
 struct vec2 {
@@ -62,7 +65,21 @@ inline vec3 support_map(const GenericShapeData& geom, vec3 direction) {
     const float eps = 1.0e-12f;
     vec3 result(0.f, 0.f, 0.f);
     const int t = geom.shape_type;
-    if (t == T_BOX) {
+    if (t == T_CONVEX_MESH) {  // support_function.py:153-172: furthest hull vertex, strict '>' keeps the first maximum
+        vec3 mesh_scale = geom.scale;
+        int num_verts = geom.mesh_point_count;
+        vec3 scaled_dir = cw_mul(direction, mesh_scale);
+        float max_dot = -1.0e10f;
+        int best_idx = 0;
+        for (int i = 0; i < num_verts; ++i) {
+            float dot_val = dot(load3(geom.mesh_points + 3 * i), scaled_dir);
+            if (dot_val > max_dot) {
+                max_dot = dot_val;
+                best_idx = i;
+            }
+        }
+        if (num_verts > 0) result = cw_mul(load3(geom.mesh_points + 3 * best_idx), mesh_scale);
+    } else if (t == T_BOX) {
         result = support_map_box(geom, direction);
     } else if (t == T_SPHERE) {
         float radius = geom.scale.x;
@@ -924,7 +941,7 @@ struct PairCtx {
     int count = 0;
 };
 
-inline bool is_discrete_shape(int t) { return t == T_BOX || t == T_PLANE; }  // collision_core.py:40-48 (meshes / triangles n/a)
+inline bool is_discrete_shape(int t) { return t == T_BOX || t == T_CONVEX_MESH || t == T_PLANE; }  // collision_core.py:40-48 (triangles n/a)
 
 // post_process_axial_on_discrete_contact (collision_core.py:174-277) followed by the writer's gap test
 // (sim/collide.py:210-254 with contact_passes_gap_check): emits into ctx
@@ -1144,6 +1161,21 @@ inline void compute_tight_aabb_from_support(const GenericShapeData& shape_data, 
     vec3 local_x(rot_mat_t.m[0][0], rot_mat_t.m[1][0], rot_mat_t.m[2][0]);
     vec3 local_y(rot_mat_t.m[0][1], rot_mat_t.m[1][1], rot_mat_t.m[2][1]);
     vec3 local_z(rot_mat_t.m[0][2], rot_mat_t.m[1][2], rot_mat_t.m[2][2]);
+    if (shape_data.shape_type == T_CONVEX_MESH) {  // collision_core.py:492-523: one pass over the vertices
+        vec3 mesh_scale = shape_data.scale;
+        vec3 scaled_x = cw_mul(local_x, mesh_scale), scaled_y = cw_mul(local_y, mesh_scale), scaled_z = cw_mul(local_z, mesh_scale);
+        float mnx = 1.0e10f, mxx = -1.0e10f, mny = 1.0e10f, mxy = -1.0e10f, mnz = 1.0e10f, mxz = -1.0e10f;
+        for (int i = 0; i < shape_data.mesh_point_count; ++i) {
+            vec3 p = load3(shape_data.mesh_points + 3 * i);
+            float vx = dot(p, scaled_x), vy = dot(p, scaled_y), vz = dot(p, scaled_z);
+            mnx = minf(mnx, vx); mxx = maxf(mxx, vx);
+            mny = minf(mny, vy); mxy = maxf(mxy, vy);
+            mnz = minf(mnz, vz); mxz = maxf(mxz, vz);
+        }
+        aabb_min = vec3(mnx, mny, mnz) + center_pos;
+        aabb_max = vec3(mxx, mxy, mxz) + center_pos;
+        return;
+    }
     float max_x = dot(local_x, support_map(shape_data, local_x));
     float max_y = dot(local_y, support_map(shape_data, local_y));
     float max_z = dot(local_z, support_map(shape_data, local_z));
@@ -1154,14 +1186,30 @@ inline void compute_tight_aabb_from_support(const GenericShapeData& shape_data, 
     aabb_max = vec3(max_x, max_y, max_z) + center_pos;
 }
 
+struct HullRef {  // model.shape_source (unscaled hull vertices) + model.shape_collision_aabb_lower / _upper of one CONVEX_MESH shape
+    const float* points = nullptr;
+    int count = 0;
+    vec3 local_aabb_lower, local_aabb_upper;
+};
+
 // One pair of narrow_phase_kernel_gjk_mpr (narrow_phase.py:1066-1216) with external AABBs + find_contacts
 // (collision_core.py:700-790).  `scale_*` are the MODEL's shape scales; finite planes are halved like geom_data.
 inline int gjk_mpr_pair(int type_a, vec3 scale_a, const transform& X_a, float margin_a, vec3 aabb_lo_a, vec3 aabb_hi_a, int type_b, vec3 scale_b,
                         const transform& X_b, float margin_b, vec3 aabb_lo_b, vec3 aabb_hi_b, float gap_sum, ContactOut* out,
-                        float& radius_eff_a, float& radius_eff_b) {
+                        float& radius_eff_a, float& radius_eff_b, const HullRef& hull_a = HullRef(), const HullRef& hull_b = HullRef()) {
     GenericShapeData shape_data_a, shape_data_b;
     shape_data_a.shape_type = type_a;
     shape_data_b.shape_type = type_b;
+    if (type_a == T_CONVEX_MESH) {  // narrow_phase.py:1096-1105: mesh pointer + cached centre of the local collision AABB
+        shape_data_a.mesh_points = hull_a.points;
+        shape_data_a.mesh_point_count = hull_a.count;
+        shape_data_a.center = 0.5f * (hull_a.local_aabb_lower + hull_a.local_aabb_upper);
+    }
+    if (type_b == T_CONVEX_MESH) {
+        shape_data_b.mesh_points = hull_b.points;
+        shape_data_b.mesh_point_count = hull_b.count;
+        shape_data_b.center = 0.5f * (hull_b.local_aabb_lower + hull_b.local_aabb_upper);
+    }
     shape_data_a.scale = type_a == T_PLANE ? vec3(scale_a.x * 0.5f, scale_a.y * 0.5f, 0.0f) : scale_a;  // geom_data (collide.py:452-453)
     shape_data_b.scale = type_b == T_PLANE ? vec3(scale_b.x * 0.5f, scale_b.y * 0.5f, 0.0f) : scale_b;
     vec3 pos_a = X_a.p, pos_b = X_b.p;

@@ -23,11 +23,13 @@ inline nb2::Xf to_nb2(const transform& t) { return nb2::Xf(to_nb2(t.p), nb2::Q4(
 // One pair through compute_gjk_mpr_contacts; contacts come back already gap-tested, in sort_sub_key order.
 inline int convex_pair(int type_a, vec3 scale_a, const transform& Xa, float margin_a, int type_b, vec3 scale_b, const transform& Xb,
                        float margin_b, float gap_sum, float* dist, vec3* pos, vec3* normal, float& reff_a, float& reff_b,
-                       vec3 lo_a = vec3(), vec3 hi_a = vec3(), vec3 lo_b = vec3(), vec3 hi_b = vec3(), int impl = 0) {
+                       vec3 lo_a = vec3(), vec3 hi_a = vec3(), vec3 lo_b = vec3(), vec3 hi_b = vec3(), int impl = 0,
+                       const cvx::HullRef& hull_a = cvx::HullRef(), const cvx::HullRef& hull_b = cvx::HullRef()) {
     reff_a = reff_b = 0.0f;
     if (impl == 0) {
         cvx::ContactOut out[5];
-        int cnt = cvx::gjk_mpr_pair(type_a, scale_a, Xa, margin_a, lo_a, hi_a, type_b, scale_b, Xb, margin_b, lo_b, hi_b, gap_sum, out, reff_a, reff_b);
+        int cnt = cvx::gjk_mpr_pair(type_a, scale_a, Xa, margin_a, lo_a, hi_a, type_b, scale_b, Xb, margin_b, lo_b, hi_b, gap_sum, out, reff_a, reff_b,
+                                    hull_a, hull_b);
         for (int i = 0; i < cnt; ++i) {
             dist[i] = out[i].distance;
             pos[i] = out[i].center;
@@ -45,6 +47,12 @@ inline int convex_pair(int type_a, vec3 scale_a, const transform& Xa, float marg
     in.margin_a = margin_a;
     in.margin_b = margin_b;
     in.gap_sum = gap_sum;
+    in.hull_a = hull_a.points;
+    in.hull_count_a = hull_a.count;
+    in.center_a = to_nb2(0.5f * (hull_a.local_aabb_lower + hull_a.local_aabb_upper));
+    in.hull_b = hull_b.points;
+    in.hull_count_b = hull_b.count;
+    in.center_b = to_nb2(0.5f * (hull_b.local_aabb_lower + hull_b.local_aabb_upper));
     nb2::V3 p[5], n[5];
     nb2::ConvexPairAabbs bb{to_nb2(lo_a), to_nb2(hi_a), to_nb2(lo_b), to_nb2(hi_b)};
     int cnt = nb2::convex_contacts_any(in, bb, dist, p, n, reff_a, reff_b);
@@ -53,6 +61,17 @@ inline int convex_pair(int type_a, vec3 scale_a, const transform& Xa, float marg
         normal[i] = from_nb2(n[i]);
     }
     return cnt;
+}
+
+inline cvx::HullRef hull_ref(const nb2_model_desc& m, int shape) {
+    cvx::HullRef h;
+    if (m.shape_type[shape] == GEO_CONVEX_MESH && m.hull_points && m.shape_hull_start) {
+        h.points = m.hull_points + 3 * size_t(m.shape_hull_start[shape]);
+        h.count = m.shape_hull_count[shape];
+        h.local_aabb_lower = load3(m.shape_collision_aabb_lower + 3 * shape);
+        h.local_aabb_upper = load3(m.shape_collision_aabb_upper + 3 * shape);
+    }
+    return h;
 }
 
 // The GJK/MPR kernel pass over the pairs the primitive kernel forwarded (narrow_phase.py:1041-1216).
@@ -70,7 +89,8 @@ inline void gjk_mpr_pairs(const nb2_model_desc& m, const float* body_q, CollideR
         // raw model scales: convex_contacts_any applies the geom_data halving of finite planes itself
         int cnt = convex_pair(m.shape_type[shape_a], load3(m.shape_scale + 3 * shape_a), A.X_ws, A.margin, m.shape_type[shape_b],
                               load3(m.shape_scale + 3 * shape_b), B.X_ws, B.margin, gap_sum,
-                              dist, pos, normal, ra, rb, A.aabb_lower, A.aabb_upper, B.aabb_lower, B.aabb_upper);
+                              dist, pos, normal, ra, rb, A.aabb_lower, A.aabb_upper, B.aabb_lower, B.aabb_upper, 0, hull_ref(m, shape_a),
+                              hull_ref(m, shape_b));
         for (int i = 0; i < cnt; ++i) {
             RawContact rc;
             // emission order == sort_sub_key order; dropped manifold points only leave holes in the sub-key sequence
@@ -123,28 +143,60 @@ inline vec3 support_map_test(int type, vec3 scale, vec3 dir, int impl = 0) {
     return from_nb2(nb2::support_map(nb2::ConvexGeom{type, to_nb2(scale)}, to_nb2(dir)));
 }
 
+inline cvx::HullRef hull_of_points(const float* points, int count, vec3 scale) {  // what the builder derives for a CONVEX_MESH shape
+    cvx::HullRef h;
+    h.points = points;
+    h.count = count;
+    if (count > 0) {  // scaled local AABB (sim/builder.py:11605-11610)
+        vec3 lo = cw_mul(load3(points), scale), hi = lo;
+        for (int i = 1; i < count; ++i) {
+            vec3 p = cw_mul(load3(points + 3 * i), scale);
+            lo = vec3(minf(lo.x, p.x), minf(lo.y, p.y), minf(lo.z, p.z));
+            hi = vec3(maxf(hi.x, p.x), maxf(hi.y, p.y), maxf(hi.z, p.z));
+        }
+        h.local_aabb_lower = lo;
+        h.local_aabb_upper = hi;
+    }
+    return h;
+}
+inline cvx::GenericShapeData cvx_geom_hull(int type, vec3 scale, const cvx::HullRef& h) {
+    cvx::GenericShapeData g = cvx_geom(type, scale);
+    if (type == GEO_CONVEX_MESH) {
+        g.mesh_points = h.points;
+        g.mesh_point_count = h.count;
+        g.center = 0.5f * (h.local_aabb_lower + h.local_aabb_upper);
+    }
+    return g;
+}
+inline nb2::ConvexGeom nb2_geom_hull(int type, vec3 scale, const cvx::HullRef& h) {
+    if (type != GEO_CONVEX_MESH) return nb2::ConvexGeom(type, to_nb2(scale));
+    return nb2::ConvexGeom(type, to_nb2(scale), to_nb2(0.5f * (h.local_aabb_lower + h.local_aabb_upper)), h.points, h.count);
+}
+
 inline int convex_pair_test(int type_a, vec3 scale_a, const transform& Xa, int type_b, vec3 scale_b, const transform& Xb, float gap_sum,
-                            float* dist5, float* pos15, float* normal15, int impl = 0, float margin_a = 0.0f, float margin_b = 0.0f) {
+                            float* dist5, float* pos15, float* normal15, int impl = 0, float margin_a = 0.0f, float margin_b = 0.0f,
+                            const cvx::HullRef& hull_a = cvx::HullRef(), const cvx::HullRef& hull_b = cvx::HullRef()) {
     float ra, rb;
     vec3 pos[5], normal[5];
     // AABBs as the stand-alone NarrowPhase computes them (narrow_phase.py:1120-1150): tight support AABB +- the shape's gap;
     // only the bounding-sphere radius of the shape facing an infinite plane depends on them
-    auto aabb = [&](int type, vec3 scale, const transform& X, vec3& lo, vec3& hi) {
+    auto aabb = [&](int type, vec3 scale, const transform& X, const cvx::HullRef& hull, vec3& lo, vec3& hi) {
         if (type == GEO_PLANE) {
             lo = X.p - vec3(1.0e6f);
             hi = X.p + vec3(1.0e6f);
             return;
         }
         vec3 l, h;
-        cvx::compute_tight_aabb_from_support(cvx_geom(type, scale), X.q, X.p, l, h);
+        cvx::compute_tight_aabb_from_support(cvx_geom_hull(type, scale, hull), X.q, X.p, l, h);
         const vec3 g(0.5f * gap_sum);
         lo = l - g;
         hi = h + g;
     };
     vec3 lo_a, hi_a, lo_b, hi_b;
-    aabb(type_a, scale_a, Xa, lo_a, hi_a);
-    aabb(type_b, scale_b, Xb, lo_b, hi_b);
-    int cnt = convex_pair(type_a, scale_a, Xa, margin_a, type_b, scale_b, Xb, margin_b, gap_sum, dist5, pos, normal, ra, rb, lo_a, hi_a, lo_b, hi_b, impl);
+    aabb(type_a, scale_a, Xa, hull_a, lo_a, hi_a);
+    aabb(type_b, scale_b, Xb, hull_b, lo_b, hi_b);
+    int cnt = convex_pair(type_a, scale_a, Xa, margin_a, type_b, scale_b, Xb, margin_b, gap_sum, dist5, pos, normal, ra, rb, lo_a, hi_a, lo_b, hi_b, impl,
+                          hull_a, hull_b);
     for (int i = 0; i < cnt; ++i) {
         store3(pos15 + 3 * i, pos[i]);
         store3(normal15 + 3 * i, normal[i]);

@@ -762,8 +762,8 @@ def test_torque_free_precession_featherstone(oracle_lib):
 
 
 def _ramp_scene():
-    """Scene of newton/tests/test_rigid_contact.py:236-432 (objects resting on a 30-degree ramp against an end wall), minus
-    the two convex-hull cubes (convex meshes are outside this library's scope; they sit furthest up the ramp)."""
+    """Scene of newton/tests/test_rigid_contact.py:236-432 (objects resting on a 30-degree ramp against an end wall),
+    including the two cubes written as convex hulls of their 8 corners (:402-425), furthest up the ramp."""
     L, TH, ANG, WALL_H, CUBE = 10.0, 0.5, math.radians(30.0), 2.0, 0.99
     W = CUBE * 2.01
     b = ModelBuilder()
@@ -804,6 +804,12 @@ def _ramp_scene():
     for side in (1.0, -1.0):
         body = b.add_body(xform=X.transform(at(side, 12.06), rq))
         b.add_shape_box(body, hx=CUBE / 2, hy=CUBE / 2, hz=CUBE / 2)
+    from newton_b200.geometry.mesh import Mesh
+
+    cube_mesh = Mesh.create_box(CUBE / 2, CUBE / 2, CUBE / 2)
+    for side in (1.0, -1.0):  # convex-hull cubes (test_rigid_contact.py:402-425)
+        body = b.add_body(xform=X.transform(at(side, 14.07), rq))
+        b.add_shape_convex_hull(body, mesh=cube_mesh, scale=(1.0, 1.0, 1.0))
     b.add_ground_plane()
     return b.finalize(), CUBE
 
