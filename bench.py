@@ -390,7 +390,7 @@ def run_native(args):
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
-        cpu_baseline = oracle_throughput(envs, frames=20, threads=os.cpu_count() or 1)
+        cpu_baseline = oracle_throughput(envs, frames=20, threads=host_threads()[0])
 
     if rank == 0:
         out = {
@@ -413,6 +413,27 @@ def run_native(args):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+def host_threads() -> tuple[int, float | None]:
+    """(threads to use, CPU quota of this container in cores or None).  The GPU boxes report 128 logical CPUs but run the
+    container under a CFS quota (cpu.max, measured 16 cores): more runnable threads than the quota only add throttling stalls."""
+    n = os.cpu_count() or 1
+    quota = None
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            a, b = f.read().split()
+        if a != "max":
+            quota = float(a) / float(b)
+    except Exception:
+        pass
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    if quota is not None:
+        n = max(1, min(n, int(round(quota))))
+    return n, quota
+
+
 ENVS_PER_SHARD = 32  # >= 32 environments per unit of CPU work; shards are handed to the threads dynamically
 
 
@@ -459,7 +480,8 @@ class CpuArm:
         except Exception:
             pass
         return {
-            "value": value, "unit": UNIT, "cores": self.threads, "physical_cores": phys, "kind": "port",
+            "value": value, "unit": UNIT, "cores": self.threads, "physical_cores": phys, "logical_cpus": os.cpu_count(),
+            "cpu_quota_cores": host_threads()[1], "kind": "port",
             "all_cores": value, "single_thread": single_value,
             "sample": f"{self.envs} envs x {frames} frames x {SUBSTEPS} substeps of the bench workload (same scene, seed and solver "
                       f"settings, settled 1.2 s first), oracle C++ port of the reference kernels; {self.n_shards} shards of "
@@ -498,7 +520,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_threads()[0]
     steps, warm = max(1, args.steps), max(0, args.warmup)
     arm = CpuArm(args.envs, threads)
     arm.settle()

@@ -177,6 +177,11 @@ typedef struct nb2_featherstone_params {
     float angular_damping;
     int32_t update_mass_matrix_interval;
     float friction_smoothing;
+    /* reference use_tile_gemm (solver_featherstone.py:142, tile kernels featherstone/kernels.py:1568-1652): form H = J^T M J on the
+       tensor cores (mma.sync m16n8k8, 3xTF32 split, fp32 accumulate) instead of the ordered FP32 sums.  Like the reference's tile
+       path it is opt-in and restricted (articulations of <= 24 dofs); results agree with the default path to ~1e-6 relative, not
+       bit for bit. */
+    int32_t use_tile_gemm;
 } nb2_featherstone_params;
 
 typedef struct nb2_model nb2_model; /* opaque: env partition, contact blocks, solver scratch */

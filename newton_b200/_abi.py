@@ -204,6 +204,7 @@ class FeatherstoneParams(C.Structure):
         ("angular_damping", C.c_float),
         ("update_mass_matrix_interval", C.c_int32),
         ("friction_smoothing", C.c_float),
+        ("use_tile_gemm", C.c_int32),
     ]
 
 

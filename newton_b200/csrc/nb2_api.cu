@@ -263,6 +263,65 @@ static nb2_status build_tables(nb2_model* m, const nb2_model_desc& d) {
                 }
             }
         }
+        // ---- H-stage schedule (see DevModel): the per-(depth, dof number) column batches of every articulation ----------------
+        h.joint_desc_mask.assign(size_t(J), 0ull);
+        h.dof_joint.assign(size_t(jqd[J]), 0);
+        h.art_batch_count.assign(size_t(d.articulation_count), 0);
+        h.art_hb_body_start.assign(size_t(d.articulation_count), 0);
+        h.art_hb_row_start.assign(size_t(d.articulation_count), 0);
+        h.hb_body_col.clear();
+        h.hb_row_col.clear();
+        for (int a = 0; a < d.articulation_count && h.featherstone_supported; ++a) {
+            const int j0 = art_start[a], j1 = art_start[a + 1], anj = j1 - j0;
+            const int ad0 = jqd[j0], n = jqd[j1] - ad0;
+            h.max_art_dofs = std::max(h.max_art_dofs, n);
+            if (n > 127) {
+                h.featherstone_supported = false;
+                h.featherstone_reason = "articulations with more than 127 dofs";
+                break;
+            }
+            int maxdep = 0;
+            for (int j = j0; j < j1; ++j) {
+                maxdep = std::max(maxdep, h.joint_depth[j]);
+                for (int k = jqd[j]; k < jqd[j + 1]; ++k) h.dof_joint[k] = (signed char)(j - j0);
+                unsigned long long m = 0ull;  // descendant-or-self: every joint i whose ancestor mask contains j
+                for (int i = j0; i < j1; ++i) m |= ((h.joint_anc_mask[i] >> (j - j0)) & 1ull) << (i - j0);
+                h.joint_desc_mask[j] = m;
+            }
+            // ancestor-or-self of joint i at a given depth (-1: i is shallower)
+            auto anc_at = [&](int i, int dep) {
+                int jb = -1;
+                for (unsigned long long m = h.joint_anc_mask[j0 + i]; m; m &= m - 1ull) {
+                    const int b = __builtin_ctzll(m);
+                    if (h.joint_depth[j0 + b] == dep) jb = b;
+                }
+                return jb;
+            };
+            h.art_hb_body_start[a] = int(h.hb_body_col.size());
+            h.art_hb_row_start[a] = int(h.hb_row_col.size());
+            int batches = 0;
+            for (int dep = 0; dep <= maxdep; ++dep)
+                for (int kk = 0; kk < 6; ++kk) {
+                    bool any = false;
+                    for (int j = j0; j < j1 && !any; ++j) any = h.joint_depth[j] == dep && jqd[j + 1] - jqd[j] > kk;
+                    if (!any) break;  // dof counts only shrink the batch
+                    for (int i = 0; i < anj; ++i) {
+                        const int jb = h.joint_depth[j0 + i] >= dep ? anc_at(i, dep) : -1;
+                        const bool on = jb >= 0 && jqd[j0 + jb + 1] - jqd[j0 + jb] > kk;
+                        h.hb_body_col.push_back(on ? (signed char)(jqd[j0 + jb] - ad0 + kk) : (signed char)-1);
+                    }
+                    for (int ra = 0; ra < n; ++ra) {
+                        const int ja = h.dof_joint[ad0 + ra];
+                        const int jb = h.joint_depth[j0 + ja] >= dep ? anc_at(ja, dep) : -1;
+                        int col = -1;
+                        if (jb >= 0 && jqd[j0 + jb + 1] - jqd[j0 + jb] > kk) col = jqd[j0 + jb] - ad0 + kk;
+                        if (col > ra) col = -1;  // upper triangle (only possible inside joint(col) itself)
+                        h.hb_row_col.push_back((signed char)col);
+                    }
+                    batches += 1;
+                }
+            h.art_batch_count[a] = batches;
+        }
         {  // a body driven by two joints ("undefined semantics" upstream): only the serial walk reproduces the array-order result
             std::vector<char> driven(size_t(B), 0);
             for (int j = 0; j < J; ++j)
@@ -350,6 +409,13 @@ static nb2_status upload_tables(nb2_model* m) {
     if ((st = upload(m, h.joint_anc_mask, &dv.joint_anc_mask))) return st;
     if ((st = upload(m, h.art_H_start, &dv.art_H_start))) return st;
     if ((st = upload(m, h.env_H_start, &dv.env_H_start))) return st;
+    if ((st = upload(m, h.art_batch_count, &dv.art_batch_count))) return st;
+    if ((st = upload(m, h.art_hb_body_start, &dv.art_hb_body_start))) return st;
+    if ((st = upload(m, h.art_hb_row_start, &dv.art_hb_row_start))) return st;
+    if ((st = upload(m, h.hb_body_col, &dv.hb_body_col))) return st;
+    if ((st = upload(m, h.hb_row_col, &dv.hb_row_col))) return st;
+    if ((st = upload(m, h.joint_desc_mask, &dv.joint_desc_mask))) return st;
+    if ((st = upload(m, h.dof_joint, &dv.dof_joint))) return st;
     void* p = nullptr;
     {
         size_t nL = std::max<size_t>(size_t(h.env_H_start.back()), 1);

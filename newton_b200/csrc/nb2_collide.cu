@@ -18,6 +18,8 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "nb2_gjk.cuh"
+#include <cstdlib>
+
 #include "nb2_internal.cuh"
 #include "nb2_math.cuh"
 
@@ -299,17 +301,20 @@ struct __align__(4) SlotRec {
 
 // CONVEX = false is instantiated for models none of whose pairs can reach the generic convex path (decided per pair type at
 // nb2_model_create): the analytic-only kernel carries neither the MPR / GJK / manifold code nor its registers and stack.
-template <int L, bool CONVEX>
-__global__ void __launch_bounds__(32) collide_kernel(DevModel M, const float* __restrict__ body_q) {
+// WARPS warps per CTA (each warp = 32/L environments): the kernel is a straight line every warp walks once, so one-warp CTAs each
+// fetch the whole instruction stream cold (48 % `stall_no_inst`, profiles/r1f_collide_kernel_quadruped.txt); warps of one CTA
+// start together and share the fetches.
+template <int L, bool CONVEX, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) collide_kernel(DevModel M, const float* __restrict__ body_q) {
     constexpr int G = 32 / L;  // environments per warp
     extern __shared__ unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane / L;
     const int l = lane % L;
     const unsigned gmask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << (grp * L));
-    const int env = blockIdx.x * G + grp;
+    const int env = (blockIdx.x * WARPS + warp) * G + grp;
     const bool live = env < M.env_count;
-    SlotRec* slots = reinterpret_cast<SlotRec*>(smem_raw) + size_t(grp) * M.max_env_slots_shapes;
+    SlotRec* slots = reinterpret_cast<SlotRec*>(smem_raw) + size_t(warp * G + grp) * M.max_env_slots_shapes;
     const nb2_model_desc& d = M.d;
 
     int ss = 0, nloc = 0, nslots = 0, bs = 0, ps = 0, np = 0, slot0 = 0;
@@ -342,6 +347,7 @@ __global__ void __launch_bounds__(32) collide_kernel(DevModel M, const float* __
         st3(slots[s].hi, hi);
     }
     __syncwarp();
+    if (WARPS > 1) __syncthreads();  // alignment only (see above)
     // ---- phase 2: pairs -> contacts -------------------------------------------------------------
     int n_total = 0;
     const int rounds = (np + L - 1) / L;
@@ -814,22 +820,38 @@ nb2_status launch_contacts_import(nb2_model* m, const nb2_contacts_view& in, cud
     return NB2_OK;
 }
 
-template <int L, bool CONVEX>
-static nb2_status launch_collide_L(nb2_model* m, const float* body_q, cudaStream_t s) {
+template <int L, bool CONVEX, int WARPS>
+static nb2_status launch_collide_W(nb2_model* m, const float* body_q, cudaStream_t s) {
     const DevModel& M = m->dev;
-    const int G = 32 / L;
-    const int blocks = (M.env_count + G - 1) / G;
-    const size_t smem = size_t(G) * M.max_env_slots_shapes * sizeof(SlotRec);
-    if (smem > 200 * 1024) {
-        set_error("collide: too many shapes per environment for the fused kernel");
-        return NB2_ERR_CAPACITY;
-    }
+    const int NE = (32 / L) * WARPS;
+    const int blocks = (M.env_count + NE - 1) / NE;
+    const size_t smem = size_t(NE) * M.max_env_slots_shapes * sizeof(SlotRec);
     if (smem > 48 * 1024)
-        NB2_CUDA_CHECK(cudaFuncSetAttribute(collide_kernel<L, CONVEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    collide_kernel<L, CONVEX><<<blocks, 32, smem, s>>>(M, body_q);
+        NB2_CUDA_CHECK(cudaFuncSetAttribute(collide_kernel<L, CONVEX, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    collide_kernel<L, CONVEX, WARPS><<<blocks, 32 * WARPS, smem, s>>>(M, body_q);
     count_launch();
     NB2_CUDA_CHECK(cudaGetLastError());
     return NB2_OK;
+}
+
+template <int L, bool CONVEX>
+static nb2_status launch_collide_L(nb2_model* m, const float* body_q, cudaStream_t s) {
+    const DevModel& M = m->dev;
+    const size_t per_warp = size_t(32 / L) * M.max_env_slots_shapes * sizeof(SlotRec);
+    if (per_warp > 200 * 1024) {
+        set_error("collide: too many shapes per environment for the fused kernel");
+        return NB2_ERR_CAPACITY;
+    }
+    static const int forced = std::getenv("NB2_COLLIDE_WARPS") ? std::atoi(std::getenv("NB2_COLLIDE_WARPS")) : 0;
+    int warps = forced;
+    if (warps <= 0) {  // as many warps per CTA as the batch puts on every SM, up to 8
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+        const long long total_warps = (M.env_count + (32 / L) - 1) / (32 / L);
+        warps = (total_warps + sms - 1) / sms >= 8 ? 8 : 1;
+    }
+    if (warps >= 8 && per_warp * 8 <= 200 * 1024) return launch_collide_W<L, CONVEX, 8>(m, body_q, s);
+    return launch_collide_W<L, CONVEX, 1>(m, body_q, s);
 }
 
 nb2_status launch_collide(nb2_model* m, const float* body_q, const nb2_contacts_view* contacts, cudaStream_t s) {

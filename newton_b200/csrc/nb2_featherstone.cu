@@ -21,6 +21,8 @@
 // strict-fp build reproduces the CPU oracle bit for bit.  Tensor cores (north_star: "only for the small dense
 // mass-matrix factor/solve") would need TF32 or 3xTF32 splits and cannot meet bit-parity; with H at 18x18 the stage is
 // ~9 k MACs per env, latency- not throughput-bound, so it stays on the FP32 pipe.
+#include <cstdlib>
+
 #include "nb2_internal.cuh"
 #include "nb2_math.cuh"
 
@@ -196,13 +198,11 @@ NB2_DEV Xf joint_transform(const nb2_model_desc& d, int type, int axis_start, in
 
 struct FsSmem {
     float *bq, *bqc, *vs, *as, *fb, *ft, *fe, *qdfk, *Is, *so, *fs, *S, *qd_in, *jf, *tau, *qdd, *qd_out, *H, *jq, *P;
-    int* dofj;
-    unsigned long long *anc, *desc;  // ancestor-or-self / descendant-or-self bit masks of the env's joints (8-byte aligned)
 };
 NB2_DEV size_t fs_smem_floats(const DevModel& M) {
     const size_t n = size_t(M.max_env_bodies) * (7 + 7 + 6 * 6 + 36 + 3 + 6) + size_t(M.max_env_joints) * 6 +
-                     size_t(M.max_env_dofs) * (6 + 5 + 1) + size_t(M.max_env_H) + size_t(M.max_env_coords);
-    return ((n + 1) & ~size_t(1)) + 4 * size_t(M.max_env_joints);  // even float count, then two u64 per joint
+                     size_t(M.max_env_dofs) * (6 + 5) + size_t(M.max_env_H) + size_t(M.max_env_coords);
+    return (n + 1) & ~size_t(1);
 }
 NB2_DEV FsSmem fs_carve(float* base, const DevModel& M) {
     FsSmem s;
@@ -228,28 +228,127 @@ NB2_DEV FsSmem fs_carve(float* base, const DevModel& M) {
     s.H = p; p += M.max_env_H;
     s.jq = p; p += M.max_env_coords;
     s.P = p; p += nb * 6;
-    s.dofj = reinterpret_cast<int*>(p); p += nd;
-    p = base + (((p - base) + 1) & ~ptrdiff_t(1));
-    s.anc = reinterpret_cast<unsigned long long*>(p);
-    s.desc = s.anc + nj;
     return s;
+}
+
+// ---- tensor-core H = J^T (M J) (reference use_tile_gemm: eval_dense_gemm_tile / the fused tile kernels, featherstone/kernels.py:
+// 1568-1652) -------------------------------------------------------------------------------------------------------------------------
+// One warp forms the H of ONE articulation at a time with mma.sync.m16n8k8 (TF32 inputs, FP32 accumulate).  The K dimension is
+// walked body by body (6 of the 8 k-slots used): per body i
+//     P_i [6 x n]  = I_i [6 x 6] . J_i [6 x n]      1 M-tile x 3 N-tiles     (J_i[:, b] = S_b if joint(b) is an ancestor-or-self of i)
+//     H  [n x n]  += J_i^T [n x 6] . P_i [6 x n]    2 M-tiles x 3 N-tiles
+// with every product taken as the 3xTF32 split  a.b ~ a_lo.b_hi + a_hi.b_lo + a_hi.b_hi  (a_hi = tf32(a), a_lo = tf32(a - a_hi)),
+// which carries ~2^-21 relative error per product - H agrees with the FP32 path to ~1e-6, not bit for bit, which is why the path is
+// opt-in (SolverFeatherstone(use_tile_gemm=True)).  n <= 24 (3 N-tiles, 2 M-tiles): checked by the launcher.
+#define NB2_GPU_FN __device__ __forceinline__
+NB2_GPU_FN unsigned to_tf32(float x) {
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+NB2_GPU_FN void mma_tf32(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+NB2_GPU_FN void mma_3xtf32(float (&c)[4], const float (&a)[4], const float (&b)[2]) {
+    unsigned ah[4], al[4], bh[2], bl[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        ah[i] = to_tf32(a[i]);
+        al[i] = to_tf32(a[i] - __uint_as_float(ah[i]));
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        bh[i] = to_tf32(b[i]);
+        bl[i] = to_tf32(b[i] - __uint_as_float(bh[i]));
+    }
+    mma_tf32(c, al, bh);  // small terms first
+    mma_tf32(c, ah, bl);
+    mma_tf32(c, ah, bh);
+}
+// S: the articulation's motion subspaces (6 floats per dof), Is: its bodies' spatial inertias (36 floats each, body i == joint i),
+// anc / dofj: ancestor masks and dof -> joint table (articulation-local), Pbuf: 6 x 24 floats of warp scratch, H: n x n output.
+__device__ __noinline__ void tile_mass_matrix(const float* S, const float* Is, const unsigned long long* anc, const signed char* dofj, int anj,
+                                              int n, float* Pbuf, float* H) {
+    const int lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+    float acc[2][3][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[mt][nt][k] = 0.0f;
+    for (int i = 0; i < anj; ++i) {
+        const unsigned long long am = anc[i];
+        const float* I = Is + 36 * i;
+        // A = I_i as a 16 x 8 tile: rows gq / gq + 8 (only rows < 6 exist), columns tq / tq + 4
+        float a1[4] = {gq < 6 ? I[6 * gq + tq] : 0.0f, 0.0f, (gq < 6 && tq < 2) ? I[6 * gq + tq + 4] : 0.0f, 0.0f};
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) {
+            const int b = 8 * nt + gq;  // this lane's column of J_i
+            const bool on = b < n && ((am >> dofj[b < n ? b : 0]) & 1ull);
+            float b1[2] = {on ? S[6 * b + tq] : 0.0f, (on && tq < 2) ? S[6 * b + tq + 4] : 0.0f};
+            float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            mma_3xtf32(c, a1, b1);
+            if (gq < 6) {  // C rows gq: P_i[gq][8 nt + 2 tq], [.. + 1]
+                Pbuf[gq * 24 + 8 * nt + 2 * tq] = c[0];
+                Pbuf[gq * 24 + 8 * nt + 2 * tq + 1] = c[1];
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int r0 = 16 * mt + gq, r1 = r0 + 8;  // rows of H = columns of J_i
+            const bool on0 = r0 < n && ((am >> dofj[r0 < n ? r0 : 0]) & 1ull), on1 = r1 < n && ((am >> dofj[r1 < n ? r1 : 0]) & 1ull);
+            float a2[4] = {on0 ? S[6 * r0 + tq] : 0.0f, on1 ? S[6 * r1 + tq] : 0.0f, (on0 && tq < 2) ? S[6 * r0 + tq + 4] : 0.0f,
+                           (on1 && tq < 2) ? S[6 * r1 + tq + 4] : 0.0f};
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) {
+                float b2[2] = {Pbuf[tq * 24 + 8 * nt + gq], tq < 2 ? Pbuf[(tq + 4) * 24 + 8 * nt + gq] : 0.0f};
+                mma_3xtf32(acc[mt][nt], a2, b2);
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) {
+            const int r0 = 16 * mt + gq, r1 = r0 + 8, c0 = 8 * nt + 2 * tq;
+            if (r0 < n && c0 < n) H[r0 * n + c0] = acc[mt][nt][0];
+            if (r0 < n && c0 + 1 < n) H[r0 * n + c0 + 1] = acc[mt][nt][1];
+            if (r1 < n && c0 < n) H[r1 * n + c0] = acc[mt][nt][2];
+            if (r1 < n && c0 + 1 < n) H[r1 * n + c0 + 1] = acc[mt][nt][3];
+        }
+    __syncwarp();
 }
 
 // PF: also write State.body_parent_f (compute_body_parent_f, featherstone/kernels.py:2371-2416) - a second instantiation, so
 // that the plain step's code is untouched (the same arrangement as xpbd_step_kernel<L, EX>).
-template <int L, bool PF>
-__global__ void __launch_bounds__(32, 14) featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view sin, nb2_state_view sout,
-                                                                    nb2_control_view ctl, int use_contacts, int update_mass, float dt) {
+//
+// WARPS warps per CTA, each warp = 32/L environments, with CTA barriers at the phase boundaries (NB2_PHASE): not needed for
+// correctness - a sub-warp group owns its environment - they keep the CTA's warps on the same stretch of this ~9 000-instruction
+// kernel, so the instruction stream is fetched once per CTA instead of once per warp (measured on xpbd_step_kernel:
+// profiles/r2b_xpbd_ab.txt).
+#define NB2_PHASE()                       \
+    do {                                  \
+        if (WARPS > 1 && phase_sync) __syncthreads(); \
+    } while (0)
+template <int L, bool PF, int WARPS, bool TILE>
+__global__ void __launch_bounds__(32 * WARPS, (WARPS >= 14 ? 1 : 14 / WARPS))
+featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view sin, nb2_state_view sout, nb2_control_view ctl, int use_contacts,
+                         int update_mass, float dt, int phase_sync) {
     constexpr int G = 32 / L;
     extern __shared__ float smem[];
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane / L, l = lane % L;
-    const int env = blockIdx.x * G + grp;
+    const int env = (blockIdx.x * WARPS + warp) * G + grp;
     const bool live = env < M.env_count;
     // groups run different trip counts (articulations / dofs per env), so barriers cover one group only
     const unsigned gmask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << (grp * L));
     const nb2_model_desc& d = M.d;
-    const FsSmem sm = fs_carve(smem + size_t(grp) * fs_smem_floats(M), M);
+    const FsSmem sm = fs_carve(smem + size_t(warp * G + grp) * fs_smem_floats(M), M);
 
     int b0 = 0, nb = 0, j0 = 0, nj = 0, a0 = 0, na = 0, d0 = 0, nd = 0, c0 = 0, ncoord = 0, slot0 = 0, nc = 0;
     if (live) {
@@ -337,6 +436,7 @@ __global__ void __launch_bounds__(32, 14) featherstone_step_kernel(DevModel M, n
         o[0] = v_int.x; o[1] = v_int.y; o[2] = v_int.z; o[3] = omega.x; o[4] = omega.y; o[5] = omega.z;
     }
     __syncwarp(gmask);
+    NB2_PHASE();
     // ---- eval_rigid_id (RNEA forward).  Only v_s / a_s recur down the tree; everything else - motion subspaces S, joint
     // velocities v_j, bias terms, spatial inertias - needs the FK poses alone and runs for all joints at once. ---------------
     for (int j = l; j < nj; j += L) {  // A: per-joint quantities (v_j parked in vs[child], c_app in as[child])
@@ -452,6 +552,7 @@ __global__ void __launch_bounds__(32, 14) featherstone_step_kernel(DevModel M, n
         st6(sm.fb + 6 * child, f_b - f_g_s);
     }
     __syncwarp(gmask);
+    NB2_PHASE();
     // ---- eval_body_contact (penalty), ordered per body over the env's contacts ---------------------------
     if (use_contacts) {
         for (int b = l; b < nb; b += L) {
@@ -503,6 +604,7 @@ __global__ void __launch_bounds__(32, 14) featherstone_step_kernel(DevModel M, n
         }
         __syncwarp(gmask);
     }
+    NB2_PHASE();
     // ---- eval_rigid_tau (RNEA backward).  The drive / limit / damping terms do not depend on the force recursion: they are
     // evaluated for all dofs at once and parked in tau[]; the level loop only adds -S.f_s in the reference's order. ---------
     for (int j = l; j < nj; j += L) {
@@ -587,7 +689,28 @@ __global__ void __launch_bounds__(32, 14) featherstone_step_kernel(DevModel M, n
         }
         __syncwarp(gmask);
     }
+    NB2_PHASE();
     // ---- H = J^T M J + Cholesky, per articulation -----------------------------------------------------------------
+    if constexpr (TILE) {
+        if (update_mass) {  // tensor-core path: the whole warp forms the H of each of its environments' articulations in turn
+            __syncwarp();
+            const size_t stride = fs_smem_floats(M);
+            for (int g = 0; g < G; ++g) {
+                const int env_g = (blockIdx.x * WARPS + warp) * G + g;
+                if (env_g >= M.env_count) continue;  // warp-uniform
+                const FsSmem sg = fs_carve(smem + size_t(warp * G + g) * stride, M);
+                const int gj0 = M.env_joint_start[env_g], gb0 = M.env_body_start[env_g], gd0 = d.joint_qd_start[gj0];
+                for (int art = M.env_art_start[env_g]; art < M.env_art_start[env_g + 1]; ++art) {
+                    const int aj0 = d.articulation_start[art], aj1 = d.articulation_start[art + 1];
+                    const int ad0 = d.joint_qd_start[aj0], n = d.joint_qd_start[aj1] - ad0;
+                    // scratch: the v_s / a_s blocks (12 floats per body, dead until the closing FK rewrites them)
+                    tile_mass_matrix(sg.S + 6 * (ad0 - gd0), sg.Is + 36 * (aj0 - gb0), M.joint_anc_mask + aj0, M.dof_joint + ad0, aj1 - aj0, n,
+                                     sg.vs, sg.H + M.art_H_start[art]);
+                }
+            }
+            __syncwarp();
+        }
+    }
     for (int a = 0; a < na; ++a) {
         const int art = a0 + a;
         const int aj0 = d.articulation_start[art], aj1 = d.articulation_start[art + 1];
@@ -603,79 +726,49 @@ __global__ void __launch_bounds__(32, 14) featherstone_step_kernel(DevModel M, n
             //   stage 2  H[a, b] = sum_i sum_r S_a[r] P_i[r] over the bodies below joint(a), in (i, r) order, a >= b
             // - the summation order of the reference's dense_gemm pair (kernels.py:1504-1538) minus its exact-zero terms, so
             // the result is bit-identical while M J is formed once per column instead of once per entry.
-            int* jdof0 = reinterpret_cast<int*>(sm.fe);  // tables in the (now dead) external-force block: 3 ints per joint
-            int* jndof = jdof0 + anj;
-            int* jdepth = jndof + anj;
+            // The batch schedule is static topology: nb2_model_create tabulated, per batch, the column each body forms (hb_body_col)
+            // and the column each row sums (hb_row_col); the kernel only indexes.  P is double-buffered (second copy in the dead
+            // external-force block), so one group barrier per batch orders "P written" -> "P read" and the next batch's stage 1
+            // overlaps the slow lanes' stage 2.
+            if constexpr (!TILE) {
             for (int e = l; e < n * n; e += L) H[e] = 0.0f;
-            int my_maxdep = 0;
-            for (int i = l; i < anj; i += L) {
-                sm.anc[i] = M.joint_anc_mask[aj0 + i];
-                jdof0[i] = d.joint_qd_start[aj0 + i] - ad0;
-                jndof[i] = d.joint_qd_start[aj0 + i + 1] - d.joint_qd_start[aj0 + i];
-                jdepth[i] = M.joint_depth[aj0 + i];
-                my_maxdep = max(my_maxdep, jdepth[i]);
-                for (int k = 0; k < jndof[i]; ++k) sm.dofj[ad0 - d0 + jdof0[i] + k] = i;
-            }
-#pragma unroll
-            for (int o = L / 2; o > 0; o >>= 1) my_maxdep = max(my_maxdep, __shfl_xor_sync(gmask, my_maxdep, o, L));
+            const int nbatch = M.art_batch_count[art];
+            const signed char* body_col = M.hb_body_col + M.art_hb_body_start[art];
+            const signed char* row_col = M.hb_row_col + M.art_hb_row_start[art];
+            const signed char* dofj = M.dof_joint + ad0;
+            const float* Sart = sm.S + 6 * (ad0 - d0);
             __syncwarp(gmask);
-            // descendant-or-self sets (bit i = body i hangs below joint j): the bodies whose block of M J touches dof row a
-            for (int j = l; j < anj; j += L) {
-                unsigned long long m = 0ull;
-                for (int i = 0; i < anj; ++i) m |= ((sm.anc[i] >> j) & 1ull) << i;
-                sm.desc[j] = m;
-            }
-            __syncwarp(gmask);
-            const int* dofj = sm.dofj + (ad0 - d0);
-            for (int dep = 0; dep <= my_maxdep; ++dep) {
-                for (int kk = 0; kk < 6; ++kk) {
-                    // does any joint of this depth own a dof number kk?  (uniform across the group: same tables)
-                    bool any = false;
-                    for (int j = 0; j < anj && !any; ++j) any = jdepth[j] == dep && jndof[j] > kk;
-                    if (!any) break;  // dof counts only shrink the batch: no joint with > kk dofs => none with > kk+1
-                    for (int i = l; i < anj; i += L) {  // stage 1
-                        if (jdepth[i] < dep) continue;
-                        int jb = -1;  // ancestor-or-self of body i at depth dep
-                        for (unsigned long long m = sm.anc[i]; m; m &= m - 1ull) {
-                            const int a = __ffsll((long long)m) - 1;
-                            if (jdepth[a] == dep) jb = a;
-                        }
-                        if (jb < 0 || jndof[jb] <= kk) continue;
-                        const S6 Sb = ld6(sm.S + 6 * (ad0 - d0 + jdof0[jb] + kk));
-                        // NB: the reference's spatial_mass indexes body_I_s by JOINT index (kernels.py:1476-1477)
-                        const float* Is = sm.Is + 36 * (aj0 + i - b0);
+            for (int t = 0; t < nbatch; ++t) {
+                float* Pb = (t & 1) ? sm.fe : sm.P;
+                for (int i = l; i < anj; i += L) {  // stage 1: P_i = I_i S_col for the bodies below the batch's joints
+                    const int col = body_col[t * anj + i];
+                    if (col < 0) continue;
+                    const S6 Sb = ld6(Sart + 6 * col);
+                    // NB: the reference's spatial_mass indexes body_I_s by JOINT index (kernels.py:1476-1477)
+                    const float* Is = sm.Is + 36 * (aj0 + i - b0);
 #pragma unroll
-                        for (int r = 0; r < 6; ++r) {
-                            float pr = 0.0f;  // P[6i+r, b] = sum_k M[6i+r, 6i+k] J[6i+k, b]
+                    for (int r = 0; r < 6; ++r) {
+                        float pr = 0.0f;  // P[6i+r, b] = sum_k M[6i+r, 6i+k] J[6i+k, b]
 #pragma unroll
-                            for (int k = 0; k < 6; ++k) pr += Is[6 * r + k] * Sb.v[k];
-                            sm.P[6 * i + r] = pr;
-                        }
+                        for (int k = 0; k < 6; ++k) pr += Is[6 * r + k] * Sb.v[k];
+                        Pb[6 * i + r] = pr;
                     }
-                    __syncwarp(gmask);
-                    for (int ra = l; ra < n; ra += L) {  // stage 2
-                        const int ja = dofj[ra];
-                        if (jdepth[ja] < dep) continue;
-                        int jb = -1;
-                        for (unsigned long long m = sm.anc[ja]; m; m &= m - 1ull) {
-                            const int a = __ffsll((long long)m) - 1;
-                            if (jdepth[a] == dep) jb = a;
-                        }
-                        if (jb < 0 || jndof[jb] <= kk) continue;
-                        const int cbb = jdof0[jb] + kk;
-                        if (ra < cbb) continue;  // upper triangle (only possible inside joint(b) itself)
-                        const S6 Sa = ld6(sm.S + 6 * (ad0 - d0 + ra));
-                        float sum = 0.0f;
-                        for (unsigned long long m = sm.desc[ja]; m; m &= m - 1ull) {  // ascending body order
-                            const int i = __ffsll((long long)m) - 1;
+                }
+                __syncwarp(gmask);
+                for (int ra = l; ra < n; ra += L) {  // stage 2: H[ra, col] over the bodies below joint(ra), ascending
+                    const int col = row_col[t * n + ra];
+                    if (col < 0) continue;
+                    const S6 Sa = ld6(Sart + 6 * ra);
+                    float sum = 0.0f;
+                    for (unsigned long long m = M.joint_desc_mask[aj0 + dofj[ra]]; m; m &= m - 1ull) {
+                        const int i = __ffsll((long long)m) - 1;
 #pragma unroll
-                            for (int r = 0; r < 6; ++r) sum += Sa.v[r] * sm.P[6 * i + r];
-                        }
-                        H[ra * n + cbb] = sum;
+                        for (int r = 0; r < 6; ++r) sum += Sa.v[r] * Pb[6 * i + r];
                     }
-                    __syncwarp(gmask);
+                    H[ra * n + col] = sum;
                 }
             }
+            }  // !TILE
             __syncwarp(gmask);
             // dense_cholesky (kernels.py:1690-1719), in place on the lower triangle; columns in order, rows in parallel
             for (int jn = 0; jn < n; ++jn) {
@@ -725,6 +818,7 @@ __global__ void __launch_bounds__(32, 14) featherstone_step_kernel(DevModel M, n
         }
         __syncwarp(gmask);
     }
+    NB2_PHASE();
     // ---- integrate_generalized_joints (jcalc_integrate, kernels.py:464-630) ----------------------------------------
     for (int j = l; j < nj; j += L) {
         const int gj = j0 + j, type = d.joint_type[gj], parent = d.joint_parent[gj], child = d.joint_child[gj];
@@ -790,6 +884,7 @@ __global__ void __launch_bounds__(32, 14) featherstone_step_kernel(DevModel M, n
     }
     __syncwarp(gmask);
     for (int i = l; i < ncoord; i += L) sout.joint_q[c0 + i] = sm.jq[i];
+    NB2_PHASE();
     // ---- eval_fk_with_velocity_conversion: level-parallel; reuses bq (poses) and vs (COM twists) ------------------------
     for (int lvl = 0; lvl <= M.max_depth; ++lvl) {
         for (int j = l; j < nj; j += L) {
@@ -875,25 +970,63 @@ __global__ void __launch_bounds__(32, 14) featherstone_step_kernel(DevModel M, n
     }
 }
 
+template <int L, bool PF, int WARPS, bool TILE>
+static nb2_status launch_fs_W(nb2_model* m, const nb2_featherstone_params& p, const nb2_state_view& in, const nb2_state_view& out,
+                              const nb2_control_view& ctl, int use_contacts, int update_mass, float dt, cudaStream_t s) {
+    const DevModel& M = m->dev;
+    constexpr int NE = (32 / L) * WARPS;
+    const int blocks = (M.env_count + NE - 1) / NE;
+    const size_t smem = fs_smem_floats(M) * NE * sizeof(float);
+    if (smem > 48 * 1024)
+        NB2_CUDA_CHECK(cudaFuncSetAttribute(featherstone_step_kernel<L, PF, WARPS, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    NB2_CUDA_CHECK(cudaFuncSetAttribute(featherstone_step_kernel<L, PF, WARPS, TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    static const int phase_sync = std::getenv("NB2_FS_PHASE_SYNC") ? std::atoi(std::getenv("NB2_FS_PHASE_SYNC")) : 1;
+    featherstone_step_kernel<L, PF, WARPS, TILE><<<blocks, 32 * WARPS, smem, s>>>(M, p, in, out, ctl, use_contacts, update_mass, dt, phase_sync);
+    count_launch();
+    NB2_CUDA_CHECK(cudaGetLastError());
+    return NB2_OK;
+}
+
+// warps per CTA: the largest compiled width the batch fills on every SM (see launch_xpbd_L), shared memory permitting
 template <int L, bool PF>
 static nb2_status launch_fs_LP(nb2_model* m, const nb2_featherstone_params& p, const nb2_state_view& in, const nb2_state_view& out,
                               const nb2_control_view& ctl, int use_contacts, int update_mass, float dt, cudaStream_t s) {
     const DevModel& M = m->dev;
-    const int G = 32 / L;
-    const int blocks = (M.env_count + G - 1) / G;
-    const size_t per_env = fs_smem_floats(M);
-    const size_t smem = per_env * G * sizeof(float);
-    if (smem > 220 * 1024) {
+    const size_t per_env = fs_smem_floats(M) * sizeof(float) * (32 / L);  // per warp
+    if (per_env > 220 * 1024) {
         set_error("featherstone_step: environment too large for the fused shared-memory kernel");
         return NB2_ERR_CAPACITY;
     }
-    if (smem > 48 * 1024)
-        NB2_CUDA_CHECK(cudaFuncSetAttribute(featherstone_step_kernel<L, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    NB2_CUDA_CHECK(cudaFuncSetAttribute(featherstone_step_kernel<L, PF>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    featherstone_step_kernel<L, PF><<<blocks, 32, smem, s>>>(M, p, in, out, ctl, use_contacts, update_mass, dt);
-    count_launch();
-    NB2_CUDA_CHECK(cudaGetLastError());
-    return NB2_OK;
+    static const int forced = std::getenv("NB2_FS_WARPS") ? std::atoi(std::getenv("NB2_FS_WARPS")) : 0;
+    int warps = forced;
+    if (warps <= 0) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+        const long long total_warps = (M.env_count + (32 / L) - 1) / (32 / L);
+        const long long per_sm = (total_warps + sms - 1) / sms;
+        warps = per_sm <= 1 ? 1 : (per_sm <= 4 ? 4 : 14);
+    }
+    if (warps >= 14 && per_env * 14 > 220 * 1024) warps = 4;
+    if (warps >= 4 && warps < 14 && per_env * 4 > 220 * 1024) warps = 1;
+    if (p.use_tile_gemm) {
+        // the tensor-core variant is compiled for the plain step of the 16- and 32-lane layouts (what use_tile_gemm targets upstream:
+        // one 18-dof articulation per world); anything else is refused instead of silently taking the FP32 path
+        if constexpr (!PF && (L == 16 || L == 32)) {
+            if (M.max_env_dofs > 24 || 12 * M.max_env_bodies < 6 * 24 || m->host.max_art_dofs > 24) {
+                set_error("nb2_featherstone_step: use_tile_gemm needs articulations of at most 24 dofs (and >= 12 bodies of scratch per env)");
+                return NB2_ERR_UNSUPPORTED;
+            }
+            if (warps >= 14) return launch_fs_W<L, PF, 14, true>(m, p, in, out, ctl, use_contacts, update_mass, dt, s);
+            if (warps >= 4) return launch_fs_W<L, PF, 4, true>(m, p, in, out, ctl, use_contacts, update_mass, dt, s);
+            return launch_fs_W<L, PF, 1, true>(m, p, in, out, ctl, use_contacts, update_mass, dt, s);
+        } else {
+            set_error("nb2_featherstone_step: use_tile_gemm is available for the plain step (no body_parent_f) of 16 / 32-lane layouts");
+            return NB2_ERR_UNSUPPORTED;
+        }
+    }
+    if (warps >= 14) return launch_fs_W<L, PF, 14, false>(m, p, in, out, ctl, use_contacts, update_mass, dt, s);
+    if (warps >= 4) return launch_fs_W<L, PF, 4, false>(m, p, in, out, ctl, use_contacts, update_mass, dt, s);
+    return launch_fs_W<L, PF, 1, false>(m, p, in, out, ctl, use_contacts, update_mass, dt, s);
 }
 
 template <int L>
@@ -919,10 +1052,8 @@ nb2_status launch_featherstone_step(nb2_model* m, const nb2_featherstone_params&
         set_error("nb2_featherstone_step: state / control arrays are NULL");
         return NB2_ERR_INVALID_ARGUMENT;
     }
-    if (in.joint_q == out.joint_q) {
-        set_error("nb2_featherstone_step: state_in must not alias state_out (in-place stepping is not implemented)");
-        return NB2_ERR_UNSUPPORTED;
-    }
+    // state_in may be state_out (reference solver_featherstone.py:472): every group finishes reading its environment's inputs
+    // (joint_q in the integration pass is the last) before it writes the outputs, and no group touches another environment.
     const int interval = p.update_mass_matrix_interval > 0 ? p.update_mass_matrix_interval : 1;
     const int update_mass = (m->featherstone_step_count % interval) == 0;
     m->featherstone_step_count += 1;

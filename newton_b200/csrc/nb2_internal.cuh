@@ -55,6 +55,16 @@ struct DevModel {
     const int* env_H_start;            // [E+1] global offset of the env's H/L storage (persistent L for update intervals)
     float* fs_L;                       // persistent Cholesky factors [env_H_start[E]]
     int max_depth, max_env_dofs, max_env_coords, max_env_H, max_env_arts;
+    // H = J^T M J schedule, derived from the joint tree at nb2_model_create (the kernel indexes, it does not walk bit masks):
+    // columns of H are formed in batches of (tree depth, dof number inside the joint) - joints of one batch are never ancestors of
+    // one another, so every body and every row sees at most one column per batch
+    const int* art_batch_count;        // [A]   batches of the articulation
+    const int* art_hb_body_start;      // [A]   offset into hb_body_col: batch-major, anj entries per batch
+    const int* art_hb_row_start;       // [A]   offset into hb_row_col: batch-major, n (dofs) entries per batch
+    const signed char* hb_body_col;    // articulation-local dof (column) whose P_i = I_i S_col body i forms in this batch, or -1
+    const signed char* hb_row_col;     // column whose entry H[row, col] row `row` sums in this batch (col <= row), or -1
+    const unsigned long long* joint_desc_mask;  // [J] bit i set <=> articulation-local body i hangs below (or is driven by) joint j
+    const signed char* dof_joint;      // [D] articulation-local joint owning each dof
     // XPBD reporting scratch (row a17): weighted contact impulses (6 planes of slot_total) and per-joint child-side impulses
     float* contact_impulse;
     float* joint_impulse;  // [6 * joint_count]
@@ -68,7 +78,10 @@ struct HostTables {
     std::vector<int2> pairs;
     std::vector<int> body_joint_start, body_joint_entry;
     std::vector<int> joint_depth, art_H_start, env_H_start;
-    std::vector<unsigned long long> joint_anc_mask;
+    std::vector<unsigned long long> joint_anc_mask, joint_desc_mask;
+    std::vector<int> art_batch_count, art_hb_body_start, art_hb_row_start;
+    std::vector<signed char> hb_body_col, hb_row_col, dof_joint;
+    int max_art_dofs = 0;  // largest articulation (dofs)
     bool featherstone_supported = true;
     bool ik_supported = true;  // false when a D6 joint has 2-3 angular axes
     bool fk_levels = true;     // eval_fk may schedule joints by tree depth (parent-before-child order, one driving joint per body)

@@ -31,6 +31,9 @@ enum { BODY_KINEMATIC = 2 };
 enum { BR_Q = 0, BR_QD = 7, BR_COM = 13, BR_INVM = 16, BR_INVI = 17, BR_I = 26, BR_SIZE = 35 };
 enum { DR_SIZE = 13 };  // delta record: lin_a, ang_a, lin_b, ang_b, active
 enum { XF_JOINT_CACHE = 1, XF_TMA = 2, XF_PHASE_SYNC = 4, XF_PHASE_SYNC_FINE = 8 };  // kernel flags
+// per-contact constants of the Jacobi loop, staged once per substep: point0, point1, normal, margin0 + margin1, the three friction
+// coefficients and the friction anchors point + offset (odd stride: lanes = consecutive contacts)
+enum { CC_P0 = 0, CC_P1 = 3, CC_N = 6, CC_MSUM = 9, CC_MU = 10, CC_MUT = 11, CC_MUR = 12, CC_Q0 = 13, CC_Q1 = 16, CC_SIZE = 19 };
 
 // Code-size control.  The first kernel version inlined and unrolled everything: 9 400 SASS instructions (150 KB) and
 // 19 % of the stall samples on instruction fetch (profiles/r1a_xpbd_step_kernel.txt).  Measured on B200 (round-1c A/B,
@@ -489,17 +492,18 @@ NB2_GPU void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" 
 
 // Shared-memory plan of one CTA (NE environments), in floats.  Identical on host and device.
 struct XpbdPlan {
-    int bodies, jcache, cpair, extra, drec, mbar, total;  // offsets of the per-CTA regions
+    int bodies, jcache, cpair, ccache, extra, drec, mbar, total;  // offsets of the per-CTA regions
     int rec_cap;                                           // delta records per env; the region doubles as the TMA staging area
 };
-__host__ __device__ inline XpbdPlan xpbd_plan(int NE, int MB, int MJ, int CC, bool ex, bool joint_cache) {
+__host__ __device__ inline XpbdPlan xpbd_plan(int NE, int MB, int MJ, int CC, bool ex, bool joint_cache, int contact_cache = 0) {
     XpbdPlan o;
     auto up4 = [](int x) { return (x + 3) & ~3; };
     o.rec_cap = MB > MJ ? (MB > CC ? MB : CC) : (MJ > CC ? MJ : CC);
     o.bodies = 0;
     o.jcache = up4(o.bodies + NE * MB * BR_SIZE);
     o.cpair = up4(o.jcache + (joint_cache ? NE * MJ * JC_SIZE : 0));
-    o.extra = up4(o.cpair + NE * CC);
+    o.ccache = up4(o.cpair + NE * CC);
+    o.extra = up4(o.ccache + NE * contact_cache * CC_SIZE);
     o.drec = up4(o.extra + (ex ? NE * MB * 14 : 0));
     o.mbar = up4(o.drec + NE * o.rec_cap * DR_SIZE);
     o.total = o.mbar + 4;
@@ -521,7 +525,7 @@ enum { ST_Q = 0, ST_QD = 7, ST_COM = 13, ST_INVM = 16, ST_I = 17, ST_INVI = 26, 
 template <int L, bool EX, int WARPS>
 __global__ void __launch_bounds__(32 * WARPS, (WARPS >= NB2_XPBD_MIN_WARPS ? 1 : NB2_XPBD_MIN_WARPS / WARPS))
 xpbd_step_kernel(DevModel M, nb2_xpbd_params P, nb2_state_view sin, nb2_state_view sout, nb2_control_view ctl, int use_contacts_flags,
-                 float dt, int flags, int contact_cap) {
+                 float dt, int flags, int contact_cap, int contact_cache) {
     const int use_contacts = use_contacts_flags & NB2_XPBD_USE_CONTACTS;
     const bool want_cimp = EX && use_contacts && (use_contacts_flags & NB2_XPBD_CONTACT_IMPULSE);
     const bool want_jimp = EX && sout.body_parent_f != nullptr;
@@ -537,7 +541,8 @@ xpbd_step_kernel(DevModel M, nb2_xpbd_params P, nb2_state_view sin, nb2_state_vi
     const int env = env0 + slot;
     const bool live = env < M.env_count;
     const nb2_model_desc& d = M.d;
-    const XpbdPlan plan = xpbd_plan(NE, M.max_env_bodies, M.max_env_joints, contact_cap, EX, joint_cache);
+    const XpbdPlan plan = xpbd_plan(NE, M.max_env_bodies, M.max_env_joints, contact_cap, EX, joint_cache, contact_cache);
+    float* ccache = smem + plan.ccache + slot * contact_cache * CC_SIZE;  // first `contact_cache` contacts of the environment
     float* bodies = smem + plan.bodies + slot * M.max_env_bodies * BR_SIZE;
     float* drec = smem + plan.drec + slot * plan.rec_cap * DR_SIZE;
     int* cpair = reinterpret_cast<int*>(smem + plan.cpair) + slot * contact_cap;
@@ -585,7 +590,27 @@ xpbd_step_kernel(DevModel M, nb2_xpbd_params P, nb2_state_view sin, nb2_state_vi
     for (int c = l; c < nc; c += L) {
         const size_t T = size_t(M.slot_total);
         int ba = __float_as_int(M.cb[CF_BODY_A * T + slot0 + c]), bb = __float_as_int(M.cb[CF_BODY_B * T + slot0 + c]);
-        cpair[c] = (ba & 0xffff) | (bb << 16);
+        // packed incidence: 15-bit body index + 1 per side (0 = the static world) and the body's KINEMATIC flag, so the
+        // iteration loop never goes back to global memory for them
+        const unsigned ka = ba >= 0 && (d.body_flags[b0 + ba] & BODY_KINEMATIC) != 0, kb = bb >= 0 && (d.body_flags[b0 + bb] & BODY_KINEMATIC) != 0;
+        cpair[c] = int(unsigned(ba + 1) | (ka << 15) | (unsigned(bb + 1) << 16) | (kb << 31));
+        if (c < contact_cache) {
+            const int s = slot0 + c;
+            float* cc = ccache + c * CC_SIZE;
+            const V3 p0(M.cb[CF_P0X * T + s], M.cb[CF_P0Y * T + s], M.cb[CF_P0Z * T + s]);
+            const V3 p1(M.cb[CF_P1X * T + s], M.cb[CF_P1Y * T + s], M.cb[CF_P1Z * T + s]);
+            const V3 o0(M.cb[CF_O0X * T + s], M.cb[CF_O0Y * T + s], M.cb[CF_O0Z * T + s]);
+            const V3 o1(M.cb[CF_O1X * T + s], M.cb[CF_O1Y * T + s], M.cb[CF_O1Z * T + s]);
+            st3(cc + CC_P0, p0);
+            st3(cc + CC_P1, p1);
+            st3(cc + CC_N, V3(M.cb[CF_NX * T + s], M.cb[CF_NY * T + s], M.cb[CF_NZ * T + s]));
+            cc[CC_MSUM] = M.cb[CF_MARGIN0 * T + s] + M.cb[CF_MARGIN1 * T + s];
+            cc[CC_MU] = M.cb[CF_MU * T + s];
+            cc[CC_MUT] = M.cb[CF_MU_TORSIONAL * T + s];
+            cc[CC_MUR] = M.cb[CF_MU_ROLLING * T + s];
+            st3(cc + CC_Q0, p0 + o0);
+            st3(cc + CC_Q1, p1 + o1);
+        }
         if (want_cimp)
 #pragma unroll
             for (int k = 0; k < 6; ++k) M.contact_impulse[k * T + slot0 + c] = 0.0f;
@@ -653,7 +678,7 @@ xpbd_step_kernel(DevModel M, nb2_xpbd_params P, nb2_state_view sin, nb2_state_vi
     if (use_masks && l < nb)
         for (int c = 0; c < nc; ++c) {
             const int pr = cpair[c];
-            const int ba = int(short(pr & 0xffff)), bb = pr >> 16;
+            const int ba = int(unsigned(pr) & 0x7fffu) - 1, bb = int((unsigned(pr) >> 16) & 0x7fffu) - 1;
             if (ba == bb) continue;  // the contact pass writes an inactive record
             if (ba == l) mask_a |= 1ull << c;
             if (bb == l) mask_b |= 1ull << c;
@@ -723,7 +748,7 @@ xpbd_step_kernel(DevModel M, nb2_xpbd_params P, nb2_state_view sin, nb2_state_vi
             for (int c = l; c < nc; c += L) {
                 const int s = slot0 + c;
                 const int pr = cpair[c];
-                const int ba = int(short(pr & 0xffff)), bb = pr >> 16;
+                const int ba = int(unsigned(pr) & 0x7fffu) - 1, bb = int((unsigned(pr) >> 16) & 0x7fffu) - 1;
                 Deltas dl;
                 float active = 0.0f;
                 if (ba != bb) {
@@ -732,14 +757,17 @@ xpbd_step_kernel(DevModel M, nb2_xpbd_params P, nb2_state_view sin, nb2_state_vi
                     const bool need_a = ba >= 0 || want_cimp, need_b = bb >= 0 || want_cimp;
                     BodyView A = ba >= 0 ? load_body(bodies + ba * BR_SIZE) : static_body();
                     BodyView B = bb >= 0 ? load_body(bodies + bb * BR_SIZE) : static_body();
-                    const V3 p0(cb[CF_P0X * T + s], cb[CF_P0Y * T + s], cb[CF_P0Z * T + s]);
-                    const V3 p1(cb[CF_P1X * T + s], cb[CF_P1Y * T + s], cb[CF_P1Z * T + s]);
-                    const V3 n(cb[CF_NX * T + s], cb[CF_NY * T + s], cb[CF_NZ * T + s]);
+                    const bool cached = c < contact_cache;
+                    const float* cc = ccache + c * CC_SIZE;
+                    const V3 p0 = cached ? ld3(cc + CC_P0) : V3(cb[CF_P0X * T + s], cb[CF_P0Y * T + s], cb[CF_P0Z * T + s]);
+                    const V3 p1 = cached ? ld3(cc + CC_P1) : V3(cb[CF_P1X * T + s], cb[CF_P1Y * T + s], cb[CF_P1Z * T + s]);
+                    const V3 n = cached ? ld3(cc + CC_N) : V3(cb[CF_NX * T + s], cb[CF_NY * T + s], cb[CF_NZ * T + s]);
                     V3 bx_a = ba >= 0 ? xpoint(A.X, p0) : V3() + p0, bx_b = bb >= 0 ? xpoint(B.X, p1) : V3() + p1;
-                    const float dpen = dot(n, bx_b - bx_a) - (cb[CF_MARGIN0 * T + s] + cb[CF_MARGIN1 * T + s]);
+                    const float dpen = dot(n, bx_b - bx_a) - (cached ? cc[CC_MSUM] : cb[CF_MARGIN0 * T + s] + cb[CF_MARGIN1 * T + s]);
                     if (dpen < 0.0f) {
                         active = 1.0f;
-                        const float mu = cb[CF_MU * T + s], mu_t = cb[CF_MU_TORSIONAL * T + s], mu_r = cb[CF_MU_ROLLING * T + s];
+                        const float mu = cached ? cc[CC_MU] : cb[CF_MU * T + s], mu_t = cached ? cc[CC_MUT] : cb[CF_MU_TORSIONAL * T + s],
+                                    mu_r = cached ? cc[CC_MUR] : cb[CF_MU_ROLLING * T + s];
                         const V3 wcom_a = ba >= 0 ? xpoint(A.X, A.com) : V3(), wcom_b = bb >= 0 ? xpoint(B.X, B.com) : V3();
                         V3 r_a = bx_a - wcom_a, r_b = bx_b - wcom_b;
                         V3 ang_a, ang_b;
@@ -750,20 +778,26 @@ xpbd_step_kernel(DevModel M, nb2_xpbd_params P, nb2_state_view sin, nb2_state_vi
                         if (need_a) { lin_da = -n * lambda_n; ang_da = ang_a * lambda_n; }
                         if (need_b) { lin_db = n * lambda_n; ang_db = ang_b * lambda_n; }
                         if (mu > 0.0f) {
-                            const V3 o0(cb[CF_O0X * T + s], cb[CF_O0Y * T + s], cb[CF_O0Z * T + s]);
-                            const V3 o1(cb[CF_O1X * T + s], cb[CF_O1Y * T + s], cb[CF_O1Z * T + s]);
-                            bx_a = ba >= 0 ? xpoint(A.X, p0 + o0) : V3() + (p0 + o0);
-                            bx_b = bb >= 0 ? xpoint(B.X, p1 + o1) : V3() + (p1 + o1);
+                            V3 q0, q1;  // contact_surface_point: point + offset
+                            if (cached) {
+                                q0 = ld3(cc + CC_Q0);
+                                q1 = ld3(cc + CC_Q1);
+                            } else {
+                                q0 = p0 + V3(cb[CF_O0X * T + s], cb[CF_O0Y * T + s], cb[CF_O0Z * T + s]);
+                                q1 = p1 + V3(cb[CF_O1X * T + s], cb[CF_O1Y * T + s], cb[CF_O1Z * T + s]);
+                            }
+                            bx_a = ba >= 0 ? xpoint(A.X, q0) : V3() + q0;
+                            bx_b = bb >= 0 ? xpoint(B.X, q1) : V3() + q1;
                             V3 delta = bx_b - bx_a;
                             V3 fd = delta - dot(n, delta) * n;
                             r_a = bx_a - wcom_a;
                             r_b = bx_b - wcom_b;
                             V3 rel_v_kin;
-                            if (ba >= 0 && (d.body_flags[b0 + ba] & BODY_KINEMATIC) != 0) {
+                            if (unsigned(pr) & 0x8000u) {  // body A is kinematic
                                 V3 v_a = cross(A.w, r_a) + A.v;
                                 rel_v_kin = rel_v_kin - (v_a - dot(n, v_a) * n);
                             }
-                            if (bb >= 0 && (d.body_flags[b0 + bb] & BODY_KINEMATIC) != 0) {
+                            if (unsigned(pr) & 0x80000000u) {  // body B is kinematic
                                 V3 v_b = cross(B.w, r_b) + B.v;
                                 rel_v_kin = rel_v_kin + (v_b - dot(n, v_b) * n);
                             }
@@ -827,7 +861,7 @@ xpbd_step_kernel(DevModel M, nb2_xpbd_params P, nb2_state_view sin, nb2_state_vi
                 } else {
                     for (int c = 0; c < nc; ++c) {
                         const int pr = cpair[c];
-                        const int ba = int(short(pr & 0xffff)), bb = pr >> 16;
+                        const int ba = int(unsigned(pr) & 0x7fffu) - 1, bb = int((unsigned(pr) >> 16) & 0x7fffu) - 1;
                         if (ba != b && bb != b) continue;
                         const float* r = drec + c * DR_SIZE;
                         if (r[12] == 0.0f) continue;
@@ -844,7 +878,7 @@ xpbd_step_kernel(DevModel M, nb2_xpbd_params P, nb2_state_view sin, nb2_state_vi
                     const float* r = drec + c * DR_SIZE;
                     if (r[12] == 0.0f) continue;  // inactive this iteration: the reference adds an exact zero
                     const int pr = cpair[c];
-                    const int ba = int(short(pr & 0xffff)), bb = pr >> 16;
+                    const int ba = int(unsigned(pr) & 0x7fffu) - 1, bb = int((unsigned(pr) >> 16) & 0x7fffu) - 1;
                     float weight = 1.0f;
                     if (P.rigid_contact_con_weighting) {
                         const float n_a = ba >= 0 ? bcnt[ba] : 0.0f, n_b = bb >= 0 ? bcnt[bb] : 0.0f;
@@ -936,7 +970,7 @@ xpbd_step_kernel(DevModel M, nb2_xpbd_params P, nb2_state_view sin, nb2_state_vi
             for (int c = l; c < nc; c += L) {
                 const int s = slot0 + c;
                 const int pr = cpair[c];
-                const int ba = int(short(pr & 0xffff)), bb = pr >> 16;
+                const int ba = int(unsigned(pr) & 0x7fffu) - 1, bb = int((unsigned(pr) >> 16) & 0x7fffu) - 1;
                 Deltas dl;
                 float active = 0.0f;
                 if (ba != bb) {
@@ -1004,7 +1038,7 @@ xpbd_step_kernel(DevModel M, nb2_xpbd_params P, nb2_state_view sin, nb2_state_vi
                 V3 dlin, dang;
                 for (int c = 0; c < nc; ++c) {
                     const int pr = cpair[c];
-                    const int ba = int(short(pr & 0xffff)), bb = pr >> 16;
+                    const int ba = int(unsigned(pr) & 0x7fffu) - 1, bb = int((unsigned(pr) >> 16) & 0x7fffu) - 1;
                     if (ba != b && bb != b) continue;
                     const float* r = drec + c * DR_SIZE;
                     if (r[12] == 0.0f) continue;
@@ -1119,7 +1153,7 @@ static nb2_status launch_xpbd_W(nb2_model* m, const nb2_xpbd_params& p, const nb
     // Budget: the CTAs of one SM share 227 KB (+1 KB reserved each); the batch wants >= ceil(envs / (G * 148)) resident warps per SM to
     // stay a single wave.  The per-joint cache rides along when it does not cost that residency.
     static const bool cache_enabled = std::getenv("NB2_XPBD_NO_JOINT_CACHE") == nullptr;  // A/B switch (profiles/r1f_xpbd_ab.txt)
-    static const int tma_enabled = env_int("NB2_XPBD_TMA", 1), phase_sync = env_int("NB2_XPBD_PHASE_SYNC", 0);
+    static const int tma_enabled = env_int("NB2_XPBD_TMA", 1), phase_sync = env_int("NB2_XPBD_PHASE_SYNC", 1);
     int flags = (tma_enabled ? XF_TMA : 0) | (phase_sync >= 1 ? XF_PHASE_SYNC : 0) | (phase_sync >= 2 ? XF_PHASE_SYNC_FINE : 0);
     XpbdPlan plan = xpbd_plan(NE, M.max_env_bodies, M.max_env_joints, contact_cap, EX, false);
     if (cache_enabled && M.d.joint_count > 0) {
@@ -1132,8 +1166,21 @@ static nb2_status launch_xpbd_W(nb2_model* m, const nb2_xpbd_params& p, const nb
             }
         }
     }
+    // contact-constant cache: as many contacts per env as still fit (up to the contact bound), keeping the residency above
+    int contact_cache = 0;
+    {
+        static const int cc_enabled = env_int("NB2_XPBD_CONTACT_CACHE", 1);
+        const int want_ctas = (14 + WARPS - 1) / WARPS;
+        const size_t budget = (size_t(227) * 1024) / want_ctas - 1024 - 64;
+        const size_t base = size_t(plan.total) * sizeof(float);
+        if (cc_enabled && use_contacts && base < budget) {
+            contact_cache = int(std::min<size_t>((budget - base) / (size_t(NE) * CC_SIZE * sizeof(float)), size_t(contact_cap)));
+            if (contact_cache > 0)
+                plan = xpbd_plan(NE, M.max_env_bodies, M.max_env_joints, contact_cap, EX, (flags & XF_JOINT_CACHE) != 0, contact_cache);
+        }
+    }
     const size_t smem = size_t(plan.total) * sizeof(float);
-    if (smem > 220 * 1024) {
+    if (smem > 220 * 1024 + 6 * 1024) {
         set_error("xpbd_step: environment too large for the fused shared-memory kernel (bodies/contacts per env)");
         return NB2_ERR_CAPACITY;
     }
@@ -1142,33 +1189,45 @@ static nb2_status launch_xpbd_W(nb2_model* m, const nb2_xpbd_params& p, const nb
     // ask for the largest shared-memory carve-out so that ~14-16 warps' worth of CTAs fit per SM
     static const int carveout = std::getenv("NB2_XPBD_CARVEOUT") ? std::atoi(std::getenv("NB2_XPBD_CARVEOUT")) : int(cudaSharedmemCarveoutMaxShared);
     NB2_CUDA_CHECK(cudaFuncSetAttribute(xpbd_step_kernel<L, EX, WARPS>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
-    xpbd_step_kernel<L, EX, WARPS><<<blocks, 32 * WARPS, smem, s>>>(M, p, in, out, ctl, use_contacts, dt, flags, contact_cap);
+    xpbd_step_kernel<L, EX, WARPS><<<blocks, 32 * WARPS, smem, s>>>(M, p, in, out, ctl, use_contacts, dt, flags, contact_cap, contact_cache);
     count_launch();
     NB2_CUDA_CHECK(cudaGetLastError());
     return NB2_OK;
 }
 
-// warps per CTA: the A/B variants are compiled only for the plain step of the 16-lane layout (the benchmark configuration)
-#ifndef NB2_XPBD_WARPS_DEFAULT
-#define NB2_XPBD_WARPS_DEFAULT 2
-#endif
+// Warps per CTA.  Measured on B200 (profiles/r2b_xpbd_ab.txt, 4096 quadruped envs): 1 / 2 / 4 warps 166 us, 7 warps 160 us,
+// 14 warps 155 us, and 148 us with the per-iteration CTA barrier - the more warps walk the same code together, the fewer times the
+// instruction stream is fetched.  The launch takes the largest compiled width that the batch can fill on every SM
+// (14 = one CTA per SM for 4096 two-env warps), falls back when shared memory does not allow it, and honours NB2_XPBD_WARPS.
 template <int L, bool EX>
 static nb2_status launch_xpbd_L(nb2_model* m, const nb2_xpbd_params& p, const nb2_state_view& in, const nb2_state_view& out,
                                 const nb2_control_view& ctl, int use_contacts, float dt, cudaStream_t s) {
-    static const int warps = env_int("NB2_XPBD_WARPS", NB2_XPBD_WARPS_DEFAULT);
+    static const int forced = env_int("NB2_XPBD_WARPS", 0);
+    int warps = forced;
+    if (warps <= 0) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+        const long long total_warps = (m->dev.env_count + (32 / L) - 1) / (32 / L);
+        const long long per_sm = (total_warps + sms - 1) / sms;
+        warps = per_sm <= 1 ? 1 : (per_sm <= 4 ? 4 : 14);
+    }
+    // shared-memory fit (the per-CTA plan grows with the warp count)
+    auto fits = [&](int w) {
+        const int ne = (32 / L) * w;
+        const int cap = m->contacts_imported ? m->dev.max_env_contact_slots : std::min(m->dev.max_env_contact_slots, m->max_env_contacts);
+        return size_t(xpbd_plan(ne, m->dev.max_env_bodies, m->dev.max_env_joints, cap, EX, false).total) * sizeof(float) <= 200 * 1024;
+    };
+    if (warps >= 14 && !fits(14)) warps = 4;
+    if (warps >= 4 && warps < 14 && !fits(4)) warps = 1;
 #ifdef NB2_XPBD_AB_VARIANTS
     if constexpr (L == 16 && !EX) {
-        switch (warps) {
-            case 1: return launch_xpbd_W<L, EX, 1>(m, p, in, out, ctl, use_contacts, dt, s);
-            case 4: return launch_xpbd_W<L, EX, 4>(m, p, in, out, ctl, use_contacts, dt, s);
-            case 7: return launch_xpbd_W<L, EX, 7>(m, p, in, out, ctl, use_contacts, dt, s);
-            case 14: return launch_xpbd_W<L, EX, 14>(m, p, in, out, ctl, use_contacts, dt, s);
-            default: break;
-        }
+        if (warps == 2) return launch_xpbd_W<L, EX, 2>(m, p, in, out, ctl, use_contacts, dt, s);
+        if (warps == 7) return launch_xpbd_W<L, EX, 7>(m, p, in, out, ctl, use_contacts, dt, s);
     }
 #endif
-    (void)warps;
-    return launch_xpbd_W<L, EX, NB2_XPBD_WARPS_DEFAULT>(m, p, in, out, ctl, use_contacts, dt, s);
+    if (warps >= 14) return launch_xpbd_W<L, EX, 14>(m, p, in, out, ctl, use_contacts, dt, s);
+    if (warps >= 4) return launch_xpbd_W<L, EX, 4>(m, p, in, out, ctl, use_contacts, dt, s);
+    return launch_xpbd_W<L, EX, 1>(m, p, in, out, ctl, use_contacts, dt, s);
 }
 
 nb2_status launch_xpbd_step(nb2_model* m, const nb2_xpbd_params& p, const nb2_state_view& in, const nb2_state_view& out,

@@ -3,7 +3,9 @@
 
 Same constructor kwargs (``:135-146``) and ``step`` signature (``:461-469``).  One fused CUDA kernel per call
 (``newton_b200/csrc/nb2_featherstone.cu``).  ``use_tile_gemm`` / ``fuse_cholesky`` select Warp tile kernels in
-the reference; here H = J^T M J and its Cholesky factor are always fused, so the flags are accepted and ignored.
+the reference.  Here H = J^T M J and its Cholesky factor are always fused (``fuse_cholesky`` is accepted and ignored);
+``use_tile_gemm=True`` forms H on the tensor cores (``mma.sync`` m16n8k8, 3xTF32) instead of the ordered FP32 sums - opt-in like
+upstream, agrees with the default path to ~1e-6 relative instead of bit for bit.
 """
 
 from __future__ import annotations
@@ -35,7 +37,8 @@ class SolverFeatherstone(SolverBase):
         if control is None:
             control = model.control(clone_variables=False)
         use_contacts = 1 if self._prepare_contacts(contacts) else 0
-        p = _abi.FeatherstoneParams(self.angular_damping, int(self.update_mass_matrix_interval), self.friction_smoothing)
+        p = _abi.FeatherstoneParams(self.angular_damping, int(self.update_mass_matrix_interval), self.friction_smoothing,
+                                    1 if self.use_tile_gemm else 0)
         st = _lib.lib().nb2_featherstone_step(
             self._native.handle, C.byref(p), C.byref(_abi.state_view(state_in, model)), C.byref(_abi.state_view(state_out, model)),
             C.byref(_abi.control_view(control, model)), use_contacts, C.c_float(dt), _lib.current_stream_ptr(model),

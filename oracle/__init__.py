@@ -166,7 +166,7 @@ class SolverFeatherstone:
         _check_cpu(model)
         self.model = model
         self._desc = _abi.model_desc(model)
-        self.params = _abi.FeatherstoneParams(angular_damping, update_mass_matrix_interval, friction_smoothing)
+        self.params = _abi.FeatherstoneParams(angular_damping, update_mass_matrix_interval, friction_smoothing, 0)
         self._h = C.c_void_p(lib().orc_featherstone_new())
 
     def __del__(self):

@@ -13,7 +13,8 @@ pipe = newton_b200.CollisionPipeline(model)
 if solver_name == "xpbd":
     solver = newton_b200.solvers.SolverXPBD(model, iterations=its)
 else:
-    solver = newton_b200.solvers.SolverFeatherstone(model)
+    import os
+    solver = newton_b200.solvers.SolverFeatherstone(model, use_tile_gemm=os.environ.get("NB2_TILE", "0") == "1")
 s0, s1, ctrl, contacts = model.state(), model.state(), model.control(), pipe.contacts()
 def frame():
     global s0, s1
