@@ -120,6 +120,13 @@ typedef struct nb2_model_desc {
        gravity_count is the number of vec3 entries actually present (1 for implicit single-world models) */
     const float* gravity;
     int32_t gravity_count;
+    /* run-time broad phases ("nxn" / "sap", reference geometry/broad_phase_nxn.py:132-218, broad_phase_sap.py): per-shape collision
+       groups (model.shape_collision_group; filter rule test_group_pair, broad_phase_common.py:221-238) and the excluded pairs
+       (model.shape_collision_filter_pairs as canonical (min, max) rows sorted lexicographically, like CollisionPipeline's
+       shape_pairs_excluded, sim/collide.py).  May be NULL / 0 when only broad_phase="explicit" is used. */
+    const int32_t* shape_collision_group;
+    const int32_t* shape_collision_filter_pairs;
+    int32_t shape_collision_filter_pair_count;
 } nb2_model_desc;
 
 /* Reference `State` arrays (sim/state.py:119-171). Pointers may be NULL when the count is zero. */
@@ -204,6 +211,16 @@ nb2_status nb2_model_notify_changed(nb2_model* model, const nb2_model_desc* desc
 int32_t nb2_model_rigid_contact_max(const nb2_model* model);
 
 /* --- hot path ------------------------------------------------------------------------------- */
+
+/* Broad-phase selection of reference CollisionPipeline(broad_phase=..., shape_pairs_max=..., include_static_kinematic_pairs=...)
+ * (sim/collide.py:1104-1133).  NB2_BROAD_PHASE_EXPLICIT sweeps model.shape_contact_pairs (the default after nb2_model_create);
+ * NXN enumerates every shape pair of a world and SAP sorts the world's shapes along the reference's fixed axis and sweeps - both
+ * apply the world / collision-group / excluded-pair / immovable filters at run time on the device and hand the surviving pairs,
+ * ordered by the deterministic contact key, to the same narrow phase.  `max_pairs_per_world` bounds the candidate list of one
+ * world (0 = every pair the world can form); the contact blocks are re-sized for it (5 contact slots per candidate pair), so
+ * nb2_model_rigid_contact_max changes.  One setting per nb2_model. */
+enum { NB2_BROAD_PHASE_EXPLICIT = 0, NB2_BROAD_PHASE_NXN = 1, NB2_BROAD_PHASE_SAP = 2 };
+nb2_status nb2_collide_configure(nb2_model* model, int32_t broad_phase, int32_t max_pairs_per_world, int32_t include_static_kinematic_pairs);
 
 /* Reference CollisionPipeline.collide(state, contacts) (sim/collide.py:1765-2207): AABBs, explicit
  * broad phase, analytic + GJK/MPR narrow phase, contact write-out.  Contacts are always written to
@@ -300,6 +317,16 @@ nb2_status nb2_view_scatter(void* attrib, const nb2_view_layout* layout, const v
 nb2_status nb2_view_articulation_mask(const uint8_t* mask, int32_t mask_ndim, const int32_t* articulation_ids,
                                       int32_t world_count, int32_t count_per_world, uint8_t* model_mask,
                                       int32_t articulation_count, void* cuda_stream);
+
+/* Reference CollisionPipeline(contact_matching="latest") (geometry/contact_match.py; call sites sim/collide.py:2033-2137): fills
+ * match_index[i] for every contact of the exported, key-sorted buffer (run nb2_contacts_sort first: matching implies
+ * deterministic order upstream) with the index of the matched contact in the PREVIOUS call's sorted buffer, -1 (pair had no
+ * contacts last frame) or -2 (pair known, but no contact within pos_threshold [m] / normal_dot_threshold, or a closer contact
+ * claimed the same old one), then stores this frame as the new history.  reset_world_mask: optional [world_count + 1] bytes
+ * (last = world -1): contacts touching a selected world start fresh; reset_all != 0 forgets the whole history first. */
+nb2_status nb2_contacts_match(nb2_model* model, const float* body_q, const nb2_contacts_view* contacts, int32_t* match_index,
+                              float pos_threshold, float normal_dot_threshold, const uint8_t* reset_world_mask, int32_t reset_all,
+                              void* cuda_stream);
 
 /* --- multi-GPU end-of-frame state gather without compute kernels --------------------------------------
  * Replaces the `ncclAllGather(body_q, body_qd)` of the reference design (there is no reference code for it: upstream is

@@ -143,6 +143,9 @@ class ModelDesc(C.Structure):
         ("hull_points", C.c_void_p),
         ("gravity", C.c_void_p),
         ("gravity_count", C.c_int32),
+        ("shape_collision_group", C.c_void_p),
+        ("shape_collision_filter_pairs", C.c_void_p),
+        ("shape_collision_filter_pair_count", C.c_int32),
     ]
 
 
@@ -233,7 +236,7 @@ _MODEL_KIND = {n: "i32" for n in (
     "body_flags", "body_world", "body_world_start", "joint_type", "joint_parent", "joint_child", "joint_ancestor",
     "joint_articulation", "joint_q_start", "joint_qd_start", "joint_target_q_start", "joint_dof_dim", "joint_world_start",
     "articulation_start", "shape_body", "shape_type", "shape_flags", "shape_world", "shape_world_start", "shape_contact_pairs",
-    "shape_hull_start", "shape_hull_count")}
+    "shape_hull_start", "shape_hull_count", "shape_collision_group")}
 _MODEL_KIND["joint_enabled"] = "bool"
 
 
@@ -245,12 +248,33 @@ def model_desc(model) -> ModelDesc:
     d.shape_pair_count = int(getattr(model, "shape_contact_pair_count", 0))
     dev = getattr(model, "device", None)
     for name, _ in ModelDesc._fields_:
-        if name in _COUNT_FIELDS or name in ("shape_pair_count", "gravity_count"):
+        if name in _COUNT_FIELDS or name in ("shape_pair_count", "gravity_count", "shape_collision_filter_pairs",
+                                             "shape_collision_filter_pair_count"):
             continue
         setattr(d, name, ptr(getattr(model, name, None), _MODEL_KIND.get(name, "f32"), dev, None, "model." + name))
     g = model.gravity
     d.gravity_count = int(g.shape[0])
+    fp = _filter_pair_array(model)
+    d.shape_collision_filter_pairs = ptr(fp, "i32", dev, None, "model.shape_collision_filter_pairs")
+    d.shape_collision_filter_pair_count = 0 if fp is None else int(fp.shape[0])
     return d
+
+
+def _filter_pair_array(model):
+    """``model.shape_collision_filter_pairs`` (a host-side set, like the reference's) as the sorted canonical ``[F, 2]`` int32 array
+    the run-time broad phases binary-search (reference ``CollisionPipeline.shape_pairs_excluded``); cached on the model."""
+    pairs = getattr(model, "shape_collision_filter_pairs", None)
+    if not pairs:
+        return None
+    cached = getattr(model, "_nb2_filter_pairs", None)
+    if cached is not None and cached[0] == len(pairs):
+        return cached[1]
+    import torch
+
+    arr = np.asarray(sorted((min(a, b), max(a, b)) for a, b in pairs), dtype=np.int32).reshape(-1, 2)
+    t = torch.from_numpy(np.ascontiguousarray(arr)).to(getattr(model, "device", "cpu"))
+    model._nb2_filter_pairs = (len(pairs), t)
+    return t
 
 
 def state_view(state, model=None) -> StateView:

@@ -18,7 +18,7 @@ STATUS = {0: "NB2_OK", 1: "NB2_ERR_INVALID_ARGUMENT", 2: "NB2_ERR_UNSUPPORTED", 
 
 # every symbol include/newton_b200.h declares
 EXPORTED_SYMBOLS = (
-    "nb2_model_create", "nb2_model_destroy", "nb2_model_notify_changed", "nb2_model_rigid_contact_max", "nb2_collide", "nb2_contacts_sort", "nb2_contacts_import",
+    "nb2_model_create", "nb2_model_destroy", "nb2_model_notify_changed", "nb2_model_rigid_contact_max", "nb2_collide_configure", "nb2_collide", "nb2_contacts_match", "nb2_contacts_sort", "nb2_contacts_import",
     "nb2_xpbd_step", "nb2_xpbd_update_contacts", "nb2_integrate_bodies", "nb2_featherstone_step", "nb2_eval_fk", "nb2_eval_ik", "nb2_eval_fk_masked",
     "nb2_view_gather", "nb2_view_scatter", "nb2_view_articulation_mask", "nb2_last_error", "nb2_kernel_launch_count", "nb2_version",
     "nb2_peer_gather_handle_bytes", "nb2_peer_gather_create", "nb2_peer_gather_buffer", "nb2_peer_gather_stride", "nb2_peer_gather_export",
@@ -49,8 +49,12 @@ def lib():
         L.nb2_model_notify_changed.restype = C.c_int
         L.nb2_model_rigid_contact_max.argtypes = [P]
         L.nb2_model_rigid_contact_max.restype = C.c_int32
+        L.nb2_collide_configure.argtypes = [P, C.c_int32, C.c_int32, C.c_int32]
+        L.nb2_collide_configure.restype = C.c_int
         L.nb2_collide.argtypes = [P, P, C.POINTER(_abi.ContactsView), P]
         L.nb2_collide.restype = C.c_int
+        L.nb2_contacts_match.argtypes = [P, P, C.POINTER(_abi.ContactsView), P, C.c_float, C.c_float, P, C.c_int32, P]
+        L.nb2_contacts_match.restype = C.c_int
         L.nb2_contacts_sort.argtypes = [P, C.POINTER(_abi.ContactsView), P]
         L.nb2_contacts_sort.restype = C.c_int
         L.nb2_contacts_import.argtypes = [P, C.POINTER(_abi.ContactsView), P]
@@ -136,6 +140,13 @@ class NativeModel:
         self.handle = handle
         self.contact_stamp = 0  # bumped whenever the contact blocks are overwritten (collide / import)
         self.rigid_contact_max = int(lib().nb2_model_rigid_contact_max(handle))
+
+    def configure_broad_phase(self, mode: int, max_pairs_per_world: int, include_static_kinematic_pairs: bool):
+        """``nb2_collide_configure``: explicit (0) / nxn (1) / sap (2); re-sizes the contact blocks, hence ``rigid_contact_max``."""
+        check(lib().nb2_collide_configure(self.handle, int(mode), int(max_pairs_per_world), 1 if include_static_kinematic_pairs else 0),
+              "nb2_collide_configure")
+        self.rigid_contact_max = int(lib().nb2_model_rigid_contact_max(self.handle))
+        self.contact_stamp += 1  # whatever sat in the old blocks is gone
 
     def notify_model_changed(self, flags: int):
         self.desc = _abi.model_desc(self.model)

@@ -14,7 +14,7 @@ LIB = os.path.join(HERE, "libnewton_b200.so")
 # latency-bound, not FP-issue-bound (profiles/).  A contracted "fast" twin is kept only for that comparison.
 LIB_FAST = os.path.join(HERE, "libnewton_b200_fast.so")
 STRICT_FLAGS = ["-fmad=false", "-DNB2_STRICT_FP=1"]
-SOURCES = ["nb2_api.cu", "nb2_collide.cu", "nb2_xpbd.cu", "nb2_featherstone.cu", "nb2_selection.cu", "nb2_peer.cu"]
+SOURCES = ["nb2_api.cu", "nb2_collide.cu", "nb2_xpbd.cu", "nb2_featherstone.cu", "nb2_selection.cu", "nb2_peer.cu", "nb2_match.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",

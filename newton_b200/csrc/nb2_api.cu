@@ -452,6 +452,123 @@ static nb2_status upload_tables(nb2_model* m) {
     return NB2_OK;
 }
 
+
+// Frees one tracked device allocation (the contact blocks are re-sized when the broad phase changes).
+static void release(nb2_model* m, const void* p) {
+    if (!p) return;
+    for (size_t i = 0; i < m->allocations.size(); ++i)
+        if (m->allocations[i] == p) {
+            cudaFree(m->allocations[i]);
+            m->allocations.erase(m->allocations.begin() + i);
+            return;
+        }
+}
+
+// Contact-block slot ranges + buffers for the current pair source: 5 slots per explicit pair, or per candidate-capacity pair of
+// the run-time broad phases.
+static nb2_status allocate_contact_blocks(nb2_model* m) {
+    DevModel& dv = m->dev;
+    HostTables& h = m->host;
+    const int E = dv.env_count;
+    release(m, dv.env_slot_start);
+    release(m, dv.cb);
+    release(m, dv.contact_impulse);
+    dv.max_env_contact_slots = 0;
+    for (int e = 0; e < E; ++e) dv.max_env_contact_slots = std::max(dv.max_env_contact_slots, h.env_slot_start[e + 1] - h.env_slot_start[e]);
+    dv.slot_total = h.env_slot_start[E];
+    nb2_status st;
+    if ((st = upload(m, h.env_slot_start, &dv.env_slot_start))) return st;
+    void* p = nullptr;
+    size_t n = std::max<size_t>(size_t(dv.slot_total) * 6, 1) * sizeof(float);
+    NB2_CUDA_CHECK(cudaMalloc(&p, n));
+    NB2_CUDA_CHECK(cudaMemset(p, 0, n));
+    m->allocations.push_back(p);
+    dv.contact_impulse = static_cast<float*>(p);
+    n = std::max<size_t>(size_t(dv.slot_total) * CF_COUNT, 1) * sizeof(float);
+    NB2_CUDA_CHECK(cudaMalloc(&p, n));
+    NB2_CUDA_CHECK(cudaMemset(p, 0, n));
+    m->allocations.push_back(p);
+    dv.cb = static_cast<float*>(p);
+    NB2_CUDA_CHECK(cudaMemset(dv.env_contact_count, 0, (size_t(E) + 1) * sizeof(int)));
+    return NB2_OK;
+}
+
+static nb2_status configure_broad_phase(nb2_model* m, int mode, int max_pairs, bool include_static_kinematic) {
+    DevModel& dv = m->dev;
+    HostTables& h = m->host;
+    const int E = dv.env_count;
+    dv.include_static_kinematic_pairs = include_static_kinematic ? 1 : 0;
+    if (mode == dv.broad_phase && (mode == NB2_BROAD_PHASE_EXPLICIT || max_pairs == m->dyn_pairs_requested)) return NB2_OK;
+    release(m, dv.dyn_pairs);
+    release(m, dv.env_dyn_count);
+    dv.dyn_pairs = nullptr;
+    dv.env_dyn_count = nullptr;
+    dv.dyn_pair_cap = 0;
+    if (mode == NB2_BROAD_PHASE_EXPLICIT) {
+        for (int e = 0; e < E; ++e) h.env_slot_start[e + 1] = h.env_slot_start[e] + 5 * (h.env_pair_start[e + 1] - h.env_pair_start[e]);
+        m->max_env_contacts = m->explicit_max_env_contacts;
+        m->has_convex_pairs = m->explicit_has_convex_pairs;
+    } else {
+        if (dv.max_env_slots_shapes > 65535) {
+            set_error("nb2_collide_configure: more than 65535 shapes in one world");
+            return NB2_ERR_CAPACITY;
+        }
+        if (!dv.d.shape_collision_group) {
+            set_error("nb2_collide_configure: broad_phase nxn / sap needs model.shape_collision_group");
+            return NB2_ERR_INVALID_ARGUMENT;
+        }
+        int cap = 0;
+        std::vector<int> caps(size_t(E), 0);
+        for (int e = 0; e < E; ++e) {
+            const long long ns = h.env_shape_start[e + 1] - h.env_shape_start[e] + dv.global_shape_count;
+            long long c = ns * (ns - 1) / 2;
+            if (max_pairs > 0) c = std::min<long long>(c, max_pairs);
+            caps[e] = int(std::min<long long>(c, 1 << 20));
+            cap = std::max(cap, caps[e]);
+        }
+        for (int e = 0; e < E; ++e) h.env_slot_start[e + 1] = h.env_slot_start[e] + 5 * caps[e];
+        if (h.env_slot_start[E] < 0 || (long long)E * cap > (1ll << 30)) {
+            set_error("nb2_collide_configure: candidate capacity too large; pass max_pairs_per_world (CollisionPipeline(shape_pairs_max=...))");
+            return NB2_ERR_CAPACITY;
+        }
+        dv.dyn_pair_cap = cap;
+        void* p = nullptr;
+        NB2_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(size_t(E) * cap, 1) * sizeof(int2)));
+        m->allocations.push_back(p);
+        dv.dyn_pairs = static_cast<int2*>(p);
+        NB2_CUDA_CHECK(cudaMalloc(&p, (size_t(E) + 1) * sizeof(int)));
+        NB2_CUDA_CHECK(cudaMemset(p, 0, (size_t(E) + 1) * sizeof(int)));
+        m->allocations.push_back(p);
+        dv.env_dyn_count = static_cast<int*>(p);
+        m->max_env_contacts = 5 * cap;
+        m->has_convex_pairs = true;  // any type pair may show up at run time
+        // excluded pairs -> sorted 64-bit keys
+        release(m, dv.filter_keys);
+        dv.filter_keys = nullptr;
+        dv.filter_count = 0;
+        if (dv.d.shape_collision_filter_pair_count > 0 && dv.d.shape_collision_filter_pairs) {
+            std::vector<int> fp;
+            nb2_status st = fetch(dv.d.shape_collision_filter_pairs, size_t(dv.d.shape_collision_filter_pair_count) * 2, fp);
+            if (st != NB2_OK) return st;
+            std::vector<long long> keys;
+            keys.reserve(fp.size() / 2);
+            for (size_t i = 0; i + 1 < fp.size(); i += 2) {
+                const long long a = std::min(fp[i], fp[i + 1]), b = std::max(fp[i], fp[i + 1]);
+                keys.push_back((a << 32) | b);
+            }
+            std::sort(keys.begin(), keys.end());
+            keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+            const long long* dk = nullptr;
+            if ((st = upload(m, keys, &dk))) return st;
+            dv.filter_keys = dk;
+            dv.filter_count = int(keys.size());
+        }
+    }
+    dv.broad_phase = mode;
+    m->dyn_pairs_requested = max_pairs;
+    return allocate_contact_blocks(m);
+}
+
 // Every entry point runs on the model's device and leaves the caller's current device as it found it (a process may drive
 // several GPUs; nb2_model_destroy is called from a garbage collector at arbitrary points).
 struct DeviceGuard {
@@ -487,6 +604,9 @@ nb2_status nb2_model_create(const nb2_model_desc* desc, int32_t device, nb2_mode
         delete m;
         return st;
     }
+    m->explicit_max_env_contacts = m->max_env_contacts;
+    m->explicit_has_convex_pairs = m->has_convex_pairs;
+    m->dev.include_static_kinematic_pairs = 1;
     *out = m;
     return NB2_OK;
 }
@@ -494,6 +614,9 @@ nb2_status nb2_model_create(const nb2_model_desc* desc, int32_t device, nb2_mode
 void nb2_model_destroy(nb2_model* model) {
     if (!model) return;
     DeviceGuard guard(model->device);
+    for (void* p : {(void*)model->match_new_keys, (void*)model->match_prev_keys, (void*)model->match_prev_claim, (void*)model->match_prev_pos,
+                    (void*)model->match_prev_normal, (void*)model->match_prev_count})
+        if (p) cudaFree(p);
     free_allocations(model);
     delete model;
 }
@@ -518,6 +641,15 @@ nb2_status nb2_model_notify_changed(nb2_model* model, const nb2_model_desc* desc
 }
 
 int32_t nb2_model_rigid_contact_max(const nb2_model* model) { return model ? model->dev.slot_total : 0; }
+
+nb2_status nb2_collide_configure(nb2_model* model, int32_t broad_phase, int32_t max_pairs_per_world, int32_t include_static_kinematic_pairs) {
+    if (!model || broad_phase < NB2_BROAD_PHASE_EXPLICIT || broad_phase > NB2_BROAD_PHASE_SAP || max_pairs_per_world < 0) {
+        set_error("nb2_collide_configure: invalid argument");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    DeviceGuard guard(model->device);
+    return configure_broad_phase(model, broad_phase, max_pairs_per_world, include_static_kinematic_pairs != 0);
+}
 
 nb2_status nb2_collide(nb2_model* model, const float* body_q, const nb2_contacts_view* contacts, void* cuda_stream) {
     if (!model || (!body_q && model->dev.d.body_count > 0)) {

@@ -323,8 +323,13 @@ __global__ void __launch_bounds__(32 * WARPS) collide_kernel(DevModel M, const f
         nloc = M.env_shape_start[env + 1] - ss;
         nslots = nloc + M.global_shape_count;
         bs = M.env_body_start[env];
-        ps = M.env_pair_start[env];
-        np = M.env_pair_start[env + 1] - ps;
+        if (M.dyn_pairs) {  // run-time broad phase: the candidates broadphase_kernel left for this env
+            ps = env * M.dyn_pair_cap;
+            np = min(M.env_dyn_count[env], M.dyn_pair_cap);
+        } else {
+            ps = M.env_pair_start[env];
+            np = M.env_pair_start[env + 1] - ps;
+        }
         slot0 = M.env_slot_start[env];
     }
     // ---- phase 1: transforms + AABBs -----------------------------------------------------------
@@ -362,9 +367,16 @@ __global__ void __launch_bounds__(32 * WARPS) collide_kernel(DevModel M, const f
         int sa = 0, sb = 0;
         float reff_a = 0.f, reff_b = 0.f, marg_a = 0.f, marg_b = 0.f;
         if (live && p < np) {
-            int2 pr = M.pairs[ps + p];
+            int2 pr = M.dyn_pairs ? M.dyn_pairs[ps + p] : M.pairs[ps + p];
             V3 alo = ld3(slots[pr.x].lo), ahi = ld3(slots[pr.x].hi), blo = ld3(slots[pr.y].lo), bhi = ld3(slots[pr.y].hi);
             bool overlap = alo.x <= bhi.x && ahi.x >= blo.x && alo.y <= bhi.y && ahi.y >= blo.y && alo.z <= bhi.z && ahi.z >= blo.z;
+            if (overlap && !M.include_static_kinematic_pairs && !M.dyn_pairs) {
+                // is_shape_pair_immovable_filtered (broad_phase_common.py:166-201) in the explicit sweep (broad_phase_nxn.py:29-69)
+                const int s1 = pr.x < nloc ? ss + pr.x : M.global_shapes[pr.x - nloc], s2 = pr.y < nloc ? ss + pr.y : M.global_shapes[pr.y - nloc];
+                const int b1 = d.shape_body[s1], b2 = d.shape_body[s2];
+                const bool im1 = b1 < 0 || (d.body_flags[b1] & 2) != 0, im2 = b2 < 0 || (d.body_flags[b2] & 2) != 0;
+                if (im1 && im2) overlap = false;
+            }
             if (overlap) {
                 sa = pr.x < nloc ? ss + pr.x : M.global_shapes[pr.x - nloc];
                 sb = pr.y < nloc ? ss + pr.y : M.global_shapes[pr.y - nloc];
@@ -516,6 +528,149 @@ __global__ void __launch_bounds__(32 * WARPS) collide_kernel(DevModel M, const f
         n_total += total;
     }
     if (live && l == 0) M.env_contact_count[env] = n_total;
+}
+
+// ---- run-time broad phases: per-world NxN enumeration / sweep-and-prune (reference geometry/broad_phase_nxn.py:132-218,
+// broad_phase_sap.py:159-515) ---------------------------------------------------------------------------------------------------
+// One sub-warp group per environment, like every kernel of this file.  The reference runs 1 (NxN) or 5 launches + 2 library sorts
+// (SAP) over global arrays with a global atomic per candidate; here a world's shapes, their AABBs and - for SAP - their sorted
+// projections live in shared memory, and the candidates leave the kernel already in deterministic contact-key order (rank sort by
+// (shape_a, shape_b) after the narrow phase's type ordering), which is what lets collide_kernel assign contact slots by prefix sum.
+NB2_DEV bool group_pair_collides(int ga, int gb) {  // test_group_pair (broad_phase_common.py:221-238)
+    if (ga == 0 || gb == 0) return false;
+    if (ga > 0) return ga == gb || gb < 0;
+    return ga != gb;
+}
+struct __align__(8) BpSlot {
+    float lo[3], hi[3];
+    float plo, phi;  // projection on the SAP axis
+    int shape;       // model shape id
+    int info;        // bit 0 collides, bit 1 global (world -1), bit 2 immovable (static or kinematic body); group in the high bits is separate
+    int group;
+    int type;
+};
+template <int L>
+__global__ void __launch_bounds__(32) broadphase_kernel(DevModel M, const float* __restrict__ body_q) {
+    constexpr int G = 32 / L;
+    extern __shared__ unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, grp = lane / L, l = lane % L;
+    const unsigned gmask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << (grp * L));
+    const int env = blockIdx.x * G + grp;
+    const bool live = env < M.env_count;
+    const nb2_model_desc& d = M.d;
+    const int cap = M.dyn_pair_cap, max_slots = M.max_env_slots_shapes;
+    // per group: slots | sort order (SAP) | candidate keys | candidate values | counter
+    const size_t per_group = size_t(max_slots) * sizeof(BpSlot) + size_t(max_slots) * sizeof(int) + size_t(cap) * (sizeof(long long) + sizeof(int)) + 16;
+    unsigned char* base = smem_raw + size_t(grp) * ((per_group + 15) & ~size_t(15));
+    BpSlot* slots = reinterpret_cast<BpSlot*>(base);
+    long long* ckey = reinterpret_cast<long long*>(base + ((size_t(max_slots) * sizeof(BpSlot) + 7) & ~size_t(7)));
+    int* cval = reinterpret_cast<int*>(ckey + cap);
+    int* order = cval + cap;
+    int* counter = order + max_slots;
+    int ss = 0, nloc = 0, ns = 0;
+    if (live) {
+        ss = M.env_shape_start[env];
+        nloc = M.env_shape_start[env + 1] - ss;
+        ns = nloc + M.global_shape_count;
+    }
+    if (l == 0) *counter = 0;
+    const V3 axis = unit(V3(0.5935f, 0.7790f, 0.1235f));  // broad_phase_sap.py:702-703
+    for (int s = l; s < ns; s += L) {
+        const int sid = s < nloc ? ss + s : M.global_shapes[s - nloc];
+        const int body = d.shape_body[sid];
+        Xf X = ldx(d.shape_transform + 7 * sid);
+        if (body != -1) X = xmul(ldx(body_q + 7 * body), X);
+        const int stype = d.shape_type[sid];
+        V3 llo, lhi, lo, hi;
+        if (stype == GEO_CONVEX_MESH) {
+            llo = ld3(d.shape_collision_aabb_lower + 3 * sid);
+            lhi = ld3(d.shape_collision_aabb_upper + 3 * sid);
+        }
+        shape_aabb(stype, ld3(d.shape_scale + 3 * sid), X, d.shape_margin[sid] + d.shape_gap[sid], d.shape_collision_radius[sid], llo, lhi, lo, hi);
+        BpSlot& r = slots[s];
+        st3(r.lo, lo);
+        st3(r.hi, hi);
+        // _sap_project_aabb (broad_phase_sap.py:44-80), AABBs pre-expanded (no extra gap)
+        const V3 half = 0.5f * (hi - lo);
+        const float radius = dot(vabs(axis), half), center = dot(axis, 0.5f * (lo + hi));
+        r.plo = center - radius;
+        r.phi = center + radius;
+        r.shape = sid;
+        r.group = d.shape_collision_group ? d.shape_collision_group[sid] : 1;
+        r.type = stype;
+        const bool immovable = body < 0 || (d.body_flags[body] & 2) != 0;
+        r.info = ((d.shape_flags[sid] & 2) ? 1 : 0) | (s >= nloc ? 2 : 0) | (immovable ? 4 : 0);
+    }
+    __syncwarp(gmask);
+    // the per-pair filter chain of _nxn_broadphase_kernel / _process_sap_work_package, then the candidate append
+    auto consider = [&](int i, int j) {
+        const BpSlot& a = slots[i];
+        const BpSlot& b = slots[j];
+        if (!(a.info & b.info & 1)) return;             // precompute_world_map keeps COLLIDE_SHAPES shapes only
+        if ((a.info & 2) && (b.info & 2)) return;       // shared-vs-shared pairs belong to the dedicated segment (no body involved)
+        if (!group_pair_collides(a.group, b.group)) return;
+        if (!M.include_static_kinematic_pairs && (a.info & 4) && (b.info & 4)) return;
+        if (!(a.lo[0] <= b.hi[0] && a.hi[0] >= b.lo[0] && a.lo[1] <= b.hi[1] && a.hi[1] >= b.lo[1] && a.lo[2] <= b.hi[2] && a.hi[2] >= b.lo[2]))
+            return;
+        const int s1 = min(a.shape, b.shape), s2 = max(a.shape, b.shape);
+        if (M.filter_count > 0) {  // is_pair_excluded: binary search of the sorted exclusion list
+            const long long key = ((long long)s1 << 32) | (long long)s2;
+            int lo = 0, hi = M.filter_count - 1;
+            while (lo <= hi) {
+                const int mid = (lo + hi) >> 1;
+                const long long m = M.filter_keys[mid];
+                if (m == key) return;
+                if (key < m) hi = mid - 1;
+                else lo = mid + 1;
+            }
+        }
+        // narrow-phase type ordering (narrow_phase.py:525-528) on the canonical (min, max) pair
+        const BpSlot& p1 = a.shape == s1 ? a : b;
+        const BpSlot& p2 = a.shape == s1 ? b : a;
+        const int i1 = a.shape == s1 ? i : j, i2 = a.shape == s1 ? j : i;
+        const bool swap = p1.type > p2.type;
+        const int sa = swap ? p2.shape : p1.shape, sb = swap ? p1.shape : p2.shape, ia = swap ? i2 : i1, ib = swap ? i1 : i2;
+        const int pos = atomicAdd(counter, 1);
+        if (pos < cap) {
+            ckey[pos] = ((long long)sa << 32) | (long long)sb;
+            cval[pos] = ia | (ib << 16);
+        }
+    };
+    if (M.broad_phase == NB2_BROAD_PHASE_SAP) {
+        // sort the world's shapes by projected lower bound (stable rank sort; ties cannot change the candidate set)
+        for (int s = l; s < ns; s += L) {
+            const float v = slots[s].plo;
+            int rank = 0;
+            for (int k = 0; k < ns; ++k) rank += (slots[k].plo < v || (slots[k].plo == v && k < s)) ? 1 : 0;
+            order[rank] = s;
+        }
+        __syncwarp(gmask);
+        for (int i = l; i < ns; i += L) {  // _sap_range_kernel: sweep while lower_j < upper_i
+            const int si = order[i];
+            const float upper = slots[si].phi;
+            for (int j = i + 1; j < ns; ++j) {
+                const int sj = order[j];
+                if (!(slots[sj].plo < upper)) break;
+                consider(si, sj);
+            }
+        }
+    } else {
+        for (int i = 0; i < ns; ++i)  // _nxn_broadphase_kernel: every pair of the world's slice
+            for (int j = i + 1 + l; j < ns; j += L) consider(i, j);
+    }
+    __syncwarp(gmask);
+    const int total = *counter, n = min(total, cap);
+    // rank sort by the deterministic contact key (keys are unique: one entry per shape pair)
+    if (live) {
+        int2* out = M.dyn_pairs + size_t(env) * cap;
+        for (int c = l; c < n; c += L) {
+            const long long key = ckey[c];
+            int rank = 0;
+            for (int k = 0; k < n; ++k) rank += ckey[k] < key ? 1 : 0;
+            out[rank] = make_int2(cval[c] & 0xffff, cval[c] >> 16);
+        }
+        if (l == 0) M.env_dyn_count[env] = total;
+    }
 }
 
 // ---- export to the reference `Contacts` arrays ---------------------------------------------------
@@ -854,10 +1009,38 @@ static nb2_status launch_collide_L(nb2_model* m, const float* body_q, cudaStream
     return launch_collide_W<L, CONVEX, 1>(m, body_q, s);
 }
 
+template <int L>
+static nb2_status launch_broadphase_L(nb2_model* m, const float* body_q, cudaStream_t s) {
+    const DevModel& M = m->dev;
+    const int G = 32 / L;
+    const size_t per_group = size_t(M.max_env_slots_shapes) * sizeof(BpSlot) + size_t(M.max_env_slots_shapes) * sizeof(int) +
+                             size_t(M.dyn_pair_cap) * (sizeof(long long) + sizeof(int)) + 16;
+    const size_t smem = ((per_group + 15) & ~size_t(15)) * G;
+    if (smem > 200 * 1024) {
+        set_error("broad phase: too many shapes / candidate pairs per world for the shared-memory sweep (lower max_pairs_per_world)");
+        return NB2_ERR_CAPACITY;
+    }
+    if (smem > 48 * 1024) NB2_CUDA_CHECK(cudaFuncSetAttribute(broadphase_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    broadphase_kernel<L><<<(M.env_count + G - 1) / G, 32, smem, s>>>(M, body_q);
+    count_launch();
+    NB2_CUDA_CHECK(cudaGetLastError());
+    return NB2_OK;
+}
+
+nb2_status launch_broadphase(nb2_model* m, const float* body_q, cudaStream_t s) {
+    if (m->dev.env_count == 0 || m->dev.d.shape_count == 0) return NB2_OK;
+    switch (m->lanes_per_env) {
+        case 8: return launch_broadphase_L<8>(m, body_q, s);
+        case 16: return launch_broadphase_L<16>(m, body_q, s);
+        default: return launch_broadphase_L<32>(m, body_q, s);
+    }
+}
+
 nb2_status launch_collide(nb2_model* m, const float* body_q, const nb2_contacts_view* contacts, cudaStream_t s) {
     const DevModel& M = m->dev;
     if (M.env_count == 0 || M.d.shape_count == 0) return NB2_OK;
     nb2_status st;
+    if (M.dyn_pairs && (st = launch_broadphase(m, body_q, s)) != NB2_OK) return st;
 #define NB2_COLLIDE_DISPATCH(LANES) \
     st = m->has_convex_pairs ? launch_collide_L<LANES, true>(m, body_q, s) : launch_collide_L<LANES, false>(m, body_q, s)
     switch (m->lanes_per_env) {

@@ -70,6 +70,15 @@ struct DevModel {
     float* joint_impulse;  // [6 * joint_count]
     // exported index -> position after nb2_contacts_sort (nullptr: export order is the final order)
     const int* export_rank;
+    // run-time broad phase (nb2_collide_configure): candidates of env e are dyn_pairs[e * dyn_pair_cap ...), env_dyn_count[e] of them
+    // (may exceed the capacity: the excess was dropped), in the (slot_a, slot_b) type-ordered, key-sorted format of `pairs`
+    int broad_phase;                 // NB2_BROAD_PHASE_*
+    int include_static_kinematic_pairs;
+    int dyn_pair_cap;
+    int2* dyn_pairs;
+    int* env_dyn_count;
+    const long long* filter_keys;    // excluded pairs as (min << 32 | max), ascending
+    int filter_count;
 };
 
 struct HostTables {
@@ -110,8 +119,15 @@ struct nb2_model {
     int* sort_rank = nullptr;     // exported index -> sorted position
     void* sort_temp = nullptr;
     size_t sort_temp_bytes = 0;
+    // contact matching history (nb2_contacts_match): previous frame's sorted keys / world midpoints / normals / claim words
+    int match_capacity = 0;
+    long long *match_new_keys = nullptr, *match_prev_keys = nullptr, *match_prev_claim = nullptr;
+    float *match_prev_pos = nullptr, *match_prev_normal = nullptr;
+    int* match_prev_count = nullptr;
     bool implicit_single = false;  // model built without begin_world(): one environment holding every entity
     bool has_convex_pairs = false;  // some pair's types have no analytic collider -> collide_kernel<L, true>
+    int explicit_max_env_contacts = 0, dyn_pairs_requested = 0;
+    bool explicit_has_convex_pairs = false;
     int max_env_contacts = 0;       // max over envs of the sum of the pairs' own contact maxima (<= 4 analytic, <= 5 manifold)
     bool contacts_imported = false; // the contact blocks hold an imported foreign buffer (any count up to the slot range)
     float xpbd_impulse_dt = 0.0f;  // dt of the last nb2_xpbd_step that accumulated contact impulses (0 = none yet)
@@ -121,6 +137,7 @@ namespace nb2 {
 void set_error(const std::string& msg);
 void count_launch(int n = 1);
 nb2_status launch_collide(nb2_model* m, const float* body_q, const nb2_contacts_view* contacts, cudaStream_t s);
+nb2_status launch_broadphase(nb2_model* m, const float* body_q, cudaStream_t s);
 nb2_status launch_xpbd_step(nb2_model* m, const nb2_xpbd_params& p, const nb2_state_view& in, const nb2_state_view& out,
                             const nb2_control_view& ctl, int use_contacts, float dt, cudaStream_t s);
 nb2_status launch_contacts_sort(nb2_model* m, const nb2_contacts_view& contacts, cudaStream_t s);

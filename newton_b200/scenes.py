@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from .utils.host_fk import host_fk  # noqa: F401  (re-exported: scenes.host_fk)
-from .sim.builder import ModelBuilder
+from .sim.builder import ModelBuilder, ShapeConfig
 from .utils import xform as X
 
 _HALF_PI = "1.57079632679"
@@ -260,6 +260,42 @@ def hull_pile_model(world_count: int = 1, device="cpu", seed: int | None = 7):
         scene.end_world()
     scene.add_ground_plane()
     return _finish(scene, device)
+
+
+def free_bodies_model(world_count: int = 2, n_bodies: int = 12, device="cpu", seed: int | None = 13, drop_pairs: bool = False):
+    """Many free bodies per world (a loose heap of spheres, boxes and capsules above the ground plane) with mixed collision groups,
+    a visual-only shape and an excluded pair: the case the run-time broad phases exist for (the explicit list grows as n^2 per
+    world).  ``drop_pairs`` empties ``model.shape_contact_pairs`` - what a model looks like when the pair list was never
+    generated - so only ``broad_phase="nxn"`` / ``"sap"`` can find contacts."""
+    rng = np.random.default_rng(seed)
+    scene = ModelBuilder()
+    for _ in range(world_count):
+        scene.begin_world()
+        first = scene.shape_count
+        for k in range(n_bodies):
+            pos = np.array([0.35 * (k % 4) - 0.5, 0.35 * ((k // 4) % 3) - 0.35, 0.25 + 0.22 * (k // 6)]) + rng.uniform(-0.03, 0.03, size=3)
+            q = X.quat_from_axis_angle(rng.normal(size=3), float(rng.uniform(0.0, 0.8)))
+            b = scene.add_body(xform=X.transform(pos, q))
+            cfg = ShapeConfig()
+            cfg.collision_group = (1, 1, 2, -1, -2, 1)[k % 6]
+            if k == 5:
+                cfg.has_shape_collision = False  # visual only
+            if k % 3 == 0:
+                scene.add_shape_sphere(b, radius=0.12, cfg=cfg)
+            elif k % 3 == 1:
+                scene.add_shape_box(b, hx=0.1, hy=0.12, hz=0.08, cfg=cfg)
+            else:
+                scene.add_shape_capsule(b, radius=0.07, half_height=0.1, cfg=cfg)
+        scene.add_shape_collision_filter_pair(first, first + 1)
+        scene.end_world()
+    gcfg = ShapeConfig()
+    gcfg.collision_group = -3
+    scene.add_ground_plane(cfg=gcfg)
+    model = _finish(scene, device)
+    if drop_pairs:
+        model.shape_contact_pairs = model.shape_contact_pairs[:0].clone()
+        model.shape_contact_pair_count = 0
+    return model
 
 
 def mixed_worlds_model(repeats: int = 2, device="cpu", seed: int | None = 9):

@@ -16,41 +16,60 @@ from .model import Contacts
 
 # reference constructor arguments (sim/collide.py:1104-1133) that only size or tune paths outside the primitive / convex scope;
 # accepted with any value so that a call site spelling out the reference defaults keeps working
-_IGNORED_OPTIONS = frozenset({"reduce_contacts", "max_triangle_pairs", "soft_contact_max", "shape_pairs_max", "verify_buffers",
-                              "contact_reduction_hashtable_size_factor", "contact_matching_pos_threshold",
-                              "contact_matching_normal_dot_threshold"})
+_IGNORED_OPTIONS = frozenset({"reduce_contacts", "max_triangle_pairs", "soft_contact_max", "verify_buffers",
+                              "contact_reduction_hashtable_size_factor"})
+MATCH_NOT_FOUND, MATCH_BROKEN = -1, -2  # reference geometry/contact_match.py:113-117
 
 
 class CollisionPipeline:
     def __init__(self, model, *, broad_phase: str | None = None, rigid_contact_max: int | None = None,
                  deterministic: bool = False, soft_contact_margin: float = 0.01, requires_grad: bool = False,
-                 export_contacts: bool = True, include_static_kinematic_pairs: bool = True, **unsupported):
+                 export_contacts: bool = True, include_static_kinematic_pairs: bool = True, contact_matching: str = "disabled",
+                 contact_matching_pos_threshold: float = 0.0005, contact_matching_normal_dot_threshold: float = 0.995,
+                 **unsupported):
         if broad_phase not in (None, "explicit", "nxn", "sap"):
             raise ValueError(f"unknown broad_phase {broad_phase!r} (expected 'explicit', 'nxn' or 'sap')")
-        # "nxn" / "sap" (broad_phase_nxn.py:132-218, broad_phase_sap.py) enumerate candidates at run time with the same
-        # world / collision-group / filter-pair rules the builder used to precompute model.shape_contact_pairs
-        # ("exact same filtering logic ... to ensure consistency between EXPLICIT mode and NXN/SAP modes",
-        # sim/builder.py:12796-12797), followed by the same AABB test.  The candidate set - and therefore the contact set
-        # in deterministic order - is identical, so all three options run the env-local AABB sweep over the pair list.
-        if getattr(model, "shape_contact_pairs", None) is None:
-            raise ValueError("model.shape_contact_pairs is missing (ModelBuilder.finalize() generates it)")
+        if contact_matching not in ("disabled", "latest", "sticky"):
+            raise ValueError(f"contact_matching must be one of 'disabled', 'latest', 'sticky', got {contact_matching!r}")
+        if contact_matching == "sticky":
+            raise NotImplementedError('contact_matching="sticky" (replay of matched contact geometry) is not implemented; use "latest"')
+        if contact_matching_pos_threshold < 0.0:
+            raise ValueError(f"contact_matching_pos_threshold must be non-negative, got {contact_matching_pos_threshold}")
+        if not -1.0 <= contact_matching_normal_dot_threshold <= 1.0:
+            raise ValueError(f"contact_matching_normal_dot_threshold must be in [-1, 1], got {contact_matching_normal_dot_threshold}")
+        self.contact_matching = contact_matching
+        self.contact_matching_pos_threshold = float(contact_matching_pos_threshold)
+        self.contact_matching_normal_dot_threshold = float(contact_matching_normal_dot_threshold)
+        if contact_matching != "disabled":
+            deterministic = True  # any matching mode implies deterministic sorting (collide.py:1269-1271)
+            if not export_contacts:
+                raise ValueError("contact matching works on the exported Contacts arrays: export_contacts must stay True")
+        self._match_reset_all = False
+        self._match_reset_mask = None
         self.broad_phase = broad_phase or "explicit"
+        if self.broad_phase == "explicit" and getattr(model, "shape_contact_pairs", None) is None:
+            raise ValueError("model.shape_contact_pairs is missing (ModelBuilder.finalize() generates it)")
         if requires_grad:
             raise NotImplementedError("differentiable contacts are out of scope")
-        if not include_static_kinematic_pairs:
-            # reference default True (collide.py:1112): pairs of two immovable shapes are kept, as in the explicit pair list;
-            # False would prune them in the broad phase (broad_phase_common.py:166-201)
-            raise NotImplementedError("CollisionPipeline(include_static_kinematic_pairs=False) is not implemented")
+        shape_pairs_max = unsupported.pop("shape_pairs_max", None)
         for k, v in unsupported.items():
             if k in _IGNORED_OPTIONS:  # tuning / capacity knobs of machinery this pipeline does not have (mesh reduction, buffers)
-                continue
-            if k == "contact_matching" and v == "disabled":
                 continue
             if v not in (None, False):
                 raise NotImplementedError(f"CollisionPipeline option {k!r}={v!r} is outside the hot-path scope")
         self.model = model
         self.device = model.device
         self._native = _lib.native_model(model)
+        # "nxn" / "sap": candidates are generated on the device every collide() from the current AABBs with the reference's
+        # run-time filters (world, collision group, excluded pairs, immovable pairs): broad_phase_nxn.py:132-218 /
+        # broad_phase_sap.py:159-515 -> broadphase_kernel (csrc/nb2_collide.cu).  model.shape_contact_pairs is not read.
+        # `shape_pairs_max` (reference: capacity of the global candidate buffer) is taken per world here: 0 / None = every pair.
+        self.include_static_kinematic_pairs = bool(include_static_kinematic_pairs)
+        mode = {"explicit": 0, "nxn": 1, "sap": 2}[self.broad_phase]
+        per_world = 0
+        if shape_pairs_max is not None and mode != 0:
+            per_world = max(1, -(-int(shape_pairs_max) // max(1, int(model.world_count))))
+        self._native.configure_broad_phase(mode, per_world, self.include_static_kinematic_pairs)
         # Contacts are always produced in a deterministic (world, sort-key) order.  deterministic=True additionally reorders
         # the exported arrays into the reference's global sort-key order (ContactSorter.sort_full, collide.py:2054-2073).
         self.deterministic = deterministic
@@ -65,8 +84,23 @@ class CollisionPipeline:
     def contacts(self) -> Contacts:
         """Allocate a :class:`Contacts` buffer sized for this pipeline (reference ``collide.py:1691-1730``)."""
         c = Contacts(self.rigid_contact_max, 0, device=self.device,
-                     requested_attributes=self.model._requested_contact_attributes)
+                     requested_attributes=self.model._requested_contact_attributes,
+                     contact_matching=self.contact_matching != "disabled")
         return c
+
+    def reset(self, world_mask=None) -> None:
+        """Forget the contact-matching history (reference ``CollisionPipeline.reset``, ``sim/collide.py:1735-1752``): all of it, or
+        only for contacts touching the worlds selected by ``world_mask`` (bool ``[world_count + 1]``, last entry = world -1).
+        Takes effect at the next ``collide()``; masks accumulate until then."""
+        if self.contact_matching == "disabled":
+            return
+        if world_mask is None:
+            self._match_reset_all = True
+            return
+        from ..solvers.solver import normalize_reset_world_mask
+
+        mask = normalize_reset_world_mask(world_mask, world_count=int(self.model.world_count), device=self.device)
+        self._match_reset_mask = mask.clone() if self._match_reset_mask is None else (self._match_reset_mask | mask)
 
     def collide(self, state, contacts, *, soft_contact_margin=None, dt=None):
         """Populate ``contacts`` from ``state.body_q`` (reference ``collide.py:1765-2207``)."""
@@ -86,3 +120,16 @@ class CollisionPipeline:
         if self.deterministic and view is not None:
             st = _lib.lib().nb2_contacts_sort(self._native.handle, view, _lib.current_stream_ptr(self.model))
             _lib.check(st, "nb2_contacts_sort")
+        if self.contact_matching != "disabled" and contacts is not None:
+            if contacts.rigid_contact_match_index is None:
+                raise ValueError("CollisionPipeline has contact_matching enabled but the Contacts buffer was created without "
+                                 "contact_matching. Use pipeline.contacts() to create a compatible buffer.")
+            mask = self._match_reset_mask
+            mask_u8 = None if mask is None else mask.to(dtype=__import__("torch").uint8)
+            st = _lib.lib().nb2_contacts_match(
+                self._native.handle, C.c_void_p(_abi.ptr(state.body_q)), view, C.c_void_p(contacts.rigid_contact_match_index.data_ptr()),
+                C.c_float(self.contact_matching_pos_threshold), C.c_float(self.contact_matching_normal_dot_threshold),
+                C.c_void_p(None if mask_u8 is None else mask_u8.data_ptr()), 1 if self._match_reset_all else 0,
+                _lib.current_stream_ptr(self.model))
+            _lib.check(st, "nb2_contacts_match")
+            self._match_reset_all, self._match_reset_mask = False, None

@@ -109,7 +109,8 @@ class Contacts:
     directly (DESIGN.md "contact hand-off").
     """
 
-    def __init__(self, rigid_contact_max: int, soft_contact_max: int = 0, device="cpu", requested_attributes=()):
+    def __init__(self, rigid_contact_max: int, soft_contact_max: int = 0, device="cpu", requested_attributes=(),
+                 contact_matching: bool = False):
         self.rigid_contact_max = int(rigid_contact_max)
         self.soft_contact_max = int(soft_contact_max)
         self.device = torch.device(device)
@@ -133,7 +134,10 @@ class Contacts:
         self.rigid_contact_stiffness = None
         self.rigid_contact_damping = None
         self.rigid_contact_friction = None
-        self.rigid_contact_match_index = None
+        # frame-to-frame correspondence (reference sim/contacts.py:315-326): index into the previous frame's sorted buffer,
+        # -1 = MATCH_NOT_FOUND, -2 = MATCH_BROKEN; allocated by CollisionPipeline(contact_matching="latest").contacts()
+        self.contact_matching = bool(contact_matching)
+        self.rigid_contact_match_index = torch.full((n,), -1, dtype=I32, device=dev) if contact_matching else None
         self.clear_buffers = False
         self._nb2_blocks = None
         self._nb2_stamp = -1  # generation of the native contact blocks this buffer mirrors (see CollisionPipeline.collide)

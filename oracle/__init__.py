@@ -59,40 +59,71 @@ def _check_cpu(model):
 class CollisionPipeline:
     """Oracle for reference ``CollisionPipeline`` (``sim/collide.py:1104-2207``).
 
-    ``broad_phase="explicit"`` sweeps ``model.shape_contact_pairs``.  ``"nxn"`` / ``"sap"`` first enumerate the pairs the NxN kernel's
-    filter admits (``oracle/broad_phase.py``, a restatement of ``broad_phase_nxn.py:124-216``) and REQUIRE that set to equal the
-    explicit list - which is what lets the same AABB sweep stand in for them; the contact order does not depend on the broad
-    phase because the export is in deterministic key order."""
+    ``broad_phase="explicit"`` sweeps ``model.shape_contact_pairs``.  ``"nxn"`` / ``"sap"`` generate the candidate pairs at run
+    time from the current AABBs (``oracle/broad_phase.py``: restatements of ``_nxn_broadphase_kernel`` and of the SAP project /
+    sort / range / sweep kernels with the reference's per-pair filters) and feed them to the same narrow phase;
+    ``model.shape_contact_pairs`` is not read.  Pairs of two global (world -1) shapes are dropped in every mode: no body is
+    involved, and the product keeps no contact blocks for them."""
 
-    def __init__(self, model, *, broad_phase=None, rigid_contact_max=None, deterministic=True):
+    def __init__(self, model, *, broad_phase=None, rigid_contact_max=None, deterministic=True, include_static_kinematic_pairs=True):
         _check_cpu(model)
         if broad_phase not in (None, "explicit", "nxn", "sap"):
             raise ValueError(f"unknown broad_phase {broad_phase!r}")
-        if broad_phase in ("nxn", "sap"):
-            from . import broad_phase as _bp
-
-            explicit = {tuple(p) for p in model.numpy("shape_contact_pairs").tolist()}
-            dynamic = _bp.model_nxn_pairs(model, getattr(model, "shape_collision_filter_pairs", ()))
-            if explicit != dynamic:
-                raise AssertionError(f"explicit pair list and the {broad_phase} filter disagree: "
-                                     f"{sorted(explicit ^ dynamic)[:8]} ...")
         self.model = model
+        self.broad_phase = broad_phase or "explicit"
+        self.include_static_kinematic_pairs = include_static_kinematic_pairs
         self.deterministic = deterministic
         self._desc = _abi.model_desc(model)
-        self.rigid_contact_max = (
-            int(rigid_contact_max) if rigid_contact_max is not None else max(1000, 5 * model.shape_contact_pair_count)
-        )
+        if self.broad_phase == "explicit":
+            pair_count = model.shape_contact_pair_count
+        else:
+            ns = np.bincount(model.numpy("shape_world")[model.numpy("shape_world") >= 0], minlength=max(1, model.world_count))
+            ng = int((model.numpy("shape_world") < 0).sum())
+            pair_count = int(sum((n + ng) * (n + ng - 1) // 2 for n in ns))
+        self.rigid_contact_max = int(rigid_contact_max) if rigid_contact_max is not None else max(1000, 5 * pair_count)
         self.candidate_count = 0
+        self.last_candidates = None
 
     def contacts(self) -> Contacts:
         return Contacts(self.rigid_contact_max, 0, device="cpu",
                         requested_attributes=self.model._requested_contact_attributes)
 
+    def _candidates(self, state):
+        from . import broad_phase as _bp
+
+        lo, hi = shape_aabbs(self.model, state.body_q)
+        fn = _bp.nxn_candidate_pairs if self.broad_phase == "nxn" else _bp.sap_candidate_pairs
+        pairs = fn(self.model, lo, hi, getattr(self.model, "shape_collision_filter_pairs", ()), self.include_static_kinematic_pairs)
+        sw = self.model.numpy("shape_world")
+        if np.all(sw < 0):  # model built without begin_world(): one implicit world holding everything (builder.py:11276)
+            return pairs
+        return [p for p in pairs if not (sw[p[0]] < 0 and sw[p[1]] < 0)]
+
     def collide(self, state, contacts, *, soft_contact_margin=None, dt=None):
         v = _abi.contacts_view(contacts)
+        desc = self._desc
+        keep = None
+        if self.broad_phase != "explicit":
+            self.last_candidates = self._candidates(state)
+            keep = np.ascontiguousarray(np.asarray(self.last_candidates, dtype=np.int32).reshape(-1, 2))
+            desc = _abi.ModelDesc.from_buffer_copy(self._desc)
+            desc.shape_contact_pairs = keep.ctypes.data if keep.size else None
+            desc.shape_pair_count = int(keep.shape[0])
+        elif not self.include_static_kinematic_pairs:
+            from . import broad_phase as _bp
+
+            m = self.model
+            bf = m.numpy("body_flags") if m.body_count else ()
+            pairs = [tuple(p) for p in m.numpy("shape_contact_pairs").tolist()
+                     if not _bp.is_shape_pair_immovable_filtered(p[0], p[1], m.numpy("shape_body"), bf, False)]
+            keep = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+            desc = _abi.ModelDesc.from_buffer_copy(self._desc)
+            desc.shape_contact_pairs = keep.ctypes.data if keep.size else None
+            desc.shape_pair_count = int(keep.shape[0])
         self.candidate_count = lib().orc_collide(
-            C.byref(self._desc), C.c_void_p(_abi.ptr(state.body_q)), C.byref(v), C.c_int(1 if self.deterministic else 0)
+            C.byref(desc), C.c_void_p(_abi.ptr(state.body_q)), C.byref(v), C.c_int(1 if self.deterministic else 0)
         )
+        del keep
 
 
 class SolverXPBD:
@@ -201,7 +232,7 @@ class _Shard(C.Structure):
 
 
 class _Loop(C.Structure):
-    _fields_ = [("solver", C.c_int32), ("substeps", C.c_int32), ("dt", C.c_float), ("xpbd", _abi.XPBDParams),
+    _fields_ = [("solver", C.c_int32), ("deterministic", C.c_int32), ("substeps", C.c_int32), ("dt", C.c_float), ("xpbd", _abi.XPBDParams),
                 ("featherstone", _abi.FeatherstoneParams)]
 
 
@@ -210,7 +241,7 @@ class FramePool:
     world shards on a persistent pool of native threads (``orc_pool_*`` in oracle.cpp).  Threads are created here, before any
     timer; :meth:`run_frames` returns the seconds measured inside the library around the parallel region only."""
 
-    def __init__(self, models, make_solver, *, substeps: int, dt: float, threads: int):
+    def __init__(self, models, make_solver, *, substeps: int, dt: float, threads: int, deterministic: bool = False):
         L = lib()
         L.orc_pool_new.restype = C.c_void_p
         L.orc_pool_free.argtypes = [C.c_void_p]
@@ -220,7 +251,7 @@ class FramePool:
         self._shards = (_Shard * len(models))()
         solver0 = None
         for i, m in enumerate(models):
-            pipe, solver = CollisionPipeline(m, deterministic=False), make_solver(m)
+            pipe, solver = CollisionPipeline(m, deterministic=deterministic), make_solver(m)
             s0, s1, ctrl, contacts = m.state(), m.state(), m.control(), pipe.contacts()
             self._keep.append((m, pipe, solver, s0, s1, ctrl, contacts))
             sh = self._shards[i]
@@ -231,6 +262,7 @@ class FramePool:
             solver0 = solver0 or solver
         self._loop = _Loop()
         self._loop.substeps, self._loop.dt = int(substeps), float(dt)
+        self._loop.deterministic = 1 if deterministic else 0  # False = the reference default (kernel emission order)
         if isinstance(solver0, SolverFeatherstone):
             self._loop.solver, self._loop.featherstone = 1, solver0.params
         else:

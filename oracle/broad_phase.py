@@ -7,7 +7,10 @@ Restatement of WHICH shape pairs the reference's dynamic broad phases may emit, 
 its AABB sweep over ``model.shape_contact_pairs`` (the explicit list) on the strength of the reference's statement that the
 builder computes that list with "the exact same filtering logic as the broad phase kernels" (``sim/builder.py:12796-12797``);
 :func:`nxn_filter_pairs` is the other side of that equation, and ``tests/test_oracle_known_answers_more.py`` checks the two
-sets are equal for every scene of the test-suite.  Python loops: small cases only.
+sets are equal for every scene of the test-suite.  Round 2: the product generates candidates at run time (``broadphase_kernel``), so this module also restates the AABB half:
+:func:`nxn_candidate_pairs` (filter + ``check_aabb_overlap``) and :func:`sap_candidate_pairs` (projection on the fixed axis,
+per-world sort, sweep while ``lower_j < upper_i``, then the same per-pair filter; ``broad_phase_sap.py:44-80, 159-420``).
+Python loops: small cases only.
 """
 
 from __future__ import annotations
@@ -100,3 +103,64 @@ def nxn_filter_pairs(shape_world, shape_flags, collision_group, filter_pairs=(),
 def model_nxn_pairs(model, filter_pairs=(), include_static_kinematic_pairs: bool = True) -> set[tuple[int, int]]:
     return nxn_filter_pairs(model.numpy("shape_world"), model.numpy("shape_flags"), model.numpy("shape_collision_group"), filter_pairs,
                             model.numpy("shape_body"), model.numpy("body_flags") if model.body_count else (), include_static_kinematic_pairs)
+
+
+def check_aabb_overlap(lo1, hi1, lo2, hi2, cutoff: float = 0.0) -> bool:
+    """broad_phase_common.py:20-37 (AABBs pre-expanded by CollisionPipeline: cutoff 0)."""
+    return bool(np.all(lo1 <= hi2 + cutoff) and np.all(hi1 >= lo2 - cutoff))
+
+
+def nxn_candidate_pairs(model, aabb_lower, aabb_upper, filter_pairs=(), include_static_kinematic_pairs: bool = True):
+    """Canonical (min, max) pairs ``_nxn_broadphase_kernel`` writes: the filter set intersected with AABB overlap."""
+    out = []
+    for s1, s2 in sorted(model_nxn_pairs(model, filter_pairs, include_static_kinematic_pairs)):
+        if check_aabb_overlap(aabb_lower[s1], aabb_upper[s1], aabb_lower[s2], aabb_upper[s2]):
+            out.append((s1, s2))
+    return out
+
+
+SAP_DIRECTION = np.array([0.5935, 0.7790, 0.1235], dtype=np.float32)
+
+
+def sap_candidate_pairs(model, aabb_lower, aabb_upper, filter_pairs=(), include_static_kinematic_pairs: bool = True):
+    """``BroadPhaseSAP.launch`` (broad_phase_sap.py:631-849): project, sort per world segment, range by binary search, sweep."""
+    shape_world, shape_flags = model.numpy("shape_world"), model.numpy("shape_flags")
+    group, shape_body = model.numpy("shape_collision_group"), model.numpy("shape_body")
+    body_flags = model.numpy("body_flags") if model.body_count else ()
+    index_map, slice_ends = precompute_world_map(shape_world, shape_flags)
+    excluded = {(min(a, b), max(a, b)) for a, b in filter_pairs}
+    d = SAP_DIRECTION / np.float32(np.sqrt(np.float32(np.dot(SAP_DIRECTION, SAP_DIRECTION))))
+    lo, hi = np.asarray(aabb_lower, dtype=np.float32), np.asarray(aabb_upper, dtype=np.float32)
+    half = np.float32(0.5) * (hi - lo)
+    radius = (np.abs(d)[None, :] * half).sum(axis=1, dtype=np.float32)
+    center = (d[None, :] * (np.float32(0.5) * (lo + hi))).sum(axis=1, dtype=np.float32)
+    plo, phi = center - radius, center + radius
+    num_regular = len(slice_ends) - 1
+    out = set()
+    start = 0
+    for segment, end in enumerate(slice_ends):
+        members = index_map[start:end]
+        order = sorted(range(len(members)), key=lambda k: (plo[members[k]], k))
+        lower_sorted = [plo[members[k]] for k in order]
+        for i, ki in enumerate(order):
+            upper = phi[members[ki]]
+            j = i + 1
+            while j < len(order) and lower_sorted[j] < upper:  # binary_search_segment: first lower >= upper ends the range
+                a, b = int(members[ki]), int(members[order[j]])
+                j += 1
+                if a == b:
+                    continue
+                s1, s2 = min(a, b), max(a, b)
+                w1, w2 = int(shape_world[s1]), int(shape_world[s2])
+                if w1 == -1 and w2 == -1 and segment < num_regular:
+                    continue
+                if not test_world_and_group_pair(w1, w2, int(group[s1]), int(group[s2])):
+                    continue
+                if is_shape_pair_immovable_filtered(s1, s2, shape_body, body_flags, include_static_kinematic_pairs):
+                    continue
+                if (s1, s2) in excluded:
+                    continue
+                if check_aabb_overlap(lo[s1], hi[s1], lo[s2], hi[s2]):
+                    out.add((s1, s2))
+        start = end
+    return sorted(out)

@@ -1,0 +1,98 @@
+"""oracle/contact_match.py - TEST INFRASTRUCTURE ONLY.
+
+NumPy restatement of the reference's frame-to-frame contact matcher in ``"latest"`` mode (``newton/_src/geometry/contact_match.py``:
+``_match_contacts_kernel`` :266-354, ``_resolve_claims_kernel`` :357-390, ``_save_sorted_state_kernel`` :442-477) on the sorted
+``Contacts`` arrays.  Sort keys follow ``make_contact_sort_key`` (``geometry/contact_data.py:59-87``) with the contact's position
+inside its pair's run as the sub key."""
+
+from __future__ import annotations
+
+import numpy as np
+
+MATCH_NOT_FOUND, MATCH_BROKEN = -1, -2
+
+
+def _qrot(q, v):
+    x, y, z, w = q
+    qv = np.array([x, y, z], dtype=np.float32)
+    v = np.asarray(v, dtype=np.float32)
+    return v * np.float32(2.0 * w * w - 1.0) + qv * np.float32(2.0 * np.dot(qv, v)) + np.cross(qv, v) * np.float32(2.0 * w)
+
+
+def _world(point, body, body_q):
+    if body == -1:
+        return np.asarray(point, dtype=np.float32)
+    X = body_q[body]
+    return _qrot(X[3:], point) + X[:3]
+
+
+class ContactMatcher:
+    def __init__(self, model, pos_threshold: float = 0.0005, normal_dot_threshold: float = 0.995):
+        self.shape_body = model.numpy("shape_body")
+        self.shape_world = model.numpy("shape_world")
+        self.world_count = int(model.world_count)
+        self.pos_threshold_sq = np.float32(pos_threshold) * np.float32(pos_threshold)
+        self.normal_dot_threshold = np.float32(normal_dot_threshold)
+        self.prev_keys = np.zeros(0, dtype=np.int64)
+        self.prev_pos = np.zeros((0, 3), dtype=np.float32)
+        self.prev_normal = np.zeros((0, 3), dtype=np.float32)
+        self.reset_mask = None
+
+    def reset(self, world_mask=None):
+        if world_mask is None:
+            self.prev_keys = self.prev_keys[:0]
+        else:
+            m = np.asarray(world_mask, dtype=bool)
+            self.reset_mask = m if self.reset_mask is None else (self.reset_mask | m)
+
+    def _selected(self, world):
+        if self.reset_mask is None:
+            return False
+        if 0 <= world < self.world_count:
+            return bool(self.reset_mask[world])
+        return world == -1 and bool(self.reset_mask[self.world_count])
+
+    def match(self, contacts, body_q):
+        """Returns match_index[:count] for the (sorted) contacts and stores them as the new history."""
+        n = min(int(contacts.rigid_contact_count[0]), contacts.rigid_contact_max)
+        s0, s1 = contacts.rigid_contact_shape0[:n].numpy().astype(np.int64), contacts.rigid_contact_shape1[:n].numpy().astype(np.int64)
+        p0, p1 = contacts.rigid_contact_point0[:n].numpy(), contacts.rigid_contact_point1[:n].numpy()
+        nrm = contacts.rigid_contact_normal[:n].numpy()
+        body_q = np.asarray(body_q, dtype=np.float32).reshape(-1, 7)
+        prefix = ((s0 & 0xFFFFF) << 43) | ((s1 & 0xFFFFF) << 23)
+        assert np.all(prefix[1:] >= prefix[:-1]), "contact matching needs key-sorted contacts (deterministic=True)"
+        keys = prefix.copy()
+        for i in range(n):
+            keys[i] |= i - int(np.searchsorted(prefix, prefix[i], side="left"))
+        pos = np.stack([np.float32(0.5) * (_world(p0[i], self.shape_body[s0[i]], body_q) + _world(p1[i], self.shape_body[s1[i]], body_q))
+                        for i in range(n)]) if n else np.zeros((0, 3), np.float32)
+        match = np.full(n, MATCH_NOT_FOUND, dtype=np.int32)
+        claim = {}
+        for i in range(n):
+            if len(self.prev_keys) == 0:
+                continue
+            if self._selected(int(self.shape_world[s0[i]])) or self._selected(int(self.shape_world[s1[i]])):
+                continue
+            lo = int(np.searchsorted(self.prev_keys, prefix[i], side="left"))
+            hi = int(np.searchsorted(self.prev_keys, prefix[i] + 0x800000, side="left"))
+            if lo >= hi:
+                continue
+            best, best_d = -1, self.pos_threshold_sq
+            for k in range(lo, hi):
+                diff = pos[i] - self.prev_pos[k]
+                dsq = np.float32(np.dot(diff, diff))
+                if dsq <= best_d and np.float32(np.dot(nrm[i], self.prev_normal[k])) >= self.normal_dot_threshold:
+                    best_d, best = dsq, k
+            if best >= 0:
+                match[i] = best
+                c = (float(best_d), int(keys[i]) & 0xFFFFFFFF)
+                if best not in claim or c < claim[best]:
+                    claim[best] = c
+            else:
+                match[i] = MATCH_BROKEN
+        for i in range(n):
+            if match[i] >= 0 and claim[int(match[i])][1] != (int(keys[i]) & 0xFFFFFFFF):
+                match[i] = MATCH_BROKEN
+        self.prev_keys, self.prev_pos, self.prev_normal = keys, pos.astype(np.float32), nrm.copy()
+        self.reset_mask = None
+        return match

@@ -330,6 +330,7 @@ struct OrcShard {
 };
 struct OrcLoop {
     int32_t solver;  // 0 = XPBD, 1 = Featherstone
+    int32_t deterministic;  // CollisionPipeline(deterministic=...): contacts in sort-key order (what the CUDA path always produces)
     int32_t substeps;
     float dt;
     nb2_xpbd_params xpbd;
@@ -363,7 +364,7 @@ void run_shard_frames(OrcShard& s, const OrcLoop& L, int frames) {
     const nb2_model_desc& m = *s.model;
     for (int i = 0; i < frames * L.substeps; ++i) {
         std::memset(s.state_0.body_f, 0, size_t(m.body_count) * 6 * sizeof(float));  // State.clear_forces (sim/state.py:189-200)
-        orc_collide(&m, s.state_0.body_q, &s.contacts, 0);
+        orc_collide(&m, s.state_0.body_q, &s.contacts, L.deterministic);
         if (L.solver == 0) orc_xpbd_step(&m, &L.xpbd, &s.state_0, &s.state_1, &s.control, &s.contacts, L.dt, nullptr);
         else orc_featherstone_step(s.featherstone, &m, &L.featherstone, &s.state_0, &s.state_1, &s.control, &s.contacts, L.dt);
         std::swap(s.state_0, s.state_1);

@@ -22,7 +22,7 @@ def _oracle_batch(oracle, model, make_solver, substeps, dt, shard_envs=32):
     while envs % n:
         n -= 1
     models = [model.shard(r, n) for r in range(n)] if n > 1 else [model]
-    pool = oracle.FramePool(models, make_solver, substeps=1, dt=dt, threads=min(os.cpu_count() or 1, n))
+    pool = oracle.FramePool(models, make_solver, substeps=1, dt=dt, threads=min(os.cpu_count() or 1, n), deterministic=True)
     pool.run_frames(substeps)
     states, contacts = pool.current_states(), pool.contacts()
     out = {name: np.concatenate([getattr(s, name).numpy() for s in states]) for name in ("body_q", "body_qd", "joint_q", "joint_qd")}
