@@ -224,11 +224,6 @@ static nb2_status build_tables(nb2_model* m, const nb2_model_desc& d) {
         for (int j = 0; j < J; ++j)
             if (jtype[j] == 6 && jdim[2 * j + 1] > 1) h.ik_supported = false;  // D6 with 2-3 angular axes
         if ((st = fetch(d.body_flags, size_t(B), bflags))) return st;
-        for (int b = 0; b < B; ++b)
-            if (bflags[b] & 2) {
-                h.featherstone_supported = false;
-                h.featherstone_reason = "kinematic bodies";
-            }
         for (int j = 0; j < J; ++j)
             if (jchild[j] != j) {  // the reference's spatial_mass indexes body_I_s by joint index (kernels.py:1476-1477)
                 h.featherstone_supported = false;

@@ -604,6 +604,10 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
         }
         __syncwarp(gmask);
     }
+    // zero_kinematic_body_forces (featherstone/kernels.py:55-63): a kinematic body ignores body_f, joint wrenches and contacts
+    for (int b = l; b < nb; b += L)
+        if (d.body_flags[b0 + b] & 2) st6(sm.fe + 6 * b, S6());
+    __syncwarp(gmask);
     NB2_PHASE();
     // ---- eval_rigid_tau (RNEA backward).  The drive / limit / damping terms do not depend on the force recursion: they are
     // evaluated for all dofs at once and parked in tau[]; the level loop only adds -S.f_s in the reference's order. ---------
@@ -772,7 +776,9 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
             __syncwarp(gmask);
             // dense_cholesky (kernels.py:1690-1719), in place on the lower triangle; columns in order, rows in parallel
             for (int jn = 0; jn < n; ++jn) {
-                float sdiag = H[jn * n + jn] + d.joint_armature[ad0 + jn];
+                // joint_armature_effective (solver_featherstone.py:269-281): 1e10 on the dofs of a joint driving a kinematic body
+                const bool kin_dof = (d.body_flags[d.joint_child[aj0 + M.dof_joint[ad0 + jn]]] & 2) != 0;
+                float sdiag = H[jn * n + jn] + (kin_dof ? 1.0e10f : d.joint_armature[ad0 + jn]);
                 for (int k = 0; k < jn; ++k) {
                     const float r = H[jn * n + k];
                     sdiag -= r * r;
@@ -817,6 +823,9 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
             }
         }
         __syncwarp(gmask);
+        for (int i = l; i < n; i += L)  // zero_kinematic_joint_qdd (kernels.py:1933-1948)
+            if (d.body_flags[d.joint_child[aj0 + M.dof_joint[ad0 + i]]] & 2) sm.qdd[ad0 - d0 + i] = 0.0f;
+        __syncwarp(gmask);
     }
     NB2_PHASE();
     // ---- integrate_generalized_joints (jcalc_integrate, kernels.py:464-630) ----------------------------------------
@@ -828,6 +837,11 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
         const float* qdd = sm.qdd - d0;
         float* qn = sm.jq - c0;
         float* qdn = sm.qd_out - d0;
+        if (d.body_flags[child] & 2) {  // copy_kinematic_joint_state (kernels.py:1951-1976): the prescribed state passes through
+            for (int i = cs; i < d.joint_q_start[gj + 1]; ++i) qn[i] = q[i];
+            for (int i = ds; i < d.joint_qd_start[gj + 1]; ++i) qdn[i] = qd[i];
+            continue;
+        }
         if (type == FJ_FIXED) continue;
         if (type == FJ_PRISMATIC || type == FJ_REVOLUTE) {
             const float qd_new = qd[ds] + qdd[ds] * dt;

@@ -308,6 +308,14 @@ inline void fs_init(const nb2_model_desc& m, FsScratch& s) {
     s.init = true;
 }
 
+// joint_armature_effective (solver_featherstone.py:269-281): dofs of a joint whose child body is kinematic get 1e10
+inline float armature_effective(const nb2_model_desc& m, int j0, int j1, int dof) {
+    for (int j = j0; j < j1; ++j)
+        if (dof >= m.joint_qd_start[j] && dof < m.joint_qd_start[j + 1])
+            return (m.body_flags[m.joint_child[j]] & BODY_KINEMATIC) ? 1.0e10f : m.joint_armature[dof];
+    return m.joint_armature[dof];
+}
+
 inline void featherstone_step(FsScratch& s, const nb2_model_desc& m, const nb2_featherstone_params& p, const nb2_state_view& sin,
                               const nb2_state_view& sout, const nb2_control_view& ctl, const nb2_contacts_view* contacts, float dt) {
     if (!s.init) fs_init(m, s);
@@ -496,7 +504,8 @@ inline void featherstone_step(FsScratch& s, const nb2_model_desc& m, const nb2_f
                     Hm[i * nd + jj] = sum;
                 }
             for (int jn = 0; jn < nd; ++jn) {  // dense_cholesky (kernels.py:1690-1719)
-                float sv = Hm[jn * nd + jn] + m.joint_armature[d0 + jn];
+                // joint_armature_effective (solver_featherstone.py:269-281): 1e10 on the dofs of joints that drive a kinematic body
+                float sv = Hm[jn * nd + jn] + armature_effective(m, j0, j1, d0 + jn);
                 for (int k = 0; k < jn; ++k) {
                     float r = Lm[jn * nd + k];
                     sv -= r * r;
@@ -531,6 +540,10 @@ inline void featherstone_step(FsScratch& s, const nb2_model_desc& m, const nb2_f
             x[i] = t / Lm[i * n + i];
         }
     }
+    // ---- zero_kinematic_joint_qdd (kernels.py:1933-1948)
+    for (int j = 0; j < J; ++j)
+        if (m.body_flags[m.joint_child[j]] & BODY_KINEMATIC)
+            for (int i = m.joint_qd_start[j]; i < m.joint_qd_start[j + 1]; ++i) s.joint_qdd[i] = 0.0f;
     // ---- integrate_generalized_joints (kernels.py:1849-1893, jcalc_integrate :464-630)
     for (int j = 0; j < J; ++j) {
         int type = m.joint_type[j], parent = m.joint_parent[j], child = m.joint_child[j];
@@ -594,6 +607,12 @@ inline void featherstone_step(FsScratch& s, const nb2_model_desc& m, const nb2_f
             }
         }
     }
+    // ---- copy_kinematic_joint_state (kernels.py:1951-1976): prescribed joint state passes through the solve
+    for (int j = 0; j < J; ++j)
+        if (m.body_flags[m.joint_child[j]] & BODY_KINEMATIC) {
+            for (int i = m.joint_q_start[j]; i < m.joint_q_start[j + 1]; ++i) sout.joint_q[i] = sin.joint_q[i];
+            for (int i = m.joint_qd_start[j]; i < m.joint_qd_start[j + 1]; ++i) s.joint_qd_out[i] = s.joint_qd_in[i];
+        }
     // ---- eval_fk_with_velocity_conversion (kernels.py:1987-2149) -> state_out.body_q / body_qd
     for (int a = 0; a < A; ++a)
         for (int i = m.articulation_start[a]; i < art_end(a); ++i) {

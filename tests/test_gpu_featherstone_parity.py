@@ -124,3 +124,69 @@ def test_eval_ik_kernel_bit_exact(oracle_lib, cuda_lib):
         newton_b200.eval_fk(mg, mg.joint_q, mg.joint_qd, sg)
         newton_b200.eval_ik(mg, sg, q, qd)
         np.testing.assert_allclose(q.cpu().numpy(), mg.joint_q.cpu().numpy(), atol=1e-6)
+
+
+def test_kinematic_bodies_and_in_place_stepping_bit_exact(oracle_lib, cuda_lib):
+    """Kinematic links under SolverFeatherstone (solver_featherstone.py:212-281, kernels.py:55-63, 1933-1976): a kinematic free base
+    with prescribed joint state pushing a dynamic probe, a kinematic revolute root carrying a dynamic pendulum and a kinematic
+    fixed root - effective armature 1e10, zeroed accelerations, joint state copied through, body forces ignored.  The GPU run
+    steps IN PLACE (state_in is state_out, solver_featherstone.py:472) and must still equal the oracle's two-state run."""
+    import torch
+
+    from newton_b200 import ModelBuilder
+    from newton_b200.utils import xform as X
+
+    b = ModelBuilder(gravity=(0.0, 0.0, 0.0))  # like the reference scenes (test_kinematic_links.py:304-398)
+    b.default_shape_cfg.ke, b.default_shape_cfg.kd, b.default_shape_cfg.kf = 1.0e4, 500.0, 0.5
+    for w in range(3):
+        b.begin_world()
+        kin = b.add_body(xform=X.transform((-0.3, 0.0, 0.5)), mass=1.0, is_kinematic=True)
+        b.add_shape_box(kin, hx=0.25, hy=0.15, hz=0.15)
+        probe = b.add_body(xform=X.transform((0.1 + 0.02 * w, 0.0, 0.5)), mass=1.0)
+        b.add_shape_sphere(probe, radius=0.1)
+        root = b.add_link(xform=X.transform((0.0, 1.0, 1.0)), mass=1.0, inertia=np.eye(3) * 0.1, is_kinematic=True)
+        pend = b.add_link(xform=X.transform((0.45, 1.0, 1.0)), mass=1.0, inertia=np.eye(3) * 0.1)
+        j0 = b.add_joint_revolute(-1, root, axis=(0.0, 1.0, 0.0), parent_xform=X.transform((0.0, 1.0, 1.0)))
+        j1 = b.add_joint_revolute(root, pend, axis=(0.0, 1.0, 0.0), parent_xform=X.transform((0.45, 0.0, 0.0)))
+        b.add_articulation([j0, j1])
+        b.add_shape_sphere(pend, xform=X.transform((0.3, 0.0, 0.0)), radius=0.1)
+        fixed = b.add_link(xform=X.transform((0.0, -1.0, 0.3)), mass=1.0, inertia=np.eye(3) * 0.1, is_kinematic=True)
+        b.add_articulation([b.add_joint_fixed(-1, fixed, parent_xform=X.transform((0.0, -1.0, 0.3)))])
+        b.add_shape_box(fixed, hx=0.25, hy=0.25, hz=0.25)
+        b.end_world()
+    b.add_ground_plane()
+    model = b.finalize()
+    scenes.host_fk(model, model.joint_q, model.joint_qd, model)
+    mg = model.to("cuda:0")
+    kin_q0 = int(model.joint_q_start[0])
+    dt = 1.0 / 480.0
+
+    def run(m, pipeline_cls, solver_cls, in_place):
+        solver, pipe = solver_cls(m, angular_damping=0.0), pipeline_cls(m)
+        s0, s1, contacts = m.state(), m.state(), pipe.contacts()
+        per_world_q = m.joint_coord_count // 3
+        per_world_qd = m.joint_dof_count // 3
+        for i in range(120):
+            for w in range(3):  # prescribed motion of the kinematic free base (generalized coordinates, like the reference test)
+                s0.joint_q[w * per_world_q + kin_q0] = -0.3 + 1.0 * i * dt
+                s0.joint_qd[w * per_world_qd] = 1.0
+                s0.joint_qd[w * per_world_qd + 12] = 2.0  # the kinematic revolute root keeps turning
+            s0.clear_forces()
+            s0.body_f[0] = torch.tensor([20.0, -15.0, 10.0, 0.5, -0.4, 0.3], device=s0.body_f.device)  # ignored: body 0 is kinematic
+            pipe.collide(s0, contacts)
+            if in_place:
+                solver.step(s0, s0, None, contacts, dt)
+            else:
+                solver.step(s0, s1, None, contacts, dt)
+                s0, s1 = s1, s0
+        return s0
+
+    ref = run(model, oracle_lib.CollisionPipeline, oracle_lib.SolverFeatherstone, False)
+    assert int(model.joint_qd_start[2]) == 12  # dof 12 = the revolute root joint of world 0 (two 6-dof free joints before it)
+    for in_place in (False, True):
+        got = run(mg, newton_b200.CollisionPipeline, newton_b200.solvers.SolverFeatherstone, in_place)
+        for name in ("joint_q", "joint_qd", "body_q", "body_qd"):
+            np.testing.assert_array_equal(getattr(got, name).cpu().numpy(), getattr(ref, name).numpy(), err_msg=f"{name} in_place={in_place}")
+    q = ref.body_q.numpy().reshape(3, -1, 7)
+    assert abs(q[0, 0, 0] - (-0.3 + 119 * dt)) < 0.05 and abs(q[0, 0, 2] - 0.5) < 1e-4  # prescribed, does not fall
+    assert q[0, 1, 0] > 0.15  # the probe was pushed

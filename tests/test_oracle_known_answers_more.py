@@ -1258,7 +1258,10 @@ def _contact_defaults(builder):
     builder.default_shape_cfg.ke, builder.default_shape_cfg.kd, builder.default_shape_cfg.kf = 1.0e4, 500.0, 0.5
 
 
-def _kin_solver(oracle_lib, model):
+def _kin_solver(oracle_lib, model, name="xpbd"):
+    """The `solvers` table of the reference test (:716-724), in-scope rows."""
+    if name == "featherstone":
+        return oracle_lib.SolverFeatherstone(model, angular_damping=0.0)
     return oracle_lib.SolverXPBD(model, iterations=5, angular_damping=0.0)
 
 
@@ -1266,8 +1269,9 @@ def _quat_close(qa, qb, min_dot):
     assert abs(float(np.dot(qa, qb))) > min_dot
 
 
-def test_kinematic_free_base_prescribed_motion_xpbd(oracle_lib):
-    """:400-481"""
+@pytest.mark.parametrize("solver_name", ["xpbd", "featherstone"])
+def test_kinematic_free_base_prescribed_motion_xpbd(oracle_lib, solver_name):
+    """:400-481 (SolverFeatherstone: effective armature 1e10, zeroed qdd and the copied-through joint state of the kinematic joint)"""
     dt, steps, x0, vx = 1.0 / 240.0, 100, -0.3, 1.0
 
     def run_once(apply_force):
@@ -1280,7 +1284,7 @@ def test_kinematic_free_base_prescribed_motion_xpbd(oracle_lib):
         model = builder.finalize()
         joint = int(np.flatnonzero(model.numpy("joint_child") == kin)[0])
         qs, qds = int(model.joint_q_start[joint]), int(model.joint_qd_start[joint])
-        solver = _kin_solver(oracle_lib, model)
+        solver = _kin_solver(oracle_lib, model, solver_name)
         pipe = oracle_lib.CollisionPipeline(model)
         contacts = pipe.contacts()
         s0, s1 = model.state(), model.state()
@@ -1360,7 +1364,8 @@ def test_kinematic_revolute_root_pendulum_prescribed_motion_xpbd(oracle_lib):
     assert free["probe_max_speed"] > 2e-2 and free["probe_displacement"] > 1e-2 and free["pendulum_max_speed"] > 2e-2
 
 
-def test_kinematic_fixed_root_is_immune_to_forces_and_stops_the_probe_xpbd(oracle_lib):
+@pytest.mark.parametrize("solver_name", ["xpbd", "featherstone"])
+def test_kinematic_fixed_root_is_immune_to_forces_and_stops_the_probe_xpbd(oracle_lib, solver_name):
     """:578-638"""
     dt, steps, probe_vx = 1.0 / 240.0, 140, 3.0
 
@@ -1375,7 +1380,7 @@ def test_kinematic_fixed_root_is_immune_to_forces_and_stops_the_probe_xpbd(oracl
         model = builder.finalize()
         joint = int(np.flatnonzero(model.numpy("joint_child") == probe)[0])
         qds = int(model.joint_qd_start[joint])
-        solver = _kin_solver(oracle_lib, model)
+        solver = _kin_solver(oracle_lib, model, solver_name)
         pipe = oracle_lib.CollisionPipeline(model)
         contacts = pipe.contacts()
         s0, s1 = model.state(), model.state()
@@ -1403,13 +1408,14 @@ def test_kinematic_fixed_root_is_immune_to_forces_and_stops_the_probe_xpbd(oracl
     assert free["probe_pos"][0] < 0.25 and abs(free["probe_qd"][0] - probe_vx) > 2.5e-1  # the probe hit the box
 
 
-def test_kinematic_runtime_toggle_xpbd(oracle_lib):
+@pytest.mark.parametrize("solver_name", ["xpbd", "featherstone"])
+def test_kinematic_runtime_toggle_xpbd(oracle_lib, solver_name):
     """:641-715 - body_flags edited at run time + notify_model_changed(BODY_PROPERTIES)."""
     builder = ModelBuilder(gravity=(0.0, 0.0, 0.0))
     body = builder.add_body(xform=X.transform((0.0, 0.0, 0.0)), mass=1.0, is_kinematic=True, label="toggle_body")
     builder.add_shape_sphere(body, radius=0.1)
     model = builder.finalize()
-    solver = _kin_solver(oracle_lib, model)
+    solver = _kin_solver(oracle_lib, model, solver_name)
     pipe = oracle_lib.CollisionPipeline(model)
     contacts = pipe.contacts()
     s0, s1 = model.state(), model.state()
