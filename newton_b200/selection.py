@@ -6,8 +6,10 @@ Model / State / Control attribute of the selection as a ``[world, articulation, 
 (``get_root_transforms``, ``get_dof_positions`` ...) and masked resets in (``set_root_transforms(..., mask=done)``,
 ``set_dof_positions`` ..., ``eval_fk(state, mask=done)``).  SURVEY.md §8(f) rank 2.
 
-Host side (this file): label matching and the layout bookkeeping (``FrequencyLayout``: offset, stride between worlds,
-stride within a world, selected value indices), the same decisions as the reference's constructor.  Device side
+Host side (this file): label matching and the layout bookkeeping - ``_Extents`` tabulates where every selected articulation's
+joints / dofs / coords / links / shapes start (NumPy, ``[world, articulation]`` arrays), the uniformity checks and strides are
+differences of those tables, and ``FrequencyLayout`` records the result per attribute frequency.  The decisions (what counts as
+"identical", which layouts are refused, the selector grammar) are the reference constructor's; the code is not.  Device side
 (``csrc/nb2_selection.cu`` through ``nb2_view_gather`` / ``nb2_view_scatter`` / ``nb2_view_articulation_mask`` /
 ``nb2_eval_fk_masked``): every copy that is not a zero-copy view.  As in the reference, a contiguous selection is returned
 as a strided *view* of the attribute (writes through it alias the source array); an index-selected (non-contiguous)
@@ -33,107 +35,30 @@ from .sim.enums import JointType
 from .sim.model import AttributeFrequency, Model
 
 
-class Slice:
-    """Hashable ``slice`` stand-in (reference ``selection.py:328-343``)."""
-
-    def __init__(self, start=None, stop=None):
-        self.start = start
-        self.stop = stop
-
-    def __hash__(self):
-        return hash((self.start, self.stop))
-
-    def __eq__(self, other):
-        return isinstance(other, Slice) and self.start == other.start and self.stop == other.stop
-
-    def __str__(self):
-        return f"({self.start}, {self.stop})"
-
-    def get(self):
-        return slice(self.start, self.stop)
-
-
-def is_contiguous_slice(indices) -> bool:
-    return all(indices[i] == indices[i - 1] + 1 for i in range(1, len(indices)))
-
-
-class FrequencyLayout:
-    """Where the selected values of one attribute frequency live (reference ``selection.py:346-382``)."""
-
-    def __init__(self, offset: int, stride_between_worlds: int, stride_within_worlds: int, value_count: int, indices: list[int], device):
-        self.offset = offset  # values to skip at the beginning of the attribute array
-        self.stride_between_worlds = stride_between_worlds
-        self.stride_within_worlds = stride_within_worlds
-        self.value_count = value_count  # values per articulation before selection
-        self.slice = None
-        self.indices = None
-        if len(indices) == 0:
-            self.slice = slice(0, 0)
-        elif is_contiguous_slice(indices):
-            self.slice = slice(indices[0], indices[-1] + 1)
-        else:
-            self.indices = torch.tensor(indices, dtype=torch.int32, device=device)
-
-    @property
-    def is_contiguous(self) -> bool:
-        return self.slice is not None
-
-    @property
-    def selected_value_count(self) -> int:
-        return self.slice.stop - self.slice.start if self.slice is not None else len(self.indices)
-
-    def __str__(self):
-        indices = self.indices if self.indices is not None else self.slice
-        return (f"FrequencyLayout(\n    offset: {self.offset}\n    stride_between_worlds: {self.stride_between_worlds}\n"
-                f"    stride_within_worlds: {self.stride_within_worlds}\n    indices: {indices}\n)")
-
-
 def get_name_from_label(label: str) -> str:
-    """Leaf component of a slash-delimited label (reference ``selection.py:385-394``)."""
+    """Leaf component of a slash-delimited label."""
     return label.rsplit("/", maxsplit=1)[-1]
 
 
 def match_labels(labels: list[str], pattern) -> list[int]:
-    """Indices of the labels matching a glob string, list of globs, compiled regex (full match) or list of indices
-    (reference ``selection.py:426-473``)."""
+    """Indices of ``labels`` selected by ``pattern`` - the selector grammar of the reference (``utils/selection.py:426-473``):
+    a glob string, a compiled regular expression (must match the WHOLE label), a list of globs (union, label order, no
+    duplicates) or a list of integer indices (returned as given, unchecked)."""
+    def by_predicate(accept):
+        return [i for i, label in enumerate(labels) if accept(label)]
+
     if isinstance(pattern, str):
-        return [idx for idx, label in enumerate(labels) if fnmatch(label, pattern)]
+        return by_predicate(lambda label: fnmatch(label, pattern))
     if isinstance(pattern, re.Pattern):
-        return [idx for idx, label in enumerate(labels) if pattern.fullmatch(label) is not None]
+        return by_predicate(lambda label: pattern.fullmatch(label) is not None)
     if not isinstance(pattern, list):
-        raise TypeError("Expected a glob string, list of glob strings, compiled string pattern, "
-                        f"or list of int indices, got: {type(pattern)}")
-    if len(pattern) == 0:
+        raise TypeError(f"Expected a glob string, list of glob strings, compiled string pattern, or list of int indices, got: {type(pattern)}")
+    kinds = {type(item) for item in pattern}
+    if not kinds or kinds == {int}:
         return pattern
-    if isinstance(pattern[0], int):
-        if all(isinstance(item, int) for item in pattern):
-            return pattern
-    elif all(isinstance(item, str) for item in pattern):
-        return [idx for idx, label in enumerate(labels) if any(fnmatch(label, item) for item in pattern)]
-    types = {type(item).__name__ for item in pattern}
-    raise TypeError(f"Expected a list of str patterns or a list of int indices, got: {', '.join(sorted(types))}")
-
-
-def find_matching_ids(pattern, labels, world_ids, world_count: int):
-    """Matching ids grouped by world + those of the global world -1 (reference ``selection.py:397-423``)."""
-    matching_ids = match_labels(labels, pattern)
-    if isinstance(pattern, list) and pattern and isinstance(pattern[0], int):
-        for idx in range(1, len(matching_ids)):
-            if matching_ids[idx] <= matching_ids[idx - 1]:
-                raise ValueError("Articulation indices must be unique and in ascending order")
-        if matching_ids[0] < 0 or matching_ids[-1] >= len(labels):
-            raise ValueError(f"Articulation indices must be in range [0, {len(labels)})")
-    grouped_ids = [[] for _ in range(world_count)]
-    global_ids = []
-    for idx in matching_ids:
-        world = int(world_ids[idx])
-        if world == -1:
-            global_ids.append(idx)
-        elif 0 <= world < world_count:
-            grouped_ids[world].append(idx)
-        else:
-            raise ValueError(f"World index out of range: {world}")
-    return grouped_ids, global_ids
+    if kinds == {str}:
+        return by_predicate(lambda label: any(fnmatch(label, glob) for glob in pattern))
+    raise TypeError("Expected a list of str patterns or a list of int indices, got: " + ", ".join(sorted(k.__name__ for k in kinds)))
 
 
 def _same_device(a, b) -> bool:
@@ -141,18 +66,83 @@ def _same_device(a, b) -> bool:
     return a.type == b.type and (a.index or 0) == (b.index or 0)
 
 
-def _all_equal(values) -> bool:
-    return all(x == values[0] for x in values)
+class FrequencyLayout:
+    """Addressing of one attribute frequency (joint, dof, coord, body, shape) through a view: selected value ``k`` of
+    articulation ``a`` of world ``w`` is element ``offset + w * stride_between_worlds + a * stride_within_worlds + sel(k)`` of
+    the attribute array.  A selection that is a run of consecutive values is kept as ``slice`` (served as a zero-copy strided
+    view); anything else as a device index array ``indices`` (served by the gather / scatter kernels).  Attribute names follow
+    the reference class of the same name so that code written against it keeps reading ``view.frequency_layouts[...]``."""
+
+    __slots__ = ("offset", "stride_between_worlds", "stride_within_worlds", "value_count", "slice", "indices")
+
+    def __init__(self, offset: int, stride_between_worlds: int, stride_within_worlds: int, value_count: int, selection, device):
+        self.offset, self.value_count = int(offset), int(value_count)  # value_count: values per articulation BEFORE selection
+        self.stride_between_worlds, self.stride_within_worlds = int(stride_between_worlds), int(stride_within_worlds)
+        sel = np.asarray(selection, dtype=np.int64)
+        self.slice = self.indices = None
+        if sel.size == 0:
+            self.slice = slice(0, 0)
+        elif np.all(np.diff(sel) == 1):
+            self.slice = slice(int(sel[0]), int(sel[-1]) + 1)
+        else:
+            self.indices = torch.tensor(sel.tolist(), dtype=torch.int32, device=device)
+
+    @property
+    def is_contiguous(self) -> bool:
+        return self.slice is not None
+
+    @property
+    def selected_value_count(self) -> int:
+        return self.slice.stop - self.slice.start if self.slice is not None else int(self.indices.numel())
+
+    def __repr__(self):
+        sel = self.slice if self.indices is None else self.indices.tolist()
+        return (f"FrequencyLayout(offset={self.offset}, between_worlds={self.stride_between_worlds}, "
+                f"within_worlds={self.stride_within_worlds}, values={self.value_count}, selection={sel})")
 
 
-def _uniform_stride(starts, what: str) -> int | None:
-    """The common difference of consecutive starts, or ``None`` when there is only one."""
-    strides = [starts[i] - starts[i - 1] for i in range(1, len(starts))]
-    if not strides:
-        return None
-    if not _all_equal(strides):
-        raise ValueError(f"Non-uniform strides {what} are not supported")
-    return strides[0]
+class _Extents:
+    """Where each selected articulation's joints / dofs / coords / links / shapes start and how many there are, as
+    ``[world, articulation]`` integer arrays - everything the uniformity checks and the strides are derived from."""
+
+    KINDS = ("joint", "dof", "coord", "link", "shape")
+
+    def __init__(self, model: Model, ids: np.ndarray, closing_joints: bool):
+        first = model.numpy("articulation_start").astype(np.int64)
+        last = first[1:] if closing_joints else model.numpy("articulation_end").astype(np.int64)
+        q0, qd0 = model.numpy("joint_q_start").astype(np.int64), model.numpy("joint_qd_start").astype(np.int64)
+        child, jtype = model.numpy("joint_child"), model.numpy("joint_type")
+        lo, hi = first[ids], last[ids]
+        self.start = {"joint": lo, "dof": qd0[lo], "coord": q0[lo]}
+        self.count = {"joint": hi - lo, "dof": qd0[hi] - qd0[lo], "coord": q0[hi] - q0[lo]}
+        self.root_type = jtype[lo]
+        link_lo, link_n, shape_lo, shape_n = (np.zeros(ids.shape, dtype=np.int64) for _ in range(4))
+        for where in np.ndindex(ids.shape):
+            links = np.unique(child[lo[where] : hi[where]])
+            shapes = [s for b in links.tolist() for s in model.body_shapes.get(b, [])]
+            link_lo[where], link_n[where] = links.min(), links.size
+            shape_lo[where], shape_n[where] = (min(shapes) if shapes else -1), len(shapes)
+        self.start.update(link=link_lo, shape=shape_lo)
+        self.count.update(link=link_n, shape=shape_n)
+
+    def identical(self) -> bool:
+        return all(np.all(c == c.flat[0]) for c in (*self.count.values(), self.root_type))
+
+    def strides(self, kind: str, fallback: int) -> tuple[int, int]:
+        """(between worlds, within a world); ``fallback`` where there is nothing to take a difference of."""
+        s = self.start[kind]
+        outer = inner = fallback
+        if s.shape[0] > 1:
+            d = np.diff(s[:, 0])
+            if np.any(d != d[0]):
+                raise ValueError("Non-uniform strides between worlds are not supported")
+            outer = int(d[0])
+        if s.shape[1] > 1:
+            d = np.diff(s, axis=1)
+            if np.any(d != d.flat[0]):
+                raise ValueError("Non-uniform strides within worlds are not supported")
+            inner = int(d.flat[0])
+        return outer, inner
 
 
 class _Plan:
@@ -162,7 +152,8 @@ class _Plan:
 
 
 class ArticulationView:
-    """Selection of identical articulations across worlds (reference ``selection.py:500-561`` for the contract).
+    """Selection of identical articulations across worlds (contract of reference ``newton.selection.ArticulationView``,
+    ``utils/selection.py:500-561``).
 
     ``pattern`` is matched against full articulation labels; ``include_joints`` / ``exclude_joints`` / ``include_links`` /
     ``exclude_links`` against the leaf component of joint / body labels (glob, list of globs, compiled regex, or indices);
@@ -175,222 +166,158 @@ class ArticulationView:
         self.model = model
         self.device = model.device
         self._plans: dict = {}
-        for parameter_name, indices in (("include_joints", include_joints), ("include_links", include_links)):
-            if (isinstance(indices, list) and all(isinstance(index, int) for index in indices)
-                    and any(indices[i] < indices[i - 1] for i in range(1, len(indices)))):
-                warnings.warn(f"Passing unsorted integer indices to ArticulationView({parameter_name}=...) is deprecated and "
-                              "will raise a ValueError in a future release. Sort the indices in ascending order before passing them.",
+        for arg, value in (("include_joints", include_joints), ("include_links", include_links)):
+            if isinstance(value, list) and value and all(isinstance(v, int) for v in value) and value != sorted(value):
+                warnings.warn(f"Passing unsorted integer indices to ArticulationView({arg}=...) is deprecated and will raise a "
+                              "ValueError in a future release. Sort the indices in ascending order before passing them.",
                               DeprecationWarning, stacklevel=2)
 
-        art_start = model.numpy("articulation_start")
-        art_end = model.numpy("articulation_end")
-        art_world = model.numpy("articulation_world")
-        joint_type = model.numpy("joint_type")
-        joint_child = model.numpy("joint_child")
-        q_start = model.numpy("joint_q_start")
-        qd_start = model.numpy("joint_qd_start")
-
-        articulation_ids, global_articulation_ids = find_matching_ids(pattern, model.articulation_label, art_world, model.world_count)
-        world_count = model.world_count
-        counts_per_world = [len(ids) for ids in articulation_ids]
-        articulation_count = sum(counts_per_world)
-        if articulation_count > 0 and global_articulation_ids:
-            raise ValueError(f"Articulation pattern '{pattern}' matches global and per-world articulations, which is currently not supported")
-        if articulation_count == 0 and global_articulation_ids:  # scenes with only global articulations
-            world_count = 1
-            articulation_count = len(global_articulation_ids)
-            counts_per_world = [articulation_count]
-            articulation_ids = [global_articulation_ids]
-        if articulation_count == 0:
-            raise KeyError(f"No articulations matching pattern '{pattern}'")
-        if not _all_equal(counts_per_world):
-            raise ValueError("Varying articulation counts per world are not supported")
-        count_per_world = counts_per_world[0]
-
-        def joint_range(arti_id):
-            begin = int(art_start[arti_id])
-            end = int(art_start[arti_id + 1]) if include_loop_closing_joints else int(art_end[arti_id])
-            return begin, end
-
-        # the first articulation is the template for names and selections
-        arti_0 = articulation_ids[0][0]
-        arti_joint_begin, arti_joint_end = joint_range(arti_0)
-        arti_joint_count = arti_joint_end - arti_joint_begin
-        arti_joint_dof_count = int(qd_start[arti_joint_end]) - int(qd_start[arti_joint_begin])
-        arti_joint_coord_count = int(q_start[arti_joint_end]) - int(q_start[arti_joint_begin])
-        arti_joint_ids = list(range(arti_joint_begin, arti_joint_end))
-        arti_joint_labels = [model.joint_label[j] for j in arti_joint_ids]
-        arti_joint_names = [get_name_from_label(label) for label in arti_joint_labels]
-        arti_joint_types = [int(joint_type[j]) for j in arti_joint_ids]
-        arti_link_ids = sorted({int(joint_child[j]) for j in arti_joint_ids})  # unique bodies, in model order
-        arti_link_count = len(arti_link_ids)
-        arti_link_labels = [model.body_label[b] for b in arti_link_ids]
-        arti_link_names = [get_name_from_label(label) for label in arti_link_labels]
-        arti_shape_ids = sorted(s for b in arti_link_ids for s in model.body_shapes.get(b, []))
-        arti_shape_count = len(arti_shape_ids)
-        arti_shape_labels = [model.shape_label[s] for s in arti_shape_ids]
-        arti_shape_names = [get_name_from_label(label) for label in arti_shape_labels]
-
-        # per-articulation starts and counts; every articulation must look like the template
-        starts = {k: [[] for _ in range(world_count)] for k in ("joint", "dof", "coord", "link", "shape")}
-        counts = {k: [[] for _ in range(world_count)] for k in ("joint", "dof", "coord", "link", "shape", "root_type")}
-        for world_id in range(world_count):
-            for arti_id in articulation_ids[world_id]:
-                joint_start, joint_end = joint_range(arti_id)
-                starts["joint"][world_id].append(joint_start)
-                counts["joint"][world_id].append(joint_end - joint_start)
-                starts["dof"][world_id].append(int(qd_start[joint_start]))
-                counts["dof"][world_id].append(int(qd_start[joint_end]) - int(qd_start[joint_start]))
-                starts["coord"][world_id].append(int(q_start[joint_start]))
-                counts["coord"][world_id].append(int(q_start[joint_end]) - int(q_start[joint_start]))
-                counts["root_type"][world_id].append(int(joint_type[joint_start]))
-                link_ids = sorted({int(joint_child[j]) for j in range(joint_start, joint_end)})
-                shape_ids = [s for b in link_ids for s in model.body_shapes.get(b, [])]
-                starts["link"][world_id].append(min(link_ids))
-                counts["link"][world_id].append(len(link_ids))
-                starts["shape"][world_id].append(min(shape_ids) if shape_ids else -1)
-                counts["shape"][world_id].append(len(shape_ids))
-        if not all(_all_equal(counts[k]) for k in counts):
+        ids = self._select_articulations(model, pattern)  # [world, articulation] Model articulation ids
+        self.world_count, self.count_per_world = ids.shape
+        self.count = ids.size
+        ext = _Extents(model, ids, include_loop_closing_joints)
+        if not ext.identical():
             raise ValueError("Articulations are not identical")
 
-        self.root_joint_type = counts["root_type"][0][0]
-        root_joint_dof_count = int(qd_start[arti_joint_begin + 1] - qd_start[arti_joint_begin])
-        self.is_fixed_base = root_joint_dof_count == 0  # every root degree of freedom locked
+        # ---- the first selected articulation is the template: names, types and what the selectors are matched against
+        t_joint0, t_dof0, t_coord0 = (int(ext.start[k][0, 0]) for k in ("joint", "dof", "coord"))
+        t_joints = list(range(t_joint0, t_joint0 + int(ext.count["joint"][0, 0])))
+        joint_child, joint_type = model.numpy("joint_child"), model.numpy("joint_type")
+        q_start, qd_start = model.numpy("joint_q_start"), model.numpy("joint_qd_start")
+        t_links = sorted({int(joint_child[j]) for j in t_joints})
+        t_shapes = sorted(s for b in t_links for s in model.body_shapes.get(b, []))
+        joint_leaf = [get_name_from_label(model.joint_label[j]) for j in t_joints]
+        link_leaf = [get_name_from_label(model.body_label[b]) for b in t_links]
+        per_articulation = {"joint": len(t_joints), "dof": int(ext.count["dof"][0, 0]), "coord": int(ext.count["coord"][0, 0]),
+                            "link": len(t_links), "shape": len(t_shapes)}
+        offsets = {k: int(ext.start[k][0, 0]) for k in _Extents.KINDS}
+        if not t_shapes:
+            offsets["shape"] = 0
+        strides = {k: ext.strides(k, per_articulation[k]) for k in _Extents.KINDS}
+
+        self.root_joint_type = int(ext.root_type[0, 0])
+        self.is_fixed_base = int(qd_start[t_joint0 + 1]) == int(qd_start[t_joint0])  # a root joint without degrees of freedom
         self.is_floating_base = self.root_joint_type in (JointType.FREE, JointType.DISTANCE)
 
-        arti_counts = {"joint": arti_joint_count, "dof": arti_joint_dof_count, "coord": arti_joint_coord_count, "link": arti_link_count,
-                       "shape": arti_shape_count}
-        offsets = {k: starts[k][0][0] for k in starts}
-        if arti_shape_count == 0:
-            offsets["shape"] = 0
-        outer, inner = {}, {}
-        for k in starts:  # strides between worlds / within a world must be uniform
-            stride = _uniform_stride([starts[k][w][0] for w in range(world_count)], "between worlds") if world_count > 1 else None
-            outer[k] = arti_counts[k] if stride is None else stride
-            if count_per_world > 1:
-                per_world = [_uniform_stride(starts[k][w], "within worlds") for w in range(world_count)]
-                if not _all_equal(per_world):
-                    raise ValueError("Non-uniform strides within worlds are not supported")
-                inner[k] = per_world[0]
-            else:
-                inner[k] = arti_counts[k]
+        # ---- joint / link selectors -> local indices inside the template
+        def resolve(selector, names, what):
+            picked = match_labels(names, selector)
+            for i in picked:
+                if not 0 <= i < len(names):
+                    raise ValueError(f"{what} indices must be in range [0, {len(names)}), got {i}")
+            return set(picked)
 
-        # joint / link selections (local indices inside the template articulation)
+        types = [int(joint_type[j]) for j in t_joints]
         if include_joints is None and include_joint_types is None:
-            joint_include = set(range(arti_joint_count))
+            keep_joints = set(range(len(t_joints)))
         else:
-            joint_include = set()
-            if include_joints is not None:
-                matching = match_labels(arti_joint_names, include_joints)
-                for index in matching:
-                    if index < 0 or index >= arti_joint_count:
-                        raise ValueError(f"include_joints indices must be in range [0, {arti_joint_count}), got {index}")
-                joint_include.update(matching)
+            keep_joints = resolve(include_joints, joint_leaf, "include_joints") if include_joints is not None else set()
             if include_joint_types is not None:
-                joint_include.update(idx for idx in range(arti_joint_count) if arti_joint_types[idx] in include_joint_types)
-        joint_exclude = set()
+                keep_joints |= {i for i, t in enumerate(types) if t in include_joint_types}
         if exclude_joints is not None:
-            joint_exclude.update(idx for idx in match_labels(arti_joint_names, exclude_joints) if 0 <= idx < arti_joint_count)
+            keep_joints -= {i for i in match_labels(joint_leaf, exclude_joints) if 0 <= i < len(t_joints)}
         if exclude_joint_types is not None:
-            joint_exclude.update(idx for idx in range(arti_joint_count) if arti_joint_types[idx] in exclude_joint_types)
-        if include_links is None:
-            link_include = set(range(arti_link_count))
-        else:
-            matching = match_labels(arti_link_names, include_links)
-            for index in matching:
-                if index < 0 or index >= arti_link_count:
-                    raise ValueError(f"include_links indices must be in range [0, {arti_link_count}), got {index}")
-            link_include = set(matching)
-        link_exclude = set()
+            keep_joints -= {i for i, t in enumerate(types) if t in exclude_joint_types}
+        keep_links = set(range(len(t_links))) if include_links is None else resolve(include_links, link_leaf, "include_links")
         if exclude_links is not None:
-            link_exclude.update(idx for idx in match_labels(arti_link_names, exclude_links) if 0 <= idx < arti_link_count)
-        selected_joint_indices = sorted(joint_include - joint_exclude)
-        selected_link_indices = sorted(link_include - link_exclude)
+            keep_links -= {i for i in match_labels(link_leaf, exclude_links) if 0 <= i < len(t_links)}
+        sel_joints, sel_links = sorted(keep_joints), sorted(keep_links)
 
-        # names and value indices of what was selected
-        self.joint_names, self.joint_labels = [], []
-        self.joint_dof_names, self.joint_dof_counts = [], []
-        self.joint_coord_names, self.joint_coord_counts = [], []
-        selected_dof_indices, selected_coord_indices = [], []
-        for joint_idx in selected_joint_indices:
-            joint_id = arti_joint_ids[joint_idx]
-            name = arti_joint_names[joint_idx]
-            self.joint_names.append(name)
-            self.joint_labels.append(arti_joint_labels[joint_idx])
-            for starts_arr, offset, names, counts_out, selected in (
-                (qd_start, offsets["dof"], self.joint_dof_names, self.joint_dof_counts, selected_dof_indices),
-                (q_start, offsets["coord"], self.joint_coord_names, self.joint_coord_counts, selected_coord_indices),
-            ):
-                begin, end = int(starts_arr[joint_id]), int(starts_arr[joint_id + 1])
-                counts_out.append(end - begin)
-                if end - begin == 1:
-                    names.append(name)
-                    selected.append(begin - offset)
-                else:
-                    for k in range(end - begin):
-                        names.append(f"{name}:{k}")
-                        selected.append(begin + k - offset)
-        self.link_names, self.link_labels, self.link_shapes = [], [], []
-        selected_shape_indices, shape_link_idx = [], {}
-        for link_idx, arti_link_idx in enumerate(selected_link_indices):
-            body_id = arti_link_ids[arti_link_idx]
-            self.link_names.append(arti_link_names[arti_link_idx])
-            self.link_labels.append(arti_link_labels[arti_link_idx])
-            for shape_id in model.body_shapes.get(body_id, []):
-                arti_shape_idx = arti_shape_ids.index(shape_id)
-                selected_shape_indices.append(arti_shape_idx)
-                shape_link_idx[arti_shape_idx] = link_idx
-            self.link_shapes.append([])
-        selected_shape_indices = sorted(selected_shape_indices)
-        self.shape_names, self.shape_labels = [], []
-        for shape_idx, arti_shape_idx in enumerate(selected_shape_indices):
-            self.shape_names.append(arti_shape_names[arti_shape_idx])
-            self.shape_labels.append(arti_shape_labels[arti_shape_idx])
-            self.link_shapes[shape_link_idx[arti_shape_idx]].append(shape_idx)
+        # ---- names of the selection and the per-value indices of its dofs / coords / shapes
+        self.joint_names = [joint_leaf[i] for i in sel_joints]
+        self.joint_labels = [model.joint_label[t_joints[i]] for i in sel_joints]
 
-        self.count = articulation_count
-        self.world_count = world_count
-        self.count_per_world = count_per_world
-        self.joint_count = len(selected_joint_indices)
-        self.joint_dof_count = len(selected_dof_indices)
-        self.joint_coord_count = len(selected_coord_indices)
-        self.link_count = len(selected_link_indices)
-        self.shape_count = len(selected_shape_indices)
+        def expand(starts, base):  # joint selection -> (value names, values per joint, value indices relative to the articulation)
+            names, counts, picked = [], [], []
+            for i in sel_joints:
+                lo, hi = int(starts[t_joints[i]]), int(starts[t_joints[i] + 1])
+                counts.append(hi - lo)
+                names.extend([joint_leaf[i]] if hi - lo == 1 else [f"{joint_leaf[i]}:{k}" for k in range(hi - lo)])
+                picked.extend(range(lo - base, hi - base))
+            return names, counts, picked
 
-        def layout(k, selected):
-            return FrequencyLayout(offsets[k], outer[k], inner[k], arti_counts[k], selected, self.device)
+        self.joint_dof_names, self.joint_dof_counts, sel_dofs = expand(qd_start, t_dof0)
+        self.joint_coord_names, self.joint_coord_counts, sel_coords = expand(q_start, t_coord0)
+        self.link_names = [link_leaf[i] for i in sel_links]
+        self.link_labels = [model.body_label[t_links[i]] for i in sel_links]
+        owner = {}  # template-local shape index -> position of its link in the selection
+        for pos, i in enumerate(sel_links):
+            for s in model.body_shapes.get(t_links[i], []):
+                owner[t_shapes.index(s)] = pos
+        sel_shapes = sorted(owner)
+        self.shape_names = [get_name_from_label(model.shape_label[t_shapes[i]]) for i in sel_shapes]
+        self.shape_labels = [model.shape_label[t_shapes[i]] for i in sel_shapes]
+        self.link_shapes = [[] for _ in sel_links]
+        for pos, i in enumerate(sel_shapes):
+            self.link_shapes[owner[i]].append(pos)
 
+        self.joint_count, self.joint_dof_count, self.joint_coord_count = len(sel_joints), len(sel_dofs), len(sel_coords)
+        self.link_count, self.shape_count = len(sel_links), len(sel_shapes)
+        F = AttributeFrequency
         self.frequency_layouts = {
-            AttributeFrequency.JOINT: layout("joint", selected_joint_indices),
-            AttributeFrequency.JOINT_DOF: layout("dof", selected_dof_indices),
-            AttributeFrequency.JOINT_COORD: layout("coord", selected_coord_indices),
-            AttributeFrequency.BODY: layout("link", selected_link_indices),
-            AttributeFrequency.SHAPE: layout("shape", selected_shape_indices),
+            freq: FrequencyLayout(offsets[k], *strides[k], per_articulation[k], sel, self.device)
+            for freq, k, sel in ((F.JOINT, "joint", sel_joints), (F.JOINT_DOF, "dof", sel_dofs), (F.JOINT_COORD, "coord", sel_coords),
+                                 (F.BODY, "link", sel_links), (F.SHAPE, "shape", sel_shapes))
         }
-        self.tendon_count = 0  # MuJoCo fixed tendons (selection.py:1017-1163) do not exist in this package
+        self.tendon_count = 0  # MuJoCo fixed tendons do not exist in this package
         self.tendon_names = []
-        self.joints_contiguous = self.frequency_layouts[AttributeFrequency.JOINT].is_contiguous
-        self.joint_dofs_contiguous = self.frequency_layouts[AttributeFrequency.JOINT_DOF].is_contiguous
-        self.joint_coords_contiguous = self.frequency_layouts[AttributeFrequency.JOINT_COORD].is_contiguous
-        self.links_contiguous = self.frequency_layouts[AttributeFrequency.BODY].is_contiguous
-        self.shapes_contiguous = self.frequency_layouts[AttributeFrequency.SHAPE].is_contiguous
+        self.joints_contiguous = self.frequency_layouts[F.JOINT].is_contiguous
+        self.joint_dofs_contiguous = self.frequency_layouts[F.JOINT_DOF].is_contiguous
+        self.joint_coords_contiguous = self.frequency_layouts[F.JOINT_COORD].is_contiguous
+        self.links_contiguous = self.frequency_layouts[F.BODY].is_contiguous
+        self.shapes_contiguous = self.frequency_layouts[F.SHAPE].is_contiguous
 
         # (world, articulation) -> Model articulation id; default masks
-        self.articulation_ids = torch.tensor(articulation_ids, dtype=torch.int32, device=self.device)
-        self.full_mask = torch.ones(world_count, dtype=torch.bool).to(self.device)
-        selected = np.zeros(model.articulation_count, dtype=np.bool_)
-        selected[np.asarray(articulation_ids, dtype=np.int64).reshape(-1)] = True
-        self.articulation_mask = torch.from_numpy(selected).to(self.device)
-
+        self.articulation_ids = torch.from_numpy(ids.astype(np.int32)).to(self.device)
+        self.full_mask = torch.ones(self.world_count, dtype=torch.bool).to(self.device)
+        member = np.zeros(model.articulation_count, dtype=np.bool_)
+        member[ids.reshape(-1)] = True
+        self.articulation_mask = torch.from_numpy(member).to(self.device)
         if verbose:
-            print(f"Articulation '{pattern}': {self.count}")
-            print(f"  Link count:     {self.link_count} ({'' if self.links_contiguous else 'non-'}contiguous)")
-            print(f"  Shape count:    {self.shape_count} ({'' if self.shapes_contiguous else 'non-'}contiguous)")
-            print(f"  Joint count:    {self.joint_count} ({'' if self.joints_contiguous else 'non-'}contiguous)")
-            print(f"  DOF count:      {self.joint_dof_count} ({'' if self.joint_dofs_contiguous else 'non-'}contiguous)")
-            print(f"  Fixed base?     {self.is_fixed_base}")
-            print(f"  Floating base?  {self.is_floating_base}")
-            print(f"Link names:\n  {self.link_names}\nJoint names:\n  {self.joint_names}\nJoint DOF names:\n  {self.joint_dof_names}")
+            print(self.describe(pattern))
+
+    @staticmethod
+    def _select_articulations(model: Model, pattern) -> np.ndarray:
+        """Model articulation ids of the selection as a ``[world, articulation]`` array.  Explicit index lists must be
+        ascending and in range; a selection lives either in the numbered worlds (the same count in each) or in the global world
+        ``-1`` (then it is one row)."""
+        labels, worlds = model.articulation_label, model.numpy("articulation_world")
+        picked = match_labels(labels, pattern)
+        if isinstance(pattern, list) and pattern and isinstance(pattern[0], int):
+            if any(b <= a for a, b in zip(picked, picked[1:])):
+                raise ValueError("Articulation indices must be unique and in ascending order")
+            if picked[0] < 0 or picked[-1] >= len(labels):
+                raise ValueError(f"Articulation indices must be in range [0, {len(labels)})")
+        rows = [[] for _ in range(model.world_count)]
+        shared = []
+        for a in picked:
+            w = int(worlds[a])
+            if w == -1:
+                shared.append(a)
+            elif 0 <= w < model.world_count:
+                rows[w].append(a)
+            else:
+                raise ValueError(f"World index out of range: {w}")
+        if any(rows) and shared:
+            raise ValueError(f"Articulation pattern '{pattern}' matches global and per-world articulations, which is currently not supported")
+        if shared:
+            rows = [shared]
+        if not any(rows):
+            raise KeyError(f"No articulations matching pattern '{pattern}'")
+        if len({len(r) for r in rows}) != 1:
+            raise ValueError("Varying articulation counts per world are not supported")
+        return np.asarray(rows, dtype=np.int64)
+
+    def describe(self, pattern="") -> str:
+        """One-paragraph summary of the selection (what ``verbose=True`` prints)."""
+        def run(flag):
+            return "contiguous" if flag else "indexed"
+
+        return (f"ArticulationView('{pattern}'): {self.count} articulations = {self.world_count} worlds x {self.count_per_world}; "
+                f"{self.link_count} links ({run(self.links_contiguous)}), {self.shape_count} shapes ({run(self.shapes_contiguous)}), "
+                f"{self.joint_count} joints ({run(self.joints_contiguous)}), {self.joint_dof_count} dofs ({run(self.joint_dofs_contiguous)}); "
+                f"fixed base: {self.is_fixed_base}, floating base: {self.is_floating_base}\n"
+                f"  links:  {self.link_names}\n  joints: {self.joint_names}\n  dofs:   {self.joint_dof_names}")
 
     @property
     def body_names(self):
@@ -414,7 +341,8 @@ class ArticulationView:
             attrib = getattr(attrib, part)
         if not isinstance(attrib, torch.Tensor):
             raise AttributeError(f"Attribute '{name}' is not an array")
-        key = (name, _slice, attrib.data_ptr(), tuple(attrib.shape))
+        slice_key = (_slice.start, _slice.stop) if isinstance(_slice, slice) else _slice
+        key = (name, slice_key, attrib.data_ptr(), tuple(attrib.shape))
         plan = self._plans.get(key)
         if plan is None:
             plan = self._plans[key] = self._make_plan(name, attrib, _slice)
@@ -425,9 +353,7 @@ class ArticulationView:
         layout = self.frequency_layouts.get(frequency)
         if layout is None:
             raise AttributeError(f"Unable to determine the layout of frequency '{frequency.name}' for attribute '{name}'")
-        if isinstance(_slice, Slice):
-            _slice = _slice.get()
-        elif not isinstance(_slice, (type(None), int, slice)):
+        if not isinstance(_slice, (type(None), int, slice)):
             raise ValueError(f"Invalid slice type: expected slice or int, got {type(_slice)}")
         indices = None
         drop = False  # an int slice drops the value dimension, like NumPy / Warp indexing
@@ -528,24 +454,24 @@ class ArticulationView:
     # ------------------------------------------------------------------ convenience wrappers (selection.py:1480-1672)
     def get_root_transforms(self, source):
         if self.is_floating_base:
-            return self._get_attribute_values("joint_q", source, _slice=Slice(0, 7))
+            return self._get_attribute_values("joint_q", source, _slice=slice(0, 7))
         return self._get_attribute_values("joint_X_p", self.model, _slice=0)
 
     def set_root_transforms(self, target, values, mask=None) -> None:
         """Call :meth:`eval_fk` afterwards to move the links."""
         if self.is_floating_base:
-            self._set_attribute_values("joint_q", target, values, mask=mask, _slice=Slice(0, 7))
+            self._set_attribute_values("joint_q", target, values, mask=mask, _slice=slice(0, 7))
         else:
             self._set_attribute_values("joint_X_p", self.model, values, mask=mask, _slice=0)
 
     def get_root_velocities(self, source):
         if self.is_floating_base:
-            return self._get_attribute_values("joint_qd", source, _slice=Slice(0, 6))
+            return self._get_attribute_values("joint_qd", source, _slice=slice(0, 6))
         return None  # non-floating articulations have no root velocity
 
     def set_root_velocities(self, target, values, mask=None) -> None:
         if self.is_floating_base:
-            self._set_attribute_values("joint_qd", target, values, mask=mask, _slice=Slice(0, 6))
+            self._set_attribute_values("joint_qd", target, values, mask=mask, _slice=slice(0, 6))
 
     def get_link_transforms(self, source):
         return self._get_attribute_values("body_q", source)
