@@ -283,10 +283,11 @@ nb2_status nb2_eval_ik(nb2_model* model, const float* body_q, const float* body_
 
 /* Reference newton.eval_fk(model, joint_q, joint_qd, state, mask=..., indices=...) (sim/articulation.py:420-475, 500-574):
  * `articulation_mask` ([articulation_count] bytes, 0 = skip) and `articulation_indices` ([index_count] int32; entries outside
- * [0, articulation_count) are ignored) may each be NULL; the reference rejects passing both and so does this call. */
+ * [0, articulation_count) are ignored) may each be NULL; the reference rejects passing both and so does this call.
+ * `body_flag_filter` (reference :254, :421; BodyFlags.ALL = 3): only bodies whose flags intersect it are written. */
 nb2_status nb2_eval_fk_masked(nb2_model* model, const float* joint_q, const float* joint_qd, float* body_q, float* body_qd,
                               const uint8_t* articulation_mask, const int32_t* articulation_indices, int32_t index_count,
-                              void* cuda_stream);
+                              int32_t body_flag_filter, void* cuda_stream);
 
 /* --- ArticulationView attribute access -------------------------------------------------------
  * Reference newton.selection.ArticulationView (utils/selection.py): `_get_attribute_array` (:1232-1357) views an attribute

@@ -73,7 +73,7 @@ def lib():
         L.nb2_eval_fk.restype = C.c_int
         L.nb2_eval_ik.argtypes = [P, P, P, P, P, P]
         L.nb2_eval_ik.restype = C.c_int
-        L.nb2_eval_fk_masked.argtypes = [P, P, P, P, P, P, P, C.c_int32, P]
+        L.nb2_eval_fk_masked.argtypes = [P, P, P, P, P, P, P, C.c_int32, C.c_int32, P]
         L.nb2_eval_fk_masked.restype = C.c_int
         L.nb2_view_gather.argtypes = [P, C.POINTER(_abi.ViewLayout), P, P]
         L.nb2_view_gather.restype = C.c_int

@@ -742,7 +742,7 @@ nb2_status nb2_eval_fk(nb2_model* model, const float* joint_q, const float* join
 
 nb2_status nb2_eval_fk_masked(nb2_model* model, const float* joint_q, const float* joint_qd, float* body_q, float* body_qd,
                               const uint8_t* articulation_mask, const int32_t* articulation_indices, int32_t index_count,
-                              void* cuda_stream) {
+                              int32_t body_flag_filter, void* cuda_stream) {
     if (!model || !joint_q || !joint_qd || !body_q || !body_qd) {
         set_error("nb2_eval_fk_masked: NULL argument");
         return NB2_ERR_INVALID_ARGUMENT;
@@ -757,7 +757,7 @@ nb2_status nb2_eval_fk_masked(nb2_model* model, const float* joint_q, const floa
     }
     DeviceGuard guard(model->device);
     return launch_eval_fk(model, joint_q, joint_qd, body_q, body_qd, static_cast<cudaStream_t>(cuda_stream), articulation_mask,
-                          articulation_indices, index_count);
+                          articulation_indices, index_count, body_flag_filter);
 }
 
 nb2_status nb2_eval_ik(nb2_model* model, const float* body_q, const float* body_qd, float* joint_q, float* joint_qd,

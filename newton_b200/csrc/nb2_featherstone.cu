@@ -1083,7 +1083,7 @@ nb2_status launch_featherstone_step(nb2_model* m, const nb2_featherstone_params&
 // substep loop.  fk_joint is one iteration of the reference's joint loop (eval_single_articulation_fk :237-418): it reads the
 // parent's freshly written pose / twist and writes the child's.
 __device__ __forceinline__ void fk_joint(const nb2_model_desc& d, int i, const float* __restrict__ joint_q, const float* __restrict__ joint_qd,
-                                         float* body_q, float* body_qd) {
+                                         float* body_q, float* body_qd, int body_flag_filter) {
     const int type = d.joint_type[i], parent = d.joint_parent[i], child = d.joint_child[i];
     const int qs = d.joint_q_start[i], qds = d.joint_qd_start[i];
     const int lin = d.joint_dof_dim[2 * i], ang = d.joint_dof_dim[2 * i + 1];
@@ -1130,6 +1130,8 @@ __device__ __forceinline__ void fk_joint(const nb2_model_desc& d, int i, const f
     else lin_o = lin_w + cross(ang_w, x_child - X_wcj.p);
     const V3 v_o = v_parent_origin + lin_o, w_o = w_parent + ang_w;
     const V3 v_com = cross(w_o, com_c) + v_o;
+    // body_flag_filter (sim/articulation.py:254, 421): a body whose flags miss the filter keeps its values; descendants read them
+    if ((d.body_flags[child] & body_flag_filter) == 0) return;
     stx(body_q + 7 * child, X_wc);
     st6(body_qd + 6 * child, S6(v_com, w_o));
 }
@@ -1150,7 +1152,7 @@ __device__ __forceinline__ int fk_articulation(const nb2_model_desc& d, int item
 // Requires parent-before-child joint order and one driving joint per body (nb2_model::fk_levels, checked at model creation).
 __global__ void __launch_bounds__(128) eval_fk_levels_kernel(DevModel M, const float* __restrict__ joint_q, const float* __restrict__ joint_qd,
                                                              float* body_q, float* body_qd, const uint8_t* __restrict__ mask,
-                                                             const int* __restrict__ indices, int count) {
+                                                             const int* __restrict__ indices, int count, int body_flag_filter) {
     const nb2_model_desc& d = M.d;
     const int lane = threadIdx.x & 31;
     const int a = fk_articulation(d, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, count, mask, indices);  // warp-uniform
@@ -1161,7 +1163,7 @@ __global__ void __launch_bounds__(128) eval_fk_levels_kernel(DevModel M, const f
     for (int o = 16; o > 0; o >>= 1) deepest = max(deepest, __shfl_xor_sync(0xffffffffu, deepest, o));
     for (int level = 0; level <= deepest; ++level) {
         for (int i = j0 + lane; i < j1; i += 32)
-            if (M.joint_depth[i] == level && d.joint_articulation[i] != -1) fk_joint(d, i, joint_q, joint_qd, body_q, body_qd);
+            if (M.joint_depth[i] == level && d.joint_articulation[i] != -1) fk_joint(d, i, joint_q, joint_qd, body_q, body_qd, body_flag_filter);
         __syncwarp();
     }
 }
@@ -1169,22 +1171,22 @@ __global__ void __launch_bounds__(128) eval_fk_levels_kernel(DevModel M, const f
 // Fallback for models whose joint order the level schedule cannot honour: one thread walks one articulation in joint order.
 __global__ void __launch_bounds__(128) eval_fk_kernel(DevModel M, const float* __restrict__ joint_q, const float* __restrict__ joint_qd,
                                                       float* body_q, float* body_qd, const uint8_t* __restrict__ mask,
-                                                      const int* __restrict__ indices, int count) {
+                                                      const int* __restrict__ indices, int count, int body_flag_filter) {
     const nb2_model_desc& d = M.d;
     const int a = fk_articulation(d, blockIdx.x * blockDim.x + threadIdx.x, count, mask, indices);
     if (a < 0) return;
     for (int i = d.articulation_start[a]; i < d.articulation_start[a + 1]; ++i)
-        if (d.joint_articulation[i] != -1) fk_joint(d, i, joint_q, joint_qd, body_q, body_qd);
+        if (d.joint_articulation[i] != -1) fk_joint(d, i, joint_q, joint_qd, body_q, body_qd, body_flag_filter);
 }
 
 nb2_status launch_eval_fk(nb2_model* m, const float* joint_q, const float* joint_qd, float* body_q, float* body_qd, cudaStream_t s,
-                          const uint8_t* mask, const int* indices, int index_count) {
+                          const uint8_t* mask, const int* indices, int index_count, int body_flag_filter) {
     const int A = indices ? index_count : m->dev.d.articulation_count;
     if (A <= 0 || m->dev.d.articulation_count == 0) return NB2_OK;
     if (m->host.fk_levels)
-        eval_fk_levels_kernel<<<(A + 3) / 4, 128, 0, s>>>(m->dev, joint_q, joint_qd, body_q, body_qd, mask, indices, A);
+        eval_fk_levels_kernel<<<(A + 3) / 4, 128, 0, s>>>(m->dev, joint_q, joint_qd, body_q, body_qd, mask, indices, A, body_flag_filter);
     else
-        eval_fk_kernel<<<(A + 127) / 128, 128, 0, s>>>(m->dev, joint_q, joint_qd, body_q, body_qd, mask, indices, A);
+        eval_fk_kernel<<<(A + 127) / 128, 128, 0, s>>>(m->dev, joint_q, joint_qd, body_q, body_qd, mask, indices, A, body_flag_filter);
     count_launch();
     NB2_CUDA_CHECK(cudaGetLastError());
     return NB2_OK;

@@ -24,8 +24,6 @@ def eval_fk(model, joint_q, joint_qd, state, mask=None, indices=None, body_flag_
     """
     if mask is not None and indices is not None:
         raise ValueError("Cannot specify both mask and indices parameters")
-    if int(body_flag_filter) != 3:  # BodyFlags.ALL; reference sim/articulation.py:421, 507-533
-        raise NotImplementedError("eval_fk(body_flag_filter=...) is not implemented in the CUDA path yet (the oracle restates it)")
     if state.body_q.is_cuda:
         import ctypes as C
 
@@ -46,13 +44,13 @@ def eval_fk(model, joint_q, joint_qd, state, mask=None, indices=None, body_flag_
         p_bq = C.c_void_p(_abi.ptr(state.body_q, "f32", dev, 7 * nb, "state.body_q"))
         p_bqd = C.c_void_p(_abi.ptr(state.body_qd, "f32", dev, 6 * nb, "state.body_qd"))
         with torch.cuda.device(nm.device_index):
-            if mask is None and indices is None:
+            if mask is None and indices is None and int(body_flag_filter) == 3:  # BodyFlags.ALL
                 st = _lib.lib().nb2_eval_fk(nm.handle, p_jq, p_jqd, p_bq, p_bqd, _lib.current_stream_ptr(model))
             else:
                 st = _lib.lib().nb2_eval_fk_masked(
                     nm.handle, p_jq, p_jqd, p_bq, p_bqd, C.c_void_p(None if mask is None else mask.data_ptr()),
                     C.c_void_p(None if indices is None else indices.data_ptr()), 0 if indices is None else indices.numel(),
-                    _lib.current_stream_ptr(model))
+                    int(body_flag_filter), _lib.current_stream_ptr(model))
             _lib.check(st, "nb2_eval_fk")
         return
     from .. import _lib

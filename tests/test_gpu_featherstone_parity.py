@@ -190,3 +190,26 @@ def test_kinematic_bodies_and_in_place_stepping_bit_exact(oracle_lib, cuda_lib):
     q = ref.body_q.numpy().reshape(3, -1, 7)
     assert abs(q[0, 0, 0] - (-0.3 + 119 * dt)) < 0.05 and abs(q[0, 0, 2] - 0.5) < 1e-4  # prescribed, does not fall
     assert q[0, 1, 0] > 0.15  # the probe was pushed
+
+
+def test_eval_fk_body_flag_filter(oracle_lib, cuda_lib):
+    """newton.eval_fk(..., body_flag_filter=BodyFlags.KINEMATIC / DYNAMIC) (sim/articulation.py:254, 421): only bodies whose flags
+    intersect the filter are written, the others keep their (stale) values and their descendants are computed from those."""
+    import torch
+
+    from newton_b200 import BodyFlags
+
+    model = scenes.quadruped_model(6, seed=5)
+    model.body_flags[::13] = int(BodyFlags.KINEMATIC)  # every trunk kinematic, the legs dynamic
+    mg = model.to("cuda:0")
+    rng = np.random.default_rng(0)
+    jq = model.joint_q.clone() + torch.from_numpy(rng.normal(scale=0.05, size=model.joint_q.shape).astype(np.float32))
+    jqd = torch.from_numpy(rng.normal(scale=0.3, size=model.joint_qd.shape).astype(np.float32))
+    for flt in (int(BodyFlags.KINEMATIC), int(BodyFlags.DYNAMIC), 3):
+        so, sg = model.state(), mg.state()
+        so.body_q += 0.01  # stale values that the filtered-out bodies must keep
+        sg.body_q += 0.01
+        oracle_lib.eval_fk(model, jq, jqd, so, body_flag_filter=flt)
+        newton_b200.eval_fk(mg, jq.to("cuda:0"), jqd.to("cuda:0"), sg, body_flag_filter=flt)
+        np.testing.assert_array_equal(sg.body_q.cpu().numpy(), so.body_q.numpy(), err_msg=str(flt))
+        np.testing.assert_array_equal(sg.body_qd.cpu().numpy(), so.body_qd.numpy(), err_msg=str(flt))
