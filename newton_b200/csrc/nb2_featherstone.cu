@@ -198,10 +198,13 @@ NB2_DEV Xf joint_transform(const nb2_model_desc& d, int type, int axis_start, in
 
 struct FsSmem {
     float *bq, *bqc, *vs, *as, *fb, *ft, *fe, *qdfk, *Is, *so, *fs, *S, *qd_in, *jf, *tau, *qdd, *qd_out, *H, *jq, *P;
+    // joint headers staged once per substep: the level passes index these instead of going to global memory for every joint's
+    // type / parent / child / depth / offsets in every pass (25 % of the stall samples were those L1 round trips)
+    int *h_type, *h_parent, *h_child, *h_depth, *h_dim, *h_q, *h_qd;
 };
 NB2_DEV size_t fs_smem_floats(const DevModel& M) {
     const size_t n = size_t(M.max_env_bodies) * (7 + 7 + 6 * 6 + 36 + 3 + 6) + size_t(M.max_env_joints) * 6 +
-                     size_t(M.max_env_dofs) * (6 + 5) + size_t(M.max_env_H) + size_t(M.max_env_coords);
+                     size_t(M.max_env_dofs) * (6 + 5) + size_t(M.max_env_H) + size_t(M.max_env_coords) + size_t(M.max_env_joints) * 8 + 2;
     return (n + 1) & ~size_t(1);
 }
 NB2_DEV FsSmem fs_carve(float* base, const DevModel& M) {
@@ -228,6 +231,14 @@ NB2_DEV FsSmem fs_carve(float* base, const DevModel& M) {
     s.H = p; p += M.max_env_H;
     s.jq = p; p += M.max_env_coords;
     s.P = p; p += nb * 6;
+    int* q = reinterpret_cast<int*>(p);
+    s.h_type = q; q += nj;
+    s.h_parent = q; q += nj;
+    s.h_child = q; q += nj;
+    s.h_depth = q; q += nj;
+    s.h_dim = q; q += 2 * nj;
+    s.h_q = q; q += nj + 1;
+    s.h_qd = q; q += nj + 1;
     return s;
 }
 
@@ -367,6 +378,25 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
     }
     const size_t T = size_t(M.slot_total);
     const float* cb = M.cb;
+    for (int j = l; j < nj; j += L) {
+        const int gj = j0 + j;
+        sm.h_type[j] = d.joint_type[gj];
+        sm.h_parent[j] = d.joint_parent[gj];
+        sm.h_child[j] = d.joint_child[gj];
+        sm.h_depth[j] = M.joint_depth[gj];
+        sm.h_dim[2 * j] = d.joint_dof_dim[2 * gj];
+        sm.h_dim[2 * j + 1] = d.joint_dof_dim[2 * gj + 1];
+        sm.h_q[j] = d.joint_q_start[gj];
+        sm.h_qd[j] = d.joint_qd_start[gj];
+    }
+    if (l == 0 && live) {
+        sm.h_q[nj] = d.joint_q_start[j0 + nj];
+        sm.h_qd[nj] = d.joint_qd_start[j0 + nj];
+    }
+    // views indexed by GLOBAL joint id, like the model arrays they shadow
+    const int *jtype = sm.h_type - j0, *jparent = sm.h_parent - j0, *jchild = sm.h_child - j0, *jdepth = sm.h_depth - j0,
+              *jdim = sm.h_dim - 2 * j0, *jqs = sm.h_q - j0, *jqds = sm.h_qd - j0;
+    __syncwarp(gmask);
 
     // ---- body_f_ext = body_f; zero scratch ------------------------------------------------------
     for (int b = l; b < nb; b += L) {
@@ -380,10 +410,10 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
     __syncwarp(gmask);
     // ---- per joint: public -> internal joint_f, FREE/DISTANCE wrench into body_f_ext -------------
     for (int j = l; j < nj; j += L) {
-        const int gj = j0 + j, type = d.joint_type[gj];
-        const int qd0 = d.joint_qd_start[gj], qd1 = d.joint_qd_start[gj + 1];
+        const int gj = j0 + j, type = jtype[gj];
+        const int qd0 = jqds[gj], qd1 = jqds[gj + 1];
         if (type == FJ_FREE || type == FJ_DISTANCE) {
-            const int child = d.joint_child[gj] - b0;
+            const int child = jchild[gj] - b0;
 #pragma unroll
             for (int k = 0; k < 6; ++k) sm.fe[6 * child + k] += ctl.joint_f[qd0 + k];  // one inbound joint per body
             for (int i = qd0; i < qd1; ++i) sm.jf[i - d0] = 0.0f;
@@ -395,8 +425,8 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
     // (scratch: X_j(q) and X_cj^-1 live in the spatial-inertia block of the joint's body, which is unused until the RNEA pass)
     for (int j = l; j < nj; j += L) {
         const int gj = j0 + j;
-        const Xf X_j = joint_transform(d, d.joint_type[gj], d.joint_qd_start[gj], d.joint_dof_dim[2 * gj], d.joint_dof_dim[2 * gj + 1],
-                                       sin.joint_q, d.joint_q_start[gj]);
+        const Xf X_j = joint_transform(d, jtype[gj], jqds[gj], jdim[2 * gj], jdim[2 * gj + 1],
+                                       sin.joint_q, jqs[gj]);
         stx(sm.Is + 36 * j, X_j);
         stx(sm.Is + 36 * j + 7, xinv(ldx(d.joint_X_c + 7 * gj)));
     }
@@ -404,8 +434,8 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
     for (int lvl = 0; lvl <= M.max_depth; ++lvl) {
         for (int j = l; j < nj; j += L) {
             const int gj = j0 + j;
-            if (M.joint_depth[gj] != lvl) continue;
-            const int parent = d.joint_parent[gj], child = d.joint_child[gj] - b0;
+            if (jdepth[gj] != lvl) continue;
+            const int parent = jparent[gj], child = jchild[gj] - b0;
             Xf X_wpj = ldx(d.joint_X_p + 7 * gj);
             if (parent >= 0) X_wpj = xmul(ldx(sm.bq + 7 * (parent - b0)), X_wpj);
             const Xf X_wc = xmul(xmul(X_wpj, ldx(sm.Is + 36 * j)), ldx(sm.Is + 36 * j + 7));
@@ -418,13 +448,13 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
     }
     // ---- public -> internal joint_qd ------------------------------------------------------------------
     for (int j = l; j < nj; j += L) {
-        const int gj = j0 + j, type = d.joint_type[gj];
-        const int qd0 = d.joint_qd_start[gj], qd1 = d.joint_qd_start[gj + 1];
+        const int gj = j0 + j, type = jtype[gj];
+        const int qd0 = jqds[gj], qd1 = jqds[gj + 1];
         if (type != FJ_FREE && type != FJ_DISTANCE) {
             for (int i = qd0; i < qd1; ++i) sm.qd_in[i - d0] = sin.joint_qd[i];
             continue;
         }
-        const int parent = d.joint_parent[gj], child = d.joint_child[gj] - b0;
+        const int parent = jparent[gj], child = jchild[gj] - b0;
         Xf X_wpj = ldx(d.joint_X_p + 7 * gj);
         if (parent >= 0) X_wpj = xmul(ldx(sm.bq + 7 * (parent - b0)), X_wpj);
         const V3 x_com = xpoint(ldx(sm.bq + 7 * child), ld3(d.body_com + 3 * (b0 + child)));
@@ -441,19 +471,19 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
     // velocities v_j, bias terms, spatial inertias - needs the FK poses alone and runs for all joints at once. ---------------
     for (int j = l; j < nj; j += L) {  // A: per-joint quantities (v_j parked in vs[child], c_app in as[child])
         const int gj = j0 + j;
-        const int type = d.joint_type[gj], parent = d.joint_parent[gj], child = d.joint_child[gj] - b0;
+        const int type = jtype[gj], parent = jparent[gj], child = jchild[gj] - b0;
         const int art = d.joint_articulation[gj];
         const int root = d.articulation_start[art];
         V3 solve_origin;
         {
-            const int rt = d.joint_type[root];
-            if (rt == FJ_FREE || rt == FJ_DISTANCE) solve_origin = ld3(sm.bqc + 7 * (d.joint_child[root] - b0));
+            const int rt = jtype[root];
+            if (rt == FJ_FREE || rt == FJ_DISTANCE) solve_origin = ld3(sm.bqc + 7 * (jchild[root] - b0));
         }
         Xf X_wpj = ldx(d.joint_X_p + 7 * gj);
         if (parent >= 0) X_wpj = xmul(ldx(sm.bq + 7 * (parent - b0)), X_wpj);
         const Xf X_s(X_wpj.p - solve_origin, X_wpj.q);
-        const int qs = d.joint_q_start[gj], qds = d.joint_qd_start[gj];
-        const int lin = d.joint_dof_dim[2 * gj], ang = d.joint_dof_dim[2 * gj + 1];
+        const int qs = jqs[gj], qds = jqds[gj];
+        const int lin = jdim[2 * gj], ang = jdim[2 * gj + 1];
         const float* jqd = sm.qd_in - d0;  // indexed with global dof ids
         float* Sout = sm.S - 6 * d0;
         S6 v_j, c_app;
@@ -520,8 +550,8 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
     for (int lvl = 0; lvl <= M.max_depth; ++lvl) {  // B: v_s = v_parent + v_j, a_s = a_parent + v_s x v_j + c_app
         for (int j = l; j < nj; j += L) {
             const int gj = j0 + j;
-            if (M.joint_depth[gj] != lvl) continue;
-            const int parent = d.joint_parent[gj], child = d.joint_child[gj] - b0;
+            if (jdepth[gj] != lvl) continue;
+            const int parent = jparent[gj], child = jchild[gj] - b0;
             const S6 v_j = ld6(sm.vs + 6 * child), c_app = ld6(sm.as + 6 * child);
             S6 v_par, a_par;
             if (parent >= 0) {
@@ -536,7 +566,7 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
         __syncwarp(gmask);
     }
     for (int j = l; j < nj; j += L) {  // C: body forces
-        const int gj = j0 + j, child = d.joint_child[gj] - b0;
+        const int gj = j0 + j, child = jchild[gj] - b0;
         const S6 v_s = ld6(sm.vs + 6 * child), a_s = ld6(sm.as + 6 * child);
         const V3 x_com_s = ld3(sm.bqc + 7 * child) - ld3(sm.so + 3 * child);
         const float mass = d.body_mass[b0 + child];
@@ -612,9 +642,9 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
     // ---- eval_rigid_tau (RNEA backward).  The drive / limit / damping terms do not depend on the force recursion: they are
     // evaluated for all dofs at once and parked in tau[]; the level loop only adds -S.f_s in the reference's order. ---------
     for (int j = l; j < nj; j += L) {
-        const int gj = j0 + j, type = d.joint_type[gj];
-        const int ds = d.joint_qd_start[gj], cs = d.joint_q_start[gj], tqs = d.joint_target_q_start[gj];
-        const int lin = d.joint_dof_dim[2 * gj], ang = d.joint_dof_dim[2 * gj + 1];
+        const int gj = j0 + j, type = jtype[gj];
+        const int ds = jqds[gj], cs = jqs[gj], tqs = d.joint_target_q_start[gj];
+        const int lin = jdim[2 * gj], ang = jdim[2 * gj + 1];
         const float* jqd = sm.qd_in - d0;
         float* tau = sm.tau - d0;
         if (type == FJ_BALL) {
@@ -632,10 +662,10 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
     for (int lvl = M.max_depth; lvl >= 0; --lvl) {
         for (int j = l; j < nj; j += L) {
             const int gj = j0 + j;
-            if (M.joint_depth[gj] != lvl) continue;
-            const int type = d.joint_type[gj], child = d.joint_child[gj] - b0;
-            const int ds = d.joint_qd_start[gj];
-            const int lin = d.joint_dof_dim[2 * gj], ang = d.joint_dof_dim[2 * gj + 1];
+            if (jdepth[gj] != lvl) continue;
+            const int type = jtype[gj], child = jchild[gj] - b0;
+            const int ds = jqds[gj];
+            const int lin = jdim[2 * gj], ang = jdim[2 * gj + 1];
             const S6 f_b = ld6(sm.fb + 6 * child), f_t = ld6(sm.ft + 6 * child), fe = ld6(sm.fe + 6 * child);
             const V3 x_com_s = ld3(sm.bqc + 7 * child) - ld3(sm.so + 3 * child);
             const S6 f_ext0(fe.top(), fe.bot() + cross(x_com_s, fe.top()));
@@ -672,7 +702,7 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
                 const int e = M.body_joint_entry[k];
                 if (e & 1) continue;  // the body is this joint's child
                 const int j = e >> 1;
-                if (M.joint_depth[j0 + j] != lvl) continue;
+                if (jdepth[j0 + j] != lvl) continue;
                 acc = acc + ld6(sm.fs + 6 * j);
                 any = true;
             }
@@ -686,7 +716,7 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
         for (int b = l; b < nb; b += L) st6(sout.body_parent_f + 6 * (b0 + b), S6());
         __syncwarp(gmask);
         for (int j = l; j < nj; j += L) {
-            const int child = d.joint_child[j0 + j] - b0;
+            const int child = jchild[j0 + j] - b0;
             const S6 f_s = ld6(sm.fs + 6 * j);
             const V3 r_com = ld3(sm.bqc + 7 * child) - ld3(sm.so + 3 * child);
             st6(sout.body_parent_f + 6 * (b0 + child), S6(f_s.top(), f_s.bot() - cross(r_com, f_s.top())));
@@ -719,7 +749,7 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
         const int art = a0 + a;
         const int aj0 = d.articulation_start[art], aj1 = d.articulation_start[art + 1];
         const int anj = aj1 - aj0;
-        const int ad0 = d.joint_qd_start[aj0], n = d.joint_qd_start[aj1] - ad0;
+        const int ad0 = jqds[aj0], n = jqds[aj1] - ad0;
         float* H = sm.H + M.art_H_start[art];
         float* Lg = M.fs_L + M.env_H_start[env] + M.art_H_start[art];
         if (update_mass) {
@@ -777,7 +807,7 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
             // dense_cholesky (kernels.py:1690-1719), in place on the lower triangle; columns in order, rows in parallel
             for (int jn = 0; jn < n; ++jn) {
                 // joint_armature_effective (solver_featherstone.py:269-281): 1e10 on the dofs of a joint driving a kinematic body
-                const bool kin_dof = (d.body_flags[d.joint_child[aj0 + M.dof_joint[ad0 + jn]]] & 2) != 0;
+                const bool kin_dof = (d.body_flags[jchild[aj0 + M.dof_joint[ad0 + jn]]] & 2) != 0;
                 float sdiag = H[jn * n + jn] + (kin_dof ? 1.0e10f : d.joint_armature[ad0 + jn]);
                 for (int k = 0; k < jn; ++k) {
                     const float r = H[jn * n + k];
@@ -824,22 +854,22 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
         }
         __syncwarp(gmask);
         for (int i = l; i < n; i += L)  // zero_kinematic_joint_qdd (kernels.py:1933-1948)
-            if (d.body_flags[d.joint_child[aj0 + M.dof_joint[ad0 + i]]] & 2) sm.qdd[ad0 - d0 + i] = 0.0f;
+            if (d.body_flags[jchild[aj0 + M.dof_joint[ad0 + i]]] & 2) sm.qdd[ad0 - d0 + i] = 0.0f;
         __syncwarp(gmask);
     }
     NB2_PHASE();
     // ---- integrate_generalized_joints (jcalc_integrate, kernels.py:464-630) ----------------------------------------
     for (int j = l; j < nj; j += L) {
-        const int gj = j0 + j, type = d.joint_type[gj], parent = d.joint_parent[gj], child = d.joint_child[gj];
-        const int cs = d.joint_q_start[gj], ds = d.joint_qd_start[gj];
+        const int gj = j0 + j, type = jtype[gj], parent = jparent[gj], child = jchild[gj];
+        const int cs = jqs[gj], ds = jqds[gj];
         const float* q = sin.joint_q;
         const float* qd = sm.qd_in - d0;
         const float* qdd = sm.qdd - d0;
         float* qn = sm.jq - c0;
         float* qdn = sm.qd_out - d0;
         if (d.body_flags[child] & 2) {  // copy_kinematic_joint_state (kernels.py:1951-1976): the prescribed state passes through
-            for (int i = cs; i < d.joint_q_start[gj + 1]; ++i) qn[i] = q[i];
-            for (int i = ds; i < d.joint_qd_start[gj + 1]; ++i) qdn[i] = qd[i];
+            for (int i = cs; i < jqs[gj + 1]; ++i) qn[i] = q[i];
+            for (int i = ds; i < jqds[gj + 1]; ++i) qdn[i] = qd[i];
             continue;
         }
         if (type == FJ_FIXED) continue;
@@ -888,7 +918,7 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
                 qdn[ds] = v_s.x; qdn[ds + 1] = v_s.y; qdn[ds + 2] = v_s.z; qdn[ds + 3] = w_s.x; qdn[ds + 4] = w_s.y; qdn[ds + 5] = w_s.z;
             }
         } else if (type == FJ_D6) {
-            const int cnt = d.joint_dof_dim[2 * gj] + d.joint_dof_dim[2 * gj + 1];
+            const int cnt = jdim[2 * gj] + jdim[2 * gj + 1];
             for (int k = 0; k < cnt; ++k) {
                 const float qd_new = qd[ds + k] + qdd[ds + k] * dt;
                 qdn[ds + k] = qd_new;
@@ -903,10 +933,10 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
     for (int lvl = 0; lvl <= M.max_depth; ++lvl) {
         for (int j = l; j < nj; j += L) {
             const int gj = j0 + j;
-            if (M.joint_depth[gj] != lvl) continue;
-            const int type = d.joint_type[gj], parent = d.joint_parent[gj], child = d.joint_child[gj] - b0;
-            const int qs = d.joint_q_start[gj], qds = d.joint_qd_start[gj];
-            const int lin = d.joint_dof_dim[2 * gj], ang = d.joint_dof_dim[2 * gj + 1];
+            if (jdepth[gj] != lvl) continue;
+            const int type = jtype[gj], parent = jparent[gj], child = jchild[gj] - b0;
+            const int qs = jqs[gj], qds = jqds[gj];
+            const int lin = jdim[2 * gj], ang = jdim[2 * gj + 1];
             const float* jq = sm.jq - c0;
             const float* jqd = sm.qd_out - d0;
             const Xf X_j = joint_transform(d, type, qds, lin, ang, jq, qs);
@@ -965,13 +995,13 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
     }
     // ---- internal -> public joint_qd ------------------------------------------------------------------------------
     for (int j = l; j < nj; j += L) {
-        const int gj = j0 + j, type = d.joint_type[gj];
-        const int qd0 = d.joint_qd_start[gj], qd1 = d.joint_qd_start[gj + 1];
+        const int gj = j0 + j, type = jtype[gj];
+        const int qd0 = jqds[gj], qd1 = jqds[gj + 1];
         if (type != FJ_FREE && type != FJ_DISTANCE) {
             for (int i = qd0; i < qd1; ++i) sout.joint_qd[i] = sm.qd_out[i - d0];
             continue;
         }
-        const int parent = d.joint_parent[gj], child = d.joint_child[gj] - b0;
+        const int parent = jparent[gj], child = jchild[gj] - b0;
         Xf X_wpj = ldx(d.joint_X_p + 7 * gj);
         if (parent >= 0) X_wpj = xmul(ldx(sm.bq + 7 * (parent - b0)), X_wpj);
         const V3 x_com = xpoint(ldx(sm.bq + 7 * child), ld3(d.body_com + 3 * (b0 + child)));
