@@ -108,13 +108,51 @@ def compute_inertia_shape(geo_type, scale, density, is_solid=True, thickness=0.0
     solid = fns[geo_type](scale)
     if is_solid:
         return solid
+    # hollow: outer solid minus an inner solid shrunk by `thickness` in every dimension (inertia.py:634-722)
+    limited = {GeoType.SPHERE: ("radius",), GeoType.BOX: ("hx", "hy", "hz"), GeoType.CAPSULE: ("radius", "half_height"),
+               GeoType.CYLINDER: ("radius", "half_height"), GeoType.CONE: ("radius", "half_height"),
+               GeoType.ELLIPSOID: ("rx", "ry", "rz")}[geo_type]
+    thickness = _hollow_thickness(GeoType(geo_type).name.lower(), thickness, [(n, scale[i]) for i, n in enumerate(limited)])
     if thickness == 0.0:
         return 0.0, solid[1], np.zeros((3, 3))
-    inner = [max(x - thickness, 0.0) for x in scale]
+    inner = [x - thickness for x in scale]
     if geo_type == GeoType.CYLINDER:
-        inner[2] = scale[2] - thickness if scale[2] > 0.0 else 0.0
+        inner = [scale[0] - thickness, scale[1] - thickness, scale[2] - thickness if len(scale) > 2 and scale[2] > 0.0 else 0.0]
     hollow = fns[geo_type](inner)
-    return solid[0] - hollow[0], solid[1], solid[2] - hollow[2]
+    m_shell = solid[0] - hollow[0]
+    if geo_type != GeoType.CONE:
+        return m_shell, solid[1], solid[2] - hollow[2]
+    # the two cones have different centres of mass: the shell's is their mass-weighted difference, and both tensors move there
+    # (parallel axes) before they are subtracted (inertia.py:692-707)
+    com_shell = (solid[0] * solid[1] - hollow[0] * hollow[1]) / m_shell
+
+    def about(mass, inertia, com):
+        d = com_shell - com
+        return inertia + mass * (np.dot(d, d) * np.eye(3) - np.outer(d, d))
+
+    return m_shell, com_shell, about(solid[0], solid[2], solid[1]) - about(hollow[0], hollow[2], hollow[1])
+
+
+def _hollow_thickness(shape_name, thickness, limits):
+    """Wall thickness of a hollow primitive must be a finite real in [0, every listed dimension) (reference ``inertia.py:48-76``);
+    zero is allowed (massless shell) with a warning."""
+    import numbers
+    import warnings
+
+    if isinstance(thickness, bool) or not isinstance(thickness, numbers.Real):
+        raise TypeError(f"thickness must be a real scalar for a hollow {shape_name} geom")
+    thickness = float(thickness)
+    if not math.isfinite(thickness):
+        raise ValueError(f"thickness must be finite for a hollow {shape_name} geom; got {thickness}")
+    if thickness < 0.0:
+        raise ValueError(f"thickness must be >= 0 for a hollow {shape_name} geom; got {thickness}")
+    if thickness == 0.0:
+        warnings.warn(f"A hollow {shape_name} geom with zero thickness has zero mass and inertia.", stacklevel=3)
+        return thickness
+    for name, value in limits:
+        if thickness >= float(value):
+            raise ValueError(f"thickness ({thickness}) must be smaller than {name} ({float(value)}) for a hollow {shape_name} geom")
+    return thickness
 
 
 def transform_inertia(mass, inertia, offset, quat):

@@ -1583,6 +1583,56 @@ def test_primitive_mass_properties_against_brute_force(name):
     np.testing.assert_allclose(np.asarray(inertia), 1000.0 * i_ref, rtol=1e-2, atol=1e-3 * np.trace(1000.0 * i_ref))
 
 
+HOLLOW_T = 0.1
+
+
+def _shrunk(name):
+    """The inner solid the reference removes from a hollow primitive: every dimension minus the wall thickness
+    (geometry/inertia.py:634-722), same local frame."""
+    t = HOLLOW_T
+    return {
+        "sphere": lambda x, y, z: x * x + y * y + z * z <= (0.7 - t) ** 2,
+        "box": lambda x, y, z: (np.abs(x) <= 0.3 - t) & (np.abs(y) <= 0.5 - t) & (np.abs(z) <= 0.7 - t),
+        "capsule": lambda x, y, z: x * x + y * y + np.maximum(np.abs(z) - (0.6 - t), 0.0) ** 2 <= (0.4 - t) ** 2,
+        "cylinder": lambda x, y, z: (x * x + y * y <= (0.5 - t) ** 2) & (np.abs(z) <= 0.8 - t),
+        "cone": lambda x, y, z: (np.abs(z) <= 0.9 - t) & (x * x + y * y <= ((0.6 - t) * (0.9 - t - z) / (1.8 - 2 * t)) ** 2),
+        "ellipsoid": lambda x, y, z: (x / (0.7 - t)) ** 2 + (y / (0.5 - t)) ** 2 + (z / (0.3 - t)) ** 2 <= 1.0,
+    }[name]
+
+
+@pytest.mark.parametrize("name", ["sphere", "box", "capsule", "cylinder", "cone", "ellipsoid"])
+def test_hollow_primitive_mass_properties_against_brute_force(name):
+    """is_solid=False: outer minus inner solid, integrated on the grid - the cone's shell has its own centre of mass."""
+    from newton_b200.geometry.inertia import compute_inertia_shape
+
+    geo_type, scale, inside, extent = PRIMITIVES[name]
+    inner = _shrunk(name)
+    mass, com, inertia = compute_inertia_shape(geo_type, scale, 1000.0, is_solid=False, thickness=HOLLOW_T)
+    half = np.asarray(extent if isinstance(extent, tuple) else (extent,) * 3, dtype=np.float64)
+    m_ref, com_ref, i_ref = _grid_mass_properties(lambda x, y, z: inside(x, y, z) & ~inner(x, y, z), (-half, half), n=200)
+    assert mass == pytest.approx(1000.0 * m_ref, rel=1.5e-2)
+    np.testing.assert_allclose(com, com_ref, atol=4e-3 * half.max())
+    np.testing.assert_allclose(np.asarray(inertia), 1000.0 * i_ref, rtol=2e-2, atol=2e-3 * np.trace(1000.0 * i_ref))
+    if name == "cone":
+        assert com[2] < -1.8 / 4.0 + 1e-9 and abs(com[2] + 0.45) > 1e-3  # not the solid cone's centre of mass
+
+
+def test_hollow_thickness_is_validated():
+    """reference geometry/inertia.py:48-76: negative, non-finite or too-thick walls raise; zero gives a massless shell + warning."""
+    from newton_b200.geometry.inertia import compute_inertia_shape
+
+    for bad in (-0.1, float("nan"), 0.7, 1.0):
+        with pytest.raises(ValueError):
+            compute_inertia_shape(GeoType.SPHERE, (0.7, 0.0, 0.0), 1000.0, is_solid=False, thickness=bad)
+    with pytest.raises(TypeError):
+        compute_inertia_shape(GeoType.BOX, (0.3, 0.5, 0.7), 1000.0, is_solid=False, thickness="thin")
+    with pytest.raises(ValueError):
+        compute_inertia_shape(GeoType.CONE, (0.6, 0.9, 0.0), 1000.0, is_solid=False, thickness=0.6)
+    with pytest.warns(UserWarning):
+        m, _, inertia = compute_inertia_shape(GeoType.BOX, (0.3, 0.5, 0.7), 1000.0, is_solid=False, thickness=0.0)
+    assert m == 0.0 and not np.asarray(inertia).any()
+
+
 def test_barrel_cylinder_body_can_be_built():
     """A dynamic body carrying a barrel cylinder gets the barrel's mass properties (it used to be refused by the builder)."""
     builder = ModelBuilder()
