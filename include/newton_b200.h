@@ -319,15 +319,32 @@ nb2_status nb2_view_articulation_mask(const uint8_t* mask, int32_t mask_ndim, co
                                       int32_t world_count, int32_t count_per_world, uint8_t* model_mask,
                                       int32_t articulation_count, void* cuda_stream);
 
-/* Reference CollisionPipeline(contact_matching="latest") (geometry/contact_match.py; call sites sim/collide.py:2033-2137): fills
- * match_index[i] for every contact of the exported, key-sorted buffer (run nb2_contacts_sort first: matching implies
+/* Options of nb2_contacts_match - the matching kwargs of reference CollisionPipeline.__init__ (sim/collide.py:1126-1131) plus the
+ * pending CollisionPipeline.reset() request (:1735-1752). */
+typedef struct nb2_match_options {
+    float pos_threshold;             /* contact_matching_pos_threshold [m] */
+    float normal_dot_threshold;      /* contact_matching_normal_dot_threshold */
+    const uint8_t* reset_world_mask; /* optional [world_count + 1] bytes (last = world -1): contacts touching a selected world start fresh */
+    int32_t reset_all;               /* != 0: forget the whole history first */
+    int32_t sticky;                  /* contact_matching="sticky": matched rows still in contact are overwritten with last frame's
+                                        point0/point1/offset0/offset1/normal (geometry/contact_match.py:529-561) */
+    /* contact_report=True (Contacts.rigid_contact_new_indices / _new_count / _broken_indices / _broken_count, sim/contacts.py:328-342):
+       all four or none.  Lists are written in ascending order (the reference's atomics give no particular order). */
+    int32_t* new_indices;
+    int32_t* new_count;
+    int32_t* broken_indices;
+    int32_t* broken_count;
+} nb2_match_options;
+
+/* Reference CollisionPipeline(contact_matching="latest" | "sticky") (geometry/contact_match.py; call sites sim/collide.py:2033-2137):
+ * fills match_index[i] for every contact of the exported, key-sorted buffer (run nb2_contacts_sort first: matching implies
  * deterministic order upstream) with the index of the matched contact in the PREVIOUS call's sorted buffer, -1 (pair had no
- * contacts last frame) or -2 (pair known, but no contact within pos_threshold [m] / normal_dot_threshold, or a closer contact
- * claimed the same old one), then stores this frame as the new history.  reset_world_mask: optional [world_count + 1] bytes
- * (last = world -1): contacts touching a selected world start fresh; reset_all != 0 forgets the whole history first. */
+ * contacts last frame) or -2 (pair known, but no contact within pos_threshold / normal_dot_threshold, or a closer contact claimed
+ * the same old one); in sticky mode replays the matched rows INTO `contacts` (the caller must then treat the model's contact
+ * blocks as stale: nb2_contacts_import before the next solver step); optionally builds the new/broken report; then stores this
+ * frame as the new history.  The history lives in the model handle: one matcher per model. */
 nb2_status nb2_contacts_match(nb2_model* model, const float* body_q, const nb2_contacts_view* contacts, int32_t* match_index,
-                              float pos_threshold, float normal_dot_threshold, const uint8_t* reset_world_mask, int32_t reset_all,
-                              void* cuda_stream);
+                              const nb2_match_options* options, void* cuda_stream);
 
 /* --- multi-GPU end-of-frame state gather without compute kernels --------------------------------------
  * Replaces the `ncclAllGather(body_q, body_qd)` of the reference design (there is no reference code for it: upstream is

@@ -202,6 +202,14 @@ class XPBDParams(C.Structure):
     ]
 
 
+class MatchOptions(C.Structure):
+    """``nb2_match_options``"""
+
+    _fields_ = [("pos_threshold", C.c_float), ("normal_dot_threshold", C.c_float), ("reset_world_mask", C.c_void_p), ("reset_all", C.c_int32),
+                ("sticky", C.c_int32), ("new_indices", C.c_void_p), ("new_count", C.c_void_p), ("broken_indices", C.c_void_p),
+                ("broken_count", C.c_void_p)]
+
+
 class FeatherstoneParams(C.Structure):
     _fields_ = [
         ("angular_damping", C.c_float),

@@ -53,7 +53,7 @@ def lib():
         L.nb2_collide_configure.restype = C.c_int
         L.nb2_collide.argtypes = [P, P, C.POINTER(_abi.ContactsView), P]
         L.nb2_collide.restype = C.c_int
-        L.nb2_contacts_match.argtypes = [P, P, C.POINTER(_abi.ContactsView), P, C.c_float, C.c_float, P, C.c_int32, P]
+        L.nb2_contacts_match.argtypes = [P, P, C.POINTER(_abi.ContactsView), P, C.POINTER(_abi.MatchOptions), P]
         L.nb2_contacts_match.restype = C.c_int
         L.nb2_contacts_sort.argtypes = [P, C.POINTER(_abi.ContactsView), P]
         L.nb2_contacts_sort.restype = C.c_int

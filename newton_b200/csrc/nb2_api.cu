@@ -610,7 +610,8 @@ void nb2_model_destroy(nb2_model* model) {
     if (!model) return;
     DeviceGuard guard(model->device);
     for (void* p : {(void*)model->match_new_keys, (void*)model->match_prev_keys, (void*)model->match_prev_claim, (void*)model->match_prev_pos,
-                    (void*)model->match_prev_normal, (void*)model->match_prev_count})
+                    (void*)model->match_prev_normal, (void*)model->match_prev_count, (void*)model->match_prev_record,
+                    (void*)model->match_prev_was_matched})
         if (p) cudaFree(p);
     free_allocations(model);
     delete model;

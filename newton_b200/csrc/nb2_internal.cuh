@@ -124,6 +124,9 @@ struct nb2_model {
     long long *match_new_keys = nullptr, *match_prev_keys = nullptr, *match_prev_claim = nullptr;
     float *match_prev_pos = nullptr, *match_prev_normal = nullptr;
     int* match_prev_count = nullptr;
+    float* match_prev_record = nullptr;      // sticky: [4][capacity] vec3 - point0, point1, offset0, offset1 of the saved frame
+    int* match_prev_was_matched = nullptr;   // contact_report: 1 where a contact of this frame kept the saved row
+    bool match_prev_has_record = false;      // the saved frame carries sticky records (the last save ran in sticky mode)
     bool implicit_single = false;  // model built without begin_world(): one environment holding every entity
     bool has_convex_pairs = false;  // some pair's types have no analytic collider -> collide_kernel<L, true>
     int explicit_max_env_contacts = 0, dyn_pairs_requested = 0;

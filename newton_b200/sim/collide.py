@@ -26,18 +26,19 @@ class CollisionPipeline:
                  deterministic: bool = False, soft_contact_margin: float = 0.01, requires_grad: bool = False,
                  export_contacts: bool = True, include_static_kinematic_pairs: bool = True, contact_matching: str = "disabled",
                  contact_matching_pos_threshold: float = 0.0005, contact_matching_normal_dot_threshold: float = 0.995,
-                 **unsupported):
+                 contact_report: bool = False, **unsupported):
         if broad_phase not in (None, "explicit", "nxn", "sap"):
             raise ValueError(f"unknown broad_phase {broad_phase!r} (expected 'explicit', 'nxn' or 'sap')")
         if contact_matching not in ("disabled", "latest", "sticky"):
             raise ValueError(f"contact_matching must be one of 'disabled', 'latest', 'sticky', got {contact_matching!r}")
-        if contact_matching == "sticky":
-            raise NotImplementedError('contact_matching="sticky" (replay of matched contact geometry) is not implemented; use "latest"')
         if contact_matching_pos_threshold < 0.0:
             raise ValueError(f"contact_matching_pos_threshold must be non-negative, got {contact_matching_pos_threshold}")
         if not -1.0 <= contact_matching_normal_dot_threshold <= 1.0:
             raise ValueError(f"contact_matching_normal_dot_threshold must be in [-1, 1], got {contact_matching_normal_dot_threshold}")
+        if contact_report and contact_matching == "disabled":
+            raise ValueError('contact_report=True requires contact_matching != "disabled"')
         self.contact_matching = contact_matching
+        self.contact_report = bool(contact_report)
         self.contact_matching_pos_threshold = float(contact_matching_pos_threshold)
         self.contact_matching_normal_dot_threshold = float(contact_matching_normal_dot_threshold)
         if contact_matching != "disabled":
@@ -85,7 +86,8 @@ class CollisionPipeline:
         """Allocate a :class:`Contacts` buffer sized for this pipeline (reference ``collide.py:1691-1730``)."""
         c = Contacts(self.rigid_contact_max, 0, device=self.device,
                      requested_attributes=self.model._requested_contact_attributes,
-                     contact_matching=self.contact_matching != "disabled")
+                     contact_matching=self.contact_matching != "disabled", contact_report=self.contact_report)
+        c._contact_matching_mode = self.contact_matching
         return c
 
     def reset(self, world_mask=None) -> None:
@@ -104,6 +106,10 @@ class CollisionPipeline:
 
     def collide(self, state, contacts, *, soft_contact_margin=None, dt=None):
         """Populate ``contacts`` from ``state.body_q`` (reference ``collide.py:1765-2207``)."""
+        if self.deterministic and contacts is not None and self.export_contacts and contacts.rigid_contact_max != self.rigid_contact_max:
+            # same rule as the reference's fixed-capacity sorter (sim/collide.py:1984-1991)
+            raise ValueError(f"Contacts buffer capacity ({contacts.rigid_contact_max}) does not match the deterministic sort buffer size "
+                             f"({self.rigid_contact_max}). Use CollisionPipeline.contacts() or pass matching rigid_contact_max.")
         view = None
         # every collide() overwrites the model's single set of contact blocks: stamp them, so that a Contacts object filled by
         # an EARLIER collide (or cleared / edited since) is recognised as stale by the solvers and re-imported from its arrays
@@ -124,12 +130,28 @@ class CollisionPipeline:
             if contacts.rigid_contact_match_index is None:
                 raise ValueError("CollisionPipeline has contact_matching enabled but the Contacts buffer was created without "
                                  "contact_matching. Use pipeline.contacts() to create a compatible buffer.")
+            if self.contact_report and contacts.rigid_contact_new_indices is None:
+                raise ValueError("CollisionPipeline has contact_report enabled but the Contacts buffer was created without "
+                                 "contact_report=True. Use pipeline.contacts() to create a compatible buffer.")
             mask = self._match_reset_mask
             mask_u8 = None if mask is None else mask.to(dtype=__import__("torch").uint8)
+            opt = _abi.MatchOptions(self.contact_matching_pos_threshold, self.contact_matching_normal_dot_threshold,
+                                    None if mask_u8 is None else mask_u8.data_ptr(), 1 if self._match_reset_all else 0,
+                                    1 if self.contact_matching == "sticky" else 0)
+            if self.contact_report:
+                n = contacts.rigid_contact_max
+                opt.new_indices = _abi.ptr(contacts.rigid_contact_new_indices, "i32", self.device, n, "contacts.rigid_contact_new_indices")
+                opt.new_count = _abi.ptr(contacts.rigid_contact_new_count, "i32", self.device, 1, "contacts.rigid_contact_new_count")
+                opt.broken_indices = _abi.ptr(contacts.rigid_contact_broken_indices, "i32", self.device, n, "contacts.rigid_contact_broken_indices")
+                opt.broken_count = _abi.ptr(contacts.rigid_contact_broken_count, "i32", self.device, 1, "contacts.rigid_contact_broken_count")
             st = _lib.lib().nb2_contacts_match(
                 self._native.handle, C.c_void_p(_abi.ptr(state.body_q)), view, C.c_void_p(contacts.rigid_contact_match_index.data_ptr()),
-                C.c_float(self.contact_matching_pos_threshold), C.c_float(self.contact_matching_normal_dot_threshold),
-                C.c_void_p(None if mask_u8 is None else mask_u8.data_ptr()), 1 if self._match_reset_all else 0,
-                _lib.current_stream_ptr(self.model))
+                C.byref(opt), _lib.current_stream_ptr(self.model))
             _lib.check(st, "nb2_contacts_match")
+            if self.contact_matching == "sticky":
+                # matched rows now carry last frame's geometry: the contact blocks nb2_collide left on the device no longer
+                # describe this buffer, so the solvers load it through nb2_contacts_import
+                contacts.invalidate_native()
             self._match_reset_all, self._match_reset_mask = False, None
+        if contacts is not None:
+            contacts._contact_matching_mode = self.contact_matching

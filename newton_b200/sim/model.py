@@ -110,7 +110,10 @@ class Contacts:
     """
 
     def __init__(self, rigid_contact_max: int, soft_contact_max: int = 0, device="cpu", requested_attributes=(),
-                 contact_matching: bool = False):
+                 contact_matching: bool = False, contact_report: bool = False):
+        if contact_report and not contact_matching:
+            raise ValueError("contact_report=True requires contact_matching=True")
+        self._contact_matching_mode = "disabled"
         self.rigid_contact_max = int(rigid_contact_max)
         self.soft_contact_max = int(soft_contact_max)
         self.device = torch.device(device)
@@ -138,9 +141,20 @@ class Contacts:
         # -1 = MATCH_NOT_FOUND, -2 = MATCH_BROKEN; allocated by CollisionPipeline(contact_matching="latest").contacts()
         self.contact_matching = bool(contact_matching)
         self.rigid_contact_match_index = torch.full((n,), -1, dtype=I32, device=dev) if contact_matching else None
+        # compact lists of rows without a match / of last frame's rows nothing matched (sim/contacts.py:328-347)
+        self.contact_report = bool(contact_report)
+        self.rigid_contact_new_indices = torch.zeros((n,), dtype=I32, device=dev) if contact_report else None
+        self.rigid_contact_new_count = torch.zeros(1, dtype=I32, device=dev) if contact_report else None
+        self.rigid_contact_broken_indices = torch.zeros((n,), dtype=I32, device=dev) if contact_report else None
+        self.rigid_contact_broken_count = torch.zeros(1, dtype=I32, device=dev) if contact_report else None
         self.clear_buffers = False
         self._nb2_blocks = None
         self._nb2_stamp = -1  # generation of the native contact blocks this buffer mirrors (see CollisionPipeline.collide)
+
+    @property
+    def contact_matching_mode(self) -> str:
+        """Matching mode of the pipeline that created or last filled this buffer (reference ``sim/contacts.py:557-565``)."""
+        return self._contact_matching_mode
 
     def clear(self, bump_generation: bool = True) -> None:
         self.contact_counters.zero_()

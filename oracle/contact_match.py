@@ -1,8 +1,9 @@
 """oracle/contact_match.py - TEST INFRASTRUCTURE ONLY.
 
-NumPy restatement of the reference's frame-to-frame contact matcher in ``"latest"`` mode (``newton/_src/geometry/contact_match.py``:
-``_match_contacts_kernel`` :266-354, ``_resolve_claims_kernel`` :357-390, ``_save_sorted_state_kernel`` :442-477) on the sorted
-``Contacts`` arrays.  Sort keys follow ``make_contact_sort_key`` (``geometry/contact_data.py:59-87``) with the contact's position
+NumPy restatement of the reference's frame-to-frame contact matcher (``newton/_src/geometry/contact_match.py``:
+``_match_contacts_kernel`` :266-354, ``_resolve_claims_kernel`` :357-390, ``_save_sorted_state_kernel`` :442-477; ``"sticky"``:
+``_replay_matched_kernel`` :529-561; ``contact_report``: ``_collect_contact_report_kernel`` :568-595) on the sorted
+``Contacts`` arrays, in the call order of ``CollisionPipeline.collide`` (``sim/collide.py:2033-2137``): match, replay, report, save.  Sort keys follow ``make_contact_sort_key`` (``geometry/contact_data.py:59-87``) with the contact's position
 inside its pair's run as the sub key."""
 
 from __future__ import annotations
@@ -27,7 +28,11 @@ def _world(point, body, body_q):
 
 
 class ContactMatcher:
-    def __init__(self, model, pos_threshold: float = 0.0005, normal_dot_threshold: float = 0.995):
+    def __init__(self, model, pos_threshold: float = 0.0005, normal_dot_threshold: float = 0.995, sticky: bool = False):
+        self.sticky = bool(sticky)
+        self.prev_record = None  # sticky: (point0, point1, offset0, offset1) of the saved frame
+        self.new_indices = np.zeros(0, dtype=np.int32)     # contact_report of the last match(): rows without a match, ascending
+        self.broken_indices = np.zeros(0, dtype=np.int32)  # rows of the previous frame nothing matched (and not reset), ascending
         self.shape_body = model.numpy("shape_body")
         self.shape_world = model.numpy("shape_world")
         self.world_count = int(model.world_count)
@@ -90,9 +95,40 @@ class ContactMatcher:
                     claim[best] = c
             else:
                 match[i] = MATCH_BROKEN
+        was_matched = np.zeros(len(self.prev_keys), dtype=bool)
         for i in range(n):
-            if match[i] >= 0 and claim[int(match[i])][1] != (int(keys[i]) & 0xFFFFFFFF):
+            if match[i] < 0:
+                continue
+            if claim[int(match[i])][1] != (int(keys[i]) & 0xFFFFFFFF):
                 match[i] = MATCH_BROKEN
+            else:
+                was_matched[int(match[i])] = True
+        if self.sticky and self.prev_record is not None:  # replay: matched rows still in contact keep last frame's record
+            o0, o1 = contacts.rigid_contact_offset0[:n].numpy(), contacts.rigid_contact_offset1[:n].numpy()
+            m0, m1 = contacts.rigid_contact_margin0[:n].numpy(), contacts.rigid_contact_margin1[:n].numpy()
+            for i in range(n):
+                k = int(match[i])
+                if k < 0:
+                    continue
+                w0, w1 = _world(p0[i], self.shape_body[s0[i]], body_q), _world(p1[i], self.shape_body[s1[i]], body_q)
+                if np.float32(np.dot(w1 - w0, nrm[i])) - (m0[i] + m1[i]) > 0.0:
+                    continue
+                p0[i], p1[i], o0[i], o1[i] = (self.prev_record[f][k] for f in range(4))  # views: writes land in `contacts`
+                nrm[i] = self.prev_normal[k]
+            pos = np.stack([np.float32(0.5) * (_world(p0[i], self.shape_body[s0[i]], body_q) + _world(p1[i], self.shape_body[s1[i]], body_q))
+                            for i in range(n)]) if n else pos
+        # report (before the history is replaced)
+        self.new_indices = np.flatnonzero(match < 0).astype(np.int32)
+        broken = []
+        for k in range(len(self.prev_keys)):
+            key = int(self.prev_keys[k])
+            a, b = (key >> 43) & 0xFFFFF, (key >> 23) & 0xFFFFF
+            if not was_matched[k] and not (self._selected(int(self.shape_world[a])) or self._selected(int(self.shape_world[b]))):
+                broken.append(k)
+        self.broken_indices = np.asarray(broken, dtype=np.int32)
         self.prev_keys, self.prev_pos, self.prev_normal = keys, pos.astype(np.float32), nrm.copy()
+        if self.sticky:
+            self.prev_record = tuple(a[:n].numpy().copy() for a in (contacts.rigid_contact_point0, contacts.rigid_contact_point1,
+                                                                     contacts.rigid_contact_offset0, contacts.rigid_contact_offset1))
         self.reset_mask = None
         return match

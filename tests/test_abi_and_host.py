@@ -195,14 +195,17 @@ def test_collision_pipeline_constructor_options():
                     verify_buffers=True, contact_reduction_hashtable_size_factor=0.25, speculative_config=None)
     with pytest.raises(_lib.Nb2Error):
         newton_b200.CollisionPipeline(m, **defaults)
-    for ok in (dict(include_static_kinematic_pairs=False), dict(contact_matching="latest"), dict(broad_phase="sap", shape_pairs_max=1000)):
+    for ok in (dict(include_static_kinematic_pairs=False), dict(contact_matching="latest"), dict(contact_matching="sticky"), dict(contact_matching="latest", contact_report=True),
+               dict(broad_phase="sap", shape_pairs_max=1000)):
         with pytest.raises(_lib.Nb2Error):  # accepted: gets as far as the no-CPU-path error
             newton_b200.CollisionPipeline(m, **ok)
-    for bad in (dict(contact_matching="sticky"), dict(contact_report=True), dict(speculative_config=object()), dict(requires_grad=True),
+    for bad in (dict(speculative_config=object()), dict(requires_grad=True),
                 dict(narrow_phase=object())):
         with pytest.raises(NotImplementedError):
             newton_b200.CollisionPipeline(m, **bad)
     with pytest.raises(ValueError):
         newton_b200.CollisionPipeline(m, contact_matching="always")
+    with pytest.raises(ValueError, match="contact_report"):  # test_contact_matching.py:686-701
+        newton_b200.CollisionPipeline(m, contact_report=True)
     with pytest.raises(ValueError):
         newton_b200.CollisionPipeline(m, broad_phase="bvh")

@@ -154,6 +154,71 @@ def test_matching_normal_threshold_and_box_manifold(oracle_lib):
     np.testing.assert_array_equal(pipe.collide(s, c), [-2] * 4)
 
 
+def _snapshot(c, n):
+    return {f: getattr(c, f"rigid_contact_{f}")[:n].numpy().copy() for f in ("point0", "point1", "offset0", "offset1", "normal")}
+
+
+def test_sticky_replays_matched_rows_and_passes_new_ones_through(oracle_lib):
+    """test_contact_matching.py:704-773 - after a 0.1 mm shift (below the 0.5 mm threshold) the fresh narrow-phase record differs, the
+    sticky record equals frame 1 byte for byte; :776-830 - a contact of a newly arrived shape is not overwritten."""
+    b = ModelBuilder()
+    b.add_ground_plane()
+    for x in (-0.5, 0.5):
+        b.add_shape_box(b.add_body(xform=X.transform((x, 0.0, 0.0995), X.quat_from_axis_angle((0.0, 0.0, 1.0), 0.3))), hx=0.1, hy=0.1, hz=0.1)
+    late = b.add_shape_sphere(b.add_body(xform=X.transform((0.0, 0.0, 10.0))), radius=0.1)
+    m = b.finalize()
+    sticky, fresh = _OracleMatchingPipeline(oracle_lib, m, sticky=True), _OracleMatchingPipeline(oracle_lib, m)
+    c, cf, s = sticky.contacts(), fresh.contacts(), m.state()
+    assert np.all(sticky.collide(s, c) == -1)
+    n1 = int(c.rigid_contact_count[0])
+    assert n1 == 8
+    first = _snapshot(c, n1)
+    s.body_q[:, 0] += 0.0001
+    s.body_q[:2, 2] -= 0.0001
+    fresh.collide(s, cf)
+    assert not np.array_equal(cf.rigid_contact_point1[:n1].numpy(), first["point1"])  # the fresh record really moved
+    np.testing.assert_array_equal(sticky.collide(s, c), np.arange(n1))
+    for f, want in first.items():
+        np.testing.assert_array_equal(getattr(c, f"rigid_contact_{f}")[:n1].numpy(), want, err_msg=f)
+    # a matched contact that has separated (fresh gap > 0) keeps the fresh record instead
+    s.body_q[0, 2] += 0.0009  # 0.3 mm above the ground now: still inside the contact margin, midpoint moved by 0.45 mm
+    match = sticky.collide(s, c)
+    np.testing.assert_array_equal(match, np.arange(n1))
+    lifted = _snapshot(c, n1)
+    assert not np.array_equal(lifted["point0"][:4], first["point0"][:4]) or not np.array_equal(lifted["point1"][:4], first["point1"][:4])
+    np.testing.assert_array_equal(lifted["point1"][4:], first["point1"][4:])
+    # the parked sphere lands: its contact is new and carries its own shape
+    s.body_q[2, :3] = torch.tensor([0.0, 0.0, 0.1])
+    match = sticky.collide(s, c)
+    n3 = int(c.rigid_contact_count[0])
+    assert n3 == n1 + 1
+    shape1 = c.rigid_contact_shape1[:n3].numpy()
+    assert np.all(match[shape1 == late] < 0) and (shape1 == late).sum() == 1 and np.all(match[shape1 != late] >= 0)
+
+
+def test_contact_report_lists_new_and_broken_rows(oracle_lib):
+    """test_contact_matching.py:424-454, 493-528: first frame all new; stable frame neither new nor broken; a sphere that flies away
+    leaves a broken row (index into the OLD sorted buffer); a masked reset silences the broken rows of the reset worlds."""
+    m = _three_spheres()
+    pipe = _OracleMatchingPipeline(oracle_lib, m)
+    c, s = pipe.contacts(), m.state()
+    pipe.collide(s, c)
+    np.testing.assert_array_equal(pipe.matcher.new_indices, [0, 1, 2])
+    assert len(pipe.matcher.broken_indices) == 0
+    pipe.collide(s, c)
+    assert len(pipe.matcher.new_indices) == 0 and len(pipe.matcher.broken_indices) == 0
+    s.body_q[1, 2] = 10.0
+    np.testing.assert_array_equal(pipe.collide(s, c), [0, 2])
+    np.testing.assert_array_equal(pipe.matcher.broken_indices, [1])
+    assert len(pipe.matcher.new_indices) == 0
+    s.body_q[1, 2] = 0.1
+    s.body_q[0, 2] = 10.0
+    pipe.matcher.reset(np.array([False, True]))  # the global slot: every old row belongs to a reset world -> nothing is "broken"
+    match = pipe.collide(s, c)
+    assert np.all(match == -1) and len(pipe.matcher.broken_indices) == 0
+    np.testing.assert_array_equal(pipe.matcher.new_indices, [0, 1])
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 def _contacts_equal(cg, co, model):
     n_g, g = canonical_contacts(cg, model)
@@ -265,3 +330,54 @@ def test_gpu_contact_matching_matches_oracle(oracle_lib, cuda_lib):
             so.step(o0, o1, None, co, 1.0 / 240)
             o0, o1 = o1, o0
     assert -1 in seen and -2 in seen and max(seen) > 5  # the run saw new, broken and matched contacts
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["latest", "sticky"])
+def test_gpu_contact_report_and_sticky_match_oracle(oracle_lib, cuda_lib, mode):
+    """contact_report=True with "latest" / "sticky" on the moving heap: match_index, the new / broken lists and (sticky) the replayed
+    Contacts arrays of every frame equal the oracle matcher's; the solver consumes the replayed buffer (re-imported), so the states stay
+    bit-identical too."""
+    from oracle.contact_match import ContactMatcher
+
+    m = scenes.free_bodies_model(2)
+    mg = m.to("cuda:0")
+    pg = newton_b200.CollisionPipeline(mg, broad_phase="nxn", contact_matching=mode, contact_report=True, contact_matching_pos_threshold=0.002)
+    po = oracle_lib.CollisionPipeline(m, broad_phase="nxn", deterministic=True)
+    matcher = ContactMatcher(m, pos_threshold=0.002, sticky=mode == "sticky")
+    sg, so = newton_b200.solvers.SolverXPBD(mg, iterations=4), oracle_lib.SolverXPBD(m, iterations=4)
+    g0, g1, o0, o1 = mg.state(), mg.state(), m.state(), m.state()
+    cg, co = pg.contacts(), po.contacts()
+    assert cg.contact_matching_mode == mode and cg.rigid_contact_new_indices is not None
+    replayed = broken_seen = 0
+    for frame in range(30):
+        pg.collide(g0, cg)
+        po.collide(o0, co)
+        fresh_point1 = co.rigid_contact_point1.numpy().copy()
+        want = matcher.match(co, o0.body_q.numpy())
+        n = int(cg.rigid_contact_count.item())
+        assert n == len(want)
+        np.testing.assert_array_equal(cg.rigid_contact_match_index[:n].cpu().numpy(), want, err_msg=f"frame {frame}")
+        nn, nb = int(cg.rigid_contact_new_count.item()), int(cg.rigid_contact_broken_count.item())
+        np.testing.assert_array_equal(cg.rigid_contact_new_indices[:nn].cpu().numpy(), matcher.new_indices, err_msg=f"new, frame {frame}")
+        np.testing.assert_array_equal(cg.rigid_contact_broken_indices[:nb].cpu().numpy(), matcher.broken_indices, err_msg=f"broken, frame {frame}")
+        broken_seen += nb
+        for f in ("point0", "point1", "offset0", "offset1", "normal", "margin0", "margin1"):
+            np.testing.assert_array_equal(getattr(cg, f"rigid_contact_{f}")[:n].cpu().numpy(), getattr(co, f"rigid_contact_{f}")[:n].numpy(),
+                                          err_msg=f"{f}, frame {frame}")
+        replayed += int((fresh_point1[:n] != co.rigid_contact_point1[:n].numpy()).any(axis=1).sum())
+        if frame == 14:
+            mask = torch.zeros(3, dtype=torch.bool, device="cuda:0")
+            mask[1] = True
+            pg.reset(mask)
+            matcher.reset(np.array([False, True, False]))
+        for _ in range(3):
+            g0.clear_forces()
+            sg.step(g0, g1, None, cg, 1.0 / 240)
+            g0, g1 = g1, g0
+            o0.clear_forces()
+            so.step(o0, o1, None, co, 1.0 / 240)
+            o0, o1 = o1, o0
+        np.testing.assert_array_equal(g0.body_q.cpu().numpy(), o0.body_q.numpy(), err_msg=f"state, frame {frame}")
+    assert broken_seen > 0
+    assert (replayed > 0) == (mode == "sticky")
