@@ -100,6 +100,9 @@ def parse_args():
     p.add_argument("--workload", default="quadruped_xpbd", choices=sorted(WORKLOADS))
     p.add_argument("--fast-fp", action="store_true", help="use the FMA-contracted twin library (not bit-exact vs the oracle)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-export-contacts", action="store_true",
+                   help="CollisionPipeline(export_contacts=False): the solver reads the contact blocks, the reference-layout Contacts arrays "
+                        "are not written (an RL loop that never looks at them); NOT the default, the headline keeps the export")
     p.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N > 1: end-of-frame state gather mechanism")
     a = p.parse_args()
     select_workload(a.workload)
@@ -198,7 +201,7 @@ def run_native(args):
     envs = args.envs
     # every rank owns `envs` worlds (weak scaling); per-rank seed so shards differ like slices of one big scene
     model = build_scene(envs, seed=1 + rank).to(dev)
-    pipeline = newton_b200.CollisionPipeline(model)
+    pipeline = newton_b200.CollisionPipeline(model, export_contacts=not args.no_export_contacts)
     solver = make_solver(newton_b200.solvers, model)
     state_0, state_1 = model.state(), model.state()
     control = model.control()
@@ -398,6 +401,7 @@ def run_native(args):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(envs, world), "impl": "native",
             "fp_mode": "fast(fma)" if args.fast_fp else "strict (bit-exact vs oracle)",
+            "contacts_exported": not args.no_export_contacts,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches_per_step * args.steps),

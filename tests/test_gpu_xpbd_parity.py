@@ -450,3 +450,64 @@ def test_convex_hull_pile_bit_exact(oracle_lib, cuda_lib, solver_name):
         assert rc == gc and rc[-1] > 20
         for name in ("body_q", "body_qd", "joint_q", "joint_qd"):
             np.testing.assert_array_equal(getattr(got, name).cpu().numpy(), getattr(ref, name).numpy(), err_msg=name)
+
+
+class _WarpStyleArray:
+    """What the boundary sees of a ``wp.array``: ``.ptr`` (device address), ``.size`` (elements), ``.dtype`` with ``_length_`` scalars per
+    element, ``.device``.  No torch API - the arrays of a reference ``State`` / ``Control`` handed to the drop-in solvers look like this
+    (``_abi.ptr``'s Warp branch)."""
+
+    class _DType:
+        def __init__(self, length):
+            self._length_ = length
+
+    def __init__(self, tensor):
+        self._keep = tensor  # owns the memory
+        self.ptr = tensor.data_ptr()
+        width = tensor.shape[-1] if tensor.dim() > 1 else 1
+        self.size = tensor.numel() // width
+        self.shape = (self.size,)
+        self.dtype = self._DType(width)
+        self.device = str(tensor.device)
+
+
+class _Bag:
+    pass
+
+
+def _warp_style(obj, names):
+    out = _Bag()
+    for n in names:
+        v = getattr(obj, n, None)
+        setattr(out, n, None if v is None else _WarpStyleArray(v))
+    return out
+
+
+def test_warp_style_arrays_cross_the_boundary(oracle_lib, cuda_lib):
+    """States and controls whose arrays expose only ``.ptr`` (the reference's ``wp.array``s, rebuilt over torch memory because Warp is
+    not installed) run through ``CollisionPipeline.collide`` / ``SolverXPBD.step`` and give the oracle's result bit for bit; an
+    undersized foreign array is refused before the call."""
+    m = _drop(scenes.quadruped_model(4, seed=5), 4, 0.5)
+    ctl_fn = lambda mm: None  # noqa: E731
+    ref, _, rcounts = simulate(m, oracle_lib.CollisionPipeline, oracle_lib.SolverXPBD, substeps=40, dt=0.005,
+                               solver_kwargs={"iterations": 4}, record_contacts=True)
+    mg = m.to("cuda:0")
+    pipe, solver = newton_b200.CollisionPipeline(mg), newton_b200.solvers.SolverXPBD(mg, iterations=4)
+    s0, s1, contacts, control = mg.state(), mg.state(), pipe.contacts(), mg.control()
+    names = ("body_q", "body_qd", "body_f", "joint_q", "joint_qd")
+    w0, w1 = _warp_style(s0, names), _warp_style(s1, names)
+    wc = _warp_style(control, ("joint_f", "joint_target_q", "joint_target_qd", "joint_act"))
+    counts = []
+    for _ in range(40):
+        s0.body_f.zero_()
+        pipe.collide(w0, contacts)
+        counts.append(int(contacts.rigid_contact_count.item()))
+        solver.step(w0, w1, wc, contacts, 0.005)
+        s0, s1, w0, w1 = s1, s0, w1, w0
+    assert counts == rcounts
+    np.testing.assert_array_equal(s0.body_q.cpu().numpy(), ref.body_q.numpy())
+    np.testing.assert_array_equal(s0.body_qd.cpu().numpy(), ref.body_qd.numpy())
+    short = _warp_style(s0, names)
+    short.body_q = _WarpStyleArray(s0.body_q[:-1])
+    with pytest.raises(ValueError, match="too small"):
+        solver.step(short, w1, wc, contacts, 0.005)
