@@ -444,6 +444,16 @@ static nb2_status upload_tables(nb2_model* m) {
     NB2_CUDA_CHECK(cudaMemset(p, 0, (size_t(dv.env_count) + 1) * sizeof(int)));
     m->allocations.push_back(p);
     dv.env_contact_offset = static_cast<int*>(p);
+    // tile chain of the fused contact export: ticket = done = 0, epoch = 1 (zeroed status words belong to epoch 0: invalid)
+    NB2_CUDA_CHECK(cudaMalloc(&p, 4 * sizeof(int)));
+    const int sync_init[4] = {0, 0, 1, 0};
+    NB2_CUDA_CHECK(cudaMemcpy(p, sync_init, sizeof(sync_init), cudaMemcpyHostToDevice));
+    m->allocations.push_back(p);
+    dv.collide_sync = static_cast<int*>(p);
+    NB2_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(size_t(dv.env_count), 1) * sizeof(unsigned long long)));
+    NB2_CUDA_CHECK(cudaMemset(p, 0, std::max<size_t>(size_t(dv.env_count), 1) * sizeof(unsigned long long)));
+    m->allocations.push_back(p);
+    dv.collide_tile_status = static_cast<unsigned long long*>(p);
     return NB2_OK;
 }
 

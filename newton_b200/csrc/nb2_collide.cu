@@ -304,15 +304,32 @@ struct __align__(4) SlotRec {
 // WARPS warps per CTA (each warp = 32/L environments): the kernel is a straight line every warp walks once, so one-warp CTAs each
 // fetch the whole instruction stream cold (48 % `stall_no_inst`, profiles/r1f_collide_kernel_quadruped.txt); warps of one CTA
 // start together and share the fetches.
-template <int L, bool CONVEX, int WARPS>
-__global__ void __launch_bounds__(32 * WARPS) collide_kernel(DevModel M, const float* __restrict__ body_q) {
+// EXPORT = true also writes the reference-layout `Contacts` arrays in the same launch (the separate contact_export_kernel is gone from
+// the default path): a CTA ("tile") knows its environments' contact counts after the pair loop; the offset of its first contact in the
+// global arrays is the sum over all earlier tiles, obtained by a decoupled look-back over one status word per tile (epoch | flag |
+// count; flag 1 = the tile's own count, 2 = inclusive prefix).  Tiles take their index from a ticket counter, so a tile only ever
+// waits on tiles that started before it; the last CTA to finish re-arms ticket / done and bumps the epoch, which makes the words of
+// the previous launch (or graph replay) invalid without a memset.  Integer sums: the offsets equal a serial scan's.
+template <int L, bool CONVEX, int WARPS, bool EXPORT>
+__global__ void __launch_bounds__(32 * WARPS) collide_kernel(DevModel M, const float* __restrict__ body_q, nb2_contacts_view out) {
     constexpr int G = 32 / L;  // environments per warp
     extern __shared__ unsigned char smem_raw[];
+    __shared__ int s_tile[2];              // tile index, epoch
+    __shared__ int s_off[WARPS * G + 1];   // per-environment contact counts -> exclusive offsets inside the tile; [WARPS*G] = tile base
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane / L;
     const int l = lane % L;
     const unsigned gmask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << (grp * L));
-    const int env = (blockIdx.x * WARPS + warp) * G + grp;
+    int tile = blockIdx.x;
+    if (EXPORT) {
+        if (threadIdx.x == 0) {
+            s_tile[0] = atomicAdd(M.collide_sync + 0, 1);
+            s_tile[1] = *reinterpret_cast<volatile int*>(M.collide_sync + 2);
+        }
+        __syncthreads();
+        tile = s_tile[0];
+    }
+    const int env = (tile * WARPS + warp) * G + grp;
     const bool live = env < M.env_count;
     SlotRec* slots = reinterpret_cast<SlotRec*>(smem_raw) + size_t(warp * G + grp) * M.max_env_slots_shapes;
     const nb2_model_desc& d = M.d;
@@ -528,6 +545,92 @@ __global__ void __launch_bounds__(32 * WARPS) collide_kernel(DevModel M, const f
         n_total += total;
     }
     if (live && l == 0) M.env_contact_count[env] = n_total;
+    if constexpr (!EXPORT) return;
+
+    // ---- fused export: tile-local offsets, look-back for the tile base, scatter -----------------------------------------------
+    typedef unsigned long long u64;
+    constexpr int NE = WARPS * G;  // environments per tile (<= 32)
+    const unsigned epoch = unsigned(s_tile[1]) & 0x3FFFFFFFu;
+    if (l == 0) s_off[warp * G + grp] = live ? n_total : 0;
+    __syncthreads();  // also makes this CTA's contact-block stores visible to the lanes that copy them out below
+    if (warp == 0) {
+        const int mine = lane < NE ? s_off[lane] : 0;
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int tile_total = __shfl_sync(0xffffffffu, incl, 31);
+        volatile u64* status = M.collide_tile_status;
+        int base = 0;
+        if (tile > 0) {
+            if (lane == 0) status[tile] = (u64(epoch) << 34) | (1ull << 32) | u64(unsigned(tile_total));
+            int look = tile - 1;
+            for (;;) {
+                const int idx = look - lane;
+                u64 st = 0;
+                for (;;) {  // spin until the 32 predecessors of this window have published for this epoch
+                    bool valid = true;
+                    if (idx >= 0) {
+                        st = status[idx];
+                        valid = unsigned(st >> 34) == epoch && ((st >> 32) & 3ull) != 0ull;
+                    }
+                    if (__all_sync(0xffffffffu, valid)) break;
+                }
+                const int flag = idx >= 0 ? int((st >> 32) & 3ull) : 2, value = idx >= 0 ? int(unsigned(st)) : 0;
+                const unsigned inclusive = __ballot_sync(0xffffffffu, flag == 2);
+                const int stop = inclusive ? __ffs(inclusive) - 1 : 31;  // nearest predecessor that already holds an inclusive prefix
+                int part = lane <= stop ? value : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                base += part;
+                if (inclusive) break;
+                look -= 32;
+            }
+        }
+        if (lane == 0) {
+            status[tile] = (u64(epoch) << 34) | (2ull << 32) | u64(unsigned(base + tile_total));
+            s_off[NE] = base;
+            if (tile == int(gridDim.x) - 1) {  // the last tile's inclusive prefix is the global count
+                M.env_contact_offset[M.env_count] = base + tile_total;
+                out.rigid_contact_count[0] = base + tile_total;
+            }
+        }
+        if (lane < NE) s_off[lane] = incl - mine;
+    }
+    __syncthreads();
+    if (live) {
+        const int dst0 = s_off[NE] + s_off[warp * G + grp];
+        if (l == 0) M.env_contact_offset[env] = dst0;
+        const size_t T = size_t(M.slot_total);
+        const float* cb = M.cb;
+        for (int c = l; c < n_total; c += L) {
+            const int s = slot0 + c, o = dst0 + c;
+            if (o >= out.rigid_contact_max) break;  // overflow: the count keeps growing, the writes are dropped (collide.py:176-177)
+            out.shape0[o] = __float_as_int(cb[CF_SHAPE0 * T + s]);
+            out.shape1[o] = __float_as_int(cb[CF_SHAPE1 * T + s]);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                out.point0[3 * o + k] = cb[(CF_P0X + k) * T + s];
+                out.point1[3 * o + k] = cb[(CF_P1X + k) * T + s];
+                out.offset0[3 * o + k] = cb[(CF_O0X + k) * T + s];
+                out.offset1[3 * o + k] = cb[(CF_O1X + k) * T + s];
+                out.normal[3 * o + k] = cb[(CF_NX + k) * T + s];
+            }
+            out.margin0[o] = cb[CF_MARGIN0 * T + s];
+            out.margin1[o] = cb[CF_MARGIN1 * T + s];
+            if (out.tids) out.tids[o] = 0;
+        }
+    }
+    if (threadIdx.x == 0) {  // re-arm the chain for the next launch
+        __threadfence();
+        if (atomicAdd(M.collide_sync + 1, 1) == int(gridDim.x) - 1) {
+            M.collide_sync[0] = 0;
+            M.collide_sync[1] = 0;
+            M.collide_sync[2] = s_tile[1] + 1;
+        }
+    }
 }
 
 // ---- run-time broad phases: per-world NxN enumeration / sweep-and-prune (reference geometry/broad_phase_nxn.py:132-218,
@@ -976,21 +1079,27 @@ nb2_status launch_contacts_import(nb2_model* m, const nb2_contacts_view& in, cud
 }
 
 template <int L, bool CONVEX, int WARPS>
-static nb2_status launch_collide_W(nb2_model* m, const float* body_q, cudaStream_t s) {
+static nb2_status launch_collide_W(nb2_model* m, const float* body_q, const nb2_contacts_view* fused_out, cudaStream_t s) {
     const DevModel& M = m->dev;
     const int NE = (32 / L) * WARPS;
     const int blocks = (M.env_count + NE - 1) / NE;
     const size_t smem = size_t(NE) * M.max_env_slots_shapes * sizeof(SlotRec);
-    if (smem > 48 * 1024)
-        NB2_CUDA_CHECK(cudaFuncSetAttribute(collide_kernel<L, CONVEX, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    collide_kernel<L, CONVEX, WARPS><<<blocks, 32 * WARPS, smem, s>>>(M, body_q);
+    if (fused_out) {
+        if (smem > 48 * 1024)
+            NB2_CUDA_CHECK(cudaFuncSetAttribute(collide_kernel<L, CONVEX, WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        collide_kernel<L, CONVEX, WARPS, true><<<blocks, 32 * WARPS, smem, s>>>(M, body_q, *fused_out);
+    } else {
+        if (smem > 48 * 1024)
+            NB2_CUDA_CHECK(cudaFuncSetAttribute(collide_kernel<L, CONVEX, WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        collide_kernel<L, CONVEX, WARPS, false><<<blocks, 32 * WARPS, smem, s>>>(M, body_q, nb2_contacts_view{});
+    }
     count_launch();
     NB2_CUDA_CHECK(cudaGetLastError());
     return NB2_OK;
 }
 
 template <int L, bool CONVEX>
-static nb2_status launch_collide_L(nb2_model* m, const float* body_q, cudaStream_t s) {
+static nb2_status launch_collide_L(nb2_model* m, const float* body_q, const nb2_contacts_view* fused_out, cudaStream_t s) {
     const DevModel& M = m->dev;
     const size_t per_warp = size_t(32 / L) * M.max_env_slots_shapes * sizeof(SlotRec);
     if (per_warp > 200 * 1024) {
@@ -1005,8 +1114,8 @@ static nb2_status launch_collide_L(nb2_model* m, const float* body_q, cudaStream
         const long long total_warps = (M.env_count + (32 / L) - 1) / (32 / L);
         warps = (total_warps + sms - 1) / sms >= 8 ? 8 : 1;
     }
-    if (warps >= 8 && per_warp * 8 <= 200 * 1024) return launch_collide_W<L, CONVEX, 8>(m, body_q, s);
-    return launch_collide_W<L, CONVEX, 1>(m, body_q, s);
+    if (warps >= 8 && per_warp * 8 <= 200 * 1024) return launch_collide_W<L, CONVEX, 8>(m, body_q, fused_out, s);
+    return launch_collide_W<L, CONVEX, 1>(m, body_q, fused_out, s);
 }
 
 template <int L>
@@ -1040,9 +1149,18 @@ nb2_status launch_collide(nb2_model* m, const float* body_q, const nb2_contacts_
     const DevModel& M = m->dev;
     if (M.env_count == 0 || M.d.shape_count == 0) return NB2_OK;
     nb2_status st;
+    if (contacts && (!contacts->rigid_contact_count || !contacts->shape0 || !contacts->shape1 || !contacts->point0 || !contacts->point1 ||
+                     !contacts->offset0 || !contacts->offset1 || !contacts->normal || !contacts->margin0 || !contacts->margin1)) {
+        set_error("nb2_collide: contacts view has NULL arrays");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
     if (M.dyn_pairs && (st = launch_broadphase(m, body_q, s)) != NB2_OK) return st;
+    // the `Contacts` arrays are written by the collide kernel itself (EXPORT = true); NB2_COLLIDE_FUSED_EXPORT=0 keeps the
+    // round-1 two-kernel path (collide, then contact_export_kernel) for A/B runs
+    static const bool fused = !(std::getenv("NB2_COLLIDE_FUSED_EXPORT") && std::atoi(std::getenv("NB2_COLLIDE_FUSED_EXPORT")) == 0);
+    const nb2_contacts_view* fused_out = (contacts && fused) ? contacts : nullptr;
 #define NB2_COLLIDE_DISPATCH(LANES) \
-    st = m->has_convex_pairs ? launch_collide_L<LANES, true>(m, body_q, s) : launch_collide_L<LANES, false>(m, body_q, s)
+    st = m->has_convex_pairs ? launch_collide_L<LANES, true>(m, body_q, fused_out, s) : launch_collide_L<LANES, false>(m, body_q, fused_out, s)
     switch (m->lanes_per_env) {
         case 8: NB2_COLLIDE_DISPATCH(8); break;
         case 16: NB2_COLLIDE_DISPATCH(16); break;
@@ -1050,12 +1168,7 @@ nb2_status launch_collide(nb2_model* m, const float* body_q, const nb2_contacts_
     }
 #undef NB2_COLLIDE_DISPATCH
     if (st != NB2_OK) return st;
-    if (contacts) {
-        if (!contacts->rigid_contact_count || !contacts->shape0 || !contacts->shape1 || !contacts->point0 || !contacts->point1 ||
-            !contacts->offset0 || !contacts->offset1 || !contacts->normal || !contacts->margin0 || !contacts->margin1) {
-            set_error("nb2_collide: contacts view has NULL arrays");
-            return NB2_ERR_INVALID_ARGUMENT;
-        }
+    if (contacts && !fused_out) {
         if (M.env_count <= 8192) {
             contact_export_kernel<true><<<(M.env_count + 3) / 4, 128, 0, s>>>(M, *contacts);
             count_launch();

@@ -47,6 +47,8 @@ struct DevModel {
     int slot_total;
     int* env_contact_count;        // [E]
     int* env_contact_offset;       // [E+1] exclusive scan, written by the export path
+    int* collide_sync;             // [3] ticket / done / epoch of the fused export's tile chain (collide_kernel)
+    unsigned long long* collide_tile_status;  // [E] (epoch | flag | count) per tile: decoupled look-back of the export offsets
     int max_env_bodies, max_env_joints, max_env_slots_shapes, max_env_pairs, max_env_contact_slots;
     // articulated-body (Featherstone) tables
     const int* joint_depth;            // [J] depth of each joint in its articulation tree (root = 0)
