@@ -566,27 +566,42 @@ __global__ void __launch_bounds__(32 * WARPS) collide_kernel(DevModel M, const f
         int base = 0;
         if (tile > 0) {
             if (lane == 0) status[tile] = (u64(epoch) << 34) | (1ull << 32) | u64(unsigned(tile_total));
+            // a window is 8 x 32 predecessors (word w of lane i is tile look - (32 w + i)), loaded together, so that the 256 tiles
+            // of a 4096-environment batch resolve in ONE L2 round trip - all tiles of a single-wave launch finish at about the same
+            // time, so inclusive prefixes are rarely there yet and the walk goes all the way back
+            constexpr int WORDS = 8;
             int look = tile - 1;
             for (;;) {
-                const int idx = look - lane;
-                u64 st = 0;
-                for (;;) {  // spin until the 32 predecessors of this window have published for this epoch
+                u64 st[WORDS];
+                for (;;) {  // spin until every predecessor of this window has published for this epoch
                     bool valid = true;
-                    if (idx >= 0) {
-                        st = status[idx];
-                        valid = unsigned(st >> 34) == epoch && ((st >> 32) & 3ull) != 0ull;
+#pragma unroll
+                    for (int w = 0; w < WORDS; ++w) {
+                        const int idx = look - (32 * w + lane);
+                        st[w] = idx >= 0 ? status[idx] : 0ull;
+                    }
+#pragma unroll
+                    for (int w = 0; w < WORDS; ++w) {
+                        const int idx = look - (32 * w + lane);
+                        if (idx >= 0) valid = valid && unsigned(st[w] >> 34) == epoch && ((st[w] >> 32) & 3ull) != 0ull;
                     }
                     if (__all_sync(0xffffffffu, valid)) break;
                 }
-                const int flag = idx >= 0 ? int((st >> 32) & 3ull) : 2, value = idx >= 0 ? int(unsigned(st)) : 0;
-                const unsigned inclusive = __ballot_sync(0xffffffffu, flag == 2);
-                const int stop = inclusive ? __ffs(inclusive) - 1 : 31;  // nearest predecessor that already holds an inclusive prefix
-                int part = lane <= stop ? value : 0;
+                bool done = false;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-                base += part;
-                if (inclusive) break;
-                look -= 32;
+                for (int w = 0; w < WORDS; ++w) {
+                    const int idx = look - (32 * w + lane);
+                    const int flag = idx >= 0 ? int((st[w] >> 32) & 3ull) : 2, value = idx >= 0 ? int(unsigned(st[w])) : 0;
+                    const unsigned inclusive = __ballot_sync(0xffffffffu, flag == 2);
+                    const int stop = inclusive ? __ffs(inclusive) - 1 : 31;  // nearest predecessor that already holds an inclusive prefix
+                    int part = (!done && lane <= stop) ? value : 0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                    base += part;
+                    done = done || inclusive != 0u;
+                }
+                if (done) break;
+                look -= 32 * WORDS;
             }
         }
         if (lane == 0) {
