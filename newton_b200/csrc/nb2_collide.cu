@@ -1170,9 +1170,11 @@ nb2_status launch_collide(nb2_model* m, const float* body_q, const nb2_contacts_
         return NB2_ERR_INVALID_ARGUMENT;
     }
     if (M.dyn_pairs && (st = launch_broadphase(m, body_q, s)) != NB2_OK) return st;
-    // the `Contacts` arrays are written by the collide kernel itself (EXPORT = true); NB2_COLLIDE_FUSED_EXPORT=0 keeps the
-    // round-1 two-kernel path (collide, then contact_export_kernel) for A/B runs
-    static const bool fused = !(std::getenv("NB2_COLLIDE_FUSED_EXPORT") && std::atoi(std::getenv("NB2_COLLIDE_FUSED_EXPORT")) == 0);
+    // NB2_COLLIDE_FUSED_EXPORT=1: the `Contacts` arrays are written by the collide kernel itself (EXPORT = true, tile chain with
+    // decoupled look-back).  Measured on B200 it LOSES to the two-kernel path (collide, then contact_export_kernel): 4096 quadruped
+    // envs, frame 690.1 vs 678.3 us L2-warm, 733.8 vs 718.0 us with L2 flushed (profiles/r2j_fused_export_ab.txt) - the 256 tiles of
+    // a single-wave launch all reach the look-back at the same time and serialise on it.  So the default is the two-kernel path.
+    static const bool fused = std::getenv("NB2_COLLIDE_FUSED_EXPORT") && std::atoi(std::getenv("NB2_COLLIDE_FUSED_EXPORT")) != 0;
     const nb2_contacts_view* fused_out = (contacts && fused) ? contacts : nullptr;
 #define NB2_COLLIDE_DISPATCH(LANES) \
     st = m->has_convex_pairs ? launch_collide_L<LANES, true>(m, body_q, fused_out, s) : launch_collide_L<LANES, false>(m, body_q, fused_out, s)

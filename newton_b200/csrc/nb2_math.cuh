@@ -99,17 +99,21 @@ NB2_DEV Q4 qunit(Q4 q) {
     return Q4(0.f, 0.f, 0.f, 1.f);
 }
 // v(2w^2-1) + 2(q.v)q +/- 2w(q x v)
+// The reference formula multiplies each cross term by q.w and then by 2; (t * q.w) * 2 == t * (2 * q.w) bit for bit (scaling by a
+// power of two commutes with rounding outside the subnormal range), so 2 * q.w is formed once per quaternion and shared with `c`.
 NB2_DEV V3 qrot(Q4 q, V3 v) {
-    float c = 2.0f * q.w * q.w - 1.0f;
+    const float w2 = 2.0f * q.w;
+    float c = w2 * q.w - 1.0f;
     float d = 2.0f * (q.x * v.x + q.y * v.y + q.z * v.z);
-    return V3(v.x * c + q.x * d + (q.y * v.z - q.z * v.y) * q.w * 2.0f, v.y * c + q.y * d + (q.z * v.x - q.x * v.z) * q.w * 2.0f,
-              v.z * c + q.z * d + (q.x * v.y - q.y * v.x) * q.w * 2.0f);
+    return V3(v.x * c + q.x * d + (q.y * v.z - q.z * v.y) * w2, v.y * c + q.y * d + (q.z * v.x - q.x * v.z) * w2,
+              v.z * c + q.z * d + (q.x * v.y - q.y * v.x) * w2);
 }
 NB2_DEV V3 qrot_inv(Q4 q, V3 v) {
-    float c = 2.0f * q.w * q.w - 1.0f;
+    const float w2 = 2.0f * q.w;
+    float c = w2 * q.w - 1.0f;
     float d = 2.0f * (q.x * v.x + q.y * v.y + q.z * v.z);
-    return V3(v.x * c + q.x * d - (q.y * v.z - q.z * v.y) * q.w * 2.0f, v.y * c + q.y * d - (q.z * v.x - q.x * v.z) * q.w * 2.0f,
-              v.z * c + q.z * d - (q.x * v.y - q.y * v.x) * q.w * 2.0f);
+    return V3(v.x * c + q.x * d - (q.y * v.z - q.z * v.y) * w2, v.y * c + q.y * d - (q.z * v.x - q.x * v.z) * w2,
+              v.z * c + q.z * d - (q.x * v.y - q.y * v.x) * w2);
 }
 
 struct M33 {

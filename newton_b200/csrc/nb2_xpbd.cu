@@ -36,17 +36,18 @@ enum { XF_JOINT_CACHE = 1, XF_TMA = 2, XF_PHASE_SYNC = 4, XF_PHASE_SYNC_FINE = 8
 enum { CC_P0 = 0, CC_P1 = 3, CC_N = 6, CC_MSUM = 9, CC_MU = 10, CC_MUT = 11, CC_MUR = 12, CC_Q0 = 13, CC_Q1 = 16, CC_SIZE = 19 };
 
 // Code-size control.  The first kernel version inlined and unrolled everything: 9 400 SASS instructions (150 KB) and
-// 19 % of the stall samples on instruction fetch (profiles/r1a_xpbd_step_kernel.txt).  Measured on B200 (round-1c A/B,
-// profiles/r1c_xpbd_code_size_ab.txt): keeping the 3-row joint loops rolled (8 200 instr.) and/or turning the shared
-// helpers into real calls (6 900 instr.) changes the kernel time by < 1 % - the fetch stalls come from 14 one-warp CTAs
-// per SM each walking its own place in the code, not from the absolute size.  The rolled loops are kept (smaller, same
-// speed); -DNB2_XPBD_NOINLINE / -DNB2_XPBD_UNROLLED rebuild the other variants.
+// 19 % of the stall samples on instruction fetch (profiles/r1a_xpbd_step_kernel.txt).  With one-warp CTAs (round 1) rolled vs.
+// unrolled 3-row joint loops and real calls vs. inlined helpers all timed within 1 % of each other
+// (profiles/r1c_xpbd_code_size_ab.txt).  With 14-warp CTAs walking the code together (round 2) the instruction stream is fetched once
+// per CTA, and the unrolled rows win: no per-row component selects / loop control, three independent rows for the scheduler to
+// interleave - 143.7 -> 139.7 us at 4096 quadruped envs (profiles/r2j_fused_export_ab.txt), so unrolled is the default.
+// -DNB2_XPBD_ROLLED / -DNB2_XPBD_NOINLINE rebuild the other variants.
 #ifdef NB2_XPBD_NOINLINE
 #define NB2_HELPER __host__ __device__ __noinline__
 #else
 #define NB2_HELPER NB2_DEV
 #endif
-#ifdef NB2_XPBD_UNROLLED
+#ifndef NB2_XPBD_ROLLED
 #define NB2_ROW_UNROLL _Pragma("unroll")
 #else
 #define NB2_ROW_UNROLL _Pragma("unroll 1")
