@@ -165,6 +165,54 @@ NB2_DEV float joint_force(float q, float qd, float tq, float tqd, float ke, floa
     return limit_f + damping_f + target_f + passive_f;
 }
 
+// wp.quat_from_matrix of the matrix whose COLUMNS are c0, c1, c2 (trace branch, else the largest diagonal element; normalized)
+NB2_DEV Q4 q_from_cols(V3 c0, V3 c1, V3 c2) {
+    const float m00 = c0.x, m10 = c0.y, m20 = c0.z, m01 = c1.x, m11 = c1.y, m21 = c1.z, m02 = c2.x, m12 = c2.y, m22 = c2.z;
+    const float tr = m00 + m11 + m22;
+    float x, y, z, w, h;
+    if (tr >= 0.0f) {
+        h = sqrtf(tr + 1.0f);
+        w = 0.5f * h;
+        h = 0.5f / h;
+        x = (m21 - m12) * h;
+        y = (m02 - m20) * h;
+        z = (m10 - m01) * h;
+    } else {
+        int md = 0;
+        if (m11 > m00) md = 1;
+        if (m22 > (md == 0 ? m00 : m11)) md = 2;
+        if (md == 0) {
+            h = sqrtf((m00 - (m11 + m22)) + 1.0f);
+            x = 0.5f * h;
+            h = 0.5f / h;
+            y = (m01 + m10) * h;
+            z = (m20 + m02) * h;
+            w = (m21 - m12) * h;
+        } else if (md == 1) {
+            h = sqrtf((m11 - (m22 + m00)) + 1.0f);
+            y = 0.5f * h;
+            h = 0.5f / h;
+            z = (m12 + m21) * h;
+            x = (m01 + m10) * h;
+            w = (m02 - m20) * h;
+        } else {
+            h = sqrtf((m22 - (m00 + m11)) + 1.0f);
+            z = 0.5f * h;
+            h = 0.5f / h;
+            x = (m20 + m02) * h;
+            y = (m12 + m21) * h;
+            w = (m10 - m01) * h;
+        }
+    }
+    return qunit(Q4(x, y, z, w));
+}
+// transform_2d_rotational_axes (sim/articulation.py:37-58): D6 joints with exactly two angular axes
+NB2_DEV void axes2(V3 a0, V3 a1, float q0, V3& o0, V3& o1) {
+    const Q4 q_off = q_from_cols(a0, a1, cross(a0, a1));
+    const V3 l0 = qrot(q_off, V3(1.f, 0.f, 0.f)), l1 = qrot(q_off, V3(0.f, 1.f, 0.f));
+    o0 = l0;
+    o1 = qrot(q_axis_angle(l0, q0), l1);
+}
 NB2_DEV void axes3(V3 a0, V3 a1, V3 a2, float q0, float q1, V3& o0, V3& o1, V3& o2) {  // transform_3d_rotational_axes
     Q4 q_0 = q_axis_angle(a0, q0);
     V3 a1w = qrot(q_0, a1);
@@ -186,6 +234,11 @@ NB2_DEV Xf joint_transform(const nb2_model_desc& d, int type, int axis_start, in
             if (lin > k) pos += ld3(d.joint_axis + 3 * (axis_start + k)) * jq[qs + k];
         const int ia = axis_start + lin, iq = qs + lin;
         if (ang == 1) rot = q_axis_angle(ld3(d.joint_axis + 3 * ia), jq[iq]);
+        if (ang == 2) {  // compute_2d_rotational_dofs (sim/articulation.py:61-82)
+            V3 w0, w1;
+            axes2(ld3(d.joint_axis + 3 * ia), ld3(d.joint_axis + 3 * (ia + 1)), jq[iq], w0, w1);
+            rot = qmul(q_axis_angle(w1, jq[iq + 1]), q_axis_angle(w0, jq[iq]));
+        }
         if (ang == 3) {
             V3 w0, w1, w2;
             axes3(ld3(d.joint_axis + 3 * ia), ld3(d.joint_axis + 3 * (ia + 1)), ld3(d.joint_axis + 3 * (ia + 2)), jq[iq], jq[iq + 1], w0, w1, w2);
@@ -508,6 +561,16 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
                 S6 S = twist_xf(X_s, S6(V3(), ld3(d.joint_axis + 3 * iqd)));
                 v_j = v_j + S * jqd[iqd];
                 st6(Sout + 6 * iqd, S);
+            }
+            if (ang == 2) {  // kernels.py:301-311
+                V3 w0, w1;
+                axes2(ld3(d.joint_axis + 3 * iqd), ld3(d.joint_axis + 3 * (iqd + 1)), sin.joint_q[iq], w0, w1);
+                S6 S0 = twist_xf(X_s, S6(V3(), w0)), S1 = twist_xf(X_s, S6(V3(), w1));
+                const float q0 = jqd[iqd], q1 = jqd[iqd + 1];
+                v_j = v_j + (S0 * q0 + S1 * q1);
+                st6(Sout + 6 * iqd, S0);
+                st6(Sout + 6 * (iqd + 1), S1);
+                c_ang += cross(w0, w1) * (q0 * q1);
             }
             if (ang == 3) {
                 V3 w0, w1, w2;
@@ -953,6 +1016,11 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
                     if (lin > k) vj_lin += ld3(d.joint_axis + 3 * (qds + k)) * jqd[qds + k];
                 const int iq = qs + lin, iqd = qds + lin;
                 if (ang == 1) vj_ang = jqd[iqd] * ld3(d.joint_axis + 3 * iqd);
+                if (ang == 2) {
+                    V3 w0, w1;
+                    axes2(ld3(d.joint_axis + 3 * iqd), ld3(d.joint_axis + 3 * (iqd + 1)), jq[iq], w0, w1);
+                    vj_ang = w0 * jqd[iqd] + w1 * jqd[iqd + 1];
+                }
                 if (ang == 3) {
                     V3 w0, w1, w2;
                     axes3(ld3(d.joint_axis + 3 * iqd), ld3(d.joint_axis + 3 * (iqd + 1)), ld3(d.joint_axis + 3 * (iqd + 2)), jq[iq], jq[iq + 1], w0, w1, w2);
@@ -1131,6 +1199,11 @@ __device__ __forceinline__ void fk_joint(const nb2_model_desc& d, int i, const f
             if (lin > k) vj_lin += ld3(d.joint_axis + 3 * (qds + k)) * joint_qd[qds + k];
         const int iq = qs + lin, iqd = qds + lin;
         if (ang == 1) vj_ang = joint_qd[iqd] * ld3(d.joint_axis + 3 * iqd);
+        if (ang == 2) {
+            V3 w0, w1;
+            axes2(ld3(d.joint_axis + 3 * iqd), ld3(d.joint_axis + 3 * (iqd + 1)), joint_q[iq], w0, w1);
+            vj_ang = w0 * joint_qd[iqd] + w1 * joint_qd[iqd + 1];
+        }
         if (ang == 3) {
             V3 w0, w1, w2;
             axes3(ld3(d.joint_axis + 3 * iqd), ld3(d.joint_axis + 3 * (iqd + 1)), ld3(d.joint_axis + 3 * (iqd + 2)), joint_q[iq], joint_q[iq + 1],

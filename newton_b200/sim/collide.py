@@ -1,9 +1,9 @@
 """``CollisionPipeline`` - drop-in for the reference class (``newton/_src/sim/collide.py:1104-2207``).
 
 Same constructor kwargs and methods (``contacts()``, ``collide(state, contacts, *, dt=None)``) for the
-in-scope configuration: ``broad_phase="explicit"`` over ``model.shape_contact_pairs``, primitive +
-convex shapes.  All work happens in ``nb2_collide`` (one fused kernel,
-plus scan + scatter when exporting to the ``Contacts`` arrays).
+in-scope configuration: ``broad_phase="explicit"`` over ``model.shape_contact_pairs`` or the run-time ``"nxn"`` / ``"sap"``
+candidates, primitive + convex shapes, optional speculative contacts, contact matching.  All work
+happens in ``nb2_collide`` / ``nb2_collide_speculative`` (one fused kernel, plus scan + scatter when exporting to the ``Contacts`` arrays).
 """
 
 from __future__ import annotations
@@ -21,12 +21,31 @@ _IGNORED_OPTIONS = frozenset({"reduce_contacts", "max_triangle_pairs", "soft_con
 MATCH_NOT_FOUND, MATCH_BROKEN = -1, -2  # reference geometry/contact_match.py:113-117
 
 
+class SpeculativeContactConfig:
+    """Reference ``CollisionPipeline.SpeculativeContactConfig`` (``sim/collide.py:1076-1102``): admit contacts that are predicted to
+    close within the collision-update interval ``dt`` passed to ``collide()``; the per-shape search gap grows by at most
+    ``max_speculative_extension`` [m]."""
+
+    def __init__(self, max_speculative_extension: float = 0.1):
+        import math
+
+        value = float(max_speculative_extension)
+        if not math.isfinite(value) or value < 0.0:
+            raise ValueError(f"max_speculative_extension must be a non-negative finite number, got {value!r}")
+        self.max_speculative_extension = value
+
+    def __repr__(self):
+        return f"SpeculativeContactConfig(max_speculative_extension={self.max_speculative_extension})"
+
+
 class CollisionPipeline:
+    SpeculativeContactConfig = SpeculativeContactConfig
+
     def __init__(self, model, *, broad_phase: str | None = None, rigid_contact_max: int | None = None,
                  deterministic: bool = False, soft_contact_margin: float = 0.01, requires_grad: bool = False,
                  export_contacts: bool = True, include_static_kinematic_pairs: bool = True, contact_matching: str = "disabled",
                  contact_matching_pos_threshold: float = 0.0005, contact_matching_normal_dot_threshold: float = 0.995,
-                 contact_report: bool = False, **unsupported):
+                 contact_report: bool = False, speculative_config: SpeculativeContactConfig | None = None, **unsupported):
         if broad_phase not in (None, "explicit", "nxn", "sap"):
             raise ValueError(f"unknown broad_phase {broad_phase!r} (expected 'explicit', 'nxn' or 'sap')")
         if contact_matching not in ("disabled", "latest", "sticky"):
@@ -47,6 +66,10 @@ class CollisionPipeline:
                 raise ValueError("contact matching works on the exported Contacts arrays: export_contacts must stay True")
         self._match_reset_all = False
         self._match_reset_mask = None
+        # speculative contacts (sim/collide.py:1315-1317): the writer admits predicted contacts, collide() needs dt
+        if speculative_config is not None:
+            SpeculativeContactConfig(speculative_config.max_speculative_extension)  # same validation for duck-typed configs
+        self.speculative_config = speculative_config
         self.broad_phase = broad_phase or "explicit"
         if self.broad_phase == "explicit" and getattr(model, "shape_contact_pairs", None) is None:
             raise ValueError("model.shape_contact_pairs is missing (ModelBuilder.finalize() generates it)")
@@ -110,6 +133,15 @@ class CollisionPipeline:
             # same rule as the reference's fixed-capacity sorter (sim/collide.py:1984-1991)
             raise ValueError(f"Contacts buffer capacity ({contacts.rigid_contact_max}) does not match the deterministic sort buffer size "
                              f"({self.rigid_contact_max}). Use CollisionPipeline.contacts() or pass matching rigid_contact_max.")
+        spec_dt = 0.0
+        if self.speculative_config is not None:  # sim/collide.py:1823-1833
+            import math
+
+            if dt is None:
+                raise ValueError("dt must be provided when speculative contacts are enabled")
+            spec_dt = float(dt)
+            if not math.isfinite(spec_dt) or spec_dt < 0.0:
+                raise ValueError(f"dt must be a non-negative finite number, got {spec_dt!r}")
         view = None
         # every collide() overwrites the model's single set of contact blocks: stamp them, so that a Contacts object filled by
         # an EARLIER collide (or cleared / edited since) is recognised as stale by the solvers and re-imported from its arrays
@@ -120,9 +152,17 @@ class CollisionPipeline:
             contacts._nb2_exported = bool(self.export_contacts)
             if self.export_contacts:
                 view = C.byref(_abi.contacts_view(contacts, self.model))
-        st = _lib.lib().nb2_collide(self._native.handle, C.c_void_p(_abi.ptr(state.body_q, "f32", self.device, 7 * int(self.model.body_count), "state.body_q")), view,
-                                    _lib.current_stream_ptr(self.model))
-        _lib.check(st, "nb2_collide")
+        nb = int(self.model.body_count)
+        body_q = C.c_void_p(_abi.ptr(state.body_q, "f32", self.device, 7 * nb, "state.body_q"))
+        if self.speculative_config is not None:
+            st = _lib.lib().nb2_collide_speculative(
+                self._native.handle, body_q, C.c_void_p(_abi.ptr(state.body_qd, "f32", self.device, 6 * nb, "state.body_qd")),
+                C.c_float(spec_dt), C.c_float(float(self.speculative_config.max_speculative_extension)), view,
+                _lib.current_stream_ptr(self.model))
+            _lib.check(st, "nb2_collide_speculative")
+        else:
+            st = _lib.lib().nb2_collide(self._native.handle, body_q, view, _lib.current_stream_ptr(self.model))
+            _lib.check(st, "nb2_collide")
         if self.deterministic and view is not None:
             st = _lib.lib().nb2_contacts_sort(self._native.handle, view, _lib.current_stream_ptr(self.model))
             _lib.check(st, "nb2_contacts_sort")

@@ -43,6 +43,7 @@ def lib():
             build()
         _LIB = C.CDLL(so)
         _LIB.orc_collide.restype = C.c_int
+        _LIB.orc_collide_speculative.restype = C.c_int
         _LIB.orc_primitive_pair.restype = C.c_int
         _LIB.orc_convex_pair.restype = C.c_int
         _LIB.orc_version.restype = C.c_char_p
@@ -65,8 +66,15 @@ class CollisionPipeline:
     ``model.shape_contact_pairs`` is not read.  Pairs of two global (world -1) shapes are dropped in every mode: no body is
     involved, and the product keeps no contact blocks for them."""
 
-    def __init__(self, model, *, broad_phase=None, rigid_contact_max=None, deterministic=True, include_static_kinematic_pairs=True):
+    def __init__(self, model, *, broad_phase=None, rigid_contact_max=None, deterministic=True, include_static_kinematic_pairs=True,
+                 speculative_config=None):
         _check_cpu(model)
+        # speculative contacts (sim/collide.py:1076-1102, 1315-1317): any object with .max_speculative_extension
+        self.speculative_config = speculative_config
+        if speculative_config is not None:
+            v = float(speculative_config.max_speculative_extension)
+            if not np.isfinite(v) or v < 0.0:
+                raise ValueError(f"max_speculative_extension must be a non-negative finite number, got {v!r}")
         if broad_phase not in (None, "explicit", "nxn", "sap"):
             raise ValueError(f"unknown broad_phase {broad_phase!r}")
         self.model = model
@@ -88,12 +96,22 @@ class CollisionPipeline:
         return Contacts(self.rigid_contact_max, 0, device="cpu",
                         requested_attributes=self.model._requested_contact_attributes)
 
-    def _candidates(self, state):
+    def _candidates(self, state, dt=0.0, max_ext=0.0):
         from . import broad_phase as _bp
 
-        lo, hi = shape_aabbs(self.model, state.body_q)
-        fn = _bp.nxn_candidate_pairs if self.broad_phase == "nxn" else _bp.sap_candidate_pairs
-        pairs = fn(self.model, lo, hi, getattr(self.model, "shape_collision_filter_pairs", ()), self.include_static_kinematic_pairs)
+        active = self.speculative_config is not None and dt > 0.0 and max_ext > 0.0
+        filt = getattr(self.model, "shape_collision_filter_pairs", ())
+        if active:  # swept AABBs: compute_shape_velocities + check_aabb_overlap_moving (collide.py:1877-1947)
+            lo, hi, disp = shape_aabbs_speculative(self.model, state.body_q, state.body_qd, dt, max_ext)
+            if self.broad_phase == "nxn":
+                pairs = _bp.nxn_candidate_pairs(self.model, lo, hi, filt, self.include_static_kinematic_pairs, displacement=disp)
+            else:
+                pairs = _bp.sap_candidate_pairs(self.model, lo, hi, filt, self.include_static_kinematic_pairs, displacement=disp,
+                                                sort_axis_displacement_limit=max_ext)
+        else:
+            lo, hi = shape_aabbs(self.model, state.body_q)
+            fn = _bp.nxn_candidate_pairs if self.broad_phase == "nxn" else _bp.sap_candidate_pairs
+            pairs = fn(self.model, lo, hi, filt, self.include_static_kinematic_pairs)
         sw = self.model.numpy("shape_world")
         if np.all(sw < 0):  # model built without begin_world(): one implicit world holding everything (builder.py:11276)
             return pairs
@@ -103,8 +121,16 @@ class CollisionPipeline:
         v = _abi.contacts_view(contacts)
         desc = self._desc
         keep = None
+        spec_dt, spec_ext = 0.0, 0.0
+        if self.speculative_config is not None:  # collide.py:1823-1833
+            if dt is None:
+                raise ValueError("dt must be provided when speculative contacts are enabled")
+            spec_dt = float(dt)
+            if not np.isfinite(spec_dt) or spec_dt < 0.0:
+                raise ValueError(f"dt must be a non-negative finite number, got {spec_dt!r}")
+            spec_ext = float(self.speculative_config.max_speculative_extension)
         if self.broad_phase != "explicit":
-            self.last_candidates = self._candidates(state)
+            self.last_candidates = self._candidates(state, spec_dt, spec_ext)
             keep = np.ascontiguousarray(np.asarray(self.last_candidates, dtype=np.int32).reshape(-1, 2))
             desc = _abi.ModelDesc.from_buffer_copy(self._desc)
             desc.shape_contact_pairs = keep.ctypes.data if keep.size else None
@@ -120,9 +146,14 @@ class CollisionPipeline:
             desc = _abi.ModelDesc.from_buffer_copy(self._desc)
             desc.shape_contact_pairs = keep.ctypes.data if keep.size else None
             desc.shape_pair_count = int(keep.shape[0])
-        self.candidate_count = lib().orc_collide(
-            C.byref(desc), C.c_void_p(_abi.ptr(state.body_q)), C.byref(v), C.c_int(1 if self.deterministic else 0)
-        )
+        if self.speculative_config is not None:
+            self.candidate_count = lib().orc_collide_speculative(
+                C.byref(desc), C.c_void_p(_abi.ptr(state.body_q)), C.c_void_p(_abi.ptr(state.body_qd)), C.c_float(spec_dt),
+                C.c_float(spec_ext), C.byref(v), C.c_int(1 if self.deterministic else 0))
+        else:
+            self.candidate_count = lib().orc_collide(
+                C.byref(desc), C.c_void_p(_abi.ptr(state.body_q)), C.byref(v), C.c_int(1 if self.deterministic else 0)
+            )
         del keep
 
 
@@ -425,6 +456,18 @@ def eval_ik(model, state, joint_q, joint_qd):
                           C.c_void_p(_abi.ptr(joint_q)), C.c_void_p(_abi.ptr(joint_qd)))
     if n:
         raise NotImplementedError("oracle eval_ik: D6 joints with 2-3 angular axes")
+
+
+def shape_aabbs_speculative(model, body_q, body_qd, dt, max_extension):
+    """compute_shape_aabbs + compute_shape_velocities: (lower, upper, displacement) per shape"""
+    d = _abi.model_desc(model)
+    lo = np.zeros((model.shape_count, 3), dtype=np.float32)
+    hi = np.zeros((model.shape_count, 3), dtype=np.float32)
+    disp = np.zeros((model.shape_count, 3), dtype=np.float32)
+    lib().orc_shape_aabbs_speculative(C.byref(d), C.c_void_p(_abi.ptr(body_q)), C.c_void_p(_abi.ptr(body_qd)), C.c_float(dt),
+                                      C.c_float(max_extension), C.c_void_p(lo.ctypes.data), C.c_void_p(hi.ctypes.data),
+                                      C.c_void_p(disp.ctypes.data))
+    return lo, hi, disp
 
 
 def shape_aabbs(model, body_q):

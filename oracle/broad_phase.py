@@ -110,11 +110,41 @@ def check_aabb_overlap(lo1, hi1, lo2, hi2, cutoff: float = 0.0) -> bool:
     return bool(np.all(lo1 <= hi2 + cutoff) and np.all(hi1 >= lo2 - cutoff))
 
 
-def nxn_candidate_pairs(model, aabb_lower, aabb_upper, filter_pairs=(), include_static_kinematic_pairs: bool = True):
-    """Canonical (min, max) pairs ``_nxn_broadphase_kernel`` writes: the filter set intersected with AABB overlap."""
+def check_aabb_overlap_moving(lo1, hi1, lo2, hi2, disp1, disp2) -> bool:
+    """broad_phase_common.py:41-80: swept overlap of box 1 moving by ``disp1 - disp2`` relative to box 2 (speculative contacts);
+    float32 arithmetic, cutoffs 0 (the AABBs are pre-expanded)."""
+    f = np.float32
+    rel = np.asarray(disp1, dtype=np.float32) - np.asarray(disp2, dtype=np.float32)
+    enter, exit_time = f(0.0), f(1.0)
+    for axis in range(3):
+        lower1, upper1, lower2, upper2, delta = f(lo1[axis]), f(hi1[axis]), f(lo2[axis]), f(hi2[axis]), f(rel[axis])
+        if delta == 0.0:
+            if lower1 > upper2 or upper1 < lower2:
+                return False
+        else:
+            with np.errstate(over="ignore"):
+                axis_enter, axis_exit = f(lower2 - upper1) / delta, f(upper2 - lower1) / delta
+            if axis_enter > axis_exit:
+                axis_enter, axis_exit = axis_exit, axis_enter
+            enter = axis_enter if axis_enter > enter else enter
+            exit_time = axis_exit if axis_exit < exit_time else exit_time
+            if enter > exit_time:
+                return False
+    return True
+
+
+def _overlap(lo, hi, s1, s2, displacement):
+    if displacement is None:
+        return check_aabb_overlap(lo[s1], hi[s1], lo[s2], hi[s2])
+    return check_aabb_overlap_moving(lo[s1], hi[s1], lo[s2], hi[s2], displacement[s1], displacement[s2])
+
+
+def nxn_candidate_pairs(model, aabb_lower, aabb_upper, filter_pairs=(), include_static_kinematic_pairs: bool = True, displacement=None):
+    """Canonical (min, max) pairs ``_nxn_broadphase_kernel`` writes: the filter set intersected with AABB overlap (swept overlap when
+    the speculative pipeline passes per-shape displacements)."""
     out = []
     for s1, s2 in sorted(model_nxn_pairs(model, filter_pairs, include_static_kinematic_pairs)):
-        if check_aabb_overlap(aabb_lower[s1], aabb_upper[s1], aabb_lower[s2], aabb_upper[s2]):
+        if _overlap(aabb_lower, aabb_upper, s1, s2, displacement):
             out.append((s1, s2))
     return out
 
@@ -122,8 +152,11 @@ def nxn_candidate_pairs(model, aabb_lower, aabb_upper, filter_pairs=(), include_
 SAP_DIRECTION = np.array([0.5935, 0.7790, 0.1235], dtype=np.float32)
 
 
-def sap_candidate_pairs(model, aabb_lower, aabb_upper, filter_pairs=(), include_static_kinematic_pairs: bool = True):
-    """``BroadPhaseSAP.launch`` (broad_phase_sap.py:631-849): project, sort per world segment, range by binary search, sweep."""
+def sap_candidate_pairs(model, aabb_lower, aabb_upper, filter_pairs=(), include_static_kinematic_pairs: bool = True, displacement=None,
+                        sort_axis_displacement_limit=None):
+    """``BroadPhaseSAP.launch`` (broad_phase_sap.py:631-849): project, sort per world segment, range by binary search, sweep.
+    With ``displacement`` (speculative contacts) the projected interval is extended by the displacement along the sort axis, clamped
+    to ``sort_axis_displacement_limit`` (``_sap_project_aabb``, :44-78), and the final test is the swept overlap."""
     shape_world, shape_flags = model.numpy("shape_world"), model.numpy("shape_flags")
     group, shape_body = model.numpy("shape_collision_group"), model.numpy("shape_body")
     body_flags = model.numpy("body_flags") if model.body_count else ()
@@ -135,6 +168,13 @@ def sap_candidate_pairs(model, aabb_lower, aabb_upper, filter_pairs=(), include_
     radius = (np.abs(d)[None, :] * half).sum(axis=1, dtype=np.float32)
     center = (d[None, :] * (np.float32(0.5) * (lo + hi))).sum(axis=1, dtype=np.float32)
     plo, phi = center - radius, center + radius
+    if displacement is not None:
+        pd = (d[None, :] * np.asarray(displacement, dtype=np.float32)).sum(axis=1, dtype=np.float32)
+        if sort_axis_displacement_limit is not None and sort_axis_displacement_limit >= 0.0:
+            lim = np.float32(sort_axis_displacement_limit)
+            pd = np.minimum(np.maximum(pd, -lim), lim)  # wp.clamp = min(max(x, lo), hi)
+        plo = plo + np.minimum(pd, np.float32(0.0))
+        phi = phi + np.maximum(pd, np.float32(0.0))
     num_regular = len(slice_ends) - 1
     out = set()
     start = 0
@@ -160,7 +200,7 @@ def sap_candidate_pairs(model, aabb_lower, aabb_upper, filter_pairs=(), include_
                     continue
                 if (s1, s2) in excluded:
                     continue
-                if check_aabb_overlap(lo[s1], hi[s1], lo[s2], hi[s2]):
+                if _overlap(lo, hi, s1, s2, displacement):
                     out.add((s1, s2))
         start = end
     return sorted(out)

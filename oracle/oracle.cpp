@@ -74,6 +74,47 @@ int orc_collide(const nb2_model_desc* m, const float* body_q, const nb2_contacts
     return res.candidate_count;
 }
 
+// CollisionPipeline(speculative_config=SpeculativeContactConfig(max_speculative_extension)).collide(state, contacts, dt=dt)
+// (reference sim/collide.py:1076-1102, 1823-1836, 1877-1904).  Also returns the shape AABBs / displacements it used, for the run-time
+// broad phases of oracle/broad_phase.py.
+int orc_collide_speculative(const nb2_model_desc* m, const float* body_q, const float* body_qd, float dt, float max_extension,
+                            const nb2_contacts_view* contacts, int deterministic) {
+    SpeculativeParams sp;
+    sp.enabled = true;
+    sp.active = dt > 0.0f && max_extension > 0.0f;
+    sp.body_qd = body_qd;
+    sp.dt = dt;
+    sp.max_extension = max_extension;
+    CollideResult res;
+    collide_primitives(*m, body_q, res, sp);
+    gjk_mpr_pairs(*m, body_q, res, sp);
+    if (deterministic)
+        std::stable_sort(res.contacts.begin(), res.contacts.end(),
+                         [](const RawContact& a, const RawContact& b) { return a.key < b.key; });
+    store_contacts(res.contacts, *contacts);
+    return res.candidate_count;
+}
+
+// compute_shape_aabbs (+ compute_shape_velocities when dt > 0 and max_extension > 0): lower / upper [shape_count x 3], and for the
+// speculative pipeline the per-shape displacement [shape_count x 3] (may be NULL)
+void orc_shape_aabbs_speculative(const nb2_model_desc* m, const float* body_q, const float* body_qd, float dt, float max_extension,
+                                 float* lower, float* upper, float* displacement) {
+    std::vector<ShapeGeom> geom;
+    compute_shape_aabbs(*m, body_q, geom);
+    SpeculativeParams sp;
+    sp.enabled = true;
+    sp.active = dt > 0.0f && max_extension > 0.0f;
+    sp.body_qd = body_qd;
+    sp.dt = dt;
+    sp.max_extension = max_extension;
+    if (sp.active) compute_shape_velocities(*m, body_q, sp, geom);
+    for (int i = 0; i < m->shape_count; ++i) {
+        store3(lower + 3 * i, geom[i].aabb_lower);
+        store3(upper + 3 * i, geom[i].aabb_upper);
+        if (displacement) store3(displacement + 3 * i, geom[i].displacement);
+    }
+}
+
 void orc_integrate_bodies(const nb2_model_desc* m, const nb2_state_view* in, const nb2_state_view* out, float angular_damping,
                           float dt) {
     integrate_bodies(*m, in->body_q, in->body_qd, in->body_f, angular_damping, dt, out->body_q, out->body_qd);

@@ -258,6 +258,19 @@ struct ShapeGeom {  // geom_data / geom_xform written by compute_shape_aabbs
     float margin;
     transform X_ws;
     vec3 aabb_lower, aabb_upper;
+    // compute_shape_velocities (speculative contacts only): shape-origin velocity, angular velocity, velocity-extended gap,
+    // displacement over the collision-update interval
+    vec3 linear_velocity, angular_velocity, displacement;
+    float search_gap = 0.0f;
+};
+
+// CollisionPipeline(speculative_config=...) + collide(dt=...) (reference sim/collide.py:1076-1102, 1823-1836)
+struct SpeculativeParams {
+    bool active = false;   // speculative_active: enabled and dt > 0 and max_speculative_extension > 0
+    bool enabled = false;  // the pipeline was built with a speculative_config (the writer is write_contact_speculative even when inactive)
+    const float* body_qd = nullptr;
+    float dt = 0.0f;
+    float max_extension = 0.0f;
 };
 
 // reference sim/collide.py:283-472 (primitive branches)
@@ -377,6 +390,82 @@ inline bool check_aabb_overlap(vec3 l1, vec3 u1, vec3 l2, vec3 u2) {  // broad_p
     const float c = 0.0f + 0.0f;
     return l1.x <= u2.x + c && u1.x >= l2.x - c && l1.y <= u2.y + c && u1.y >= l2.y - c && l1.z <= u2.z + c &&
            u1.z >= l2.z - c;
+}
+
+// reference sim/collide.py:475-541 (compute_shape_velocities): runs after compute_shape_aabbs when speculative contacts are active
+inline void compute_shape_velocities(const nb2_model_desc& m, const float* body_q, const SpeculativeParams& sp, std::vector<ShapeGeom>& g) {
+    for (int sid = 0; sid < m.shape_count; ++sid) {
+        ShapeGeom& o = g[sid];
+        const int body_id = m.shape_body[sid];
+        if (body_id == -1) {
+            o.linear_velocity = vec3(0.f);
+            o.angular_velocity = vec3(0.f);
+            o.search_gap = m.shape_gap[sid];
+            o.displacement = vec3(0.f);
+            continue;
+        }
+        transform X_wb = transform::load(body_q + 7 * body_id);
+        transform X_ws = X_wb * transform::load(m.shape_transform + 7 * sid);
+        vec3 shape_origin_world = X_ws.p;
+        vec3 com_world = transform_point(X_wb, load3(m.body_com + 3 * body_id));
+        spatial twist = spatial::load(sp.body_qd + 6 * body_id);
+        vec3 com_velocity = twist.top, angular_velocity = twist.bot;
+        vec3 shape_origin_velocity = com_velocity + cross(angular_velocity, shape_origin_world - com_world);
+        o.linear_velocity = shape_origin_velocity;
+        o.angular_velocity = angular_velocity;
+        vec3 local_lower = load3(m.shape_collision_aabb_lower + 3 * sid), local_upper = load3(m.shape_collision_aabb_upper + 3 * sid);
+        vec3 al = vabs(local_lower), au = vabs(local_upper);
+        vec3 furthest(maxf(al.x, au.x), maxf(al.y, au.y), maxf(al.z, au.z));
+        float angular_radius = maxf(length(furthest), m.shape_collision_radius[sid]);
+        float angular_speed_bound = length(angular_velocity) * angular_radius;
+        float search_extension = minf((length(shape_origin_velocity) + angular_speed_bound) * sp.dt, sp.max_extension);
+        o.search_gap = m.shape_gap[sid] + search_extension;
+        vec3 displacement = shape_origin_velocity * sp.dt;
+        float angular_extension = angular_speed_bound * sp.dt;
+        o.displacement = displacement;
+        float ae = minf(angular_extension, sp.max_extension);
+        o.aabb_lower = o.aabb_lower - vec3(ae, ae, ae);
+        o.aabb_upper = o.aabb_upper + vec3(ae, ae, ae);
+    }
+}
+
+// broad_phase_common.py:41-80 (check_aabb_overlap_moving, cutoffs 0): swept overlap over the relative displacement
+inline bool check_aabb_overlap_moving(const ShapeGeom& a, const ShapeGeom& b) {
+    const float cutoff_combined = 0.0f + 0.0f;
+    vec3 rel = a.displacement - b.displacement;
+    float enter = 0.0f, exit_time = 1.0f;
+    for (int axis = 0; axis < 3; ++axis) {
+        float lower1 = a.aabb_lower[axis], upper1 = a.aabb_upper[axis];
+        float lower2 = b.aabb_lower[axis] - cutoff_combined, upper2 = b.aabb_upper[axis] + cutoff_combined;
+        float delta = rel[axis];
+        if (delta == 0.0f) {
+            if (lower1 > upper2 || upper1 < lower2) return false;
+        } else {
+            float axis_enter = (lower2 - upper1) / delta, axis_exit = (upper2 - lower1) / delta;
+            if (axis_enter > axis_exit) std::swap(axis_enter, axis_exit);
+            enter = maxf(enter, axis_enter);
+            exit_time = minf(exit_time, axis_exit);
+            if (enter > exit_time) return false;
+        }
+    }
+    return true;
+}
+
+// contact_data.py:187-233: prepare_speculative_contact + contact_passes_speculative_gap_check.  `gap_sum` is the AUTHORED pair gap.
+inline bool speculative_admit(const ShapeGeom& A, const ShapeGeom& B, vec3 center, vec3 n_ab, float distance, float radius_eff_a,
+                              float radius_eff_b, float margin_a, float margin_b, float gap_sum, const SpeculativeParams& sp) {
+    vec3 normal = normalize(n_ab);
+    vec3 point_a = center - normal * (0.5f * distance + radius_eff_a);
+    vec3 point_b = center + normal * (0.5f * distance + radius_eff_b);
+    float total_separation_needed = radius_eff_a + radius_eff_b + margin_a + margin_b;
+    float physical_separation = dot(point_b - point_a, normal) - total_separation_needed;
+    if (physical_separation <= gap_sum) return true;
+    // compute_contact_approach_speed / compute_contact_predictive_score (:92-135); geom_transform holds the shape origins
+    vec3 velocity_a = A.linear_velocity + cross(A.angular_velocity, point_a - A.X_ws.p);
+    vec3 velocity_b = B.linear_velocity + cross(B.angular_velocity, point_b - B.X_ws.p);
+    float approach_speed = maxf(-dot(velocity_b - velocity_a, normal), 0.0f);
+    float extension = minf(approach_speed * sp.dt, sp.max_extension);
+    return extension - physical_separation >= 0.0f;
 }
 
 struct RawContact {  // ContactData + output of write_contact
@@ -506,16 +595,20 @@ struct CollideResult {
 // compute_shape_aabbs + explicit broad phase + primitive narrow phase.  Candidate pairs are visited in
 // shape_contact_pairs order (the reference CPU device visits them in (t mod 256, t div 256) order, which only
 // permutes slots; compare under the deterministic sort key).
-inline void collide_primitives(const nb2_model_desc& m, const float* body_q, CollideResult& res) {
+inline void collide_primitives(const nb2_model_desc& m, const float* body_q, CollideResult& res,
+                               const SpeculativeParams& sp = SpeculativeParams()) {
     std::vector<ShapeGeom> geom;
     compute_shape_aabbs(m, body_q, geom);
+    if (sp.active) compute_shape_velocities(m, body_q, sp, geom);
     res.contacts.clear();
     res.gjk_pairs.clear();
     res.candidate_count = 0;
     for (int t = 0; t < m.shape_pair_count; ++t) {
         int s1 = m.shape_contact_pairs[2 * t + 0], s2 = m.shape_contact_pairs[2 * t + 1];
         // is_shape_pair_immovable_filtered: include_static_kinematic_pairs defaults to True -> never filtered
-        if (!check_aabb_overlap(geom[s1].aabb_lower, geom[s1].aabb_upper, geom[s2].aabb_lower, geom[s2].aabb_upper)) continue;
+        if (sp.active ? !check_aabb_overlap_moving(geom[s1], geom[s2])
+                      : !check_aabb_overlap(geom[s1].aabb_lower, geom[s1].aabb_upper, geom[s2].aabb_lower, geom[s2].aabb_upper))
+            continue;
         res.candidate_count += 1;
         int shape_a = s1, shape_b = s2;
         if (shape_a == shape_b || shape_a < 0 || shape_b < 0) continue;
@@ -525,7 +618,10 @@ inline void collide_primitives(const nb2_model_desc& m, const float* body_q, Col
         const ShapeGeom& A = geom[shape_a];
         const ShapeGeom& B = geom[shape_b];
         float margin_offset_a = A.margin, margin_offset_b = B.margin;
-        float gap_sum = m.shape_gap[shape_a] + m.shape_gap[shape_b];
+        // the kernel's shape_gap argument is the velocity-extended search gap when speculation is active (collide.py:1832, 2010);
+        // the admission test below uses the authored gaps (writer_data.shape_gap, narrow_phase.py:885-888)
+        const float base_gap_sum = m.shape_gap[shape_a] + m.shape_gap[shape_b];
+        float gap_sum = sp.active ? A.search_gap + B.search_gap : base_gap_sum;
         float radius_eff_a = 0.f, radius_eff_b = 0.f;
         if (type_a == GEO_SPHERE || type_a == GEO_CAPSULE) radius_eff_a = A.scale.x;
         if (type_b == GEO_SPHERE || type_b == GEO_CAPSULE) radius_eff_b = B.scale.x;
@@ -540,7 +636,11 @@ inline void collide_primitives(const nb2_model_desc& m, const float* body_q, Col
             vec3 nn = normalize(normal);
             for (int i = 0; i < 4; ++i) {
                 if (!(dist[i] < MAXVAL)) continue;
-                if (!gap_check_precomputed(pos[i], dist[i], radius_eff_a, radius_eff_b, nn, total_separation_needed, gap_sum))
+                if (sp.enabled) {
+                    if (!speculative_admit(A, B, pos[i], normal, dist[i], radius_eff_a, radius_eff_b, margin_offset_a, margin_offset_b,
+                                           base_gap_sum, sp))
+                        continue;
+                } else if (!gap_check_precomputed(pos[i], dist[i], radius_eff_a, radius_eff_b, nn, total_separation_needed, gap_sum))
                     continue;
                 RawContact rc;
                 write_contact(m, body_q, shape_a, shape_b, pos[i], normal, dist[i], radius_eff_a, radius_eff_b,

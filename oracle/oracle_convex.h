@@ -935,10 +935,18 @@ struct ContactOut {  // what write_contact receives: centre, normal A->B, signed
     vec3 center, normal;
     float distance;
 };
+// write_contact_speculative (sim/collide.py:257-280): the writer admits a contact that is present now (separation <= the AUTHORED
+// pair gap) or predicted within the collision-update horizon (contact_data.py:187-233)
+struct SpeculativeWriter {
+    bool enabled = false;
+    float base_gap_sum = 0.f, dt = 0.f, max_extension = 0.f;
+    vec3 origin_a, origin_b, linear_velocity_a, linear_velocity_b, angular_velocity_a, angular_velocity_b;
+};
 struct PairCtx {
     float radius_eff_a = 0.f, radius_eff_b = 0.f, margin_a = 0.f, margin_b = 0.f, gap_sum = 0.f;
     ContactOut out[5];
     int count = 0;
+    SpeculativeWriter spec;
 };
 
 inline bool is_discrete_shape(int t) { return t == T_BOX || t == T_CONVEX_MESH || t == T_PLANE; }  // collision_core.py:40-48 (triangles n/a)
@@ -1005,7 +1013,16 @@ inline void post_process_and_write(PairCtx& ctx, vec3 contact_point_center, vec3
     vec3 a_w = contact_point_center - n * (0.5f * contact_distance + ctx.radius_eff_a);
     vec3 b_w = contact_point_center + n * (0.5f * contact_distance + ctx.radius_eff_b);
     float d = dot(b_w - a_w, n) - total_separation_needed;
-    if (d > ctx.gap_sum) return;
+    if (ctx.spec.enabled) {
+        const SpeculativeWriter& w = ctx.spec;
+        if (!(d <= w.base_gap_sum)) {
+            vec3 velocity_a = w.linear_velocity_a + cross(w.angular_velocity_a, a_w - w.origin_a);
+            vec3 velocity_b = w.linear_velocity_b + cross(w.angular_velocity_b, b_w - w.origin_b);
+            float approach_speed = maxf(-dot(velocity_b - velocity_a, n), 0.0f);
+            float extension = minf(approach_speed * w.dt, w.max_extension);
+            if (!(extension - d >= 0.0f)) return;
+        }
+    } else if (d > ctx.gap_sum) return;
     ContactOut& o = ctx.out[ctx.count++];
     o.center = contact_point_center;
     o.normal = contact_normal_a_to_b;
@@ -1196,7 +1213,8 @@ struct HullRef {  // model.shape_source (unscaled hull vertices) + model.shape_c
 // (collision_core.py:700-790).  `scale_*` are the MODEL's shape scales; finite planes are halved like geom_data.
 inline int gjk_mpr_pair(int type_a, vec3 scale_a, const transform& X_a, float margin_a, vec3 aabb_lo_a, vec3 aabb_hi_a, int type_b, vec3 scale_b,
                         const transform& X_b, float margin_b, vec3 aabb_lo_b, vec3 aabb_hi_b, float gap_sum, ContactOut* out,
-                        float& radius_eff_a, float& radius_eff_b, const HullRef& hull_a = HullRef(), const HullRef& hull_b = HullRef()) {
+                        float& radius_eff_a, float& radius_eff_b, const HullRef& hull_a = HullRef(), const HullRef& hull_b = HullRef(),
+                        const SpeculativeWriter* spec = nullptr) {
     GenericShapeData shape_data_a, shape_data_b;
     shape_data_a.shape_type = type_a;
     shape_data_b.shape_type = type_b;
@@ -1230,6 +1248,9 @@ inline int gjk_mpr_pair(int type_a, vec3 scale_a, const transform& X_a, float ma
         quat plane_quat = is_infinite_plane_a ? quat_a : quat_b;
         vec3 other_center = is_infinite_plane_a ? bsphere_center_b : bsphere_center_a;
         float other_radius = is_infinite_plane_a ? bsphere_radius_b : bsphere_radius_a;
+        // speculative + external AABBs (narrow_phase.py:1170-1175): the AABBs describe the current geometry, so the pair's search
+        // extension (here gap_sum = the velocity-extended gaps) is added to the non-plane shape's overlap radius
+        if (spec && spec->enabled) other_radius += gap_sum;
         vec3 plane_normal = quat_rotate(plane_quat, vec3(0.f, 0.f, 1.f));
         float center_dist = dot(other_center - plane_pos, plane_normal);
         if (!(center_dist <= other_radius)) return 0;
@@ -1251,6 +1272,7 @@ inline int gjk_mpr_pair(int type_a, vec3 scale_a, const transform& X_a, float ma
     if (is_infinite_plane_a) pos_a_adjusted = to_cube(shape_data_a, quat_a, pos_a, pos_b, bsphere_radius_b + gap_sum);
     if (is_infinite_plane_b) pos_b_adjusted = to_cube(shape_data_b, quat_b, pos_b, pos_a, bsphere_radius_a + gap_sum);
     PairCtx ctx;
+    if (spec) ctx.spec = *spec;
     compute_gjk_mpr_contacts(ctx, shape_data_a, shape_data_b, quat_a, quat_b, pos_a_adjusted, pos_b_adjusted, gap_sum, margin_a, margin_b);
     for (int i = 0; i < ctx.count; ++i) out[i] = ctx.out[i];
     radius_eff_a = ctx.radius_eff_a;

@@ -105,6 +105,23 @@ inline float joint_force(float q, float qd, float target_q, float target_qd, flo
     float passive_f = -damping * qd;
     return limit_f + damping_f + target_f + passive_f;
 }
+// sim/articulation.py:37-82 transform_2d_rotational_axes / compute_2d_rotational_dofs: the two axes are orthonormalised through
+// q_off = quat_from_matrix([axis_0 axis_1 axis_0 x axis_1]); axis 1 is carried through the rotation about axis 0.
+inline void transform_2d_rotational_axes(vec3 axis_0, vec3 axis_1, float q0, vec3& a0, vec3& a1) {
+    quat q_off = quat_from_matrix(matrix_from_cols(axis_0, axis_1, cross(axis_0, axis_1)));
+    vec3 local_0 = quat_rotate(q_off, vec3(1.f, 0.f, 0.f));
+    vec3 local_1 = quat_rotate(q_off, vec3(0.f, 1.f, 0.f));
+    a0 = local_0;
+    quat q_0 = quat_from_axis_angle(a0, q0);
+    a1 = quat_rotate(q_0, local_1);
+}
+inline void compute_2d_rotational_dofs(vec3 axis_0, vec3 axis_1, float q0, float q1, float qd0, float qd1, quat& rot, vec3& vel) {
+    vec3 a0, a1;
+    transform_2d_rotational_axes(axis_0, axis_1, q0, a0, a1);
+    quat q_0 = quat_from_axis_angle(a0, q0), q_1 = quat_from_axis_angle(a1, q1);
+    rot = q_1 * q_0;
+    vel = a0 * qd0 + a1 * qd1;
+}
 // sim/articulation.py transform_3d_rotational_axes / compute_3d_rotational_dofs
 inline void transform_3d_rotational_axes(vec3 a0, vec3 a1, vec3 a2, float q0, float q1, vec3& o0, vec3& o1, vec3& o2) {
     quat q_0 = quat_from_axis_angle(a0, q0);
@@ -147,6 +164,11 @@ inline transform jcalc_transform(const nb2_model_desc& m, int type, int axis_sta
             if (lin > k) pos += load3(m.joint_axis + 3 * (axis_start + k)) * joint_q[q_start + k];
         int ia = axis_start + lin, iq = q_start + lin;
         if (ang == 1) rot = quat_from_axis_angle(load3(m.joint_axis + 3 * ia), joint_q[iq]);
+        if (ang == 2) {
+            vec3 vel;
+            compute_2d_rotational_dofs(load3(m.joint_axis + 3 * ia), load3(m.joint_axis + 3 * (ia + 1)), joint_q[iq], joint_q[iq + 1], 0.f, 0.f, rot,
+                                       vel);
+        }
         if (ang == 3) {
             vec3 vel;
             compute_3d_rotational_dofs(load3(m.joint_axis + 3 * ia), load3(m.joint_axis + 3 * (ia + 1)), load3(m.joint_axis + 3 * (ia + 2)),
@@ -188,6 +210,16 @@ inline void jcalc_motion(const nb2_model_desc& m, int type, const float* joint_q
             sv6 S = transform_twist(X_sc, sv6(vec3(), axis(iqd)));
             v_j_s = v_j_s + S * joint_qd[iqd];
             S.store(joint_S_s + 6 * iqd);
+        }
+        if (ang == 2) {  // kernels.py:301-311
+            vec3 a0, a1;
+            transform_2d_rotational_axes(axis(iqd), axis(iqd + 1), joint_q[iq], a0, a1);
+            sv6 S0 = transform_twist(X_sc, sv6(vec3(), a0)), S1 = transform_twist(X_sc, sv6(vec3(), a1));
+            float qd0 = joint_qd[iqd], qd1 = joint_qd[iqd + 1];
+            v_j_s = v_j_s + (S0 * qd0 + S1 * qd1);
+            S0.store(joint_S_s + 6 * iqd);
+            S1.store(joint_S_s + 6 * (iqd + 1));
+            c_app_ang += cross(a0, a1) * (qd0 * qd1);
         }
         if (ang == 3) {
             vec3 a0, a1, a2;
@@ -636,6 +668,10 @@ inline void featherstone_step(FsScratch& s, const nb2_model_desc& m, const nb2_f
                     if (lin > k) vj_lin += axis(qds + k) * jqd[qds + k];
                 int iq = qs + lin, iqd = qds + lin;
                 if (ang == 1) vj_ang = jqd[iqd] * axis(iqd);
+                if (ang == 2) {
+                    quat rot;
+                    compute_2d_rotational_dofs(axis(iqd), axis(iqd + 1), jq[iq], jq[iq + 1], jqd[iqd], jqd[iqd + 1], rot, vj_ang);
+                }
                 if (ang == 3) {
                     quat rot;
                     compute_3d_rotational_dofs(axis(iqd), axis(iqd + 1), axis(iqd + 2), jq[iq], jq[iq + 1], jq[iq + 2], jqd[iqd], jqd[iqd + 1],
@@ -725,6 +761,10 @@ inline void eval_articulation_fk(const nb2_model_desc& m, const float* joint_q, 
                     if (lin > k) vj_lin += axis(qds + k) * joint_qd[qds + k];
                 int iq = qs + lin, iqd = qds + lin;
                 if (ang == 1) vj_ang = joint_qd[iqd] * axis(iqd);
+                if (ang == 2) {
+                    quat rot;
+                    compute_2d_rotational_dofs(axis(iqd), axis(iqd + 1), joint_q[iq], joint_q[iq + 1], joint_qd[iqd], joint_qd[iqd + 1], rot, vj_ang);
+                }
                 if (ang == 3) {
                     quat rot;
                     compute_3d_rotational_dofs(axis(iqd), axis(iqd + 1), axis(iqd + 2), joint_q[iq], joint_q[iq + 1], joint_q[iq + 2],

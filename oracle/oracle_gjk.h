@@ -24,12 +24,13 @@ inline nb2::Xf to_nb2(const transform& t) { return nb2::Xf(to_nb2(t.p), nb2::Q4(
 inline int convex_pair(int type_a, vec3 scale_a, const transform& Xa, float margin_a, int type_b, vec3 scale_b, const transform& Xb,
                        float margin_b, float gap_sum, float* dist, vec3* pos, vec3* normal, float& reff_a, float& reff_b,
                        vec3 lo_a = vec3(), vec3 hi_a = vec3(), vec3 lo_b = vec3(), vec3 hi_b = vec3(), int impl = 0,
-                       const cvx::HullRef& hull_a = cvx::HullRef(), const cvx::HullRef& hull_b = cvx::HullRef()) {
+                       const cvx::HullRef& hull_a = cvx::HullRef(), const cvx::HullRef& hull_b = cvx::HullRef(),
+                       const cvx::SpeculativeWriter* spec = nullptr) {
     reff_a = reff_b = 0.0f;
     if (impl == 0) {
         cvx::ContactOut out[5];
         int cnt = cvx::gjk_mpr_pair(type_a, scale_a, Xa, margin_a, lo_a, hi_a, type_b, scale_b, Xb, margin_b, lo_b, hi_b, gap_sum, out, reff_a, reff_b,
-                                    hull_a, hull_b);
+                                    hull_a, hull_b, spec);
         for (int i = 0; i < cnt; ++i) {
             dist[i] = out[i].distance;
             pos[i] = out[i].center;
@@ -75,22 +76,39 @@ inline cvx::HullRef hull_ref(const nb2_model_desc& m, int shape) {
 }
 
 // The GJK/MPR kernel pass over the pairs the primitive kernel forwarded (narrow_phase.py:1041-1216).
-inline void gjk_mpr_pairs(const nb2_model_desc& m, const float* body_q, CollideResult& res) {
+inline void gjk_mpr_pairs(const nb2_model_desc& m, const float* body_q, CollideResult& res,
+                          const SpeculativeParams& sp = SpeculativeParams()) {
     if (res.gjk_pairs.empty()) return;
     std::vector<ShapeGeom> geom;
     compute_shape_aabbs(m, body_q, geom);
+    if (sp.active) compute_shape_velocities(m, body_q, sp, geom);
     for (auto& pr : res.gjk_pairs) {
         const int shape_a = pr.first, shape_b = pr.second;
         const ShapeGeom& A = geom[shape_a];
         const ShapeGeom& B = geom[shape_b];
         float dist[5], ra, rb;
         vec3 pos[5], normal[5];
-        const float gap_sum = m.shape_gap[shape_a] + m.shape_gap[shape_b];
+        const float base_gap_sum = m.shape_gap[shape_a] + m.shape_gap[shape_b];
+        // speculative: the kernel sees the velocity-extended search gaps (collide.py:1832, 2010), the writer the authored ones
+        const float gap_sum = sp.active ? A.search_gap + B.search_gap : base_gap_sum;
+        cvx::SpeculativeWriter w;
+        if (sp.enabled) {
+            w.enabled = true;
+            w.base_gap_sum = base_gap_sum;
+            w.dt = sp.dt;
+            w.max_extension = sp.max_extension;
+            w.origin_a = A.X_ws.p;
+            w.origin_b = B.X_ws.p;
+            w.linear_velocity_a = A.linear_velocity;
+            w.linear_velocity_b = B.linear_velocity;
+            w.angular_velocity_a = A.angular_velocity;
+            w.angular_velocity_b = B.angular_velocity;
+        }
         // raw model scales: convex_contacts_any applies the geom_data halving of finite planes itself
         int cnt = convex_pair(m.shape_type[shape_a], load3(m.shape_scale + 3 * shape_a), A.X_ws, A.margin, m.shape_type[shape_b],
                               load3(m.shape_scale + 3 * shape_b), B.X_ws, B.margin, gap_sum,
                               dist, pos, normal, ra, rb, A.aabb_lower, A.aabb_upper, B.aabb_lower, B.aabb_upper, 0, hull_ref(m, shape_a),
-                              hull_ref(m, shape_b));
+                              hull_ref(m, shape_b), sp.enabled ? &w : nullptr);
         for (int i = 0; i < cnt; ++i) {
             RawContact rc;
             // emission order == sort_sub_key order; dropped manifold points only leave holes in the sub-key sequence

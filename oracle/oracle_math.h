@@ -159,6 +159,49 @@ inline mat33 quat_to_matrix(quat q) {
     return mat33(c1.x, c2.x, c3.x, c1.y, c2.y, c3.y, c1.z, c2.z, c3.z);
 }
 
+// wp.matrix_from_cols / wp.quat_from_matrix (warp/native/mat.h, quat.h): trace branch, else the largest diagonal element;
+// the result is normalized.  Used by the two-angular-axis D6 joint (sim/articulation.py:37-58).
+inline mat33 matrix_from_cols(vec3 c0, vec3 c1, vec3 c2) { return mat33(c0.x, c1.x, c2.x, c0.y, c1.y, c2.y, c0.z, c1.z, c2.z); }
+inline quat quat_from_matrix(const mat33& a) {
+    const float tr = a.m[0][0] + a.m[1][1] + a.m[2][2];
+    float x, y, z, w, h;
+    if (tr >= 0.0f) {
+        h = std::sqrt(tr + 1.0f);
+        w = 0.5f * h;
+        h = 0.5f / h;
+        x = (a.m[2][1] - a.m[1][2]) * h;
+        y = (a.m[0][2] - a.m[2][0]) * h;
+        z = (a.m[1][0] - a.m[0][1]) * h;
+    } else {
+        int max_diag = 0;
+        if (a.m[1][1] > a.m[0][0]) max_diag = 1;
+        if (a.m[2][2] > a.m[max_diag][max_diag]) max_diag = 2;
+        if (max_diag == 0) {
+            h = std::sqrt((a.m[0][0] - (a.m[1][1] + a.m[2][2])) + 1.0f);
+            x = 0.5f * h;
+            h = 0.5f / h;
+            y = (a.m[0][1] + a.m[1][0]) * h;
+            z = (a.m[2][0] + a.m[0][2]) * h;
+            w = (a.m[2][1] - a.m[1][2]) * h;
+        } else if (max_diag == 1) {
+            h = std::sqrt((a.m[1][1] - (a.m[2][2] + a.m[0][0])) + 1.0f);
+            y = 0.5f * h;
+            h = 0.5f / h;
+            z = (a.m[1][2] + a.m[2][1]) * h;
+            x = (a.m[0][1] + a.m[1][0]) * h;
+            w = (a.m[0][2] - a.m[2][0]) * h;
+        } else {
+            h = std::sqrt((a.m[2][2] - (a.m[0][0] + a.m[1][1])) + 1.0f);
+            z = 0.5f * h;
+            h = 0.5f / h;
+            x = (a.m[2][0] + a.m[0][2]) * h;
+            y = (a.m[1][2] + a.m[2][1]) * h;
+            w = (a.m[1][0] - a.m[0][1]) * h;
+        }
+    }
+    return normalize(quat(x, y, z, w));
+}
+
 struct transform {
     vec3 p;
     quat q;

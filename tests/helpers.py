@@ -7,12 +7,12 @@ import torch
 
 
 def simulate(model, pipeline_cls, solver_cls, *, substeps, dt, solver_kwargs=None, collide=True, control=None,
-             record_contacts=False, solver_attrs=None, update_contacts=False):
+             record_contacts=False, solver_attrs=None, update_contacts=False, pipeline_kwargs=None, collide_dt=None):
     """`collide -> step -> swap` loop exactly as the reference examples run it (example_basic_urdf.py:117-135)."""
     solver = solver_cls(model, **(solver_kwargs or {}))
     for k, v in (solver_attrs or {}).items():
         setattr(solver, k, v)
-    pipe = pipeline_cls(model) if (collide and pipeline_cls is not None) else None
+    pipe = pipeline_cls(model, **(pipeline_kwargs or {})) if (collide and pipeline_cls is not None) else None
     s0, s1 = model.state(), model.state()
     ctrl = control if control is not None else model.control()
     contacts = pipe.contacts() if pipe is not None else None
@@ -20,7 +20,10 @@ def simulate(model, pipeline_cls, solver_cls, *, substeps, dt, solver_kwargs=Non
     for _ in range(substeps):
         s0.clear_forces()
         if pipe is not None:
-            pipe.collide(s0, contacts)
+            if collide_dt is None:
+                pipe.collide(s0, contacts)
+            else:
+                pipe.collide(s0, contacts, dt=collide_dt)
             if record_contacts:
                 counts.append(int(contacts.rigid_contact_count.item()))
         solver.step(s0, s1, ctrl, contacts, dt)
