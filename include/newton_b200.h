@@ -229,6 +229,18 @@ nb2_status nb2_collide_configure(nb2_model* model, int32_t broad_phase, int32_t 
  * deterministic (env, sort-key) order and `rigid_contact_count[0]` is set. */
 nb2_status nb2_collide(nb2_model* model, const float* body_q, const nb2_contacts_view* contacts, void* cuda_stream);
 
+/* Reference CollisionPipeline(speculative_config=SpeculativeContactConfig(max_speculative_extension)).collide(state, contacts, dt=dt)
+ * (sim/collide.py:257-280 write_contact_speculative, :475-541 compute_shape_velocities, :1076-1102, :1823-1962;
+ * geometry/contact_data.py:92-233; broad_phase_common.py:41-80; broad_phase_sap.py:44-78; narrow_phase.py:241-246, 885-888).
+ * Same outputs as nb2_collide; in addition a contact is admitted when the two surface points are predicted to close within `dt`
+ * (closing speed along the normal x dt, capped at `max_speculative_extension`, >= the current separation).  With dt > 0 and an
+ * extension > 0 every broad phase tests the AABBs swept over the shapes' relative displacement (grown by the angular travel), and
+ * the colliders see per-shape gaps extended by min((|v_origin| + |w| r) dt, max_speculative_extension); the stored contact
+ * geometry (points, offsets, margins) stays the physical one.  `body_qd` is State.body_qd (COM twists).  dt == 0 or an extension of
+ * 0 keeps the speculative writer's admission rule only, like the reference.  Needs model.shape_collision_aabb_lower/_upper. */
+nb2_status nb2_collide_speculative(nb2_model* model, const float* body_q, const float* body_qd, float dt, float max_speculative_extension,
+                                   const nb2_contacts_view* contacts, void* cuda_stream);
+
 /* Reference CollisionPipeline(deterministic=True): ContactSorter.sort_full by make_contact_sort_key (sim/collide.py:2054-2073,
  * geometry/contact_sort.py, contact_data.py:59-87).  nb2_collide exports contacts in (world, sort key) order; this call
  * reorders the exported arrays of the SAME `contacts` buffer into the reference's global key order (stable radix sort on

@@ -18,7 +18,7 @@ STATUS = {0: "NB2_OK", 1: "NB2_ERR_INVALID_ARGUMENT", 2: "NB2_ERR_UNSUPPORTED", 
 
 # every symbol include/newton_b200.h declares
 EXPORTED_SYMBOLS = (
-    "nb2_model_create", "nb2_model_destroy", "nb2_model_notify_changed", "nb2_model_rigid_contact_max", "nb2_collide_configure", "nb2_collide", "nb2_contacts_match", "nb2_contacts_sort", "nb2_contacts_import",
+    "nb2_model_create", "nb2_model_destroy", "nb2_model_notify_changed", "nb2_model_rigid_contact_max", "nb2_collide_configure", "nb2_collide", "nb2_collide_speculative", "nb2_contacts_match", "nb2_contacts_sort", "nb2_contacts_import",
     "nb2_xpbd_step", "nb2_xpbd_update_contacts", "nb2_integrate_bodies", "nb2_featherstone_step", "nb2_eval_fk", "nb2_eval_ik", "nb2_eval_fk_masked",
     "nb2_view_gather", "nb2_view_scatter", "nb2_view_articulation_mask", "nb2_last_error", "nb2_kernel_launch_count", "nb2_version",
     "nb2_peer_gather_handle_bytes", "nb2_peer_gather_create", "nb2_peer_gather_buffer", "nb2_peer_gather_stride", "nb2_peer_gather_export",
@@ -53,6 +53,8 @@ def lib():
         L.nb2_collide_configure.restype = C.c_int
         L.nb2_collide.argtypes = [P, P, C.POINTER(_abi.ContactsView), P]
         L.nb2_collide.restype = C.c_int
+        L.nb2_collide_speculative.argtypes = [P, P, P, C.c_float, C.c_float, C.POINTER(_abi.ContactsView), P]
+        L.nb2_collide_speculative.restype = C.c_int
         L.nb2_contacts_match.argtypes = [P, P, C.POINTER(_abi.ContactsView), P, C.POINTER(_abi.MatchOptions), P]
         L.nb2_contacts_match.restype = C.c_int
         L.nb2_contacts_sort.argtypes = [P, C.POINTER(_abi.ContactsView), P]

@@ -11,6 +11,8 @@
 #include <cstring>
 #include <mutex>
 
+#include <cmath>
+
 #include "nb2_internal.cuh"
 
 namespace nb2 {
@@ -664,8 +666,39 @@ nb2_status nb2_collide(nb2_model* model, const float* body_q, const nb2_contacts
     }
     model->dev.export_rank = nullptr;  // a fresh export is in (world, key) order until nb2_contacts_sort runs
     model->contacts_imported = false;
+    model->dev.spec_mode = 0;
+    model->dev.spec_body_qd = nullptr;
+    model->dev.spec_dt = model->dev.spec_max_ext = 0.0f;
     DeviceGuard guard(model->device);
     return launch_collide(model, body_q, contacts, static_cast<cudaStream_t>(cuda_stream));
+}
+
+nb2_status nb2_collide_speculative(nb2_model* model, const float* body_q, const float* body_qd, float dt, float max_speculative_extension,
+                                   const nb2_contacts_view* contacts, void* cuda_stream) {
+    if (!model || ((!body_q || !body_qd) && model->dev.d.body_count > 0)) {
+        set_error("nb2_collide_speculative: NULL argument");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    if (!(dt >= 0.0f) || !(max_speculative_extension >= 0.0f) || std::isinf(dt) || std::isinf(max_speculative_extension)) {
+        set_error("nb2_collide_speculative: dt and max_speculative_extension must be non-negative finite numbers");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    if (!model->dev.d.shape_collision_aabb_lower || !model->dev.d.shape_collision_aabb_upper || !model->dev.d.body_com) {
+        set_error("nb2_collide_speculative: model.shape_collision_aabb_lower / _upper / body_com are required");
+        return NB2_ERR_INVALID_ARGUMENT;
+    }
+    model->dev.export_rank = nullptr;
+    model->contacts_imported = false;
+    // speculative_active (sim/collide.py:1831): without a horizon or an extension only the writer's admission rule differs
+    model->dev.spec_mode = (dt > 0.0f && max_speculative_extension > 0.0f) ? 2 : 1;
+    model->dev.spec_body_qd = body_qd;
+    model->dev.spec_dt = dt;
+    model->dev.spec_max_ext = max_speculative_extension;
+    DeviceGuard guard(model->device);
+    const nb2_status st = launch_collide(model, body_q, contacts, static_cast<cudaStream_t>(cuda_stream));
+    model->dev.spec_mode = 0;
+    model->dev.spec_body_qd = nullptr;
+    return st;
 }
 
 nb2_status nb2_contacts_sort(nb2_model* model, const nb2_contacts_view* c, void* cuda_stream) {

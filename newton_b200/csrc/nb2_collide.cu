@@ -285,6 +285,70 @@ NB2_DEV void shape_aabb(int type, V3 scale, const Xf& X, float gap_eff, float co
     hi = pos + he + mvv;
 }
 
+// compute_shape_velocities (sim/collide.py:475-541) for one shape whose world transform X_ws is known: shape-origin velocity,
+// angular velocity, velocity-extended search gap, displacement over the collision-update interval; the AABB grows by the (capped)
+// angular travel.  Static shapes (body -1) keep zero motion and their authored gap.
+struct ShapeMotion {
+    V3 lin, ang, disp;
+    float search_gap;
+};
+NB2_DEV ShapeMotion shape_motion(const DevModel& M, const float* __restrict__ body_q, int sid, int body, const Xf& X_ws, V3& lo, V3& hi) {
+    const nb2_model_desc& d = M.d;
+    ShapeMotion o;
+    o.search_gap = d.shape_gap[sid];
+    if (body == -1) return o;
+    const Xf X_wb = ldx(body_q + 7 * body);
+    const V3 com_world = xpoint(X_wb, ld3(d.body_com + 3 * body));
+    const V3 com_velocity = ld3(M.spec_body_qd + 6 * body), angular_velocity = ld3(M.spec_body_qd + 6 * body + 3);
+    const V3 origin_velocity = com_velocity + cross(angular_velocity, X_ws.p - com_world);
+    o.lin = origin_velocity;
+    o.ang = angular_velocity;
+    const V3 furthest = vmax(vabs(ld3(d.shape_collision_aabb_lower + 3 * sid)), vabs(ld3(d.shape_collision_aabb_upper + 3 * sid)));
+    const float angular_radius = fmax_w(len(furthest), d.shape_collision_radius[sid]);
+    const float angular_speed_bound = len(angular_velocity) * angular_radius;
+    const float search_extension = fmin_w((len(origin_velocity) + angular_speed_bound) * M.spec_dt, M.spec_max_ext);
+    o.search_gap = d.shape_gap[sid] + search_extension;
+    o.disp = origin_velocity * M.spec_dt;
+    const float ae = fmin_w(angular_speed_bound * M.spec_dt, M.spec_max_ext);
+    lo = lo - V3(ae, ae, ae);
+    hi = hi + V3(ae, ae, ae);
+    return o;
+}
+// check_aabb_overlap_moving (broad_phase_common.py:41-80, cutoffs 0): box 1 swept by the RELATIVE displacement against box 2
+NB2_DEV bool aabb_overlap_moving(V3 lo1, V3 hi1, V3 lo2, V3 hi2, V3 rel) {
+    float enter = 0.0f, exit_time = 1.0f;
+#pragma unroll
+    for (int axis = 0; axis < 3; ++axis) {
+        const float lower1 = lo1.get(axis), upper1 = hi1.get(axis), lower2 = lo2.get(axis), upper2 = hi2.get(axis), delta = rel.get(axis);
+        if (delta == 0.0f) {
+            if (lower1 > upper2 || upper1 < lower2) return false;
+        } else {
+            float axis_enter = (lower2 - upper1) / delta, axis_exit = (upper2 - lower1) / delta;
+            if (axis_enter > axis_exit) {
+                const float t = axis_enter;
+                axis_enter = axis_exit;
+                axis_exit = t;
+            }
+            enter = fmax_w(enter, axis_enter);
+            exit_time = fmin_w(exit_time, axis_exit);
+            if (enter > exit_time) return false;
+        }
+    }
+    return true;
+}
+// prepare_speculative_contact + contact_passes_speculative_gap_check (contact_data.py:187-233)
+NB2_DEV bool speculative_admit(const ShapeMotion& ma, V3 origin_a, const ShapeMotion& mb, V3 origin_b, V3 center, V3 nn, float dist, float reff_a,
+                               float reff_b, float total_sep, float base_gap_sum, float dt, float max_ext) {
+    const V3 a_w = center - nn * (0.5f * dist + reff_a);
+    const V3 b_w = center + nn * (0.5f * dist + reff_b);
+    const float separation = dot(b_w - a_w, nn) - total_sep;
+    if (separation <= base_gap_sum) return true;
+    const V3 va = ma.lin + cross(ma.ang, a_w - origin_a), vb = mb.lin + cross(mb.ang, b_w - origin_b);
+    const float approach = fmax_w(-dot(vb - va, nn), 0.0f);
+    const float extension = fmin_w(approach * dt, max_ext);
+    return extension - separation >= 0.0f;
+}
+
 struct PairGeom {
     int type;
     V3 scale;
@@ -298,6 +362,19 @@ struct __align__(4) SlotRec {
     float lo[3];
     float hi[3];
 };
+
+// Speculative contacts only (DevModel::spec_mode != 0): per-slot motion record next to the SlotRec table
+struct __align__(4) SlotMotionRec {
+    float lin[3], ang[3], disp[3], search_gap;
+};
+NB2_DEV ShapeMotion ld_motion(const SlotMotionRec& r) {
+    ShapeMotion o;
+    o.lin = ld3(r.lin);
+    o.ang = ld3(r.ang);
+    o.disp = ld3(r.disp);
+    o.search_gap = r.search_gap;
+    return o;
+}
 
 // CONVEX = false is instantiated for models none of whose pairs can reach the generic convex path (decided per pair type at
 // nb2_model_create): the analytic-only kernel carries neither the MPR / GJK / manifold code nor its registers and stack.
@@ -333,6 +410,12 @@ __global__ void __launch_bounds__(32 * WARPS) collide_kernel(DevModel M, const f
     const bool live = env < M.env_count;
     SlotRec* slots = reinterpret_cast<SlotRec*>(smem_raw) + size_t(warp * G + grp) * M.max_env_slots_shapes;
     const nb2_model_desc& d = M.d;
+    // speculative contacts run in the generic instantiation only (launch_collide picks CONVEX = true for them)
+    const int spec_mode = CONVEX ? M.spec_mode : 0;
+    SlotMotionRec* motion = nullptr;
+    if (CONVEX && spec_mode != 0)
+        motion = reinterpret_cast<SlotMotionRec*>(reinterpret_cast<SlotRec*>(smem_raw) + size_t(WARPS * G) * M.max_env_slots_shapes) +
+                 size_t(warp * G + grp) * M.max_env_slots_shapes;
 
     int ss = 0, nloc = 0, nslots = 0, bs = 0, ps = 0, np = 0, slot0 = 0;
     if (live) {
@@ -364,6 +447,15 @@ __global__ void __launch_bounds__(32 * WARPS) collide_kernel(DevModel M, const f
             lhi = ld3(d.shape_collision_aabb_upper + 3 * sid);
         }
         shape_aabb(stype, ld3(d.shape_scale + 3 * sid), X, margin + d.shape_gap[sid], d.shape_collision_radius[sid], llo, lhi, lo, hi);
+        if (CONVEX && motion) {
+            ShapeMotion mo;
+            mo.search_gap = d.shape_gap[sid];
+            if (spec_mode == 2) mo = shape_motion(M, body_q, sid, body, X, lo, hi);
+            st3(motion[s].lin, mo.lin);
+            st3(motion[s].ang, mo.ang);
+            st3(motion[s].disp, mo.disp);
+            motion[s].search_gap = mo.search_gap;
+        }
         stx(slots[s].x, X);
         st3(slots[s].lo, lo);
         st3(slots[s].hi, hi);
@@ -387,6 +479,8 @@ __global__ void __launch_bounds__(32 * WARPS) collide_kernel(DevModel M, const f
             int2 pr = M.dyn_pairs ? M.dyn_pairs[ps + p] : M.pairs[ps + p];
             V3 alo = ld3(slots[pr.x].lo), ahi = ld3(slots[pr.x].hi), blo = ld3(slots[pr.y].lo), bhi = ld3(slots[pr.y].hi);
             bool overlap = alo.x <= bhi.x && ahi.x >= blo.x && alo.y <= bhi.y && ahi.y >= blo.y && alo.z <= bhi.z && ahi.z >= blo.z;
+            if (CONVEX && spec_mode == 2)  // swept test over the relative displacement (the explicit sweep passes (s1, s2) = the stored pair)
+                overlap = aabb_overlap_moving(alo, ahi, blo, bhi, ld3(motion[pr.x].disp) - ld3(motion[pr.y].disp));
             if (overlap && !M.include_static_kinematic_pairs && !M.dyn_pairs) {
                 // is_shape_pair_immovable_filtered (broad_phase_common.py:166-201) in the explicit sweep (broad_phase_nxn.py:29-69)
                 const int s1 = pr.x < nloc ? ss + pr.x : M.global_shapes[pr.x - nloc], s2 = pr.y < nloc ? ss + pr.y : M.global_shapes[pr.y - nloc];
@@ -402,7 +496,9 @@ __global__ void __launch_bounds__(32 * WARPS) collide_kernel(DevModel M, const f
                 Xf Xa = ldx(slots[pr.x].x), Xb = ldx(slots[pr.y].x);
                 marg_a = d.shape_margin[sa];
                 marg_b = d.shape_margin[sb];
-                const float gap_sum = d.shape_gap[sa] + d.shape_gap[sb];
+                // speculative: the colliders see the velocity-extended search gaps, the admission test the authored ones
+                const float base_gap_sum = d.shape_gap[sa] + d.shape_gap[sb];
+                const float gap_sum = (CONVEX && spec_mode == 2) ? motion[pr.x].search_gap + motion[pr.y].search_gap : base_gap_sum;
                 const bool early_gjk = ta >= GEO_ELLIPSOID || tb == GEO_CONE || (ta == GEO_CAPSULE && tb > GEO_CAPSULE);
                 bool analytic = false;
                 float dist[4] = {NB2_MAXVAL, NB2_MAXVAL, NB2_MAXVAL, NB2_MAXVAL};
@@ -465,6 +561,12 @@ __global__ void __launch_bounds__(32 * WARPS) collide_kernel(DevModel M, const f
                         cnorm[i] = normal;
                         if (dist[i] < NB2_MAXVAL) {
                             // _contact_passes_gap_check_precomputed (contact_data.py:138-156)
+                            if (CONVEX && spec_mode != 0) {
+                                if (speculative_admit(ld_motion(motion[pr.x]), Xa.p, ld_motion(motion[pr.y]), Xb.p, pos[i], nn, dist[i], reff_a, reff_b,
+                                                      tsn, base_gap_sum, M.spec_dt, M.spec_max_ext))
+                                    vmask |= 1u << i;
+                                continue;
+                            }
                             V3 a_w = pos[i] - nn * (0.5f * dist[i] + reff_a);
                             V3 b_w = pos[i] + nn * (0.5f * dist[i] + reff_b);
                             float dd = dot(b_w - a_w, nn) - tsn;
@@ -474,6 +576,21 @@ __global__ void __launch_bounds__(32 * WARPS) collide_kernel(DevModel M, const f
                 } else if (CONVEX) {
                     ConvexShape A{ta, sca, Xa, marg_a, d.shape_gap[sa], alo, ahi};
                     ConvexShape Bc{tb, scb, Xb, marg_b, d.shape_gap[sb], blo, bhi};
+                    ConvexSpec cs;
+                    if (spec_mode != 0) {
+                        const ShapeMotion ma = ld_motion(motion[pr.x]), mb = ld_motion(motion[pr.y]);
+                        A.gap = ma.search_gap;  // == the authored gap when speculation is inactive
+                        Bc.gap = mb.search_gap;
+                        cs.base_gap_sum = base_gap_sum;
+                        cs.dt = M.spec_dt;
+                        cs.max_extension = M.spec_max_ext;
+                        cs.origin_a = Xa.p;
+                        cs.origin_b = Xb.p;
+                        cs.lin_a = ma.lin;
+                        cs.lin_b = mb.lin;
+                        cs.ang_a = ma.ang;
+                        cs.ang_b = mb.ang;
+                    }
                     if (ta == GEO_CONVEX_MESH) {  // narrow_phase.py:1096-1105
                         A.hull = d.hull_points + 3 * size_t(d.shape_hull_start[sa]);
                         A.hull_count = d.shape_hull_count[sa];
@@ -484,7 +601,7 @@ __global__ void __launch_bounds__(32 * WARPS) collide_kernel(DevModel M, const f
                         Bc.hull_count = d.shape_hull_count[sb];
                         Bc.center = 0.5f * (ld3(d.shape_collision_aabb_lower + 3 * sb) + ld3(d.shape_collision_aabb_upper + 3 * sb));
                     }
-                    vmask = convex_pair_contacts(A, Bc, cdist, cpos, cnorm, reff_a, reff_b);
+                    vmask = convex_pair_contacts(A, Bc, cdist, cpos, cnorm, reff_a, reff_b, spec_mode != 0 ? &cs : nullptr);
                 }
             }
         }
@@ -661,6 +778,8 @@ NB2_DEV bool group_pair_collides(int ga, int gb) {  // test_group_pair (broad_ph
 }
 struct __align__(8) BpSlot {
     float lo[3], hi[3];
+    float disp[3];   // speculative contacts: displacement over the collision-update interval (zero otherwise)
+    float pad;
     float plo, phi;  // projection on the SAP axis
     int shape;       // model shape id
     int info;        // bit 0 collides, bit 1 global (world -1), bit 2 immovable (static or kinematic body); group in the high bits is separate
@@ -706,13 +825,21 @@ __global__ void __launch_bounds__(32) broadphase_kernel(DevModel M, const float*
         }
         shape_aabb(stype, ld3(d.shape_scale + 3 * sid), X, d.shape_margin[sid] + d.shape_gap[sid], d.shape_collision_radius[sid], llo, lhi, lo, hi);
         BpSlot& r = slots[s];
+        V3 disp;
+        if (M.spec_mode == 2) disp = shape_motion(M, body_q, sid, body, X, lo, hi).disp;  // also grows the AABB by the angular travel
         st3(r.lo, lo);
         st3(r.hi, hi);
+        st3(r.disp, disp);
         // _sap_project_aabb (broad_phase_sap.py:44-80), AABBs pre-expanded (no extra gap)
         const V3 half = 0.5f * (hi - lo);
         const float radius = dot(vabs(axis), half), center = dot(axis, 0.5f * (lo + hi));
         r.plo = center - radius;
         r.phi = center + radius;
+        if (M.spec_mode == 2) {  // the interval also covers the displacement along the sort axis, clamped to the extension cap
+            const float pd = clamp_w(dot(axis, disp), -M.spec_max_ext, M.spec_max_ext);
+            r.plo += fmin_w(pd, 0.0f);
+            r.phi += fmax_w(pd, 0.0f);
+        }
         r.shape = sid;
         r.group = d.shape_collision_group ? d.shape_collision_group[sid] : 1;
         r.type = stype;
@@ -728,7 +855,9 @@ __global__ void __launch_bounds__(32) broadphase_kernel(DevModel M, const float*
         if ((a.info & 2) && (b.info & 2)) return;       // shared-vs-shared pairs belong to the dedicated segment (no body involved)
         if (!group_pair_collides(a.group, b.group)) return;
         if (!M.include_static_kinematic_pairs && (a.info & 4) && (b.info & 4)) return;
-        if (!(a.lo[0] <= b.hi[0] && a.hi[0] >= b.lo[0] && a.lo[1] <= b.hi[1] && a.hi[1] >= b.lo[1] && a.lo[2] <= b.hi[2] && a.hi[2] >= b.lo[2]))
+        if (M.spec_mode == 2) {  // check_aabb_overlap_moving: swept over the relative displacement (symmetric in the two shapes)
+            if (!aabb_overlap_moving(ld3(a.lo), ld3(a.hi), ld3(b.lo), ld3(b.hi), ld3(a.disp) - ld3(b.disp))) return;
+        } else if (!(a.lo[0] <= b.hi[0] && a.hi[0] >= b.lo[0] && a.lo[1] <= b.hi[1] && a.hi[1] >= b.lo[1] && a.lo[2] <= b.hi[2] && a.hi[2] >= b.lo[2]))
             return;
         const int s1 = min(a.shape, b.shape), s2 = max(a.shape, b.shape);
         if (M.filter_count > 0) {  // is_pair_excluded: binary search of the sorted exclusion list
@@ -1098,7 +1227,7 @@ static nb2_status launch_collide_W(nb2_model* m, const float* body_q, const nb2_
     const DevModel& M = m->dev;
     const int NE = (32 / L) * WARPS;
     const int blocks = (M.env_count + NE - 1) / NE;
-    const size_t smem = size_t(NE) * M.max_env_slots_shapes * sizeof(SlotRec);
+    const size_t smem = size_t(NE) * M.max_env_slots_shapes * (sizeof(SlotRec) + (CONVEX && M.spec_mode != 0 ? sizeof(SlotMotionRec) : 0));
     if (fused_out) {
         if (smem > 48 * 1024)
             NB2_CUDA_CHECK(cudaFuncSetAttribute(collide_kernel<L, CONVEX, WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -1116,7 +1245,7 @@ static nb2_status launch_collide_W(nb2_model* m, const float* body_q, const nb2_
 template <int L, bool CONVEX>
 static nb2_status launch_collide_L(nb2_model* m, const float* body_q, const nb2_contacts_view* fused_out, cudaStream_t s) {
     const DevModel& M = m->dev;
-    const size_t per_warp = size_t(32 / L) * M.max_env_slots_shapes * sizeof(SlotRec);
+    const size_t per_warp = size_t(32 / L) * M.max_env_slots_shapes * (sizeof(SlotRec) + (CONVEX && M.spec_mode != 0 ? sizeof(SlotMotionRec) : 0));
     if (per_warp > 200 * 1024) {
         set_error("collide: too many shapes per environment for the fused kernel");
         return NB2_ERR_CAPACITY;
@@ -1175,9 +1304,11 @@ nb2_status launch_collide(nb2_model* m, const float* body_q, const nb2_contacts_
     // envs, frame 690.1 vs 678.3 us L2-warm, 733.8 vs 718.0 us with L2 flushed (profiles/r2j_fused_export_ab.txt) - the 256 tiles of
     // a single-wave launch all reach the look-back at the same time and serialise on it.  So the default is the two-kernel path.
     static const bool fused = std::getenv("NB2_COLLIDE_FUSED_EXPORT") && std::atoi(std::getenv("NB2_COLLIDE_FUSED_EXPORT")) != 0;
-    const nb2_contacts_view* fused_out = (contacts && fused) ? contacts : nullptr;
+    // speculative contacts live in the generic (CONVEX = true) instantiation only, with the two-kernel export
+    const bool generic = m->has_convex_pairs || M.spec_mode != 0;
+    const nb2_contacts_view* fused_out = (contacts && fused && M.spec_mode == 0) ? contacts : nullptr;
 #define NB2_COLLIDE_DISPATCH(LANES) \
-    st = m->has_convex_pairs ? launch_collide_L<LANES, true>(m, body_q, fused_out, s) : launch_collide_L<LANES, false>(m, body_q, fused_out, s)
+    st = generic ? launch_collide_L<LANES, true>(m, body_q, fused_out, s) : launch_collide_L<LANES, false>(m, body_q, fused_out, s)
     switch (m->lanes_per_env) {
         case 8: NB2_COLLIDE_DISPATCH(8); break;
         case 16: NB2_COLLIDE_DISPATCH(16); break;

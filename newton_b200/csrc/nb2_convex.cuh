@@ -751,11 +751,20 @@ NB2_CALL void post_process_contact(V3& center, float& dist, V3 normal, float ref
     }
 }
 
+// write_contact_speculative (sim/collide.py:257-280, contact_data.py:92-233): the writer admits a contact that is present now
+// (separation <= the AUTHORED pair gap) or predicted to close within the collision-update interval.  `gap_sum` of the pair is then
+// the velocity-extended SEARCH gap (collide.py:1832, 2010).  Origins are the shapes' own world origins (geom_transform), also for
+// an infinite plane that is replaced by its box proxy.
+struct ConvexSpec {
+    float base_gap_sum, dt, max_extension;
+    V3 origin_a, origin_b, lin_a, lin_b, ang_a, ang_b;
+};
 struct ConvexPairIn {
     int type_a, type_b;
     V3 scale_a, scale_b;
     Xf Xa, Xb;
     float margin_a, margin_b, gap_sum;
+    const ConvexSpec* spec = nullptr;
     // CONVEX_MESH only: unscaled hull vertices (shape_source) and the centre of the scaled local AABB (Minkowski-centre seed)
     const float* hull_a = nullptr;
     const float* hull_b = nullptr;
@@ -806,7 +815,15 @@ NB2_DEV int convex_contacts(const ConvexPairIn& in, float* odist, V3* opos, V3* 
         const V3 a_w = center_w - nn * (0.5f * dist + reff_a);
         const V3 b_w = center_w + nn * (0.5f * dist + reff_b);
         const float dd = dot(b_w - a_w, nn) - total_sep;
-        if (dd > in.gap_sum) return;
+        if (in.spec) {
+            const ConvexSpec& w = *in.spec;
+            if (!(dd <= w.base_gap_sum)) {  // contact_passes_speculative_gap_check: predictive score >= 0
+                const V3 va = w.lin_a + cross(w.ang_a, a_w - w.origin_a), vb = w.lin_b + cross(w.ang_b, b_w - w.origin_b);
+                const float approach = fmax_w(-dot(vb - va, nn), 0.0f);
+                const float extension = fmin_w(approach * w.dt, w.max_extension);
+                if (!(extension - dd >= 0.0f)) return;
+            }
+        } else if (dd > in.gap_sum) return;
         odist[count] = dist;
         opos[count] = center_w;
         onorm[count] = normal_w;
@@ -987,7 +1004,9 @@ NB2_DEV int convex_contacts_any(ConvexPairIn in, const ConvexPairAabbs& bb, floa
         const V3 other_center = inf_a ? cb : ca;
         const float other_radius = inf_a ? rb : ra;
         const V3 n = qrot(plane.q, V3(0.f, 0.f, 1.f));
-        if (dot(other_center - plane.p, n) > other_radius) return 0;  // check_infinite_plane_bsphere_overlap
+        // check_infinite_plane_bsphere_overlap; speculative mode adds the pair's search extension to the non-plane shape's overlap
+        // radius (narrow_phase.py:1170-1175) - the proxy below is sized from the plain radius + one pair gap
+        if (dot(other_center - plane.p, n) > (in.spec ? other_radius + in.gap_sum : other_radius)) return 0;
         const V3 other_pos = inf_a ? in.Xb.p : in.Xa.p;
         const float size = (other_radius + in.gap_sum) * 10.0f;  // lateral_size == depth
         const float dist_n = dot(other_pos - plane.p, n);

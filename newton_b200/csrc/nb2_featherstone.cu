@@ -407,6 +407,7 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane / L, l = lane % L;
+    if (int(blockIdx.x) * WARPS * G >= M.env_count) return;  // padding CTA of the NB2_FS_MIN_GRID experiment (before any barrier)
     const int env = (blockIdx.x * WARPS + warp) * G + grp;
     const bool live = env < M.env_count;
     // groups run different trip counts (articulations / dofs per env), so barriers cover one group only
@@ -1093,7 +1094,8 @@ static nb2_status launch_fs_W(nb2_model* m, const nb2_featherstone_params& p, co
         NB2_CUDA_CHECK(cudaFuncSetAttribute(featherstone_step_kernel<L, PF, WARPS, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     NB2_CUDA_CHECK(cudaFuncSetAttribute(featherstone_step_kernel<L, PF, WARPS, TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     static const int phase_sync = std::getenv("NB2_FS_PHASE_SYNC") ? std::atoi(std::getenv("NB2_FS_PHASE_SYNC")) : 1;
-    featherstone_step_kernel<L, PF, WARPS, TILE><<<blocks, 32 * WARPS, smem, s>>>(M, p, in, out, ctl, use_contacts, update_mass, dt, phase_sync);
+    static const int min_grid = std::getenv("NB2_FS_MIN_GRID") ? std::atoi(std::getenv("NB2_FS_MIN_GRID")) : 0;  // A/B: idle padding CTAs
+    featherstone_step_kernel<L, PF, WARPS, TILE><<<blocks < min_grid ? min_grid : blocks, 32 * WARPS, smem, s>>>(M, p, in, out, ctl, use_contacts, update_mass, dt, phase_sync);
     count_launch();
     NB2_CUDA_CHECK(cudaGetLastError());
     return NB2_OK;

@@ -17,8 +17,9 @@ struct ConvexShape {
 };
 // Returns a bit mask of valid entries in dist/pos/normal (up to 5 manifold contacts, emission order = sort_sub_key order).
 NB2_DEV unsigned convex_pair_contacts(const ConvexShape& a, const ConvexShape& b, float* dist, V3* pos, V3* normal, float& reff_a,
-                                      float& reff_b) {
+                                      float& reff_b, const ConvexSpec* spec = nullptr) {
     ConvexPairIn in;
+    in.spec = spec;
     in.type_a = a.type;
     in.type_b = b.type;
     in.scale_a = a.scale;

@@ -81,6 +81,11 @@ struct DevModel {
     int* env_dyn_count;
     const long long* filter_keys;    // excluded pairs as (min << 32 | max), ascending
     int filter_count;
+    // speculative contacts (nb2_collide_speculative): 0 = off, 1 = enabled but inactive for this call (dt == 0 or extension == 0:
+    // only the writer's admission rule changes), 2 = active (shape velocities, swept broad phase, velocity-extended search gaps)
+    int spec_mode;
+    const float* spec_body_qd;
+    float spec_dt, spec_max_ext;
 };
 
 struct HostTables {

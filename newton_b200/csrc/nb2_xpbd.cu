@@ -539,6 +539,7 @@ xpbd_step_kernel(DevModel M, nb2_xpbd_params P, nb2_state_view sin, nb2_state_vi
     const int grp = lane / L, l = lane % L;
     const int slot = warp * G + grp;  // environment slot inside the CTA
     const int env0 = blockIdx.x * NE;
+    if (env0 >= M.env_count) return;  // padding CTA of the NB2_XPBD_MIN_GRID experiment (whole CTA, before any barrier)
     const int env = env0 + slot;
     const bool live = env < M.env_count;
     const nb2_model_desc& d = M.d;
@@ -1190,7 +1191,10 @@ static nb2_status launch_xpbd_W(nb2_model* m, const nb2_xpbd_params& p, const nb
     // ask for the largest shared-memory carve-out so that ~14-16 warps' worth of CTAs fit per SM
     static const int carveout = std::getenv("NB2_XPBD_CARVEOUT") ? std::atoi(std::getenv("NB2_XPBD_CARVEOUT")) : int(cudaSharedmemCarveoutMaxShared);
     NB2_CUDA_CHECK(cudaFuncSetAttribute(xpbd_step_kernel<L, EX, WARPS>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
-    xpbd_step_kernel<L, EX, WARPS><<<blocks, 32 * WARPS, smem, s>>>(M, p, in, out, ctl, use_contacts, dt, flags, contact_cap, contact_cache);
+    // A/B switch: pad the grid with idle CTAs up to this many (profiles/: does a grid below the SM count change the issue rate?)
+    static const int min_grid = env_int("NB2_XPBD_MIN_GRID", 0);
+    const int grid = blocks < min_grid ? min_grid : blocks;
+    xpbd_step_kernel<L, EX, WARPS><<<grid, 32 * WARPS, smem, s>>>(M, p, in, out, ctl, use_contacts, dt, flags, contact_cap, contact_cache);
     count_launch();
     NB2_CUDA_CHECK(cudaGetLastError());
     return NB2_OK;

@@ -196,11 +196,10 @@ def test_collision_pipeline_constructor_options():
     with pytest.raises(_lib.Nb2Error):
         newton_b200.CollisionPipeline(m, **defaults)
     for ok in (dict(include_static_kinematic_pairs=False), dict(contact_matching="latest"), dict(contact_matching="sticky"), dict(contact_matching="latest", contact_report=True),
-               dict(broad_phase="sap", shape_pairs_max=1000)):
+               dict(broad_phase="sap", shape_pairs_max=1000), dict(speculative_config=newton_b200.SpeculativeContactConfig(0.2))):
         with pytest.raises(_lib.Nb2Error):  # accepted: gets as far as the no-CPU-path error
             newton_b200.CollisionPipeline(m, **ok)
-    for bad in (dict(speculative_config=object()), dict(requires_grad=True),
-                dict(narrow_phase=object())):
+    for bad in (dict(requires_grad=True), dict(narrow_phase=object())):
         with pytest.raises(NotImplementedError):
             newton_b200.CollisionPipeline(m, **bad)
     with pytest.raises(ValueError):
