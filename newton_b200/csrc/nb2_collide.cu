@@ -363,6 +363,20 @@ struct __align__(4) SlotRec {
     float hi[3];
 };
 
+// Write-out staging (DevModel::lane_per_contact): the narrow phase leaves a pair's candidates in the registers of ONE lane - the 4
+// contacts of a foot would be converted and stored by that lane one after the other while the group's other lanes idle.  Instead
+// every lane drops its admitted candidates (and the pair's constants) into shared memory, and the group converts / stores them one
+// lane per CONTACT: the write_contact code runs once per round instead of up to five times, and exists once in the binary.
+struct __align__(4) StageContact {
+    float center[3], normal[3], dist;
+    int pair_lane;
+};
+struct __align__(4) StagePair {
+    int sa, sb;
+    float reff_a, reff_b, marg_a, marg_b;
+};
+__host__ __device__ inline size_t stage_bytes_per_group(int L) { return size_t(L) * 5 * sizeof(StageContact) + size_t(L) * sizeof(StagePair); }
+
 // Speculative contacts only (DevModel::spec_mode != 0): per-slot motion record next to the SlotRec table
 struct __align__(4) SlotMotionRec {
     float lin[3], ang[3], disp[3], search_gap;
@@ -416,6 +430,14 @@ __global__ void __launch_bounds__(32 * WARPS) collide_kernel(DevModel M, const f
     if (CONVEX && spec_mode != 0)
         motion = reinterpret_cast<SlotMotionRec*>(reinterpret_cast<SlotRec*>(smem_raw) + size_t(WARPS * G) * M.max_env_slots_shapes) +
                  size_t(warp * G + grp) * M.max_env_slots_shapes;
+    StageContact* stage_c = nullptr;
+    StagePair* stage_p = nullptr;
+    if (M.lane_per_contact) {
+        unsigned char* sbase = smem_raw + size_t(WARPS * G) * M.max_env_slots_shapes * (sizeof(SlotRec) + (CONVEX && spec_mode != 0 ? sizeof(SlotMotionRec) : 0)) +
+                               size_t(warp * G + grp) * stage_bytes_per_group(L);
+        stage_c = reinterpret_cast<StageContact*>(sbase);
+        stage_p = reinterpret_cast<StagePair*>(sbase + size_t(L) * 5 * sizeof(StageContact));
+    }
 
     int ss = 0, nloc = 0, nslots = 0, bs = 0, ps = 0, np = 0, slot0 = 0;
     if (live) {
@@ -615,7 +637,62 @@ __global__ void __launch_bounds__(32 * WARPS) collide_kernel(DevModel M, const f
         }
         const int total = __shfl_sync(0xffffffffu, incl, L - 1, L);
         int slot = slot0 + n_total + (incl - cnt);
-        if (cnt > 0) {
+        if (stage_c) {
+            if (cnt > 0) {
+                StagePair& sp = stage_p[l];
+                sp.sa = sa; sp.sb = sb;
+                sp.reff_a = reff_a; sp.reff_b = reff_b; sp.marg_a = marg_a; sp.marg_b = marg_b;
+                int k = incl - cnt;
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    if (!(vmask & (1u << i))) continue;
+                    StageContact& sc = stage_c[k++];
+                    st3(sc.center, cpos[i]);
+                    st3(sc.normal, cnorm[i]);
+                    sc.dist = cdist[i];
+                    sc.pair_lane = l;
+                }
+            }
+            __syncwarp();
+            float* cb = M.cb;
+            const size_t T = size_t(M.slot_total);
+            for (int c = l; c < total; c += L) {
+                const StageContact& sc = stage_c[c];
+                const StagePair& sp = stage_p[sc.pair_lane];
+                const int psa = sp.sa, psb = sp.sb;
+                const float ra = sp.reff_a, rb = sp.reff_b;
+                const int body0 = d.shape_body[psa], body1 = d.shape_body[psb];
+                const Xf Xbw_a = body0 == -1 ? Xf() : xinv(ldx(body_q + 7 * body0));
+                const Xf Xbw_b = body1 == -1 ? Xf() : xinv(ldx(body_q + 7 * body1));
+                const int o = slot0 + n_total + c;
+                // write_contact (collide.py:210-254): world contact -> body-frame points / offsets
+                const V3 n = unit(ld3(sc.normal)), center = ld3(sc.center);
+                const V3 a_w = center - n * (0.5f * sc.dist + ra);
+                const V3 b_w = center + n * (0.5f * sc.dist + rb);
+                const float om_a = ra + sp.marg_a, om_b = rb + sp.marg_b;
+                const V3 p0 = xpoint(Xbw_a, a_w), p1 = xpoint(Xbw_b, b_w);
+                const V3 o0 = xvec(Xbw_a, om_a * n), o1 = xvec(Xbw_b, -om_b * n);
+                cb[CF_BODY_A * T + o] = __int_as_float(body0 >= 0 ? body0 - bs : -1);
+                cb[CF_BODY_B * T + o] = __int_as_float(body1 >= 0 ? body1 - bs : -1);
+                cb[CF_SHAPE0 * T + o] = __int_as_float(psa);
+                cb[CF_SHAPE1 * T + o] = __int_as_float(psb);
+                cb[CF_P0X * T + o] = p0.x; cb[CF_P0Y * T + o] = p0.y; cb[CF_P0Z * T + o] = p0.z;
+                cb[CF_P1X * T + o] = p1.x; cb[CF_P1Y * T + o] = p1.y; cb[CF_P1Z * T + o] = p1.z;
+                cb[CF_O0X * T + o] = o0.x; cb[CF_O0Y * T + o] = o0.y; cb[CF_O0Z * T + o] = o0.z;
+                cb[CF_O1X * T + o] = o1.x; cb[CF_O1Y * T + o] = o1.y; cb[CF_O1Z * T + o] = o1.z;
+                cb[CF_NX * T + o] = n.x; cb[CF_NY * T + o] = n.y; cb[CF_NZ * T + o] = n.z;
+                cb[CF_MARGIN0 * T + o] = om_a;
+                cb[CF_MARGIN1 * T + o] = om_b;
+                cb[CF_MU * T + o] = (d.shape_material_mu[psa] + d.shape_material_mu[psb]) / 2.0f;
+                cb[CF_MU_TORSIONAL * T + o] = (d.shape_material_mu_torsional[psa] + d.shape_material_mu_torsional[psb]) / 2.0f;
+                cb[CF_MU_ROLLING * T + o] = (d.shape_material_mu_rolling[psa] + d.shape_material_mu_rolling[psb]) / 2.0f;
+                cb[CF_KE * T + o] = 0.5f * (d.shape_material_ke[psa] + d.shape_material_ke[psb]);
+                cb[CF_KD * T + o] = 0.5f * (d.shape_material_kd[psa] + d.shape_material_kd[psb]);
+                cb[CF_KF * T + o] = 0.5f * (d.shape_material_kf[psa] + d.shape_material_kf[psb]);
+                cb[CF_KA * T + o] = 0.5f * (d.shape_material_ka[psa] + d.shape_material_ka[psb]);
+            }
+            __syncwarp();  // the staging area is rewritten in the next round
+        } else if (cnt > 0) {
             const int body0 = d.shape_body[sa], body1 = d.shape_body[sb];
             const Xf Xbw_a = body0 == -1 ? Xf() : xinv(ldx(body_q + 7 * body0));
             const Xf Xbw_b = body1 == -1 ? Xf() : xinv(ldx(body_q + 7 * body1));
@@ -1227,7 +1304,8 @@ static nb2_status launch_collide_W(nb2_model* m, const float* body_q, const nb2_
     const DevModel& M = m->dev;
     const int NE = (32 / L) * WARPS;
     const int blocks = (M.env_count + NE - 1) / NE;
-    const size_t smem = size_t(NE) * M.max_env_slots_shapes * (sizeof(SlotRec) + (CONVEX && M.spec_mode != 0 ? sizeof(SlotMotionRec) : 0));
+    const size_t smem = size_t(NE) * M.max_env_slots_shapes * (sizeof(SlotRec) + (CONVEX && M.spec_mode != 0 ? sizeof(SlotMotionRec) : 0)) +
+                        (M.lane_per_contact ? size_t(NE) * stage_bytes_per_group(L) : 0);
     if (fused_out) {
         if (smem > 48 * 1024)
             NB2_CUDA_CHECK(cudaFuncSetAttribute(collide_kernel<L, CONVEX, WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -1245,7 +1323,8 @@ static nb2_status launch_collide_W(nb2_model* m, const float* body_q, const nb2_
 template <int L, bool CONVEX>
 static nb2_status launch_collide_L(nb2_model* m, const float* body_q, const nb2_contacts_view* fused_out, cudaStream_t s) {
     const DevModel& M = m->dev;
-    const size_t per_warp = size_t(32 / L) * M.max_env_slots_shapes * (sizeof(SlotRec) + (CONVEX && M.spec_mode != 0 ? sizeof(SlotMotionRec) : 0));
+    const size_t per_warp = size_t(32 / L) * (M.max_env_slots_shapes * (sizeof(SlotRec) + (CONVEX && M.spec_mode != 0 ? sizeof(SlotMotionRec) : 0)) +
+                                              (M.lane_per_contact ? stage_bytes_per_group(L) : 0));
     if (per_warp > 200 * 1024) {
         set_error("collide: too many shapes per environment for the fused kernel");
         return NB2_ERR_CAPACITY;
@@ -1304,6 +1383,9 @@ nb2_status launch_collide(nb2_model* m, const float* body_q, const nb2_contacts_
     // envs, frame 690.1 vs 678.3 us L2-warm, 733.8 vs 718.0 us with L2 flushed (profiles/r2j_fused_export_ab.txt) - the 256 tiles of
     // a single-wave launch all reach the look-back at the same time and serialise on it.  So the default is the two-kernel path.
     static const bool fused = std::getenv("NB2_COLLIDE_FUSED_EXPORT") && std::atoi(std::getenv("NB2_COLLIDE_FUSED_EXPORT")) != 0;
+    // one lane per contact in the write-out (NB2_COLLIDE_LANE_PER_CONTACT=0: one lane per pair, the round-1 arrangement; A/B in profiles/)
+    static const bool lane_per_contact = !(std::getenv("NB2_COLLIDE_LANE_PER_CONTACT") && std::atoi(std::getenv("NB2_COLLIDE_LANE_PER_CONTACT")) == 0);
+    m->dev.lane_per_contact = lane_per_contact ? 1 : 0;
     // speculative contacts live in the generic (CONVEX = true) instantiation only, with the two-kernel export
     const bool generic = m->has_convex_pairs || M.spec_mode != 0;
     const nb2_contacts_view* fused_out = (contacts && fused && M.spec_mode == 0) ? contacts : nullptr;

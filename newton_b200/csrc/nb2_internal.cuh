@@ -83,6 +83,7 @@ struct DevModel {
     int filter_count;
     // speculative contacts (nb2_collide_speculative): 0 = off, 1 = enabled but inactive for this call (dt == 0 or extension == 0:
     // only the writer's admission rule changes), 2 = active (shape velocities, swept broad phase, velocity-extended search gaps)
+    int lane_per_contact;  // collide_kernel write-out: 1 = one lane per contact through a shared-memory staging area
     int spec_mode;
     const float* spec_body_qd;
     float spec_dt, spec_max_ext;

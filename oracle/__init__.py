@@ -370,6 +370,21 @@ def _f32(a):
     return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
 
 
+def convex_pair_speculative(type_a, scale_a, xform_a, type_b, scale_b, xform_b, search_gap_sum, base_gap_sum, dt, max_extension, lin_a, ang_a,
+                            lin_b, ang_b, impl="oracle"):
+    """``convex_pair`` with the speculative writer (write_contact_speculative): the pair sees ``search_gap_sum``, admission uses
+    ``base_gap_sum`` + the predictive score from the shapes' velocities (origins = the transforms' positions)."""
+    sa, sb, xa, xb = _f32(scale_a), _f32(scale_b), _f32(xform_a), _f32(xform_b)
+    spec = _f32(np.concatenate([[base_gap_sum, dt, max_extension], xa[:3], xb[:3], lin_a, lin_b, ang_a, ang_b]))
+    dist, pos, n = np.zeros(5, np.float32), np.zeros((5, 3), np.float32), np.zeros((5, 3), np.float32)
+    L = lib()
+    L.orc_convex_pair_spec.restype = C.c_int
+    cnt = L.orc_convex_pair_spec(int(type_a), C.c_void_p(sa.ctypes.data), C.c_void_p(xa.ctypes.data), int(type_b), C.c_void_p(sb.ctypes.data),
+                                 C.c_void_p(xb.ctypes.data), C.c_float(search_gap_sum), C.c_void_p(spec.ctypes.data), C.c_void_p(dist.ctypes.data),
+                                 C.c_void_p(pos.ctypes.data), C.c_void_p(n.ctypes.data), C.c_int(IMPLS[impl]))
+    return cnt, dist, pos, n
+
+
 def convex_pair_hull(type_a, scale_a, xform_a, hull_a, type_b, scale_b, xform_b, hull_b, gap_sum=0.2, impl="oracle"):
     """``convex_pair`` with CONVEX_MESH operands: ``hull_*`` = unscaled vertices ``[n, 3]`` (None for primitives)."""
     sa, sb, xa, xb = _f32(scale_a), _f32(scale_b), _f32(xform_a), _f32(xform_b)

@@ -266,6 +266,25 @@ int orc_convex_pair(int type_a, const float* scale_a, const float* xform_a, int 
                             transform::load(xform_b), gap_sum, dist5, pos15, normal15, impl, margin_a, margin_b);
 }
 
+// ... with the speculative writer: `gap_sum` is then the velocity-extended SEARCH gap, spec21 = base_gap_sum, dt, max_extension,
+// origin_a, origin_b, linear_velocity_a, linear_velocity_b, angular_velocity_a, angular_velocity_b
+int orc_convex_pair_spec(int type_a, const float* scale_a, const float* xform_a, int type_b, const float* scale_b, const float* xform_b,
+                         float gap_sum, const float* spec21, float* dist5, float* pos15, float* normal15, int impl) {
+    cvx::SpeculativeWriter w;
+    w.enabled = true;
+    w.base_gap_sum = spec21[0];
+    w.dt = spec21[1];
+    w.max_extension = spec21[2];
+    w.origin_a = load3(spec21 + 3);
+    w.origin_b = load3(spec21 + 6);
+    w.linear_velocity_a = load3(spec21 + 9);
+    w.linear_velocity_b = load3(spec21 + 12);
+    w.angular_velocity_a = load3(spec21 + 15);
+    w.angular_velocity_b = load3(spec21 + 18);
+    return convex_pair_test(type_a, load3(scale_a), transform::load(xform_a), type_b, load3(scale_b), transform::load(xform_b), gap_sum, dist5,
+                            pos15, normal15, impl, 0.0f, 0.0f, cvx::HullRef(), cvx::HullRef(), &w);
+}
+
 // ... with CONVEX_MESH operands: hull_* = unscaled vertices [n x 3] (NULL / 0 for primitives); the local AABB (centre seed) is
 // derived from the vertices like ModelBuilder.finalize does
 int orc_convex_pair_hull(int type_a, const float* scale_a, const float* xform_a, const float* hull_a, int n_a, int type_b, const float* scale_b,

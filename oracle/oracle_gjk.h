@@ -54,6 +54,19 @@ inline int convex_pair(int type_a, vec3 scale_a, const transform& Xa, float marg
     in.hull_b = hull_b.points;
     in.hull_count_b = hull_b.count;
     in.center_b = to_nb2(0.5f * (hull_b.local_aabb_lower + hull_b.local_aabb_upper));
+    nb2::ConvexSpec cs;
+    if (spec && spec->enabled) {
+        cs.base_gap_sum = spec->base_gap_sum;
+        cs.dt = spec->dt;
+        cs.max_extension = spec->max_extension;
+        cs.origin_a = to_nb2(spec->origin_a);
+        cs.origin_b = to_nb2(spec->origin_b);
+        cs.lin_a = to_nb2(spec->linear_velocity_a);
+        cs.lin_b = to_nb2(spec->linear_velocity_b);
+        cs.ang_a = to_nb2(spec->angular_velocity_a);
+        cs.ang_b = to_nb2(spec->angular_velocity_b);
+        in.spec = &cs;
+    }
     nb2::V3 p[5], n[5];
     nb2::ConvexPairAabbs bb{to_nb2(lo_a), to_nb2(hi_a), to_nb2(lo_b), to_nb2(hi_b)};
     int cnt = nb2::convex_contacts_any(in, bb, dist, p, n, reff_a, reff_b);
@@ -193,7 +206,8 @@ inline nb2::ConvexGeom nb2_geom_hull(int type, vec3 scale, const cvx::HullRef& h
 
 inline int convex_pair_test(int type_a, vec3 scale_a, const transform& Xa, int type_b, vec3 scale_b, const transform& Xb, float gap_sum,
                             float* dist5, float* pos15, float* normal15, int impl = 0, float margin_a = 0.0f, float margin_b = 0.0f,
-                            const cvx::HullRef& hull_a = cvx::HullRef(), const cvx::HullRef& hull_b = cvx::HullRef()) {
+                            const cvx::HullRef& hull_a = cvx::HullRef(), const cvx::HullRef& hull_b = cvx::HullRef(),
+                            const cvx::SpeculativeWriter* spec = nullptr) {
     float ra, rb;
     vec3 pos[5], normal[5];
     // AABBs as the stand-alone NarrowPhase computes them (narrow_phase.py:1120-1150): tight support AABB +- the shape's gap;
@@ -214,7 +228,7 @@ inline int convex_pair_test(int type_a, vec3 scale_a, const transform& Xa, int t
     aabb(type_a, scale_a, Xa, hull_a, lo_a, hi_a);
     aabb(type_b, scale_b, Xb, hull_b, lo_b, hi_b);
     int cnt = convex_pair(type_a, scale_a, Xa, margin_a, type_b, scale_b, Xb, margin_b, gap_sum, dist5, pos, normal, ra, rb, lo_a, hi_a, lo_b, hi_b, impl,
-                          hull_a, hull_b);
+                          hull_a, hull_b, spec);
     for (int i = 0; i < cnt; ++i) {
         store3(pos15 + 3 * i, pos[i]);
         store3(normal15 + 3 * i, normal[i]);

@@ -74,6 +74,34 @@ def test_pair_contacts_bit_equal(oracle_lib, name_a, name_b):
         assert produced > 0  # the sample must actually reach the contact-producing branches
 
 
+@pytest.mark.parametrize("name_a,name_b", list(itertools.product(T, T)))
+def test_pair_contacts_with_the_speculative_writer_bit_equal(oracle_lib, name_a, name_b):
+    """write_contact_speculative (predictive admission, search gap for the pair, plane-proxy overlap radius) in both translations"""
+    import oracle
+
+    rng = np.random.default_rng(31 + 1000 * T[name_a] + T[name_b])
+    ta, tb = T[name_a], T[name_b]
+    produced = extra = 0
+    for _ in range(40):
+        sa, sb = _rand_scale(rng, ta), _rand_scale(rng, tb)
+        xa, xb = _rand_pose_pair(rng)
+        base = float(rng.choice([0.0, 0.02]))
+        search = base + float(rng.uniform(0.0, 0.6))
+        dt, ext = float(rng.choice([0.0, 0.01, 0.05])), float(rng.choice([0.1, 0.5]))
+        approach = (xb[:3] - xa[:3]) * rng.uniform(-2.0, 12.0)  # A moving towards (or away from) B
+        la, lb = approach.astype(np.float32), rng.normal(size=3).astype(np.float32)
+        wa, wb = rng.normal(size=3).astype(np.float32) * 2.0, rng.normal(size=3).astype(np.float32) * 2.0
+        r0 = oracle.convex_pair_speculative(ta, sa, xa, tb, sb, xb, search, base, dt, ext, la, wa, lb, wb, impl="oracle")
+        r1 = oracle.convex_pair_speculative(ta, sa, xa, tb, sb, xb, search, base, dt, ext, la, wa, lb, wb, impl="product_host")
+        assert r0[0] == r1[0], (sa, sb, xa, xb, base, search, dt, ext)
+        for a, b in zip(r0[1:], r1[1:]):
+            assert np.array_equal(_bits(a), _bits(b)), (sa, sb, xa, xb, base, search, dt, ext)
+        produced += r0[0]
+        extra += r0[0] - oracle.convex_pair(ta, sa, xa, tb, sb, xb, base, "oracle")[0]
+    if not (ta == T["plane"] and tb == T["plane"]):
+        assert produced > 0
+
+
 @pytest.mark.parametrize("name_a,name_b", list(itertools.product(SOLID, SOLID)))
 def test_mpr_and_gjk_cores_bit_equal(oracle_lib, name_a, name_b):
     import oracle
