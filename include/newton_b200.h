@@ -288,8 +288,8 @@ nb2_status nb2_eval_fk(nb2_model* model, const float* joint_q, const float* join
                        void* cuda_stream);
 
 /* Reference newton.eval_ik (sim/articulation.py:640-932): body_q/body_qd -> joint_q/joint_qd for every joint that belongs to
- * an articulation (FREE/DISTANCE linear velocities in the public COM convention).  D6 joints with two or three angular axes
- * (invert_{2,3}d_rotational_dofs) return NB2_ERR_UNSUPPORTED. */
+ * an articulation (FREE/DISTANCE linear velocities in the public COM convention).  D6 joints with two or three angular axes go
+ * through invert_{2,3}d_rotational_dofs (:85-126, 177-236; Euler decomposition of the relative rotation in the joint's own basis). */
 nb2_status nb2_eval_ik(nb2_model* model, const float* body_q, const float* body_qd, float* joint_q, float* joint_qd,
                        void* cuda_stream);
 

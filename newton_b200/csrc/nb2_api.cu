@@ -222,9 +222,6 @@ static nb2_status build_tables(nb2_model* m, const nb2_model_desc& d) {
         if ((st = fetch(d.joint_ancestor, size_t(J), janc))) return st;
         if ((st = fetch(d.joint_type, size_t(J), jtype))) return st;
         if ((st = fetch(d.joint_dof_dim, size_t(J) * 2, jdim))) return st;
-        h.ik_supported = true;
-        for (int j = 0; j < J; ++j)
-            if (jtype[j] == 6 && jdim[2 * j + 1] > 1) h.ik_supported = false;  // D6 with 2-3 angular axes
         if ((st = fetch(d.body_flags, size_t(B), bflags))) return st;
         for (int j = 0; j < J; ++j)
             if (jchild[j] != j) {  // the reference's spatial_mass indexes body_I_s by joint index (kernels.py:1476-1477)
@@ -809,10 +806,6 @@ nb2_status nb2_eval_ik(nb2_model* model, const float* body_q, const float* body_
     if (!model || !body_q || !body_qd || !joint_q || !joint_qd) {
         set_error("nb2_eval_ik: NULL argument");
         return NB2_ERR_INVALID_ARGUMENT;
-    }
-    if (!model->host.ik_supported) {
-        set_error("nb2_eval_ik: D6 joints with two or three angular axes are not supported");
-        return NB2_ERR_UNSUPPORTED;
     }
     DeviceGuard guard(model->device);
     return launch_eval_ik(model, body_q, body_qd, joint_q, joint_qd, static_cast<cudaStream_t>(cuda_stream));

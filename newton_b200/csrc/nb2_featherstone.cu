@@ -1302,6 +1302,51 @@ NB2_DEV float twist_angle_signed(V3 axis, Q4 q) {  // wp.quat_twist_angle_signed
     return 2.0f * atan2_w(dot(V3(q.x, q.y, q.z), axis), q.w);
 }
 
+// newton.math.quat_decompose (math/spatial.py:150-175): wp.quat_to_euler(q, 2, 1, 0), each angle wrapped to [-pi, pi); for
+// q = qx(a) qy(b) qz(c) the result is (a, b, c)
+NB2_DEV float wrap_pm_pi(float theta) {
+    const float pi = 3.14159265358979323846f, two_pi = 2.0f * pi;
+    float wrapped = fmodf(theta + pi, two_pi);
+    if (wrapped < 0.0f) wrapped += two_pi;
+    return wrapped - pi;
+}
+NB2_DEV V3 q_decompose(Q4 q) {
+    const float a = q.w - q.y, b = q.z - q.x, c = q.y + q.w, d = -q.x - q.z;
+    const float n_ab = a * a + b * b;
+    float theta2 = acos_w(2.0f * n_ab / (n_ab + c * c + d * d) - 1.0f);
+    const float theta_plus = atan2_w(b, a), theta_minus = atan2_w(d, c);
+    const float theta1 = theta_plus - theta_minus;
+    float theta3 = theta_plus + theta_minus;
+    theta3 = -theta3;
+    theta2 -= 1.57079632679489661923f;
+    return V3(wrap_pm_pi(theta3), wrap_pm_pi(theta2), wrap_pm_pi(theta1));
+}
+// invert_2d / invert_3d_rotational_dofs (sim/articulation.py:85-126, 177-236); `three` selects the 3-axis variant
+NB2_DEV void invert_rotational_dofs(bool three, V3 axis_0, V3 axis_1, V3 axis_2, Q4 q_p, Q4 q_c, V3 w_err, float* angles_out, float* vel_out) {
+    const V3 axis_2_rh = cross(axis_0, axis_1);
+    float s = 1.0f;
+    if (three && dot(axis_2_rh, axis_2) < 0.0f) s = -1.0f;
+    const Q4 q_off = q_from_cols(axis_0, axis_1, axis_2_rh);
+    const Q4 q_pc = qmul(qmul(qmul(qconj(q_off), qconj(q_p)), q_c), q_off);
+    const V3 angles = q_decompose(q_pc);
+    const V3 l0 = qrot(q_off, V3(1.f, 0.f, 0.f)), l1 = qrot(q_off, V3(0.f, 1.f, 0.f)), l2 = qrot(q_off, V3(0.f, 0.f, 1.f));
+    const V3 a0 = l0;
+    const Q4 q_0 = q_axis_angle(a0, angles.x);
+    const V3 a1 = qrot(q_0, l1);
+    const Q4 q_1 = q_axis_angle(a1, angles.y);
+    const V3 a2 = qrot(qmul(q_1, q_0), l2);
+    const V3 w_err_p = qrot_inv(q_p, w_err);
+    const V3 c12 = cross(a1, a2), c02 = cross(a0, a2), c01 = cross(a0, a1);
+    angles_out[0] = angles.x;
+    angles_out[1] = angles.y;
+    vel_out[0] = dot(w_err_p, c12) / dot(a0, c12);
+    vel_out[1] = dot(w_err_p, c02) / dot(a1, c02);
+    if (three) {
+        angles_out[2] = s * angles.z;
+        vel_out[2] = s * (dot(w_err_p, c01) / dot(a2, c01));
+    }
+}
+
 __global__ void __launch_bounds__(128) eval_ik_kernel(DevModel M, const float* __restrict__ body_q, const float* __restrict__ body_qd,
                                                       float* __restrict__ joint_q, float* __restrict__ joint_qd) {
     const nb2_model_desc& d = M.d;
@@ -1365,6 +1410,11 @@ __global__ void __launch_bounds__(128) eval_ik_kernel(DevModel M, const float* _
             const V3 ax = ld3(d.joint_axis + 3 * (qd_start + lin));
             joint_q[q_start + lin] = twist_angle_signed(ax, q_pc);
             joint_qd[qd_start + lin] = dot(w_err, xvec(X_wpj, ax));
+        }
+        if (ang >= 2) {
+            const int ia = qd_start + lin;
+            invert_rotational_dofs(ang == 3, ld3(d.joint_axis + 3 * ia), ld3(d.joint_axis + 3 * (ia + 1)),
+                                   ang == 3 ? ld3(d.joint_axis + 3 * (ia + 2)) : V3(), q_p, q_c, w_err, joint_q + q_start + lin, joint_qd + qd_start + lin);
         }
     }
 }

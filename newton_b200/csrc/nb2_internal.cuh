@@ -100,7 +100,6 @@ struct HostTables {
     std::vector<signed char> hb_body_col, hb_row_col, dof_joint;
     int max_art_dofs = 0;  // largest articulation (dofs)
     bool featherstone_supported = true;
-    bool ik_supported = true;  // false when a D6 joint has 2-3 angular axes
     bool fk_levels = true;     // eval_fk may schedule joints by tree depth (parent-before-child order, one driving joint per body)
     std::string featherstone_reason;
 };

@@ -467,10 +467,8 @@ def eval_fk(model, joint_q, joint_qd, state, mask=None, indices=None, body_flag_
 def eval_ik(model, state, joint_q, joint_qd):
     """newton.eval_ik: body_q / body_qd -> joint_q / joint_qd (sim/articulation.py:640-932)."""
     d = _abi.model_desc(model)
-    n = lib().orc_eval_ik(C.byref(d), C.c_void_p(_abi.ptr(state.body_q)), C.c_void_p(_abi.ptr(state.body_qd)),
-                          C.c_void_p(_abi.ptr(joint_q)), C.c_void_p(_abi.ptr(joint_qd)))
-    if n:
-        raise NotImplementedError("oracle eval_ik: D6 joints with 2-3 angular axes")
+    lib().orc_eval_ik(C.byref(d), C.c_void_p(_abi.ptr(state.body_q)), C.c_void_p(_abi.ptr(state.body_qd)),
+                      C.c_void_p(_abi.ptr(joint_q)), C.c_void_p(_abi.ptr(joint_qd)))
 
 
 def shape_aabbs_speculative(model, body_q, body_qd, dt, max_extension):

@@ -811,8 +811,51 @@ inline float quat_twist_angle_signed(vec3 axis, quat q) {
     return 2.0f * atan2_w(proj, q.w);
 }
 
+// invert_2d_rotational_dofs / invert_3d_rotational_dofs (sim/articulation.py:85-126, 177-236): joint angles and rates of a D6 joint
+// with two / three angular axes from the relative orientation and the angular-velocity error
+inline void invert_2d_rotational_dofs(vec3 axis_0, vec3 axis_1, quat q_p, quat q_c, vec3 w_err, float* angles2, float* vel2) {
+    quat q_off = quat_from_matrix(matrix_from_cols(axis_0, axis_1, cross(axis_0, axis_1)));
+    quat q_pc = quat_inverse(q_off) * quat_inverse(q_p) * q_c * q_off;
+    vec3 angles = quat_decompose(q_pc);
+    vec3 local_0 = quat_rotate(q_off, vec3(1.f, 0.f, 0.f)), local_1 = quat_rotate(q_off, vec3(0.f, 1.f, 0.f)),
+         local_2 = quat_rotate(q_off, vec3(0.f, 0.f, 1.f));
+    vec3 a0 = local_0;
+    quat q_0 = quat_from_axis_angle(a0, angles.x);
+    vec3 a1 = quat_rotate(q_0, local_1);
+    quat q_1 = quat_from_axis_angle(a1, angles.y);
+    vec3 a2 = quat_rotate(q_1 * q_0, local_2);
+    vec3 w_err_p = quat_rotate_inv(q_p, w_err);
+    vec3 c12 = cross(a1, a2), c02 = cross(a0, a2);
+    angles2[0] = angles.x;
+    angles2[1] = angles.y;
+    vel2[0] = dot(w_err_p, c12) / dot(a0, c12);
+    vel2[1] = dot(w_err_p, c02) / dot(a1, c02);
+}
+inline void invert_3d_rotational_dofs(vec3 axis_0, vec3 axis_1, vec3 axis_2, quat q_p, quat q_c, vec3 w_err, float* angles3, float* vel3) {
+    vec3 axis_2_rh = cross(axis_0, axis_1);
+    float s = 1.0f;
+    if (dot(axis_2_rh, axis_2) < 0.0f) s = -1.0f;  // left-handed user triple: third angle / rate change sign
+    quat q_off = quat_from_matrix(matrix_from_cols(axis_0, axis_1, axis_2_rh));
+    quat q_pc = quat_inverse(q_off) * quat_inverse(q_p) * q_c * q_off;
+    vec3 angles = quat_decompose(q_pc);
+    vec3 local_0 = quat_rotate(q_off, vec3(1.f, 0.f, 0.f)), local_1 = quat_rotate(q_off, vec3(0.f, 1.f, 0.f)),
+         local_2 = quat_rotate(q_off, vec3(0.f, 0.f, 1.f));
+    vec3 a0 = local_0;
+    quat q_0 = quat_from_axis_angle(a0, angles.x);
+    vec3 a1 = quat_rotate(q_0, local_1);
+    quat q_1 = quat_from_axis_angle(a1, angles.y);
+    vec3 a2 = quat_rotate(q_1 * q_0, local_2);
+    vec3 w_err_p = quat_rotate_inv(q_p, w_err);
+    vec3 c12 = cross(a1, a2), c02 = cross(a0, a2), c01 = cross(a0, a1);
+    angles3[0] = angles.x;
+    angles3[1] = angles.y;
+    angles3[2] = s * angles.z;
+    vel3[0] = dot(w_err_p, c12) / dot(a0, c12);
+    vel3[1] = dot(w_err_p, c02) / dot(a1, c02);
+    vel3[2] = s * (dot(w_err_p, c01) / dot(a2, c01));
+}
+
 // ---- public newton.eval_ik (sim/articulation.py:640-932 eval_articulation_ik; one joint per thread, no mask) ---------------
-// D6 joints with 2 or 3 angular axes (invert_{2,3}d_rotational_dofs) are not restated: returns the number of such joints.
 inline int eval_articulation_ik(const nb2_model_desc& m, const float* body_q, const float* body_qd, float* joint_q, float* joint_qd) {
     int unsupported = 0;
     for (int a = 0; a < m.articulation_count; ++a)
@@ -878,7 +921,12 @@ inline int eval_articulation_ik(const nb2_model_desc& m, const float* body_q, co
                     joint_q[q_start + lin] = quat_twist_angle_signed(ax, q_pc);
                     joint_qd[qd_start + lin] = dot(w_err, transform_vector(X_wpj, ax));
                 }
-                if (ang > 1) unsupported += 1;
+                if (ang == 2)
+                    invert_2d_rotational_dofs(axis(qd_start + lin), axis(qd_start + lin + 1), q_p, q_c, w_err, joint_q + q_start + lin,
+                                              joint_qd + qd_start + lin);
+                if (ang == 3)
+                    invert_3d_rotational_dofs(axis(qd_start + lin), axis(qd_start + lin + 1), axis(qd_start + lin + 2), q_p, q_c, w_err,
+                                              joint_q + q_start + lin, joint_qd + qd_start + lin);
             }
         }
     return unsupported;

@@ -202,6 +202,31 @@ inline quat quat_from_matrix(const mat33& a) {
     return normalize(quat(x, y, z, w));
 }
 
+// newton.math.quat_decompose (reference math/spatial.py:150-175): wp.quat_to_euler(q, 2, 1, 0) with every angle wrapped to
+// [-pi, pi).  wp.quat_to_euler is a Warp built-in (not vendored); restated as the direct quaternion -> Euler conversion of
+// Bernardes & Viollet (2022) for the Tait-Bryan sequence (i, j, k) = (Z, Y, X).  What the reference relies on - and what pins this
+// restatement - is that for q = qx(a) * qy(b) * qz(c) the result is (a, b, c) (invert_3d_rotational_dofs inverts
+// compute_3d_rotational_dofs, sim/articulation.py:150-236; test_kinematics.py:1057-1104 to 1e-6).  Bit-level order unpinned.
+inline float wrap_angle_pm_pi(float theta) {  // math/spatial.py:133-147; wp.mod = fmod
+    const float pi = 3.14159265358979323846f, two_pi = 2.0f * pi;
+    float wrapped = std::fmod(theta + pi, two_pi);
+    if (wrapped < 0.0f) wrapped += two_pi;
+    return wrapped - pi;
+}
+inline vec3 quat_decompose(quat q) {
+    // (i, j, k) = (3, 2, 1) in the paper's 1-based numbering, not proper: sign = (i - j)(j - k)(k - i) / 2 = -1; t = (w, x, y, z)
+    const float a = q.w - q.y, b = q.z - q.x, c = q.y + q.w, d = -q.x - q.z;
+    const float n_ab = a * a + b * b;
+    float theta2 = acos_w(2.0f * n_ab / (n_ab + c * c + d * d) - 1.0f);
+    const float theta_plus = atan2_w(b, a), theta_minus = atan2_w(d, c);
+    const float theta1 = theta_plus - theta_minus;
+    float theta3 = theta_plus + theta_minus;
+    theta3 = -theta3;
+    theta2 -= 1.57079632679489661923f;
+    // theta1 turns about Z, theta2 about Y, theta3 about X: returned in (x, y, z) order
+    return vec3(wrap_angle_pm_pi(theta3), wrap_angle_pm_pi(theta2), wrap_angle_pm_pi(theta1));
+}
+
 struct transform {
     vec3 p;
     quat q;

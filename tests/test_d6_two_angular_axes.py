@@ -145,7 +145,90 @@ def test_universal_joint_pendulum_conserves_energy(oracle_lib, gravity):
     np.testing.assert_allclose(chk.body_qd.numpy(), s0.body_qd.numpy(), atol=1e-4)
 
 
+# ---- eval_ik on multi-axis D6 joints (invert_2d / invert_3d_rotational_dofs, sim/articulation.py:85-126, 177-236) ---------------------
+
+
+def _d6_model(axes, parent_rot=None):
+    b = ModelBuilder(gravity=0.0)
+    child = b.add_link(mass=1.0, inertia=np.eye(3) * 0.1)
+    px = X.transform((0.1, -0.2, 0.3), parent_rot) if parent_rot is not None else None
+    j = b.add_joint_d6(parent=-1, child=child, parent_xform=px, angular_axes=[JointDofConfig.create_unlimited(a) for a in axes])
+    b.add_articulation([j])
+    return b.finalize(), child
+
+
+def test_fk_ik_d6_left_handed_angular_axes(oracle_lib):
+    """newton/tests/test_kinematics.py:1057-1104, verbatim numbers: axes (X, Z, Y) form a left-handed triple; the body rotation is the
+    intrinsic product qfa(X, q0) qfa(Z, q1) qfa(Y, q2) (1e-6), the angular velocity is the transported-axes sum (1e-6), and
+    eval_ik recovers joint_q and joint_qd (1e-6)."""
+    model, child = _d6_model(((1.0, 0.0, 0.0), (0.0, 0.0, 1.0), (0.0, 1.0, 0.0)))
+    q_vals, qd_vals = np.array([0.5, -0.4, 0.7], np.float32), np.array([0.9, -0.6, 0.3], np.float32)
+    state = model.state()
+    state.joint_q.copy_(_f32(q_vals))
+    state.joint_qd.copy_(_f32(qd_vals))
+    oracle_lib.eval_fk(model, state.joint_q, state.joint_qd, state)
+    rot = state.body_q.numpy()[child][3:].astype(np.float64)
+    qa = X.quat_from_axis_angle
+    expected = X.quat_mul(X.quat_mul(qa((1, 0, 0), 0.5), qa((0, 0, 1), -0.4)), qa((0, 1, 0), 0.7))
+    np.testing.assert_allclose(rot, expected, atol=1e-6)
+    q_0 = qa((1, 0, 0), 0.5)
+    axis_1_w = X.quat_rotate(q_0, np.array([0.0, 0.0, 1.0]))
+    q_1 = qa(axis_1_w, -0.4)
+    axis_2_w = X.quat_rotate(X.quat_mul(q_1, q_0), np.array([0.0, 1.0, 0.0]))
+    expected_w = np.array([1.0, 0.0, 0.0]) * 0.9 + axis_1_w * -0.6 + axis_2_w * 0.3
+    np.testing.assert_allclose(state.body_qd.numpy()[child][3:], expected_w, atol=1e-6)
+    q_ik, qd_ik = torch.zeros_like(model.joint_q), torch.zeros_like(model.joint_qd)
+    oracle_lib.eval_ik(model, state, q_ik, qd_ik)
+    np.testing.assert_allclose(q_ik.numpy(), q_vals, atol=1e-6)
+    np.testing.assert_allclose(qd_ik.numpy(), qd_vals, atol=1e-6)
+
+
+@pytest.mark.parametrize("axes", [((1.0, 0.0, 0.0), (0.0, 0.0, 1.0)), ((0.0, 0.0, 1.0), (1.0, 0.0, 0.0)), ((0.0, 1.0, 0.0), (0.0, 0.0, 1.0)),
+                                  ((1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0)), ((0.0, 0.0, 1.0), (0.0, 1.0, 0.0), (1.0, 0.0, 0.0))])
+def test_ik_inverts_fk_on_multi_axis_d6(oracle_lib, axes):
+    """eval_ik(eval_fk(q, qd)) == (q, qd) for two- and three-axis D6 joints under a rotated, offset parent frame"""
+    model, _ = _d6_model(axes, parent_rot=X.quat_from_axis_angle((0.3, -0.5, 0.8), 0.9))
+    rng = np.random.default_rng(len(axes))
+    for _ in range(8):
+        q = rng.uniform(-1.2, 1.2, len(axes)).astype(np.float32)
+        qd = rng.uniform(-2.0, 2.0, len(axes)).astype(np.float32)
+        state = model.state()
+        state.joint_q.copy_(_f32(q))
+        state.joint_qd.copy_(_f32(qd))
+        oracle_lib.eval_fk(model, state.joint_q, state.joint_qd, state)
+        q_ik, qd_ik = torch.zeros_like(model.joint_q), torch.zeros_like(model.joint_qd)
+        oracle_lib.eval_ik(model, state, q_ik, qd_ik)
+        np.testing.assert_allclose(q_ik.numpy(), q, atol=2e-6)
+        np.testing.assert_allclose(qd_ik.numpy(), qd, atol=1e-5)
+
+
 # ---- GPU parity -------------------------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.gpu
+def test_gpu_eval_ik_multi_axis_d6_bit_exact(oracle_lib, cuda_lib):
+    import newton_b200
+
+    for axes in (((1.0, 0.0, 0.0), (0.0, 0.0, 1.0)), ((1.0, 0.0, 0.0), (0.0, 0.0, 1.0), (0.0, 1.0, 0.0)), ((0.0, 0.0, 1.0), (0.0, 1.0, 0.0), (1.0, 0.0, 0.0))):
+        model, _ = _d6_model(axes, parent_rot=X.quat_from_axis_angle((0.3, -0.5, 0.8), 0.9))
+        rng = np.random.default_rng(7 + len(axes))
+        mg = model.to("cuda:0")
+        for _ in range(6):
+            q = rng.uniform(-1.2, 1.2, len(axes)).astype(np.float32)
+            qd = rng.uniform(-2.0, 2.0, len(axes)).astype(np.float32)
+            state = model.state()
+            state.joint_q.copy_(_f32(q))
+            state.joint_qd.copy_(_f32(qd))
+            oracle_lib.eval_fk(model, state.joint_q, state.joint_qd, state)
+            q_ref, qd_ref = torch.zeros_like(model.joint_q), torch.zeros_like(model.joint_qd)
+            oracle_lib.eval_ik(model, state, q_ref, qd_ref)
+            sg = mg.state()
+            sg.body_q.copy_(state.body_q)
+            sg.body_qd.copy_(state.body_qd)
+            q_g, qd_g = torch.zeros_like(mg.joint_q), torch.zeros_like(mg.joint_qd)
+            newton_b200.eval_ik(mg, sg, q_g, qd_g)
+            np.testing.assert_array_equal(q_g.cpu().numpy(), q_ref.numpy())
+            np.testing.assert_array_equal(qd_g.cpu().numpy(), qd_ref.numpy())
 
 
 @pytest.mark.gpu
