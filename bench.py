@@ -284,11 +284,12 @@ def run_native(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup, sampler=None):
+        if sampler:
+            sampler.start()  # before the warm-up and the barrier: forking nvidia-smi costs rank 0 several ms - inside the synchronised
+            #                  region that start-up skew is what every other rank then waits for in the final drain (N = 4: 5 ms / 50 frames)
         for _ in range(warmup):
             fn()
         barrier()
-        if sampler:
-            sampler.start()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         for a, b in ev:
             flush.zero_()  # evict L2 (126 MB) between timed steps; not inside the timed events
