@@ -161,17 +161,34 @@ class PeerStateGather:
             self.offsets.append(off)
             off += (t.numel() * t.element_size() + 15) & ~15
         self.bytes = off
+        # Every rank reaches every collective below whether or not its own local step failed (a rank that raised early would leave
+        # the others waiting inside all_gather_object for the NCCL timeout): local failures are recorded, agreed on, raised together.
         h = C.c_void_p()
-        _lib.check(self._lib.nb2_peer_gather_create(self.device.index, self.rank, self.world, self.bytes, C.byref(h)),
-                   "nb2_peer_gather_create")
-        self._h = h
+        self._h = None
         nh = int(self._lib.nb2_peer_gather_handle_bytes())
         mine = C.create_string_buffer(nh)
-        _lib.check(self._lib.nb2_peer_gather_export(h, mine), "nb2_peer_gather_export")
+        err = None
+        try:
+            _lib.check(self._lib.nb2_peer_gather_create(self.device.index, self.rank, self.world, self.bytes, C.byref(h)),
+                       "nb2_peer_gather_create")
+            self._h = h
+            _lib.check(self._lib.nb2_peer_gather_export(h, mine), "nb2_peer_gather_export")
+        except Exception as e:  # noqa: BLE001 - reported below, on every rank
+            err = f"rank {self.rank}: {e}"
         handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(mine.raw), group=group)
-        _lib.check(self._lib.nb2_peer_gather_connect(h, C.c_char_p(b"".join(handles))), "nb2_peer_gather_connect")
-        dist.barrier(group=group)  # every rank has mapped every buffer before the first push
+        dist.all_gather_object(handles, (err, bytes(mine.raw)), group=group)
+        errors = [e for e, _ in handles if e]
+        if not errors:
+            try:
+                _lib.check(self._lib.nb2_peer_gather_connect(h, C.c_char_p(b"".join(b for _, b in handles))), "nb2_peer_gather_connect")
+            except Exception as e:  # noqa: BLE001
+                err = f"rank {self.rank}: {e}"
+            connected = [None] * self.world
+            dist.all_gather_object(connected, err, group=group)  # doubles as the barrier: every rank has mapped every buffer
+            errors = [e for e in connected if e]
+        if errors:
+            self.close()
+            raise RuntimeError("peer gather unavailable: " + "; ".join(errors))
         self.stride = int(self._lib.nb2_peer_gather_stride(h))
         self._snap = torch.empty(self.stride, dtype=torch.uint8, device=self.device)
         self._copy_stream = torch.cuda.Stream(device=self.device)
