@@ -11,7 +11,14 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("NB2_LIB") or os.path.join(_HERE, "libnewton_b200.so")
+# Floating-point mode of the kernels.  "strict" (default): no FMA contraction, correctly rounded inverse trig - the build that
+# reproduces the CPU oracle bit for bit.  NB2_FP=fast selects the twin library compiled with nvcc's default contraction: same
+# sources, same contact indices / counts on the test scenes, body state within the north-star tolerance (1e-5 relative after 100
+# substeps, tests/test_gpu_fast_fp.py), about 10 % faster on the XPBD step (profiles/r2o_fp_modes.txt).  NB2_LIB overrides both.
+FP_MODE = os.environ.get("NB2_FP", "strict").lower()
+if FP_MODE not in ("strict", "fast"):
+    raise ValueError(f"NB2_FP={FP_MODE!r}: expected 'strict' or 'fast'")
+LIB_PATH = os.environ.get("NB2_LIB") or os.path.join(_HERE, "libnewton_b200_fast.so" if FP_MODE == "fast" else "libnewton_b200.so")
 _lib = None
 
 STATUS = {0: "NB2_OK", 1: "NB2_ERR_INVALID_ARGUMENT", 2: "NB2_ERR_UNSUPPORTED", 3: "NB2_ERR_CUDA", 4: "NB2_ERR_CAPACITY"}

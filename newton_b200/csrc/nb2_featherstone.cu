@@ -648,55 +648,85 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
     __syncwarp(gmask);
     NB2_PHASE();
     // ---- eval_body_contact (penalty), ordered per body over the env's contacts ---------------------------
+    // Two passes per chunk of contacts.  (A) one lane per CONTACT evaluates the penalty force once (the scan-per-body version made
+    // every foot lane evaluate its ~4 contacts one after the other, each behind a chain of dependent global loads) and parks
+    // (f_total, r_a x f_total, r_b x f_total, body pair) in a scratch record; (B) one lane per BODY adds its records in contact order,
+    // side A before side B - the summation order of the reference's serial device, so the result is bit-identical.  The records
+    // live in whichever dead block is larger: H (not formed yet) or v_s / a_s (dead between the RNEA forward pass and the closing FK).
     if (use_contacts) {
-        for (int b = l; b < nb; b += L) {
-            V3 facc = ld3(sm.fe + 6 * b), tacc = ld3(sm.fe + 6 * b + 3);
-            for (int c = 0; c < nc; ++c) {
+        constexpr int CR = 11;  // odd stride: lanes = consecutive contacts hit different banks
+        const int cap_h = M.max_env_H / CR, cap_v = (12 * M.max_env_bodies) / CR;
+        float* crec = cap_h >= cap_v ? sm.H : sm.vs;
+        const int ccap = cap_h >= cap_v ? cap_h : cap_v;  // >= 1: an environment has at least one body
+        for (int cbase = 0; cbase < nc; cbase += ccap) {
+            const int cend = min(nc, cbase + ccap);
+            for (int c = cbase + l; c < cend; c += L) {
                 const int s = slot0 + c;
                 const int ba = __float_as_int(cb[CF_BODY_A * T + s]), bb = __float_as_int(cb[CF_BODY_B * T + s]);
-                if (ba != b && bb != b) continue;
-                const float ke = cb[CF_KE * T + s], kd = cb[CF_KD * T + s], kf = cb[CF_KF * T + s], ka = cb[CF_KA * T + s], mu = cb[CF_MU * T + s];
-                const V3 n = -V3(cb[CF_NX * T + s], cb[CF_NY * T + s], cb[CF_NZ * T + s]);
-                V3 bx_a(cb[CF_P0X * T + s], cb[CF_P0Y * T + s], cb[CF_P0Z * T + s]);
-                V3 bx_b(cb[CF_P1X * T + s], cb[CF_P1Y * T + s], cb[CF_P1Z * T + s]);
-                V3 r_a, r_b;
-                if (ba >= 0) {
-                    const Xf X = ldx(sm.bq + 7 * ba);
-                    bx_a = xpoint(X, bx_a) - cb[CF_MARGIN0 * T + s] * n;
-                    r_a = bx_a - xpoint(X, ld3(d.body_com + 3 * (b0 + ba)));
-                }
-                if (bb >= 0) {
-                    const Xf X = ldx(sm.bq + 7 * bb);
-                    bx_b = xpoint(X, bx_b) + cb[CF_MARGIN1 * T + s] * n;
-                    r_b = bx_b - xpoint(X, ld3(d.body_com + 3 * (b0 + bb)));
-                }
-                const float dd = dot(n, bx_a - bx_b);
-                if (dd >= ka) continue;
-                V3 bv_a, bv_b;
-                if (ba >= 0) bv_a = ld3(sm.qdfk + 6 * ba) + cross(ld3(sm.qdfk + 6 * ba + 3), r_a);
-                if (bb >= 0) bv_b = ld3(sm.qdfk + 6 * bb) + cross(ld3(sm.qdfk + 6 * bb + 3), r_b);
-                const V3 v = bv_a - bv_b;
-                const float vn = dot(n, v);
-                const V3 vt = v - n * vn;
-                const float fn = dd * ke;
-                const float fd = fmin_w(vn, 0.0f) * kd * (dd < 0.0f ? 1.0f : 0.0f);
-                V3 ft;
-                if (dd < 0.0f) {
-                    const float a2 = dot(vt, vt), delta = P.friction_smoothing;
-                    const float vs = (a2 <= delta * delta) ? 0.5f * a2 : delta * (sqrtf(a2) - 0.5f * delta);
-                    if (vs > 0.0f) {
-                        const V3 fr = vt / vs;
-                        ft = fr * fmin_w(kf * vs, -mu * (fn + fd));
+                float* rec = crec + (c - cbase) * CR;
+                int code = 0;
+                if (ba >= 0 || bb >= 0) {
+                    const float ke = cb[CF_KE * T + s], kd = cb[CF_KD * T + s], kf = cb[CF_KF * T + s], ka = cb[CF_KA * T + s], mu = cb[CF_MU * T + s];
+                    const V3 n = -V3(cb[CF_NX * T + s], cb[CF_NY * T + s], cb[CF_NZ * T + s]);
+                    V3 bx_a(cb[CF_P0X * T + s], cb[CF_P0Y * T + s], cb[CF_P0Z * T + s]);
+                    V3 bx_b(cb[CF_P1X * T + s], cb[CF_P1Y * T + s], cb[CF_P1Z * T + s]);
+                    V3 r_a, r_b;
+                    if (ba >= 0) {
+                        const Xf X = ldx(sm.bq + 7 * ba);
+                        bx_a = xpoint(X, bx_a) - cb[CF_MARGIN0 * T + s] * n;
+                        r_a = bx_a - xpoint(X, ld3(d.body_com + 3 * (b0 + ba)));
+                    }
+                    if (bb >= 0) {
+                        const Xf X = ldx(sm.bq + 7 * bb);
+                        bx_b = xpoint(X, bx_b) + cb[CF_MARGIN1 * T + s] * n;
+                        r_b = bx_b - xpoint(X, ld3(d.body_com + 3 * (b0 + bb)));
+                    }
+                    const float dd = dot(n, bx_a - bx_b);
+                    if (dd < ka) {
+                        V3 bv_a, bv_b;
+                        if (ba >= 0) bv_a = ld3(sm.qdfk + 6 * ba) + cross(ld3(sm.qdfk + 6 * ba + 3), r_a);
+                        if (bb >= 0) bv_b = ld3(sm.qdfk + 6 * bb) + cross(ld3(sm.qdfk + 6 * bb + 3), r_b);
+                        const V3 v = bv_a - bv_b;
+                        const float vn = dot(n, v);
+                        const V3 vt = v - n * vn;
+                        const float fn = dd * ke;
+                        const float fd = fmin_w(vn, 0.0f) * kd * (dd < 0.0f ? 1.0f : 0.0f);
+                        V3 ft;
+                        if (dd < 0.0f) {
+                            const float a2 = dot(vt, vt), delta = P.friction_smoothing;
+                            const float vs = (a2 <= delta * delta) ? 0.5f * a2 : delta * (sqrtf(a2) - 0.5f * delta);
+                            if (vs > 0.0f) {
+                                const V3 fr = vt / vs;
+                                ft = fr * fmin_w(kf * vs, -mu * (fn + fd));
+                            }
+                        }
+                        const V3 f_total = n * (fn + fd) + ft;
+                        st3(rec, f_total);
+                        st3(rec + 3, cross(r_a, f_total));
+                        st3(rec + 6, cross(r_b, f_total));
+                        code = (ba + 1) | ((bb + 1) << 16);
                     }
                 }
-                const V3 f_total = n * (fn + fd) + ft;
-                if (ba == b) { facc -= f_total; tacc -= cross(r_a, f_total); }
-                if (bb == b) { facc += f_total; tacc += cross(r_b, f_total); }
+                reinterpret_cast<int*>(rec)[9] = code;  // 0 = no contribution (beyond the adhesion distance / no body)
             }
-            st3(sm.fe + 6 * b, facc);
-            st3(sm.fe + 6 * b + 3, tacc);
+            __syncwarp(gmask);
+            for (int b = l; b < nb; b += L) {
+                V3 facc = ld3(sm.fe + 6 * b), tacc = ld3(sm.fe + 6 * b + 3);
+                bool any = false;
+                for (int c = 0; c < cend - cbase; ++c) {
+                    const float* rec = crec + c * CR;
+                    const int code = reinterpret_cast<const int*>(rec)[9];
+                    const int ba = (code & 0xffff) - 1, bb = (code >> 16) - 1;
+                    if (ba == b) { facc -= ld3(rec); tacc -= ld3(rec + 3); any = true; }
+                    if (bb == b) { facc += ld3(rec); tacc += ld3(rec + 6); any = true; }
+                }
+                if (any) {
+                    st3(sm.fe + 6 * b, facc);
+                    st3(sm.fe + 6 * b + 3, tacc);
+                }
+            }
+            __syncwarp(gmask);
         }
-        __syncwarp(gmask);
     }
     // zero_kinematic_body_forces (featherstone/kernels.py:55-63): a kinematic body ignores body_f, joint wrenches and contacts
     for (int b = l; b < nb; b += L)
@@ -835,6 +865,23 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
             const signed char* row_col = M.hb_row_col + M.art_hb_row_start[art];
             const signed char* dofj = M.dof_joint + ad0;
             const float* Sart = sm.S + 6 * (ad0 - d0);
+            // The schedule tables are per articulation, i.e. every environment reads its own copy: inside the batch loop each
+            // lookup was a dependent global load (7 % of the stall samples, profiles/r2o_featherstone_step_kernel_hot_lines.txt).
+            // They are staged once - row masks, then the two byte tables - in the dead v_s / a_s block when they fit.
+            const int words_body = (nbatch * anj + 3) >> 2, words_row = (nbatch * n + 3) >> 2;
+            const bool staged = 2 * n + words_body + words_row <= 12 * M.max_env_bodies;
+            const unsigned long long* row_mask = nullptr;  // staged: descendant mask of the joint of dof `ra`
+            if (staged) {
+                unsigned long long* sm_mask = reinterpret_cast<unsigned long long*>(sm.vs);
+                signed char* sm_body = reinterpret_cast<signed char*>(sm.vs + 2 * n);
+                signed char* sm_row = sm_body + 4 * words_body;
+                for (int i = l; i < n; i += L) sm_mask[i] = M.joint_desc_mask[aj0 + dofj[i]];
+                for (int i = l; i < nbatch * anj; i += L) sm_body[i] = body_col[i];
+                for (int i = l; i < nbatch * n; i += L) sm_row[i] = row_col[i];
+                row_mask = sm_mask;
+                body_col = sm_body;
+                row_col = sm_row;
+            }
             __syncwarp(gmask);
             for (int t = 0; t < nbatch; ++t) {
                 float* Pb = (t & 1) ? sm.fe : sm.P;
@@ -858,7 +905,7 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
                     if (col < 0) continue;
                     const S6 Sa = ld6(Sart + 6 * ra);
                     float sum = 0.0f;
-                    for (unsigned long long m = M.joint_desc_mask[aj0 + dofj[ra]]; m; m &= m - 1ull) {
+                    for (unsigned long long m = staged ? row_mask[ra] : M.joint_desc_mask[aj0 + dofj[ra]]; m; m &= m - 1ull) {
                         const int i = __ffsll((long long)m) - 1;
 #pragma unroll
                         for (int r = 0; r < 6; ++r) sum += Sa.v[r] * Pb[6 * i + r];
@@ -868,11 +915,17 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
             }
             }  // !TILE
             __syncwarp(gmask);
+            // joint_armature_effective (solver_featherstone.py:269-281): 1e10 on the dofs of a joint driving a kinematic body.  The
+            // reference adds it to the diagonal first thing in column jn; adding it here for all columns at once is the same sum
+            // without a three-deep dependent global load in each of the n serial column steps.
+            for (int i = l; i < n; i += L) {
+                const bool kin_dof = (d.body_flags[jchild[aj0 + M.dof_joint[ad0 + i]]] & 2) != 0;
+                H[i * n + i] = H[i * n + i] + (kin_dof ? 1.0e10f : d.joint_armature[ad0 + i]);
+            }
+            __syncwarp(gmask);
             // dense_cholesky (kernels.py:1690-1719), in place on the lower triangle; columns in order, rows in parallel
             for (int jn = 0; jn < n; ++jn) {
-                // joint_armature_effective (solver_featherstone.py:269-281): 1e10 on the dofs of a joint driving a kinematic body
-                const bool kin_dof = (d.body_flags[jchild[aj0 + M.dof_joint[ad0 + jn]]] & 2) != 0;
-                float sdiag = H[jn * n + jn] + (kin_dof ? 1.0e10f : d.joint_armature[ad0 + jn]);
+                float sdiag = H[jn * n + jn];
                 for (int k = 0; k < jn; ++k) {
                     const float r = H[jn * n + k];
                     sdiag -= r * r;
