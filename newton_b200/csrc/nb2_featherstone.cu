@@ -923,24 +923,34 @@ featherstone_step_kernel(DevModel M, nb2_featherstone_params P, nb2_state_view s
                 H[i * n + i] = H[i * n + i] + (kin_dof ? 1.0e10f : d.joint_armature[ad0 + i]);
             }
             __syncwarp(gmask);
-            // dense_cholesky (kernels.py:1690-1719), in place on the lower triangle; columns in order, rows in parallel
+            // dense_cholesky (kernels.py:1690-1719), in place on the lower triangle; columns in order, rows in parallel.  Every lane
+            // forms the pivot (same serial sum) next to its own row's entry of the column: the two subtraction chains are independent,
+            // so they share one k loop and overlap.  The pivot is stored one step late - after the group barrier that ends its column -
+            // because lanes still reading H[jn, jn] as the start of their own pivot sum must not see the square root.
+            float pivot = 0.0f;
             for (int jn = 0; jn < n; ++jn) {
+                if (l == 0 && jn > 0) H[(jn - 1) * n + (jn - 1)] = pivot;
+                const int i0 = jn + 1 + l;
                 float sdiag = H[jn * n + jn];
+                float t = i0 < n ? H[i0 * n + jn] : 0.0f;
                 for (int k = 0; k < jn; ++k) {
                     const float r = H[jn * n + k];
                     sdiag -= r * r;
+                    if (i0 < n) t -= H[i0 * n + k] * r;
                 }
                 sdiag = sqrtf(sdiag);
                 const float invS = 1.0f / sdiag;
-                __syncwarp(gmask);
-                for (int i = jn + 1 + l; i < n; i += L) {
-                    float t = H[i * n + jn];
-                    for (int k = 0; k < jn; ++k) t -= H[i * n + k] * H[jn * n + k];
-                    H[i * n + jn] = t * invS;
+                if (i0 < n) H[i0 * n + jn] = t * invS;
+                for (int i = i0 + L; i < n; i += L) {  // more rows than lanes
+                    float t2 = H[i * n + jn];
+                    for (int k = 0; k < jn; ++k) t2 -= H[i * n + k] * H[jn * n + k];
+                    H[i * n + jn] = t2 * invS;
                 }
-                if (l == 0) H[jn * n + jn] = sdiag;
+                pivot = sdiag;
                 __syncwarp(gmask);
             }
+            if (l == 0 && n > 0) H[(n - 1) * n + (n - 1)] = pivot;
+            __syncwarp(gmask);
             for (int e = l; e < n * n; e += L) Lg[e] = H[e];
         } else {
             for (int e = l; e < n * n; e += L) H[e] = Lg[e];
