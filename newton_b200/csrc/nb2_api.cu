@@ -116,6 +116,19 @@ static nb2_status build_tables(nb2_model* m, const nb2_model_desc& d) {
         if (implicit_single) return 0;
         return shape_world[s];
     };
+    std::vector<int> hull_count;
+    {
+        bool any_mesh = false;
+        for (int s = 0; s < S; ++s) any_mesh = any_mesh || shape_type[s] == 8;
+        if (any_mesh) {
+            if (!d.hull_points || !d.shape_hull_start || !d.shape_hull_count) {
+                set_error("MESH shapes need model.hull_points / shape_hull_start / shape_hull_count (the mesh vertex pool)");
+                return NB2_ERR_INVALID_ARGUMENT;
+            }
+            if ((st = fetch(d.shape_hull_count, size_t(S), hull_count))) return st;
+        }
+    }
+    m->has_mesh_pairs = false;
     // ---- pairs: group by env, order shapes by type, sort by the deterministic contact key ----
     struct PairRec { int env; int64_t key; int sa, sb; int max_contacts; };
     std::vector<PairRec> recs;
@@ -132,7 +145,7 @@ static nb2_status build_tables(nb2_model* m, const nb2_model_desc& d) {
         {   // shapes the narrow phase of this library covers: analytic primitives + convex primitives through MPR/GJK
             const int ta = shape_type[sa], tb = shape_type[sb];
             // PLANE SPHERE CAPSULE ELLIPSOID CYLINDER BOX CONE CONVEX_MESH
-            auto known = [](int t) { return t == 1 || (t >= 3 && t <= 7) || t == 9 || t == 10; };
+            auto known = [](int t) { return t == 1 || (t >= 3 && t <= 10); };  // 8 = MESH (plane route only, below)
             if (!known(ta) || !known(tb)) {
                 set_error("shape pair (" + std::to_string(sa) + "," + std::to_string(sb) + "): geometry types " + std::to_string(ta) + "/" +
                           std::to_string(tb) + " are outside the supported set (plane, sphere, capsule, ellipsoid, cylinder, box, cone, "
@@ -143,6 +156,19 @@ static nb2_status build_tables(nb2_model* m, const nb2_model_desc& d) {
                 (!d.hull_points || !d.shape_hull_start || !d.shape_hull_count || !d.shape_collision_aabb_lower || !d.shape_collision_aabb_upper)) {
                 set_error("CONVEX_MESH shapes need model.hull_points / shape_hull_start / shape_hull_count / shape_collision_aabb_lower / _upper");
                 return NB2_ERR_INVALID_ARGUMENT;
+            }
+            if (ta == 8 || tb == 8) {  // mesh routing (narrow_phase.py:594-640)
+                const bool infinite_plane_a = ta == 1 && shape_scale[3 * sa] == 0.0f && shape_scale[3 * sa + 1] == 0.0f;
+                if (!(infinite_plane_a && tb == 8)) {
+                    set_error("shape pair (" + std::to_string(sa) + "," + std::to_string(sb) + "): a MESH shape collides with infinite planes "
+                              "only (one contact per vertex); mesh-mesh / mesh-convex / mesh-finite-plane need the reference's BVH / SDF "
+                              "routes, which are out of scope - filter the pair or use a convex hull");
+                    return NB2_ERR_UNSUPPORTED;
+                }
+                // narrow_phase.py:628: the pair is stored (mesh, plane) - shape_a of its contacts and of their sort key is the mesh
+                m->has_mesh_pairs = true;
+                recs.push_back({env, ((int64_t(sb) & 0xFFFFF) << 43) | ((int64_t(sa) & 0xFFFFF) << 23), sb, sa, hull_count[sb]});
+                continue;
             }
             {   // narrow_phase.py:642-655 + the analytic chain of narrow_phase.py:657-864: everything else is MPR / GJK
                 // (a plane that gets there - cone, barrel cylinder lying on its side - is replaced by a box proxy)
@@ -161,6 +187,7 @@ static nb2_status build_tables(nb2_model* m, const nb2_model_desc& d) {
         return a.env != b.env ? a.env < b.env : a.key < b.key;
     });
     h.env_pair_start.assign(size_t(E) + 1, 0);
+    h.env_slot_start.assign(size_t(E) + 1, 0);
     h.pairs.clear();
     h.pairs.reserve(recs.size());
     {
@@ -175,7 +202,7 @@ static nb2_status build_tables(nb2_model* m, const nb2_model_desc& d) {
                     if (h.global_shapes[g] == s) return nloc + int(g);
                 return -1;
             };
-            int env_max = 0;
+            int env_max = 0, env_slots = 0;
             for (; i < recs.size() && recs[i].env == e; ++i) {
                 env_max += recs[i].max_contacts;
                 m->max_env_contacts = std::max(m->max_env_contacts, env_max);
@@ -184,15 +211,16 @@ static nb2_status build_tables(nb2_model* m, const nb2_model_desc& d) {
                     set_error("contact pair references a shape outside its world");
                     return NB2_ERR_INVALID_ARGUMENT;
                 }
-                h.pairs.push_back(make_int2(a, b));
+                const bool mesh_pair = shape_type[recs[i].sa] == 8;  // (mesh, plane): flagged for the collide kernel
+                h.pairs.push_back(make_int2(a, mesh_pair ? (b | NB2_PAIR_MESH_PLANE) : b));
+                env_slots += mesh_pair ? recs[i].max_contacts : 5;
             }
+            h.env_slot_start[e + 1] = h.env_slot_start[e] + env_slots;
         }
         h.env_pair_start[E] = int(h.pairs.size());
+        h.explicit_env_slot_start = h.env_slot_start;
     }
-    // ---- contact-block slot ranges: 5 slots per pair (<= 4 analytic, <= 5 manifold contacts) ----
-    h.env_slot_start.assign(size_t(E) + 1, 0);
-    for (int e = 0; e < E; ++e)
-        h.env_slot_start[e + 1] = h.env_slot_start[e] + 5 * (h.env_pair_start[e + 1] - h.env_pair_start[e]);
+    // (contact-block slot ranges: 5 slots per pair - <= 4 analytic, <= 5 manifold contacts - and one per vertex of a mesh-plane pair)
     // ---- per-body joint adjacency in joint order (parent entry before child entry of the same joint) ----
     h.body_joint_start.assign(size_t(B) + 1, 0);
     for (int j = 0; j < J; ++j) {
@@ -365,6 +393,7 @@ static nb2_status build_tables(nb2_model* m, const nb2_model_desc& d) {
         dv.max_env_contact_slots = std::max(dv.max_env_contact_slots, h.env_slot_start[e + 1] - h.env_slot_start[e]);
     }
     dv.slot_total = h.env_slot_start[E];
+    dv.has_mesh_pairs = m->has_mesh_pairs ? 1 : 0;
     m->lanes_per_env =
         std::min(32, std::max(8, pow2_at_least(std::max({dv.max_env_bodies, dv.max_env_joints, std::min(dv.max_env_pairs, 32)}))));
     {   // small batches cannot fill the GPU with warps: give each environment a full warp so its contact / pair loops need
@@ -508,8 +537,12 @@ static nb2_status configure_broad_phase(nb2_model* m, int mode, int max_pairs, b
     dv.dyn_pairs = nullptr;
     dv.env_dyn_count = nullptr;
     dv.dyn_pair_cap = 0;
+    if (mode != NB2_BROAD_PHASE_EXPLICIT && m->has_mesh_pairs) {
+        set_error("nb2_collide_configure: MESH shapes are supported with the explicit broad phase only");
+        return NB2_ERR_UNSUPPORTED;
+    }
     if (mode == NB2_BROAD_PHASE_EXPLICIT) {
-        for (int e = 0; e < E; ++e) h.env_slot_start[e + 1] = h.env_slot_start[e] + 5 * (h.env_pair_start[e + 1] - h.env_pair_start[e]);
+        h.env_slot_start = h.explicit_env_slot_start;  // 5 per pair, one per vertex for mesh-plane pairs
         m->max_env_contacts = m->explicit_max_env_contacts;
         m->has_convex_pairs = m->explicit_has_convex_pairs;
     } else {

@@ -25,7 +25,7 @@
 
 namespace nb2 {
 
-enum { GEO_PLANE = 1, GEO_SPHERE = 3, GEO_CAPSULE = 4, GEO_ELLIPSOID = 5, GEO_CYLINDER = 6, GEO_BOX = 7, GEO_CONE = 9, GEO_CONVEX_MESH = 10 };
+enum { GEO_PLANE = 1, GEO_SPHERE = 3, GEO_CAPSULE = 4, GEO_ELLIPSOID = 5, GEO_CYLINDER = 6, GEO_BOX = 7, GEO_MESH = 8, GEO_CONE = 9, GEO_CONVEX_MESH = 10 };
 #define NB2_MAXVAL 1.0e10f
 
 // ---- analytic colliders --------------------------------------------------------------------------
@@ -220,7 +220,7 @@ NB2_DEV void shape_aabb(int type, V3 scale, const Xf& X, float gap_eff, float co
     V3 pos = X.p;
     V3 mvv(gap_eff, gap_eff, gap_eff);
     V3 he;
-    if (type == GEO_CONVEX_MESH) {  // has_local_aabb (collide.py:420-444): the builder's scaled local AABB rotated into the world
+    if (type == GEO_CONVEX_MESH || type == GEO_MESH) {  // has_local_aabb (collide.py:348, 420-444): the builder's scaled local AABB rotated into the world
         const V3 center = (local_lo + local_hi) * 0.5f, half = (local_hi - local_lo) * 0.5f;
         const V3 wc = qrot(X.q, center) + pos;
         const V3 r0 = qrot(X.q, V3(1.f, 0.f, 0.f)), r1 = qrot(X.q, V3(0.f, 1.f, 0.f)), r2 = qrot(X.q, V3(0.f, 0.f, 1.f));
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(32 * WARPS) collide_kernel(DevModel M, const f
         V3 lo, hi;
         const int stype = d.shape_type[sid];
         V3 llo, lhi;
-        if (stype == GEO_CONVEX_MESH) {
+        if (stype == GEO_CONVEX_MESH || stype == GEO_MESH) {
             llo = ld3(d.shape_collision_aabb_lower + 3 * sid);
             lhi = ld3(d.shape_collision_aabb_upper + 3 * sid);
         }
@@ -497,8 +497,11 @@ __global__ void __launch_bounds__(32 * WARPS) collide_kernel(DevModel M, const f
         V3 cpos[5], cnorm[5];
         int sa = 0, sb = 0;
         float reff_a = 0.f, reff_b = 0.f, marg_a = 0.f, marg_b = 0.f;
+        int mesh_a = -1, mesh_b = -1;  // slots of an overlapping (mesh, infinite plane) pair: handled by the whole group below
         if (live && p < np) {
             int2 pr = M.dyn_pairs ? M.dyn_pairs[ps + p] : M.pairs[ps + p];
+            const bool mesh_pair = CONVEX && (pr.y & NB2_PAIR_MESH_PLANE) != 0;  // explicit list only (nb2_model_create)
+            pr.y &= ~NB2_PAIR_MESH_PLANE;
             V3 alo = ld3(slots[pr.x].lo), ahi = ld3(slots[pr.x].hi), blo = ld3(slots[pr.y].lo), bhi = ld3(slots[pr.y].hi);
             bool overlap = alo.x <= bhi.x && ahi.x >= blo.x && alo.y <= bhi.y && ahi.y >= blo.y && alo.z <= bhi.z && ahi.z >= blo.z;
             if (CONVEX && spec_mode == 2)  // swept test over the relative displacement (the explicit sweep passes (s1, s2) = the stored pair)
@@ -509,6 +512,11 @@ __global__ void __launch_bounds__(32 * WARPS) collide_kernel(DevModel M, const f
                 const int b1 = d.shape_body[s1], b2 = d.shape_body[s2];
                 const bool im1 = b1 < 0 || (d.body_flags[b1] & 2) != 0, im2 = b2 < 0 || (d.body_flags[b2] & 2) != 0;
                 if (im1 && im2) overlap = false;
+            }
+            if (CONVEX && overlap && mesh_pair) {
+                mesh_a = pr.x;
+                mesh_b = pr.y;
+                overlap = false;
             }
             if (overlap) {
                 sa = pr.x < nloc ? ss + pr.x : M.global_shapes[pr.x - nloc];
@@ -627,116 +635,200 @@ __global__ void __launch_bounds__(32 * WARPS) collide_kernel(DevModel M, const f
                 }
             }
         }
-        const int cnt = __popc(vmask);
-        // segmented exclusive scan of cnt over the L lanes of this group
-        int incl = cnt;
+        // A round's contacts leave in pair order.  A (mesh, plane) pair emits one contact per vertex - far more than a lane's five
+        // candidates - so the round is cut into segments at the mesh lanes: [staged pairs][mesh pair k][staged pairs] ..., each written
+        // behind the previous one.  Rounds without mesh pairs (every round of the analytic-only instantiation) are one segment.
+        unsigned mesh_lanes = 0;
+        int nseg = 1;
+        if (CONVEX && M.has_mesh_pairs) {
+            mesh_lanes = (__ballot_sync(0xffffffffu, mesh_a >= 0) >> (grp * L)) & (L == 32 ? 0xffffffffu : ((1u << L) - 1u));
+            nseg = 1 + __popc(mesh_lanes);
 #pragma unroll
-        for (int o = 1; o < L; o <<= 1) {
-            int v = __shfl_up_sync(0xffffffffu, incl, o, L);
-            if (l >= o) incl += v;
+            for (int o = 16; o >= L; o >>= 1) nseg = max(nseg, __shfl_xor_sync(0xffffffffu, nseg, o));  // warp-uniform trip count
         }
-        const int total = __shfl_sync(0xffffffffu, incl, L - 1, L);
-        int slot = slot0 + n_total + (incl - cnt);
-        if (stage_c) {
-            if (cnt > 0) {
-                StagePair& sp = stage_p[l];
-                sp.sa = sa; sp.sb = sb;
-                sp.reff_a = reff_a; sp.reff_b = reff_b; sp.marg_a = marg_a; sp.marg_b = marg_b;
-                int k = incl - cnt;
-#pragma unroll
-                for (int i = 0; i < 5; ++i) {
-                    if (!(vmask & (1u << i))) continue;
-                    StageContact& sc = stage_c[k++];
-                    st3(sc.center, cpos[i]);
-                    st3(sc.normal, cnorm[i]);
-                    sc.dist = cdist[i];
-                    sc.pair_lane = l;
-                }
+        int seg_lo = 0;
+        for (int seg = 0; seg < nseg; ++seg) {
+            const int seg_hi = mesh_lanes ? __ffs(mesh_lanes) - 1 : L;  // next mesh lane of this group, or the end of the round
+            const int cnt = (l >= seg_lo && l < seg_hi) ? __popc(vmask) : 0;
+            // segmented exclusive scan of cnt over the L lanes of this group
+            int incl = cnt;
+    #pragma unroll
+            for (int o = 1; o < L; o <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, o, L);
+                if (l >= o) incl += v;
             }
-            __syncwarp();
-            float* cb = M.cb;
-            const size_t T = size_t(M.slot_total);
-            for (int c = l; c < total; c += L) {
-                const StageContact& sc = stage_c[c];
-                const StagePair& sp = stage_p[sc.pair_lane];
-                const int psa = sp.sa, psb = sp.sb;
-                const float ra = sp.reff_a, rb = sp.reff_b;
-                const int body0 = d.shape_body[psa], body1 = d.shape_body[psb];
+            const int total = __shfl_sync(0xffffffffu, incl, L - 1, L);
+            int slot = slot0 + n_total + (incl - cnt);
+            if (stage_c) {
+                if (cnt > 0) {
+                    StagePair& sp = stage_p[l];
+                    sp.sa = sa; sp.sb = sb;
+                    sp.reff_a = reff_a; sp.reff_b = reff_b; sp.marg_a = marg_a; sp.marg_b = marg_b;
+                    int k = incl - cnt;
+    #pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        if (!(vmask & (1u << i))) continue;
+                        StageContact& sc = stage_c[k++];
+                        st3(sc.center, cpos[i]);
+                        st3(sc.normal, cnorm[i]);
+                        sc.dist = cdist[i];
+                        sc.pair_lane = l;
+                    }
+                }
+                __syncwarp();
+                float* cb = M.cb;
+                const size_t T = size_t(M.slot_total);
+                for (int c = l; c < total; c += L) {
+                    const StageContact& sc = stage_c[c];
+                    const StagePair& sp = stage_p[sc.pair_lane];
+                    const int psa = sp.sa, psb = sp.sb;
+                    const float ra = sp.reff_a, rb = sp.reff_b;
+                    const int body0 = d.shape_body[psa], body1 = d.shape_body[psb];
+                    const Xf Xbw_a = body0 == -1 ? Xf() : xinv(ldx(body_q + 7 * body0));
+                    const Xf Xbw_b = body1 == -1 ? Xf() : xinv(ldx(body_q + 7 * body1));
+                    const int o = slot0 + n_total + c;
+                    // write_contact (collide.py:210-254): world contact -> body-frame points / offsets
+                    const V3 n = unit(ld3(sc.normal)), center = ld3(sc.center);
+                    const V3 a_w = center - n * (0.5f * sc.dist + ra);
+                    const V3 b_w = center + n * (0.5f * sc.dist + rb);
+                    const float om_a = ra + sp.marg_a, om_b = rb + sp.marg_b;
+                    const V3 p0 = xpoint(Xbw_a, a_w), p1 = xpoint(Xbw_b, b_w);
+                    const V3 o0 = xvec(Xbw_a, om_a * n), o1 = xvec(Xbw_b, -om_b * n);
+                    cb[CF_BODY_A * T + o] = __int_as_float(body0 >= 0 ? body0 - bs : -1);
+                    cb[CF_BODY_B * T + o] = __int_as_float(body1 >= 0 ? body1 - bs : -1);
+                    cb[CF_SHAPE0 * T + o] = __int_as_float(psa);
+                    cb[CF_SHAPE1 * T + o] = __int_as_float(psb);
+                    cb[CF_P0X * T + o] = p0.x; cb[CF_P0Y * T + o] = p0.y; cb[CF_P0Z * T + o] = p0.z;
+                    cb[CF_P1X * T + o] = p1.x; cb[CF_P1Y * T + o] = p1.y; cb[CF_P1Z * T + o] = p1.z;
+                    cb[CF_O0X * T + o] = o0.x; cb[CF_O0Y * T + o] = o0.y; cb[CF_O0Z * T + o] = o0.z;
+                    cb[CF_O1X * T + o] = o1.x; cb[CF_O1Y * T + o] = o1.y; cb[CF_O1Z * T + o] = o1.z;
+                    cb[CF_NX * T + o] = n.x; cb[CF_NY * T + o] = n.y; cb[CF_NZ * T + o] = n.z;
+                    cb[CF_MARGIN0 * T + o] = om_a;
+                    cb[CF_MARGIN1 * T + o] = om_b;
+                    cb[CF_MU * T + o] = (d.shape_material_mu[psa] + d.shape_material_mu[psb]) / 2.0f;
+                    cb[CF_MU_TORSIONAL * T + o] = (d.shape_material_mu_torsional[psa] + d.shape_material_mu_torsional[psb]) / 2.0f;
+                    cb[CF_MU_ROLLING * T + o] = (d.shape_material_mu_rolling[psa] + d.shape_material_mu_rolling[psb]) / 2.0f;
+                    cb[CF_KE * T + o] = 0.5f * (d.shape_material_ke[psa] + d.shape_material_ke[psb]);
+                    cb[CF_KD * T + o] = 0.5f * (d.shape_material_kd[psa] + d.shape_material_kd[psb]);
+                    cb[CF_KF * T + o] = 0.5f * (d.shape_material_kf[psa] + d.shape_material_kf[psb]);
+                    cb[CF_KA * T + o] = 0.5f * (d.shape_material_ka[psa] + d.shape_material_ka[psb]);
+                }
+                __syncwarp();  // the staging area is rewritten in the next round
+            } else if (cnt > 0) {
+                const int body0 = d.shape_body[sa], body1 = d.shape_body[sb];
                 const Xf Xbw_a = body0 == -1 ? Xf() : xinv(ldx(body_q + 7 * body0));
                 const Xf Xbw_b = body1 == -1 ? Xf() : xinv(ldx(body_q + 7 * body1));
-                const int o = slot0 + n_total + c;
-                // write_contact (collide.py:210-254): world contact -> body-frame points / offsets
-                const V3 n = unit(ld3(sc.normal)), center = ld3(sc.center);
-                const V3 a_w = center - n * (0.5f * sc.dist + ra);
-                const V3 b_w = center + n * (0.5f * sc.dist + rb);
-                const float om_a = ra + sp.marg_a, om_b = rb + sp.marg_b;
-                const V3 p0 = xpoint(Xbw_a, a_w), p1 = xpoint(Xbw_b, b_w);
-                const V3 o0 = xvec(Xbw_a, om_a * n), o1 = xvec(Xbw_b, -om_b * n);
-                cb[CF_BODY_A * T + o] = __int_as_float(body0 >= 0 ? body0 - bs : -1);
-                cb[CF_BODY_B * T + o] = __int_as_float(body1 >= 0 ? body1 - bs : -1);
-                cb[CF_SHAPE0 * T + o] = __int_as_float(psa);
-                cb[CF_SHAPE1 * T + o] = __int_as_float(psb);
-                cb[CF_P0X * T + o] = p0.x; cb[CF_P0Y * T + o] = p0.y; cb[CF_P0Z * T + o] = p0.z;
-                cb[CF_P1X * T + o] = p1.x; cb[CF_P1Y * T + o] = p1.y; cb[CF_P1Z * T + o] = p1.z;
-                cb[CF_O0X * T + o] = o0.x; cb[CF_O0Y * T + o] = o0.y; cb[CF_O0Z * T + o] = o0.z;
-                cb[CF_O1X * T + o] = o1.x; cb[CF_O1Y * T + o] = o1.y; cb[CF_O1Z * T + o] = o1.z;
-                cb[CF_NX * T + o] = n.x; cb[CF_NY * T + o] = n.y; cb[CF_NZ * T + o] = n.z;
-                cb[CF_MARGIN0 * T + o] = om_a;
-                cb[CF_MARGIN1 * T + o] = om_b;
-                cb[CF_MU * T + o] = (d.shape_material_mu[psa] + d.shape_material_mu[psb]) / 2.0f;
-                cb[CF_MU_TORSIONAL * T + o] = (d.shape_material_mu_torsional[psa] + d.shape_material_mu_torsional[psb]) / 2.0f;
-                cb[CF_MU_ROLLING * T + o] = (d.shape_material_mu_rolling[psa] + d.shape_material_mu_rolling[psb]) / 2.0f;
-                cb[CF_KE * T + o] = 0.5f * (d.shape_material_ke[psa] + d.shape_material_ke[psb]);
-                cb[CF_KD * T + o] = 0.5f * (d.shape_material_kd[psa] + d.shape_material_kd[psb]);
-                cb[CF_KF * T + o] = 0.5f * (d.shape_material_kf[psa] + d.shape_material_kf[psb]);
-                cb[CF_KA * T + o] = 0.5f * (d.shape_material_ka[psa] + d.shape_material_ka[psb]);
+                const float mu = (d.shape_material_mu[sa] + d.shape_material_mu[sb]) / 2.0f;
+                const float mut = (d.shape_material_mu_torsional[sa] + d.shape_material_mu_torsional[sb]) / 2.0f;
+                const float mur = (d.shape_material_mu_rolling[sa] + d.shape_material_mu_rolling[sb]) / 2.0f;
+                const float ke = 0.5f * (d.shape_material_ke[sa] + d.shape_material_ke[sb]);
+                const float kd = 0.5f * (d.shape_material_kd[sa] + d.shape_material_kd[sb]);
+                const float kf = 0.5f * (d.shape_material_kf[sa] + d.shape_material_kf[sb]);
+                const float ka = 0.5f * (d.shape_material_ka[sa] + d.shape_material_ka[sb]);
+                float* cb = M.cb;
+                const size_t T = size_t(M.slot_total);
+    #pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    if (!(vmask & (1u << i))) continue;
+                    // write_contact (collide.py:210-254): world contact -> body-frame points / offsets
+                    V3 n = unit(cnorm[i]);
+                    V3 a_w = cpos[i] - n * (0.5f * cdist[i] + reff_a);
+                    V3 b_w = cpos[i] + n * (0.5f * cdist[i] + reff_b);
+                    float om_a = reff_a + marg_a, om_b = reff_b + marg_b;
+                    V3 p0 = xpoint(Xbw_a, a_w), p1 = xpoint(Xbw_b, b_w);
+                    V3 o0 = xvec(Xbw_a, om_a * n), o1 = xvec(Xbw_b, -om_b * n);
+                    cb[CF_BODY_A * T + slot] = __int_as_float(body0 >= 0 ? body0 - bs : -1);
+                    cb[CF_BODY_B * T + slot] = __int_as_float(body1 >= 0 ? body1 - bs : -1);
+                    cb[CF_SHAPE0 * T + slot] = __int_as_float(sa);
+                    cb[CF_SHAPE1 * T + slot] = __int_as_float(sb);
+                    cb[CF_P0X * T + slot] = p0.x; cb[CF_P0Y * T + slot] = p0.y; cb[CF_P0Z * T + slot] = p0.z;
+                    cb[CF_P1X * T + slot] = p1.x; cb[CF_P1Y * T + slot] = p1.y; cb[CF_P1Z * T + slot] = p1.z;
+                    cb[CF_O0X * T + slot] = o0.x; cb[CF_O0Y * T + slot] = o0.y; cb[CF_O0Z * T + slot] = o0.z;
+                    cb[CF_O1X * T + slot] = o1.x; cb[CF_O1Y * T + slot] = o1.y; cb[CF_O1Z * T + slot] = o1.z;
+                    cb[CF_NX * T + slot] = n.x; cb[CF_NY * T + slot] = n.y; cb[CF_NZ * T + slot] = n.z;
+                    cb[CF_MARGIN0 * T + slot] = om_a;
+                    cb[CF_MARGIN1 * T + slot] = om_b;
+                    cb[CF_MU * T + slot] = mu;
+                    cb[CF_MU_TORSIONAL * T + slot] = mut;
+                    cb[CF_MU_ROLLING * T + slot] = mur;
+                    cb[CF_KE * T + slot] = ke;
+                    cb[CF_KD * T + slot] = kd;
+                    cb[CF_KF * T + slot] = kf;
+                    cb[CF_KA * T + slot] = ka;
+                    slot += 1;
+                }
             }
-            __syncwarp();  // the staging area is rewritten in the next round
-        } else if (cnt > 0) {
-            const int body0 = d.shape_body[sa], body1 = d.shape_body[sb];
-            const Xf Xbw_a = body0 == -1 ? Xf() : xinv(ldx(body_q + 7 * body0));
-            const Xf Xbw_b = body1 == -1 ? Xf() : xinv(ldx(body_q + 7 * body1));
-            const float mu = (d.shape_material_mu[sa] + d.shape_material_mu[sb]) / 2.0f;
-            const float mut = (d.shape_material_mu_torsional[sa] + d.shape_material_mu_torsional[sb]) / 2.0f;
-            const float mur = (d.shape_material_mu_rolling[sa] + d.shape_material_mu_rolling[sb]) / 2.0f;
-            const float ke = 0.5f * (d.shape_material_ke[sa] + d.shape_material_ke[sb]);
-            const float kd = 0.5f * (d.shape_material_kd[sa] + d.shape_material_kd[sb]);
-            const float kf = 0.5f * (d.shape_material_kf[sa] + d.shape_material_kf[sb]);
-            const float ka = 0.5f * (d.shape_material_ka[sa] + d.shape_material_ka[sb]);
-            float* cb = M.cb;
-            const size_t T = size_t(M.slot_total);
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                if (!(vmask & (1u << i))) continue;
-                // write_contact (collide.py:210-254): world contact -> body-frame points / offsets
-                V3 n = unit(cnorm[i]);
-                V3 a_w = cpos[i] - n * (0.5f * cdist[i] + reff_a);
-                V3 b_w = cpos[i] + n * (0.5f * cdist[i] + reff_b);
-                float om_a = reff_a + marg_a, om_b = reff_b + marg_b;
-                V3 p0 = xpoint(Xbw_a, a_w), p1 = xpoint(Xbw_b, b_w);
-                V3 o0 = xvec(Xbw_a, om_a * n), o1 = xvec(Xbw_b, -om_b * n);
-                cb[CF_BODY_A * T + slot] = __int_as_float(body0 >= 0 ? body0 - bs : -1);
-                cb[CF_BODY_B * T + slot] = __int_as_float(body1 >= 0 ? body1 - bs : -1);
-                cb[CF_SHAPE0 * T + slot] = __int_as_float(sa);
-                cb[CF_SHAPE1 * T + slot] = __int_as_float(sb);
-                cb[CF_P0X * T + slot] = p0.x; cb[CF_P0Y * T + slot] = p0.y; cb[CF_P0Z * T + slot] = p0.z;
-                cb[CF_P1X * T + slot] = p1.x; cb[CF_P1Y * T + slot] = p1.y; cb[CF_P1Z * T + slot] = p1.z;
-                cb[CF_O0X * T + slot] = o0.x; cb[CF_O0Y * T + slot] = o0.y; cb[CF_O0Z * T + slot] = o0.z;
-                cb[CF_O1X * T + slot] = o1.x; cb[CF_O1Y * T + slot] = o1.y; cb[CF_O1Z * T + slot] = o1.z;
-                cb[CF_NX * T + slot] = n.x; cb[CF_NY * T + slot] = n.y; cb[CF_NZ * T + slot] = n.z;
-                cb[CF_MARGIN0 * T + slot] = om_a;
-                cb[CF_MARGIN1 * T + slot] = om_b;
-                cb[CF_MU * T + slot] = mu;
-                cb[CF_MU_TORSIONAL * T + slot] = mut;
-                cb[CF_MU_ROLLING * T + slot] = mur;
-                cb[CF_KE * T + slot] = ke;
-                cb[CF_KD * T + slot] = kd;
-                cb[CF_KF * T + slot] = kf;
-                cb[CF_KA * T + slot] = ka;
-                slot += 1;
+            n_total += total;
+            if (CONVEX && seg_hi < L) {
+                // ---- mesh vs infinite plane (narrow_phase.py:1761-1861, reduce_contacts=False): the group walks the vertices L at a
+                // time; a vertex within gap + margin of the plane is a contact (shape_a = mesh, normal mesh -> plane), kept in vertex order
+                const int ma = __shfl_sync(gmask, mesh_a, seg_hi, L), mb = __shfl_sync(gmask, mesh_b, seg_hi, L);
+                const int msa = ma < nloc ? ss + ma : M.global_shapes[ma - nloc], psb = mb < nloc ? ss + mb : M.global_shapes[mb - nloc];
+                const Xf Xm = ldx(slots[ma].x), Xp = ldx(slots[mb].x);
+                const Xf Xp_inv = xinv(Xp);
+                const V3 pn = xvec(Xp, V3(0.f, 0.f, 1.f));
+                const V3 mscale = ld3(d.shape_scale + 3 * msa);
+                const float marg_m = d.shape_margin[msa], marg_p = d.shape_margin[psb];
+                const float gap_sum = d.shape_gap[msa] + d.shape_gap[psb];
+                const float* verts = d.hull_points + 3 * size_t(d.shape_hull_start[msa]);
+                const int nv = d.shape_hull_count[msa];
+                const int body0 = d.shape_body[msa], body1 = d.shape_body[psb];
+                const Xf Xbw_a = body0 == -1 ? Xf() : xinv(ldx(body_q + 7 * body0));
+                const Xf Xbw_b = body1 == -1 ? Xf() : xinv(ldx(body_q + 7 * body1));
+                float* cb = M.cb;
+                const size_t T = size_t(M.slot_total);
+                int written = 0;
+                for (int v0 = 0; v0 < nv; v0 += L) {
+                    const int vi = v0 + l;
+                    bool hit = false;
+                    V3 a_w, b_w, n;
+                    if (vi < nv) {
+                        const V3 vw = xpoint(Xm, cmul(ld3(verts + 3 * vi), mscale));
+                        const V3 ip = xpoint(Xp_inv, vw);
+                        const V3 on_plane = xpoint(Xp, V3(ip.x, ip.y, 0.0f));
+                        const float dist = dot(vw - on_plane, pn);
+                        if (dist < gap_sum + (marg_m + marg_p)) {
+                            // write_contact with its own gap test (collide.py:210-254; radius_eff = 0)
+                            const V3 center = (vw + on_plane) * 0.5f;
+                            n = unit(-pn);
+                            a_w = center - n * (0.5f * dist + 0.0f);
+                            b_w = center + n * (0.5f * dist + 0.0f);
+                            const float dd = dot(b_w - a_w, n) - (0.0f + 0.0f + marg_m + marg_p);
+                            hit = !(dd > gap_sum);
+                        }
+                    }
+                    const unsigned hits = (__ballot_sync(gmask, hit) >> (grp * L)) & (L == 32 ? 0xffffffffu : ((1u << L) - 1u));
+                    if (hit) {
+                        const int o = slot0 + n_total + written + __popc(hits & ((1u << l) - 1u));
+                        const float om_a = 0.0f + marg_m, om_b = 0.0f + marg_p;
+                        const V3 p0 = xpoint(Xbw_a, a_w), p1 = xpoint(Xbw_b, b_w);
+                        const V3 o0 = xvec(Xbw_a, om_a * n), o1 = xvec(Xbw_b, -om_b * n);
+                        cb[CF_BODY_A * T + o] = __int_as_float(body0 >= 0 ? body0 - bs : -1);
+                        cb[CF_BODY_B * T + o] = __int_as_float(body1 >= 0 ? body1 - bs : -1);
+                        cb[CF_SHAPE0 * T + o] = __int_as_float(msa);
+                        cb[CF_SHAPE1 * T + o] = __int_as_float(psb);
+                        cb[CF_P0X * T + o] = p0.x; cb[CF_P0Y * T + o] = p0.y; cb[CF_P0Z * T + o] = p0.z;
+                        cb[CF_P1X * T + o] = p1.x; cb[CF_P1Y * T + o] = p1.y; cb[CF_P1Z * T + o] = p1.z;
+                        cb[CF_O0X * T + o] = o0.x; cb[CF_O0Y * T + o] = o0.y; cb[CF_O0Z * T + o] = o0.z;
+                        cb[CF_O1X * T + o] = o1.x; cb[CF_O1Y * T + o] = o1.y; cb[CF_O1Z * T + o] = o1.z;
+                        cb[CF_NX * T + o] = n.x; cb[CF_NY * T + o] = n.y; cb[CF_NZ * T + o] = n.z;
+                        cb[CF_MARGIN0 * T + o] = om_a;
+                        cb[CF_MARGIN1 * T + o] = om_b;
+                        cb[CF_MU * T + o] = (d.shape_material_mu[msa] + d.shape_material_mu[psb]) / 2.0f;
+                        cb[CF_MU_TORSIONAL * T + o] = (d.shape_material_mu_torsional[msa] + d.shape_material_mu_torsional[psb]) / 2.0f;
+                        cb[CF_MU_ROLLING * T + o] = (d.shape_material_mu_rolling[msa] + d.shape_material_mu_rolling[psb]) / 2.0f;
+                        cb[CF_KE * T + o] = 0.5f * (d.shape_material_ke[msa] + d.shape_material_ke[psb]);
+                        cb[CF_KD * T + o] = 0.5f * (d.shape_material_kd[msa] + d.shape_material_kd[psb]);
+                        cb[CF_KF * T + o] = 0.5f * (d.shape_material_kf[msa] + d.shape_material_kf[psb]);
+                        cb[CF_KA * T + o] = 0.5f * (d.shape_material_ka[msa] + d.shape_material_ka[psb]);
+                    }
+                    written += __popc(hits);
+                }
+                n_total += written;
             }
+            seg_lo = seg_hi + 1;
+            mesh_lanes &= mesh_lanes - 1;
         }
-        n_total += total;
     }
     if (live && l == 0) M.env_contact_count[env] = n_total;
     if constexpr (!EXPORT) return;
@@ -896,7 +988,7 @@ __global__ void __launch_bounds__(32) broadphase_kernel(DevModel M, const float*
         if (body != -1) X = xmul(ldx(body_q + 7 * body), X);
         const int stype = d.shape_type[sid];
         V3 llo, lhi, lo, hi;
-        if (stype == GEO_CONVEX_MESH) {
+        if (stype == GEO_CONVEX_MESH || stype == GEO_MESH) {
             llo = ld3(d.shape_collision_aabb_lower + 3 * sid);
             lhi = ld3(d.shape_collision_aabb_upper + 3 * sid);
         }
@@ -1387,7 +1479,7 @@ nb2_status launch_collide(nb2_model* m, const float* body_q, const nb2_contacts_
     static const bool lane_per_contact = !(std::getenv("NB2_COLLIDE_LANE_PER_CONTACT") && std::atoi(std::getenv("NB2_COLLIDE_LANE_PER_CONTACT")) == 0);
     m->dev.lane_per_contact = lane_per_contact ? 1 : 0;
     // speculative contacts live in the generic (CONVEX = true) instantiation only, with the two-kernel export
-    const bool generic = m->has_convex_pairs || M.spec_mode != 0;
+    const bool generic = m->has_convex_pairs || M.spec_mode != 0 || m->has_mesh_pairs;  // mesh-plane pairs: generic instantiation only
     const nb2_contacts_view* fused_out = (contacts && fused && M.spec_mode == 0) ? contacts : nullptr;
 #define NB2_COLLIDE_DISPATCH(LANES) \
     st = generic ? launch_collide_L<LANES, true>(m, body_q, fused_out, s) : launch_collide_L<LANES, false>(m, body_q, fused_out, s)

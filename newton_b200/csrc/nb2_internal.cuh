@@ -85,12 +85,17 @@ struct DevModel {
     // only the writer's admission rule changes), 2 = active (shape velocities, swept broad phase, velocity-extended search gaps)
     int lane_per_contact;  // collide_kernel write-out: 1 = one lane per contact through a shared-memory staging area
     int spec_mode;
+    int has_mesh_pairs;    // the explicit pair list holds (mesh, infinite plane) pairs
     const float* spec_body_qd;
     float spec_dt, spec_max_ext;
 };
 
+// explicit pair list: bit set on .y of a (mesh slot, plane slot) pair - one contact per mesh vertex (narrow_phase.py:1761-1861)
+enum : int { NB2_PAIR_MESH_PLANE = 0x40000000 };
+
 struct HostTables {
     std::vector<int> env_body_start, env_joint_start, env_shape_start, env_pair_start, env_slot_start, env_art_start;
+    std::vector<int> explicit_env_slot_start;  // slot ranges of the explicit pair list (restored when the broad phase goes back to it)
     std::vector<int> global_shapes;
     std::vector<int2> pairs;
     std::vector<int> body_joint_start, body_joint_entry;
@@ -136,6 +141,7 @@ struct nb2_model {
     bool match_prev_has_record = false;      // the saved frame carries sticky records (the last save ran in sticky mode)
     bool implicit_single = false;  // model built without begin_world(): one environment holding every entity
     bool has_convex_pairs = false;  // some pair's types have no analytic collider -> collide_kernel<L, true>
+    bool has_mesh_pairs = false;    // the explicit pair list holds (mesh, infinite plane) pairs (flag NB2_PAIR_MESH_PLANE on .y)
     int explicit_max_env_contacts = 0, dyn_pairs_requested = 0;
     bool explicit_has_convex_pairs = false;
     int max_env_contacts = 0;       // max over envs of the sum of the pairs' own contact maxima (<= 4 analytic, <= 5 manifold)

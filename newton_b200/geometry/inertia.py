@@ -167,7 +167,7 @@ def transform_inertia(mass, inertia, offset, quat):
 def compute_shape_radius(geo_type, scale, src=None):
     """Bounding-sphere radius (reference ``geometry/utils.py:73-127``)."""
     s = np.abs(np.asarray(scale, dtype=np.float64))
-    if geo_type == GeoType.CONVEX_MESH and src is not None:  # bounding sphere of the scaled local AABB (utils.py:86-97)
+    if geo_type in (GeoType.CONVEX_MESH, GeoType.MESH) and src is not None:  # bounding sphere of the scaled local AABB (utils.py:86-97)
         v = np.asarray(src.vertices, dtype=np.float64) * np.asarray(scale, dtype=np.float64)
         return float(0.5 * np.linalg.norm(v.max(axis=0) - v.min(axis=0)))
     if geo_type == GeoType.SPHERE:

@@ -539,13 +539,13 @@ class ModelBuilder:
         cfg = cfg or self.default_shape_cfg
         tf = X.transform_identity() if xform is None else np.asarray(xform, dtype=np.float64)
         type = GeoType(type)
-        if type == GeoType.CONVEX_MESH:
+        if type in (GeoType.CONVEX_MESH, GeoType.MESH):
             if src is None:
-                raise ValueError("CONVEX_MESH shapes need a Mesh (src=...)")
+                raise ValueError(f"{type.name} shapes need a Mesh (src=...)")
             # mesh-backed shapes keep the sign of the scale (sim/builder.py:6524); mirrored hulls are not needed here
             scale = (1.0, 1.0, 1.0) if scale is None else tuple(float(s) for s in scale)
             if any(s <= 0.0 for s in scale):
-                raise NotImplementedError("convex hulls with zero / negative (mirroring) scale")
+                raise NotImplementedError("mesh-backed shapes with zero / negative (mirroring) scale")
         else:
             scale = (1.0, 1.0, 1.0) if scale is None else tuple(abs(float(s)) for s in scale)
         self.shape_source.append(src)
@@ -588,7 +588,7 @@ class ModelBuilder:
                     if self.shape_flags[cs] & ShapeFlags.COLLIDE_SHAPES:
                         self.add_shape_collision_filter_pair(shape, cs)
         if not is_static and cfg.density > 0.0 and body >= 0 and not self.body_lock_inertia[body]:
-            if type == GeoType.CONVEX_MESH:
+            if type in (GeoType.CONVEX_MESH, GeoType.MESH):
                 from ..geometry.mesh import compute_inertia_mesh
 
                 # mass properties of the SCALED hull (reference compute_inertia_shape, geometry/inertia.py:726-742)
@@ -639,6 +639,12 @@ class ModelBuilder:
     def add_shape_convex_hull(self, body, *, xform=None, mesh=None, scale=None, cfg=None, label=None) -> int:
         """Reference ``sim/builder.py:7201-7241``: the vertices of ``mesh`` are taken as the hull (GeoType.CONVEX_MESH)."""
         return self.add_shape(body=body, type=GeoType.CONVEX_MESH, xform=xform, cfg=cfg, scale=scale, src=mesh, label=label)
+
+    def add_shape_mesh(self, body, *, xform=None, mesh=None, scale=None, cfg=None, label=None) -> int:
+        """Reference ``sim/builder.py:7157-7199``: triangle-mesh collision shape (GeoType.MESH).  The hot path covers the
+        mesh-vs-infinite-plane route (one contact per mesh vertex near the plane, ``narrow_phase.py:1761-1861``); pairs of a mesh
+        with anything else need the reference's BVH / SDF machinery and are refused when the native model is created."""
+        return self.add_shape(body=body, type=GeoType.MESH, xform=xform, cfg=cfg, scale=scale, src=mesh, label=label)
 
     def add_shape_cone(self, body, *, xform=None, radius=1.0, half_height=0.5, cfg=None, label=None) -> int:
         """Cone along +z, apex up (reference ``sim/builder.py`` ``add_shape_cone``; support map ``support_function.py:316-336``)."""
@@ -855,15 +861,18 @@ class ModelBuilder:
         for s in range(self.shape_count):
             t, scale, src = self.shape_type[s], np.asarray(self.shape_scale[s], dtype=np.float64), self.shape_source[s]
             start = count = 0
-            if t == GeoType.CONVEX_MESH:
-                if id(src) not in ranges:
+            if t in (GeoType.CONVEX_MESH, GeoType.MESH):
+                # MESH: every vertex in file order (the vertex index is the contact's sort sub key, narrow_phase.py:1855)
+                rk = (id(src), int(t))
+                if rk not in ranges:
                     v = src.vertices
-                    _, first = np.unique(v, axis=0, return_index=True)
-                    v = v[np.sort(first)]
-                    ranges[id(src)] = (total, v.shape[0], v)
+                    if t == GeoType.CONVEX_MESH:
+                        _, first = np.unique(v, axis=0, return_index=True)
+                        v = v[np.sort(first)]
+                    ranges[rk] = (total, v.shape[0], v)
                     pool.append(v)
                     total += v.shape[0]
-                start, count, v = ranges[id(src)]
+                start, count, v = ranges[rk]
                 a, b = v.min(axis=0) * scale, v.max(axis=0) * scale
                 lo, hi = np.minimum(a, b), np.maximum(a, b)
             elif t == GeoType.SPHERE:

@@ -76,6 +76,15 @@ class CollisionPipeline:
         if requires_grad:
             raise NotImplementedError("differentiable contacts are out of scope")
         shape_pairs_max = unsupported.pop("shape_pairs_max", None)
+        st = getattr(model, "shape_type", None)
+        if st is not None and st.numel() and bool((st == 8).any()):  # GeoType.MESH
+            # mesh-vs-infinite-plane contacts are produced per vertex, unreduced (narrow_phase.py:1761-1861); the reference's default
+            # reduce_contacts=True runs them through its global hash-table reduction, which this pipeline does not have
+            if unsupported.get("reduce_contacts", True) is not False:
+                raise NotImplementedError("models with MESH shapes need CollisionPipeline(reduce_contacts=False): mesh-plane contacts are "
+                                          "written per vertex; the global contact reduction is outside the hot-path scope")
+            if self.broad_phase != "explicit" or speculative_config is not None:
+                raise NotImplementedError("MESH shapes are supported with broad_phase='explicit' and without speculative contacts")
         for k, v in unsupported.items():
             if k in _IGNORED_OPTIONS:  # tuning / capacity knobs of machinery this pipeline does not have (mesh reduction, buffers)
                 continue

@@ -88,7 +88,11 @@ class CollisionPipeline:
             ns = np.bincount(model.numpy("shape_world")[model.numpy("shape_world") >= 0], minlength=max(1, model.world_count))
             ng = int((model.numpy("shape_world") < 0).sum())
             pair_count = int(sum((n + ng) * (n + ng - 1) // 2 for n in ns))
-        self.rigid_contact_max = int(rigid_contact_max) if rigid_contact_max is not None else max(1000, 5 * pair_count)
+        st = model.numpy("shape_type")
+        mesh_vertices = 0
+        if (st == 8).any():  # GeoType.MESH: one contact per vertex and plane (narrow_phase.py:1761-1861)
+            mesh_vertices = int(model.numpy("shape_hull_count")[st == 8].sum()) * max(1, int((st == 1).sum()))
+        self.rigid_contact_max = int(rigid_contact_max) if rigid_contact_max is not None else max(1000, 5 * pair_count + mesh_vertices)
         self.candidate_count = 0
         self.last_candidates = None
 
@@ -154,6 +158,8 @@ class CollisionPipeline:
             self.candidate_count = lib().orc_collide(
                 C.byref(desc), C.c_void_p(_abi.ptr(state.body_q)), C.byref(v), C.c_int(1 if self.deterministic else 0)
             )
+            if self.candidate_count < 0:
+                raise NotImplementedError("oracle: mesh-mesh / mesh-convex / mesh-finite-plane pairs (BVH / SDF routes) are not restated")
         del keep
 
 

@@ -67,6 +67,12 @@ int orc_collide(const nb2_model_desc* m, const float* body_q, const nb2_contacts
     CollideResult res;
     collide_primitives(*m, body_q, res);
     gjk_mpr_pairs(*m, body_q, res);
+    if (res.unsupported_mesh_pairs > 0) return -1;  // mesh-mesh / mesh-convex / mesh-finite-plane: not restated
+    {
+        std::vector<ShapeGeom> geom;
+        if (!res.mesh_plane_pairs.empty()) compute_shape_aabbs(*m, body_q, geom);
+        mesh_plane_contacts(*m, body_q, geom, res);
+    }
     if (deterministic)
         std::stable_sort(res.contacts.begin(), res.contacts.end(),
                          [](const RawContact& a, const RawContact& b) { return a.key < b.key; });

@@ -336,8 +336,8 @@ inline void compute_shape_aabbs(const nb2_model_desc& m, const float* body_q, st
                     radius * std::sqrt(r0.z * r0.z + r1.z * r1.z) + half_height * std::fabs(r2.z));
             lo = pos - he - margin_vec;
             hi = pos + he + margin_vec;
-        } else if (geo_type == GEO_CONVEX_MESH) {
-            // has_local_aabb (collide.py:420-444): the builder's scaled local AABB, rotated into the world frame
+        } else if (geo_type == GEO_CONVEX_MESH || geo_type == GEO_MESH) {
+            // has_local_aabb (collide.py:348, 420-444): the builder's scaled local AABB, rotated into the world frame
             vec3 local_lo = load3(m.shape_collision_aabb_lower + 3 * sid), local_hi = load3(m.shape_collision_aabb_upper + 3 * sid);
             vec3 center = (local_lo + local_hi) * 0.5f;
             vec3 half = (local_hi - local_lo) * 0.5f;
@@ -589,8 +589,43 @@ inline bool routes_to_gjk_early(int type_a, int type_b) {
 struct CollideResult {
     std::vector<RawContact> contacts;            // in reference CPU emission order for candidate order = pair order
     std::vector<std::pair<int, int>> gjk_pairs;  // (shape_a, shape_b) type-sorted pairs for the GJK/MPR kernel
+    std::vector<std::pair<int, int>> mesh_plane_pairs;  // (mesh, plane) as narrow_phase.py:620-631 stores them
+    int unsupported_mesh_pairs = 0;              // mesh-mesh / mesh-convex / mesh-finite-plane routes (BVH / SDF paths: out of scope)
     int candidate_count = 0;
 };
+
+// narrow_phase_process_mesh_plane_contacts_kernel (narrow_phase.py:1761-1861), reduce_contacts=False: every mesh vertex within
+// gap + margin of an INFINITE plane becomes one contact (shape_a = mesh, normal from the mesh to the plane, sub key = vertex
+// index), written through write_contact with its own gap test (output_index = -1, collide.py:210-254).  Mesh vertices are the
+// shape's range of model.hull_points (the reference reads wp.Mesh.points behind shape_source).
+inline void mesh_plane_contacts(const nb2_model_desc& m, const float* body_q, const std::vector<ShapeGeom>& geom, CollideResult& res) {
+    for (const auto& pr : res.mesh_plane_pairs) {
+        const int mesh_shape = pr.first, plane_shape = pr.second;
+        const int v0 = m.shape_hull_start[mesh_shape], nv = m.shape_hull_count[mesh_shape];
+        const transform X_mesh_ws = geom[mesh_shape].X_ws, X_plane_ws = geom[plane_shape].X_ws;
+        const transform X_plane_sw = transform_inverse(X_plane_ws);
+        const vec3 plane_normal = transform_vector(X_plane_ws, vec3(0.f, 0.f, 1.f));
+        const vec3 mesh_scale = geom[mesh_shape].scale;
+        const float margin_mesh = geom[mesh_shape].margin, margin_plane = geom[plane_shape].margin;
+        const float total_margin_offset = margin_mesh + margin_plane;
+        const float gap_sum = m.shape_gap[mesh_shape] + m.shape_gap[plane_shape];
+        for (int vi = 0; vi < nv; ++vi) {
+            const vec3 vertex_local = cw_mul(load3(m.hull_points + 3 * size_t(v0 + vi)), mesh_scale);
+            const vec3 vertex_world = transform_point(X_mesh_ws, vertex_local);
+            const vec3 in_plane = transform_point(X_plane_sw, vertex_world);
+            const vec3 point_on_plane = transform_point(X_plane_ws, vec3(in_plane.x, in_plane.y, 0.0f));
+            const vec3 diff = vertex_world - point_on_plane;
+            const float distance = dot(diff, plane_normal);
+            if (distance < gap_sum + total_margin_offset) {
+                const vec3 contact_pos = (vertex_world + point_on_plane) * 0.5f;
+                RawContact rc;
+                if (write_contact(m, body_q, mesh_shape, plane_shape, contact_pos, -plane_normal, distance, 0.0f, 0.0f, margin_mesh,
+                                  margin_plane, vi, true, rc))
+                    res.contacts.push_back(rc);
+            }
+        }
+    }
+}
 
 // compute_shape_aabbs + explicit broad phase + primitive narrow phase.  Candidate pairs are visited in
 // shape_contact_pairs order (the reference CPU device visits them in (t mod 256, t div 256) order, which only
@@ -602,6 +637,8 @@ inline void collide_primitives(const nb2_model_desc& m, const float* body_q, Col
     if (sp.active) compute_shape_velocities(m, body_q, sp, geom);
     res.contacts.clear();
     res.gjk_pairs.clear();
+    res.mesh_plane_pairs.clear();
+    res.unsupported_mesh_pairs = 0;
     res.candidate_count = 0;
     for (int t = 0; t < m.shape_pair_count; ++t) {
         int s1 = m.shape_contact_pairs[2 * t + 0], s2 = m.shape_contact_pairs[2 * t + 1];
@@ -614,6 +651,13 @@ inline void collide_primitives(const nb2_model_desc& m, const float* body_q, Col
         if (shape_a == shape_b || shape_a < 0 || shape_b < 0) continue;
         int type_a = m.shape_type[shape_a], type_b = m.shape_type[shape_b];
         if (type_a > type_b) { std::swap(shape_a, shape_b); std::swap(type_a, type_b); }
+        if (type_a == GEO_MESH || type_b == GEO_MESH) {  // mesh routing (narrow_phase.py:594-640), ahead of the analytic chain
+            const vec3 sa = load3(m.shape_scale + 3 * shape_a);
+            const bool infinite_plane_a = type_a == GEO_PLANE && sa.x == 0.0f && sa.y == 0.0f;
+            if (infinite_plane_a && type_b == GEO_MESH) res.mesh_plane_pairs.emplace_back(shape_b, shape_a);
+            else res.unsupported_mesh_pairs += 1;
+            continue;
+        }
         if (routes_to_gjk_early(type_a, type_b)) { res.gjk_pairs.emplace_back(shape_a, shape_b); continue; }
         const ShapeGeom& A = geom[shape_a];
         const ShapeGeom& B = geom[shape_b];
