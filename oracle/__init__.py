@@ -67,8 +67,10 @@ class CollisionPipeline:
     involved, and the product keeps no contact blocks for them."""
 
     def __init__(self, model, *, broad_phase=None, rigid_contact_max=None, deterministic=True, include_static_kinematic_pairs=True,
-                 speculative_config=None):
+                 speculative_config=None, reduce_contacts=False):
         _check_cpu(model)
+        if reduce_contacts:  # mesh contacts: only narrow_phase_process_mesh_plane_contacts_kernel (the unreduced variant) is restated
+            raise NotImplementedError("the oracle restates the unreduced mesh-plane kernel only (reduce_contacts=False)")
         # speculative contacts (sim/collide.py:1076-1102, 1315-1317): any object with .max_speculative_extension
         self.speculative_config = speculative_config
         if speculative_config is not None:

@@ -52,6 +52,12 @@ def _universal_joint():
     return m
 
 
+def _mesh_on_plane():
+    from tests.test_mesh_plane import mixed_mesh_model
+
+    return mixed_mesh_model(2, seed=4)
+
+
 def _speculative_kwargs():
     from newton_b200 import SpeculativeContactConfig
 
@@ -68,6 +74,8 @@ CASES = {
     # round 2: speculative contacts through the SAP broad phase (60 ms horizon), and a D6 joint with two angular axes
     "heap_speculative_xpbd": (_speculative_heap, "SolverXPBD", {"iterations": 4}, 40, 0.004, _speculative_kwargs, 0.06, True),
     "universal_joint_featherstone": (_universal_joint, "SolverFeatherstone", {"angular_damping": 0.0}, 150, 0.001, None, None, False),
+    # round 2: triangle-mesh shapes against the ground plane (one contact per vertex), boxes / a sphere around them
+    "mesh_plane_xpbd": (_mesh_on_plane, "SolverXPBD", {"iterations": 4}, 60, 1.0 / 240, lambda: {"reduce_contacts": False}, None, True),
 }
 
 
