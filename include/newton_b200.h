@@ -110,7 +110,12 @@ typedef struct nb2_model_desc {
        + shape_hull_count[s]) (UNSCALED vertices, vec3; count 0 for every other shape type; shapes may share a range).
        shape_collision_aabb_lower / _upper: local AABB with the shape scale baked in (model.shape_collision_aabb_lower,
        sim/builder.py:11605-11610, 11686-11687), read by compute_shape_aabbs (sim/collide.py:420-444) and as the Minkowski-centre
-       seed of MPR / GJK (narrow_phase.py:1102-1105).  All five may be NULL when the model has no CONVEX_MESH shape. */
+       seed of MPR / GJK (narrow_phase.py:1102-1105).  All five may be NULL when the model has no CONVEX_MESH / MESH shape.
+       MESH shapes (GeoType 8; ModelBuilder.add_shape_mesh, sim/builder.py:7157-7199) use the same pool - ALL vertices of the mesh in
+       file order, not deduplicated: the vertex index is the sort sub key of its contact - and collide with INFINITE planes only, one
+       contact per vertex within gap + margin (narrow_phase_process_mesh_plane_contacts_kernel, narrow_phase.py:1761-1861, i.e.
+       CollisionPipeline(reduce_contacts=False)); a pair of a MESH with anything else makes nb2_model_create fail with
+       NB2_ERR_UNSUPPORTED (the reference's BVH / SDF routes are outside this library), and so does broad_phase nxn / sap. */
     const float* shape_collision_aabb_lower;
     const float* shape_collision_aabb_upper;
     const int32_t* shape_hull_start;

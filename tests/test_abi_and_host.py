@@ -123,6 +123,48 @@ def test_two_rank_gloo_state_gather(tmp_path):
     assert "GATHER_OK" in out.stdout
 
 
+@pytest.mark.parametrize("fail_at", ["create", "connect"])
+def test_peer_gather_constructor_fails_on_every_rank_together(tmp_path, fail_at):
+    """PeerStateGather.__init__ (N > 1 bench path): when ONE rank cannot create / connect its CUDA-IPC buffers, every rank must
+    leave the constructor with the same error - a rank raising on its own would leave the others inside the handle exchange until the
+    collective times out, and bench.py's fallback to NCCL would never be reached.  2 gloo ranks, the native calls replaced by a stub."""
+    script = tmp_path / "rank.py"
+    script.write_text(
+        "import sys, torch, torch.distributed as dist\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from newton_b200 import _lib\n"
+        "from newton_b200.sim.sharding import PeerStateGather\n"
+        "dist.init_process_group('gloo')\n"
+        "r = dist.get_rank()\n"
+        f"FAIL_AT = {fail_at!r}\n"
+        "class Stub:\n"
+        "    def nb2_peer_gather_handle_bytes(self): return 8\n"
+        "    def nb2_peer_gather_create(self, *a): return 3 if (FAIL_AT == 'create' and r == 1) else 0\n"
+        "    def nb2_peer_gather_export(self, h, buf): return 0\n"
+        "    def nb2_peer_gather_connect(self, h, handles): return 3 if (FAIL_AT == 'connect' and r == 1) else 0\n"
+        "    def nb2_peer_gather_destroy(self, h): return None\n"
+        "    def nb2_last_error(self): return b'stub failure'\n"
+        "_lib._lib = Stub()\n"
+        "class T:\n"
+        "    device = torch.device('cpu'); shape = (4, 7); dtype = torch.float32\n"
+        "    def numel(self): return 28\n"
+        "    def element_size(self): return 4\n"
+        "try:\n"
+        "    PeerStateGather([T()])\n"
+        "    print(f'RANK{r}_CONSTRUCTED')\n"
+        "except RuntimeError as e:\n"
+        "    assert 'rank 1' in str(e), str(e)\n"
+        "    print(f'RANK{r}_RAISED')\n"
+        "dist.barrier()\n"
+        "dist.destroy_process_group()\n"
+    )
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541" if fail_at == "create" else "29542", str(script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert "RANK0_RAISED" in out.stdout and "RANK1_RAISED" in out.stdout, out.stdout
+
+
 def test_oracle_eval_fk_matches_host_walk(oracle_lib):
     """The fp32 oracle restatement of newton.eval_fk (sim/articulation.py:237-424) against the independent float64
     NumPy walk the builder uses: quadruped (FREE + 12 REVOLUTE per env) and the double pendulum, random velocities."""
