@@ -171,6 +171,16 @@ def test_oracle_mixed_scene_counts(oracle_lib, plane_first):
     assert out.body_q.numpy().reshape(3, 4, 7)[:, 1, 2].min() > 0.1  # the blobs did not sink through
 
 
+def test_world_shards_carry_their_meshes(oracle_lib):
+    """Model.shard (N > 1 path): a shard keeps indexing the shared vertex pool, so shard-by-shard == monolithic bit for bit."""
+    m = mixed_mesh_model(4, seed=3)
+    kw = {"iterations": 4}
+    full, _, _ = simulate(m, oracle_lib.CollisionPipeline, oracle_lib.SolverXPBD, substeps=40, dt=1.0 / 240, solver_kwargs=kw)
+    parts = [simulate(m.shard(r, 2), oracle_lib.CollisionPipeline, oracle_lib.SolverXPBD, substeps=40, dt=1.0 / 240, solver_kwargs=kw)[0]
+             for r in range(2)]
+    np.testing.assert_array_equal(np.concatenate([p.body_q.numpy() for p in parts]), full.body_q.numpy())
+
+
 # ---- GPU ----------------------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("plane_first", [False, True])
