@@ -13,4 +13,6 @@ for w in box_stacks_xpbd quadruped_featherstone quadruped_xpbd_stock; do
   python bench.py --workload $w --steps 100 --warmup 5 --no-cpu-baseline > $O/r2q_bench_$w.json 2>/dev/null; cut -c1-160 $O/r2q_bench_$w.json
 done
 timeout -k 5 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 240 --csv --log-file $O/r2q_launches.csv python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-fast-twin > $O/r2q_ncu_bench.log 2>&1
+{ echo "=== featherstone, shuffle substitutions (default)"; python scripts/quick_bench.py 4096 8 quad featherstone 2>&1 | tail -2
+  echo "=== featherstone, NB2_FS_SHFL_SUBST=0 (round-2p substitutions)"; NB2_FS_SHFL_SUBST=0 python scripts/quick_bench.py 4096 8 quad featherstone 2>&1 | tail -2; } > $O/r2q_featherstone_subst_ab.txt 2>&1; cat $O/r2q_featherstone_subst_ab.txt
 python scripts/smoke_entry.py > $O/r2q_smoke.txt 2>&1; tail -1 $O/r2q_smoke.txt
