@@ -183,8 +183,14 @@ class ClockSampler:
 def run_native(args):
     import torch.distributed as dist
 
+    if args.fast_fp:  # the library is chosen when newton_b200._lib is imported: set the switch BEFORE the import
+        os.environ.pop("NB2_LIB", None)
+        os.environ["NB2_FP"] = "fast"
     import newton_b200
     from newton_b200 import _lib, scenes
+
+    if args.fast_fp:
+        assert _lib.LIB_PATH.endswith("libnewton_b200_fast.so"), _lib.LIB_PATH
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -196,9 +202,6 @@ def run_native(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    if args.fast_fp:
-        os.environ["NB2_LIB"] = os.path.join(ROOT, "newton_b200", "libnewton_b200_fast.so")
-
     envs = args.envs
     # every rank owns `envs` worlds (weak scaling); per-rank seed so shards differ like slices of one big scene
     model = build_scene(envs, seed=1 + rank).to(dev)

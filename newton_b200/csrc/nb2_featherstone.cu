@@ -1193,8 +1193,10 @@ static nb2_status launch_fs_W(nb2_model* m, const nb2_featherstone_params& p, co
         NB2_CUDA_CHECK(cudaFuncSetAttribute(featherstone_step_kernel<L, PF, WARPS, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     NB2_CUDA_CHECK(cudaFuncSetAttribute(featherstone_step_kernel<L, PF, WARPS, TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     static const int phase_sync = std::getenv("NB2_FS_PHASE_SYNC") ? std::atoi(std::getenv("NB2_FS_PHASE_SYNC")) : 1;
-    // NB2_FS_SHFL_SUBST=0 falls back to the shared-memory substitutions of round 2p (A/B switch; both are bit-exact)
-    static const int shfl_subst = std::getenv("NB2_FS_SHFL_SUBST") ? std::atoi(std::getenv("NB2_FS_SHFL_SUBST")) : 1;
+    // NB2_FS_SHFL_SUBST=1: substitutions with shuffle broadcasts and the products of the backward pass in the upper triangle.  Bit-exact
+    // (the round-2q GPU suite ran with it) but it LOSES: 82.4 vs 80.3 us at 4096 quadruped envs (profiles/r2q_featherstone_subst_ab.txt) -
+    // the divergent per-lane row loops around every shuffle cost more than the barriers they replace.  Default: the round-2p path.
+    static const int shfl_subst = std::getenv("NB2_FS_SHFL_SUBST") ? std::atoi(std::getenv("NB2_FS_SHFL_SUBST")) : 0;
     const int kflags = (phase_sync ? 1 : 0) | (shfl_subst ? 2 : 0);
     static const int min_grid = std::getenv("NB2_FS_MIN_GRID") ? std::atoi(std::getenv("NB2_FS_MIN_GRID")) : 0;  // A/B: idle padding CTAs
     featherstone_step_kernel<L, PF, WARPS, TILE><<<blocks < min_grid ? min_grid : blocks, 32 * WARPS, smem, s>>>(M, p, in, out, ctl, use_contacts, update_mass, dt, kflags);
