@@ -1469,6 +1469,10 @@ nb2_status launch_collide(nb2_model* m, const float* body_q, const nb2_contacts_
         set_error("nb2_collide: contacts view has NULL arrays");
         return NB2_ERR_INVALID_ARGUMENT;
     }
+    if (m->has_mesh_pairs && M.spec_mode != 0) {
+        set_error("nb2_collide_speculative: MESH shapes are not supported with speculative contacts");
+        return NB2_ERR_UNSUPPORTED;
+    }
     if (M.dyn_pairs && (st = launch_broadphase(m, body_q, s)) != NB2_OK) return st;
     // NB2_COLLIDE_FUSED_EXPORT=1: the `Contacts` arrays are written by the collide kernel itself (EXPORT = true, tile chain with
     // decoupled look-back).  Measured on B200 it LOSES to the two-kernel path (collide, then contact_export_kernel): 4096 quadruped
