@@ -171,6 +171,63 @@ def test_oracle_mixed_scene_counts(oracle_lib, plane_first):
     assert out.body_q.numpy().reshape(3, 4, 7)[:, 1, 2].min() > 0.1  # the blobs did not sink through
 
 
+# ---- newton/tests/test_mesh_aabb.py:17-154: the broad-phase AABB of a mesh is its rotated LOCAL box, not a bounding sphere -----------
+def _box_mesh(hx, hy, hz):
+    c = np.array([[sx * hx, sy * hy, sz * hz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], dtype=np.float32)
+    return Mesh(c, BOX_TRIS)
+
+
+def _mesh_model(mesh, pos, rot=None, scale=None):
+    b = ModelBuilder()
+    body = b.add_body(xform=X.transform(pos, rot if rot is not None else X.quat_identity()))
+    b.add_shape_mesh(body, mesh=mesh, **({"scale": scale} if scale is not None else {}))
+    b.add_ground_plane()
+    return b.finalize()
+
+
+def _aabb(oracle_lib, m, shape=0):
+    lo, hi = oracle_lib.shape_aabbs(m, m.body_q)
+    margin = float(m.shape_margin[shape] + m.shape_gap[shape])
+    return np.asarray(lo)[shape], np.asarray(hi)[shape], margin
+
+
+def test_mesh_aabb_axis_aligned_is_tight(oracle_lib):
+    hx, hy, hz = 0.2, 0.2, 0.05
+    pos = (0.0, 0.0, 1.0)
+    lo, hi, margin = _aabb(oracle_lib, _mesh_model(_box_mesh(hx, hy, hz), pos))
+    np.testing.assert_allclose(lo, np.array(pos) - (hx, hy, hz) - margin, atol=1e-4)
+    np.testing.assert_allclose(hi, np.array(pos) + (hx, hy, hz) + margin, atol=1e-4)
+
+
+def test_mesh_aabb_flat_table_does_not_reach_the_gripper(oracle_lib):
+    b = ModelBuilder()
+    table = b.add_body(xform=X.transform((0.0, 0.0, 0.05), X.quat_identity()))
+    st = b.add_shape_mesh(table, mesh=_box_mesh(0.2, 0.2, 0.05))
+    gripper = b.add_body(xform=X.transform((0.0, 0.0, 0.375), X.quat_identity()))
+    sg = b.add_shape_mesh(gripper, mesh=_box_mesh(0.03, 0.02, 0.04))
+    b.add_shape_collision_filter_pair(st, sg)  # (the pair itself is a mesh-mesh route; only the boxes are looked at here)
+    b.add_ground_plane()
+    m = b.finalize()
+    lo, hi = oracle_lib.shape_aabbs(m, m.body_q)
+    margin = float(m.shape_margin[0] + m.shape_gap[0])
+    assert hi[0][2] < 0.1 + margin + 0.01
+    assert lo[1][2] > hi[0][2]
+
+
+def test_mesh_aabb_rotated(oracle_lib):
+    hx, hy, hz = 1.0, 0.1, 0.1
+    rot = X.quat_from_axis_angle((0.0, 0.0, 1.0), np.pi / 2.0)
+    lo, hi, margin = _aabb(oracle_lib, _mesh_model(_box_mesh(hx, hy, hz), (0.0, 0.0, 2.0), rot))
+    np.testing.assert_allclose(hi - lo, 2 * np.array([hy, hx, hz]) + 2 * margin, atol=0.02)
+
+
+def test_mesh_aabb_nonuniform_scale(oracle_lib):
+    pos, sc = (0.0, 0.0, 5.0), (2.0, 0.5, 3.0)
+    lo, hi, margin = _aabb(oracle_lib, _mesh_model(_box_mesh(1.0, 1.0, 1.0), pos, scale=sc))
+    np.testing.assert_allclose(lo, np.array(pos) - sc - margin, atol=1e-4)
+    np.testing.assert_allclose(hi, np.array(pos) + sc + margin, atol=1e-4)
+
+
 def test_world_shards_carry_their_meshes(oracle_lib):
     """Model.shard (N > 1 path): a shard keeps indexing the shared vertex pool, so shard-by-shard == monolithic bit for bit."""
     m = mixed_mesh_model(4, seed=3)
