@@ -265,6 +265,20 @@ class SolverFeatherstone:
                                     C.byref(cv), ctp, C.c_float(dt))
 
 
+    def mass_matrix(self, articulation: int = 0):
+        """H = J^T M J of one articulation as the last ``step()`` formed it (before the armature goes onto the diagonal): test
+        access to the dense stage, used to pin it against the closed forms of ``newton/tests/test_jacobian_mass_matrix.py``."""
+        n_max = int(self.model.joint_dof_count)
+        out = np.zeros(n_max * n_max, dtype=np.float32)
+        L = lib()
+        L.orc_featherstone_mass_matrix.restype = C.c_int
+        n = L.orc_featherstone_mass_matrix(self._h, C.byref(self._desc), C.c_int(articulation), C.c_void_p(out.ctypes.data),
+                                            C.c_int(out.size))
+        if n < 0:
+            raise RuntimeError("mass_matrix: call step() first / bad articulation index")
+        return out[: n * n].reshape(n, n).copy()
+
+
 class _Shard(C.Structure):
     _fields_ = [("model", C.c_void_p), ("state_0", _abi.StateView), ("state_1", _abi.StateView), ("control", _abi.ControlView),
                 ("contacts", _abi.ContactsView), ("featherstone", C.c_void_p)]

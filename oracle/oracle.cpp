@@ -242,6 +242,19 @@ void orc_featherstone_step(void* h, const nb2_model_desc* m, const nb2_featherst
 
 // ---- unit-level hooks for known-answer tests ------------------------------------------------------
 // One analytic pair: types/scales/transforms in, up to 4 (distance, position) + normal out.
+// Test access to the dense stage: H = J^T M J of articulation `art` as formed by the last orc_featherstone_step on this scratch
+// (eval_dense_gemm pair, kernels.py:1504-1538; before the armature is added in dense_cholesky).  Returns the number of dofs n
+// (out receives n*n floats, row-major) or -1.
+int orc_featherstone_mass_matrix(void* h, const nb2_model_desc* m, int art, float* out, int capacity) {
+    FsScratch& s = *static_cast<FsScratch*>(h);
+    if (!s.init || art < 0 || art >= m->articulation_count || size_t(art) >= s.H_start.size()) return -1;
+    const int j0 = m->articulation_start[art], j1 = m->articulation_start[art + 1];
+    const int n = m->joint_qd_start[j1] - m->joint_qd_start[j0];
+    if (n * n > capacity) return -1;
+    for (int i = 0; i < n * n; ++i) out[i] = s.H[size_t(s.H_start[art]) + i];
+    return n;
+}
+
 int orc_primitive_pair(int type_a, const float* scale_a, const float* xform_a, int type_b, const float* scale_b,
                        const float* xform_b, float plane_box_margin, float* dist4, float* pos12, float* normal3) {
     float d[4];

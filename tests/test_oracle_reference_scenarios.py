@@ -206,3 +206,97 @@ def test_fk_of_every_joint_kind_matches_an_independent_walk_and_ik_inverts_it(or
     else:
         np.testing.assert_allclose(qb, q, atol=5e-6)
     np.testing.assert_allclose(qd_back.numpy(), model.joint_qd.numpy(), atol=5e-6)
+
+
+# ---- test_jacobian_mass_matrix.py: the dense stage H = J^T M J (Featherstone rows a23 / a24) against closed forms --------------------
+# The reference tests call newton.eval_mass_matrix; here H is read back from the oracle's solver scratch after one step (same
+# eval_dense_gemm arithmetic, kernels.py:1504-1538).  Configurations are chosen where the solver's internal generalized velocity
+# equals the public one (fixed bases; a free base at identity pose with its COM at the origin).
+def _H_after_step(oracle_lib, model, joint_q=None, joint_qd=None):
+    solver = oracle_lib.SolverFeatherstone(model, angular_damping=0.0)
+    s0, s1 = model.state(), model.state()
+    if joint_q is not None:
+        s0.joint_q.copy_(torch.tensor(joint_q, dtype=torch.float32))
+    if joint_qd is not None:
+        s0.joint_qd.copy_(torch.tensor(joint_qd, dtype=torch.float32))
+    oracle_lib.eval_fk(model, s0.joint_q, s0.joint_qd, s0)
+    solver.step(s0, s1, model.control(), None, 1.0e-4)
+    return solver.mass_matrix(0).astype(np.float64), s0
+
+
+def test_mass_matrix_fixed_base_pendulum_is_the_parallel_axis_inertia(oracle_lib):
+    """test_jacobian_mass_matrix.py:413-437: H = I_zz + m L^2."""
+    mass, length, inertia_zz = 2.0, 0.75, 0.2
+    b = ModelBuilder(up_axis="z", gravity=(0.0, 0.0, 0.0))
+    body = b.add_link(mass=mass, inertia=np.diag([0.1, 0.15, inertia_zz]))
+    j = b.add_joint_revolute(-1, body, axis=(0.0, 0.0, 1.0), child_xform=X.transform((-length, 0.0, 0.0)), armature=0.0)
+    b.add_articulation([j])
+    H, _ = _H_after_step(oracle_lib, b.finalize())
+    assert H.shape == (1, 1)
+    np.testing.assert_allclose(H[0, 0], inertia_zz + mass * length**2, rtol=1e-6, atol=1e-6)
+
+
+def test_mass_matrix_floating_base_pendulum_matches_the_closed_form(oracle_lib):
+    """test_jacobian_mass_matrix.py:163-197, 440-469: free base + one revolute child, identity pose, zero angle: 7 x 7."""
+    base_mass, child_mass, length = 3.0, 2.0, 0.6
+    base_inertia, child_inertia = (0.4, 0.5, 0.6), (0.2, 0.25, 0.3)
+    b = ModelBuilder(up_axis="z", gravity=(0.0, 0.0, 0.0))
+    base = b.add_link(mass=base_mass, inertia=np.diag(base_inertia))
+    child = b.add_link(mass=child_mass, inertia=np.diag(child_inertia))
+    jf = b.add_joint_free(base)
+    jr = b.add_joint_revolute(base, child, axis=(0.0, 0.0, 1.0), child_xform=X.transform((-length, 0.0, 0.0)), armature=0.0)
+    b.add_articulation([jf, jr])
+    H, _ = _H_after_step(oracle_lib, b.finalize())
+    T = np.zeros((6, 7))  # child COM twist from qd (free translation, free angular velocity, revolute rate)
+    T[0, 0] = T[1, 1] = T[2, 2] = 1.0
+    T[2, 4], T[1, 5], T[1, 6] = -length, length, length
+    T[3, 3] = T[4, 4] = T[5, 5] = T[5, 6] = 1.0
+    expected = T.T @ np.diag([child_mass] * 3 + list(child_inertia)) @ T
+    expected[np.arange(6), np.arange(6)] += [base_mass] * 3 + list(base_inertia)
+    assert H.shape == (7, 7)
+    np.testing.assert_allclose(H, expected, rtol=1e-6, atol=1e-6)
+
+
+def test_mass_matrix_two_link_pendulum_is_symmetric_positive_definite(oracle_lib):
+    """test_jacobian_mass_matrix.py:321-410."""
+    b = ModelBuilder()
+    b1 = b.add_link(mass=1.0, inertia=np.eye(3) * 0.01)
+    b2 = b.add_link(xform=X.transform((1.0, 0.0, 0.0)), mass=2.0, inertia=np.eye(3) * 0.02)
+    j1 = b.add_joint_revolute(-1, b1, axis=(0.0, 0.0, 1.0), armature=0.0)
+    j2 = b.add_joint_revolute(b1, b2, axis=(0.0, 0.0, 1.0), parent_xform=X.transform((1.0, 0.0, 0.0)), armature=0.0)
+    b.add_articulation([j1, j2])
+    H, _ = _H_after_step(oracle_lib, b.finalize(), joint_q=[0.3, 0.5])
+    np.testing.assert_allclose(H, H.T, rtol=1e-5, atol=1e-6)
+    assert np.linalg.eigvalsh(0.5 * (H + H.T)).min() > 0.0
+
+
+def test_mass_matrix_gives_the_kinetic_energy_of_the_body_twists(oracle_lib):
+    """test_jacobian_mass_matrix.py:13-53, 859-878: revolute base + translated prismatic slider with offset centres of mass:
+    0.5 qd^T H qd == sum of 0.5 m v_com^2 + 0.5 w^T I_world w."""
+    b = ModelBuilder(up_axis="y", gravity=(0.0, 0.0, 0.0))
+    base = b.add_link(mass=2.0)
+    slider = b.add_link(mass=1.5)
+    b.add_shape_box(base, hx=0.2, hy=0.1, hz=0.1)
+    b.add_shape_box(slider, hx=0.15, hy=0.1, hz=0.08)
+    b.body_com[base] = np.array([0.2, 0.0, 0.0])
+    b.body_com[slider] = np.array([0.35, 0.0, -0.1])
+    j0 = b.add_joint_revolute(-1, base, axis=(0.0, 0.0, 1.0), armature=0.0)
+    j1 = b.add_joint_prismatic(base, slider, axis=(1.0, 0.0, 0.0), parent_xform=X.transform((1.0, 0.0, 0.4)),
+                               child_xform=X.transform((0.2, 0.0, -0.15)), armature=0.0)
+    b.add_articulation([j0, j1])
+    model = b.finalize()
+    qd = np.array([0.9, -0.25])
+    H, s0 = _H_after_step(oracle_lib, model, joint_q=[0.4, 0.6], joint_qd=qd.tolist())
+    body_q, body_qd = s0.body_q.numpy().astype(np.float64), s0.body_qd.numpy().astype(np.float64)
+    I, m = model.body_inertia.numpy().astype(np.float64), model.body_mass.numpy().astype(np.float64)
+    kinetic = 0.0
+    for k in (base, slider):
+        R = X.quat_to_matrix(body_q[k, 3:]) if hasattr(X, "quat_to_matrix") else None
+        if R is None:
+            x, y, z, w = body_q[k, 3:]
+            R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                          [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                          [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        v, w_ = body_qd[k, :3], body_qd[k, 3:]
+        kinetic += 0.5 * m[k] * float(v @ v) + 0.5 * float(w_ @ (R @ I[k] @ R.T @ w_))
+    np.testing.assert_allclose(0.5 * float(qd @ H @ qd), kinetic, atol=1e-5, rtol=1e-5)
