@@ -300,3 +300,49 @@ def test_mass_matrix_gives_the_kinetic_energy_of_the_body_twists(oracle_lib):
         v, w_ = body_qd[k, :3], body_qd[k, 3:]
         kinetic += 0.5 * m[k] * float(v @ v) + 0.5 * float(w_ @ (R @ I[k] @ R.T @ w_))
     np.testing.assert_allclose(0.5 * float(qd @ H @ qd), kinetic, atol=1e-5, rtol=1e-5)
+
+
+# ---- test_multiworld_body_properties.py:20-116: per-world centres of mass give the single-world trajectories --------------------------
+def _per_world_com_model(coms):
+    scene = ModelBuilder()
+    for com in coms:
+        template = ModelBuilder()
+        base = template.add_link(mass=5.0, com=com, inertia=np.eye(3) * 0.1)
+        template.add_articulation([template.add_joint_free(base)])
+        scene.begin_world()
+        scene.add_builder(template)
+        scene.end_world()
+    return scene.finalize()
+
+
+def _tumble(oracle_lib, model, solver_name, steps=100, dt=1e-3):
+    solver = oracle_lib.SolverFeatherstone(model, angular_damping=0.0) if solver_name == "featherstone" else \
+        oracle_lib.SolverXPBD(model, iterations=2, angular_damping=0.0)
+    s0, s1, control = model.state(), model.state(), model.control()
+    nw = model.world_count
+    q = s0.joint_q.numpy().reshape(nw, -1).copy()
+    q[:, 2] = 1.0
+    qd = s0.joint_qd.numpy().reshape(nw, -1).copy()
+    qd[:, 3], qd[:, 4] = 1.0, 0.5  # a spin is what makes a wrong centre of mass visible (v_origin = v_com - w x com)
+    s0.joint_q.copy_(torch.from_numpy(q.reshape(-1)))
+    s0.joint_qd.copy_(torch.from_numpy(qd.reshape(-1)))
+    oracle_lib.eval_fk(model, s0.joint_q, s0.joint_qd, s0)
+    for _ in range(steps):
+        s0.clear_forces()
+        solver.step(s0, s1, control, None, dt)
+        s0, s1 = s1, s0
+    if solver_name == "xpbd":
+        oracle_lib.eval_ik(model, s0, s0.joint_q, s0.joint_qd)
+    return s0.joint_q.numpy().reshape(nw, -1).copy()
+
+
+@pytest.mark.parametrize("solver_name", ["featherstone", "xpbd"])
+def test_per_world_com_matches_single_world_runs(oracle_lib, solver_name):
+    com_a, com_b = (0.0, 0.0, 0.0), (0.05, 0.0, -0.02)
+    ref = [_tumble(oracle_lib, _per_world_com_model([c]), solver_name)[0] for c in (com_a, com_b)]
+    multi = _tumble(oracle_lib, _per_world_com_model([com_a, com_b]), solver_name)
+    np.testing.assert_allclose(multi[0], ref[0], atol=1e-4)
+    np.testing.assert_allclose(multi[1], ref[1], atol=1e-4)
+    assert np.abs(ref[0] - ref[1]).max() > 1e-3  # the two centres of mass do give different motions
+    np.testing.assert_array_equal(multi[0], ref[0])  # worlds never interact: in fact bit for bit
+    np.testing.assert_array_equal(multi[1], ref[1])
