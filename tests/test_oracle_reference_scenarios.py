@@ -346,3 +346,52 @@ def test_per_world_com_matches_single_world_runs(oracle_lib, solver_name):
     assert np.abs(ref[0] - ref[1]).max() > 1e-3  # the two centres of mass do give different motions
     np.testing.assert_array_equal(multi[0], ref[0])  # worlds never interact: in fact bit for bit
     np.testing.assert_array_equal(multi[1], ref[1])
+
+
+# ---- test_kinematics.py:260-375: a prismatic joint hanging off a revolute base, offset anchors and centres of mass --------------------
+def _revolute_prismatic_chain():
+    b = ModelBuilder(up_axis="y", gravity=(0.0, 0.0, 0.0))
+    base, slider = b.add_link(mass=1.0), b.add_link(mass=1.0)
+    b.body_com[base] = np.array([0.2, 0.0, 0.0])
+    b.body_com[slider] = np.array([0.35, 0.0, -0.1])
+    j0 = b.add_joint_revolute(-1, base, axis=(0.0, 0.0, 1.0))
+    j1 = b.add_joint_prismatic(base, slider, axis=(1.0, 0.0, 0.0), parent_xform=X.transform((1.0, 0.0, 0.4)),
+                               child_xform=X.transform((0.2, 0.0, -0.15)))
+    b.add_articulation([j0, j1])
+    return b.finalize(), slider
+
+
+def _fk(oracle_lib, model, q, qd):
+    s = model.state()
+    s.joint_q.copy_(torch.tensor(q, dtype=torch.float32))
+    s.joint_qd.copy_(torch.tensor(qd, dtype=torch.float32))
+    oracle_lib.eval_fk(model, s.joint_q, s.joint_qd, s)
+    return s
+
+
+def test_fk_prismatic_descendant_origin_velocity_matches_finite_difference(oracle_lib):
+    """test_kinematics.py:260-323: the slider's ORIGIN velocity implied by its COM twist == (x(q + qd dt) - x(q)) / dt, tol 5e-3."""
+    model, slider = _revolute_prismatic_chain()
+    q, qd, dt = np.array([0.55, 0.8]), np.array([1.1, -0.35]), 1.0e-4
+    s0, s1 = _fk(oracle_lib, model, q, qd), _fk(oracle_lib, model, q + qd * dt, qd)
+    bq, bq1, bqd = s0.body_q.numpy().astype(np.float64), s1.body_q.numpy().astype(np.float64), s0.body_qd.numpy().astype(np.float64)
+    fd = (bq1[slider, :3] - bq[slider, :3]) / dt
+    # origin velocity from the COM twist: v_origin = v_com - w x (R com)   (test_kinematics.py origin_velocity_from_body_qd)
+    x, y, z, w = bq[slider, 3:]
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    com_w = R @ model.body_com.numpy()[slider].astype(np.float64)
+    v_origin = bqd[slider, :3] - np.cross(bqd[slider, 3:], com_w)
+    np.testing.assert_allclose(fd, v_origin, atol=5.0e-3)
+
+
+def test_ik_prismatic_descendant_recovers_joint_state(oracle_lib):
+    """test_kinematics.py:326-375: eval_ik(eval_fk(q, qd)) == (q, qd) to 1e-6."""
+    model, _ = _revolute_prismatic_chain()
+    q, qd = np.array([0.55, 0.8], dtype=np.float32), np.array([1.1, -0.35], dtype=np.float32)
+    s = _fk(oracle_lib, model, q, qd)
+    rq, rqd = torch.zeros_like(s.joint_q), torch.zeros_like(s.joint_qd)
+    oracle_lib.eval_ik(model, s, rq, rqd)
+    np.testing.assert_allclose(rq.numpy(), q, atol=1.0e-6)
+    np.testing.assert_allclose(rqd.numpy(), qd, atol=1.0e-6)
