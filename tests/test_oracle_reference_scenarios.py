@@ -395,3 +395,29 @@ def test_ik_prismatic_descendant_recovers_joint_state(oracle_lib):
     oracle_lib.eval_ik(model, s, rq, rqd)
     np.testing.assert_allclose(rq.numpy(), q, atol=1.0e-6)
     np.testing.assert_allclose(rqd.numpy(), qd, atol=1.0e-6)
+
+
+def test_featherstone_step_reports_a_twist_consistent_with_its_own_motion(oracle_lib):
+    """The same check on the SOLVER's closing FK (eval_fk_with_velocity_conversion, featherstone/kernels.py): between two consecutive
+    state_out's of SolverFeatherstone the slider's origin moves by its reported origin velocity * dt (test_kinematics.py:578-637 runs
+    this through newton.eval_fk only; the solver writes body_q / body_qd itself)."""
+    model, slider = _revolute_prismatic_chain()
+    solver = oracle_lib.SolverFeatherstone(model, angular_damping=0.0)
+    s0 = _fk(oracle_lib, model, [0.55, 0.8], [1.1, -0.35])
+    s1, s2, control, dt = model.state(), model.state(), model.control(), 1.0e-4
+    solver.step(s0, s1, control, None, dt)
+    solver.step(s1, s2, control, None, dt)
+    bq1, bq2 = s1.body_q.numpy().astype(np.float64), s2.body_q.numpy().astype(np.float64)
+    com = model.body_com.numpy()[slider].astype(np.float64)
+
+    def origin_velocity(state):
+        bq, bqd = state.body_q.numpy().astype(np.float64)[slider], state.body_qd.numpy().astype(np.float64)[slider]
+        x, y, z, w = bq[3:]
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        return bqd[:3] - np.cross(bqd[3:], R @ com)
+
+    fd = (bq2[slider, :3] - bq1[slider, :3]) / dt
+    np.testing.assert_allclose(fd, origin_velocity(s2), atol=5.0e-3)  # semi-implicit: the step moves with the NEW rates
+    assert np.linalg.norm(fd) > 0.5  # and it does move
