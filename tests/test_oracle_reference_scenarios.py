@@ -421,3 +421,50 @@ def test_featherstone_step_reports_a_twist_consistent_with_its_own_motion(oracle
     fd = (bq2[slider, :3] - bq1[slider, :3]) / dt
     np.testing.assert_allclose(fd, origin_velocity(s2), atol=5.0e-3)  # semi-implicit: the step moves with the NEW rates
     assert np.linalg.norm(fd) > 0.5  # and it does move
+
+
+# ---- test_control_force.py:17-262: joint_f on a FREE joint that hangs off a rotated (kinematic, fixed) parent ----------------------
+def _descendant_free_model(child_com):
+    b = ModelBuilder(up_axis="y", gravity=(0.0, 0.0, 0.0))
+    base = b.add_link(is_kinematic=True, mass=1.0)
+    child = b.add_link(mass=1.0)
+    b.add_shape_sphere(base, radius=0.1)
+    b.add_shape_sphere(child, radius=0.1)
+    b.body_com[child] = np.asarray(child_com, dtype=np.float64)
+    j0 = b.add_joint_fixed(-1, base, parent_xform=X.transform((0.0, 0.0, 0.0), X.quat_from_axis_angle((0.0, 0.0, 1.0), math.pi * 0.5)))
+    j1 = b.add_joint_free(child, parent=base)
+    b.add_articulation([j0, j1])
+    return b.finalize(), base, child
+
+
+def _into_parent_frame(q_xyzw, v):
+    x, y, z, w = (float(c) for c in q_xyzw)
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    return R.T @ np.asarray(v, dtype=np.float64)
+
+
+@pytest.mark.parametrize("wrench,kind", [((10.0, 0.0, 0.0, 0.0, 0.0, 0.0), "force"), ((0.0, 0.0, 0.0, 10.0, 0.0, 0.0), "torque")])
+def test_featherstone_descendant_free_joint_f_acts_in_world_coordinates(oracle_lib, wrench, kind):
+    """A FREE joint's generalized force is a WORLD wrench even under a rotated parent; the joint_qd the solver returns is the body
+    twist expressed in the PARENT frame (test_control_force.py:201-262)."""
+    model, base, child = _descendant_free_model((0.2, -0.1, 0.05))
+    solver = oracle_lib.SolverFeatherstone(model, angular_damping=0.0)
+    s0, s1, control = model.state(), model.state(), model.control()
+    oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, s0)
+    d0 = int(model.joint_qd_start[1])
+    f = np.zeros(model.joint_dof_count, dtype=np.float32)
+    f[d0:d0 + 6] = wrench
+    control.joint_f.copy_(torch.from_numpy(f))
+    solver.step(s0, s1, control, None, 0.01)
+    body_qd = s1.body_qd.numpy()[child]
+    base_q = s1.body_q.numpy()[base]
+    expected = np.concatenate([_into_parent_frame(base_q[3:7], body_qd[:3]), _into_parent_frame(base_q[3:7], body_qd[3:6])])
+    if kind == "force":
+        assert body_qd[0] > 1.0e-2
+        assert np.linalg.norm(body_qd[1:3]) < 1.0e-6 and np.linalg.norm(body_qd[3:6]) < 1.0e-6
+    else:
+        assert np.linalg.norm(body_qd[:3]) < 3.0e-3
+        assert body_qd[3] > 0.0 and np.linalg.norm(body_qd[4:6]) < 1.0e-5
+    np.testing.assert_allclose(s1.joint_qd.numpy()[d0:d0 + 6], expected, atol=1.0e-6, rtol=1.0e-6)
