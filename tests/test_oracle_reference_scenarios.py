@@ -468,3 +468,37 @@ def test_featherstone_descendant_free_joint_f_acts_in_world_coordinates(oracle_l
         assert np.linalg.norm(body_qd[:3]) < 3.0e-3
         assert body_qd[3] > 0.0 and np.linalg.norm(body_qd[4:6]) < 1.0e-5
     np.testing.assert_allclose(s1.joint_qd.numpy()[d0:d0 + 6], expected, atol=1.0e-6, rtol=1.0e-6)
+
+
+# ---- test_body_force.py:447-520: force and torque together on a rotated free body with an offset centre of mass ---------------------
+@pytest.mark.parametrize("solver_name", ["xpbd", "featherstone"])
+@pytest.mark.parametrize("com_offset", [(0.5, 0.0, 0.0), (0.0, 0.3, 0.0), (0.0, 0.0, 0.4), (0.2, 0.3, 0.1)])
+@pytest.mark.parametrize("use_control", [False, True])
+def test_combined_force_and_torque_with_com_offset(oracle_lib, solver_name, com_offset, use_control):
+    b = ModelBuilder(gravity=(0.0, 0.0, 0.0))
+    rot = X.quat_from_axis_angle((1.0, 0.0, 0.0), math.pi * 0.5)  # the wrench is a WORLD wrench: a rotated body shows it
+    body = b.add_body(xform=X.transform((0.0, 0.0, 1.0), rot))
+    b.add_shape_box(body, hx=0.1, hy=0.1, hz=0.1)
+    b.body_com[body] = np.asarray(com_offset, dtype=np.float64)
+    model = b.finalize()
+    solver = oracle_lib.SolverXPBD(model, angular_damping=0.0) if solver_name == "xpbd" else oracle_lib.SolverFeatherstone(model)
+    s0, s1 = model.state(), model.state()
+    control = model.control() if use_control else None
+    oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, s0)
+    wrench = torch.tensor([10.0, 0.0, 0.0, 0.0, 0.0, 10.0])
+    dt, n = 0.01, 10
+    for _ in range(n):
+        if use_control:
+            control.joint_f.copy_(wrench)
+        else:
+            s0.body_f.copy_(wrench.view(1, 6))
+            s1.body_f.copy_(wrench.view(1, 6))
+        solver.step(s0, s1, control, None, dt)
+        s0, s1 = s1, s0
+    qd = s0.body_qd.numpy()[body]
+    v_exp = 10.0 / float(model.body_mass[body]) * dt * n
+    w_exp = 10.0 / float(model.body_inertia[body][2, 2]) * dt * n
+    assert qd[0] == pytest.approx(v_exp, abs=5e-2 * (1 + abs(v_exp)))
+    assert abs(qd[1]) < 1e-3 and abs(qd[2]) < 1e-3
+    assert abs(qd[3]) < 1e-3 and abs(qd[4]) < 1e-3
+    assert qd[5] == pytest.approx(w_exp, abs=5e-2 * (1 + abs(w_exp)))
