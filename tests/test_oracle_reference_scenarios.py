@@ -502,3 +502,33 @@ def test_combined_force_and_torque_with_com_offset(oracle_lib, solver_name, com_
     assert abs(qd[1]) < 1e-3 and abs(qd[2]) < 1e-3
     assert abs(qd[3]) < 1e-3 and abs(qd[4]) < 1e-3
     assert qd[5] == pytest.approx(w_exp, abs=5e-2 * (1 + abs(w_exp)))
+
+
+# ---- test_body_force.py:161-199: FREE joint under a kinematic revolute parent turned by 90 degrees ----------------------------------
+@pytest.mark.parametrize("solver_name", ["featherstone", "xpbd"])
+def test_descendant_free_joint_f_world_force_under_rotated_parent(oracle_lib, solver_name):
+    b = ModelBuilder(up_axis="y", gravity=(0.0, 0.0, 0.0))
+    parent = b.add_link(is_kinematic=True, mass=1.0)
+    child = b.add_link(mass=1.0)
+    b.add_shape_sphere(parent, radius=0.1)
+    b.add_shape_sphere(child, radius=0.1)
+    b.body_com[child] = np.array([0.2, -0.1, 0.05])
+    j0 = b.add_joint_revolute(-1, parent, axis=(0.0, 0.0, 1.0))
+    j1 = b.add_joint_free(child, parent=parent)
+    b.add_articulation([j0, j1])
+    model = b.finalize()
+    solver = oracle_lib.SolverFeatherstone(model, angular_damping=0.0) if solver_name == "featherstone" else \
+        oracle_lib.SolverXPBD(model, angular_damping=0.0)
+    s0, s1, control = model.state(), model.state(), model.control()
+    q = model.joint_q.numpy().copy()
+    q[0] = np.pi / 2.0
+    s0.joint_q.copy_(torch.from_numpy(q))
+    oracle_lib.eval_fk(model, s0.joint_q, s0.joint_qd, s0)
+    d0 = int(model.joint_qd_start[1])
+    f = np.zeros(model.joint_dof_count, dtype=np.float32)
+    f[d0:d0 + 6] = (10.0, 0.0, 0.0, 0.0, 0.0, 0.0)
+    control.joint_f.copy_(torch.from_numpy(f))
+    solver.step(s0, s1, control, None, 0.01)
+    qd = s1.body_qd.numpy()[child]
+    assert qd[0] > 1.0e-2
+    assert np.abs(qd[1:]).max() < 1.0e-6
