@@ -532,3 +532,73 @@ def test_descendant_free_joint_f_world_force_under_rotated_parent(oracle_lib, so
     qd = s1.body_qd.numpy()[child]
     assert qd[0] > 1.0e-2
     assert np.abs(qd[1:]).max() < 1.0e-6
+
+
+# ---- test_physics_verification.py:806-1035: four-bar linkage, loop closed by a revolute joint outside the articulation ---------------
+def _freudenstein(theta2, a, b, c, d):
+    """Rocker angle of the open configuration (test_physics_verification.py:807-835)."""
+    K1, K2, K3 = d / a, d / c, (a * a - b * b + c * c + d * d) / (2.0 * a * c)
+    A, B, C = K1 - np.cos(theta2), -np.sin(theta2), K2 * np.cos(theta2) - K3
+    theta4 = np.arctan2(B, A) + np.arccos(np.clip(C / np.sqrt(A * A + B * B), -1.0, 1.0))
+    cx, cy = d + c * np.cos(theta4) - a * np.cos(theta2), c * np.sin(theta4) - a * np.sin(theta2)
+    return np.arctan2(cy, cx), theta4
+
+
+def test_xpbd_fourbar_linkage_follows_the_freudenstein_equation(oracle_lib):
+    """The reference runs this mechanism through SolverMuJoCo (equality constraint or loop joint) and asks for < 0.1 deg rocker-angle
+    error against the closed form and < 1 mm loop-closure error over two crank revolutions.  XPBD closes the loop with the same
+    positional joint rows it uses inside the tree; driven by a (gentler: the explicit force path is not MuJoCo's implicit one)
+    velocity PD on the crank it meets the same two bars."""
+    a, b, c, d, th = 0.2, 0.5, 0.4, 0.5, 0.02
+    theta3_0, _ = _freudenstein(0.0, a, b, c, d)
+    delta = np.arctan2(-b * np.sin(theta3_0), d - a - b * np.cos(theta3_0)) - theta3_0
+    cfg = newton_b200.ShapeConfig()
+    cfg.density, cfg.has_shape_collision = 1000.0, False
+    B = ModelBuilder(up_axis="y", gravity=(0.0, 0.0, 0.0))
+    crank, coupler, rocker = B.add_link(), B.add_link(), B.add_link()
+    for body, length in ((crank, a), (coupler, b), (rocker, c)):
+        B.add_shape_box(body, hx=length / 2.0, hy=th, hz=th, cfg=cfg)
+    kw = dict(axis=(0.0, 0.0, 1.0), armature=0.0, limit_ke=0.0, limit_kd=0.0, target_ke=0.0, target_kd=0.0)
+    rz = lambda ang: X.quat_from_axis_angle((0.0, 0.0, 1.0), float(ang))  # noqa: E731
+    j0 = B.add_joint_revolute(-1, crank, child_xform=X.transform((-a / 2.0, 0.0, 0.0)), **kw)
+    j1 = B.add_joint_revolute(crank, coupler, parent_xform=X.transform((a / 2.0, 0.0, 0.0), rz(theta3_0)),
+                              child_xform=X.transform((-b / 2.0, 0.0, 0.0)), **kw)
+    j2 = B.add_joint_revolute(coupler, rocker, parent_xform=X.transform((b / 2.0, 0.0, 0.0), rz(delta)),
+                              child_xform=X.transform((-c / 2.0, 0.0, 0.0)), **kw)
+    B.add_articulation([j0, j1, j2])
+    j_loop = B.add_joint_revolute(-1, rocker, parent_xform=X.transform((d, 0.0, 0.0)), child_xform=X.transform((c / 2.0, 0.0, 0.0)), **kw)
+    B.joint_articulation[j_loop] = -1
+    model = B.finalize()
+    solver = oracle_lib.SolverXPBD(model, iterations=10, angular_damping=0.0)
+    s0, s1, control = model.state(), model.state(), model.control()
+    oracle_lib.eval_fk(model, model.joint_q, model.joint_qd, s0)
+    kp, omega_target, dt = 2.0, 2.0 * np.pi, 1.0e-3
+    jq, jqd = torch.zeros_like(s0.joint_q), torch.zeros_like(s0.joint_qd)
+    max_angle_deg = max_closure = turned = last = 0.0
+    for i in range(2000):
+        oracle_lib.eval_ik(model, s0, jq, jqd)
+        f = np.zeros(model.joint_dof_count, dtype=np.float32)
+        f[0] = kp * (omega_target - float(jqd[0]))
+        control.joint_f.copy_(torch.from_numpy(f))
+        s0.clear_forces()
+        solver.step(s0, s1, control, None, dt)
+        s0, s1 = s1, s0
+        step = float(jq[0]) - last
+        turned += (step + np.pi) % (2.0 * np.pi) - np.pi
+        last = float(jq[0])
+        if i < 20 or i % 10:
+            continue
+        bq = s0.body_q.numpy().astype(np.float64)
+        theta2 = 2.0 * np.arctan2(bq[crank, 5], bq[crank, 6])
+        _, theta4 = _freudenstein(theta2, a, b, c, d)
+        theta4_sim = np.arctan2(bq[rocker, 1], bq[rocker, 0] - d)
+        max_angle_deg = max(max_angle_deg, np.degrees(abs((theta4_sim - theta4 + np.pi) % (2.0 * np.pi) - np.pi)))
+        x, y, z, w = bq[rocker, 3:]
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        tip = bq[rocker, :3] + R @ np.array([c / 2.0, 0.0, 0.0])
+        max_closure = max(max_closure, float(np.linalg.norm(tip - np.array([d, 0.0, 0.0]))))
+    assert max_angle_deg < 0.1      # test_physics_verification.py:1013-1017
+    assert max_closure < 1.0e-3     # :1019-1023
+    assert turned > 0.9 * 2.0 * np.pi  # the crank went round (the reference's stiffer drive makes two turns in the same 2 s)
