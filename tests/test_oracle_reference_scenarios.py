@@ -602,3 +602,61 @@ def test_xpbd_fourbar_linkage_follows_the_freudenstein_equation(oracle_lib):
     assert max_angle_deg < 0.1      # test_physics_verification.py:1013-1017
     assert max_closure < 1.0e-3     # :1019-1023
     assert turned > 0.9 * 2.0 * np.pi  # the crank went round (the reference's stiffer drive makes two turns in the same 2 s)
+
+
+# ---- test_physics_verification.py:1050-1227: a revolute LOOP joint must also lock the out-of-plane rotation -------------------------
+def _ball_crank_fourbar(loop_kind):
+    a, b, c, d, th = 0.2, 0.5, 0.4, 0.5, 0.02
+    theta3_0, _ = _freudenstein(0.0, a, b, c, d)
+    delta = np.arctan2(-b * np.sin(theta3_0), d - a - b * np.cos(theta3_0)) - theta3_0
+    cfg = newton_b200.ShapeConfig()
+    cfg.density, cfg.has_shape_collision = 1000.0, False
+    B = ModelBuilder(up_axis="y", gravity=(0.0, -9.81, -5.0))  # Y swings the mechanism in its plane, Z tries to buckle it
+    crank, coupler, rocker = B.add_link(), B.add_link(), B.add_link()
+    for body, length in ((crank, a), (coupler, b), (rocker, c)):
+        B.add_shape_box(body, hx=length / 2.0, hy=th, hz=th, cfg=cfg)
+    rz = lambda ang: X.quat_from_axis_angle((0.0, 0.0, 1.0), float(ang))  # noqa: E731
+    j0 = B.add_joint_ball(-1, crank, child_xform=X.transform((-a / 2.0, 0.0, 0.0)))  # 3 rotational dofs: only Z is four-bar motion
+    j1 = B.add_joint_revolute(crank, coupler, axis=(0.0, 0.0, 1.0), parent_xform=X.transform((a / 2.0, 0.0, 0.0), rz(theta3_0)),
+                              child_xform=X.transform((-b / 2.0, 0.0, 0.0)))
+    j2 = B.add_joint_revolute(coupler, rocker, axis=(0.0, 0.0, 1.0), parent_xform=X.transform((b / 2.0, 0.0, 0.0), rz(delta)),
+                              child_xform=X.transform((-c / 2.0, 0.0, 0.0)))
+    B.add_articulation([j0, j1, j2])
+    pxf, cxf = X.transform((d, 0.0, 0.0)), X.transform((c / 2.0, 0.0, 0.0))
+    j_loop = B.add_joint_revolute(-1, rocker, axis=(0.0, 0.0, 1.0), parent_xform=pxf, child_xform=cxf) if loop_kind == "revolute" else \
+        B.add_joint_ball(-1, rocker, parent_xform=pxf, child_xform=cxf)
+    B.joint_articulation[j_loop] = -1
+    return B.finalize(), crank, rocker, c, d
+
+
+@pytest.mark.parametrize("loop_kind", ["revolute", "ball"])
+def test_xpbd_revolute_loop_joint_keeps_the_mechanism_planar(oracle_lib, loop_kind):
+    """The reference's bars (SolverMuJoCo): max |z| of the rocker < 0.02, the crank swings (max |y| > 0.01), closure error < 10 mm.
+    The counterexample it describes - a loop closure that only pins the point lets Z gravity buckle the mechanism - is the BALL
+    loop joint here: same closure accuracy, but it does leave the plane."""
+    model, crank, rocker, c, d = _ball_crank_fourbar(loop_kind)
+    solver = oracle_lib.SolverXPBD(model, iterations=10, angular_damping=0.0)
+    s0, s1, control = model.state(), model.state(), model.control()
+    qd = model.joint_qd.numpy().copy()
+    qd[2] = 2.0 * np.pi  # ball joint rates (wx, wy, wz): one in-plane revolution per second
+    s0.joint_qd.copy_(torch.from_numpy(qd))
+    oracle_lib.eval_fk(model, model.joint_q, s0.joint_qd, s0)
+    max_z = max_crank_y = 0.0
+    for i in range(2000):
+        s0.clear_forces()
+        solver.step(s0, s1, control, None, 5.0e-4)
+        s0, s1 = s1, s0
+        if i % 100 == 0:
+            bq = s0.body_q.numpy()
+            max_z, max_crank_y = max(max_z, abs(float(bq[rocker, 2]))), max(max_crank_y, abs(float(bq[crank, 1])))
+    bq = s0.body_q.numpy().astype(np.float64)
+    x, y, z, w = bq[rocker, 3:]
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    closure = float(np.linalg.norm(bq[rocker, :3] + R @ np.array([c / 2.0, 0.0, 0.0]) - np.array([d, 0.0, 0.0])))
+    assert max_crank_y > 0.01 and closure < 0.01
+    if loop_kind == "revolute":
+        assert max_z < 0.02
+    else:
+        assert max_z > 0.05  # point closure only: the out-of-plane dofs of the ball crank are free
